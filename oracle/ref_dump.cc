@@ -1,0 +1,332 @@
+// oracle/ref_dump.cc -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// A small driver over the UNMODIFIED reference library (oracle/_ref/libslate_ref.so,
+// built by oracle/build_ref.sh).  For one (routine, type, n, nb, seeds) it
+//   1. generates the inputs with the reference's own matgen (Philox-2x64 keyed on
+//      global (i, j, seed): matgen/random.cc:54-159),
+//   2. runs the reference's Target::HostTask path through the same simplified-API
+//      calls the reference tester makes (test/test_gemm.cc:177, test_posv.cc:211,
+//      test_gesv.cc:233, test_herk.cc, test_trsm.cc),
+//   3. writes inputs / outputs / pivots as raw little-endian column-major arrays and
+//      prints one JSON line with the wall time of the routine.
+// The numpy restatement in oracle/slate_oracle.py and the CUDA path are both compared
+// against these files (tests/golden/ holds the small committed ones; the script that
+// produced them is tests/golden/make_golden.py).
+//
+// usage: ref_dump ROUTINE TYPE n nb seedA seedB seedC OUTPREFIX [key=value ...]
+//   ROUTINE  gen | gemm | herk | potrf | getrf | trsm | gesv_mixed | norms
+//   TYPE     s | d | c | z
+//   keys     kind=rand|rand_dominant  la=1  ib=16  threads=N  dump=0|1  nrhs=10  pt=panel threads
+//            m= k= (gemm/herk rectangular)  uplo=l|u
+#include "slate/slate.hh"
+#include "slate/generate_matrix.hh"
+#include "lapack/flops.hh"
+
+#include <omp.h>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+
+struct Args {
+    std::string routine, type, prefix;
+    int64_t n = 0, nb = 0, seedA = 42, seedB = 43, seedC = 44;
+    std::map<std::string, std::string> kv;
+    std::string get(const std::string& k, const std::string& d) const {
+        auto it = kv.find(k);
+        return it == kv.end() ? d : it->second;
+    }
+    int64_t geti(const std::string& k, int64_t d) const {
+        auto it = kv.find(k);
+        return it == kv.end() ? d : std::atoll(it->second.c_str());
+    }
+};
+
+template <typename T>
+void write_raw(const std::string& path, const T* data, size_t count)
+{
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (! f) { std::perror(path.c_str()); std::exit(2); }
+    std::fwrite(data, sizeof(T), count, f);
+    std::fclose(f);
+}
+
+// Gather a general tiled matrix into one column-major m-by-n array.
+template <typename T>
+std::vector<T> to_dense(slate::Matrix<T>& A)
+{
+    int64_t m = A.m(), n = A.n();
+    std::vector<T> out(size_t(m) * n);
+    int64_t j0 = 0;
+    for (int64_t j = 0; j < A.nt(); ++j) {
+        int64_t i0 = 0;
+        for (int64_t i = 0; i < A.mt(); ++i) {
+            A.tileGetForReading(i, j, slate::LayoutConvert::ColMajor);
+            auto t = A(i, j);
+            for (int64_t jj = 0; jj < t.nb(); ++jj)
+                for (int64_t ii = 0; ii < t.mb(); ++ii)
+                    out[size_t(i0 + ii) + size_t(j0 + jj) * m] = t(ii, jj);
+            i0 += A.tileMb(i);
+        }
+        j0 += A.tileNb(j);
+    }
+    return out;
+}
+
+// Gather the stored triangle of a Hermitian/triangular matrix (other triangle = 0).
+template <typename MatrixT, typename T>
+std::vector<T> tz_to_dense(MatrixT& A, bool lower)
+{
+    int64_t n = A.n();
+    std::vector<T> out(size_t(n) * n, T(0));
+    int64_t j0 = 0;
+    for (int64_t j = 0; j < A.nt(); ++j) {
+        int64_t i0 = 0;
+        for (int64_t i = 0; i < A.mt(); ++i) {
+            bool stored = lower ? (i >= j) : (i <= j);
+            if (stored) {
+                A.tileGetForReading(i, j, slate::LayoutConvert::ColMajor);
+                auto t = A(i, j);
+                for (int64_t jj = 0; jj < t.nb(); ++jj)
+                    for (int64_t ii = 0; ii < t.mb(); ++ii)
+                        out[size_t(i0 + ii) + size_t(j0 + jj) * n] = t(ii, jj);
+            }
+            i0 += A.tileMb(i);
+        }
+        j0 += A.tileNb(j);
+    }
+    return out;
+}
+
+template <typename T>
+slate::Matrix<T> make_matrix(int64_t m, int64_t n, int64_t nb, int64_t seed, const std::string& kind)
+{
+    slate::Matrix<T> A(m, n, nb, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+    A.insertLocalTiles();
+    slate::MatgenParams p;
+    p.verbose = 0; p.kind = kind; p.cond_request = NAN; p.cond_actual = NAN; p.condD = NAN; p.seed = seed;
+    slate::generate_matrix(p, A);
+    return A;
+}
+
+template <typename T>
+int run(const Args& a)
+{
+    using real_t = blas::real_type<T>;
+    const int64_t n = a.n, nb = a.nb;
+    const bool dump = a.geti("dump", 1) != 0;
+    const int64_t la = a.geti("la", 1);
+    const int64_t ib = a.geti("ib", 16);
+    const int64_t nrhs = a.geti("nrhs", 10);
+    const int64_t pt = a.geti("pt", std::max(omp_get_max_threads() / 2, 1));
+    slate::Options opts = {
+        {slate::Option::Lookahead, la},
+        {slate::Option::Target, slate::Target::HostTask},
+        {slate::Option::InnerBlocking, ib},
+        {slate::Option::MaxPanelThreads, pt},
+    };
+    double seconds = 0, gflop = 0;
+    int64_t info = 0;
+    int iters = 0;
+    auto tic = [] { return Clock::now(); };
+    auto toc = [](Clock::time_point t0) {
+        return std::chrono::duration<double>(Clock::now() - t0).count(); };
+
+    // tester defaults: alpha = pi + sqrt(2) i, beta = e + sqrt(3) i  (test/test.cc:447-448)
+    T alpha = blas::make_scalar<T>(real_t(3.141592653589793), real_t(1.414213562373095));
+    T beta  = blas::make_scalar<T>(real_t(2.718281828459045), real_t(1.732050807568877));
+
+    if (a.routine == "gen") {
+        std::string kind = a.get("kind", "rand");
+        auto A = make_matrix<T>(a.geti("m", n), n, nb, a.seedA, kind);
+        auto d = to_dense(A);
+        write_raw(a.prefix + ".A.bin", d.data(), d.size());
+    }
+    else if (a.routine == "gemm") {
+        int64_t m = a.geti("m", n), k = a.geti("k", n);
+        auto A = make_matrix<T>(m, k, nb, a.seedA, "rand");
+        auto B = make_matrix<T>(k, n, nb, a.seedB, "rand");
+        auto C = make_matrix<T>(m, n, nb, a.seedC, "rand");
+        if (dump) {
+            auto d = to_dense(A); write_raw(a.prefix + ".A.bin", d.data(), d.size());
+            d = to_dense(B);      write_raw(a.prefix + ".B.bin", d.data(), d.size());
+            d = to_dense(C);      write_raw(a.prefix + ".C.bin", d.data(), d.size());
+        }
+        auto t0 = tic();
+        slate::multiply(alpha, A, B, beta, C, opts);
+        seconds = toc(t0);
+        gflop = blas::Gflop<T>::gemm(m, n, k);
+        if (dump) { auto d = to_dense(C); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
+    }
+    else if (a.routine == "herk") {
+        int64_t k = a.geti("k", n);
+        bool lower = a.get("uplo", "l") == "l";
+        auto A = make_matrix<T>(n, k, nb, a.seedA, "rand");
+        slate::HermitianMatrix<T> C(lower ? slate::Uplo::Lower : slate::Uplo::Upper, n, nb,
+                                    slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        C.insertLocalTiles();
+        slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedC;
+        p.cond_request = p.cond_actual = p.condD = NAN;
+        slate::generate_matrix(p, C);
+        if (dump) {
+            auto d = to_dense(A); write_raw(a.prefix + ".A.bin", d.data(), d.size());
+            d = tz_to_dense<slate::HermitianMatrix<T>, T>(C, lower);
+            write_raw(a.prefix + ".C.bin", d.data(), d.size());
+        }
+        real_t ra = std::real(alpha), rb = std::real(beta);
+        auto t0 = tic();
+        slate::rank_k_update(ra, A, rb, C, opts);
+        seconds = toc(t0);
+        gflop = blas::Gflop<T>::herk(n, k);
+        if (dump) {
+            auto d = tz_to_dense<slate::HermitianMatrix<T>, T>(C, lower);
+            write_raw(a.prefix + ".out.bin", d.data(), d.size());
+        }
+    }
+    else if (a.routine == "potrf") {
+        bool lower = a.get("uplo", "l") == "l";
+        slate::HermitianMatrix<T> A(lower ? slate::Uplo::Lower : slate::Uplo::Upper, n, nb,
+                                    slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        A.insertLocalTiles();
+        slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand_dominant"); p.seed = a.seedA;
+        p.cond_request = p.cond_actual = p.condD = NAN;
+        slate::generate_matrix(p, A);
+        if (dump) {
+            auto d = tz_to_dense<slate::HermitianMatrix<T>, T>(A, lower);
+            write_raw(a.prefix + ".A.bin", d.data(), d.size());
+        }
+        auto t0 = tic();
+        info = slate::chol_factor(A, opts);
+        seconds = toc(t0);
+        gflop = lapack::Gflop<T>::potrf(n);
+        if (dump) {
+            auto d = tz_to_dense<slate::HermitianMatrix<T>, T>(A, lower);
+            write_raw(a.prefix + ".out.bin", d.data(), d.size());
+        }
+    }
+    else if (a.routine == "getrf") {
+        int64_t m = a.geti("m", n);
+        auto A = make_matrix<T>(m, n, nb, a.seedA, a.get("kind", "rand"));
+        if (dump) { auto d = to_dense(A); write_raw(a.prefix + ".A.bin", d.data(), d.size()); }
+        slate::Pivots pivots;
+        auto t0 = tic();
+        info = slate::lu_factor(A, pivots, opts);
+        seconds = toc(t0);
+        gflop = lapack::Gflop<T>::getrf(m, n);
+        if (dump) {
+            auto d = to_dense(A); write_raw(a.prefix + ".out.bin", d.data(), d.size());
+            // pivots: for each block column k, min(mb,nb) pairs (tileIndex, elementOffset)
+            // relative to the panel sub-matrix A(k:mt-1, k)   (include/slate/types.hh:84-105)
+            std::vector<int64_t> flat;
+            for (auto& col : pivots)
+                for (auto& pv : col) { flat.push_back(pv.tileIndex()); flat.push_back(pv.elementOffset()); }
+            write_raw(a.prefix + ".piv.bin", flat.data(), flat.size());
+        }
+    }
+    else if (a.routine == "trsm") {
+        // Left/Lower/NoTrans/NonUnit solve  A X = alpha B, A = rand_dominant lower triangle
+        int64_t m = a.geti("m", n);   // A is m x m, B is m x n
+        slate::TriangularMatrix<T> A(slate::Uplo::Lower, slate::Diag::NonUnit, m, nb,
+                                     slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        A.insertLocalTiles();
+        slate::MatgenParams p; p.verbose = 0; p.kind = "rand_dominant"; p.seed = a.seedA;
+        p.cond_request = p.cond_actual = p.condD = NAN;
+        slate::generate_matrix(p, A);
+        auto B = make_matrix<T>(m, n, nb, a.seedB, "rand");
+        if (dump) {
+            auto d = tz_to_dense<slate::TriangularMatrix<T>, T>(A, true);
+            write_raw(a.prefix + ".A.bin", d.data(), d.size());
+            d = to_dense(B); write_raw(a.prefix + ".B.bin", d.data(), d.size());
+        }
+        auto t0 = tic();
+        slate::triangular_solve(alpha, A, B, opts);
+        seconds = toc(t0);
+        gflop = blas::Gflop<T>::trsm(slate::Side::Left, m, n);
+        if (dump) { auto d = to_dense(B); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
+    }
+    else if (a.routine == "gesv_mixed") {
+        if constexpr (std::is_same<real_t, double>::value) {
+            auto A = make_matrix<T>(n, n, nb, a.seedA, a.get("kind", "rand"));
+            auto B = make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
+            slate::Matrix<T> X(n, nrhs, nb, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+            X.insertLocalTiles();
+            if (dump) {
+                auto d = to_dense(A); write_raw(a.prefix + ".A.bin", d.data(), d.size());
+                d = to_dense(B);      write_raw(a.prefix + ".B.bin", d.data(), d.size());
+            }
+            slate::Pivots pivots;
+            auto t0 = tic();
+            info = slate::gesv_mixed(A, pivots, B, X, iters, opts);
+            seconds = toc(t0);
+            gflop = lapack::Gflop<T>::gesv(n, nrhs);
+            if (dump) { auto d = to_dense(X); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
+        }
+        else {
+            std::fprintf(stderr, "gesv_mixed needs type d or z\n");
+            return 2;
+        }
+    }
+    else if (a.routine == "norms") {
+        // max / one / inf / fro of a general rand matrix: slate::norm (src/norm.cc)
+        int64_t m = a.geti("m", n);
+        auto A = make_matrix<T>(m, n, nb, a.seedA, a.get("kind", "rand"));
+        if (dump) { auto d = to_dense(A); write_raw(a.prefix + ".A.bin", d.data(), d.size()); }
+        real_t v[4];
+        auto t0 = tic();
+        v[0] = slate::norm(slate::Norm::Max, A, opts);
+        v[1] = slate::norm(slate::Norm::One, A, opts);
+        v[2] = slate::norm(slate::Norm::Inf, A, opts);
+        v[3] = slate::norm(slate::Norm::Fro, A, opts);
+        seconds = toc(t0);
+        double vd[4] = { double(v[0]), double(v[1]), double(v[2]), double(v[3]) };
+        write_raw(a.prefix + ".out.bin", vd, 4);
+    }
+    else {
+        std::fprintf(stderr, "unknown routine %s\n", a.routine.c_str());
+        return 2;
+    }
+    std::printf("{\"routine\": \"%s\", \"type\": \"%s\", \"n\": %lld, \"nb\": %lld, \"seconds\": %.6f, "
+                "\"gflops\": %.3f, \"threads\": %d, \"info\": %lld, \"iters\": %d, \"target\": \"HostTask\"}\n",
+                a.routine.c_str(), a.type.c_str(), (long long) n, (long long) nb, seconds,
+                seconds > 0 ? gflop / seconds : 0.0, omp_get_max_threads(), (long long) info, iters);
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+    if (argc < 9) {
+        std::fprintf(stderr,
+            "usage: %s ROUTINE TYPE n nb seedA seedB seedC OUTPREFIX [key=value ...]\n", argv[0]);
+        return 2;
+    }
+    int provided = 0;
+    MPI_Init_thread(&argc, &argv, MPI_THREAD_MULTIPLE, &provided);
+    Args a;
+    a.routine = argv[1]; a.type = argv[2];
+    a.n = std::atoll(argv[3]); a.nb = std::atoll(argv[4]);
+    a.seedA = std::atoll(argv[5]); a.seedB = std::atoll(argv[6]); a.seedC = std::atoll(argv[7]);
+    a.prefix = argv[8];
+    for (int i = 9; i < argc; ++i) {
+        std::string s = argv[i];
+        auto eq = s.find('=');
+        if (eq != std::string::npos) a.kv[s.substr(0, eq)] = s.substr(eq + 1);
+    }
+    if (a.kv.count("threads")) omp_set_num_threads(std::atoi(a.kv["threads"].c_str()));
+    int rc = 2;
+    if      (a.type == "d") rc = run<double>(a);
+    else if (a.type == "z") rc = run<std::complex<double>>(a);
+    else if (a.type == "s") rc = run<float>(a);
+    else if (a.type == "c") rc = run<std::complex<float>>(a);
+    MPI_Finalize();
+    return rc;
+}

@@ -1,0 +1,465 @@
+"""oracle/slate_oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+CPU (numpy) restatement of the reference algorithms on the hot path.  It is the
+checker for the CUDA path; it is never imported by the product package
+(slate_b200/).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference leg may import it.
+
+PINNED: every function below is checked against the UNMODIFIED reference built by
+oracle/build_ref.sh (oracle/_ref/ref_dump, the reference's own HostTask path) --
+bit-exact for the Philox generator and the pivot vectors, to a few ulp for the
+floating-point factors -- by tests/test_oracle.py, using the committed fixtures in
+tests/golden/ (made by tests/golden/make_golden.py) and, when oracle/_ref is
+present, live runs of ref_dump.
+
+Each function cites the reference file:line it restates.  The arithmetic that the
+reference delegates to host BLAS/LAPACK (dgemm, dsyrk, dtrsm, dpotrf; OpenBLAS in
+this image) is done here with numpy/scipy calls of the same mathematical
+operation, tile by tile and in the reference's order of tile operations, so
+results agree to rounding, not bitwise.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ----------------------------------------------------------------------------
+# matgen: Philox-2x64 keyed on (global i, global j, seed)
+# reference: matgen/random.cc:54-77 (philox_2x64), :83-91 (rand_to_real), :96-159
+# ----------------------------------------------------------------------------
+_PHILOX_MULT = np.uint64(0x9E3779B97F4A7C15)
+_PHILOX_SEED_INC = np.uint64(0xD2B74407B1CE6E93)
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def _mulhilo64(a: np.ndarray, b: np.uint64):
+    """128-bit product of uint64 array `a` with scalar `b` -> (lo, hi), wrap-around uint64."""
+    a = a.astype(np.uint64, copy=False)
+    a_lo, a_hi = a & _M32, a >> np.uint64(32)
+    b_lo, b_hi = b & _M32, b >> np.uint64(32)
+    ll = a_lo * b_lo
+    lh = a_lo * b_hi
+    hl = a_hi * b_lo
+    hh = a_hi * b_hi
+    mid = (ll >> np.uint64(32)) + (lh & _M32) + (hl & _M32)
+    lo = (ll & _M32) | ((mid & _M32) << np.uint64(32))
+    hi = hh + (lh >> np.uint64(32)) + (hl >> np.uint64(32)) + (mid >> np.uint64(32))
+    return lo, hi
+
+
+def philox_2x64(i: np.ndarray, j: np.ndarray, seed: int):
+    """10 rounds of Philox-2x64 on counter (i, j), key `seed` (matgen/random.cc:54-77)."""
+    with np.errstate(over="ignore"):
+        s0 = np.asarray(i, dtype=np.int64).astype(np.uint64)
+        s1 = np.asarray(j, dtype=np.int64).astype(np.uint64)
+        s0, s1 = np.broadcast_arrays(s0, s1)
+        key = np.uint64(np.int64(seed).astype(np.uint64))
+        for rnd in range(10):
+            if rnd != 0:
+                key = key + _PHILOX_SEED_INC
+            lo, hi = _mulhilo64(s1, _PHILOX_MULT)
+            s0, s1 = lo, hi ^ key ^ s0
+    return s0, s1
+
+
+def _to_real(bits: np.ndarray, dtype):
+    """uniform [0,1) from the top `digits` bits (matgen/random.cc:83-91)."""
+    digits = np.finfo(dtype).nmant + 1
+    return (bits >> np.uint64(64 - digits)).astype(dtype) / dtype(2.0 ** digits)
+
+
+def generate(kind: str, m: int, n: int, seed: int, dtype=np.float64,
+             i0: int = 0, j0: int = 0, n_global: int | None = None) -> np.ndarray:
+    """Dense m-by-n block starting at global (i0, j0) of the reference `rand` /
+    `rand_dominant` test matrix (matgen/generate_type_rand.hh:28-79: uniform [0,1),
+    dominant adds n to the diagonal; complex: (re, im) from the two Philox words)."""
+    dtype = np.dtype(dtype)
+    real = np.float32 if dtype in (np.dtype(np.float32), np.dtype(np.complex64)) else np.float64
+    ii = np.arange(i0, i0 + m, dtype=np.int64)[:, None]
+    jj = np.arange(j0, j0 + n, dtype=np.int64)[None, :]
+    b0, b1 = philox_2x64(ii, jj, seed)
+    A = _to_real(b0, real)
+    if dtype.kind == "c":
+        A = A + 1j * _to_real(b1, real)
+    A = np.asfortranarray(A.astype(dtype))
+    if kind == "rand_dominant":
+        ng = n if n_global is None else n_global
+        d = np.arange(max(i0, j0), min(i0 + m, j0 + n))
+        A[d - i0, d - j0] += ng
+    elif kind != "rand":
+        raise ValueError(kind)
+    return A
+
+
+# ----------------------------------------------------------------------------
+# tile helpers
+# ----------------------------------------------------------------------------
+def _tiles(n: int, nb: int):
+    return [(s, min(s + nb, n)) for s in range(0, n, nb)]
+
+
+def cabs1(x):
+    """|re| + |im| (blaspp cabs1; used by the pivot search, Tile_getrf.hh:213)."""
+    x = np.asarray(x)
+    return np.abs(x.real) + np.abs(x.imag) if np.iscomplexobj(x) else np.abs(x)
+
+
+# ----------------------------------------------------------------------------
+# gemm: C = alpha A B + beta C as gemmC does it (src/gemmC.cc:124-182): beta applied
+# with the k = 0 block, then one rank-nb update per block column k of A.
+# tile op: include/slate/Tile_blas.hh:29-98 -> blas::gemm
+# ----------------------------------------------------------------------------
+def gemm(alpha, A, B, beta, C, nb: int):
+    C = np.array(C, order="F", copy=True)
+    kt = _tiles(A.shape[1], nb)
+    for idx, (k0, k1) in enumerate(kt):
+        b = beta if idx == 0 else 1.0
+        for (j0, j1) in _tiles(C.shape[1], nb):
+            for (i0, i1) in _tiles(C.shape[0], nb):
+                C[i0:i1, j0:j1] = alpha * (A[i0:i1, k0:k1] @ B[k0:k1, j0:j1]) + b * C[i0:i1, j0:j1]
+    return C
+
+
+# ----------------------------------------------------------------------------
+# herk: lower C = alpha A A^H + beta C (src/herk.cc:25-162; internal_herk.cc:47-110):
+# diagonal tiles by tile herk (only the stored triangle is defined), off-diagonal by gemm.
+# ----------------------------------------------------------------------------
+def herk(alpha, A, beta, C, nb: int, lower: bool = True):
+    C = np.array(C, order="F", copy=True)
+    n = C.shape[0]
+    kt = _tiles(A.shape[1], nb)
+    for idx, (k0, k1) in enumerate(kt):
+        b = beta if idx == 0 else 1.0
+        for (j0, j1) in _tiles(n, nb):
+            for (i0, i1) in _tiles(n, nb):
+                if (lower and i0 < j0) or (not lower and i0 > j0):
+                    continue
+                upd = alpha * (A[i0:i1, k0:k1] @ A[j0:j1, k0:k1].conj().T) + b * C[i0:i1, j0:j1]
+                if i0 == j0:
+                    mask = np.tril(np.ones_like(upd, dtype=bool)) if lower else np.triu(np.ones_like(upd, dtype=bool))
+                    blk = C[i0:i1, j0:j1]
+                    blk[mask] = upd[mask]
+                    if np.iscomplexobj(blk):
+                        di = np.arange(blk.shape[0])
+                        blk[di, di] = blk[di, di].real
+                else:
+                    C[i0:i1, j0:j1] = upd
+    return C
+
+
+# ----------------------------------------------------------------------------
+# potrf: right-looking tile Cholesky, lower (src/potrf.cc:84-195):
+#   per k: potrf(A_kk) (internal_potrf.cc -> lapack::potrf), trsm of the column
+#   (internal_trsm.cc: Right, Lower, ConjTrans, NonUnit), herk/gemm trailing update.
+# Returns (L with the strict upper triangle zeroed, info).
+# ----------------------------------------------------------------------------
+def potrf(A, nb: int):
+    from scipy.linalg import solve_triangular
+    A = np.array(A, order="F", copy=True)
+    n = A.shape[0]
+    tl = _tiles(n, nb)
+    info = 0
+    for k, (k0, k1) in enumerate(tl):
+        Akk = np.tril(A[k0:k1, k0:k1])
+        Akk = Akk + np.tril(Akk, -1).conj().T
+        try:
+            L = np.linalg.cholesky(Akk)
+        except np.linalg.LinAlgError:
+            # first non-positive leading minor, 1-based global index (LAPACK info)
+            for r in range(1, k1 - k0 + 1):
+                try:
+                    np.linalg.cholesky(Akk[:r, :r])
+                except np.linalg.LinAlgError:
+                    info = k0 + r
+                    break
+            break
+        A[k0:k1, k0:k1] = L
+        if k1 < n:
+            # A(i,k) <- A(i,k) L^{-H}
+            A[k1:, k0:k1] = solve_triangular(L, A[k1:, k0:k1].conj().T, lower=True).conj().T
+            P = A[k1:, k0:k1]
+            for (j0, j1) in tl[k + 1:]:
+                for (i0, i1) in tl[k + 1:]:
+                    if i0 < j0:
+                        continue
+                    A[i0:i1, j0:j1] -= P[i0 - k1:i1 - k1] @ P[j0 - k1:j1 - k1].conj().T
+    return np.tril(A), info
+
+
+# ----------------------------------------------------------------------------
+# getrf: tile LU with partial pivoting.
+#   panel  : src/internal/Tile_getrf.hh:160-447 (ib-blocked, pivot = first strict max of
+#            cabs1 starting from the diagonal entry -- ties keep the LOWEST row; scale by
+#            the reciprocal unless |pivot| < safe_min; zero pivot -> info = j+1, continue)
+#   driver : src/getrf.cc:84-236 (permuteRows right, trsm Left/Lower/Unit, gemm update,
+#            then permuteRows to the left)
+# Returns (LU, pivots, info); pivots[k] is a list of (tileIndex, elementOffset) relative to
+# the panel sub-matrix A(k:mt-1, k)  (include/slate/types.hh:84-105).
+# ----------------------------------------------------------------------------
+def getrf_panel(P: np.ndarray, diag_len: int, ib: int, nb_rows: int):
+    """Factor the m-by-nb panel P in place; returns (pivot rows (panel-relative), info)."""
+    m, nbc = P.shape
+    safe_min = np.finfo(P.real.dtype).tiny
+    piv = np.zeros(diag_len, dtype=np.int64)
+    info = 0
+    for k in range(0, diag_len, ib):
+        kb = min(diag_len - k, ib)
+        for j in range(k, k + kb):
+            col = cabs1(P[j:, j])
+            r = j + int(np.argmax(col))          # first maximum = lowest row among ties
+            piv[j] = r
+            if r != j:
+                P[[j, r], :] = P[[r, j], :]
+            pv = P[j, j]
+            if cabs1(pv) >= safe_min:
+                P[j + 1:, j] *= (1.0 / pv)
+            elif pv != 0:
+                P[j + 1:, j] /= pv
+            elif info == 0:
+                info = j + 1
+            if k + kb > j + 1:
+                P[j + 1:, j + 1:k + kb] -= np.outer(P[j + 1:, j], P[j, j + 1:k + kb])
+        if k + kb < nbc:
+            # trsm on the top rows of the stripe, then rank-kb update to the right
+            L = np.tril(P[k:k + kb, k:k + kb], -1) + np.eye(kb, dtype=P.dtype)
+            P[k:k + kb, k + kb:] = np.linalg.solve(L, P[k:k + kb, k + kb:]) if kb > 1 else P[k:k + kb, k + kb:]
+            P[k + kb:, k + kb:] -= P[k + kb:, k:k + kb] @ P[k:k + kb, k + kb:]
+    return piv, info
+
+
+def getrf(A, nb: int, ib: int = 16):
+    from scipy.linalg import solve_triangular
+    A = np.array(A, order="F", copy=True)
+    m, n = A.shape
+    info = 0
+    pivots = []
+    kk = 0
+    for k in range(min(-(-m // nb), -(-n // nb))):
+        r0, c0 = k * nb, k * nb
+        r1, c1 = min(r0 + nb, m), min(c0 + nb, n)
+        diag_len = min(r1 - r0, c1 - c0)
+        panel = A[r0:, c0:c1]
+        piv, iinfo = getrf_panel(panel, diag_len, ib, nb)
+        if info == 0 and iinfo > 0:
+            info = kk + iinfo
+        pivots.append([(int(p // nb), int(p % nb)) for p in piv])
+        # apply the row interchanges to the columns right and left of the panel
+        for j, p in enumerate(piv):
+            if p != j:
+                A[[r0 + j, r0 + p], c1:] = A[[r0 + p, r0 + j], c1:]
+                A[[r0 + j, r0 + p], :c0] = A[[r0 + p, r0 + j], :c0]
+        if c1 < n:
+            Lkk = A[r0:r1, c0:c1][:, :diag_len]
+            A[r0:r1, c1:] = solve_triangular(Lkk[:diag_len], A[r0:r1, c1:], lower=True, unit_diagonal=True)
+            if r1 < m:
+                for (j0, j1) in _tiles(n, nb)[k + 1:]:
+                    A[r1:, j0:j1] -= A[r1:, c0:c1] @ A[r0:r1, j0:j1]
+        kk += c1 - c0
+    return A, pivots, info
+
+
+def pivots_to_perm(pivots, m: int, nb: int) -> np.ndarray:
+    """Row permutation p such that (P A)[i] = A[p[i]] for slate::Pivots semantics."""
+    perm = np.arange(m)
+    for k, col in enumerate(pivots):
+        r0 = k * nb
+        for j, (ti, off) in enumerate(col):
+            a, b = r0 + j, r0 + ti * nb + off
+            if a != b:
+                perm[[a, b]] = perm[[b, a]]
+    return perm
+
+
+# ----------------------------------------------------------------------------
+# trsm with one triangular tile against a block row/column (internal_trsm.cc:40-92)
+# ----------------------------------------------------------------------------
+def trsm_tile(side: str, uplo: str, op: str, diag: str, alpha, T, B):
+    from scipy.linalg import solve_triangular
+    lower = uplo == "L"
+    Tm = np.tril(T) if lower else np.triu(T)
+    trans = {"N": 0, "T": 1, "C": 2}[op]
+    unit = diag == "U"
+    if side == "L":
+        return solve_triangular(Tm, alpha * B, lower=lower, trans=trans, unit_diagonal=unit)
+    # X op(T) = alpha B  <=>  op(T)^T X^T = alpha B^T
+    if op == "N":
+        Xt = solve_triangular(Tm, (alpha * B).T, lower=lower, trans=1, unit_diagonal=unit)
+    elif op == "T":
+        Xt = solve_triangular(Tm, (alpha * B).T, lower=lower, trans=0, unit_diagonal=unit)
+    else:
+        Xt = solve_triangular(Tm.conj(), (alpha * B).T, lower=lower, trans=0, unit_diagonal=unit)
+    return Xt.T
+
+
+# ----------------------------------------------------------------------------
+# memory-bound tile kernels (src/cuda/*.cu; include/slate/internal/device.hh:92-281)
+# ----------------------------------------------------------------------------
+def geadd(alpha, A, beta, B):            # device_geadd.cu:61-85
+    return alpha * A + beta * B
+
+
+def gescale(numer, denom, A):            # device_gescale.cu:42-60   (A *= numer/denom)
+    return A * (numer / denom)
+
+
+def gescale_row_col(equed: str, R, C, A):  # device_gescale_row_col.cu:42-140
+    out = np.array(A, copy=True)
+    if equed in ("R", "B"):
+        out = out * np.asarray(R)[:, None]
+    if equed in ("C", "B"):
+        out = out * np.asarray(C)[None, :]
+    return out
+
+
+def geset(offdiag, diag, m, n, dtype=np.float64):   # device_geset.cu:44-70
+    A = np.full((m, n), offdiag, dtype=dtype, order="F")
+    d = np.arange(min(m, n))
+    A[d, d] = diag
+    return A
+
+
+def tz_mask(uplo: str, m: int, n: int):
+    i = np.arange(m)[:, None]
+    j = np.arange(n)[None, :]
+    return (i >= j) if uplo == "L" else (i <= j)
+
+
+def tzset(uplo, offdiag, diag, A):       # device_tzset.cu:23-75
+    out = np.array(A, copy=True)
+    msk = tz_mask(uplo, *A.shape)
+    out[msk] = offdiag
+    d = np.arange(min(A.shape))
+    out[d, d] = diag
+    return out
+
+
+def tzadd(uplo, alpha, A, beta, B):      # device_tzadd.cu:43-70
+    out = np.array(B, copy=True)
+    msk = tz_mask(uplo, *A.shape)
+    out[msk] = (alpha * A + beta * B)[msk]
+    return out
+
+
+def tzscale(uplo, numer, denom, A):      # device_tzscale.cu:42-66
+    out = np.array(A, copy=True)
+    msk = tz_mask(uplo, *A.shape)
+    out[msk] = (A * (numer / denom))[msk]
+    return out
+
+
+def tzcopy(uplo, A, B, dtype):           # device_tzcopy.cu:41-68
+    out = np.array(B, copy=True).astype(dtype)
+    msk = tz_mask(uplo, *A.shape)
+    out[msk] = A.astype(dtype)[msk]
+    return out
+
+
+def _max_nan(a):
+    """NaN-propagating max (device_util.cuh:22-25)."""
+    a = np.asarray(a)
+    return np.nan if np.isnan(a).any() else (a.max() if a.size else 0.0)
+
+
+def genorm(norm: str, A):
+    """Per-tile partial result of device::genorm (device_genorm.cu:44-281):
+    'M' -> scalar max|a|; 'O' -> column sums (n); 'I' -> row sums (m);
+    'F' -> (scale, sumsq) with scale^2 * sumsq = sum |a|^2."""
+    absA = np.abs(A)
+    if norm == "M":
+        return _max_nan(absA)
+    if norm == "O":
+        return absA.sum(axis=0)
+    if norm == "I":
+        return absA.sum(axis=1)
+    if norm == "F":
+        scale = _max_nan(absA) if A.size else 0.0
+        if scale == 0 or np.isnan(scale):
+            return np.array([scale if np.isnan(scale) else 0.0, 1.0])
+        return np.array([scale, ((absA / scale) ** 2).sum()])
+    raise ValueError(norm)
+
+
+def genorm_colmax(A):                    # ge_col_norms_max_kernel (device_genorm.cu:285-)
+    return np.array([_max_nan(np.abs(A[:, j])) for j in range(A.shape[1])])
+
+
+def henorm(norm: str, uplo: str, A):
+    """Hermitian tile stored in one triangle (device_henorm.cu): result of the full matrix."""
+    msk = tz_mask(uplo, *A.shape)
+    T = np.where(msk, A, 0)
+    F = T + np.conj(np.where(msk & ~np.eye(A.shape[0], dtype=bool), A, 0)).T
+    if np.iscomplexobj(F):
+        d = np.arange(F.shape[0])
+        F[d, d] = F[d, d].real
+    if norm == "M":
+        return _max_nan(np.abs(F))
+    if norm in ("O", "I"):
+        return np.abs(F).sum(axis=0)
+    return genorm("F", F)
+
+
+def trnorm(norm: str, uplo: str, diag: str, A):   # device_trnorm.cu
+    msk = tz_mask(uplo, *A.shape)
+    T = np.where(msk, A, 0).astype(A.dtype)
+    if diag == "U":
+        d = np.arange(min(A.shape))
+        T[d, d] = 1
+    return genorm(norm, T)
+
+
+def combine_norm(norm: str, parts):
+    """Reduce per-tile partials to the matrix norm the way src/norm.cc / internal_genorm.cc do."""
+    if norm == "M":
+        return _max_nan(np.array(parts))
+    if norm == "F":
+        scale, sumsq = 0.0, 1.0
+        for (s, q) in parts:                      # combine_sumsq (device_util.cuh:243-262)
+            if s > scale:
+                sumsq = q + sumsq * (scale / s) ** 2 if s != 0 else sumsq
+                scale = s
+            elif scale != 0:
+                sumsq = sumsq + q * (s / scale) ** 2
+        return scale * np.sqrt(sumsq)
+    raise ValueError(norm)
+
+
+# ----------------------------------------------------------------------------
+# tester residual checks (the acceptance criteria)
+# ----------------------------------------------------------------------------
+def gemm_check(alpha, A, B, beta, C0, C, seed: int = 7):
+    """|| C X - (alpha A (B X) + beta C0 X) ||_1 / ||Y||_1  must be <= 3 eps
+    (test/test_gemm.cc:137-157,192-208); X = rand n-by-nrhs (nrhs = 10)."""
+    n = C.shape[1]
+    X = generate("rand", n, 10, seed, C.dtype)
+    Y = alpha * (A @ (B @ X)) + beta * (C0 @ X)
+    y_norm = np.abs(Y).sum(axis=0).max()
+    R = C @ X - Y
+    return np.abs(R).sum(axis=0).max() / y_norm
+
+
+def solve_residual(A, X, B):
+    """|| B - A X ||_1 / (n ||A||_1 ||X||_1) <= tol * eps / 2, tol = 50
+    (test/test_posv.cc:304-345, test/test_gesv.cc:330-380, test/test.cc:356)."""
+    n = A.shape[0]
+    R = B - A @ X
+    one = lambda M: np.abs(M).sum(axis=0).max()
+    return one(R) / (n * one(A) * one(X))
+
+
+def flops_gemm(m, n, k, complex_=False):      # blaspp/include/blas/flops.hh:100-104,312-324
+    return (8.0 if complex_ else 2.0) * m * n * k
+
+
+def flops_potrf(n):                           # lapackpp/include/lapack/flops.hh:56-60
+    n = float(n)
+    return (n ** 3 / 6 + n ** 2 / 2 + n / 3) + (n ** 3 / 6 - n / 6)
+
+
+def flops_getrf(m, n):                        # lapackpp/include/lapack/flops.hh:27-39 (m >= n)
+    m, n = float(m), float(n)
+    if m >= n:
+        fm = m * n * n / 2 - n ** 3 / 6 + m * n / 2 - n * n / 2 + 2 * n / 3
+        fa = m * n * n / 2 - n ** 3 / 6 - m * n / 2 + n / 6
+    else:
+        fm = n * m * m / 2 - m ** 3 / 6 + n * m / 2 - m * m / 2 + 2 * m / 3
+        fa = n * m * m / 2 - m ** 3 / 6 - n * m / 2 + m / 6
+    return fm + fa
