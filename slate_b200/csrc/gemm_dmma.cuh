@@ -54,8 +54,14 @@ struct GemmCfg {
     static constexpr int THREADS = CONSUMER_WARPS * 32 + 128;   // + producer warpgroup (1 active warp)
     static constexpr int CTAS_PER_SM = 2;
     static constexpr int PRODUCER_REGS = 40;
-    // half of the SM register file per CTA: consumers get what the producer warpgroup gives up
-    static constexpr int CONSUMER_REGS = ((32768 - 128 * PRODUCER_REGS) / (CONSUMER_WARPS * 32)) / 8 * 8;
+    // The CTA's register pool is what the launch allocates (THREADS x LAUNCH_REGS); consumers may
+    // only grow into what the producer warpgroup gives back -- asking for more deadlocks in
+    // setmaxnreg.inc.
+    static constexpr int LAUNCH_REGS = (65536 / (CTAS_PER_SM * THREADS)) / 8 * 8;
+    static constexpr int CONSUMER_REGS =
+        ((THREADS * LAUNCH_REGS - 128 * PRODUCER_REGS) / (CONSUMER_WARPS * 32)) / 8 * 8;
+    static_assert(CONSUMER_WARPS * 32 * CONSUMER_REGS + 128 * PRODUCER_REGS <= THREADS * LAUNCH_REGS,
+                  "setmaxnreg budget exceeds the CTA register pool");
     static constexpr int PAD = 4;
     static constexpr int LDK = BK + PAD;                        // K-major stride (doubles)
     static constexpr int LDA_MN = BM + PAD, LDB_MN = BN + PAD;  // MN-major strides

@@ -1,0 +1,69 @@
+// runtime.hh -- host runtime of libslate_b200: process grid, HBM-resident tile matrix,
+// and the factorisation / multiply drivers that schedule the trailing-matrix update.
+//
+// What it mirrors in the reference (and how it differs, B200-first):
+//   * slate::Matrix / HermitianMatrix (include/slate/Matrix.hh, BaseMatrix.hh): 2-D block-cyclic
+//     tile map, tileRank(i,j) = (i % p) + (j % q) * p  (GridOrder::Col, include/slate/func.hh:96-104).
+//     Here one process owns ONE B200 and all of its tiles live in one HBM pool for the whole
+//     life of the matrix -- there is no host<->device MOSI traffic inside a driver; the MOSI state
+//     machine collapses to "owner copy (Modified) + read-only panel workspace copies (Shared)"
+//     that are overwritten two steps later.
+//   * device_regions_build (src/internal/internal_batch.hh:227-347): pointer batches are built
+//     ONCE per driver call on the host for every step (a "plan"), uploaded in one copy and reused;
+//     the reference rebuilds and re-uploads them at every step.
+//   * tileBcast / listBcast / listBcastMT (include/slate/BaseMatrix.hh:1889-2140): the panel
+//     broadcast is p NCCL broadcasts of contiguous pool ranges per step on the panel stream.
+//   * the OpenMP task DAG with lookahead (src/potrf.cc:84-195, src/getrf.cc:84-236,
+//     src/gemmC.cc:89-196) becomes two CUDA streams (panel = high priority, trailing) ordered
+//     by events; the host never blocks inside the step loop.
+#pragma once
+#include "common.cuh"
+#include <nccl.h>
+#include <vector>
+
+namespace sb200 {
+
+struct Grid {
+    int p = 1, q = 1, rank = 0;
+    int prow = 0, pcol = 0;
+    ncclComm_t world = nullptr;      // null when p*q == 1
+    ncclComm_t row_comm = nullptr;   // ranks with the same prow (size q), rank order = pcol
+    ncclComm_t col_comm = nullptr;   // ranks with the same pcol (size p), rank order = prow
+    int size() const { return p * q; }
+    int rank_of(int64_t i, int64_t j) const { return int(i % p) + int(j % q) * p; }
+};
+
+struct Matrix {
+    Grid*   g = nullptr;
+    int     kind = 'G';            // 'G' general, 'H' Hermitian/symmetric, lower tiles stored
+    int     layout = 'C';          // tile layout: 'C' column-major (all drivers here)
+    int64_t m = 0, n = 0, nb = 0, mt = 0, nt = 0;
+    int64_t mt_loc = 0, nt_loc = 0;          // local tile rows / cols
+    std::vector<int64_t> col_start;          // tile index of the first stored tile of local col jl
+    int64_t ntiles_loc = 0;
+    double* pool = nullptr;                  // ntiles_loc * nb*nb doubles, every tile ld = nb
+    double  last_ms = 0.0;
+
+    int64_t tile_elems() const { return nb * nb; }
+    int64_t tile_mb(int64_t i) const { return i == mt - 1 ? m - i * nb : nb; }
+    int64_t tile_nb(int64_t j) const { return j == nt - 1 ? n - j * nb : nb; }
+    bool    stored(int64_t i, int64_t j) const { return kind == 'G' || i >= j; }
+    bool    is_local(int64_t i, int64_t j) const { return g->rank_of(i, j) == g->rank; }
+    // first local tile row index >= i0 for process row prow
+    int64_t first_local_row(int64_t i0) const
+    {
+        int64_t il = (i0 - g->prow + g->p - 1) / g->p;
+        return il < 0 ? 0 : il;
+    }
+    // device pointer of local tile (i, j); caller guarantees is_local && stored
+    double* tile(int64_t i, int64_t j) const
+    {
+        const int64_t il = (i - g->prow) / g->p, jl = (j - g->pcol) / g->q;
+        int64_t idx;
+        if (kind == 'G') idx = col_start[jl] + il;
+        else             idx = col_start[jl] + (il - first_local_row(j));
+        return pool + idx * tile_elems();
+    }
+};
+
+} // namespace sb200
