@@ -331,6 +331,13 @@ int sb200_potrf_d(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
 int sb200_getrf_d(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
 /* device time of the last driver call on this matrix, milliseconds (CUDA events) */
 double sb200_last_driver_ms(sb200_matrix_t A);
+/* out4 = { driver ms, summed ms of the trailing-update GEMM launches (events on their stream),
+ *          algorithmic flops of those launches, number of those launches } */
+int sb200_last_driver_stats(sb200_matrix_t A, double* out4);
+/* FP64 pipe peak probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure):
+ * kind 0 = DMMA.8x8x4, 1 = DFMA; launches ctas_per_sm x SMs CTAs; *flops = work of the launch. */
+int sb200_fp64_peak_probe(int kind, int iters, int ctas_per_sm, double* d_scratch, double* flops,
+                          sb200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,276 @@
+// norms.cu -- per-tile partial norms (seam 2: device::genorm / henorm / synorm / synormOffdiag /
+// trnorm; reference src/cuda/device_{genorm,henorm,synorm,trnorm}.cu and device_util.cuh).
+//
+// Output layout is the reference's (device_genorm.cu:373-445): per tile t
+//   Max  -> values[t]            (ldv = 1), NaN-propagating (device_util.cuh:22-25)
+//   One  -> values[t*ldv + j]    column sums        Inf -> values[t*ldv + i]   row sums
+//   Fro  -> values[2t] = scale, values[2t+1] = sumsq  with scale^2 * sumsq = sum |a|^2
+//   scope Columns + Max -> values[t*ldv + j] = max_i |a_ij|   (ge_col_norms_max_kernel)
+// The reference uses shared-memory tree reductions and, for Frobenius, a serial combine on
+// thread 0 (device_genorm.cu:268-277).  Here: one CTA (512 threads) per tile, warp-shuffle
+// reductions, deterministic combine order, columns walked by warps (coalesced 256-byte lines)
+// and rows by threads (coalesced across the CTA).
+#include "common.cuh"
+
+namespace sb200 {
+
+template <typename T> struct RealOf { using type = T; };
+template <> struct RealOf<cuDoubleComplex> { using type = double; };
+template <> struct RealOf<cuFloatComplex>  { using type = float; };
+
+__device__ inline float  abs_(float a) { return fabsf(a); }
+__device__ inline double abs_(double a) { return fabs(a); }
+__device__ inline float  abs_(cuFloatComplex a) { return cuCabsf(a); }
+__device__ inline double abs_(cuDoubleComplex a) { return cuCabs(a); }
+// Hermitian diagonal: only the real part counts (device_henorm.cu uses abs(real(a_jj)))
+__device__ inline float  abs_real(float a) { return fabsf(a); }
+__device__ inline double abs_real(double a) { return fabs(a); }
+__device__ inline float  abs_real(cuFloatComplex a) { return fabsf(a.x); }
+__device__ inline double abs_real(cuDoubleComplex a) { return fabs(a.x); }
+
+template <typename R> __device__ inline R max_nan(R a, R b)
+{
+    return (a != a) ? a : ((b != b) ? b : (a > b ? a : b));
+}
+
+// (scale, sumsq) accumulation, LAPACK lassq style (device_util.cuh:243-268 add_sumsq / combine_sumsq)
+template <typename R> __device__ inline void add_sumsq(R& scale, R& sumsq, R absx)
+{
+    if (absx != absx) { scale = absx; return; }                 // NaN poisons the result
+    if (scale != scale) return;
+    if (absx == R(0)) return;
+    if (scale < absx) { const R r = scale / absx; sumsq = R(1) + sumsq * r * r; scale = absx; }
+    else              { const R r = absx / scale; sumsq += r * r; }
+}
+template <typename R> __device__ inline void combine_sumsq(R& scale, R& sumsq, R scale2, R sumsq2)
+{
+    if (scale2 != scale2) { scale = scale2; return; }
+    if (scale != scale) return;
+    if (scale2 == R(0)) return;
+    if (scale == R(0)) { scale = scale2; sumsq = sumsq2; return; }
+    if (scale > scale2) { const R r = scale2 / scale; sumsq += sumsq2 * r * r; }
+    else                { const R r = scale / scale2; sumsq = sumsq * r * r + sumsq2; scale = scale2; }
+}
+
+template <typename R> __device__ inline R warp_sum(R v)
+{
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <typename R> __device__ inline R warp_max_nan(R v)
+{
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Element classes for the structured tiles.
+//   shape 0: general;  1: lower trapezoid (i >= j);  2: upper trapezoid (i <= j)
+//   sym  0: plain (ge / tr);  1: Hermitian/symmetric diagonal tile stored in `shape`
+//            (off-diagonal entries count for both (i,j) and (j,i); herm: diag uses |real|)
+//   unit: triangular with implicit unit diagonal
+struct NormCfg { int shape, sym, herm, unit; };
+
+__device__ inline bool in_shape(const NormCfg& c, int i, int j)
+{
+    return c.shape == 0 || (c.shape == 1 ? i >= j : i <= j);
+}
+
+template <typename T>
+__device__ inline typename RealOf<T>::type elem_abs(const NormCfg& c, const T* a, int64_t lda, int i, int j)
+{
+    using R = typename RealOf<T>::type;
+    if (i == j && c.unit) return R(1);
+    if (i == j && c.herm) return abs_real(a[i + j * lda]);
+    return abs_(a[i + j * lda]);
+}
+
+constexpr int NORM_THREADS = 512;
+
+// mode: 'M' max, 'O' one (column sums [+ row part for sym]), 'I' inf (row sums), 'F' fro,
+//       'C' column maxima, 'B' both column sums (values[0..n)) and row sums (values[n..n+m))
+template <typename T>
+__global__ void __launch_bounds__(NORM_THREADS)
+norm_kernel(int mode, NormCfg cfg, int m, int n, const T* const* A, int64_t lda,
+            typename RealOf<T>::type* values, int64_t ldv)
+{
+    using R = typename RealOf<T>::type;
+    const T* a = A[blockIdx.x];
+    R* out = values + int64_t(blockIdx.x) * ldv;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = NORM_THREADS / 32;
+    __shared__ R red[2 * NW];
+
+    if (mode == 'M' || mode == 'F') {
+        R vmax = 0, scale = 0, sumsq = 1;
+        for (int j = warp; j < n; j += NW) {
+            for (int i = lane; i < m; i += 32) {
+                if (! in_shape(cfg, i, j)) continue;
+                const R v = elem_abs(cfg, a, lda, i, j);
+                if (mode == 'M') vmax = max_nan(vmax, v);
+                else {
+                    add_sumsq(scale, sumsq, v);
+                    if (cfg.sym && i != j) add_sumsq(scale, sumsq, v);     // mirrored entry
+                }
+            }
+        }
+        if (mode == 'M') {
+            vmax = warp_max_nan(vmax);
+            if (lane == 0) red[warp] = vmax;
+            __syncthreads();
+            if (warp == 0) {
+                R v = lane < NW ? red[lane] : R(0);
+                v = warp_max_nan(v);
+                if (lane == 0) out[0] = v;
+            }
+        }
+        else {
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const R s2 = __shfl_xor_sync(0xffffffffu, scale, o), q2 = __shfl_xor_sync(0xffffffffu, sumsq, o);
+                combine_sumsq(scale, sumsq, s2, q2);     // only lane 0's (deterministic) result is used
+            }
+            if (lane == 0) { red[2 * warp] = scale; red[2 * warp + 1] = sumsq; }
+            __syncthreads();
+            if (tid == 0) {
+                R s = red[0], q = red[1];
+                for (int w = 1; w < NW; ++w) combine_sumsq(s, q, red[2 * w], red[2 * w + 1]);
+                out[0] = s; out[1] = q;
+            }
+        }
+        return;
+    }
+
+    if (mode == 'O' || mode == 'C' || mode == 'B') {
+        // column pass: one warp per column
+        for (int j = warp; j < n; j += NW) {
+            R acc = 0;
+            for (int i = lane; i < m; i += 32) {
+                if (! in_shape(cfg, i, j)) continue;
+                const R v = elem_abs(cfg, a, lda, i, j);
+                acc = (mode == 'C') ? max_nan(acc, v) : acc + v;
+            }
+            acc = (mode == 'C') ? warp_max_nan(acc) : warp_sum(acc);
+            if (lane == 0) out[j] = acc;
+        }
+    }
+    if (mode == 'I' || mode == 'B' || (mode == 'O' && cfg.sym)) {
+        if (mode == 'O') __syncthreads();          // column sums of this CTA are written
+        // row pass: one thread per row (coalesced across the CTA), deterministic order in j
+        for (int i = tid; i < m; i += NORM_THREADS) {
+            R acc = 0;
+            for (int j = 0; j < n; ++j) {
+                if (! in_shape(cfg, i, j)) continue;
+                if (mode == 'O' && i == j) continue;            // sym: diagonal already in the column sum
+                acc += elem_abs(cfg, a, lda, i, j);
+            }
+            if (mode == 'I') out[i] = acc;
+            else if (mode == 'B') out[n + i] = acc;
+            else out[i] += acc;                                 // sym one-norm: mirrored part of column i
+        }
+    }
+}
+
+template <typename T>
+static int launch_norm(int mode, NormCfg cfg, int64_t m, int64_t n, const T* const* A, int64_t lda,
+                       typename RealOf<T>::type* values, int64_t ldv, int64_t batch, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (m < 0 || n < 0 || batch < 0) return SB200_EINVAL;
+    if (batch == 0) return SB200_OK;
+    if (m > 0x7fffffff || n > 0x7fffffff || batch > 0x7fffffff || lda < m) return SB200_EINVAL;
+    int64_t need = 1;
+    if (mode == 'O' || mode == 'C') need = n;
+    if (mode == 'I') need = m;
+    if (mode == 'F') need = 2;
+    if (mode == 'B') need = m + n;
+    if (ldv < need) return SB200_EINVAL;
+    if (m == 0 || n == 0) {
+        // empty tiles: zero result (reference: device_genorm.cu:393-395)
+        cudaError_t e = cudaMemsetAsync(values, 0, size_t(batch) * ldv * sizeof(R), s);
+        return e == cudaSuccess ? SB200_OK : int(e);
+    }
+    norm_kernel<T><<<unsigned(batch), NORM_THREADS, 0, s>>>(mode, cfg, int(m), int(n), A, lda, values, ldv);
+    return launch_status();
+}
+
+static int norm_mode(int norm, int scope)
+{
+    if (scope == 'C') return norm == 'M' ? 'C' : -1;
+    if (scope != 'M') return -1;
+    return (norm == 'M' || norm == 'O' || norm == 'I' || norm == 'F') ? norm : -1;
+}
+
+} // namespace sb200
+
+using namespace sb200;
+#define ST cudaStream_t(stream)
+typedef const cuDoubleComplex* const* zcpp;
+
+extern "C" {
+
+int sb200_genorm_batched_d(int norm, int scope, int64_t m, int64_t n, const double* const* dA, int64_t lda,
+                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
+{
+    const int mode = norm_mode(norm, scope);
+    if (mode < 0) return SB200_ENOTSUP;
+    return launch_norm<double>(mode, NormCfg{0, 0, 0, 0}, m, n, dA, lda, values, ldv, batch, ST);
+}
+int sb200_genorm_batched_s(int norm, int scope, int64_t m, int64_t n, const float* const* dA, int64_t lda,
+                           float* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
+{
+    const int mode = norm_mode(norm, scope);
+    if (mode < 0) return SB200_ENOTSUP;
+    return launch_norm<float>(mode, NormCfg{0, 0, 0, 0}, m, n, dA, lda, values, ldv, batch, ST);
+}
+int sb200_genorm_batched_z(int norm, int scope, int64_t m, int64_t n, const sb200_c64* const* dA, int64_t lda,
+                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
+{
+    const int mode = norm_mode(norm, scope);
+    if (mode < 0) return SB200_ENOTSUP;
+    return launch_norm<cuDoubleComplex>(mode, NormCfg{0, 0, 0, 0}, m, n, zcpp(dA), lda, values, ldv, batch, ST);
+}
+
+// Hermitian / symmetric DIAGONAL tiles: One == Inf (device_henorm.cu:300-345)
+static int he_mode(int norm) { return norm == 'I' ? 'O' : norm_mode(norm, 'M'); }
+
+int sb200_henorm_batched_d(int norm, int uplo, int64_t n, const double* const* dA, int64_t lda,
+                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
+{
+    if (! valid_uplo(uplo)) return SB200_EINVAL;
+    if (he_mode(norm) < 0) return SB200_ENOTSUP;
+    return launch_norm<double>(he_mode(norm), NormCfg{uplo == 'L' ? 1 : 2, 1, 1, 0}, n, n, dA, lda, values, ldv, batch, ST);
+}
+int sb200_henorm_batched_z(int norm, int uplo, int64_t n, const sb200_c64* const* dA, int64_t lda,
+                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
+{
+    if (! valid_uplo(uplo)) return SB200_EINVAL;
+    if (he_mode(norm) < 0) return SB200_ENOTSUP;
+    return launch_norm<cuDoubleComplex>(he_mode(norm), NormCfg{uplo == 'L' ? 1 : 2, 1, 1, 0}, n, n, zcpp(dA), lda, values, ldv, batch, ST);
+}
+int sb200_synorm_batched_d(int norm, int uplo, int64_t n, const double* const* dA, int64_t lda,
+                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
+{
+    if (! valid_uplo(uplo)) return SB200_EINVAL;
+    if (he_mode(norm) < 0) return SB200_ENOTSUP;
+    return launch_norm<double>(he_mode(norm), NormCfg{uplo == 'L' ? 1 : 2, 1, 0, 0}, n, n, dA, lda, values, ldv, batch, ST);
+}
+// full off-diagonal tile of a symmetric matrix: column sums in values[0..n), row sums in
+// values[n..n+m)  (synorm_offdiag_one_kernel, device_synorm.cu:381-431)
+int sb200_synorm_offdiag_batched_d(int norm, int64_t m, int64_t n, const double* const* dA, int64_t lda,
+                                   double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
+{
+    if (norm != 'O' && norm != 'I') return SB200_ENOTSUP;
+    return launch_norm<double>('B', NormCfg{0, 0, 0, 0}, m, n, dA, lda, values, ldv, batch, ST);
+}
+int sb200_trnorm_batched_d(int norm, int uplo, int diag, int64_t m, int64_t n, const double* const* dA, int64_t lda,
+                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
+{
+    if (! valid_uplo(uplo) || ! valid_diag(diag)) return SB200_EINVAL;
+    const int mode = norm_mode(norm, 'M');
+    if (mode < 0) return SB200_ENOTSUP;
+    return launch_norm<double>(mode, NormCfg{uplo == 'L' ? 1 : 2, 0, 0, diag == 'U'}, m, n, dA, lda, values, ldv, batch, ST);
+}
+
+} // extern "C"

@@ -127,10 +127,43 @@ static int launch_batches(const std::vector<Batch>& bs, const PlanBuffer& pb, in
     return SB200_OK;
 }
 
+static double batches_flops(const std::vector<Batch>& bs)
+{
+    double f = 0;
+    for (const auto& b : bs) {
+        // ALGORITHMIC flops: a triangle-masked (herk/syrk diagonal) tile counts n(n+1)k
+        // (blaspp/include/blas/flops.hh syrk), whatever the kernel computes above the diagonal
+        const double per = b.tri ? double(b.n) * (b.n + 1.0) * b.k : 2.0 * b.m * b.n * b.k;
+        f += per * double(b.C.size());
+    }
+    return f;
+}
+
+static int64_t batches_launches(const std::vector<Batch>& bs) { return int64_t(bs.size()); }
+
 struct Streams {
     cudaStream_t panel = nullptr, trail = nullptr;
     std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> tev;          // timing event pairs around the trailing-update launches
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int time_begin(cudaStream_t s)
+    {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        tev.push_back(e);
+        CUDA_TRY(cudaEventRecord(e, s));
+        return SB200_OK;
+    }
+    int time_end(cudaStream_t s) { return time_begin(s); }
+    double timed_ms()
+    {
+        double tot = 0;
+        for (size_t i = 0; i + 1 < tev.size(); i += 2) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, tev[i], tev[i + 1]) == cudaSuccess) tot += ms;
+        }
+        return tot;
+    }
     int init(size_t nevents)
     {
         int lo, hi;
@@ -146,6 +179,7 @@ struct Streams {
     ~Streams()
     {
         for (auto e : ev) if (e) cudaEventDestroy(e);
+        for (auto e : tev) if (e) cudaEventDestroy(e);
         if (t0) cudaEventDestroy(t0);
         if (t1) cudaEventDestroy(t1);
         if (panel) cudaStreamDestroy(panel);
@@ -222,6 +256,8 @@ int potrf_driver(Matrix& A, int64_t* info_out)
 
     Streams st;
     SB_TRY(st.init(size_t(2 * nt)));
+    double trail_flops = 0;
+    int64_t trail_launches = 0;
     auto P_done = [&](int64_t k) { return st.ev[k]; };
     auto T_done = [&](int64_t k) { return st.ev[nt + k]; };
     SB_TRY(pb.upload(st.panel));
@@ -286,7 +322,13 @@ int potrf_driver(Matrix& A, int64_t* info_out)
         CUDA_TRY(cudaEventRecord(P_done(k), P));
         // -- trailing update of columns >= k+2
         CUDA_TRY(cudaStreamWaitEvent(T, P_done(k), 0));
-        SB_TRY(launch_batches(s.tr, pb, 'N', 'T', -1.0, 1.0, ld, T));
+        if (! s.tr.empty()) {
+            SB_TRY(st.time_begin(T));
+            SB_TRY(launch_batches(s.tr, pb, 'N', 'T', -1.0, 1.0, ld, T));
+            SB_TRY(st.time_end(T));
+            trail_flops += batches_flops(s.tr);
+            trail_launches += batches_launches(s.tr);
+        }
         CUDA_TRY(cudaEventRecord(T_done(k), T));
     }
     CUDA_TRY(cudaStreamWaitEvent(st.panel, T_done(nt - 1), 0));
@@ -298,6 +340,9 @@ int potrf_driver(Matrix& A, int64_t* info_out)
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, st.t0, st.t1));
     A.last_ms = ms;
+    A.last_trail_ms = st.timed_ms();
+    A.last_trail_flops = trail_flops;
+    A.last_trail_launches = trail_launches;
     int64_t info = hinfo;
     if (multi) {
         // first failing minor over all ranks (reference: internal_reduce_info.cc:23-38, MPI_MIN)
@@ -354,6 +399,8 @@ int gemm_driver(double alpha, Matrix& A, Matrix& B, double beta, Matrix& C)
         pb.reserve(plan[k]);
     }
     Streams st;
+    double trail_flops = 0;
+    int64_t trail_launches = 0;
     SB_TRY(st.init(size_t(2 * kt)));
     auto P_done = [&](int64_t k) { return st.ev[k]; };
     auto T_done = [&](int64_t k) { return st.ev[kt + k]; };
@@ -391,7 +438,11 @@ int gemm_driver(double alpha, Matrix& A, Matrix& B, double beta, Matrix& C)
             CUDA_TRY(cudaEventRecord(P_done(k), P));
             CUDA_TRY(cudaStreamWaitEvent(T, P_done(k), 0));
         }
+        SB_TRY(st.time_begin(T));
         SB_TRY(launch_batches(plan[k], pb, 'N', 'N', alpha, k == 0 ? beta : 1.0, ld, T));
+        SB_TRY(st.time_end(T));
+        trail_flops += batches_flops(plan[k]);
+        trail_launches += batches_launches(plan[k]);
         CUDA_TRY(cudaEventRecord(T_done(k), T));
     }
     CUDA_TRY(cudaEventRecord(st.t1, st.trail));
@@ -400,6 +451,9 @@ int gemm_driver(double alpha, Matrix& A, Matrix& B, double beta, Matrix& C)
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, st.t0, st.t1));
     C.last_ms = ms;
+    C.last_trail_ms = st.timed_ms();
+    C.last_trail_flops = trail_flops;
+    C.last_trail_launches = trail_launches;
     return SB200_OK;
 }
 
@@ -495,6 +549,16 @@ int sb200_matrix_destroy(sb200_matrix_t h)
 
 int64_t sb200_matrix_local_tiles(sb200_matrix_t h) { return h ? h->A.ntiles_loc : 0; }
 double  sb200_last_driver_ms(sb200_matrix_t h) { return h ? h->A.last_ms : 0.0; }
+
+int sb200_last_driver_stats(sb200_matrix_t h, double* out4)
+{
+    if (! h || ! out4) return SB200_EINVAL;
+    out4[0] = h->A.last_ms;
+    out4[1] = h->A.last_trail_ms;
+    out4[2] = h->A.last_trail_flops;
+    out4[3] = double(h->A.last_trail_launches);
+    return SB200_OK;
+}
 
 int sb200_matrix_generate_d(sb200_matrix_t h, int kind_code, int64_t seed, sb200_stream_t stream)
 {

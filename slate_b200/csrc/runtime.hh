@@ -42,7 +42,10 @@ struct Matrix {
     std::vector<int64_t> col_start;          // tile index of the first stored tile of local col jl
     int64_t ntiles_loc = 0;
     double* pool = nullptr;                  // ntiles_loc * nb*nb doubles, every tile ld = nb
-    double  last_ms = 0.0;
+    double  last_ms = 0.0;                   // device time of the last driver call (CUDA events)
+    double  last_trail_ms = 0.0;             // summed duration of its trailing-update GEMM launches
+    double  last_trail_flops = 0.0;          // algorithmic flops of those launches
+    int64_t last_trail_launches = 0;
 
     int64_t tile_elems() const { return nb * nb; }
     int64_t tile_mb(int64_t i) const { return i == mt - 1 ? m - i * nb : nb; }

@@ -110,12 +110,24 @@ class Grid:
             pass
 
 
+_DEFAULT_GRID: Grid | None = None
+
+
+def default_grid() -> Grid:
+    """The 1 x 1 grid (this process's current GPU) shared by matrices created without a grid,
+    so that operands of one call live on the same grid object."""
+    global _DEFAULT_GRID
+    if _DEFAULT_GRID is None or _DEFAULT_GRID._h is None:
+        _DEFAULT_GRID = Grid()
+    return _DEFAULT_GRID
+
+
 class Matrix:
     """General m-by-n tile matrix, nb-by-nb tiles, 2-D block-cyclic over the grid, resident in HBM."""
     _kind = "G"
 
     def __init__(self, m: int, n: int, nb: int, grid: Grid | None = None):
-        self.grid = grid or Grid()
+        self.grid = grid or default_grid()
         self.m, self.n, self.nb = int(m), int(n), int(nb)
         h = c_ptr()
         check(_matrix_create(self.grid._h, ord(self._kind), ord("C"), self.m, self.n, self.nb, ctypes.byref(h)),

@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures in tests/golden/ from the UNMODIFIED reference.
+
+Runs oracle/_ref/ref_dump (built from /root/reference by oracle/build_ref.sh: the reference's own
+matgen + Target::HostTask drivers, OpenMP + OpenBLAS) for small seeded problems and stores inputs
+are NOT stored (they are regenerated bit-exactly from the seed by the Philox generator; one
+generator fixture pins that), only outputs:
+
+  gen_{s,d,c,z}.npz      Philox matrices (rand and rand_dominant), bit-exact pin of matgen
+  potrf_d.npz            L = chol(A) lower, n=384 nb=128, rand_dominant seed 42
+  getrf_d.npz            LU and slate::Pivots (tileIndex, elementOffset), n=384 nb=128 ib=16, rand seed 42
+  getrf_d_ragged.npz     same, n=300 nb=128 (ragged last tile)
+  gemm_d.npz, gemm_z.npz C = alpha A B + beta C, tester alpha/beta, n=256 nb=64
+  herk_d.npz, herk_z.npz C = alpha A A^H + beta C lower, n=256 k=128 nb=64
+  trsm_d.npz             Left/Lower/NoTrans/NonUnit solve, m=256 n=128 nb=64
+  norms_d.npz            max/one/inf/fro of rand 200x136
+  gesv_mixed_d.npz       solution + iteration count, n=256 nb=64
+
+Usage (in the build container, where /root/reference exists):  python tests/golden/make_golden.py
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+EXE = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+OUT = os.path.dirname(os.path.abspath(__file__))
+DT = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
+
+
+def run(routine, t, n, nb, seeds=(42, 43, 44), **kv):
+    tmp = tempfile.mkdtemp()
+    prefix = os.path.join(tmp, "x")
+    cmd = [EXE, routine, t, str(n), str(nb), *map(str, seeds), prefix] + [f"{k}={v}" for k, v in kv.items()]
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="4")
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True)
+    meta = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    files = {}
+    for f in os.listdir(tmp):
+        key = f.split(".")[1]
+        dtype = np.int64 if key == "piv" else (np.float64 if (routine == "norms" and key == "out") else DT[t])
+        files[key] = np.fromfile(os.path.join(tmp, f), dtype=dtype)
+    return files, meta
+
+
+def main():
+    if not os.path.exists(EXE):
+        sys.exit("oracle/_ref/ref_dump missing: run oracle/build_ref.sh first")
+    for t in "sdcz":
+        a, _ = run("gen", t, 96, 32, seeds=(5, 6, 7), kind="rand", m=80)
+        b, _ = run("gen", t, 96, 32, seeds=(7, 6, 7), kind="rand_dominant")
+        np.savez_compressed(os.path.join(OUT, f"gen_{t}.npz"), rand=a["A"].reshape(80, 96, order="F"),
+                            rand_dominant=b["A"].reshape(96, 96, order="F"))
+    f, meta = run("potrf", "d", 384, 128)
+    np.savez_compressed(os.path.join(OUT, "potrf_d.npz"), out=f["out"].reshape(384, 384, order="F"), info=meta["info"])
+    for name, n in (("getrf_d", 384), ("getrf_d_ragged", 300)):
+        f, meta = run("getrf", "d", n, 128, ib=16, pt=1)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), out=f["out"].reshape(n, n, order="F"),
+                            piv=f["piv"].reshape(-1, 2), info=meta["info"])
+    for t in "dz":
+        f, _ = run("gemm", t, 256, 64)
+        np.savez_compressed(os.path.join(OUT, f"gemm_{t}.npz"), out=f["out"].reshape(256, 256, order="F"))
+        f, _ = run("herk", t, 256, 64, k=128)
+        np.savez_compressed(os.path.join(OUT, f"herk_{t}.npz"), out=f["out"].reshape(256, 256, order="F"))
+    f, _ = run("trsm", "d", 128, 64, m=256)
+    np.savez_compressed(os.path.join(OUT, "trsm_d.npz"), out=f["out"].reshape(256, 128, order="F"))
+    f, _ = run("norms", "d", 136, 64, m=200)
+    np.savez_compressed(os.path.join(OUT, "norms_d.npz"), out=f["out"])
+    f, meta = run("gesv_mixed", "d", 256, 64)
+    np.savez_compressed(os.path.join(OUT, "gesv_mixed_d.npz"), out=f["out"].reshape(256, 10, order="F"),
+                        iters=meta["iters"], info=meta["info"])
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
