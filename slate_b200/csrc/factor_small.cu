@@ -2,23 +2,21 @@
 //   * potrf_diag_kernel : Cholesky of one IB x IB (IB = 64) diagonal block in shared memory,
 //                         also emits inv(L) so the following block solve is a plain GEMM
 //   * trtri_diag_kernel : inverts the IB x IB diagonal blocks of a triangular tile
-// and the host compositions built on them and on the DMMA GEMM:
-//   * sb200_potrf_tile_d   (replaces cusolverDnDpotrf: lapackpp/src/cuda/cuda_potrf.cc,
-//                           call site src/internal/internal_potrf.cc:57-81)
-//   * sb200_trsm_batched_d (replaces cublasDtrsmBatched: blaspp/src/device_batch_trsm.cc:27-130,
-//                           call site src/internal/internal_trsm.cc:132-262)
+// and the host compositions built on them and on the batched tile GEMM:
+//   * sb200_potrf_tile_{d,s}   (replaces cusolverDn?potrf: lapackpp/src/cuda/cuda_potrf.cc,
+//                               call site src/internal/internal_potrf.cc:57-81)
+//   * sb200_trsm_batched_{d,s} (replaces cublas?trsmBatched: blaspp/src/device_batch_trsm.cc:27-130,
+//                               call site src/internal/internal_trsm.cc:132-262)
 // Block algorithm: invert the diagonal IB-blocks once, then block substitution where every
-// step is a batched DMMA GEMM over all tiles of the block row/column (the approach MAGMA /
-// cuBLAS take for large trsm; backward error is governed by cond of the IB x IB blocks only).
+// step is a batched GEMM over all tiles of the block row/column (FP64: DMMA tensor cores) --
+// the approach MAGMA / cuBLAS take for large trsm; backward error is governed by the
+// conditioning of the IB x IB diagonal blocks only.
 #include "gemm_dmma.cuh"
 
 namespace sb200 {
 
 constexpr int IB = 64;
-constexpr size_t SMALL_SMEM = 2 * IB * (IB + 1) * sizeof(double);
-
-// opt the two small kernels in to > 48 KB of dynamic shared memory (once per device)
-static void small_kernels_init();
+template <typename T> constexpr size_t small_smem() { return 2 * IB * (IB + 1) * sizeof(T); }
 
 // ---------------------------------------------------------------------------------------------
 // One CTA (256 threads) factors A (nv x nv, nv <= 64, lower, column-major, lda) in shared
@@ -26,36 +24,35 @@ static void small_kernels_init();
 // zero above the diagonal) to Winv.  On a non-positive pivot at column j writes
 // *info = info_base + j + 1 (first failure only) and stops.
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
-potrf_diag_kernel(double* __restrict__ A, int lda, int nv, double* __restrict__ Winv,
+potrf_diag_kernel(T* __restrict__ A, int lda, int nv, T* __restrict__ Winv,
                   int* __restrict__ info, int info_base)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    double (*L)[IB + 1] = reinterpret_cast<double (*)[IB + 1]>(smem_dyn);
-    double (*X)[IB + 1] = L + IB;
+    T (*L)[IB + 1] = reinterpret_cast<T (*)[IB + 1]>(smem_dyn);
+    T (*X)[IB + 1] = L + IB;
     __shared__ int fail;
     const int tid = threadIdx.x;
     if (tid == 0) fail = 0;
     for (int e = tid; e < IB * IB; e += 256) {
         const int i = e % IB, j = e / IB;
-        L[i][j] = (i < nv && j < nv && i >= j) ? A[i + int64_t(j) * lda] : (i == j ? 1.0 : 0.0);
+        L[i][j] = (i < nv && j < nv && i >= j) ? A[i + int64_t(j) * lda] : (i == j ? T(1) : T(0));
     }
     __syncthreads();
     if (*info != 0) return;          // an earlier block already failed: leave the tile alone
 
     for (int j = 0; j < nv; ++j) {
-        const double d = L[j][j];
-        if (!(d > 0.0)) {            // also catches NaN
+        const T d = L[j][j];
+        if (!(d > T(0))) {           // also catches NaN
             if (tid == 0) { fail = j + 1; }
         }
         __syncthreads();
         if (fail) break;
-        const double r = sqrt(d);
+        const T r = sqrt(d);
         __syncthreads();
-        // scale column j
         for (int i = j + tid; i < nv; i += 256) L[i][j] = (i == j) ? r : L[i][j] / r;
         __syncthreads();
-        // rank-1 update of the trailing lower triangle
         const int rem = nv - j - 1;
         for (int e = tid; e < rem * rem; e += 256) {
             const int i = j + 1 + e % rem, c = j + 1 + e / rem;
@@ -67,7 +64,6 @@ potrf_diag_kernel(double* __restrict__ A, int lda, int nv, double* __restrict__ 
         if (tid == 0 && *info == 0) *info = info_base + fail;
         return;
     }
-    // write L back
     for (int e = tid; e < nv * nv; e += 256) {
         const int i = e % nv, j = e / nv;
         if (i >= j) A[i + int64_t(j) * lda] = L[i][j];
@@ -75,10 +71,10 @@ potrf_diag_kernel(double* __restrict__ A, int lda, int nv, double* __restrict__ 
     // inverse by forward substitution, one column per thread (columns >= nv: identity)
     if (tid < IB) {
         const int j = tid;
-        for (int i = 0; i < IB; ++i) X[i][j] = 0.0;
-        X[j][j] = 1.0 / L[j][j];
+        for (int i = 0; i < IB; ++i) X[i][j] = T(0);
+        X[j][j] = T(1) / L[j][j];
         for (int i = j + 1; i < IB; ++i) {
-            double s = 0.0;
+            T s = T(0);
             for (int l = j; l < i; ++l) s = fma(L[i][l], X[l][j], s);
             X[i][j] = -s / L[i][i];
         }
@@ -95,58 +91,57 @@ potrf_diag_kernel(double* __restrict__ A, int lda, int nv, double* __restrict__ 
 // written to W + b*IB*IB (ld = IB), zero in the other triangle, padded with identity when the
 // last block is ragged.  lower != 0: T lower triangular; unit != 0: unit diagonal.
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
-trtri_diag_kernel(const double* __restrict__ T, int ldt, int na, int lower, int unit,
-                  double* __restrict__ W)
+trtri_diag_kernel(const T* __restrict__ Tm, int ldt, int na, int lower, int unit, T* __restrict__ W)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    double (*L)[IB + 1] = reinterpret_cast<double (*)[IB + 1]>(smem_dyn);   // always handled as LOWER:
-    double (*X)[IB + 1] = L + IB;                                           // upper blocks are transposed in
+    T (*L)[IB + 1] = reinterpret_cast<T (*)[IB + 1]>(smem_dyn);   // always handled as LOWER:
+    T (*X)[IB + 1] = L + IB;                                       // upper blocks are transposed in
     const int b = blockIdx.x, tid = threadIdx.x;
     const int o = b * IB;
     const int nv = min(IB, na - o);
     for (int e = tid; e < IB * IB; e += 256) {
         const int i = e % IB, j = e / IB;
-        double v = (i == j) ? 1.0 : 0.0;
+        T v = (i == j) ? T(1) : T(0);
         if (i < nv && j < nv) {
-            if (lower) { if (i > j) v = T[o + i + int64_t(o + j) * ldt]; else if (i == j && !unit) v = T[o + i + int64_t(o + j) * ldt]; }
-            else       { if (i > j) v = T[o + j + int64_t(o + i) * ldt]; else if (i == j && !unit) v = T[o + i + int64_t(o + j) * ldt]; }
+            if (i > j)                v = lower ? Tm[o + i + int64_t(o + j) * ldt] : Tm[o + j + int64_t(o + i) * ldt];
+            else if (i == j && !unit) v = Tm[o + i + int64_t(o + j) * ldt];
         }
         L[i][j] = v;
     }
     __syncthreads();
     if (tid < IB) {
         const int j = tid;
-        for (int i = 0; i < IB; ++i) X[i][j] = 0.0;
-        X[j][j] = 1.0 / L[j][j];
+        for (int i = 0; i < IB; ++i) X[i][j] = T(0);
+        X[j][j] = T(1) / L[j][j];
         for (int i = j + 1; i < IB; ++i) {
-            double s = 0.0;
+            T s = T(0);
             for (int l = j; l < i; ++l) s = fma(L[i][l], X[l][j], s);
             X[i][j] = -s / L[i][i];
         }
     }
     __syncthreads();
-    double* Wb = W + int64_t(b) * IB * IB;
+    T* Wb = W + int64_t(b) * IB * IB;
     for (int e = tid; e < IB * IB; e += 256) {
         const int i = e % IB, j = e / IB;
         Wb[e] = lower ? X[i][j] : X[j][i];      // inverse of the transpose = transpose of the inverse
     }
 }
 
+template <typename T>
 static void small_kernels_init()
 {
     static thread_local bool done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (done[dev & 63]) return;
-    cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMALL_SMEM));
-    cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMALL_SMEM));
+    cudaFuncSetAttribute(potrf_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem<T>()));
+    cudaFuncSetAttribute(trtri_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem<T>()));
     done[dev & 63] = true;
 }
 
-// ---------------------------------------------------------------------------------------------
 // per-device scratch for callers that pass work == NULL
-// ---------------------------------------------------------------------------------------------
 static void* device_scratch(size_t bytes)
 {
     struct Slot { void* p = nullptr; size_t n = 0; };
@@ -163,9 +158,10 @@ static void* device_scratch(size_t bytes)
     return s.p;
 }
 
-static GemmParamsD gp(int m, int n, int k, double alpha, double beta, int batch)
+template <typename T>
+static GemmParamsT<T> gp(int m, int n, int k, T alpha, T beta, int batch)
 {
-    GemmParamsD p{};
+    GemmParamsT<T> p{};
     p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta; p.batch = batch; p.tri = 0;
     return p;
 }
@@ -173,14 +169,16 @@ static GemmParamsD gp(int m, int n, int k, double alpha, double beta, int batch)
 // column-major block solve over a batch of B tiles with ONE triangular tile T (na x na):
 //   right: B_t <- alpha B_t op(T)^{-1}   (B_t is m x na)
 //   left : B_t <- alpha op(T)^{-1} B_t   (B_t is na x n)
-int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, double alpha,
-                    const double* T, int ldt, double* const* dB, int64_t offB, int ldb, int batch,
-                    double* W, cudaStream_t stream)
+// In-place GEMM steps are safe because one CTA covers the whole 64-wide aliased dimension.
+template <typename T>
+int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alpha,
+                  const T* Tm, int ldt, T* const* dB, int64_t offB, int ldb, int batch,
+                  T* W, cudaStream_t stream)
 {
     const int na = left ? m : n;
     const int nblk = int(ceil_div(na, IB));
-    small_kernels_init();
-    trtri_diag_kernel<<<nblk, 256, SMALL_SMEM, stream>>>(T, ldt, na, lower ? 1 : 0, unit ? 1 : 0, W);
+    small_kernels_init<T>();
+    trtri_diag_kernel<T><<<nblk, 256, small_smem<T>(), stream>>>(Tm, ldt, na, lower ? 1 : 0, unit ? 1 : 0, W);
     int st = launch_status();
     if (st) return st;
     const bool trans = (op != 'N');
@@ -195,90 +193,90 @@ int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, doub
         const int r0 = forward ? 0 : jo + jv;            // already-solved block range [r0, r1)
         const int r1 = forward ? jo : na;
         const int rk = r1 - r0;
-        double scale = alpha;
+        T scale = alpha;
         if (!left) {
             if (rk > 0) {
                 // B_j <- alpha B_j - X[:, r0:r1] * M[r0:r1, j],  M = op(T)
-                GemmParamsD p = gp(m, jv, rk, -1.0, alpha, batch);
+                GemmParamsT<T> p = gp<T>(m, jv, rk, T(-1), alpha, batch);
                 p.A = dB; p.offA = offB + int64_t(r0) * ldb; p.lda = ldb;
-                p.B0 = trans ? T + jo + int64_t(r0) * ldt : T + r0 + int64_t(jo) * ldt;
+                p.B0 = trans ? Tm + jo + int64_t(r0) * ldt : Tm + r0 + int64_t(jo) * ldt;
                 p.ldb = ldt; p.strideB = 0;
                 p.C = dB; p.offC = offB + int64_t(jo) * ldb; p.ldc = ldb;
-                if ((st = launch_gemm_d('N', opT, p, stream))) return st;
-                scale = 1.0;
+                if ((st = launch_gemm<T>('N', opT, p, stream))) return st;
+                scale = T(1);
             }
-            // B_j <- scale * B_j * op(Winv_j)   (in place: one CTA column covers all jv <= 64 columns)
-            GemmParamsD p = gp(m, jv, jv, scale, 0.0, batch);
+            // B_j <- scale * B_j * op(Winv_j)
+            GemmParamsT<T> p = gp<T>(m, jv, jv, scale, T(0), batch);
             p.A = dB; p.offA = offB + int64_t(jo) * ldb; p.lda = ldb;
             p.B0 = W + int64_t(j) * IB * IB; p.ldb = IB; p.strideB = 0;
             p.C = dB; p.offC = offB + int64_t(jo) * ldb; p.ldc = ldb;
-            if ((st = launch_gemm_d('N', opT, p, stream))) return st;
+            if ((st = launch_gemm<T>('N', opT, p, stream))) return st;
         }
         else {
             if (rk > 0) {
                 // B_j <- alpha B_j - M[j, r0:r1] * X[r0:r1, :]
-                GemmParamsD p = gp(jv, n, rk, -1.0, alpha, batch);
-                p.A0 = trans ? T + r0 + int64_t(jo) * ldt : T + jo + int64_t(r0) * ldt;
+                GemmParamsT<T> p = gp<T>(jv, n, rk, T(-1), alpha, batch);
+                p.A0 = trans ? Tm + r0 + int64_t(jo) * ldt : Tm + jo + int64_t(r0) * ldt;
                 p.lda = ldt; p.strideA = 0;
                 p.B = dB; p.offB = offB + r0; p.ldb = ldb;
                 p.C = dB; p.offC = offB + jo; p.ldc = ldb;
-                if ((st = launch_gemm_d(opT, 'N', p, stream))) return st;
-                scale = 1.0;
+                if ((st = launch_gemm<T>(opT, 'N', p, stream))) return st;
+                scale = T(1);
             }
-            // B_j <- scale * op(Winv_j) * B_j   (in place: one CTA row covers all jv <= 64 rows)
-            GemmParamsD p = gp(jv, n, jv, scale, 0.0, batch);
+            // B_j <- scale * op(Winv_j) * B_j
+            GemmParamsT<T> p = gp<T>(jv, n, jv, scale, T(0), batch);
             p.A0 = W + int64_t(j) * IB * IB; p.lda = IB; p.strideA = 0;
             p.B = dB; p.offB = offB + jo; p.ldb = ldb;
             p.C = dB; p.offC = offB + jo; p.ldc = ldb;
-            if ((st = launch_gemm_d(opT, 'N', p, stream))) return st;
+            if ((st = launch_gemm<T>(opT, 'N', p, stream))) return st;
         }
     }
     return SB200_OK;
 }
 
-// lower Cholesky of one n x n tile, blocked by IB; W >= 2*IB*IB doubles + 1 pointer slot
-int potrf_tile_lower_d(int n, double* A, int lda, int* dinfo, int info_base, double* W, cudaStream_t stream)
+// lower Cholesky of one n x n tile, blocked by IB; W >= IB*IB elements
+template <typename T>
+int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cudaStream_t stream)
 {
     int st;
-    small_kernels_init();
+    small_kernels_init<T>();
     for (int jo = 0; jo < n; jo += IB) {
         const int jv = min(IB, n - jo);
-        double* Ajj = A + jo + int64_t(jo) * lda;
-        potrf_diag_kernel<<<1, 256, SMALL_SMEM, stream>>>(Ajj, lda, jv, W, dinfo, info_base + jo);
+        T* Ajj = A + jo + int64_t(jo) * lda;
+        potrf_diag_kernel<T><<<1, 256, small_smem<T>(), stream>>>(Ajj, lda, jv, W, dinfo, info_base + jo);
         if ((st = launch_status())) return st;
         const int rest = n - jo - jv;
         if (rest <= 0) break;
-        double* Pnl = A + (jo + jv) + int64_t(jo) * lda;          // rest x jv block below the diagonal
+        T* Pnl = A + (jo + jv) + int64_t(jo) * lda;          // rest x jv block below the diagonal
         // panel <- panel * inv(L_jj)^T   (in place)
-        GemmParamsD p = gp(rest, jv, jv, 1.0, 0.0, 1);
+        GemmParamsT<T> p = gp<T>(rest, jv, jv, T(1), T(0), 1);
         p.A0 = Pnl; p.lda = lda; p.B0 = W; p.ldb = IB; p.C0 = Pnl; p.ldc = lda;
-        if ((st = launch_gemm_d('N', 'T', p, stream))) return st;
+        if ((st = launch_gemm<T>('N', 'T', p, stream))) return st;
         // trailing lower triangle -= panel panel^T
-        GemmParamsD q = gp(rest, rest, jv, -1.0, 1.0, 1);
+        GemmParamsT<T> q = gp<T>(rest, rest, jv, T(-1), T(1), 1);
         q.A0 = Pnl; q.lda = lda; q.B0 = Pnl; q.ldb = lda;
         q.C0 = A + (jo + jv) + int64_t(jo + jv) * lda; q.ldc = lda; q.tri = 1;
-        if ((st = launch_gemm_d('N', 'T', q, stream))) return st;
+        if ((st = launch_gemm<T>('N', 'T', q, stream))) return st;
     }
     return SB200_OK;
 }
 
-} // namespace sb200
-
-using namespace sb200;
-
-extern "C" {
-
-size_t sb200_trsm_work_bytes_d(int side, int64_t m, int64_t n)
+// double-precision entry points used by the runtime
+int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, double alpha,
+                    const double* T, int ldt, double* const* dB, int64_t offB, int ldb, int batch,
+                    double* W, cudaStream_t stream)
 {
-    const int64_t na = (side == 'L') ? m : n;
-    return size_t(ceil_div(na > 0 ? na : 1, IB)) * IB * IB * sizeof(double);
+    return trsm_colmajor<double>(left, lower, op, unit, m, n, alpha, T, ldt, dB, offB, ldb, batch, W, stream);
+}
+int potrf_tile_lower_d(int n, double* A, int lda, int* dinfo, int info_base, double* W, cudaStream_t stream)
+{
+    return potrf_tile_lower<double>(n, A, lda, dinfo, info_base, W, stream);
 }
 
-int sb200_trsm_batched_d(int layout, int side, int uplo, int op, int diag,
-                         int64_t m, int64_t n, double alpha,
-                         const double* dA, int64_t lda,
-                         double* const* dB, int64_t ldb,
-                         int64_t batch, void* work, sb200_stream_t stream)
+template <typename T>
+static int trsm_batched_t(int layout, int side, int uplo, int op, int diag, int64_t m, int64_t n, T alpha,
+                          const T* dA, int64_t lda, T* const* dB, int64_t ldb, int64_t batch, void* work,
+                          cudaStream_t stream)
 {
     if (! valid_layout(layout) || ! valid_side(side) || ! valid_uplo(uplo) || ! valid_op(op) || ! valid_diag(diag))
         return SB200_EINVAL;
@@ -294,32 +292,61 @@ int sb200_trsm_batched_d(int layout, int side, int uplo, int op, int diag,
     }
     const int64_t na = left ? m : n;
     if (lda < na || ldb < m) return SB200_EINVAL;
-    double* W = static_cast<double*>(work);
+    const size_t wbytes = size_t(ceil_div(na, IB)) * IB * IB * sizeof(T);
+    T* W = static_cast<T*>(work);
     if (! W) {
-        W = static_cast<double*>(device_scratch(sb200_trsm_work_bytes_d(left ? 'L' : 'R', m, n)));
+        W = static_cast<T*>(device_scratch(wbytes));
         if (! W) return SB200_ENOMEM;
     }
-    return trsm_colmajor_d(left, lower, op, diag == 'U', int(m), int(n), alpha, dA, int(lda),
-                           dB, 0, int(ldb), int(batch), W, cudaStream_t(stream));
+    return trsm_colmajor<T>(left, lower, op, diag == 'U', int(m), int(n), alpha, dA, int(lda),
+                            dB, 0, int(ldb), int(batch), W, stream);
 }
 
-size_t sb200_potrf_work_bytes_d(int64_t n) { (void) n; return size_t(IB) * IB * sizeof(double); }
-
-int sb200_potrf_tile_d(int uplo, int64_t n, double* dA, int64_t lda,
-                       int* dinfo, void* work, sb200_stream_t stream)
+template <typename T>
+static int potrf_tile_t(int uplo, int64_t n, T* dA, int64_t lda, int* dinfo, void* work, cudaStream_t stream)
 {
     if (! valid_uplo(uplo) || n < 0 || lda < (n > 1 ? n : 1) || n > 0x7fffffff || lda > 0x7fffffff)
         return SB200_EINVAL;
     if (uplo != 'L') return SB200_ENOTSUP;    // SLATE's potrf driver works on the lower triangle (src/potrf.cc:230-240)
-    cudaError_t e = cudaMemsetAsync(dinfo, 0, sizeof(int), cudaStream_t(stream));
+    cudaError_t e = cudaMemsetAsync(dinfo, 0, sizeof(int), stream);
     if (e != cudaSuccess) return int(e);
     if (n == 0) return SB200_OK;
-    double* W = static_cast<double*>(work);
+    T* W = static_cast<T*>(work);
     if (! W) {
-        W = static_cast<double*>(device_scratch(sb200_potrf_work_bytes_d(n)));
+        W = static_cast<T*>(device_scratch(size_t(IB) * IB * sizeof(T)));
         if (! W) return SB200_ENOMEM;
     }
-    return potrf_tile_lower_d(int(n), dA, int(lda), dinfo, 0, W, cudaStream_t(stream));
+    return potrf_tile_lower<T>(int(n), dA, int(lda), dinfo, 0, W, stream);
 }
+
+} // namespace sb200
+
+using namespace sb200;
+
+extern "C" {
+
+size_t sb200_trsm_work_bytes_d(int side, int64_t m, int64_t n)
+{
+    const int64_t na = (side == 'L') ? m : n;
+    return size_t(ceil_div(na > 0 ? na : 1, IB)) * IB * IB * sizeof(double);
+}
+
+int sb200_trsm_batched_d(int layout, int side, int uplo, int op, int diag, int64_t m, int64_t n, double alpha,
+                         const double* dA, int64_t lda, double* const* dB, int64_t ldb,
+                         int64_t batch, void* work, sb200_stream_t stream)
+{ return trsm_batched_t<double>(layout, side, uplo, op, diag, m, n, alpha, dA, lda, dB, ldb, batch, work, cudaStream_t(stream)); }
+
+int sb200_trsm_batched_s(int layout, int side, int uplo, int op, int diag, int64_t m, int64_t n, float alpha,
+                         const float* dA, int64_t lda, float* const* dB, int64_t ldb,
+                         int64_t batch, void* work, sb200_stream_t stream)
+{ return trsm_batched_t<float>(layout, side, uplo, op, diag, m, n, alpha, dA, lda, dB, ldb, batch, work, cudaStream_t(stream)); }
+
+size_t sb200_potrf_work_bytes_d(int64_t n) { (void) n; return size_t(IB) * IB * sizeof(double); }
+
+int sb200_potrf_tile_d(int uplo, int64_t n, double* dA, int64_t lda, int* dinfo, void* work, sb200_stream_t stream)
+{ return potrf_tile_t<double>(uplo, n, dA, lda, dinfo, work, cudaStream_t(stream)); }
+
+int sb200_potrf_tile_s(int uplo, int64_t n, float* dA, int64_t lda, int* dinfo, void* work, sb200_stream_t stream)
+{ return potrf_tile_t<float>(uplo, n, dA, lda, dinfo, work, cudaStream_t(stream)); }
 
 } // extern "C"

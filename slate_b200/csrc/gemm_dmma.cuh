@@ -24,21 +24,28 @@
 
 namespace sb200 {
 
-struct GemmParamsD {
-    const double* const* A;      // device pointer arrays (batch entries)
-    const double* const* B;
-    double* const*       C;
+template <typename T>
+struct GemmParamsT {
+    const T* const* A;           // device pointer arrays (batch entries)
+    const T* const* B;
+    T* const*       C;
     int64_t offA, offB, offC;    // element offsets added to every pointer
     int64_t strideA, strideB, strideC;  // used when the array pointer is null: base + t*stride
-    const double* A0;
-    const double* B0;
-    double*       C0;
+    const T* A0;
+    const T* B0;
+    T*       C0;
     int m, n, k;
     int lda, ldb, ldc;
-    double alpha, beta;
+    T alpha, beta;
     int batch;
     int tri;                     // 0 full, 1 keep lower (row >= col), 2 keep upper (row <= col)
+    int herk;                    // complex herk: force the diagonal of C real (generic kernel only)
 };
+using GemmParamsD = GemmParamsT<double>;
+
+// Type-generic launcher: double -> DMMA kernel below; float / complex -> gemm_generic.cu.
+// opA / opB in 'N','T','C' refer to the column-major problem C = alpha op(A) op(B) + beta C.
+template <typename T> int launch_gemm(int opA, int opB, GemmParamsT<T> p, cudaStream_t stream);
 
 // Tile configuration.  CTA tile BM x BN x 16; consumer warps own WM x WN warp tiles
 // (WM/8 x WN/8 DMMA accumulator pairs); consumer warps fill whole warpgroups so that

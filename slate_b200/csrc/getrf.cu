@@ -1,7 +1,540 @@
-// getrf.cu -- LU with partial pivoting (placeholder until the GPU panel lands).
+// getrf.cu -- LU with partial pivoting: GPU panel, fused row interchanges, driver.
+//
+// Reference: src/getrf.cc:22-244 (driver), src/internal/internal_getrf.cc:21-121 +
+// src/internal/Tile_getrf.hh:160-447 (panel, ALWAYS on the host CPU in the reference: tiles are
+// pulled device->host and pushed back at every step), src/internal/internal_swap.cc:510-805
+// (permuteRows<Devices>: one cublas?swap launch per pivot row per block column).
+//
+// B200-first redesign:
+//   * The panel is factored ON THE GPU.  A cooperative kernel keeps a whole m x 32 column block
+//     resident in shared memory, rows spread over up to 148 CTAs (<= 768 rows each); per
+//     column there is ONE grid-wide barrier: every CTA publishes its local |max| candidate row,
+//     all CTAs redundantly pick the winner, swap, scale and rank-1 update from shared memory.
+//     HBM traffic of a block = one read + one write.  Blocks are chained right-looking with
+//     the DMMA GEMM (trsm + rank-32 update), as the reference's ib-blocked panel does.
+//   * Pivot rule = the reference's (Tile_getrf.hh:196-289): start from the diagonal entry, take
+//     the first strictly larger |a_ij| scanning rows in increasing order (ties keep the lowest
+//     row; equals the reference run with one panel thread); scale by the reciprocal unless
+//     |pivot| < safe_min; exact zero pivot -> info = column+1 and the column is left unscaled.
+//   * Row interchanges of a whole panel are applied to a block-column range in ONE launch.
+//   * Column-major tiles throughout (the reference converts to row-major for its swap BLAS
+//     calls, src/getrf.cc:51-55); the fused swap kernel takes either layout.
 #include "runtime.hh"
-extern "C" int sb200_getrf_d(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
+#include "gemm_dmma.cuh"
+#include <cooperative_groups.h>
+#include <cfloat>
+#include <climits>
+#include <cstdio>
+
+namespace cg = cooperative_groups;
+
+namespace sb200 {
+
+int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, double alpha,
+                    const double* T, int ldt, double* const* dB, int64_t offB, int ldb, int batch,
+                    double* W, cudaStream_t stream);
+
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return int(e_); } while (0)
+#define SB_TRY(x) do { int s_ = (x); if (s_ != SB200_OK) return s_; } while (0)
+
+constexpr int PW = 32;            // panel base-block width (the tester's ib 32)
+constexpr int PROWS_MAX = 768;    // rows of the block one CTA keeps in shared memory
+constexpr int PTHREADS = 256;
+
+// ------------------------------------------------------------------------------------------
+// Fused row interchanges: pivot jj in [j0, j1) swaps stack row jj with stack row
+// piv_tile[jj]*nb + piv_off[jj]; applied in order (forward) or reversed.  One thread per matrix
+// column; `tiles[t + jt*ldt]` is tile t of the stack in block column jt.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+laswp_kernel(double* const* __restrict__ tiles, int64_t ldt, int mb, int nb, int ld, int colmajor,
+             const int64_t* __restrict__ piv_tile, const int64_t* __restrict__ piv_off,
+             int j0, int j1, int forward, int64_t col_lo, int64_t col_hi)
 {
-    (void) A; (void) pivots; (void) opts; (void) info;
-    return SB200_ENOTSUP;
+    extern __shared__ int s_piv[];               // (j1 - j0) panel-relative target rows
+    for (int e = threadIdx.x; e < j1 - j0; e += blockDim.x)
+        s_piv[e] = int(piv_tile[j0 + e] * mb + piv_off[j0 + e]);
+    __syncthreads();
+    const int64_t gc = col_lo + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gc >= col_hi) return;
+    const int64_t jt = gc / nb;
+    const int cc = int(gc - jt * nb);
+    double* const* stack = tiles + jt * ldt;
+    const int64_t coff = colmajor ? int64_t(cc) * ld : cc;
+    const int64_t rstr = colmajor ? 1 : ld;
+    const int cnt = j1 - j0;
+    for (int s = 0; s < cnt; ++s) {
+        const int e = forward ? s : cnt - 1 - s;
+        const int r1 = j0 + e, r2 = s_piv[e];
+        if (r1 == r2) continue;
+        double* p1 = stack[r1 / mb] + int64_t(r1 % mb) * rstr + coff;
+        double* p2 = stack[r2 / mb] + int64_t(r2 % mb) * rstr + coff;
+        const double t = *p1; *p1 = *p2; *p2 = t;
+    }
 }
+
+static int launch_laswp(double* const* tiles, int64_t ldt, int mb, int nb, int ld, int colmajor,
+                        const int64_t* piv_tile, const int64_t* piv_off, int j0, int j1, int forward,
+                        int64_t col_lo, int64_t col_hi, cudaStream_t s)
+{
+    if (col_hi <= col_lo || j1 <= j0) return SB200_OK;
+    const int64_t cols = col_hi - col_lo;
+    laswp_kernel<<<unsigned(ceil_div(cols, 256)), 256, size_t(j1 - j0) * sizeof(int), s>>>(
+        tiles, ldt, mb, nb, ld, colmajor, piv_tile, piv_off, j0, j1, forward, col_lo, col_hi);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------
+// Cooperative panel base block: columns [c0, c0+w) of the panel (tile stack `tiles`, panel rows
+// [c0, m_p) active), rows_per rows per CTA held in shared memory.
+// ------------------------------------------------------------------------------------------
+struct BaseArgs {
+    double* const* tiles;
+    int nb, m_p, c0, w, rows_per;
+    int64_t* piv_tile; int64_t* piv_off;
+    double* gval; int* grow; double* gcand; double* gdiag;     // [2][G], [2][G], [2][G][PW], [2][PW]
+    int* info; int info_base;
+};
+
+__global__ void __launch_bounds__(PTHREADS)
+getrf_base_kernel(const BaseArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double blk[];                 // [w][RP]
+    __shared__ double s_prow[PW], s_drow[PW];
+    __shared__ double s_val[PTHREADS / 32];
+    __shared__ int    s_row[PTHREADS / 32];
+    __shared__ int    s_p, s_w;
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int RP = a.rows_per | 1;
+    const int r_begin = a.c0 + b * a.rows_per;
+    const int r_end = min(r_begin + a.rows_per, a.m_p);
+    const int nr = max(r_end - r_begin, 0);
+    const int nb = a.nb;
+
+    for (int c = 0; c < a.w; ++c)
+        for (int lr = tid; lr < nr; lr += PTHREADS) {
+            const int r = r_begin + lr;
+            blk[c * RP + lr] = a.tiles[r / nb][(r % nb) + int64_t(a.c0 + c) * nb];
+        }
+    __syncthreads();
+
+    for (int j = 0; j < a.w; ++j) {
+        const int d = a.c0 + j;                    // panel row of the diagonal entry
+        const int par = j & 1;
+        // ---- local candidate: first maximum of |a| over this CTA's rows below the diagonal
+        double best = -1.0;
+        int brow = INT_MAX;
+        for (int lr = tid; lr < nr; lr += PTHREADS) {
+            const int r = r_begin + lr;
+            if (r > d) {
+                const double v = fabs(blk[j * RP + lr]);
+                if (v > best) { best = v; brow = r; }      // rows ascend per thread: first max kept
+            }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+            if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; }
+        }
+        if (lane == 0) { s_val[warp] = best; s_row[warp] = brow; }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < PTHREADS / 32 ? s_val[lane] : -1.0;
+            brow = lane < PTHREADS / 32 ? s_row[lane] : INT_MAX;
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+                if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; }
+            }
+            if (lane == 0) { a.gval[par * G + b] = best; a.grow[par * G + b] = brow; s_p = brow; }
+        }
+        __syncthreads();
+        if (tid < a.w) {
+            const int cr = s_p;
+            if (cr != INT_MAX) a.gcand[(int64_t(par) * G + b) * PW + tid] = blk[tid * RP + (cr - r_begin)];
+            if (d >= r_begin && d < r_end) a.gdiag[par * PW + tid] = blk[tid * RP + (d - r_begin)];
+        }
+        __threadfence();
+        grid.sync();
+
+        // ---- every CTA picks the same winner: diagonal first, then strictly larger candidates
+        if (warp == 0) {
+            double bv = -1.0;
+            int br = INT_MAX, bw = -1;
+            for (int c = lane; c < G; c += 32) {
+                const double v = a.gval[par * G + c];
+                const int r = a.grow[par * G + c];
+                if (v > bv || (v == bv && r < br)) { bv = v; br = r; bw = c; }
+            }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, br, o);
+                const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; bw = ow; }
+            }
+            if (lane == 0) {
+                const double dv = fabs(a.gdiag[par * PW + j]);
+                if (bv > dv) { s_p = br; s_w = bw; }        // strict: the diagonal wins ties (and NaN)
+                else         { s_p = d;  s_w = -1; }
+            }
+        }
+        __syncthreads();
+        const int p = s_p;
+        if (tid < a.w) {
+            s_drow[tid] = a.gdiag[par * PW + tid];
+            s_prow[tid] = (p == d) ? s_drow[tid] : a.gcand[(int64_t(par) * G + s_w) * PW + tid];
+        }
+        __syncthreads();
+        if (p != d && tid < a.w) {
+            if (p >= r_begin && p < r_end) blk[tid * RP + (p - r_begin)] = s_drow[tid];
+            if (d >= r_begin && d < r_end) blk[tid * RP + (d - r_begin)] = s_prow[tid];
+        }
+        if (b == 0 && tid == 0) {
+            a.piv_tile[d] = p / nb;
+            a.piv_off[d] = p % nb;
+        }
+        __syncthreads();
+        const double pv = s_prow[j];
+        if (pv == 0.0) {
+            if (b == 0 && tid == 0 && *a.info == 0) *a.info = a.info_base + d + 1;
+        }
+        else {
+            const bool use_rcp = fabs(pv) >= DBL_MIN;
+            const double rcp = 1.0 / pv;
+            for (int lr = tid; lr < nr; lr += PTHREADS) {
+                const int r = r_begin + lr;
+                if (r > d) {
+                    double l = blk[j * RP + lr];
+                    l = use_rcp ? l * rcp : l / pv;
+                    blk[j * RP + lr] = l;
+                    for (int c = j + 1; c < a.w; ++c)
+                        blk[c * RP + lr] = fma(-l, s_prow[c], blk[c * RP + lr]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int c = 0; c < a.w; ++c)
+        for (int lr = tid; lr < nr; lr += PTHREADS) {
+            const int r = r_begin + lr;
+            a.tiles[r / nb][(r % nb) + int64_t(a.c0 + c) * nb] = blk[c * RP + lr];
+        }
+}
+
+struct PanelScratch {
+    double* gval = nullptr; int* grow = nullptr; double* gcand = nullptr; double* gdiag = nullptr;
+    double* W = nullptr;            // trsm workspace of the panel stream
+    int max_ctas = 0;
+    void* raw = nullptr;
+    int init()
+    {
+        int dev = 0, sms = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        max_ctas = sms;
+        const size_t G = size_t(sms);
+        const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8;
+        CUDA_TRY(cudaMalloc(&raw, bytes));
+        char* p = static_cast<char*>(raw);
+        gval = reinterpret_cast<double*>(p); p += 2 * G * 8;
+        grow = reinterpret_cast<int*>(p);    p += 2 * G * 8;
+        gcand = reinterpret_cast<double*>(p); p += 2 * G * PW * 8;
+        gdiag = reinterpret_cast<double*>(p); p += 2 * PW * 8;
+        W = reinterpret_cast<double*>(p);
+        static thread_local bool attr_done[64] = {};
+        if (! attr_done[dev & 63]) {
+            CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          int(PW * (PROWS_MAX | 1) * sizeof(double))));
+            attr_done[dev & 63] = true;
+        }
+        return SB200_OK;
+    }
+    ~PanelScratch() { if (raw) cudaFree(raw); }
+};
+
+// Factor the panel given as a stack of `ntile` tiles (device pointer array `stack`, nb x nb, ld =
+// nb; last tile has m_p - (ntile-1)*nb rows), kw columns, diag_len = min(m_p, kw) pivots.
+static int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
+                         int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
+                         PanelScratch& ps, cudaStream_t s)
+{
+    const int diag_len = std::min(m_p, kw);
+    for (int c0 = 0; c0 < diag_len; c0 += PW) {
+        const int w = std::min(PW, diag_len - c0);
+        const int active = m_p - c0;
+        int rows_per = std::max(int(ceil_div(active, ps.max_ctas)), std::min(active, PROWS_MAX));
+        rows_per = std::max(rows_per, PW);
+        if (rows_per > PROWS_MAX) return SB200_ENOTSUP;       // panel taller than 148 * 768 rows
+        const int G = int(ceil_div(active, rows_per));
+        BaseArgs a{stack, nb, m_p, c0, w, rows_per, piv_tile, piv_off,
+                   ps.gval, ps.grow, ps.gcand, ps.gdiag, dinfo, info_base};
+        void* args[] = {&a};
+        const size_t smem = size_t(w) * (rows_per | 1) * sizeof(double);
+        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel),
+                                                    dim3(G), dim3(PTHREADS), args, smem, s);
+        if (e != cudaSuccess) return int(e);
+        SB_TRY(launch_status());
+        // interchanges of this block applied to the rest of the panel (left and right of the block)
+        SB_TRY(launch_laswp(stack, 0, nb, nb, nb, 1, piv_tile, piv_off, c0, c0 + w, 1, 0, c0, s));
+        SB_TRY(launch_laswp(stack, 0, nb, nb, nb, 1, piv_tile, piv_off, c0, c0 + w, 1, c0 + w, kw, s));
+        const int rest = kw - c0 - w;
+        if (rest <= 0) continue;
+        // U12 = L11^{-1} A12  (top tile, rows c0..c0+w)
+        SB_TRY(trsm_colmajor_d(true, true, 'N', true, w, rest, 1.0, tile0 + c0 + int64_t(c0) * nb, nb,
+                               stack, c0 + int64_t(c0 + w) * nb, nb, 1, ps.W, s));
+        // A22 -= L21 U12
+        const double* U12 = tile0 + c0 + int64_t(c0 + w) * nb;
+        const int top_rows = std::min(nb, m_p) - (c0 + w);
+        if (top_rows > 0) {
+            GemmParamsD p{};
+            p.m = top_rows; p.n = rest; p.k = w; p.alpha = -1.0; p.beta = 1.0; p.batch = 1;
+            p.A0 = tile0 + (c0 + w) + int64_t(c0) * nb; p.lda = nb;
+            p.B0 = U12; p.ldb = nb;
+            p.C0 = tile0 + (c0 + w) + int64_t(c0 + w) * nb; p.ldc = nb;
+            SB_TRY(launch_gemm_d('N', 'N', p, s));
+        }
+        const int full = (m_p % nb == 0) ? ntile - 1 : ntile - 2;      // full-height tiles below tile 0
+        if (full > 0) {
+            GemmParamsD p{};
+            p.m = nb; p.n = rest; p.k = w; p.alpha = -1.0; p.beta = 1.0; p.batch = full;
+            p.A = stack + 1; p.offA = int64_t(c0) * nb; p.lda = nb;
+            p.B0 = U12; p.ldb = nb; p.strideB = 0;
+            p.C = stack + 1; p.offC = int64_t(c0 + w) * nb; p.ldc = nb;
+            SB_TRY(launch_gemm_d('N', 'N', p, s));
+        }
+        if (ntile > 1 && m_p % nb != 0) {
+            GemmParamsD p{};
+            p.m = m_p % nb; p.n = rest; p.k = w; p.alpha = -1.0; p.beta = 1.0; p.batch = 1;
+            p.A = stack + (ntile - 1); p.offA = int64_t(c0) * nb; p.lda = nb;
+            p.B0 = U12; p.ldb = nb;
+            p.C = stack + (ntile - 1); p.offC = int64_t(c0 + w) * nb; p.ldc = nb;
+            SB_TRY(launch_gemm_d('N', 'N', p, s));
+        }
+    }
+    return SB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// driver (single GPU in this round; the multi-GPU variant gathers the panel on the diagonal owner)
+// ------------------------------------------------------------------------------------------
+struct GBatch { int m, n, k; std::vector<const double*> A, B; std::vector<double*> C; size_t off = 0; };
+
+static void gb_add(std::vector<GBatch>& v, int m, int n, int k, const double* A, const double* B, double* C)
+{
+    for (auto& b : v)
+        if (b.m == m && b.n == n && b.k == k) { b.A.push_back(A); b.B.push_back(B); b.C.push_back(C); return; }
+    v.push_back(GBatch{m, n, k, {A}, {B}, {C}, 0});
+}
+
+int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
+{
+    Grid& g = *A.g;
+    if (A.kind != 'G' || A.layout != 'C') return SB200_EINVAL;
+    if (g.size() > 1) return SB200_ENOTSUP;
+    CUDA_TRY(cudaDeviceSynchronize());
+    const int64_t mt = A.mt, nt = A.nt, nb = A.nb;
+    const int ld = int(nb);
+    const int64_t kt = std::min(mt, nt);
+    const int64_t mn = std::min(A.m, A.n);
+    if (mn == 0) { if (info_out) *info_out = 0; return SB200_OK; }
+
+    // tile pointer tables: column-major (stacks of a block column) and row-major (block rows)
+    std::vector<double*> tbl(size_t(mt * nt)), tblT(size_t(mt * nt));
+    for (int64_t j = 0; j < nt; ++j)
+        for (int64_t i = 0; i < mt; ++i) {
+            tbl[size_t(i + j * mt)] = A.tile(i, j);
+            tblT[size_t(j + i * nt)] = A.tile(i, j);
+        }
+    // per-step GEMM batches: lookahead column k+1 and trailing columns >= k+2
+    struct Step { std::vector<GBatch> la, tr; };
+    std::vector<Step> steps(static_cast<size_t>(kt));
+    std::vector<const void*> hostptrs;
+    for (int64_t k = 0; k < kt; ++k) {
+        const int kw = int(A.tile_nb(k));
+        for (int64_t j = k + 1; j < nt; ++j)
+            for (int64_t i = k + 1; i < mt; ++i)
+                gb_add(j == k + 1 ? steps[k].la : steps[k].tr, int(A.tile_mb(i)), int(A.tile_nb(j)), kw,
+                       A.tile(i, k), A.tile(k, j), A.tile(i, j));
+        for (auto* lst : {&steps[k].la, &steps[k].tr})
+            for (auto& b : *lst) {
+                b.off = hostptrs.size();
+                hostptrs.insert(hostptrs.end(), b.A.begin(), b.A.end());
+                hostptrs.insert(hostptrs.end(), b.B.begin(), b.B.end());
+                hostptrs.insert(hostptrs.end(), b.C.begin(), b.C.end());
+            }
+    }
+    void** dplan = nullptr; double** dtbl = nullptr; double** dtblT = nullptr;
+    int64_t* dpiv = nullptr; int* dinfo = nullptr; double* Wt = nullptr;
+    auto cleanup = [&] {
+        if (dplan) cudaFree(dplan); if (dtbl) cudaFree(dtbl); if (dtblT) cudaFree(dtblT);
+        if (dpiv) cudaFree(dpiv); if (dinfo) cudaFree(dinfo); if (Wt) cudaFree(Wt);
+    };
+    struct Guard { decltype(cleanup)& f; ~Guard() { f(); } } guard{cleanup};
+    CUDA_TRY(cudaMalloc(&dplan, std::max<size_t>(hostptrs.size(), 1) * sizeof(void*)));
+    CUDA_TRY(cudaMalloc(&dtbl, tbl.size() * sizeof(double*)));
+    CUDA_TRY(cudaMalloc(&dtblT, tblT.size() * sizeof(double*)));
+    CUDA_TRY(cudaMalloc(&dpiv, size_t(2 * kt * nb) * sizeof(int64_t)));
+    CUDA_TRY(cudaMalloc(&dinfo, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&Wt, size_t(ceil_div(nb, 64)) * 64 * 64 * sizeof(double)));
+    int64_t* dpiv_tile = dpiv;
+    int64_t* dpiv_off = dpiv + kt * nb;
+
+    PanelScratch ps;
+    SB_TRY(ps.init());
+    cudaStream_t P = nullptr, T = nullptr;
+    int lo, hi;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&P, cudaStreamNonBlocking, hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&T, cudaStreamNonBlocking, lo));
+    std::vector<cudaEvent_t> ev(size_t(2 * kt));
+    for (auto& e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t t0, t1;
+    CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
+    auto P_done = [&](int64_t k) { return ev[size_t(k)]; };
+    auto T_done = [&](int64_t k) { return ev[size_t(kt + k)]; };
+    int status = SB200_OK;
+    double trail_flops = 0; int64_t trail_launches = 0;
+
+    auto run_batches = [&](const std::vector<GBatch>& bs, cudaStream_t s) -> int {
+        for (const auto& b : bs) {
+            GemmParamsD p{};
+            const size_t cnt = b.C.size();
+            p.A = reinterpret_cast<const double* const*>(dplan + b.off);
+            p.B = reinterpret_cast<const double* const*>(dplan + b.off + cnt);
+            p.C = reinterpret_cast<double* const*>(dplan + b.off + 2 * cnt);
+            p.m = b.m; p.n = b.n; p.k = b.k; p.lda = ld; p.ldb = ld; p.ldc = ld;
+            p.alpha = -1.0; p.beta = 1.0; p.batch = int(cnt);
+            SB_TRY(launch_gemm_d('N', 'N', p, s));
+        }
+        return SB200_OK;
+    };
+    // row-k solve U(k, j0..j1) = L_kk^{-1} A(k, j0..j1) on stream s with workspace W
+    auto row_trsm = [&](int64_t k, int64_t j0, int64_t j1, double* W, cudaStream_t s) -> int {
+        if (j1 <= j0) return SB200_OK;
+        const int kw = int(std::min(A.tile_mb(k), A.tile_nb(k)));
+        const int64_t jfull_end = (A.tile_nb(nt - 1) == nb) ? j1 : std::min(j1, nt - 1);
+        if (jfull_end > j0)
+            SB_TRY(trsm_colmajor_d(true, true, 'N', true, kw, int(nb), 1.0, A.tile(k, k), ld,
+                                   dtblT + j0 + k * nt, 0, ld, int(jfull_end - j0), W, s));
+        if (jfull_end < j1)
+            SB_TRY(trsm_colmajor_d(true, true, 'N', true, kw, int(A.tile_nb(nt - 1)), 1.0, A.tile(k, k), ld,
+                                   dtblT + (nt - 1) + k * nt, 0, ld, 1, W, s));
+        return SB200_OK;
+    };
+
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMemcpyAsync(dplan, hostptrs.data(), hostptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, P));
+        CUDA_TRY(cudaMemcpyAsync(dtbl, tbl.data(), tbl.size() * sizeof(double*), cudaMemcpyHostToDevice, P));
+        CUDA_TRY(cudaMemcpyAsync(dtblT, tblT.data(), tblT.size() * sizeof(double*), cudaMemcpyHostToDevice, P));
+        CUDA_TRY(cudaMemsetAsync(dinfo, 0, sizeof(int), P));
+        CUDA_TRY(cudaStreamSynchronize(P));
+        CUDA_TRY(cudaEventRecord(t0, P));
+        for (int64_t k = 0; k < kt; ++k) {
+            const int kw = int(A.tile_nb(k));
+            const int m_p = int(A.m - k * nb);
+            const int diag_len = std::min(m_p, kw);
+            int64_t* pt = dpiv_tile + k * nb;
+            int64_t* po = dpiv_off + k * nb;
+            double* const* stack_k = dtbl + k + k * mt;
+            // ---- panel k (column k already carries every earlier update: lookahead below)
+            SB_TRY(getrf_panel_d(stack_k, A.tile(k, k), int(mt - k), int(nb), m_p, kw, pt, po, dinfo, int(k * nb), ps, P));
+            CUDA_TRY(cudaEventRecord(P_done(k), P));
+            // ---- trailing update of columns >= k+2 and interchanges to the left, normal priority
+            CUDA_TRY(cudaStreamWaitEvent(T, P_done(k), 0));
+            SB_TRY(launch_laswp(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1, 0, k * nb, T));
+            if (k + 2 < nt) {
+                SB_TRY(launch_laswp(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1, (k + 2) * nb, A.n, T));
+                SB_TRY(row_trsm(k, k + 2, nt, Wt, T));
+                if (! steps[k].tr.empty()) {
+                    cudaEvent_t a0, a1;
+                    CUDA_TRY(cudaEventCreate(&a0)); CUDA_TRY(cudaEventCreate(&a1));
+                    tev.push_back(a0); tev.push_back(a1);
+                    CUDA_TRY(cudaEventRecord(a0, T));
+                    SB_TRY(run_batches(steps[k].tr, T));
+                    CUDA_TRY(cudaEventRecord(a1, T));
+                    for (const auto& b : steps[k].tr) trail_flops += 2.0 * b.m * b.n * b.k * double(b.C.size());
+                    trail_launches += int64_t(steps[k].tr.size());
+                }
+            }
+            CUDA_TRY(cudaEventRecord(T_done(k), T));
+            // ---- lookahead: bring column k+1 up to date on the panel stream
+            if (k + 1 < nt) {
+                if (k >= 1) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 1), 0));
+                SB_TRY(launch_laswp(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1,
+                                    (k + 1) * nb, std::min<int64_t>((k + 2) * nb, A.n), P));
+                SB_TRY(row_trsm(k, k + 1, k + 2, ps.W, P));
+                SB_TRY(run_batches(steps[k].la, P));
+            }
+        }
+        CUDA_TRY(cudaStreamWaitEvent(P, T_done(kt - 1), 0));
+        CUDA_TRY(cudaEventRecord(t1, P));
+        CUDA_TRY(cudaStreamSynchronize(P));
+        CUDA_TRY(cudaStreamSynchronize(T));
+        return SB200_OK;
+    };
+    status = body();
+    if (status == SB200_OK) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        A.last_ms = ms;
+        double tms = 0;
+        for (size_t i = 0; i + 1 < tev.size(); i += 2) { float x = 0; if (cudaEventElapsedTime(&x, tev[i], tev[i + 1]) == cudaSuccess) tms += x; }
+        A.last_trail_ms = tms; A.last_trail_flops = trail_flops; A.last_trail_launches = trail_launches;
+        int hinfo = 0;
+        cudaMemcpy(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost);
+        if (info_out) *info_out = hinfo;
+        if (pivots_out) {
+            std::vector<int64_t> ht(size_t(kt * nb)), ho(size_t(kt * nb));
+            cudaMemcpy(ht.data(), dpiv_tile, ht.size() * sizeof(int64_t), cudaMemcpyDeviceToHost);
+            cudaMemcpy(ho.data(), dpiv_off, ho.size() * sizeof(int64_t), cudaMemcpyDeviceToHost);
+            int64_t o = 0;
+            for (int64_t k = 0; k < kt; ++k) {
+                const int64_t dl = std::min(A.m - k * nb, A.tile_nb(k));
+                for (int64_t j = 0; j < dl && o < mn; ++j, ++o) {
+                    pivots_out[2 * o] = ht[size_t(k * nb + j)];
+                    pivots_out[2 * o + 1] = ho[size_t(k * nb + j)];
+                }
+            }
+        }
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    for (auto e : tev) cudaEventDestroy(e);
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    if (P) cudaStreamDestroy(P);
+    if (T) cudaStreamDestroy(T);
+    return status;
+}
+
+} // namespace sb200
+
+using namespace sb200;
+struct sb200_matrix_s { Matrix A; };
+
+extern "C" {
+
+int sb200_getrf_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
+{
+    (void) opts;     // inner blocking is fixed at 32, lookahead at 1, pivot threshold at 1.0
+    if (! h) return SB200_EINVAL;
+    return getrf_driver(h->A, pivots, info);
+}
+
+int sb200_permute_rows_d(int layout, int forward, int64_t npiv,
+                         const int64_t* d_piv_tile, const int64_t* d_piv_off,
+                         double* const* dTiles, int64_t mt, int64_t ncolblocks,
+                         int64_t tile_mb, int64_t ncols, int64_t ld, sb200_stream_t stream)
+{
+    if (! valid_layout(layout) || npiv < 0 || mt < 1 || ncolblocks < 0 || tile_mb < 1 || ncols < 0) return SB200_EINVAL;
+    if (npiv == 0 || ncolblocks == 0 || ncols == 0) return SB200_OK;
+    if (npiv > 0x7fffffff || tile_mb > 0x7fffffff || ld > 0x7fffffff) return SB200_EINVAL;
+    // `ncols` columns per tile, block columns are `ncols` wide
+    return launch_laswp(dTiles, mt, int(tile_mb), int(ncols), int(ld), layout == 'C', d_piv_tile, d_piv_off,
+                        0, int(npiv), forward != 0, 0, ncolblocks * ncols, cudaStream_t(stream));
+}
+
+} // extern "C"

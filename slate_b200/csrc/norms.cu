@@ -11,12 +11,10 @@
 // reductions, deterministic combine order, columns walked by warps (coalesced 256-byte lines)
 // and rows by threads (coalesced across the CTA).
 #include "common.cuh"
+#include "scalar_ops.cuh"
 
 namespace sb200 {
 
-template <typename T> struct RealOf { using type = T; };
-template <> struct RealOf<cuDoubleComplex> { using type = double; };
-template <> struct RealOf<cuFloatComplex>  { using type = float; };
 
 __device__ inline float  abs_(float a) { return fabsf(a); }
 __device__ inline double abs_(double a) { return fabs(a); }

@@ -9,36 +9,9 @@
 // a single tile is spread over 64+ CTAs and a batch saturates HBM.  All kernels are pure streaming:
 // algorithmic bytes = traffic.
 #include "common.cuh"
+#include "scalar_ops.cuh"
 
 namespace sb200 {
-
-// ----------------------------------------------------------------------------- scalar helpers
-template <typename T> struct Scalar;
-template <> struct Scalar<float>  { using real = float;  static constexpr bool cplx = false; };
-template <> struct Scalar<double> { using real = double; static constexpr bool cplx = false; };
-template <> struct Scalar<cuFloatComplex>  { using real = float;  static constexpr bool cplx = true; };
-template <> struct Scalar<cuDoubleComplex> { using real = double; static constexpr bool cplx = true; };
-
-__host__ __device__ inline float  mul(float a, float b) { return a * b; }
-__host__ __device__ inline double mul(double a, double b) { return a * b; }
-__host__ __device__ inline cuFloatComplex  mul(cuFloatComplex a, cuFloatComplex b) { return cuCmulf(a, b); }
-__host__ __device__ inline cuDoubleComplex mul(cuDoubleComplex a, cuDoubleComplex b) { return cuCmul(a, b); }
-__host__ __device__ inline float  add(float a, float b) { return a + b; }
-__host__ __device__ inline double add(double a, double b) { return a + b; }
-__host__ __device__ inline cuFloatComplex  add(cuFloatComplex a, cuFloatComplex b) { return cuCaddf(a, b); }
-__host__ __device__ inline cuDoubleComplex add(cuDoubleComplex a, cuDoubleComplex b) { return cuCadd(a, b); }
-__host__ __device__ inline float  divide(float a, float b) { return a / b; }
-__host__ __device__ inline double divide(double a, double b) { return a / b; }
-__host__ __device__ inline cuFloatComplex  divide(cuFloatComplex a, cuFloatComplex b) { return cuCdivf(a, b); }
-__host__ __device__ inline cuDoubleComplex divide(cuDoubleComplex a, cuDoubleComplex b) { return cuCdiv(a, b); }
-__host__ __device__ inline float  rscale(float a, float r) { return a * r; }
-__host__ __device__ inline double rscale(double a, double r) { return a * r; }
-__host__ __device__ inline cuFloatComplex  rscale(cuFloatComplex a, float r) { return make_cuFloatComplex(a.x * r, a.y * r); }
-__host__ __device__ inline cuDoubleComplex rscale(cuDoubleComplex a, double r) { return make_cuDoubleComplex(a.x * r, a.y * r); }
-__host__ __device__ inline float  conj_(float a) { return a; }
-__host__ __device__ inline double conj_(double a) { return a; }
-__host__ __device__ inline cuFloatComplex  conj_(cuFloatComplex a) { return cuConjf(a); }
-__host__ __device__ inline cuDoubleComplex conj_(cuDoubleComplex a) { return cuConj(a); }
 
 // precision / domain conversions of device::gecopy (device_gecopy.cu:22-39 copy_a2b)
 template <typename D, typename S> __device__ inline D convert(S a);
