@@ -65,32 +65,38 @@ int         sb200_device_count(void);
 /* number of kernels launched by this library since load (all threads); bench.py's gpu_launches */
 int64_t     sb200_launch_count(void);
 
+/* ===========================================================================
+ * Type families.  Every kernel entry point exists for the four SLATE scalar types; the
+ * declarations below are generated with an X-macro: SB200_FOR_TYPES(M) expands
+ * M(suffix, scalar type, real type).
+ * =========================================================================== */
+#define SB200_FOR_TYPES(M) \
+    M(s, float,     float)  \
+    M(d, double,    double) \
+    M(c, sb200_c32, float)  \
+    M(z, sb200_c64, double)
+
 /* ---------------------------------------------------------------------------
  * Batched tile GEMM:  C_t = alpha * op(A_t) * op(B_t) + beta * C_t,  t < batch
  * replaces blas::batch::gemm fixed-size path -> cublas?gemmBatched
  * (blaspp/src/device_batch_gemm.cc:76-130; call sites src/internal/internal_gemm.cc:498-504,
- *  internal_herk.cc:510-516).  FP64 real/complex run on the FP64 tensor-core MMA (DMMA).
+ *  internal_herk.cc:510-516).  FP64 real and complex run on the FP64 tensor-core MMA (DMMA).
+ *   _batched : dA/dB/dC are DEVICE arrays of device pointers (as cublas?gemmBatched)
+ *   _strided : tile t is base + t*stride (batch == 1: a single GEMM; replaces blas::gemm(queue),
+ *              blaspp/src/device_gemm.cc -> cublas?gemm)
  * ------------------------------------------------------------------------- */
-int sb200_gemm_batched_d(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k,
-                         double alpha, const double* const* dA, int64_t lda,
-                         const double* const* dB, int64_t ldb,
-                         double beta, double* const* dC, int64_t ldc,
-                         int64_t batch, sb200_stream_t stream);
-int sb200_gemm_batched_z(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k,
-                         sb200_c64 alpha, const sb200_c64* const* dA, int64_t lda,
-                         const sb200_c64* const* dB, int64_t ldb,
-                         sb200_c64 beta, sb200_c64* const* dC, int64_t ldc,
-                         int64_t batch, sb200_stream_t stream);
-int sb200_gemm_batched_s(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k,
-                         float alpha, const float* const* dA, int64_t lda,
-                         const float* const* dB, int64_t ldb,
-                         float beta, float* const* dC, int64_t ldc,
-                         int64_t batch, sb200_stream_t stream);
-int sb200_gemm_batched_c(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k,
-                         sb200_c32 alpha, const sb200_c32* const* dA, int64_t lda,
-                         const sb200_c32* const* dB, int64_t ldb,
-                         sb200_c32 beta, sb200_c32* const* dC, int64_t ldc,
-                         int64_t batch, sb200_stream_t stream);
+#define SB200_DECL_GEMM(X, T, R) \
+int sb200_gemm_batched_##X(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k, \
+                           T alpha, const T* const* dA, int64_t lda, \
+                           const T* const* dB, int64_t ldb, \
+                           T beta, T* const* dC, int64_t ldc, \
+                           int64_t batch, sb200_stream_t stream); \
+int sb200_gemm_strided_##X(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k, \
+                           T alpha, const T* dA, int64_t lda, int64_t strideA, \
+                           const T* dB, int64_t ldb, int64_t strideB, \
+                           T beta, T* dC, int64_t ldc, int64_t strideC, \
+                           int64_t batch, sb200_stream_t stream);
+SB200_FOR_TYPES(SB200_DECL_GEMM)
 
 /* Same operation with per-array element offsets (A_t = dA[t] + offA, ...): lets the
  * host runtime address sub-blocks of resident tiles without rebuilding pointer arrays. */
@@ -103,28 +109,27 @@ int sb200_gemm_batched_off_d(int layout, int opA, int opB, int64_t m, int64_t n,
 /* ---------------------------------------------------------------------------
  * Batched HERK / SYRK on the stored triangle:
  *   C_t = alpha * op(A_t) * op(A_t)^H + beta * C_t   (herk; alpha, beta real; imag(diag) := 0)
- *   C_t = alpha * op(A_t) * op(A_t)^T + beta * C_t   (syrk)
+ *   C_t = alpha * op(A_t) * op(A_t)^T + beta * C_t   (syrk; alpha, beta of the scalar type)
  * replaces blas::batch::herk/syrk = a LOOP of per-tile cublas?herk/?syrk on forked
- * streams (blaspp/src/device_batch_herk.cc:57-73) and the single-tile blas::herk
- * (src/internal/internal_herk.cc:380-385) with one launch.
- * op = 'N': A_t is n-by-k;  op = 'C'/'T': A_t is k-by-n.
+ * streams (blaspp/src/device_batch_herk.cc:57-73, device_batch_syrk.cc) and the single-tile
+ * blas::herk / blas::syrk (blaspp/src/device_herk.cc, device_syrk.cc; call site
+ * src/internal/internal_herk.cc:380-385) with one launch.
+ * op = 'N': A_t is n-by-k;  op = 'C'/'T': A_t is k-by-n.  For real types herk == syrk.
  * ------------------------------------------------------------------------- */
-int sb200_herk_batched_d(int layout, int uplo, int op, int64_t n, int64_t k,
-                         double alpha, const double* const* dA, int64_t lda,
-                         double beta, double* const* dC, int64_t ldc,
-                         int64_t batch, sb200_stream_t stream);
-int sb200_herk_batched_z(int layout, int uplo, int op, int64_t n, int64_t k,
-                         double alpha, const sb200_c64* const* dA, int64_t lda,
-                         double beta, sb200_c64* const* dC, int64_t ldc,
-                         int64_t batch, sb200_stream_t stream);
-int sb200_syrk_batched_d(int layout, int uplo, int op, int64_t n, int64_t k,
-                         double alpha, const double* const* dA, int64_t lda,
-                         double beta, double* const* dC, int64_t ldc,
-                         int64_t batch, sb200_stream_t stream);
-int sb200_herk_batched_s(int layout, int uplo, int op, int64_t n, int64_t k,
-                         float alpha, const float* const* dA, int64_t lda,
-                         float beta, float* const* dC, int64_t ldc,
-                         int64_t batch, sb200_stream_t stream);
+#define SB200_DECL_HERK(X, T, R) \
+int sb200_herk_batched_##X(int layout, int uplo, int op, int64_t n, int64_t k, \
+                           R alpha, const T* const* dA, int64_t lda, \
+                           R beta, T* const* dC, int64_t ldc, \
+                           int64_t batch, sb200_stream_t stream); \
+int sb200_syrk_batched_##X(int layout, int uplo, int op, int64_t n, int64_t k, \
+                           T alpha, const T* const* dA, int64_t lda, \
+                           T beta, T* const* dC, int64_t ldc, \
+                           int64_t batch, sb200_stream_t stream); \
+int sb200_herk_##X(int layout, int uplo, int op, int64_t n, int64_t k, \
+                   R alpha, const T* dA, int64_t lda, R beta, T* dC, int64_t ldc, sb200_stream_t stream); \
+int sb200_syrk_##X(int layout, int uplo, int op, int64_t n, int64_t k, \
+                   T alpha, const T* dA, int64_t lda, T beta, T* dC, int64_t ldc, sb200_stream_t stream);
+SB200_FOR_TYPES(SB200_DECL_HERK)
 
 /* ---------------------------------------------------------------------------
  * Batched TRSM with ONE triangular tile shared by the batch (SLATE replicates the
@@ -132,20 +137,18 @@ int sb200_herk_batched_s(int layout, int uplo, int op, int64_t n, int64_t k,
  *   side 'L':  B_t <- alpha * op(A)^{-1} * B_t      side 'R':  B_t <- alpha * B_t * op(A)^{-1}
  * replaces blas::batch::trsm -> cublas?trsmBatched (blaspp/src/device_batch_trsm.cc:27-130).
  * `dA` is the device pointer of the single na-by-na triangular tile (na = m for 'L', n for 'R').
- * `work` is device scratch of at least sb200_trsm_work_bytes_X(...) bytes (the inverted
+ * `work` is device scratch of at least sb200_trsm_work_bytes(...) bytes (the inverted
  * diagonal blocks); it may be NULL, in which case an internal per-device scratch is used.
  * ------------------------------------------------------------------------- */
 size_t sb200_trsm_work_bytes_d(int side, int64_t m, int64_t n);
-int sb200_trsm_batched_d(int layout, int side, int uplo, int op, int diag,
-                         int64_t m, int64_t n, double alpha,
-                         const double* dA, int64_t lda,
-                         double* const* dB, int64_t ldb,
-                         int64_t batch, void* work, sb200_stream_t stream);
-int sb200_trsm_batched_s(int layout, int side, int uplo, int op, int diag,
-                         int64_t m, int64_t n, float alpha,
-                         const float* dA, int64_t lda,
-                         float* const* dB, int64_t ldb,
-                         int64_t batch, void* work, sb200_stream_t stream);
+size_t sb200_trsm_work_bytes(int dtype /* 's','d','c','z' */, int side, int64_t m, int64_t n);
+#define SB200_DECL_TRSM(X, T, R) \
+int sb200_trsm_batched_##X(int layout, int side, int uplo, int op, int diag, \
+                           int64_t m, int64_t n, T alpha, \
+                           const T* dA, int64_t lda, \
+                           T* const* dB, int64_t ldb, \
+                           int64_t batch, void* work, sb200_stream_t stream);
+SB200_FOR_TYPES(SB200_DECL_TRSM)
 
 /* ---------------------------------------------------------------------------
  * Cholesky factorisation of one diagonal tile on the device, LAPACK info in *dinfo
@@ -153,20 +156,20 @@ int sb200_trsm_batched_s(int layout, int side, int uplo, int op, int diag,
  * replaces lapack::potrf(uplo, n, dA, ldda, dinfo, queue) -> cusolverDn?potrf
  * (lapackpp/src/cuda/cuda_potrf.cc; call site src/internal/internal_potrf.cc:72-78).
  * ------------------------------------------------------------------------- */
-int sb200_potrf_tile_d(int uplo, int64_t n, double* dA, int64_t lda,
-                       int* dinfo, void* work, sb200_stream_t stream);
-int sb200_potrf_tile_s(int uplo, int64_t n, float* dA, int64_t lda,
-                       int* dinfo, void* work, sb200_stream_t stream);
 size_t sb200_potrf_work_bytes_d(int64_t n);
+#define SB200_DECL_POTRF(X, T, R) \
+int sb200_potrf_tile_##X(int uplo, int64_t n, T* dA, int64_t lda, \
+                         int* dinfo, void* work, sb200_stream_t stream);
+SB200_FOR_TYPES(SB200_DECL_POTRF)
 
 /* ---------------------------------------------------------------------------
- * Fused row interchanges for getrf on RowMajor tiles: applies all `npiv` pivots of
- * one panel to a whole block row/column set in ONE launch.
+ * Fused row interchanges for getrf: applies all `npiv` pivots of one panel to a whole
+ * block row/column set in ONE launch.
  * replaces the per-pivot-row cublas?swap loop of internal::permuteRows<Devices>
  * (src/internal/internal_swap.cc:674-688: nb launches per block column per step).
  *
  * The block column is given as `mt` tiles stacked vertically; dTiles[t + j*mt] is tile t of
- * block column j (tile_rows[t] rows each, ncols columns, RowMajor with leading dimension ld,
+ * block column j (tile_mb rows each, ncols columns, RowMajor with leading dimension ld,
  * or ColMajor when layout == 'C').  Pivot i swaps global row i of the stack with row
  * (piv_tile[i], piv_off[i]) -- the reference's Pivot{tileIndex, elementOffset}
  * (include/slate/types.hh:84-105) -- applied in order i = 0..npiv-1 (forward) or reversed.
@@ -178,106 +181,81 @@ int sb200_permute_rows_d(int layout, int forward, int64_t npiv,
                          sb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------
- * Seam 2: memory-bound tile kernels (slate::device::*, include/slate/internal/device.hh).
- * All batched over device pointer arrays; tile = m-by-n, column-major, leading dim ld.
+ * Seam 2: memory-bound tile kernels (slate::device::*, include/slate/internal/device.hh:92-281).
+ * Tiles are m-by-n, column-major, leading dim ld.  `_batched` entries take DEVICE arrays of
+ * device pointers (the caller uploads them, as for the reference: src/internal/internal_geadd.cc:163-165);
+ * the un-suffixed single-tile entries take the tile pointer itself.
+ * uplo: 'G' whole tile (ge*), 'L' / 'U' trapezoid (tz*).
  * ------------------------------------------------------------------------- */
-/* B = alpha*A + beta*B                     device::batch::geadd  (src/cuda/device_geadd.cu:215-260) */
-int sb200_geadd_batched_d(int64_t m, int64_t n, double alpha, const double* const* dA, int64_t lda,
-                          double beta, double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_geadd_batched_s(int64_t m, int64_t n, float alpha, const float* const* dA, int64_t lda,
-                          float beta, float* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_geadd_batched_z(int64_t m, int64_t n, sb200_c64 alpha, const sb200_c64* const* dA, int64_t lda,
-                          sb200_c64 beta, sb200_c64* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-/* A *= numer/denom                         device::batch::gescale (src/cuda/device_gescale.cu:200-240) */
-int sb200_gescale_batched_d(int64_t m, int64_t n, double numer, double denom,
-                            double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream);
-int sb200_gescale_batched_s(int64_t m, int64_t n, float numer, float denom,
-                            float* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream);
-int sb200_gescale_batched_z(int64_t m, int64_t n, sb200_c64 numer, sb200_c64 denom,
-                            sb200_c64* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream);
-/* A_ij *= R_i * C_j (equilibration)        device::gescale_row_col_batch (device_gescale_row_col.cu:150-210)
- * equed: 'R' rows only, 'C' cols only, 'B' both.  dR/dC: device arrays of pointers to scale vectors. */
-int sb200_gescale_row_col_batched_d(int equed, int64_t m, int64_t n,
-                                    const double* const* dR, const double* const* dC,
-                                    double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream);
-/* offdiag -> A_ij (i != j), diag -> A_ii    device::batch::geset   (src/cuda/device_geset.cu:180-220) */
-int sb200_geset_batched_d(int64_t m, int64_t n, double offdiag, double diag,
-                          double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream);
-int sb200_geset_batched_s(int64_t m, int64_t n, float offdiag, float diag,
-                          float* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream);
-int sb200_geset_batched_z(int64_t m, int64_t n, sb200_c64 offdiag, sb200_c64 diag,
-                          sb200_c64* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream);
-/* precision-converting copy B = A           device::gecopy          (src/cuda/device_gecopy.cu:75-115) */
-int sb200_gecopy_batched_dd(int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                            double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_gecopy_batched_ds(int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                            float* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_gecopy_batched_sd(int64_t m, int64_t n, const float* const* dA, int64_t lda,
-                            double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_gecopy_batched_ss(int64_t m, int64_t n, const float* const* dA, int64_t lda,
-                            float* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_gecopy_batched_zz(int64_t m, int64_t n, const sb200_c64* const* dA, int64_t lda,
-                            sb200_c64* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_gecopy_batched_zc(int64_t m, int64_t n, const sb200_c64* const* dA, int64_t lda,
-                            sb200_c32* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_gecopy_batched_cz(int64_t m, int64_t n, const sb200_c32* const* dA, int64_t lda,
-                            sb200_c64* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-/* trapezoid variants (uplo 'L'|'U')          device::tzset/tzadd/tzcopy/tzscale (src/cuda/device_tz*.cu) */
-int sb200_tzset_batched_d(int uplo, int64_t m, int64_t n, double offdiag, double diag,
-                          double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream);
-int sb200_tzadd_batched_d(int uplo, int64_t m, int64_t n, double alpha, const double* const* dA, int64_t lda,
-                          double beta, double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_tzscale_batched_d(int uplo, int64_t m, int64_t n, double numer, double denom,
-                            double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream);
-int sb200_tzcopy_batched_dd(int uplo, int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                            double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_tzcopy_batched_ds(int uplo, int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                            float* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-int sb200_tzcopy_batched_sd(int uplo, int64_t m, int64_t n, const float* const* dA, int64_t lda,
-                            double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
-/* transposes                                 device::transpose / transpose_batch (src/cuda/device_transpose.cu)
- * in-place square (n-by-n) and out-of-place rectangular (A m-by-n -> AT n-by-m); conj != 0 conjugates (complex) */
-int sb200_transpose_inplace_batched_d(int64_t n, double* const* dA, int64_t lda,
-                                      int64_t batch, sb200_stream_t stream);
-int sb200_transpose_batched_d(int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                              double* const* dAT, int64_t ldat, int64_t batch, sb200_stream_t stream);
-int sb200_transpose_inplace_batched_z(int conj, int64_t n, sb200_c64* const* dA, int64_t lda,
-                                      int64_t batch, sb200_stream_t stream);
-int sb200_transpose_batched_z(int conj, int64_t m, int64_t n, const sb200_c64* const* dA, int64_t lda,
-                              sb200_c64* const* dAT, int64_t ldat, int64_t batch, sb200_stream_t stream);
-int sb200_transpose_inplace_batched_s(int64_t n, float* const* dA, int64_t lda,
-                                      int64_t batch, sb200_stream_t stream);
-int sb200_transpose_batched_s(int64_t m, int64_t n, const float* const* dA, int64_t lda,
-                              float* const* dAT, int64_t ldat, int64_t batch, sb200_stream_t stream);
-/* per-tile norms                             device::genorm / henorm / synorm / trnorm (src/cuda/device_*norm.cu)
- * norm 'M' max, 'O' one, 'I' inf, 'F' frobenius; scope 'M' matrix (per-tile partial results),
- * 'C' columns (norm 'M' only: per-column max, used by colNorms).
- * values layout as the reference (device_genorm.cu:373-445): ldv >= 1 (max), n (one), m (inf), 2 (fro: scale, sumsq);
- * tile t writes values[t*ldv ...].  NaN-propagating max (device_util.cuh:22-25). */
-int sb200_genorm_batched_d(int norm, int scope, int64_t m, int64_t n,
-                           const double* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream);
-int sb200_genorm_batched_s(int norm, int scope, int64_t m, int64_t n,
-                           const float* const* dA, int64_t lda,
-                           float* values, int64_t ldv, int64_t batch, sb200_stream_t stream);
-int sb200_genorm_batched_z(int norm, int scope, int64_t m, int64_t n,
-                           const sb200_c64* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream);
-int sb200_henorm_batched_d(int norm, int uplo, int64_t n,
-                           const double* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream);
-int sb200_henorm_batched_z(int norm, int uplo, int64_t n,
-                           const sb200_c64* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream);
-int sb200_synorm_batched_d(int norm, int uplo, int64_t n,
-                           const double* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream);
-int sb200_synorm_offdiag_batched_d(int norm, int64_t m, int64_t n,
-                                   const double* const* dA, int64_t lda,
-                                   double* values, int64_t ldv, int64_t batch, sb200_stream_t stream);
-int sb200_trnorm_batched_d(int norm, int uplo, int diag, int64_t m, int64_t n,
-                           const double* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream);
+#define SB200_DECL_TILE_OPS(X, T, R) \
+/* B = alpha*A + beta*B       device::geadd / batch::geadd / tzadd (src/cuda/device_geadd.cu:121-146,234-262; device_tzadd.cu) */ \
+int sb200_geadd_##X(int64_t m, int64_t n, T alpha, const T* dA, int64_t lda, T beta, T* dB, int64_t ldb, sb200_stream_t stream); \
+int sb200_geadd_batched_##X(int64_t m, int64_t n, T alpha, const T* const* dA, int64_t lda, \
+                            T beta, T* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream); \
+int sb200_tzadd_batched_##X(int uplo, int64_t m, int64_t n, T alpha, const T* const* dA, int64_t lda, \
+                            T beta, T* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream); \
+/* A *= numer/denom            device::gescale / batch::gescale / batch::tzscale (device_gescale.cu, device_tzscale.cu) */ \
+int sb200_gescale_##X(int64_t m, int64_t n, T numer, T denom, T* dA, int64_t lda, sb200_stream_t stream); \
+int sb200_gescale_batched_##X(int64_t m, int64_t n, T numer, T denom, \
+                              T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream); \
+int sb200_tzscale_batched_##X(int uplo, int64_t m, int64_t n, R numer, R denom, \
+                              T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream); \
+/* A_ij *= R_i * C_j           device::gescale_row_col_batch (device_gescale_row_col.cu:150-210); \
+ * equed 'R' rows only, 'C' cols only, 'B' both; scale vectors of the scalar type (_t) or real type (_r) */ \
+int sb200_gescale_row_col_batched_##X(int equed, int64_t m, int64_t n, \
+                                      const T* const* dR, const T* const* dC, \
+                                      T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream); \
+int sb200_gescale_row_col_real_batched_##X(int equed, int64_t m, int64_t n, \
+                                      const R* const* dR, const R* const* dC, \
+                                      T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream); \
+/* offdiag -> A_ij (i != j), diag -> A_ii   device::geset / tzset + batch:: (device_geset.cu, device_tzset.cu) */ \
+int sb200_geset_##X(int uplo, int64_t m, int64_t n, T offdiag, T diag, T* dA, int64_t lda, sb200_stream_t stream); \
+int sb200_geset_batched_##X(int64_t m, int64_t n, T offdiag, T diag, \
+                            T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream); \
+int sb200_tzset_batched_##X(int uplo, int64_t m, int64_t n, T offdiag, T diag, \
+                            T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream); \
+/* transposes                   device::transpose / transpose_batch (src/cuda/device_transpose.cu): \
+ * in-place square (n-by-n) and out-of-place (A m-by-n -> AT n-by-m); conj != 0 conjugates */ \
+int sb200_transpose_inplace_##X(int conj, int64_t n, T* dA, int64_t lda, sb200_stream_t stream); \
+int sb200_transpose_##X(int conj, int64_t m, int64_t n, const T* dA, int64_t lda, T* dAT, int64_t ldat, sb200_stream_t stream); \
+int sb200_transpose_inplace_batched_##X(int conj, int64_t n, T* const* dA, int64_t lda, \
+                                        int64_t batch, sb200_stream_t stream); \
+int sb200_transpose_batched_##X(int conj, int64_t m, int64_t n, const T* const* dA, int64_t lda, \
+                                T* const* dAT, int64_t ldat, int64_t batch, sb200_stream_t stream); \
+/* per-tile norms               device::genorm / henorm / synorm / synormOffdiag / trnorm (src/cuda/device_*norm.cu) \
+ * norm 'M' max, 'O' one, 'I' inf, 'F' frobenius; scope 'M' matrix (per-tile partial results), \
+ * 'C' columns (norm 'M' only: per-column max, used by colNorms). \
+ * values layout as the reference (device_genorm.cu:373-445): ldv >= 1 (max), n (one), m (inf), 2 (fro: scale, sumsq); \
+ * tile t writes values[t*ldv ...].  NaN-propagating max (device_util.cuh:22-25). */ \
+int sb200_genorm_batched_##X(int norm, int scope, int64_t m, int64_t n, \
+                             const T* const* dA, int64_t lda, \
+                             R* values, int64_t ldv, int64_t batch, sb200_stream_t stream); \
+int sb200_henorm_batched_##X(int norm, int uplo, int64_t n, \
+                             const T* const* dA, int64_t lda, \
+                             R* values, int64_t ldv, int64_t batch, sb200_stream_t stream); \
+int sb200_synorm_batched_##X(int norm, int uplo, int64_t n, \
+                             const T* const* dA, int64_t lda, \
+                             R* values, int64_t ldv, int64_t batch, sb200_stream_t stream); \
+int sb200_synorm_offdiag_batched_##X(int norm, int64_t m, int64_t n, \
+                                     const T* const* dA, int64_t lda, \
+                                     R* values, int64_t ldv, int64_t batch, sb200_stream_t stream); \
+int sb200_trnorm_batched_##X(int norm, int uplo, int diag, int64_t m, int64_t n, \
+                             const T* const* dA, int64_t lda, \
+                             R* values, int64_t ldv, int64_t batch, sb200_stream_t stream);
+SB200_FOR_TYPES(SB200_DECL_TILE_OPS)
+
+/* precision / domain converting copies B = A   device::gecopy / tzcopy (src/cuda/device_gecopy.cu:75-235,
+ * device_tzcopy.cu): suffix = <source><destination>; every pair the reference instantiates. */
+#define SB200_FOR_COPY_PAIRS(M) \
+    M(ss, float, float)         M(sd, float, double)        M(dd, double, double)       M(ds, double, float) \
+    M(cc, sb200_c32, sb200_c32) M(cz, sb200_c32, sb200_c64) M(zz, sb200_c64, sb200_c64) M(zc, sb200_c64, sb200_c32) \
+    M(sc, float, sb200_c32)     M(dz, double, sb200_c64)
+#define SB200_DECL_COPY(XY, S, D) \
+int sb200_gecopy_batched_##XY(int64_t m, int64_t n, const S* const* dA, int64_t lda, \
+                              D* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream); \
+int sb200_tzcopy_batched_##XY(int uplo, int64_t m, int64_t n, const S* const* dA, int64_t lda, \
+                              D* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream);
+SB200_FOR_COPY_PAIRS(SB200_DECL_COPY)
 
 /* ---------------------------------------------------------------------------
  * Host runtime (C++ inside the library, exposed as opaque handles): a tile matrix

@@ -15,6 +15,13 @@ class SB200Error(RuntimeError):
 
 
 def _load():
+    # libslate_b200.so needs libnccl.so.2.  torch bundles a NEWER NCCL than the system one and
+    # refuses to import once the older library is resident (undefined ncclDevCommCreate), so make
+    # sure torch's copy is the one the process loads: import torch first, when it is installed.
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

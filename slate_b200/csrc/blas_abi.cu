@@ -1,0 +1,139 @@
+// blas_abi.cu -- C ABI of the contraction kernels (seam 1): batched / strided tile GEMM,
+// HERK and SYRK for the four SLATE scalar types.  Argument checking and the row-major
+// operand swap live here; the kernels are in gemm_dmma.cuh (FP64 real: DMMA tensor cores),
+// gemm_zdmma.cu (FP64 complex: DMMA, 4 real MMAs per complex MMA) and gemm_generic.cu
+// (float / complex<float>).
+//
+// Reference interface replaced: blas::batch::gemm / herk / syrk, blas::gemm / herk / syrk
+// (blaspp/src/device_batch_gemm.cc:27-155, device_batch_herk.cc:30-75, device_batch_syrk.cc,
+// device_gemm.cc, device_herk.cc, device_syrk.cc).
+#include "gemm_dmma.cuh"
+#include "scalar_ops.cuh"
+#include <algorithm>
+
+namespace sb200 {
+
+template <typename A> struct Cu { using type = A; };
+template <> struct Cu<sb200_c32> { using type = cuFloatComplex; };
+template <> struct Cu<sb200_c64> { using type = cuDoubleComplex; };
+static inline float  cv(float v) { return v; }
+static inline double cv(double v) { return v; }
+static inline cuFloatComplex  cv(sb200_c32 v) { return make_cuFloatComplex(v.re, v.im); }
+static inline cuDoubleComplex cv(sb200_c64 v) { return make_cuDoubleComplex(v.re, v.im); }
+template <typename T> constexpr bool is_complex_v = false;
+template <> constexpr bool is_complex_v<cuFloatComplex> = true;
+template <> constexpr bool is_complex_v<cuDoubleComplex> = true;
+
+// One implementation for pointer-array and strided operands: exactly one of (dA, A0) is set.
+template <typename T>
+static int gemm_impl(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k,
+                     T alpha, const T* const* dA, const T* A0, int64_t strideA, int64_t offA, int64_t lda,
+                     const T* const* dB, const T* B0, int64_t strideB, int64_t offB, int64_t ldb,
+                     T beta, T* const* dC, T* C0, int64_t strideC, int64_t offC, int64_t ldc,
+                     int64_t batch, int tri, int herk, cudaStream_t stream)
+{
+    if (! valid_layout(layout) || ! valid_op(opA) || ! valid_op(opB)) return SB200_EINVAL;
+    if (m < 0 || n < 0 || k < 0 || batch < 0) return SB200_EINVAL;
+    if (m == 0 || n == 0 || batch == 0) return SB200_OK;
+    if (m > 0x7fffffff || n > 0x7fffffff || k > 0x7fffffff
+        || lda > 0x7fffffff || ldb > 0x7fffffff || ldc > 0x7fffffff || batch > 0x7fffffff)
+        return SB200_EINVAL;
+    if (layout == 'R') {
+        // row-major C = op(A) op(B)  <=>  column-major C^T = op(B)^T op(A)^T: swap operands and m/n
+        // (same trick as the reference: blaspp/src/device_batch_gemm.cc:114-121)
+        std::swap(opA, opB); std::swap(dA, dB); std::swap(A0, B0); std::swap(strideA, strideB);
+        std::swap(offA, offB); std::swap(lda, ldb); std::swap(m, n);
+        if (tri == 1) tri = 2; else if (tri == 2) tri = 1;
+    }
+    const int64_t rowsA = (opA == 'N') ? m : k, rowsB = (opB == 'N') ? k : n;
+    if (lda < std::max<int64_t>(rowsA, 1) || ldb < std::max<int64_t>(rowsB, 1) || ldc < m) return SB200_EINVAL;
+    GemmParamsT<T> p{};
+    p.A = dA; p.B = dB; p.C = dC;
+    p.A0 = A0; p.B0 = B0; p.C0 = C0;
+    p.strideA = strideA; p.strideB = strideB; p.strideC = strideC;
+    p.offA = offA; p.offB = offB; p.offC = offC;
+    p.m = int(m); p.n = int(n); p.k = int(k);
+    p.lda = int(lda); p.ldb = int(ldb); p.ldc = int(ldc);
+    p.alpha = alpha; p.beta = beta; p.batch = int(batch); p.tri = tri; p.herk = herk;
+    return launch_gemm<T>(opA, opB, p, stream);
+}
+
+// herk: alpha/beta real, op in {N, C} (real types also T); syrk: op in {N, T} (real types also C)
+template <typename T>
+static int rank_k_impl(bool herk, int layout, int uplo, int op, int64_t n, int64_t k,
+                       T alpha, const T* const* dA, const T* A0, int64_t lda,
+                       T beta, T* const* dC, T* C0, int64_t ldc, int64_t batch, cudaStream_t stream)
+{
+    if (! valid_uplo(uplo) || ! valid_op(op)) return SB200_EINVAL;
+    if (is_complex_v<T> && op == (herk ? 'T' : 'C')) return SB200_EINVAL;
+    const int tri = (uplo == 'L') ? 1 : 2;
+    const int other = (herk && is_complex_v<T>) ? 'C' : 'T';
+    const int opA = (op == 'N') ? 'N' : other;
+    const int opB = (op == 'N') ? other : 'N';
+    return gemm_impl<T>(layout, opA, opB, n, n, k, alpha, dA, A0, 0, 0, lda, dA, A0, 0, 0, lda,
+                        beta, dC, C0, 0, 0, ldc, batch, tri, (herk && is_complex_v<T>) ? 1 : 0, stream);
+}
+
+} // namespace sb200
+
+using namespace sb200;
+#define ST cudaStream_t(stream)
+#define CT(T) Cu<T>::type
+#define CPP(T, p) reinterpret_cast<const Cu<T>::type* const*>(p)
+#define PP(T, p)  reinterpret_cast<Cu<T>::type* const*>(p)
+#define CP(T, p)  reinterpret_cast<const Cu<T>::type*>(p)
+#define P(T, p)   reinterpret_cast<Cu<T>::type*>(p)
+
+extern "C" {
+
+#define SB200_DEF_GEMM(X, T, R) \
+int sb200_gemm_batched_##X(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k, \
+                           T alpha, const T* const* dA, int64_t lda, const T* const* dB, int64_t ldb, \
+                           T beta, T* const* dC, int64_t ldc, int64_t batch, sb200_stream_t stream) \
+{ \
+    if (batch > 0 && m > 0 && n > 0 && (! dA || ! dB || ! dC)) return SB200_EINVAL; \
+    return gemm_impl<CT(T)>(layout, opA, opB, m, n, k, cv(alpha), CPP(T, dA), nullptr, 0, 0, lda, \
+                            CPP(T, dB), nullptr, 0, 0, ldb, cv(beta), PP(T, dC), nullptr, 0, 0, ldc, batch, 0, 0, ST); \
+} \
+int sb200_gemm_strided_##X(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k, \
+                           T alpha, const T* dA, int64_t lda, int64_t strideA, \
+                           const T* dB, int64_t ldb, int64_t strideB, \
+                           T beta, T* dC, int64_t ldc, int64_t strideC, int64_t batch, sb200_stream_t stream) \
+{ \
+    return gemm_impl<CT(T)>(layout, opA, opB, m, n, k, cv(alpha), nullptr, CP(T, dA), strideA, 0, lda, \
+                            nullptr, CP(T, dB), strideB, 0, ldb, cv(beta), nullptr, P(T, dC), strideC, 0, ldc, batch, 0, 0, ST); \
+}
+SB200_FOR_TYPES(SB200_DEF_GEMM)
+
+int sb200_gemm_batched_off_d(int layout, int opA, int opB, int64_t m, int64_t n, int64_t k,
+                             double alpha, const double* const* dA, int64_t offA, int64_t lda,
+                             const double* const* dB, int64_t offB, int64_t ldb,
+                             double beta, double* const* dC, int64_t offC, int64_t ldc,
+                             int64_t batch, sb200_stream_t stream)
+{
+    return gemm_impl<double>(layout, opA, opB, m, n, k, alpha, dA, nullptr, 0, offA, lda, dB, nullptr, 0, offB, ldb,
+                             beta, dC, nullptr, 0, offC, ldc, batch, 0, 0, ST);
+}
+
+#define SB200_DEF_HERK(X, T, R) \
+int sb200_herk_batched_##X(int layout, int uplo, int op, int64_t n, int64_t k, \
+                           R alpha, const T* const* dA, int64_t lda, R beta, T* const* dC, int64_t ldc, \
+                           int64_t batch, sb200_stream_t stream) \
+{ return rank_k_impl<CT(T)>(true, layout, uplo, op, n, k, from_real<CT(T)>(alpha), CPP(T, dA), nullptr, lda, \
+                            from_real<CT(T)>(beta), PP(T, dC), nullptr, ldc, batch, ST); } \
+int sb200_syrk_batched_##X(int layout, int uplo, int op, int64_t n, int64_t k, \
+                           T alpha, const T* const* dA, int64_t lda, T beta, T* const* dC, int64_t ldc, \
+                           int64_t batch, sb200_stream_t stream) \
+{ return rank_k_impl<CT(T)>(false, layout, uplo, op, n, k, cv(alpha), CPP(T, dA), nullptr, lda, \
+                            cv(beta), PP(T, dC), nullptr, ldc, batch, ST); } \
+int sb200_herk_##X(int layout, int uplo, int op, int64_t n, int64_t k, \
+                   R alpha, const T* dA, int64_t lda, R beta, T* dC, int64_t ldc, sb200_stream_t stream) \
+{ return rank_k_impl<CT(T)>(true, layout, uplo, op, n, k, from_real<CT(T)>(alpha), nullptr, CP(T, dA), lda, \
+                            from_real<CT(T)>(beta), nullptr, P(T, dC), ldc, 1, ST); } \
+int sb200_syrk_##X(int layout, int uplo, int op, int64_t n, int64_t k, \
+                   T alpha, const T* dA, int64_t lda, T beta, T* dC, int64_t ldc, sb200_stream_t stream) \
+{ return rank_k_impl<CT(T)>(false, layout, uplo, op, n, k, cv(alpha), nullptr, CP(T, dA), lda, \
+                            cv(beta), nullptr, P(T, dC), ldc, 1, ST); }
+SB200_FOR_TYPES(SB200_DEF_HERK)
+
+} // extern "C"

@@ -12,6 +12,7 @@
 // the approach MAGMA / cuBLAS take for large trsm; backward error is governed by the
 // conditioning of the IB x IB diagonal blocks only.
 #include "gemm_dmma.cuh"
+#include "scalar_ops.cuh"
 
 namespace sb200 {
 
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(256)
 potrf_diag_kernel(T* __restrict__ A, int lda, int nv, T* __restrict__ Winv,
                   int* __restrict__ info, int info_base)
 {
+    using R = typename RealOf<T>::type;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     T (*L)[IB + 1] = reinterpret_cast<T (*)[IB + 1]>(smem_dyn);
     T (*X)[IB + 1] = L + IB;
@@ -37,26 +39,27 @@ potrf_diag_kernel(T* __restrict__ A, int lda, int nv, T* __restrict__ Winv,
     if (tid == 0) fail = 0;
     for (int e = tid; e < IB * IB; e += 256) {
         const int i = e % IB, j = e / IB;
-        L[i][j] = (i < nv && j < nv && i >= j) ? A[i + int64_t(j) * lda] : (i == j ? T(1) : T(0));
+        L[i][j] = (i < nv && j < nv && i >= j) ? A[i + int64_t(j) * lda]
+                                               : (i == j ? from_real<T>(R(1)) : zero_of<T>());
     }
     __syncthreads();
     if (*info != 0) return;          // an earlier block already failed: leave the tile alone
 
     for (int j = 0; j < nv; ++j) {
-        const T d = L[j][j];
-        if (!(d > T(0))) {           // also catches NaN
+        const R d = real_of(L[j][j]);        // Hermitian: the imaginary part of the diagonal is ignored
+        if (!(d > R(0))) {                   // also catches NaN
             if (tid == 0) { fail = j + 1; }
         }
         __syncthreads();
         if (fail) break;
-        const T r = sqrt(d);
+        const R r = sqrt(d);
         __syncthreads();
-        for (int i = j + tid; i < nv; i += 256) L[i][j] = (i == j) ? r : L[i][j] / r;
+        for (int i = j + tid; i < nv; i += 256) L[i][j] = (i == j) ? from_real<T>(r) : div_real(L[i][j], r);
         __syncthreads();
         const int rem = nv - j - 1;
         for (int e = tid; e < rem * rem; e += 256) {
             const int i = j + 1 + e % rem, c = j + 1 + e / rem;
-            if (i >= c) L[i][c] -= L[i][j] * L[c][j];
+            if (i >= c) L[i][c] = sub(L[i][c], mul(L[i][j], conj_(L[c][j])));
         }
         __syncthreads();
     }
@@ -71,12 +74,12 @@ potrf_diag_kernel(T* __restrict__ A, int lda, int nv, T* __restrict__ Winv,
     // inverse by forward substitution, one column per thread (columns >= nv: identity)
     if (tid < IB) {
         const int j = tid;
-        for (int i = 0; i < IB; ++i) X[i][j] = T(0);
-        X[j][j] = T(1) / L[j][j];
+        for (int i = 0; i < IB; ++i) X[i][j] = zero_of<T>();
+        X[j][j] = divide(from_real<T>(R(1)), L[j][j]);
         for (int i = j + 1; i < IB; ++i) {
-            T s = T(0);
-            for (int l = j; l < i; ++l) s = fma(L[i][l], X[l][j], s);
-            X[i][j] = -s / L[i][i];
+            T s = zero_of<T>();
+            for (int l = j; l < i; ++l) fma_acc(s, L[i][l], X[l][j]);
+            X[i][j] = divide(neg(s), L[i][i]);
         }
     }
     __syncthreads();
@@ -95,6 +98,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 trtri_diag_kernel(const T* __restrict__ Tm, int ldt, int na, int lower, int unit, T* __restrict__ W)
 {
+    using R = typename RealOf<T>::type;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     T (*L)[IB + 1] = reinterpret_cast<T (*)[IB + 1]>(smem_dyn);   // always handled as LOWER:
     T (*X)[IB + 1] = L + IB;                                       // upper blocks are transposed in
@@ -103,7 +107,7 @@ trtri_diag_kernel(const T* __restrict__ Tm, int ldt, int na, int lower, int unit
     const int nv = min(IB, na - o);
     for (int e = tid; e < IB * IB; e += 256) {
         const int i = e % IB, j = e / IB;
-        T v = (i == j) ? T(1) : T(0);
+        T v = (i == j) ? from_real<T>(R(1)) : zero_of<T>();
         if (i < nv && j < nv) {
             if (i > j)                v = lower ? Tm[o + i + int64_t(o + j) * ldt] : Tm[o + j + int64_t(o + i) * ldt];
             else if (i == j && !unit) v = Tm[o + i + int64_t(o + j) * ldt];
@@ -113,12 +117,12 @@ trtri_diag_kernel(const T* __restrict__ Tm, int ldt, int na, int lower, int unit
     __syncthreads();
     if (tid < IB) {
         const int j = tid;
-        for (int i = 0; i < IB; ++i) X[i][j] = T(0);
-        X[j][j] = T(1) / L[j][j];
+        for (int i = 0; i < IB; ++i) X[i][j] = zero_of<T>();
+        X[j][j] = divide(from_real<T>(R(1)), L[j][j]);
         for (int i = j + 1; i < IB; ++i) {
-            T s = T(0);
-            for (int l = j; l < i; ++l) s = fma(L[i][l], X[l][j], s);
-            X[i][j] = -s / L[i][i];
+            T s = zero_of<T>();
+            for (int l = j; l < i; ++l) fma_acc(s, L[i][l], X[l][j]);
+            X[i][j] = divide(neg(s), L[i][i]);
         }
     }
     __syncthreads();
@@ -183,7 +187,7 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
     if (st) return st;
     const bool trans = (op != 'N');
     const bool eff_lower = (lower != trans);        // op(T) as a math matrix
-    const int opT = trans ? 'T' : 'N';
+    const int opT = trans ? op : 'N';          // 'C' conjugates (complex)
 
     for (int s = 0; s < nblk; ++s) {
         // right/upper and left/lower sweep forward; right/lower and left/upper sweep backward
@@ -197,16 +201,16 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
         if (!left) {
             if (rk > 0) {
                 // B_j <- alpha B_j - X[:, r0:r1] * M[r0:r1, j],  M = op(T)
-                GemmParamsT<T> p = gp<T>(m, jv, rk, T(-1), alpha, batch);
+                GemmParamsT<T> p = gp<T>(m, jv, rk, from_real<T>(-1), alpha, batch);
                 p.A = dB; p.offA = offB + int64_t(r0) * ldb; p.lda = ldb;
                 p.B0 = trans ? Tm + jo + int64_t(r0) * ldt : Tm + r0 + int64_t(jo) * ldt;
                 p.ldb = ldt; p.strideB = 0;
                 p.C = dB; p.offC = offB + int64_t(jo) * ldb; p.ldc = ldb;
                 if ((st = launch_gemm<T>('N', opT, p, stream))) return st;
-                scale = T(1);
+                scale = from_real<T>(1);
             }
             // B_j <- scale * B_j * op(Winv_j)
-            GemmParamsT<T> p = gp<T>(m, jv, jv, scale, T(0), batch);
+            GemmParamsT<T> p = gp<T>(m, jv, jv, scale, zero_of<T>(), batch);
             p.A = dB; p.offA = offB + int64_t(jo) * ldb; p.lda = ldb;
             p.B0 = W + int64_t(j) * IB * IB; p.ldb = IB; p.strideB = 0;
             p.C = dB; p.offC = offB + int64_t(jo) * ldb; p.ldc = ldb;
@@ -215,16 +219,16 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
         else {
             if (rk > 0) {
                 // B_j <- alpha B_j - M[j, r0:r1] * X[r0:r1, :]
-                GemmParamsT<T> p = gp<T>(jv, n, rk, T(-1), alpha, batch);
+                GemmParamsT<T> p = gp<T>(jv, n, rk, from_real<T>(-1), alpha, batch);
                 p.A0 = trans ? Tm + r0 + int64_t(jo) * ldt : Tm + jo + int64_t(r0) * ldt;
                 p.lda = ldt; p.strideA = 0;
                 p.B = dB; p.offB = offB + r0; p.ldb = ldb;
                 p.C = dB; p.offC = offB + jo; p.ldc = ldb;
                 if ((st = launch_gemm<T>(opT, 'N', p, stream))) return st;
-                scale = T(1);
+                scale = from_real<T>(1);
             }
             // B_j <- scale * op(Winv_j) * B_j
-            GemmParamsT<T> p = gp<T>(jv, n, jv, scale, T(0), batch);
+            GemmParamsT<T> p = gp<T>(jv, n, jv, scale, zero_of<T>(), batch);
             p.A0 = W + int64_t(j) * IB * IB; p.lda = IB; p.strideA = 0;
             p.B = dB; p.offB = offB + jo; p.ldb = ldb;
             p.C = dB; p.offC = offB + jo; p.ldc = ldb;
@@ -248,15 +252,15 @@ int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cuda
         const int rest = n - jo - jv;
         if (rest <= 0) break;
         T* Pnl = A + (jo + jv) + int64_t(jo) * lda;          // rest x jv block below the diagonal
-        // panel <- panel * inv(L_jj)^T   (in place)
-        GemmParamsT<T> p = gp<T>(rest, jv, jv, T(1), T(0), 1);
+        // panel <- panel * inv(L_jj)^H   (in place)
+        GemmParamsT<T> p = gp<T>(rest, jv, jv, from_real<T>(1), zero_of<T>(), 1);
         p.A0 = Pnl; p.lda = lda; p.B0 = W; p.ldb = IB; p.C0 = Pnl; p.ldc = lda;
-        if ((st = launch_gemm<T>('N', 'T', p, stream))) return st;
-        // trailing lower triangle -= panel panel^T
-        GemmParamsT<T> q = gp<T>(rest, rest, jv, T(-1), T(1), 1);
+        if ((st = launch_gemm<T>('N', 'C', p, stream))) return st;
+        // trailing lower triangle -= panel panel^H
+        GemmParamsT<T> q = gp<T>(rest, rest, jv, from_real<T>(-1), from_real<T>(1), 1);
         q.A0 = Pnl; q.lda = lda; q.B0 = Pnl; q.ldb = lda;
-        q.C0 = A + (jo + jv) + int64_t(jo + jv) * lda; q.ldc = lda; q.tri = 1;
-        if ((st = launch_gemm<T>('N', 'T', q, stream))) return st;
+        q.C0 = A + (jo + jv) + int64_t(jo + jv) * lda; q.ldc = lda; q.tri = 1; q.herk = 1;
+        if ((st = launch_gemm<T>('N', 'C', q, stream))) return st;
     }
     return SB200_OK;
 }
@@ -319,34 +323,37 @@ static int potrf_tile_t(int uplo, int64_t n, T* dA, int64_t lda, int* dinfo, voi
     return potrf_tile_lower<T>(int(n), dA, int(lda), dinfo, 0, W, stream);
 }
 
+template <typename A> struct Cu { using type = A; };
+template <> struct Cu<sb200_c32> { using type = cuFloatComplex; };
+template <> struct Cu<sb200_c64> { using type = cuDoubleComplex; };
+static inline float  cv(float v) { return v; }
+static inline double cv(double v) { return v; }
+static inline cuFloatComplex  cv(sb200_c32 v) { return make_cuFloatComplex(v.re, v.im); }
+static inline cuDoubleComplex cv(sb200_c64 v) { return make_cuDoubleComplex(v.re, v.im); }
+
 } // namespace sb200
 
 using namespace sb200;
 
 extern "C" {
 
-size_t sb200_trsm_work_bytes_d(int side, int64_t m, int64_t n)
+size_t sb200_trsm_work_bytes(int dtype, int side, int64_t m, int64_t n)
 {
     const int64_t na = (side == 'L') ? m : n;
-    return size_t(ceil_div(na > 0 ? na : 1, IB)) * IB * IB * sizeof(double);
+    const size_t es = dtype == 's' ? 4 : (dtype == 'd' || dtype == 'c') ? 8 : 16;
+    return size_t(ceil_div(na > 0 ? na : 1, IB)) * IB * IB * es;
 }
-
-int sb200_trsm_batched_d(int layout, int side, int uplo, int op, int diag, int64_t m, int64_t n, double alpha,
-                         const double* dA, int64_t lda, double* const* dB, int64_t ldb,
-                         int64_t batch, void* work, sb200_stream_t stream)
-{ return trsm_batched_t<double>(layout, side, uplo, op, diag, m, n, alpha, dA, lda, dB, ldb, batch, work, cudaStream_t(stream)); }
-
-int sb200_trsm_batched_s(int layout, int side, int uplo, int op, int diag, int64_t m, int64_t n, float alpha,
-                         const float* dA, int64_t lda, float* const* dB, int64_t ldb,
-                         int64_t batch, void* work, sb200_stream_t stream)
-{ return trsm_batched_t<float>(layout, side, uplo, op, diag, m, n, alpha, dA, lda, dB, ldb, batch, work, cudaStream_t(stream)); }
-
+size_t sb200_trsm_work_bytes_d(int side, int64_t m, int64_t n) { return sb200_trsm_work_bytes('d', side, m, n); }
 size_t sb200_potrf_work_bytes_d(int64_t n) { (void) n; return size_t(IB) * IB * sizeof(double); }
 
-int sb200_potrf_tile_d(int uplo, int64_t n, double* dA, int64_t lda, int* dinfo, void* work, sb200_stream_t stream)
-{ return potrf_tile_t<double>(uplo, n, dA, lda, dinfo, work, cudaStream_t(stream)); }
-
-int sb200_potrf_tile_s(int uplo, int64_t n, float* dA, int64_t lda, int* dinfo, void* work, sb200_stream_t stream)
-{ return potrf_tile_t<float>(uplo, n, dA, lda, dinfo, work, cudaStream_t(stream)); }
+#define SB200_DEF_FACTOR(X, T, R) \
+int sb200_trsm_batched_##X(int layout, int side, int uplo, int op, int diag, int64_t m, int64_t n, T alpha, \
+                           const T* dA, int64_t lda, T* const* dB, int64_t ldb, \
+                           int64_t batch, void* work, sb200_stream_t stream) \
+{ return trsm_batched_t<Cu<T>::type>(layout, side, uplo, op, diag, m, n, cv(alpha), \
+      reinterpret_cast<const Cu<T>::type*>(dA), lda, reinterpret_cast<Cu<T>::type* const*>(dB), ldb, batch, work, cudaStream_t(stream)); } \
+int sb200_potrf_tile_##X(int uplo, int64_t n, T* dA, int64_t lda, int* dinfo, void* work, sb200_stream_t stream) \
+{ return potrf_tile_t<Cu<T>::type>(uplo, n, reinterpret_cast<Cu<T>::type*>(dA), lda, dinfo, work, cudaStream_t(stream)); }
+SB200_FOR_TYPES(SB200_DEF_FACTOR)
 
 } // extern "C"

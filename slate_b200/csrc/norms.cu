@@ -200,75 +200,59 @@ static int norm_mode(int norm, int scope)
     return (norm == 'M' || norm == 'O' || norm == 'I' || norm == 'F') ? norm : -1;
 }
 
+// Hermitian / symmetric DIAGONAL tiles: One == Inf (device_henorm.cu:300-345)
+static int he_mode(int norm) { return norm == 'I' ? 'O' : norm_mode(norm, 'M'); }
+
+template <typename A> struct Cu { using type = A; };
+template <> struct Cu<sb200_c32> { using type = cuFloatComplex; };
+template <> struct Cu<sb200_c64> { using type = cuDoubleComplex; };
+
 } // namespace sb200
 
 using namespace sb200;
 #define ST cudaStream_t(stream)
-typedef const cuDoubleComplex* const* zcpp;
+#define CPP(T, p) reinterpret_cast<const Cu<T>::type* const*>(p)
 
 extern "C" {
 
-int sb200_genorm_batched_d(int norm, int scope, int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
-{
-    const int mode = norm_mode(norm, scope);
-    if (mode < 0) return SB200_ENOTSUP;
-    return launch_norm<double>(mode, NormCfg{0, 0, 0, 0}, m, n, dA, lda, values, ldv, batch, ST);
+#define SB200_DEF_NORMS(X, T, R) \
+int sb200_genorm_batched_##X(int norm, int scope, int64_t m, int64_t n, const T* const* dA, int64_t lda, \
+                             R* values, int64_t ldv, int64_t batch, sb200_stream_t stream) \
+{ \
+    const int mode = norm_mode(norm, scope); \
+    if (mode < 0) return SB200_ENOTSUP; \
+    return launch_norm<Cu<T>::type>(mode, NormCfg{0, 0, 0, 0}, m, n, CPP(T, dA), lda, values, ldv, batch, ST); \
+} \
+int sb200_henorm_batched_##X(int norm, int uplo, int64_t n, const T* const* dA, int64_t lda, \
+                             R* values, int64_t ldv, int64_t batch, sb200_stream_t stream) \
+{ \
+    if (! valid_uplo(uplo)) return SB200_EINVAL; \
+    if (he_mode(norm) < 0) return SB200_ENOTSUP; \
+    return launch_norm<Cu<T>::type>(he_mode(norm), NormCfg{uplo == 'L' ? 1 : 2, 1, 1, 0}, n, n, CPP(T, dA), lda, values, ldv, batch, ST); \
+} \
+int sb200_synorm_batched_##X(int norm, int uplo, int64_t n, const T* const* dA, int64_t lda, \
+                             R* values, int64_t ldv, int64_t batch, sb200_stream_t stream) \
+{ \
+    if (! valid_uplo(uplo)) return SB200_EINVAL; \
+    if (he_mode(norm) < 0) return SB200_ENOTSUP; \
+    return launch_norm<Cu<T>::type>(he_mode(norm), NormCfg{uplo == 'L' ? 1 : 2, 1, 0, 0}, n, n, CPP(T, dA), lda, values, ldv, batch, ST); \
+} \
+/* full off-diagonal tile of a symmetric matrix: column sums in values[0..n), row sums in \
+ * values[n..n+m)  (synorm_offdiag_one_kernel, device_synorm.cu:381-431) */ \
+int sb200_synorm_offdiag_batched_##X(int norm, int64_t m, int64_t n, const T* const* dA, int64_t lda, \
+                                     R* values, int64_t ldv, int64_t batch, sb200_stream_t stream) \
+{ \
+    if (norm != 'O' && norm != 'I') return SB200_ENOTSUP; \
+    return launch_norm<Cu<T>::type>('B', NormCfg{0, 0, 0, 0}, m, n, CPP(T, dA), lda, values, ldv, batch, ST); \
+} \
+int sb200_trnorm_batched_##X(int norm, int uplo, int diag, int64_t m, int64_t n, const T* const* dA, int64_t lda, \
+                             R* values, int64_t ldv, int64_t batch, sb200_stream_t stream) \
+{ \
+    if (! valid_uplo(uplo) || ! valid_diag(diag)) return SB200_EINVAL; \
+    const int mode = norm_mode(norm, 'M'); \
+    if (mode < 0) return SB200_ENOTSUP; \
+    return launch_norm<Cu<T>::type>(mode, NormCfg{uplo == 'L' ? 1 : 2, 0, 0, diag == 'U'}, m, n, CPP(T, dA), lda, values, ldv, batch, ST); \
 }
-int sb200_genorm_batched_s(int norm, int scope, int64_t m, int64_t n, const float* const* dA, int64_t lda,
-                           float* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
-{
-    const int mode = norm_mode(norm, scope);
-    if (mode < 0) return SB200_ENOTSUP;
-    return launch_norm<float>(mode, NormCfg{0, 0, 0, 0}, m, n, dA, lda, values, ldv, batch, ST);
-}
-int sb200_genorm_batched_z(int norm, int scope, int64_t m, int64_t n, const sb200_c64* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
-{
-    const int mode = norm_mode(norm, scope);
-    if (mode < 0) return SB200_ENOTSUP;
-    return launch_norm<cuDoubleComplex>(mode, NormCfg{0, 0, 0, 0}, m, n, zcpp(dA), lda, values, ldv, batch, ST);
-}
-
-// Hermitian / symmetric DIAGONAL tiles: One == Inf (device_henorm.cu:300-345)
-static int he_mode(int norm) { return norm == 'I' ? 'O' : norm_mode(norm, 'M'); }
-
-int sb200_henorm_batched_d(int norm, int uplo, int64_t n, const double* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
-{
-    if (! valid_uplo(uplo)) return SB200_EINVAL;
-    if (he_mode(norm) < 0) return SB200_ENOTSUP;
-    return launch_norm<double>(he_mode(norm), NormCfg{uplo == 'L' ? 1 : 2, 1, 1, 0}, n, n, dA, lda, values, ldv, batch, ST);
-}
-int sb200_henorm_batched_z(int norm, int uplo, int64_t n, const sb200_c64* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
-{
-    if (! valid_uplo(uplo)) return SB200_EINVAL;
-    if (he_mode(norm) < 0) return SB200_ENOTSUP;
-    return launch_norm<cuDoubleComplex>(he_mode(norm), NormCfg{uplo == 'L' ? 1 : 2, 1, 1, 0}, n, n, zcpp(dA), lda, values, ldv, batch, ST);
-}
-int sb200_synorm_batched_d(int norm, int uplo, int64_t n, const double* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
-{
-    if (! valid_uplo(uplo)) return SB200_EINVAL;
-    if (he_mode(norm) < 0) return SB200_ENOTSUP;
-    return launch_norm<double>(he_mode(norm), NormCfg{uplo == 'L' ? 1 : 2, 1, 0, 0}, n, n, dA, lda, values, ldv, batch, ST);
-}
-// full off-diagonal tile of a symmetric matrix: column sums in values[0..n), row sums in
-// values[n..n+m)  (synorm_offdiag_one_kernel, device_synorm.cu:381-431)
-int sb200_synorm_offdiag_batched_d(int norm, int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                                   double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
-{
-    if (norm != 'O' && norm != 'I') return SB200_ENOTSUP;
-    return launch_norm<double>('B', NormCfg{0, 0, 0, 0}, m, n, dA, lda, values, ldv, batch, ST);
-}
-int sb200_trnorm_batched_d(int norm, int uplo, int diag, int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                           double* values, int64_t ldv, int64_t batch, sb200_stream_t stream)
-{
-    if (! valid_uplo(uplo) || ! valid_diag(diag)) return SB200_EINVAL;
-    const int mode = norm_mode(norm, 'M');
-    if (mode < 0) return SB200_ENOTSUP;
-    return launch_norm<double>(mode, NormCfg{uplo == 'L' ? 1 : 2, 0, 0, diag == 'U'}, m, n, dA, lda, values, ldv, batch, ST);
-}
+SB200_FOR_TYPES(SB200_DEF_NORMS)
 
 } // extern "C"

@@ -46,6 +46,25 @@ __host__ __device__ inline double real_part_only(double a) { return a; }
 __host__ __device__ inline cuFloatComplex  real_part_only(cuFloatComplex a) { return make_cuFloatComplex(a.x, 0.f); }
 __host__ __device__ inline cuDoubleComplex real_part_only(cuDoubleComplex a) { return make_cuDoubleComplex(a.x, 0.0); }
 
+
+__host__ __device__ inline float  real_of(float a) { return a; }
+__host__ __device__ inline double real_of(double a) { return a; }
+__host__ __device__ inline float  real_of(cuFloatComplex a) { return a.x; }
+__host__ __device__ inline double real_of(cuDoubleComplex a) { return a.x; }
+__host__ __device__ inline float  sub(float a, float b) { return a - b; }
+__host__ __device__ inline double sub(double a, double b) { return a - b; }
+__host__ __device__ inline cuFloatComplex  sub(cuFloatComplex a, cuFloatComplex b) { return cuCsubf(a, b); }
+__host__ __device__ inline cuDoubleComplex sub(cuDoubleComplex a, cuDoubleComplex b) { return cuCsub(a, b); }
+__host__ __device__ inline float  neg(float a) { return -a; }
+__host__ __device__ inline double neg(double a) { return -a; }
+__host__ __device__ inline cuFloatComplex  neg(cuFloatComplex a) { return make_cuFloatComplex(-a.x, -a.y); }
+__host__ __device__ inline cuDoubleComplex neg(cuDoubleComplex a) { return make_cuDoubleComplex(-a.x, -a.y); }
+// a / r with r real
+__host__ __device__ inline float  div_real(float a, float r) { return a / r; }
+__host__ __device__ inline double div_real(double a, double r) { return a / r; }
+__host__ __device__ inline cuFloatComplex  div_real(cuFloatComplex a, float r) { return make_cuFloatComplex(a.x / r, a.y / r); }
+__host__ __device__ inline cuDoubleComplex div_real(cuDoubleComplex a, double r) { return make_cuDoubleComplex(a.x / r, a.y / r); }
+
 // acc += a * b
 __device__ inline void fma_acc(float& acc, float a, float b) { acc = fmaf(a, b, acc); }
 __device__ inline void fma_acc(double& acc, double a, double b) { acc = fma(a, b, acc); }

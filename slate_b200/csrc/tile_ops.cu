@@ -64,33 +64,42 @@ static int launch_foreach(int64_t m, int64_t n, int64_t batch, int mask, F f, cu
 }
 
 // ----------------------------------------------------------------------------- functors
+// A tile operand is either a device pointer array (batched entry points) or one tile pointer
+// (the reference's single-tile device::geadd / gescale / geset / tzset / transpose).
+template <typename T> struct Ptrs {
+    T* const* arr; T* one;
+    __device__ __forceinline__ T* operator[](int t) const { return arr ? arr[t] : one; }
+};
+template <typename T> static Ptrs<T> ptrs(T* const* arr) { return Ptrs<T>{arr, nullptr}; }
+template <typename T> static Ptrs<T> one(T* p) { return Ptrs<T>{nullptr, p}; }
+
 template <typename T> struct AddOp {          // B = alpha A + beta B
-    const T* const* A; T* const* B; int64_t lda, ldb; T alpha, beta;
+    Ptrs<const T> A; Ptrs<T> B; int64_t lda, ldb; T alpha, beta;
     __device__ void operator()(int t, int i, int j) const {
         T* b = B[t] + i + j * ldb;
         *b = add(mul(alpha, A[t][i + j * lda]), mul(beta, *b));
     }
 };
 template <typename T> struct ScaleOp {        // A *= numer / denom
-    T* const* A; int64_t lda; T mult;
+    Ptrs<T> A; int64_t lda; T mult;
     __device__ void operator()(int t, int i, int j) const { T* a = A[t] + i + j * lda; *a = mul(*a, mult); }
 };
-template <typename T> struct ScaleRowColOp {  // A_ij *= R_i C_j
-    T* const* A; int64_t lda; const T* const* R; const T* const* C; int use_r, use_c;
+template <typename T, typename S> struct ScaleRowColOp {  // A_ij *= R_i C_j  (S = T or real(T))
+    Ptrs<T> A; int64_t lda; const S* const* R; const S* const* C; int use_r, use_c;
     __device__ void operator()(int t, int i, int j) const {
         T* a = A[t] + i + j * lda;
         T v = *a;
-        if (use_r) v = mul(v, R[t][i]);
-        if (use_c) v = mul(v, C[t][j]);
+        if (use_r) v = mul(v, convert<T, S>(R[t][i]));
+        if (use_c) v = mul(v, convert<T, S>(C[t][j]));
         *a = v;
     }
 };
 template <typename T> struct SetOp {          // offdiag / diag fill
-    T* const* A; int64_t lda; T offdiag, diag;
+    Ptrs<T> A; int64_t lda; T offdiag, diag;
     __device__ void operator()(int t, int i, int j) const { A[t][i + j * lda] = (i == j) ? diag : offdiag; }
 };
 template <typename S, typename D> struct CopyOp {   // B = convert(A)
-    const S* const* A; D* const* B; int64_t lda, ldb;
+    Ptrs<const S> A; Ptrs<D> B; int64_t lda, ldb;
     __device__ void operator()(int t, int i, int j) const { B[t][i + j * ldb] = convert<D, S>(A[t][i + j * lda]); }
 };
 
@@ -98,7 +107,7 @@ template <typename S, typename D> struct CopyOp {   // B = convert(A)
 // Out-of-place: AT (n x m) = A^T (A m x n).  32 x 32 shared tiles (+1 pad), both sides coalesced.
 template <typename T>
 __global__ void __launch_bounds__(256)
-transpose_oop_kernel(int m, int n, const T* const* A, int64_t lda, T* const* AT, int64_t ldat, int conj, int batch)
+transpose_oop_kernel(int m, int n, Ptrs<const T> A, int64_t lda, Ptrs<T> AT, int64_t ldat, int conj, int batch)
 {
     __shared__ T tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
@@ -127,7 +136,7 @@ transpose_oop_kernel(int m, int n, const T* const* A, int64_t lda, T* const* AT,
 // In-place square: swap 32x32 block pairs (bi > bj) through shared memory; diagonal blocks alone.
 template <typename T>
 __global__ void __launch_bounds__(256)
-transpose_inplace_kernel(int n, T* const* A, int64_t lda, int conj, int batch)
+transpose_inplace_kernel(int n, Ptrs<T> A, int64_t lda, int conj, int batch)
 {
     __shared__ T t1[32][33], t2[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -164,8 +173,8 @@ transpose_inplace_kernel(int n, T* const* A, int64_t lda, int conj, int batch)
 }
 
 template <typename T>
-static int launch_transpose_oop(int conj, int64_t m, int64_t n, const T* const* A, int64_t lda,
-                                T* const* AT, int64_t ldat, int64_t batch, cudaStream_t s)
+static int launch_transpose_oop(int conj, int64_t m, int64_t n, Ptrs<const T> A, int64_t lda,
+                                Ptrs<T> AT, int64_t ldat, int64_t batch, cudaStream_t s)
 {
     if (m < 0 || n < 0 || batch < 0 || lda < m || ldat < n) return SB200_EINVAL;
     if (m == 0 || n == 0 || batch == 0) return SB200_OK;
@@ -176,7 +185,7 @@ static int launch_transpose_oop(int conj, int64_t m, int64_t n, const T* const* 
 }
 
 template <typename T>
-static int launch_transpose_inplace(int conj, int64_t n, T* const* A, int64_t lda, int64_t batch, cudaStream_t s)
+static int launch_transpose_inplace(int conj, int64_t n, Ptrs<T> A, int64_t lda, int64_t batch, cudaStream_t s)
 {
     if (n < 0 || batch < 0 || lda < n) return SB200_EINVAL;
     if (n == 0 || batch == 0) return SB200_OK;
@@ -188,144 +197,114 @@ static int launch_transpose_inplace(int conj, int64_t n, T* const* A, int64_t ld
 
 // ----------------------------------------------------------------------------- typed entry helpers
 template <typename T>
-static int geadd_t(int mask, int64_t m, int64_t n, T alpha, const T* const* A, int64_t lda, T beta,
-                   T* const* B, int64_t ldb, int64_t batch, cudaStream_t s)
+static int geadd_t(int mask, int64_t m, int64_t n, T alpha, Ptrs<const T> A, int64_t lda, T beta,
+                   Ptrs<T> B, int64_t ldb, int64_t batch, cudaStream_t s)
 {
-    if (lda < m || ldb < m) return SB200_EINVAL;
+    if (mask < 0 || lda < m || ldb < m) return SB200_EINVAL;
     return launch_foreach(m, n, batch, mask, AddOp<T>{A, B, lda, ldb, alpha, beta}, s);
 }
 template <typename T>
-static int gescale_t(int mask, int64_t m, int64_t n, T numer, T denom, T* const* A, int64_t lda, int64_t batch, cudaStream_t s)
+static int gescale_t(int mask, int64_t m, int64_t n, T numer, T denom, Ptrs<T> A, int64_t lda, int64_t batch, cudaStream_t s)
 {
-    if (lda < m) return SB200_EINVAL;
+    if (mask < 0 || lda < m) return SB200_EINVAL;
     return launch_foreach(m, n, batch, mask, ScaleOp<T>{A, lda, divide(numer, denom)}, s);
 }
 template <typename T>
-static int geset_t(int mask, int64_t m, int64_t n, T offdiag, T diag, T* const* A, int64_t lda, int64_t batch, cudaStream_t s)
+static int geset_t(int mask, int64_t m, int64_t n, T offdiag, T diag, Ptrs<T> A, int64_t lda, int64_t batch, cudaStream_t s)
 {
-    if (lda < m) return SB200_EINVAL;
+    if (mask < 0 || lda < m) return SB200_EINVAL;
     return launch_foreach(m, n, batch, mask, SetOp<T>{A, lda, offdiag, diag}, s);
 }
 template <typename S, typename D>
-static int gecopy_t(int mask, int64_t m, int64_t n, const S* const* A, int64_t lda, D* const* B, int64_t ldb, int64_t batch, cudaStream_t s)
+static int gecopy_t(int mask, int64_t m, int64_t n, Ptrs<const S> A, int64_t lda, Ptrs<D> B, int64_t ldb, int64_t batch, cudaStream_t s)
 {
-    if (lda < m || ldb < m) return SB200_EINVAL;
+    if (mask < 0 || lda < m || ldb < m) return SB200_EINVAL;
     return launch_foreach(m, n, batch, mask, CopyOp<S, D>{A, B, lda, ldb}, s);
 }
+template <typename T, typename S>
+static int gescale_row_col_t(int equed, int64_t m, int64_t n, const S* const* R, const S* const* C,
+                             Ptrs<T> A, int64_t lda, int64_t batch, cudaStream_t s)
+{
+    if (equed != 'R' && equed != 'C' && equed != 'B') return SB200_EINVAL;
+    if (lda < m) return SB200_EINVAL;
+    return launch_foreach(m, n, batch, 0, ScaleRowColOp<T, S>{A, lda, R, C, equed != 'C', equed != 'R'}, s);
+}
 
-static inline int mask_of(int uplo) { return uplo == 'L' ? 1 : (uplo == 'U' ? 2 : -1); }
-static inline cuDoubleComplex z(sb200_c64 v) { return make_cuDoubleComplex(v.re, v.im); }
+// uplo code -> mask: 'G' whole tile, 'L' lower trapezoid, 'U' upper trapezoid
+static inline int mask_of(int uplo) { return uplo == 'G' ? 0 : (uplo == 'L' ? 1 : (uplo == 'U' ? 2 : -1)); }
+static inline int tz_mask_of(int uplo) { return uplo == 'L' ? 1 : (uplo == 'U' ? 2 : -1); }
+
+// ABI scalar/pointer types -> CUDA types (layout-compatible)
+template <typename A> struct Cu { using type = A; };
+template <> struct Cu<sb200_c32> { using type = cuFloatComplex; };
+template <> struct Cu<sb200_c64> { using type = cuDoubleComplex; };
+static inline float  cv(float v) { return v; }
+static inline double cv(double v) { return v; }
+static inline cuFloatComplex  cv(sb200_c32 v) { return make_cuFloatComplex(v.re, v.im); }
+static inline cuDoubleComplex cv(sb200_c64 v) { return make_cuDoubleComplex(v.re, v.im); }
 
 } // namespace sb200
 
 using namespace sb200;
 #define ST cudaStream_t(stream)
-typedef const cuDoubleComplex* const* zcpp;
-typedef cuDoubleComplex* const* zpp;
-typedef const cuFloatComplex* const* ccpp;
-typedef cuFloatComplex* const* cpp_;
+#define CU(T) typename Cu<T>::type
+#define PA(T, p)  ptrs(reinterpret_cast<Cu<T>::type* const*>(p))
+#define PCA(T, p) ptrs(reinterpret_cast<const Cu<T>::type* const*>(p))
+#define P1(T, p)  one(reinterpret_cast<Cu<T>::type*>(p))
+#define PC1(T, p) one(reinterpret_cast<const Cu<T>::type*>(p))
 
 extern "C" {
 
-// ---- geadd
-int sb200_geadd_batched_d(int64_t m, int64_t n, double alpha, const double* const* dA, int64_t lda,
-                          double beta, double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return geadd_t<double>(0, m, n, alpha, dA, lda, beta, dB, ldb, batch, ST); }
-int sb200_geadd_batched_s(int64_t m, int64_t n, float alpha, const float* const* dA, int64_t lda,
-                          float beta, float* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return geadd_t<float>(0, m, n, alpha, dA, lda, beta, dB, ldb, batch, ST); }
-int sb200_geadd_batched_z(int64_t m, int64_t n, sb200_c64 alpha, const sb200_c64* const* dA, int64_t lda,
-                          sb200_c64 beta, sb200_c64* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return geadd_t<cuDoubleComplex>(0, m, n, z(alpha), zcpp(dA), lda, z(beta), zpp(dB), ldb, batch, ST); }
-int sb200_tzadd_batched_d(int uplo, int64_t m, int64_t n, double alpha, const double* const* dA, int64_t lda,
-                          double beta, double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ if (mask_of(uplo) < 0) return SB200_EINVAL; return geadd_t<double>(mask_of(uplo), m, n, alpha, dA, lda, beta, dB, ldb, batch, ST); }
+#define SB200_DEF_TILE_OPS(X, T, R) \
+int sb200_geadd_##X(int64_t m, int64_t n, T alpha, const T* dA, int64_t lda, T beta, T* dB, int64_t ldb, sb200_stream_t stream) \
+{ return geadd_t<Cu<T>::type>(0, m, n, cv(alpha), PC1(T, dA), lda, cv(beta), P1(T, dB), ldb, 1, ST); } \
+int sb200_geadd_batched_##X(int64_t m, int64_t n, T alpha, const T* const* dA, int64_t lda, \
+                            T beta, T* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream) \
+{ return geadd_t<Cu<T>::type>(0, m, n, cv(alpha), PCA(T, dA), lda, cv(beta), PA(T, dB), ldb, batch, ST); } \
+int sb200_tzadd_batched_##X(int uplo, int64_t m, int64_t n, T alpha, const T* const* dA, int64_t lda, \
+                            T beta, T* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream) \
+{ return geadd_t<Cu<T>::type>(tz_mask_of(uplo), m, n, cv(alpha), PCA(T, dA), lda, cv(beta), PA(T, dB), ldb, batch, ST); } \
+int sb200_gescale_##X(int64_t m, int64_t n, T numer, T denom, T* dA, int64_t lda, sb200_stream_t stream) \
+{ return gescale_t<Cu<T>::type>(0, m, n, cv(numer), cv(denom), P1(T, dA), lda, 1, ST); } \
+int sb200_gescale_batched_##X(int64_t m, int64_t n, T numer, T denom, \
+                              T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream) \
+{ return gescale_t<Cu<T>::type>(0, m, n, cv(numer), cv(denom), PA(T, dA), lda, batch, ST); } \
+int sb200_tzscale_batched_##X(int uplo, int64_t m, int64_t n, R numer, R denom, \
+                              T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream) \
+{ return gescale_t<Cu<T>::type>(tz_mask_of(uplo), m, n, from_real<Cu<T>::type>(numer), from_real<Cu<T>::type>(denom), PA(T, dA), lda, batch, ST); } \
+int sb200_gescale_row_col_batched_##X(int equed, int64_t m, int64_t n, const T* const* dR, const T* const* dC, \
+                                      T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream) \
+{ return gescale_row_col_t<Cu<T>::type, Cu<T>::type>(equed, m, n, reinterpret_cast<const Cu<T>::type* const*>(dR), \
+      reinterpret_cast<const Cu<T>::type* const*>(dC), PA(T, dA), lda, batch, ST); } \
+int sb200_gescale_row_col_real_batched_##X(int equed, int64_t m, int64_t n, const R* const* dR, const R* const* dC, \
+                                      T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream) \
+{ return gescale_row_col_t<Cu<T>::type, R>(equed, m, n, dR, dC, PA(T, dA), lda, batch, ST); } \
+int sb200_geset_##X(int uplo, int64_t m, int64_t n, T offdiag, T diag, T* dA, int64_t lda, sb200_stream_t stream) \
+{ return geset_t<Cu<T>::type>(mask_of(uplo), m, n, cv(offdiag), cv(diag), P1(T, dA), lda, 1, ST); } \
+int sb200_geset_batched_##X(int64_t m, int64_t n, T offdiag, T diag, \
+                            T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream) \
+{ return geset_t<Cu<T>::type>(0, m, n, cv(offdiag), cv(diag), PA(T, dA), lda, batch, ST); } \
+int sb200_tzset_batched_##X(int uplo, int64_t m, int64_t n, T offdiag, T diag, \
+                            T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream) \
+{ return geset_t<Cu<T>::type>(tz_mask_of(uplo), m, n, cv(offdiag), cv(diag), PA(T, dA), lda, batch, ST); } \
+int sb200_transpose_inplace_##X(int conj, int64_t n, T* dA, int64_t lda, sb200_stream_t stream) \
+{ return launch_transpose_inplace<Cu<T>::type>(conj, n, P1(T, dA), lda, 1, ST); } \
+int sb200_transpose_##X(int conj, int64_t m, int64_t n, const T* dA, int64_t lda, T* dAT, int64_t ldat, sb200_stream_t stream) \
+{ return launch_transpose_oop<Cu<T>::type>(conj, m, n, PC1(T, dA), lda, P1(T, dAT), ldat, 1, ST); } \
+int sb200_transpose_inplace_batched_##X(int conj, int64_t n, T* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream) \
+{ return launch_transpose_inplace<Cu<T>::type>(conj, n, PA(T, dA), lda, batch, ST); } \
+int sb200_transpose_batched_##X(int conj, int64_t m, int64_t n, const T* const* dA, int64_t lda, \
+                                T* const* dAT, int64_t ldat, int64_t batch, sb200_stream_t stream) \
+{ return launch_transpose_oop<Cu<T>::type>(conj, m, n, PCA(T, dA), lda, PA(T, dAT), ldat, batch, ST); }
+SB200_FOR_TYPES(SB200_DEF_TILE_OPS)
 
-// ---- gescale
-int sb200_gescale_batched_d(int64_t m, int64_t n, double numer, double denom,
-                            double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ return gescale_t<double>(0, m, n, numer, denom, dA, lda, batch, ST); }
-int sb200_gescale_batched_s(int64_t m, int64_t n, float numer, float denom,
-                            float* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ return gescale_t<float>(0, m, n, numer, denom, dA, lda, batch, ST); }
-int sb200_gescale_batched_z(int64_t m, int64_t n, sb200_c64 numer, sb200_c64 denom,
-                            sb200_c64* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ return gescale_t<cuDoubleComplex>(0, m, n, z(numer), z(denom), zpp(dA), lda, batch, ST); }
-int sb200_tzscale_batched_d(int uplo, int64_t m, int64_t n, double numer, double denom,
-                            double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ if (mask_of(uplo) < 0) return SB200_EINVAL; return gescale_t<double>(mask_of(uplo), m, n, numer, denom, dA, lda, batch, ST); }
-
-int sb200_gescale_row_col_batched_d(int equed, int64_t m, int64_t n,
-                                    const double* const* dR, const double* const* dC,
-                                    double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{
-    if (equed != 'R' && equed != 'C' && equed != 'B') return SB200_EINVAL;
-    if (lda < m) return SB200_EINVAL;
-    return launch_foreach(m, n, batch, 0,
-                          ScaleRowColOp<double>{dA, lda, dR, dC, equed != 'C', equed != 'R'}, ST);
-}
-
-// ---- geset / tzset
-int sb200_geset_batched_d(int64_t m, int64_t n, double offdiag, double diag,
-                          double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ return geset_t<double>(0, m, n, offdiag, diag, dA, lda, batch, ST); }
-int sb200_geset_batched_s(int64_t m, int64_t n, float offdiag, float diag,
-                          float* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ return geset_t<float>(0, m, n, offdiag, diag, dA, lda, batch, ST); }
-int sb200_geset_batched_z(int64_t m, int64_t n, sb200_c64 offdiag, sb200_c64 diag,
-                          sb200_c64* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ return geset_t<cuDoubleComplex>(0, m, n, z(offdiag), z(diag), zpp(dA), lda, batch, ST); }
-int sb200_tzset_batched_d(int uplo, int64_t m, int64_t n, double offdiag, double diag,
-                          double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ if (mask_of(uplo) < 0) return SB200_EINVAL; return geset_t<double>(mask_of(uplo), m, n, offdiag, diag, dA, lda, batch, ST); }
-
-// ---- gecopy / tzcopy
-int sb200_gecopy_batched_dd(int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                            double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return gecopy_t<double, double>(0, m, n, dA, lda, dB, ldb, batch, ST); }
-int sb200_gecopy_batched_ds(int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                            float* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return gecopy_t<double, float>(0, m, n, dA, lda, dB, ldb, batch, ST); }
-int sb200_gecopy_batched_sd(int64_t m, int64_t n, const float* const* dA, int64_t lda,
-                            double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return gecopy_t<float, double>(0, m, n, dA, lda, dB, ldb, batch, ST); }
-int sb200_gecopy_batched_ss(int64_t m, int64_t n, const float* const* dA, int64_t lda,
-                            float* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return gecopy_t<float, float>(0, m, n, dA, lda, dB, ldb, batch, ST); }
-int sb200_gecopy_batched_zz(int64_t m, int64_t n, const sb200_c64* const* dA, int64_t lda,
-                            sb200_c64* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return gecopy_t<cuDoubleComplex, cuDoubleComplex>(0, m, n, zcpp(dA), lda, zpp(dB), ldb, batch, ST); }
-int sb200_gecopy_batched_zc(int64_t m, int64_t n, const sb200_c64* const* dA, int64_t lda,
-                            sb200_c32* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return gecopy_t<cuDoubleComplex, cuFloatComplex>(0, m, n, zcpp(dA), lda, cpp_(dB), ldb, batch, ST); }
-int sb200_gecopy_batched_cz(int64_t m, int64_t n, const sb200_c32* const* dA, int64_t lda,
-                            sb200_c64* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ return gecopy_t<cuFloatComplex, cuDoubleComplex>(0, m, n, ccpp(dA), lda, zpp(dB), ldb, batch, ST); }
-int sb200_tzcopy_batched_dd(int uplo, int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                            double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ if (mask_of(uplo) < 0) return SB200_EINVAL; return gecopy_t<double, double>(mask_of(uplo), m, n, dA, lda, dB, ldb, batch, ST); }
-int sb200_tzcopy_batched_ds(int uplo, int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                            float* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ if (mask_of(uplo) < 0) return SB200_EINVAL; return gecopy_t<double, float>(mask_of(uplo), m, n, dA, lda, dB, ldb, batch, ST); }
-int sb200_tzcopy_batched_sd(int uplo, int64_t m, int64_t n, const float* const* dA, int64_t lda,
-                            double* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream)
-{ if (mask_of(uplo) < 0) return SB200_EINVAL; return gecopy_t<float, double>(mask_of(uplo), m, n, dA, lda, dB, ldb, batch, ST); }
-
-// ---- transposes
-int sb200_transpose_inplace_batched_d(int64_t n, double* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ return launch_transpose_inplace<double>(0, n, dA, lda, batch, ST); }
-int sb200_transpose_batched_d(int64_t m, int64_t n, const double* const* dA, int64_t lda,
-                              double* const* dAT, int64_t ldat, int64_t batch, sb200_stream_t stream)
-{ return launch_transpose_oop<double>(0, m, n, dA, lda, dAT, ldat, batch, ST); }
-int sb200_transpose_inplace_batched_z(int conj, int64_t n, sb200_c64* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ return launch_transpose_inplace<cuDoubleComplex>(conj, n, zpp(dA), lda, batch, ST); }
-int sb200_transpose_batched_z(int conj, int64_t m, int64_t n, const sb200_c64* const* dA, int64_t lda,
-                              sb200_c64* const* dAT, int64_t ldat, int64_t batch, sb200_stream_t stream)
-{ return launch_transpose_oop<cuDoubleComplex>(conj, m, n, zcpp(dA), lda, zpp(dAT), ldat, batch, ST); }
-int sb200_transpose_inplace_batched_s(int64_t n, float* const* dA, int64_t lda, int64_t batch, sb200_stream_t stream)
-{ return launch_transpose_inplace<float>(0, n, dA, lda, batch, ST); }
-int sb200_transpose_batched_s(int64_t m, int64_t n, const float* const* dA, int64_t lda,
-                              float* const* dAT, int64_t ldat, int64_t batch, sb200_stream_t stream)
-{ return launch_transpose_oop<float>(0, m, n, dA, lda, dAT, ldat, batch, ST); }
+#define SB200_DEF_COPY(XY, S, D) \
+int sb200_gecopy_batched_##XY(int64_t m, int64_t n, const S* const* dA, int64_t lda, \
+                              D* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream) \
+{ return gecopy_t<Cu<S>::type, Cu<D>::type>(0, m, n, PCA(S, dA), lda, PA(D, dB), ldb, batch, ST); } \
+int sb200_tzcopy_batched_##XY(int uplo, int64_t m, int64_t n, const S* const* dA, int64_t lda, \
+                              D* const* dB, int64_t ldb, int64_t batch, sb200_stream_t stream) \
+{ return gecopy_t<Cu<S>::type, Cu<D>::type>(tz_mask_of(uplo), m, n, PCA(S, dA), lda, PA(D, dB), ldb, batch, ST); }
+SB200_FOR_COPY_PAIRS(SB200_DEF_COPY)
 
 } // extern "C"

@@ -11,14 +11,19 @@ HEADER = os.path.join(ROOT, "include", "slate_b200.h")
 
 
 def declared_symbols():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    """Every function the header declares, after the C preprocessor has expanded the per-type
+    X-macros (SB200_FOR_TYPES)."""
+    import subprocess
+    src = subprocess.run(["gcc", "-E", "-P", "-x", "c", HEADER], capture_output=True, text=True, check=True).stdout
     return sorted(set(re.findall(r"\b(sb200_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_declares_the_hot_path_surface():
     syms = declared_symbols()
-    for must in ["sb200_gemm_batched_d", "sb200_herk_batched_d", "sb200_trsm_batched_d", "sb200_potrf_tile_d",
+    assert len(syms) > 150          # 4 scalar types x every seam-1 / seam-2 entry point
+    for must in ["sb200_gemm_batched_z", "sb200_trsm_batched_c", "sb200_potrf_tile_z", "sb200_gecopy_batched_dz",
+                 "sb200_henorm_batched_c", "sb200_transpose_inplace_s", "sb200_gemm_strided_d",
+                 "sb200_gemm_batched_d", "sb200_herk_batched_d", "sb200_trsm_batched_d", "sb200_potrf_tile_d",
                  "sb200_permute_rows_d", "sb200_geadd_batched_d", "sb200_genorm_batched_d",
                  "sb200_transpose_batched_d", "sb200_potrf_d", "sb200_getrf_d", "sb200_gemm_d"]:
         assert must in syms

@@ -69,7 +69,7 @@ def test_gemm_unaligned_pointers_and_odd_ld():
     assert np.array_equal(out[m:], C[m:])            # rows beyond m untouched
 
 
-@pytest.mark.parametrize("t", ["d", "z", "s"])
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
 @pytest.mark.parametrize("layout", ["C", "R"])
 @pytest.mark.parametrize("uplo", ["L", "U"])
 @pytest.mark.parametrize("op", ["N", "C"])
@@ -80,7 +80,7 @@ def test_herk_batched(t, layout, uplo, op, n, k):
     shpA = (n, k) if op == "N" else (k, n)
     A = rng_tiles(rng, batch, *shpA, t); C = rng_tiles(rng, batch, n, n, t)
     alpha, beta = -1.0, 1.0
-    opc = "C" if t == "z" else "T"
+    opc = "C" if t in "cz" else "T"
     full = [alpha * (opmat(a, "N" if op == "N" else opc) @ opmat(a, opc if op == "N" else "N")) + beta * c for a, c in zip(A, C)]
     mask = np.tril(np.ones((n, n), bool)) if uplo == "L" else np.triu(np.ones((n, n), bool))
     st = (lambda x: x) if layout == "C" else (lambda x: np.asfortranarray(x.T))
@@ -94,26 +94,35 @@ def test_herk_batched(t, layout, uplo, op, n, k):
     tol = 3 * np.sqrt(k) * EPS[t] * 4
     for x, r, c in zip(out, full, C):
         exp = np.where(mask, r, c)                   # other triangle untouched
-        if t == "z":
+        if t in "cz":
             d = np.arange(n); exp[d, d] = exp[d, d].real
         assert np.abs(x - exp).max() <= tol * np.abs(r).max()
 
 
-@pytest.mark.parametrize("t", ["d", "s"])
+@pytest.mark.parametrize("t", ["d", "s", "z", "c"])
 @pytest.mark.parametrize("layout", ["C", "R"])
 @pytest.mark.parametrize("side", ["L", "R"])
 @pytest.mark.parametrize("uplo", ["L", "U"])
-@pytest.mark.parametrize("op", ["N", "T"])
+@pytest.mark.parametrize("op", ["N", "T", "C"])
 @pytest.mark.parametrize("diag", ["N", "U"])
 @pytest.mark.parametrize("m,n", [(64, 48), (200, 136), (77, 53), (512, 512)])
 def test_trsm_batched(t, layout, side, uplo, op, diag, m, n):
+    if t in "ds" and op == "C":
+        pytest.skip("C == T for real types (covered by T)")
+    if (m, n) == (512, 512) and (t in "sc" or op == "T" and t == "z"):
+        pytest.skip("production tile size is checked for d (all ops) and z (N, C)")
     rng = np.random.default_rng(4)
     batch = 2
     na = m if side == "L" else n
-    T = (rng.random((na, na)) / na + np.eye(na) * (1 + rng.random(na))).astype(NP[t])
+    T = rng.random((na, na)) / na + np.eye(na) * (1 + rng.random(na))
+    if t in "cz":
+        T = T + 1j * rng.random((na, na)) / na
+    T = T.astype(NP[t])
     B = rng_tiles(rng, batch, m, n, t)
-    alpha = 0.7
-    ref = [o.trsm_tile(side, uplo, op, diag, alpha, T.astype(np.float64), b.astype(np.float64)) for b in B]
+    alpha = 0.7 - 0.2j if t in "cz" else 0.7
+    wide = np.complex128 if t in "cz" else np.float64
+    ref = [o.trsm_tile(side, uplo, op, diag, alpha, T.astype(wide), b.astype(wide)) for b in B]
+    # row-major storage of X == column-major storage of X^T
     st = (lambda x: x) if layout == "C" else (lambda x: np.asfortranarray(x.T))
     dT, dB = DevTiles([st(T)]), DevTiles([st(b) for b in B])
     f = fn(f"sb200_trsm_batched_{t}", [c_int] * 5 + [c_i64, c_i64, SC[t], c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr])
@@ -126,21 +135,75 @@ def test_trsm_batched(t, layout, side, uplo, op, diag, m, n):
         assert np.abs(x - r).max() <= 200 * EPS[t] * np.abs(r).max()
 
 
-@pytest.mark.parametrize("t", ["d", "s"])
+@pytest.mark.parametrize("t", ["d", "s", "z", "c"])
 @pytest.mark.parametrize("n", [37, 64, 200, 512])
 def test_potrf_tile(t, n):
     rng = np.random.default_rng(5)
     G = rng.random((n, n))
-    A = (G @ G.T + n * np.eye(n)).astype(NP[t])
+    if t in "cz":
+        G = G + 1j * rng.random((n, n))
+    A = (G @ G.conj().T + n * np.eye(n)).astype(NP[t])
     dA = DevTiles([A.copy()])
     info = dev_zeros(1, np.int32)
     f = fn(f"sb200_potrf_tile_{t}", [c_int, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr])
     assert f(ord("L"), n, dA.t[0].data_ptr(), n, info.data_ptr(), None, stream()) == 0
     out = dA.get()[0]
     assert int(info.cpu()[0]) == 0
-    ref = np.linalg.cholesky(A.astype(np.float64))
+    ref = np.linalg.cholesky(A.astype(np.complex128 if t in "cz" else np.float64))
     assert np.abs(np.tril(out) - ref).max() <= 50 * EPS[t] * np.abs(ref).max()
     assert np.array_equal(np.triu(out, 1), np.triu(A, 1))         # strict upper triangle untouched
+
+
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+def test_syrk_and_single_tile_rank_k(t):
+    """blas::batch::syrk / blas::syrk / blas::herk single-tile forms (device_batch_syrk.cc, device_syrk.cc,
+    device_herk.cc): complex syrk keeps a complex diagonal, herk forces it real."""
+    rng = np.random.default_rng(31)
+    n, k, batch = 150, 40, 2
+    A = rng_tiles(rng, batch, n, k, t); C = rng_tiles(rng, batch, n, n, t)
+    alpha, beta = (0.5 + 0.25j, 1.5 - 1j) if t in "cz" else (0.5, 1.5)
+    dA, dC = DevTiles(A), DevTiles(C)
+    f = fn(f"sb200_syrk_batched_{t}", [c_int] * 3 + [c_i64] * 2 + [SC[t], c_ptr, c_i64, SC[t], c_ptr, c_i64, c_i64, c_ptr])
+    assert f(ord("C"), ord("L"), ord("N"), n, k, scal(t, alpha), dA.p, n, scal(t, beta), dC.p, n, batch, stream()) == 0
+    mask = np.tril(np.ones((n, n), bool))
+    tol = 3 * np.sqrt(k) * EPS[t] * 4
+    for x, a, c in zip(dC.get(), A, C):
+        r = alpha * (a @ a.T) + beta * c
+        assert np.abs(x - np.where(mask, r, c)).max() <= tol * np.abs(r).max()
+    # single tile herk, upper, op = C (A is k x n)
+    At = rng_tiles(rng, 1, k, n, t); C1 = rng_tiles(rng, 1, n, n, t)
+    dA1, dC1 = DevTiles(At), DevTiles(C1)
+    g = fn(f"sb200_herk_{t}", [c_int] * 3 + [c_i64] * 2 + [RSC[t], c_ptr, c_i64, RSC[t], c_ptr, c_i64, c_ptr])
+    assert g(ord("C"), ord("U"), ord("C"), n, k, RSC[t](-1.0), dA1.t[0].data_ptr(), k, RSC[t](1.0), dC1.t[0].data_ptr(), n, stream()) == 0
+    r = -1.0 * (At[0].conj().T @ At[0]) + C1[0]
+    exp = np.where(mask.T, r, C1[0])
+    if t in "cz":
+        d = np.arange(n); exp[d, d] = exp[d, d].real
+    assert np.abs(dC1.get()[0] - exp).max() <= tol * np.abs(r).max()
+    # complex herk rejects op = T, complex syrk rejects op = C (blas::batch::herk_check semantics)
+    if t in "cz":
+        assert g(ord("C"), ord("U"), ord("T"), n, k, RSC[t](-1.0), dA1.t[0].data_ptr(), k, RSC[t](1.0), dC1.t[0].data_ptr(), n, stream()) == -1
+
+
+@pytest.mark.parametrize("t", ["d", "z"])
+def test_gemm_strided(t):
+    """blas::gemm(queue) single GEMM and strided batches (device_gemm.cc): base + t * stride addressing."""
+    import torch
+    rng = np.random.default_rng(32)
+    m, n, k, batch = 96, 80, 40, 3
+    dt = NP[t]
+    mk = lambda r, c: (rng.random((batch, c, r)) + (1j * rng.random((batch, c, r)) if t == "z" else 0)).astype(dt)
+    A, B, C = mk(m, k), mk(k, n), mk(m, n)          # [t] holds the column-major tile as a (cols, rows) array
+    tA, tB, tC = (torch.from_numpy(x.view(np.float64)).cuda() for x in (A, B, C))
+    alpha, beta = (2.0 - 1j, 0.5 + 0.5j) if t == "z" else (2.0, 0.5)
+    f = fn(f"sb200_gemm_strided_{t}", [c_int] * 3 + [c_i64] * 3 + [SC[t], c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, SC[t], c_ptr, c_i64, c_i64, c_i64, c_ptr])
+    assert f(ord("C"), ord("N"), ord("N"), m, n, k, scal(t, alpha), tA.data_ptr(), m, m * k, tB.data_ptr(), k, k * n,
+             scal(t, beta), tC.data_ptr(), m, m * n, batch, stream()) == 0
+    sync()
+    out = tC.cpu().numpy().view(dt).reshape(batch, n, m)
+    for i in range(batch):
+        r = alpha * (A[i].T @ B[i].T) + beta * C[i].T
+        assert np.abs(out[i].T - r).max() <= 3 * np.sqrt(k) * EPS[t] * 4 * np.abs(r).max()
 
 
 def test_potrf_tile_reports_first_bad_minor():
@@ -189,13 +252,13 @@ def test_permute_rows(layout, forward):
 
 
 # ------------------------------------------------------------------------------- tile kernels
-@pytest.mark.parametrize("t", ["d", "s", "z"])
+@pytest.mark.parametrize("t", ["d", "s", "z", "c"])
 @pytest.mark.parametrize("m,n", [(64, 48), (257, 129), (512, 512), (1, 7)])
 def test_geadd_gescale_geset(t, m, n):
     rng = np.random.default_rng(7)
     batch = 3
     A = rng_tiles(rng, batch, m, n, t); B = rng_tiles(rng, batch, m, n, t)
-    alpha, beta = (1.5 - 0.5j, 0.25 + 2j) if t == "z" else (1.5, 0.25)
+    alpha, beta = (1.5 - 0.5j, 0.25 + 2j) if t in "cz" else (1.5, 0.25)
     dA, dB = DevTiles(A), DevTiles(B)
     f = fn(f"sb200_geadd_batched_{t}", [c_i64, c_i64, SC[t], c_ptr, c_i64, SC[t], c_ptr, c_i64, c_i64, c_ptr])
     assert f(m, n, scal(t, alpha), dA.p, m, scal(t, beta), dB.p, m, batch, stream()) == 0
@@ -239,7 +302,7 @@ def test_trapezoid_kernels(uplo, m, n):
         assert np.array_equal(x, o.tzcopy(uplo, c, np.zeros((m, n), np.float32), np.float32))
 
 
-@pytest.mark.parametrize("pair", ["dd", "ds", "sd", "ss", "zz", "zc", "cz"])
+@pytest.mark.parametrize("pair", ["dd", "ds", "sd", "ss", "zz", "zc", "cz", "cc", "sc", "dz"])
 def test_gecopy_converting(pair):
     rng = np.random.default_rng(9)
     m, n, batch = 130, 70, 2
@@ -264,35 +327,71 @@ def test_gescale_row_col():
             assert np.allclose(x, o.gescale_row_col(eq, r[:, 0], c[:, 0], a), rtol=2e-16, atol=0)
 
 
-@pytest.mark.parametrize("t", ["d", "s", "z"])
+@pytest.mark.parametrize("t", ["d", "s", "z", "c"])
 @pytest.mark.parametrize("m,n", [(64, 64), (100, 36), (33, 257), (512, 512)])
 def test_transposes(t, m, n):
     rng = np.random.default_rng(11)
     batch = 2
     A = rng_tiles(rng, batch, m, n, t)
     dA = DevTiles(A); dT = DevTiles([np.zeros((n, m), NP[t], order="F") for _ in range(batch)])
-    if t == "z":
-        f = fn("sb200_transpose_batched_z", [c_int, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr])
-        assert f(1, m, n, dA.p, m, dT.p, n, batch, stream()) == 0
-        exp = [a.conj().T for a in A]
-    else:
-        f = fn(f"sb200_transpose_batched_{t}", [c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr])
-        assert f(m, n, dA.p, m, dT.p, n, batch, stream()) == 0
-        exp = [a.T for a in A]
-    for x, e in zip(dT.get(), exp):
-        assert np.array_equal(x, e)
+    conj = 1 if t in "cz" else 0
+    f = fn(f"sb200_transpose_batched_{t}", [c_int, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr])
+    assert f(conj, m, n, dA.p, m, dT.p, n, batch, stream()) == 0
+    for x, a in zip(dT.get(), A):
+        assert np.array_equal(x, a.conj().T if conj else a.T)
+    # single-tile out-of-place entry (device::transpose, device_transpose.cu): tile 0 -> tile 1 of dT
+    g = fn(f"sb200_transpose_{t}", [c_int, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr])
+    assert g(0, m, n, dA.t[1].data_ptr(), m, dT.t[0].data_ptr(), n, stream()) == 0
+    assert np.array_equal(dT.get()[0], A[1].T)
     if m == n:
-        if t == "z":
-            f = fn("sb200_transpose_inplace_batched_z", [c_int, c_i64, c_ptr, c_i64, c_i64, c_ptr])
-            assert f(0, n, dA.p, n, batch, stream()) == 0
-        else:
-            f = fn(f"sb200_transpose_inplace_batched_{t}", [c_i64, c_ptr, c_i64, c_i64, c_ptr])
-            assert f(n, dA.p, n, batch, stream()) == 0
+        f = fn(f"sb200_transpose_inplace_batched_{t}", [c_int, c_i64, c_ptr, c_i64, c_i64, c_ptr])
+        assert f(0, n, dA.p, n, batch, stream()) == 0
         for x, a in zip(dA.get(), A):
             assert np.array_equal(x, a.T)
+        g = fn(f"sb200_transpose_inplace_{t}", [c_int, c_i64, c_ptr, c_i64, c_ptr])
+        assert g(conj, n, dA.t[0].data_ptr(), n, stream()) == 0
+        assert np.array_equal(dA.get()[0], A[0].conj() if conj else A[0])
 
 
-@pytest.mark.parametrize("t", ["d", "s", "z"])
+@pytest.mark.parametrize("t", ["d", "s", "z", "c"])
+def test_single_tile_entries(t):
+    """The reference's un-batched device::geadd / gescale / geset / tzset (device_geadd.cu:121-146,
+    device_gescale.cu:79-110, device_geset.cu:98-125, device_tzset.cu:98-130)."""
+    rng = np.random.default_rng(21)
+    m, n = 130, 70
+    A = rng_tiles(rng, 1, m, n, t); B = rng_tiles(rng, 1, m, n, t)
+    dA, dB = DevTiles(A), DevTiles(B)
+    alpha, beta = (1.5 - 0.5j, 0.25 + 2j) if t in "cz" else (1.5, 0.25)
+    f = fn(f"sb200_geadd_{t}", [c_i64, c_i64, SC[t], c_ptr, c_i64, SC[t], c_ptr, c_i64, c_ptr])
+    assert f(m, n, scal(t, alpha), dA.t[0].data_ptr(), m, scal(t, beta), dB.t[0].data_ptr(), m, stream()) == 0
+    r = o.geadd(alpha, A[0], beta, B[0])
+    assert np.abs(dB.get()[0] - r).max() <= 4 * EPS[t] * np.abs(r).max()
+    f = fn(f"sb200_gescale_{t}", [c_i64, c_i64, SC[t], SC[t], c_ptr, c_i64, c_ptr])
+    assert f(m, n, scal(t, 3.0), scal(t, 2.0), dA.t[0].data_ptr(), m, stream()) == 0
+    assert np.abs(dA.get()[0] - o.gescale(3.0, 2.0, A[0])).max() <= 6 * EPS[t] * np.abs(A[0]).max()
+    f = fn(f"sb200_geset_{t}", [c_int, c_i64, c_i64, SC[t], SC[t], c_ptr, c_i64, c_ptr])
+    assert f(ord("G"), m, n, scal(t, 0.5), scal(t, 9.0), dA.t[0].data_ptr(), m, stream()) == 0
+    assert np.array_equal(dA.get()[0], o.geset(0.5, 9.0, m, n, NP[t]))
+    assert f(ord("L"), m, n, scal(t, 2.0), scal(t, 1.0), dA.t[0].data_ptr(), m, stream()) == 0
+    assert np.array_equal(dA.get()[0], o.tzset("L", 2.0, 1.0, o.geset(0.5, 9.0, m, n, NP[t])))
+
+
+@pytest.mark.parametrize("t", ["z", "c"])
+def test_gescale_row_col_real_scales_on_complex_tiles(t):
+    rng = np.random.default_rng(22)
+    m, n, batch = 96, 80, 2
+    A = rng_tiles(rng, batch, m, n, t)
+    rt = REAL[t]
+    R = [rng.random((m, 1)).astype(rt) for _ in range(batch)]; Cc = [rng.random((n, 1)).astype(rt) for _ in range(batch)]
+    f = fn(f"sb200_gescale_row_col_real_batched_{t}", [c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr])
+    dA, dR, dC = DevTiles(A), DevTiles(R), DevTiles(Cc)
+    assert f(ord("B"), m, n, dR.p, dC.p, dA.p, m, batch, stream()) == 0
+    for x, a, r, c in zip(dA.get(), A, R, Cc):
+        ref = o.gescale_row_col("B", r[:, 0], c[:, 0], a)
+        assert np.abs(x - ref).max() <= 4 * EPS[t] * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("t", ["d", "s", "z", "c"])
 @pytest.mark.parametrize("m,n", [(64, 48), (200, 136), (512, 512)])
 def test_genorm(t, m, n):
     rng = np.random.default_rng(12)
@@ -309,7 +408,7 @@ def test_genorm(t, m, n):
         sync()
         v = vals.cpu().numpy().reshape(batch, ldv)
         for k, a in enumerate(A):
-            r = o.genorm(norm, a.astype(np.complex128 if t == "z" else np.float64))
+            r = o.genorm(norm, a.astype(np.complex128 if t in "cz" else np.float64))
             if norm == "F":
                 assert abs(v[k, 0] * np.sqrt(v[k, 1]) - r[0] * np.sqrt(r[1])) <= tol * r[0] * np.sqrt(r[1])
             elif norm == "M":
