@@ -223,7 +223,7 @@ int sb200_transpose_inplace_batched_##X(int conj, int64_t n, T* const* dA, int64
 int sb200_transpose_batched_##X(int conj, int64_t m, int64_t n, const T* const* dA, int64_t lda, \
                                 T* const* dAT, int64_t ldat, int64_t batch, sb200_stream_t stream); \
 /* per-tile norms               device::genorm / henorm / synorm / synormOffdiag / trnorm (src/cuda/device_*norm.cu) \
- * norm 'M' max, 'O' one, 'I' inf, 'F' frobenius; scope 'M' matrix (per-tile partial results), \
+ * norm 'M' max, 'O' (or '1', lapack::Norm::One's own character) one, 'I' inf, 'F' frobenius; scope 'M' matrix (per-tile partial results), \
  * 'C' columns (norm 'M' only: per-column max, used by colNorms). \
  * values layout as the reference (device_genorm.cu:373-445): ldv >= 1 (max), n (one), m (inf), 2 (fro: scale, sumsq); \
  * tile t writes values[t*ldv ...].  NaN-propagating max (device_util.cuh:22-25). */ \

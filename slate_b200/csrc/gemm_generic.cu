@@ -9,6 +9,7 @@
 // DESIGN.md.)
 #include "gemm_dmma.cuh"
 #include "scalar_ops.cuh"
+#include <cstdlib>
 
 namespace sb200 {
 
@@ -119,6 +120,12 @@ int launch_gemm_d(int opA, int opB, GemmParamsD p, cudaStream_t stream);
 template <> int launch_gemm<double>(int opA, int opB, GemmParamsT<double> p, cudaStream_t s) { return launch_gemm_d(opA, opB, p, s); }
 template <> int launch_gemm<float>(int opA, int opB, GemmParamsT<float> p, cudaStream_t s) { return launch_generic(opA, opB, p, s); }
 template <> int launch_gemm<cuFloatComplex>(int opA, int opB, GemmParamsT<cuFloatComplex> p, cudaStream_t s) { return launch_generic(opA, opB, p, s); }
-template <> int launch_gemm<cuDoubleComplex>(int opA, int opB, GemmParamsT<cuDoubleComplex> p, cudaStream_t s) { return launch_generic(opA, opB, p, s); }
+int launch_gemm_z(int opA, int opB, GemmParamsT<cuDoubleComplex> p, cudaStream_t stream);     // gemm_zdmma.cu
+template <> int launch_gemm<cuDoubleComplex>(int opA, int opB, GemmParamsT<cuDoubleComplex> p, cudaStream_t s)
+{
+    // complex128 runs on the FP64 tensor cores; SB200_ZGEMM_SIMT=1 selects the SIMT kernel (A/B debugging only)
+    static const bool simt = [] { const char* e = getenv("SB200_ZGEMM_SIMT"); return e && atoi(e) != 0; }();
+    return simt ? launch_generic(opA, opB, p, s) : launch_gemm_z(opA, opB, p, s);
+}
 
 } // namespace sb200

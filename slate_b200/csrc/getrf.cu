@@ -19,27 +19,21 @@
 //   * Row interchanges of a whole panel are applied to a block-column range in ONE launch.
 //   * Column-major tiles throughout (the reference converts to row-major for its swap BLAS
 //     calls, src/getrf.cc:51-55); the fused swap kernel takes either layout.
-#include "runtime.hh"
+#include "getrf_internal.hh"
 #include "gemm_dmma.cuh"
 #include <cooperative_groups.h>
 #include <cfloat>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
 namespace sb200 {
 
-int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, double alpha,
-                    const double* T, int ldt, double* const* dB, int64_t offB, int ldb, int batch,
-                    double* W, cudaStream_t stream);
-
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return int(e_); } while (0)
 #define SB_TRY(x) do { int s_ = (x); if (s_ != SB200_OK) return s_; } while (0)
 
-constexpr int PW = 32;            // panel base-block width (the tester's ib 32)
-constexpr int PROWS_MAX = 768;    // rows of the block one CTA keeps in shared memory
-constexpr int PTHREADS = 256;
 
 // ------------------------------------------------------------------------------------------
 // Fused row interchanges: pivot jj in [j0, j1) swaps stack row jj with stack row
@@ -94,6 +88,7 @@ struct BaseArgs {
     int64_t* piv_tile; int64_t* piv_off;
     double* gval; int* grow; double* gcand; double* gdiag;     // [2][G], [2][G], [2][G][PW], [2][PW]
     int* info; int info_base;
+    int* rowmap;       // optional: rowmap[x] = panel row whose ORIGINAL content now sits at position x
 };
 
 __global__ void __launch_bounds__(PTHREADS)
@@ -196,6 +191,7 @@ getrf_base_kernel(const BaseArgs a)
         if (b == 0 && tid == 0) {
             a.piv_tile[d] = p / nb;
             a.piv_off[d] = p % nb;
+            if (a.rowmap && p != d) { const int t = a.rowmap[d]; a.rowmap[d] = a.rowmap[p]; a.rowmap[p] = t; }
         }
         __syncthreads();
         const double pv = s_prow[j];
@@ -225,42 +221,35 @@ getrf_base_kernel(const BaseArgs a)
         }
 }
 
-struct PanelScratch {
-    double* gval = nullptr; int* grow = nullptr; double* gcand = nullptr; double* gdiag = nullptr;
-    double* W = nullptr;            // trsm workspace of the panel stream
-    int max_ctas = 0;
-    void* raw = nullptr;
-    int init()
-    {
-        int dev = 0, sms = 0;
-        CUDA_TRY(cudaGetDevice(&dev));
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        max_ctas = sms;
-        const size_t G = size_t(sms);
-        const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8;
-        CUDA_TRY(cudaMalloc(&raw, bytes));
-        char* p = static_cast<char*>(raw);
-        gval = reinterpret_cast<double*>(p); p += 2 * G * 8;
-        grow = reinterpret_cast<int*>(p);    p += 2 * G * 8;
-        gcand = reinterpret_cast<double*>(p); p += 2 * G * PW * 8;
-        gdiag = reinterpret_cast<double*>(p); p += 2 * PW * 8;
-        W = reinterpret_cast<double*>(p);
-        static thread_local bool attr_done[64] = {};
-        if (! attr_done[dev & 63]) {
-            CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          int(PW * (PROWS_MAX | 1) * sizeof(double))));
-            attr_done[dev & 63] = true;
-        }
-        return SB200_OK;
+int PanelScratch::init()
+{
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    max_ctas = sms;
+    const size_t G = size_t(sms);
+    const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8;
+    CUDA_TRY(cudaMalloc(&raw, bytes));
+    char* p = static_cast<char*>(raw);
+    gval = reinterpret_cast<double*>(p); p += 2 * G * 8;
+    grow = reinterpret_cast<int*>(p);    p += 2 * G * 8;
+    gcand = reinterpret_cast<double*>(p); p += 2 * G * PW * 8;
+    gdiag = reinterpret_cast<double*>(p); p += 2 * PW * 8;
+    W = reinterpret_cast<double*>(p);
+    static thread_local bool attr_done[64] = {};
+    if (! attr_done[dev & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(PW * (PROWS_MAX | 1) * sizeof(double))));
+        attr_done[dev & 63] = true;
     }
-    ~PanelScratch() { if (raw) cudaFree(raw); }
-};
+    return SB200_OK;
+}
 
 // Factor the panel given as a stack of `ntile` tiles (device pointer array `stack`, nb x nb, ld =
 // nb; last tile has m_p - (ntile-1)*nb rows), kw columns, diag_len = min(m_p, kw) pivots.
-static int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
-                         int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
-                         PanelScratch& ps, cudaStream_t s)
+int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
+                  int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
+                  PanelScratch& ps, cudaStream_t s, int* rowmap)
 {
     const int diag_len = std::min(m_p, kw);
     for (int c0 = 0; c0 < diag_len; c0 += PW) {
@@ -271,7 +260,7 @@ static int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb,
         if (rows_per > PROWS_MAX) return SB200_ENOTSUP;       // panel taller than 148 * 768 rows
         const int G = int(ceil_div(active, rows_per));
         BaseArgs a{stack, nb, m_p, c0, w, rows_per, piv_tile, piv_off,
-                   ps.gval, ps.grow, ps.gcand, ps.gdiag, dinfo, info_base};
+                   ps.gval, ps.grow, ps.gcand, ps.gdiag, dinfo, info_base, rowmap};
         void* args[] = {&a};
         const size_t smem = size_t(w) * (rows_per | 1) * sizeof(double);
         cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel),
@@ -334,7 +323,11 @@ int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
 {
     Grid& g = *A.g;
     if (A.kind != 'G' || A.layout != 'C') return SB200_EINVAL;
-    if (g.size() > 1) return SB200_ENOTSUP;
+    // SB200_GETRF_DIST=1 runs the p x q algorithm on a single rank too (test hook: same code path
+    // as the multi-GPU runs, minus the NCCL calls)
+    const char* fd = getenv("SB200_GETRF_DIST");
+    const bool force_dist = fd && atoi(fd) != 0;
+    if (g.size() > 1 || force_dist) return getrf_driver_dist(A, pivots_out, info_out);
     CUDA_TRY(cudaDeviceSynchronize());
     const int64_t mt = A.mt, nt = A.nt, nb = A.nb;
     const int ld = int(nb);

@@ -1,0 +1,34 @@
+// getrf_internal.hh -- pieces of the LU path shared by getrf.cu (single rank) and getrf_dist.cu (p x q grid)
+#pragma once
+#include "runtime.hh"
+
+namespace sb200 {
+
+constexpr int PW = 32;            // panel base-block width (the tester's ib 32)
+constexpr int PROWS_MAX = 768;    // rows of the block one CTA keeps in shared memory
+constexpr int PTHREADS = 256;
+
+// scratch of the cooperative panel kernel (per driver call)
+struct PanelScratch {
+    double* gval = nullptr; int* grow = nullptr; double* gcand = nullptr; double* gdiag = nullptr;
+    double* W = nullptr;            // trsm workspace of the panel stream
+    int max_ctas = 0;
+    void* raw = nullptr;
+    int init();
+    ~PanelScratch() { if (raw) cudaFree(raw); }
+};
+
+// Factor the panel given as a stack of `ntile` tiles (device pointer array `stack`, nb x nb, ld = nb;
+// last tile has m_p - (ntile-1)*nb rows), kw columns.  rowmap (optional, m_p ints, pre-set to the
+// identity): on return rowmap[x] = panel row whose ORIGINAL content sits at position x.
+int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
+                  int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
+                  PanelScratch& ps, cudaStream_t s, int* rowmap = nullptr);
+
+int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, double alpha,
+                    const double* T, int ldt, double* const* dB, int64_t offB, int ldb, int batch,
+                    double* W, cudaStream_t stream);
+
+int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out);
+
+} // namespace sb200

@@ -195,6 +195,7 @@ static int launch_norm(int mode, NormCfg cfg, int64_t m, int64_t n, const T* con
 
 static int norm_mode(int norm, int scope)
 {
+    if (norm == '1') norm = 'O';        // lapack::Norm::One is the character '1' (blaspp to_char); 'O' is accepted too
     if (scope == 'C') return norm == 'M' ? 'C' : -1;
     if (scope != 'M') return -1;
     return (norm == 'M' || norm == 'O' || norm == 'I' || norm == 'F') ? norm : -1;
@@ -202,6 +203,7 @@ static int norm_mode(int norm, int scope)
 
 // Hermitian / symmetric DIAGONAL tiles: One == Inf (device_henorm.cu:300-345)
 static int he_mode(int norm) { return norm == 'I' ? 'O' : norm_mode(norm, 'M'); }
+static bool is_one_or_inf(int norm) { return norm == 'O' || norm == '1' || norm == 'I'; }
 
 template <typename A> struct Cu { using type = A; };
 template <> struct Cu<sb200_c32> { using type = cuFloatComplex; };
@@ -242,7 +244,7 @@ int sb200_synorm_batched_##X(int norm, int uplo, int64_t n, const T* const* dA, 
 int sb200_synorm_offdiag_batched_##X(int norm, int64_t m, int64_t n, const T* const* dA, int64_t lda, \
                                      R* values, int64_t ldv, int64_t batch, sb200_stream_t stream) \
 { \
-    if (norm != 'O' && norm != 'I') return SB200_ENOTSUP; \
+    if (! is_one_or_inf(norm)) return SB200_ENOTSUP; \
     return launch_norm<Cu<T>::type>('B', NormCfg{0, 0, 0, 0}, m, n, CPP(T, dA), lda, values, ldv, batch, ST); \
 } \
 int sb200_trnorm_batched_##X(int norm, int uplo, int diag, int64_t m, int64_t n, const T* const* dA, int64_t lda, \

@@ -488,7 +488,8 @@ int sb200_grid_create(int p, int q, int rank, const void* nccl_unique_id, sb200_
         memcpy(&id, nccl_unique_id, sizeof(id));
         if (ncclCommInitRank(&g.world, p * q, id, rank) != ncclSuccess) { delete h; return SB200_ENCCL; }
         if (ncclCommSplit(g.world, g.prow, g.pcol, &g.row_comm, nullptr) != ncclSuccess
-            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm, nullptr) != ncclSuccess) {
+            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm, nullptr) != ncclSuccess
+            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm2, nullptr) != ncclSuccess) {
             delete h; return SB200_ENCCL;
         }
     }
@@ -501,6 +502,7 @@ int sb200_grid_destroy(sb200_grid_t h)
     if (! h) return SB200_OK;
     if (h->g.row_comm) ncclCommDestroy(h->g.row_comm);
     if (h->g.col_comm) ncclCommDestroy(h->g.col_comm);
+    if (h->g.col_comm2) ncclCommDestroy(h->g.col_comm2);
     if (h->g.world) ncclCommDestroy(h->g.world);
     delete h;
     return SB200_OK;

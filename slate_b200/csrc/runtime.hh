@@ -29,6 +29,7 @@ struct Grid {
     ncclComm_t world = nullptr;      // null when p*q == 1
     ncclComm_t row_comm = nullptr;   // ranks with the same prow (size q), rank order = pcol
     ncclComm_t col_comm = nullptr;   // ranks with the same pcol (size p), rank order = prow
+    ncclComm_t col_comm2 = nullptr;  // second communicator over the same ranks: collectives of the trailing stream
     int size() const { return p * q; }
     int rank_of(int64_t i, int64_t j) const { return int(i % p) + int(j % q) * p; }
 };

@@ -158,3 +158,34 @@ def test_full_size_potrf_properties(sl):
     res = np.abs(ax - llx).sum() / (n * a_norm1 * np.abs(x).sum())
     assert res <= 50 * EPS / 2
     assert A.last_driver_ms > 0
+
+
+@pytest.mark.parametrize("n,nb", [(384, 128), (300, 128), (1024, 256), (2048, 512)])
+def test_getrf_grid_algorithm_on_one_rank(sl, n, nb, monkeypatch):
+    """The p x q LU driver (getrf_dist.cu: panel workspace, row-map permutation instead of sequential
+    swaps, U workspace) forced onto a 1 x 1 grid: must reproduce the oracle's pivots and factors."""
+    monkeypatch.setenv("SB200_GETRF_DIST", "1")
+    A = sl.Matrix(n, n, nb).generate("rand", 42)
+    piv, info = sl.getrf(A)
+    assert info == 0
+    LU = A.to_host()
+    A0 = o.generate("rand", n, n, 42)
+    LUo, pivo, _ = o.getrf(A0, nb, 32)
+    assert piv == pivo
+    assert np.abs(LU - LUo).max() <= 1e-11 * np.abs(LUo).max()
+
+
+def test_getrf_grid_algorithm_rectangular_and_singular(sl, monkeypatch):
+    monkeypatch.setenv("SB200_GETRF_DIST", "1")
+    for (m, n, nb) in [(700, 300, 128), (300, 700, 128)]:
+        A = sl.Matrix(m, n, nb).generate("rand", 7)
+        piv, info = sl.getrf(A)
+        A0 = o.generate("rand", m, n, 7)
+        LUo, pivo, info_o = o.getrf(A0, nb, 32)
+        assert info == info_o == 0 and piv == pivo
+        assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
+    n, nb = 256, 64
+    A0 = o.generate("rand", n, n, 3); A0[:, 100] = 0.0
+    A = sl.Matrix(n, n, nb); A.from_host(np.asfortranarray(A0))
+    _, info = sl.getrf(A)
+    assert info == o.getrf(A0, nb, 32)[2] == 101
