@@ -222,11 +222,12 @@ def main():
     sampler = ClockSampler(local_rank); sampler.start()
     launches0 = lib.sb200_launch_count()
     barrier(); w0 = time.perf_counter()
-    step_ms, trail_ms, trail_flops, trail_launches = [], 0.0, 0.0, 0.0
+    step_ms, trail_ms, trail_flops, trail_launches, panel_ms = [], 0.0, 0.0, 0.0, 0.0
     for _ in range(args.steps):
         restore(); run()
         check(lib.sb200_last_driver_stats(out._h, stats))
         step_ms.append(stats[0]); trail_ms += stats[1]; trail_flops += stats[2]; trail_launches += stats[3]
+        panel_ms += out.last_panel_ms
     barrier(); w1 = time.perf_counter()
     launches = lib.sb200_launch_count() - launches0
     clocks = sampler.stop()
@@ -261,36 +262,39 @@ def main():
                 "peak_source": "FP64 DMMA.8x8x4 probe measured live in this run (sb200_fp64_peak_probe); "
                                "MEASURED_PEAKS.json carries no FP64 figure",
                 "launches_timed": int(trail_launches),
+                "trailing_ms_per_step": trail_ms / args.steps, "panel_stream_ms_per_step": panel_ms / args.steps,
                 "whole_step_frac_of_peak": value / (world * peak) if peak else None}
 
-    # ---- e2e: public API with HOST buffers (pinned), H2D + factor + D2H inside the timed region
+    # ---- e2e: public API with HOST buffers (pinned), H2D + driver + D2H inside the timed region.
+    #      Every rank moves ITS tiles (packed local tile storage, as Matrix::insertLocalTiles hands
+    #      SLATE caller-owned memory); wall clock between barriers, max over ranks.
     e2e = None
     if not args.no_e2e:
-        tiles = out.local_tiles
-        host = torch.empty((n, n), dtype=torch.float64).pin_memory() if world == 1 else None
-        if world == 1:
-            A0.to_host(host)          # setup (untimed): host copy of the seeded input
-            res = torch.empty((n, n), dtype=torch.float64).pin_memory()
-            e2e_ms = []
-            for it in range(2 + args.steps):
-                barrier(); t0 = time.perf_counter()
-                A.from_host(host, sync=False)
-                if routine == "gemm":
-                    run()
-                else:
-                    run()
-                A.to_host(res)
-                barrier(); t1 = time.perf_counter()
-                if it >= 2:
-                    e2e_ms.append((t1 - t0) * 1e3)
-            em = sum(e2e_ms) / len(e2e_ms)
-            nbytes = tiles * nb * nb * 8
-            e2e = {"value": fl / (em * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": em,
-                   "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes),
-                   "note": "pinned host column-major matrix -> Matrix.from_host -> driver -> Matrix.to_host"}
+        nelem = out.local_tiles * nb * nb
+        host = torch.empty(nelem, dtype=torch.float64).pin_memory()
+        res = torch.empty(nelem, dtype=torch.float64).pin_memory()
+        A0.to_host_local(host)            # setup (untimed): host copy of the seeded input
+        e2e_ms = []
+        for it in range(1 + args.steps):
+            barrier(); t0 = time.perf_counter()
+            A.from_host_local(host, sync=False)
+            run()
+            A.to_host_local(res)
+            barrier(); t1 = time.perf_counter()
+            if it >= 1:
+                e2e_ms.append((t1 - t0) * 1e3)
+        te = torch.tensor([sum(e2e_ms) / len(e2e_ms), float(nelem * 8)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = te.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = te.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            em, nbytes = float(tmax[0]), float(tsum[1])
         else:
-            e2e = {"value": None, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                   "note": "e2e measured at N=1 only in this round"}
+            em, nbytes = float(te[0]), float(te[1])
+        e2e = {"value": fl / (em * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": em,
+               "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes),
+               "note": "pinned host tiles -> Matrix.from_host_local -> driver -> Matrix.to_host_local on every rank; "
+                       "bytes summed over ranks, time = max over ranks"}
+        del host, res
 
     # ---- CPU baseline: reference HostTask on this box's cores, bounded sample (rank 0, N = 1)
     cpu = None

@@ -107,6 +107,28 @@ int sb200_gemm_batched_off_d(int layout, int opA, int opB, int64_t m, int64_t n,
                              int64_t batch, sb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Mixed-precision trailing update on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+ * TMEM): FP32 emulated by three TF32 MMAs per product (hi*hi + hi*lo + lo*hi).  This is the
+ * contraction of the LOW-PRECISION factorisation inside gesv_mixed (src/gesv_mixed.cc:106-300,
+ * where the reference calls internal::gemm<Devices, float> -> cublasSgemmBatched).
+ *
+ * Operands are PACKED once per panel into the tensor core's canonical shared-memory layout and
+ * then streamed by the GEMM with 1-D TMA bulk copies:
+ *   side 'A': the m x k operand op(X) (op 'N': X is m x k; 'T': X is k x m), units of 128 rows;
+ *   side 'B': the k x n operand op(X) packed as its n x k transpose, units of 256 rows.
+ * sb200_tf32x3_packed_bytes(side, rows, k) = bytes of one packed operand (rows = m or n).
+ *   C_t = alpha * A_t * B_t + beta * C_t,  C_t column-major m x n (ldc), FP32.
+ * ------------------------------------------------------------------------- */
+size_t sb200_tf32x3_packed_bytes(int side, int64_t rows, int64_t k);
+int sb200_tf32x3_pack_batched_s(int side, int op, int64_t rows, int64_t k,
+                                const float* const* dX, int64_t ldx, void* const* dPacked,
+                                int64_t batch, sb200_stream_t stream);
+int sb200_gemm_tf32x3_packed_s(int64_t m, int64_t n, int64_t k, float alpha,
+                               const void* const* dApacked, const void* const* dBpacked,
+                               float beta, float* const* dC, int64_t ldc,
+                               int64_t batch, sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Batched HERK / SYRK on the stored triangle:
  *   C_t = alpha * op(A_t) * op(A_t)^H + beta * C_t   (herk; alpha, beta real; imag(diag) := 0)
  *   C_t = alpha * op(A_t) * op(A_t)^T + beta * C_t   (syrk; alpha, beta of the scalar type)
@@ -288,6 +310,11 @@ int sb200_matrix_generate_d(sb200_matrix_t A, int kind_code, int64_t seed, sb200
  * (only locally owned tiles are touched); pinned or pageable. */
 int sb200_matrix_from_host_d(sb200_matrix_t A, const double* hA, int64_t lda, sb200_stream_t stream);
 int sb200_matrix_to_host_d(sb200_matrix_t A, double* hA, int64_t lda, sb200_stream_t stream);
+/* the same for the packed LOCAL tiles only: `htiles` holds sb200_matrix_local_tiles(A) tiles of
+ * nb*nb elements (ld = nb) in the matrix's pool order -- local block column, then local block row --
+ * i.e. the caller-owned tile storage of Matrix::insertLocalTiles (include/slate/Matrix.hh:631-662). */
+int sb200_matrix_from_host_local_d(sb200_matrix_t A, const double* htiles, sb200_stream_t stream);
+int sb200_matrix_to_host_local_d(sb200_matrix_t A, double* htiles, sb200_stream_t stream);
 int sb200_matrix_copy_d(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream);
 int64_t sb200_matrix_local_tiles(sb200_matrix_t A);
 
@@ -309,6 +336,9 @@ int sb200_potrf_d(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
 int sb200_getrf_d(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
 /* device time of the last driver call on this matrix, milliseconds (CUDA events) */
 double sb200_last_driver_ms(sb200_matrix_t A);
+/* summed device time of the panel-stream critical work (diagonal factor / LU panel + solve +
+ * broadcast) of the last driver call, milliseconds: the part the lookahead has to hide */
+double sb200_last_driver_panel_ms(sb200_matrix_t A);
 /* out4 = { driver ms, summed ms of the trailing-update GEMM launches (events on their stream),
  *          algorithmic flops of those launches, number of those launches } */
 int sb200_last_driver_stats(sb200_matrix_t A, double* out4);

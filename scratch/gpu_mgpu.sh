@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
 # Multi-GPU parity + bench lines at N ranks.  usage: gpurun --gpus N --timeout 900 -- 'bash scratch/gpu_mgpu.sh N [check] [bench]'
-set -uo pipefail
+set -o pipefail
+MGPU_SHAPES="${MGPU_SHAPES:-}"
 N="${1:-2}"; shift || true
 WHAT="${*:-check bench}"
 OUT=gpurun_out
@@ -9,7 +10,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu_n$N.csv 2>&1
 nvidia-smi topo -m > $OUT/topo_n$N.txt 2>&1
 if [[ "$WHAT" == *check* ]]; then
-    timeout 420 $TR --master-port 29511 scratch/mgpu_check.py > $OUT/mgpu_check_n$N.log 2>&1
+    timeout 420 $TR --master-port 29511 scratch/mgpu_check.py $MGPU_SHAPES > $OUT/mgpu_check_n$N.log 2>&1
     echo "mgpu_check exit $?" >> $OUT/mgpu_check_n$N.log
     grep -E "grid|MGPU|exit|Error|error" $OUT/mgpu_check_n$N.log | tail -30
 fi

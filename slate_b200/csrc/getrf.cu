@@ -249,8 +249,11 @@ int PanelScratch::init()
 // nb; last tile has m_p - (ntile-1)*nb rows), kw columns, diag_len = min(m_p, kw) pivots.
 int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
                   int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
-                  PanelScratch& ps, cudaStream_t s, int* rowmap)
+                  PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph)
 {
+    PhaseTimer off_timer;
+    off_timer.on = false;
+    PhaseTimer& pt = ph ? *ph : off_timer;
     const int diag_len = std::min(m_p, kw);
     for (int c0 = 0; c0 < diag_len; c0 += PW) {
         const int w = std::min(PW, diag_len - c0);
@@ -263,18 +266,25 @@ int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_
                    ps.gval, ps.grow, ps.gcand, ps.gdiag, dinfo, info_base, rowmap};
         void* args[] = {&a};
         const size_t smem = size_t(w) * (rows_per | 1) * sizeof(double);
+        pt.begin("pnl_base", s);
         cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel),
                                                     dim3(G), dim3(PTHREADS), args, smem, s);
         if (e != cudaSuccess) return int(e);
         SB_TRY(launch_status());
+        pt.end(s);
         // interchanges of this block applied to the rest of the panel (left and right of the block)
+        pt.begin("pnl_laswp", s);
         SB_TRY(launch_laswp(stack, 0, nb, nb, nb, 1, piv_tile, piv_off, c0, c0 + w, 1, 0, c0, s));
         SB_TRY(launch_laswp(stack, 0, nb, nb, nb, 1, piv_tile, piv_off, c0, c0 + w, 1, c0 + w, kw, s));
+        pt.end(s);
         const int rest = kw - c0 - w;
         if (rest <= 0) continue;
         // U12 = L11^{-1} A12  (top tile, rows c0..c0+w)
+        pt.begin("pnl_trsm", s);
         SB_TRY(trsm_colmajor_d(true, true, 'N', true, w, rest, 1.0, tile0 + c0 + int64_t(c0) * nb, nb,
                                stack, c0 + int64_t(c0 + w) * nb, nb, 1, ps.W, s));
+        pt.end(s);
+        pt.begin("pnl_gemm", s);
         // A22 -= L21 U12
         const double* U12 = tile0 + c0 + int64_t(c0 + w) * nb;
         const int top_rows = std::min(nb, m_p) - (c0 + w);
@@ -303,6 +313,7 @@ int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_
             p.C = stack + (ntile - 1); p.offC = int64_t(c0 + w) * nb; p.ldc = nb;
             SB_TRY(launch_gemm_d('N', 'N', p, s));
         }
+        pt.end(s);
     }
     return SB200_OK;
 }
@@ -385,13 +396,21 @@ int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
     CUDA_TRY(cudaStreamCreateWithPriority(&T, cudaStreamNonBlocking, lo));
     std::vector<cudaEvent_t> ev(size_t(2 * kt));
     for (auto& e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    std::vector<cudaEvent_t> tev;
+    std::vector<cudaEvent_t> tev, pev;
+    auto ptime = [&](cudaStream_t st) -> int {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        pev.push_back(e);
+        CUDA_TRY(cudaEventRecord(e, st));
+        return SB200_OK;
+    };
     cudaEvent_t t0, t1;
     CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
     auto P_done = [&](int64_t k) { return ev[size_t(k)]; };
     auto T_done = [&](int64_t k) { return ev[size_t(kt + k)]; };
     int status = SB200_OK;
     double trail_flops = 0; int64_t trail_launches = 0;
+    PhaseTimer ph;
 
     auto run_batches = [&](const std::vector<GBatch>& bs, cudaStream_t s) -> int {
         for (const auto& b : bs) {
@@ -435,7 +454,10 @@ int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
             int64_t* po = dpiv_off + k * nb;
             double* const* stack_k = dtbl + k + k * mt;
             // ---- panel k (column k already carries every earlier update: lookahead below)
-            SB_TRY(getrf_panel_d(stack_k, A.tile(k, k), int(mt - k), int(nb), m_p, kw, pt, po, dinfo, int(k * nb), ps, P));
+            SB_TRY(ptime(P));
+            SB_TRY(getrf_panel_d(stack_k, A.tile(k, k), int(mt - k), int(nb), m_p, kw, pt, po, dinfo, int(k * nb), ps, P,
+                                 nullptr, &ph));
+            SB_TRY(ptime(P));
             CUDA_TRY(cudaEventRecord(P_done(k), P));
             // ---- trailing update of columns >= k+2 and interchanges to the left, normal priority
             CUDA_TRY(cudaStreamWaitEvent(T, P_done(k), 0));
@@ -458,10 +480,14 @@ int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
             // ---- lookahead: bring column k+1 up to date on the panel stream
             if (k + 1 < nt) {
                 if (k >= 1) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 1), 0));
+                ph.begin("la_swap_trsm", P);
                 SB_TRY(launch_laswp(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1,
                                     (k + 1) * nb, std::min<int64_t>((k + 2) * nb, A.n), P));
                 SB_TRY(row_trsm(k, k + 1, k + 2, ps.W, P));
+                ph.end(P);
+                ph.begin("la_gemm", P);
                 SB_TRY(run_batches(steps[k].la, P));
+                ph.end(P);
             }
         }
         CUDA_TRY(cudaStreamWaitEvent(P, T_done(kt - 1), 0));
@@ -471,6 +497,7 @@ int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
         return SB200_OK;
     };
     status = body();
+    ph.report("getrf", g.rank);
     if (status == SB200_OK) {
         float ms = 0;
         cudaEventElapsedTime(&ms, t0, t1);
@@ -478,6 +505,9 @@ int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
         double tms = 0;
         for (size_t i = 0; i + 1 < tev.size(); i += 2) { float x = 0; if (cudaEventElapsedTime(&x, tev[i], tev[i + 1]) == cudaSuccess) tms += x; }
         A.last_trail_ms = tms; A.last_trail_flops = trail_flops; A.last_trail_launches = trail_launches;
+        double pms = 0;
+        for (size_t i = 0; i + 1 < pev.size(); i += 2) { float x = 0; if (cudaEventElapsedTime(&x, pev[i], pev[i + 1]) == cudaSuccess) pms += x; }
+        A.last_panel_ms = pms;
         int hinfo = 0;
         cudaMemcpy(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost);
         if (info_out) *info_out = hinfo;
@@ -497,6 +527,7 @@ int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
     }
     for (auto e : ev) cudaEventDestroy(e);
     for (auto e : tev) cudaEventDestroy(e);
+    for (auto e : pev) cudaEventDestroy(e);
     cudaEventDestroy(t0); cudaEventDestroy(t1);
     if (P) cudaStreamDestroy(P);
     if (T) cudaStreamDestroy(T);

@@ -244,13 +244,21 @@ int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out)
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CUDA_TRY(cudaStreamCreateWithPriority(&P, cudaStreamNonBlocking, hi));
     CUDA_TRY(cudaStreamCreateWithPriority(&T, cudaStreamNonBlocking, lo));
-    std::vector<cudaEvent_t> ev(size_t(2 * kt)), tev;
+    std::vector<cudaEvent_t> ev(size_t(2 * kt)), tev, pev;
+    auto ptime = [&](cudaStream_t st) -> int {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        pev.push_back(e);
+        CUDA_TRY(cudaEventRecord(e, st));
+        return SB200_OK;
+    };
     for (auto& e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaEvent_t t0, t1;
     CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
     auto P_done = [&](int64_t k) { return ev[size_t(k)]; };
     auto T_done = [&](int64_t k) { return ev[size_t(kt + k)]; };
     double trail_flops = 0; int64_t trail_launches = 0;
+    PhaseTimer ph;
 
     auto run_batches = [&](const std::vector<GBatchD>& bs, cudaStream_t s) -> int {
         for (const auto& b : bs) {
@@ -340,6 +348,8 @@ int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out)
 
             // ---- panel: gather on the root, factor, broadcast tiles + pivots + row map
             if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));       // pws[k & 1] is free again
+            SB_TRY(ptime(P));
+            ph.begin("gather", P);
             if (pcol == kq && p > 1) {
                 NCCL_TRY(ncclGroupStart());
                 if (g.rank == root) {
@@ -351,15 +361,17 @@ int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out)
                     NCCL_TRY(ncclSend(A.tile(first_row(prow, k), k), size_t(count_rows(prow, k) * te), ncclDouble, kp, g.col_comm, P));
                 NCCL_TRY(ncclGroupEnd());
             }
+            ph.end(P);
             if (g.rank == root) {
                 iota_kernel<<<unsigned(ceil_div(m_p, 256)), 256, 0, P>>>(rowmapb.as<int>(), m_p);
                 SB_TRY(launch_status());
                 double* const* stack_k = reinterpret_cast<double* const*>(dplan + steps[k].stack_off);
                 SB_TRY(getrf_panel_d(stack_k, A.tile(k, k), int(mt - k), int(nb), m_p, kw, pt, po, infob.as<int>(),
-                                     int(k * nb), ps, P, rowmapb.as<int>()));
+                                     int(k * nb), ps, P, rowmapb.as<int>(), &ph));
                 perm_pack_kernel<<<unsigned(ceil_div(ntop, 256)), 256, 0, P>>>(rowmapb.as<int>(), pt, po, int(nb), ntop, perm);
                 SB_TRY(launch_status());
             }
+            ph.begin("bcast", P);
             if (multi) {
                 NCCL_TRY(ncclGroupStart());
                 for (int r = 0; r < p; ++r) {
@@ -382,11 +394,15 @@ int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out)
                 CUDA_TRY(cudaMemcpyAsync(pws_tile(k, k), A.tile(k, k), size_t((mt - k) * te) * sizeof(double),
                                          cudaMemcpyDeviceToDevice, P));
             }
+            ph.end(P);
+            SB_TRY(ptime(P));
             CUDA_TRY(cudaEventRecord(P_done(k), P));
 
             // ---- trailing stream: interchanges on every local column except k (and k+1: lookahead), U row, GEMM
             CUDA_TRY(cudaStreamWaitEvent(T, P_done(k), 0));
+            ph.begin("tr_permute_solve", T);
             SB_TRY(permute_and_solve(k, 0, nt_loc, int(k), int(k + 1), false, T, g.col_comm2, wt.as<double>()));
+            ph.end(T);
             if (! steps[k].tr.empty()) {
                 cudaEvent_t a0, a1;
                 CUDA_TRY(cudaEventCreate(&a0)); CUDA_TRY(cudaEventCreate(&a1));
@@ -403,8 +419,12 @@ int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out)
             if (k + 1 < nt && int((k + 1) % q) == pcol) {
                 if (k >= 1) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 1), 0));
                 const int jl = int((k + 1 - pcol) / q);
+                ph.begin("la_permute_solve", P);
                 SB_TRY(permute_and_solve(k, jl, jl + 1, -1, -1, true, P, g.col_comm, ps.W));
+                ph.end(P);
+                ph.begin("la_gemm", P);
                 SB_TRY(run_batches(steps[k].la, P));
+                ph.end(P);
             }
         }
         CUDA_TRY(cudaStreamWaitEvent(P, T_done(kt - 1), 0));
@@ -414,6 +434,7 @@ int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out)
         return SB200_OK;
     };
     int status = body();
+    ph.report("getrf_dist", g.rank);
     if (status == SB200_OK) {
         float ms = 0;
         cudaEventElapsedTime(&ms, t0, t1);
@@ -421,6 +442,9 @@ int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out)
         double tms = 0;
         for (size_t i = 0; i + 1 < tev.size(); i += 2) { float x = 0; if (cudaEventElapsedTime(&x, tev[i], tev[i + 1]) == cudaSuccess) tms += x; }
         A.last_trail_ms = tms; A.last_trail_flops = trail_flops; A.last_trail_launches = trail_launches;
+        double pms = 0;
+        for (size_t i = 0; i + 1 < pev.size(); i += 2) { float x = 0; if (cudaEventElapsedTime(&x, pev[i], pev[i + 1]) == cudaSuccess) pms += x; }
+        A.last_panel_ms = pms;
         int hinfo = 0;
         cudaMemcpy(&hinfo, infob.p, sizeof(int), cudaMemcpyDeviceToHost);
         int64_t info = hinfo;
@@ -452,6 +476,7 @@ int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out)
     }
     for (auto e : ev) cudaEventDestroy(e);
     for (auto e : tev) cudaEventDestroy(e);
+    for (auto e : pev) cudaEventDestroy(e);
     cudaEventDestroy(t0); cudaEventDestroy(t1);
     if (P) cudaStreamDestroy(P);
     if (T) cudaStreamDestroy(T);

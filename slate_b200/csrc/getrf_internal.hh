@@ -23,7 +23,7 @@ struct PanelScratch {
 // identity): on return rowmap[x] = panel row whose ORIGINAL content sits at position x.
 int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
                   int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
-                  PanelScratch& ps, cudaStream_t s, int* rowmap = nullptr);
+                  PanelScratch& ps, cudaStream_t s, int* rowmap = nullptr, PhaseTimer* ph = nullptr);
 
 int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, double alpha,
                     const double* T, int ldt, double* const* dB, int64_t offB, int ldb, int batch,

@@ -145,6 +145,24 @@ struct Streams {
     cudaStream_t panel = nullptr, trail = nullptr;
     std::vector<cudaEvent_t> ev;
     std::vector<cudaEvent_t> tev;          // timing event pairs around the trailing-update launches
+    std::vector<cudaEvent_t> pev;          // timing event pairs around the panel work of every step
+    int ptime(cudaStream_t s)
+    {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        pev.push_back(e);
+        CUDA_TRY(cudaEventRecord(e, s));
+        return SB200_OK;
+    }
+    double panel_ms()
+    {
+        double tot = 0;
+        for (size_t i = 0; i + 1 < pev.size(); i += 2) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, pev[i], pev[i + 1]) == cudaSuccess) tot += ms;
+        }
+        return tot;
+    }
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int time_begin(cudaStream_t s)
     {
@@ -180,6 +198,7 @@ struct Streams {
     {
         for (auto e : ev) if (e) cudaEventDestroy(e);
         for (auto e : tev) if (e) cudaEventDestroy(e);
+        for (auto e : pev) if (e) cudaEventDestroy(e);
         if (t0) cudaEventDestroy(t0);
         if (t1) cudaEventDestroy(t1);
         if (panel) cudaStreamDestroy(panel);
@@ -255,6 +274,7 @@ int potrf_driver(Matrix& A, int64_t* info_out)
     }
 
     Streams st;
+    PhaseTimer ph;
     SB_TRY(st.init(size_t(2 * nt)));
     double trail_flops = 0;
     int64_t trail_launches = 0;
@@ -275,12 +295,17 @@ int potrf_driver(Matrix& A, int64_t* info_out)
         // -- lookahead update of column k by panel k-1 (after every older trailing update)
         if (k >= 1) {
             if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));
+            ph.begin("la_update", P);
             SB_TRY(launch_batches(steps[k - 1].la, pb, 'N', 'T', -1.0, 1.0, ld, P));
+            ph.end(P);
         }
         // -- diagonal tile
+        SB_TRY(st.ptime(P));
         const double* Lkk = nullptr;
+        ph.begin("potrf_tile", P);
         if (g.rank == owner)
             SB_TRY(potrf_tile_lower_d(kw, A.tile(k, k), ld, static_cast<int*>(dinfo.p), int(k * nb), W_potrf, P));
+        ph.end(P);
         if (k + 1 < nt) {
             if (multi) {
                 double* db = static_cast<double*>(dbuf.p) + (k & 1) * te;
@@ -293,6 +318,7 @@ int potrf_driver(Matrix& A, int64_t* info_out)
             }
             else Lkk = A.tile(k, k);
             // -- panel solve A(i,k) <- A(i,k) L_kk^{-T}
+            ph.begin("panel_trsm", P);
             if (in_col) {
                 if (! s.panel.empty())
                     SB_TRY(trsm_colmajor_d(false, true, 'T', false, int(nb), kw, 1.0, Lkk, ld,
@@ -303,7 +329,9 @@ int potrf_driver(Matrix& A, int64_t* info_out)
                                            reinterpret_cast<double* const*>(pb.dev + s.panel_last_off), 0, ld,
                                            int(s.panel_last.size()), W_trsm, P));
             }
+            ph.end(P);
             // -- panel broadcast: every rank receives the whole factored block column
+            ph.begin("panel_bcast", P);
             if (multi) {
                 if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));   // ws[k&1] is free again
                 NCCL_TRY(ncclGroupStart());
@@ -318,7 +346,9 @@ int potrf_driver(Matrix& A, int64_t* info_out)
                 }
                 NCCL_TRY(ncclGroupEnd());
             }
+            ph.end(P);
         }
+        SB_TRY(st.ptime(P));
         CUDA_TRY(cudaEventRecord(P_done(k), P));
         // -- trailing update of columns >= k+2
         CUDA_TRY(cudaStreamWaitEvent(T, P_done(k), 0));
@@ -343,6 +373,8 @@ int potrf_driver(Matrix& A, int64_t* info_out)
     A.last_trail_ms = st.timed_ms();
     A.last_trail_flops = trail_flops;
     A.last_trail_launches = trail_launches;
+    A.last_panel_ms = st.panel_ms();
+    ph.report("potrf", g.rank);
     int64_t info = hinfo;
     if (multi) {
         // first failing minor over all ranks (reference: internal_reduce_info.cc:23-38, MPI_MIN)
@@ -551,6 +583,7 @@ int sb200_matrix_destroy(sb200_matrix_t h)
 
 int64_t sb200_matrix_local_tiles(sb200_matrix_t h) { return h ? h->A.ntiles_loc : 0; }
 double  sb200_last_driver_ms(sb200_matrix_t h) { return h ? h->A.last_ms : 0.0; }
+double  sb200_last_driver_panel_ms(sb200_matrix_t h) { return h ? h->A.last_panel_ms : 0.0; }
 
 int sb200_last_driver_stats(sb200_matrix_t h, double* out4)
 {
@@ -612,6 +645,27 @@ int sb200_matrix_to_host_d(sb200_matrix_t h, double* hA, int64_t lda, sb200_stre
 {
     if (! h || ! hA) return SB200_EINVAL;
     return matrix_host_copy(h->A, hA, lda, true, cudaStream_t(stream));
+}
+
+// local tiles <-> a packed host buffer in pool order (local block column, then local block row;
+// every tile nb*nb, ld = nb): the host-side layout a caller gets from Matrix::insertLocalTiles with
+// its own contiguous storage (include/slate/Matrix.hh:631-662).  One contiguous copy.
+int sb200_matrix_from_host_local_d(sb200_matrix_t h, const double* htiles, sb200_stream_t stream)
+{
+    if (! h || ! htiles) return SB200_EINVAL;
+    Matrix& A = h->A;
+    CUDA_TRY(cudaMemcpyAsync(A.pool, htiles, size_t(A.ntiles_loc) * A.tile_elems() * sizeof(double),
+                             cudaMemcpyHostToDevice, cudaStream_t(stream)));
+    return SB200_OK;
+}
+
+int sb200_matrix_to_host_local_d(sb200_matrix_t h, double* htiles, sb200_stream_t stream)
+{
+    if (! h || ! htiles) return SB200_EINVAL;
+    Matrix& A = h->A;
+    CUDA_TRY(cudaMemcpyAsync(htiles, A.pool, size_t(A.ntiles_loc) * A.tile_elems() * sizeof(double),
+                             cudaMemcpyDeviceToHost, cudaStream_t(stream)));
+    return SB200_OK;
 }
 
 int sb200_matrix_copy_d(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream)

@@ -20,6 +20,9 @@
 #include "common.cuh"
 #include <nccl.h>
 #include <vector>
+#include <string>
+#include <cstdio>
+#include <cstdlib>
 
 namespace sb200 {
 
@@ -47,6 +50,7 @@ struct Matrix {
     double  last_trail_ms = 0.0;             // summed duration of its trailing-update GEMM launches
     double  last_trail_flops = 0.0;          // algorithmic flops of those launches
     int64_t last_trail_launches = 0;
+    double  last_panel_ms = 0.0;             // summed duration of the panel-stream critical work (factor + solve + broadcast)
 
     int64_t tile_elems() const { return nb * nb; }
     int64_t tile_mb(int64_t i) const { return i == mt - 1 ? m - i * nb : nb; }
@@ -67,6 +71,43 @@ struct Matrix {
         if (kind == 'G') idx = col_start[jl] + il;
         else             idx = col_start[jl] + (il - first_local_row(j));
         return pool + idx * tile_elems();
+    }
+};
+
+// Optional per-phase device timing of a driver call (SB200_PHASES=1): event pairs around named
+// phases of the panel / trailing streams, summed per phase and printed to stderr as one JSON line
+// when the driver returns.  Used to find what the lookahead has to hide; off by default.
+struct PhaseTimer {
+    struct Rec { const char* name; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    bool on = false;
+    PhaseTimer() { const char* e = getenv("SB200_PHASES"); on = e && atoi(e) != 0; }
+    void begin(const char* name, cudaStream_t s)
+    {
+        if (! on) return;
+        Rec r{name, nullptr, nullptr};
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, s);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t s) { if (on && ! recs.empty()) cudaEventRecord(recs.back().b, s); }
+    void report(const char* what, int rank)
+    {
+        if (! on) return;
+        cudaDeviceSynchronize();
+        std::vector<std::pair<std::string, std::pair<double, int>>> sums;
+        for (auto& r : recs) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            bool found = false;
+            for (auto& x : sums) if (x.first == r.name) { x.second.first += ms; x.second.second++; found = true; }
+            if (! found) sums.push_back({r.name, {ms, 1}});
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        recs.clear();
+        fprintf(stderr, "{\"sb200_phases\": \"%s\", \"rank\": %d", what, rank);
+        for (auto& x : sums) fprintf(stderr, ", \"%s\": [%.3f, %d]", x.first.c_str(), x.second.first, x.second.second);
+        fprintf(stderr, "}\n");
     }
 };
 

@@ -36,6 +36,9 @@ _matrix_destroy = _sig("sb200_matrix_destroy", [c_ptr])
 _matrix_generate = _sig("sb200_matrix_generate_d", [c_ptr, c_int, c_i64, c_ptr])
 _matrix_from_host = _sig("sb200_matrix_from_host_d", [c_ptr, c_ptr, c_i64, c_ptr])
 _matrix_to_host = _sig("sb200_matrix_to_host_d", [c_ptr, c_ptr, c_i64, c_ptr])
+_matrix_from_host_local = _sig("sb200_matrix_from_host_local_d", [c_ptr, c_ptr, c_ptr])
+_matrix_to_host_local = _sig("sb200_matrix_to_host_local_d", [c_ptr, c_ptr, c_ptr])
+_last_panel_ms = _sig("sb200_last_driver_panel_ms", [c_ptr], c_dbl)
 _matrix_copy = _sig("sb200_matrix_copy_d", [c_ptr, c_ptr, c_ptr])
 _matrix_local_tiles = _sig("sb200_matrix_local_tiles", [c_ptr], c_i64)
 _last_ms = _sig("sb200_last_driver_ms", [c_ptr], c_dbl)
@@ -162,6 +165,31 @@ class Matrix:
         torch.cuda.current_stream().synchronize()
         return out
 
+    def from_host_local(self, htiles, sync: bool = True):
+        """Copy this rank's tiles from a packed host buffer (torch CPU float64 tensor, ideally pinned,
+        of local_tiles * nb * nb elements in pool order: local block column, then local block row)."""
+        self._check_local(htiles)
+        check(_matrix_from_host_local(self._h, htiles.data_ptr(), _stream()), "from_host_local")
+        if sync:
+            import torch
+            torch.cuda.current_stream().synchronize()
+        return self
+
+    def to_host_local(self, htiles, sync: bool = True):
+        self._check_local(htiles)
+        check(_matrix_to_host_local(self._h, htiles.data_ptr(), _stream()), "to_host_local")
+        if sync:
+            import torch
+            torch.cuda.current_stream().synchronize()
+        return htiles
+
+    def _check_local(self, t):
+        import torch
+        need = self.local_tiles * self.nb * self.nb
+        if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.dtype == torch.float64
+                and t.is_contiguous() and t.numel() == need):
+            raise Exception_(f"local tile buffer must be a contiguous float64 CPU tensor of {need} elements")
+
     def copy_from(self, other: "Matrix"):
         check(_matrix_copy(self._h, other._h, _stream()), "copy")
         return self
@@ -173,6 +201,10 @@ class Matrix:
     @property
     def last_driver_ms(self) -> float:
         return float(_last_ms(self._h))
+
+    @property
+    def last_panel_ms(self) -> float:
+        return float(_last_panel_ms(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

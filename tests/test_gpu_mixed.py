@@ -1,0 +1,112 @@
+"""GPU parity tests (pytest -m gpu) of the mixed-precision path: the tcgen05 FP32-emulated
+(3 x TF32) batched tile GEMM and its operand packing, through the C ABI.
+
+Oracle: the FP64 product of the SAME float32 inputs (numpy).  Tolerance: the emulation drops the
+lo*lo term (< 2^-22 |a||b| per product) and truncates lo to 11 bits, so the result must be within
+    tol = (2^-20 + sqrt(k) * eps_f32) * |A| |B|   element-wise  (+ |alpha|,|beta| scaling)
+of the exact product -- i.e. FP32-class accuracy, 2^10 times tighter than a plain TF32 GEMM
+(which the last test demonstrates by checking that plain-TF32 error WOULD fail the bound)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests.gpu_util import DevTiles, fn, sync, stream, c_i64, c_int, c_flt, c_ptr
+
+pytestmark = pytest.mark.gpu
+EPS32 = float(np.finfo(np.float32).eps)
+
+
+def _packed(side, op, tiles, rows, k):
+    """Pack a list of float32 tiles on the device; returns (device byte buffers, pointer array)."""
+    import torch
+    from slate_b200._lib import lib
+    lib.sb200_tf32x3_packed_bytes.restype = ctypes.c_size_t
+    lib.sb200_tf32x3_packed_bytes.argtypes = [c_int, c_i64, c_i64]
+    nbytes = lib.sb200_tf32x3_packed_bytes(ord(side), rows, k)
+    assert nbytes > 0
+    bufs = [torch.full((nbytes,), 0x7f, dtype=torch.uint8, device="cuda") for _ in tiles]   # poison
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    d = DevTiles(tiles)
+    pack = fn("sb200_tf32x3_pack_batched_s", [c_int, c_int, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr])
+    ld = max(1, tiles[0].shape[0])
+    assert pack(ord(side), ord(op), rows, k, d.p, ld, ptrs.data_ptr(), len(tiles), stream()) == 0
+    return bufs, ptrs, d
+
+
+def _run(m, n, k, batch, alpha, beta, opA="N", opB="N", seed=0, scale=1.0):
+    rng = np.random.default_rng(seed)
+    shpA = (m, k) if opA == "N" else (k, m)
+    shpB = (k, n) if opB == "N" else (n, k)
+    A = [np.asfortranarray(((rng.random(shpA) - 0.3) * scale).astype(np.float32)) for _ in range(batch)]
+    B = [np.asfortranarray((rng.random(shpB) - 0.3).astype(np.float32)) for _ in range(batch)]
+    C = [np.asfortranarray(rng.random((m, n)).astype(np.float32)) for _ in range(batch)]
+    ba, pa, _ka = _packed("A", opA, A, m, k)
+    bb, pb, _kb = _packed("B", opB, B, n, k)
+    dC = DevTiles(C)
+    gemm = fn("sb200_gemm_tf32x3_packed_s", [c_i64] * 3 + [c_flt, c_ptr, c_ptr, c_flt, c_ptr, c_i64, c_i64, c_ptr])
+    assert gemm(m, n, k, alpha, pa.data_ptr(), pb.data_ptr(), beta, dC.p, max(1, m), batch, stream()) == 0
+    sync()
+    out = dC.get()
+    op = lambda x, o: x if o == "N" else x.T
+    worst = 0.0
+    for a, b, c, x in zip(A, B, C, out):
+        a64, b64 = op(a, opA).astype(np.float64), op(b, opB).astype(np.float64)
+        ref = alpha * (a64 @ b64) + beta * c.astype(np.float64)
+        bound = (2.0 ** -20 + np.sqrt(k) * EPS32) * (abs(alpha) * (np.abs(a64) @ np.abs(b64)) + abs(beta) * np.abs(c)) \
+            + 4 * EPS32 * np.abs(ref)
+        err = np.abs(x.astype(np.float64) - ref)
+        assert (err <= bound).all(), f"max err/bound = {(err / bound).max():.3f} at m={m} n={n} k={k}"
+        worst = max(worst, float(err.max() / np.abs(ref).max()))
+    return worst
+
+
+@pytest.mark.parametrize("m,n,k,batch", [(128, 256, 16, 1), (128, 256, 64, 2), (512, 512, 512, 3),
+                                         (256, 512, 32, 2), (384, 256, 48, 1)])
+def test_tf32x3_gemm_full_blocks(m, n, k, batch):
+    _run(m, n, k, batch, -1.0, 1.0)
+
+
+@pytest.mark.parametrize("m,n,k", [(100, 200, 24), (129, 257, 17), (488, 488, 488), (1, 1, 1), (300, 40, 512)])
+def test_tf32x3_gemm_ragged(m, n, k):
+    """Zero-padded packing + masked epilogue: rows/cols/k that are not multiples of the block."""
+    _run(m, n, k, 2, 3.1, 2.7, seed=3)
+
+
+@pytest.mark.parametrize("opA,opB", [("N", "T"), ("T", "N"), ("T", "T")])
+def test_tf32x3_gemm_transposed_operands(opA, opB):
+    _run(256, 256, 96, 2, -1.0, 1.0, opA, opB, seed=5)
+
+
+def test_tf32x3_beta_zero_ignores_c_and_wide_dynamic_range():
+    import torch
+    _run(256, 256, 128, 1, 2.0, 0.0, seed=7, scale=1e6)
+    # beta == 0 must not propagate NaNs that sit in C
+    m = n = 128; k = 32
+    rng = np.random.default_rng(8)
+    A = [np.asfortranarray(rng.random((m, k)).astype(np.float32))]
+    B = [np.asfortranarray(rng.random((k, n)).astype(np.float32))]
+    C = [np.full((m, n), np.nan, dtype=np.float32, order="F")]
+    _ba, pa, _ka = _packed("A", "N", A, m, k)
+    _bb, pb, _kb = _packed("B", "N", B, n, k)
+    dC = DevTiles(C)
+    gemm = fn("sb200_gemm_tf32x3_packed_s", [c_i64] * 3 + [c_flt, c_ptr, c_ptr, c_flt, c_ptr, c_i64, c_i64, c_ptr])
+    assert gemm(m, n, k, 1.0, pa.data_ptr(), pb.data_ptr(), 0.0, dC.p, m, 1, stream()) == 0
+    out = dC.get()[0]
+    assert np.isfinite(out).all()
+    ref = A[0].astype(np.float64) @ B[0].astype(np.float64)
+    assert np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_tf32x3_is_fp32_class_not_tf32_class():
+    """Accuracy class: the 3-product kernel is ~2^-21 accurate; ONE TF32 plane of the same kind of
+    inputs is ~2^-11 (what a plain tcgen05 kind::tf32 GEMM would give)."""
+    rng = np.random.default_rng(11)
+    m = n = 256; k = 512
+    a = rng.random((m, k)).astype(np.float32); b = rng.random((k, n)).astype(np.float32)
+    trunc = lambda x: (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    tf32_err = np.abs(trunc(a).astype(np.float64) @ trunc(b).astype(np.float64) - ref).max() / np.abs(ref).max()
+    ours = _run(m, n, k, 1, 1.0, 0.0, seed=11)
+    assert tf32_err > 1e-4
+    assert ours < 3e-6, ours
