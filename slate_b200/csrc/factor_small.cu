@@ -133,6 +133,155 @@ trtri_diag_kernel(const T* __restrict__ Tm, int ldt, int na, int lower, int unit
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast variants for the real types (the critical path of every dpotrf / dgetrf step).
+// 64 threads, one matrix ROW (Cholesky) or one COLUMN of the inverse per thread, held in
+// registers; the only shared-memory traffic is the broadcast of one column per elimination step,
+// and there is ONE __syncthreads per column (the kernels above need four and walk the trailing
+// block with div/mod indexing).  Same results up to rounding: the update is formed as
+// a_ic - (a_ij / d) * a_cj with the un-normalised column, L_ij = a_ij / sqrt(d) at the end.
+// ---------------------------------------------------------------------------------------------
+template <typename R> constexpr size_t fast_smem() { return (size_t(IB) * (IB + 1) + IB) * sizeof(R); }
+
+// X = inv(L) for a 64 x 64 lower-triangular L held in shared memory as Ls[j * IB + i] = L_ij
+// (entries above the diagonal are never read), rd[i] = 1 / L_ii.  Thread j = threadIdx.x owns
+// column j: forward substitution in axpy form, so the only dependent chain is x_i -> x_{i+1}.
+template <typename R>
+__device__ __forceinline__ void inv_lower_column(const R* __restrict__ Ls, const R* __restrict__ rd,
+                                                 int j, R (&x)[IB])
+{
+    #pragma unroll
+    for (int k = 0; k < IB; ++k) x[k] = (k == j) ? R(1) : R(0);
+    #pragma unroll
+    for (int i = 0; i < IB; ++i) {
+        x[i] *= rd[i];
+        const R xi = x[i];
+        #pragma unroll
+        for (int k = i + 1; k < IB; ++k) x[k] = fma(-Ls[i * IB + k], xi, x[k]);
+    }
+}
+
+// stage the columns held in registers through a padded buffer and write W[i + j*IB] = X_ij
+// (transpose_out: W[i + j*IB] = X_ji) with coalesced stores.  All 64 threads must call it.
+template <typename R>
+__device__ __forceinline__ void store_inverse(R* __restrict__ Xs, const R (&x)[IB], int tid,
+                                              R* __restrict__ W, bool transpose_out)
+{
+    __syncthreads();                               // everybody is done reading Ls (aliased by Xs)
+    #pragma unroll
+    for (int i = 0; i < IB; ++i) Xs[i * (IB + 1) + tid] = x[i];          // Xs[i][j = tid]
+    __syncthreads();
+    if (! transpose_out) {
+        #pragma unroll 8
+        for (int j = 0; j < IB; ++j) W[tid + j * IB] = Xs[tid * (IB + 1) + j];
+    }
+    else {
+        #pragma unroll 8
+        for (int j = 0; j < IB; ++j) W[tid + j * IB] = Xs[j * (IB + 1) + tid];
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(IB, 1)
+potrf_diag_fast_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv,
+                       int* __restrict__ info, int info_base)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    R* Ls = reinterpret_cast<R*>(smem_dyn);        // [IB*(IB+1)]: columns (stride IB), later padded staging
+    R* rd = Ls + IB * (IB + 1);                    // [IB] reciprocal diagonal
+    const int i = threadIdx.x;                     // this thread's row
+    if (*info != 0) return;                        // an earlier block already failed: leave the tile alone
+    R a[IB];
+    #pragma unroll
+    for (int c = 0; c < IB; ++c)
+        a[c] = (i < nv && c < nv) ? (c <= i ? A[i + int64_t(c) * lda] : R(0)) : (i == c ? R(1) : R(0));
+    int fail = 0;
+    R rdiag = R(1);
+    #pragma unroll
+    for (int j = 0; j < IB; ++j) {
+        Ls[j * IB + i] = a[j];
+        __syncthreads();
+        const R d = Ls[j * IB + j];
+        if (fail == 0 && !(d > R(0))) fail = j + 1;          // also catches NaN; uniform over the CTA
+        const R w = a[j] / d;
+        #pragma unroll
+        for (int c = j + 1; c < IB; ++c) a[c] = fma(-w, Ls[j * IB + c], a[c]);
+        const R r = sqrt(d);
+        a[j] = (i == j) ? r : a[j] / r;
+        if (i == j) rdiag = R(1) / r;
+    }
+    if (fail) {
+        if (i == 0 && *info == 0) *info = info_base + fail;
+        return;
+    }
+    #pragma unroll
+    for (int c = 0; c < IB; ++c)
+        if (c <= i && i < nv) A[i + int64_t(c) * lda] = a[c];
+    // L (final) into shared memory for the inverse; rows above the diagonal are never read
+    __syncthreads();
+    #pragma unroll
+    for (int c = 0; c < IB; ++c) Ls[c * IB + i] = a[c];
+    rd[i] = rdiag;
+    __syncthreads();
+    R x[IB];
+    inv_lower_column<R>(Ls, rd, i, x);
+    store_inverse<R>(Ls, x, i, Winv, false);
+}
+
+// fast trtri of the diagonal IB-blocks (real types): same contract as trtri_diag_kernel
+template <typename R>
+__global__ void __launch_bounds__(IB, 1)
+trtri_diag_fast_kernel(const R* __restrict__ Tm, int ldt, int na, int lower, int unit, R* __restrict__ W)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    R* Ls = reinterpret_cast<R*>(smem_dyn);
+    R* rd = Ls + IB * (IB + 1);
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int o = b * IB;
+    const int nv = min(IB, na - o);
+    // always handled as LOWER: upper blocks are transposed in.  Thread = row i of the lower block.
+    #pragma unroll 8
+    for (int j = 0; j < IB; ++j) {
+        const int i = tid;
+        R v = (i == j) ? R(1) : R(0);
+        if (i < nv && j < nv) {
+            if (i > j)                v = lower ? Tm[o + i + int64_t(o + j) * ldt] : Tm[o + j + int64_t(o + i) * ldt];
+            else if (i == j && !unit) v = Tm[o + i + int64_t(o + j) * ldt];
+        }
+        Ls[j * IB + i] = v;
+        if (i == j) rd[i] = R(1) / v;
+    }
+    __syncthreads();
+    R x[IB];
+    inv_lower_column<R>(Ls, rd, tid, x);
+    // inverse of the transpose = transpose of the inverse
+    store_inverse<R>(Ls, x, tid, W + int64_t(b) * IB * IB, lower == 0);
+}
+
+template <typename T> struct IsRealType { static constexpr bool value = false; };
+template <> struct IsRealType<float>  { static constexpr bool value = true; };
+template <> struct IsRealType<double> { static constexpr bool value = true; };
+
+template <typename T>
+static int launch_potrf_diag(T* A, int lda, int nv, T* Winv, int* info, int info_base, cudaStream_t stream)
+{
+    if constexpr (IsRealType<T>::value)
+        potrf_diag_fast_kernel<T><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+    else
+        potrf_diag_kernel<T><<<1, 256, small_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+    return launch_status();
+}
+
+template <typename T>
+static int launch_trtri_diag(int nblk, const T* Tm, int ldt, int na, int lower, int unit, T* W, cudaStream_t stream)
+{
+    if constexpr (IsRealType<T>::value)
+        trtri_diag_fast_kernel<T><<<nblk, IB, fast_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
+    else
+        trtri_diag_kernel<T><<<nblk, 256, small_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
+    return launch_status();
+}
+
 template <typename T>
 static void small_kernels_init()
 {
@@ -142,6 +291,10 @@ static void small_kernels_init()
     if (done[dev & 63]) return;
     cudaFuncSetAttribute(potrf_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem<T>()));
     cudaFuncSetAttribute(trtri_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem<T>()));
+    if constexpr (IsRealType<T>::value) {
+        cudaFuncSetAttribute(potrf_diag_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
+        cudaFuncSetAttribute(trtri_diag_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
+    }
     done[dev & 63] = true;
 }
 
@@ -182,8 +335,7 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
     const int na = left ? m : n;
     const int nblk = int(ceil_div(na, IB));
     small_kernels_init<T>();
-    trtri_diag_kernel<T><<<nblk, 256, small_smem<T>(), stream>>>(Tm, ldt, na, lower ? 1 : 0, unit ? 1 : 0, W);
-    int st = launch_status();
+    int st = launch_trtri_diag<T>(nblk, Tm, ldt, na, lower ? 1 : 0, unit ? 1 : 0, W, stream);
     if (st) return st;
     const bool trans = (op != 'N');
     const bool eff_lower = (lower != trans);        // op(T) as a math matrix
@@ -247,8 +399,7 @@ int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cuda
     for (int jo = 0; jo < n; jo += IB) {
         const int jv = min(IB, n - jo);
         T* Ajj = A + jo + int64_t(jo) * lda;
-        potrf_diag_kernel<T><<<1, 256, small_smem<T>(), stream>>>(Ajj, lda, jv, W, dinfo, info_base + jo);
-        if ((st = launch_status())) return st;
+        if ((st = launch_potrf_diag<T>(Ajj, lda, jv, W, dinfo, info_base + jo, stream))) return st;
         const int rest = n - jo - jv;
         if (rest <= 0) break;
         T* Pnl = A + (jo + jv) + int64_t(jo) * lda;          // rest x jv block below the diagonal

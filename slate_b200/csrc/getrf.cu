@@ -89,6 +89,9 @@ struct BaseArgs {
     double* gval; int* grow; double* gcand; double* gdiag;     // [2][G], [2][G], [2][G][PW], [2][PW]
     int* info; int info_base;
     int* rowmap;       // optional: rowmap[x] = panel row whose ORIGINAL content now sits at position x
+    int kw_wide;       // > 0: the LAST CTA of the grid owns no rows and applies every interchange of this
+                       // block to the panel columns outside [c0, c0+w) (all kw_wide columns of the panel)
+                       // while the other CTAs go on factoring -- no laswp launches between blocks
 };
 
 __global__ void __launch_bounds__(PTHREADS)
@@ -193,6 +196,18 @@ getrf_base_kernel(const BaseArgs a)
             a.piv_off[d] = p % nb;
             if (a.rowmap && p != d) { const int t = a.rowmap[d]; a.rowmap[d] = a.rowmap[p]; a.rowmap[p] = t; }
         }
+        if (a.kw_wide > 0 && b == G - 1 && p != d) {
+            // thread t always handles panel columns t, t + PTHREADS, ...: the interchanges of one column
+            // are applied in pivot order by one thread (rows d and p of later pivots may coincide)
+            double* rd_ = a.tiles[d / nb] + (d % nb);
+            double* rp_ = a.tiles[p / nb] + (p % nb);
+            for (int c = tid; c < a.kw_wide; c += PTHREADS)
+                if (c < a.c0 || c >= a.c0 + a.w) {
+                    const double t0 = rd_[int64_t(c) * nb], t1 = rp_[int64_t(c) * nb];
+                    rd_[int64_t(c) * nb] = t1;
+                    rp_[int64_t(c) * nb] = t0;
+                }
+        }
         __syncthreads();
         const double pv = s_prow[j];
         if (pv == 0.0) {
@@ -247,7 +262,116 @@ int PanelScratch::init()
 
 // Factor the panel given as a stack of `ntile` tiles (device pointer array `stack`, nb x nb, ld =
 // nb; last tile has m_p - (ntile-1)*nb rows), kw columns, diag_len = min(m_p, kw) pivots.
-int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
+// Panel algorithm selector: SB200_PANEL=1 right-looking 32-column blocks with laswp launches between
+// them; SB200_PANEL=2 (default) recursive panel, interchanges applied to the whole panel width inside
+// the base kernel.  Both give the pivot sequence of unblocked partial pivoting.
+static int panel_version()
+{
+    const char* e = getenv("SB200_PANEL");
+    return e ? atoi(e) : 2;
+}
+
+namespace {
+struct PanelCtx {
+    double* const* stack; double* tile0; int ntile, nb, m_p, kw;
+    int64_t* piv_tile; int64_t* piv_off; int* dinfo; int info_base;
+    PanelScratch* ps; cudaStream_t s; int* rowmap; PhaseTimer* pt;
+};
+}
+
+// one cooperative launch: columns [c0, c0+w) over panel rows [c0, m_p), interchanges applied to all
+// kw panel columns by the extra (row-less) CTA
+static int panel_base_wide(const PanelCtx& x, int c0, int w)
+{
+    const int active = x.m_p - c0;
+    const int ctas = x.ps->max_ctas - 1;                       // one SM is kept for the interchange CTA
+    int rows_per = std::max(int(ceil_div(active, ctas)), std::min(active, PROWS_MAX));
+    rows_per = std::max(rows_per, PW);
+    if (rows_per > PROWS_MAX) return SB200_ENOTSUP;
+    const int G = int(ceil_div(active, rows_per));
+    BaseArgs a{x.stack, x.nb, x.m_p, c0, w, rows_per, x.piv_tile, x.piv_off,
+               x.ps->gval, x.ps->grow, x.ps->gcand, x.ps->gdiag, x.dinfo, x.info_base, x.rowmap, x.kw};
+    void* args[] = {&a};
+    const size_t smem = size_t(w) * (rows_per | 1) * sizeof(double);
+    x.pt->begin("pnl_base", x.s);
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel),
+                                                dim3(G + 1), dim3(PTHREADS), args, smem, x.s);
+    if (e != cudaSuccess) return int(e);
+    SB_TRY(launch_status());
+    x.pt->end(x.s);
+    return SB200_OK;
+}
+
+// columns [cc, cc+n2) of the panel, given that columns [c0, c0+w1) are factored:
+//   U12 = L11^{-1} A12 (rows c0..c0+w1 of the top tile), then A22 -= L21 U12 on rows [c0+w1, m_p)
+static int panel_update(const PanelCtx& x, int c0, int w1, int cc, int n2)
+{
+    if (n2 <= 0 || w1 <= 0) return SB200_OK;
+    const int nb = x.nb;
+    x.pt->begin("pnl_trsm", x.s);
+    SB_TRY(trsm_colmajor_d(true, true, 'N', true, w1, n2, 1.0, x.tile0 + c0 + int64_t(c0) * nb, nb,
+                           x.stack, c0 + int64_t(cc) * nb, nb, 1, x.ps->W, x.s));
+    x.pt->end(x.s);
+    x.pt->begin("pnl_gemm", x.s);
+    const double* U12 = x.tile0 + c0 + int64_t(cc) * nb;
+    const int r0 = c0 + w1;                                   // first row of A22 (inside the top tile)
+    const int top_rows = std::min(nb, x.m_p) - r0;
+    if (top_rows > 0) {
+        GemmParamsD p{};
+        p.m = top_rows; p.n = n2; p.k = w1; p.alpha = -1.0; p.beta = 1.0; p.batch = 1;
+        p.A0 = x.tile0 + r0 + int64_t(c0) * nb; p.lda = nb;
+        p.B0 = U12; p.ldb = nb;
+        p.C0 = x.tile0 + r0 + int64_t(cc) * nb; p.ldc = nb;
+        SB_TRY(launch_gemm_d('N', 'N', p, x.s));
+    }
+    const int full = (x.m_p % nb == 0) ? x.ntile - 1 : x.ntile - 2;      // full-height tiles below tile 0
+    if (full > 0) {
+        GemmParamsD p{};
+        p.m = nb; p.n = n2; p.k = w1; p.alpha = -1.0; p.beta = 1.0; p.batch = full;
+        p.A = x.stack + 1; p.offA = int64_t(c0) * nb; p.lda = nb;
+        p.B0 = U12; p.ldb = nb; p.strideB = 0;
+        p.C = x.stack + 1; p.offC = int64_t(cc) * nb; p.ldc = nb;
+        SB_TRY(launch_gemm_d('N', 'N', p, x.s));
+    }
+    if (x.ntile > 1 && x.m_p % nb != 0) {
+        GemmParamsD p{};
+        p.m = x.m_p % nb; p.n = n2; p.k = w1; p.alpha = -1.0; p.beta = 1.0; p.batch = 1;
+        p.A = x.stack + (x.ntile - 1); p.offA = int64_t(c0) * nb; p.lda = nb;
+        p.B0 = U12; p.ldb = nb;
+        p.C = x.stack + (x.ntile - 1); p.offC = int64_t(cc) * nb; p.ldc = nb;
+        SB_TRY(launch_gemm_d('N', 'N', p, x.s));
+    }
+    x.pt->end(x.s);
+    return SB200_OK;
+}
+
+// recursive LU of columns [c0, c0+w); on entry they carry every update of the columns left of c0 and
+// every interchange chosen so far; on return so do ALL panel columns (base kernels swap panel-wide)
+static int panel_recurse(const PanelCtx& x, int c0, int w)
+{
+    if (w <= PW) return panel_base_wide(x, c0, w);
+    int w1 = int(ceil_div(w / 2, PW)) * PW;
+    if (w1 >= w) w1 = w - PW;
+    SB_TRY(panel_recurse(x, c0, w1));
+    SB_TRY(panel_update(x, c0, w1, c0 + w1, w - w1));
+    return panel_recurse(x, c0 + w1, w - w1);
+}
+
+static int getrf_panel_v2(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
+                          int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
+                          PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph)
+{
+    PhaseTimer off_timer;
+    off_timer.on = false;
+    PanelCtx x{stack, tile0, ntile, nb, m_p, kw, piv_tile, piv_off, dinfo, info_base, &ps, s, rowmap,
+               ph ? ph : &off_timer};
+    const int diag_len = std::min(m_p, kw);
+    SB_TRY(panel_recurse(x, 0, diag_len));
+    // wide last panel (m_p < kw): the columns right of the square part only get U = L^{-1} A
+    return panel_update(x, 0, diag_len, diag_len, kw - diag_len);
+}
+
+static int getrf_panel_v1(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
                   int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
                   PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph)
 {
@@ -316,6 +440,14 @@ int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_
         pt.end(s);
     }
     return SB200_OK;
+}
+
+int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
+                  int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
+                  PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph)
+{
+    return (panel_version() == 1 ? getrf_panel_v1 : getrf_panel_v2)(
+        stack, tile0, ntile, nb, m_p, kw, piv_tile, piv_off, dinfo, info_base, ps, s, rowmap, ph);
 }
 
 // ------------------------------------------------------------------------------------------
