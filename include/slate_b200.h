@@ -347,6 +347,68 @@ int sb200_last_driver_stats(sb200_matrix_t A, double* out4);
 int sb200_fp64_peak_probe(int kind, int iters, int ctas_per_sm, double* d_scratch, double* flops,
                           sb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Round-1 widening of the host runtime: all four scalar types, herk, the solve path and the
+ * mixed-precision drivers.  The matrix handle carries its element type; the un-suffixed data
+ * movement entries below work for every type (host buffers hold elements of that type).
+ * ------------------------------------------------------------------------- */
+int sb200_matrix_dtype(sb200_matrix_t A);                 /* 's', 'd', 'c' or 'z' */
+int sb200_matrix_generate(sb200_matrix_t A, int kind_code, int64_t seed, sb200_stream_t stream);
+int sb200_matrix_from_host(sb200_matrix_t A, const void* hA, int64_t lda, sb200_stream_t stream);
+int sb200_matrix_to_host(sb200_matrix_t A, void* hA, int64_t lda, sb200_stream_t stream);
+int sb200_matrix_from_host_local(sb200_matrix_t A, const void* htiles, sb200_stream_t stream);
+int sb200_matrix_to_host_local(sb200_matrix_t A, void* htiles, sb200_stream_t stream);
+int sb200_matrix_copy(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream);
+
+/* host-only description of the 2-D block-cyclic tile map (no GPU needed):
+ * tileRank (include/slate/func.hh:96-104, GridOrder::Col), the number of tiles a rank stores, and the
+ * slot of tile (i, j) in its owner's packed local buffer (sb200_matrix_{from,to}_host_local order). */
+int     sb200_tile_rank(int p, int q, int64_t i, int64_t j);
+int64_t sb200_local_tile_count(int kind, int p, int q, int rank, int64_t m, int64_t n, int64_t nb);
+int64_t sb200_local_tile_index(int kind, int p, int q, int64_t m, int64_t n, int64_t nb, int64_t i, int64_t j);
+
+#define SB200_DECL_RUNTIME(X, T, R) \
+int sb200_matrix_create_##X(sb200_grid_t g, int kind, int layout, int64_t m, int64_t n, int64_t nb, sb200_matrix_t* out); \
+/* C = alpha A B + beta C                       slate::gemm -> gemmC (src/gemmC.cc:39-202) */ \
+int sb200_gemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
+/* C = alpha A A^H + beta C, C Hermitian lower  slate::herk (src/herk.cc:25-162; real types: syrk) */ \
+int sb200_herk_mat_##X(R alpha, sb200_matrix_t A, R beta, sb200_matrix_t C, const sb200_options_t* opts); \
+/* A = L L^H, lower                             slate::potrf (src/potrf.cc:22-210) */ \
+int sb200_potrf_##X(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info); \
+/* B <- A^{-1} B from the Cholesky factor       slate::potrs (src/potrs.cc:54-77); 1 x 1 grid this round */ \
+int sb200_potrs_##X(sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
+/* C = alpha A X + beta C, A Hermitian lower, Side::Left   slate::hemm (src/hemmC.cc); 1 x 1 grid */ \
+int sb200_hemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
+/* norm(Norm::Inf, A), A general or Hermitian   slate::norm (src/norm.cc); 1 x 1 grid */ \
+int sb200_norm_inf_##X(sb200_matrix_t A, double* value);
+SB200_FOR_TYPES(SB200_DECL_RUNTIME)
+
+/* FP32 factorisations of the mixed-precision solvers; the _tc05 variants run the trailing-matrix
+ * update on the tcgen05 FP32-emulated (3 x TF32) tensor-core kernel (gemm_tc05.cu). getrf_*_s: 1 x 1 grid. */
+int sb200_potrf_tc05_s(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
+int sb200_getrf_s(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
+int sb200_getrf_tc05_s(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
+/* B <- A^{-1} B from the LU factors and pivots   slate::getrs (src/getrs.cc:25-66); 1 x 1 grid */
+int sb200_getrs_d(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
+int sb200_getrs_s(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
+
+/* slate::posv_mixed / gesv_mixed <double, float> (src/posv_mixed.cc:111-297, src/gesv_mixed.cc:106-300):
+ * factor a float copy of A (tcgen05 trailing update), solve, refine in FP64 until
+ * max|r_j| <= max|x_j| * ||A||_inf * tolerance for every column j.
+ * *iter: >= 0 refinement iterations; -3 low-precision factorisation failed; -(max_iterations+1) not converged
+ * (then, with use_fallback_solver, A is factored and the system solved in FP64 -- A is overwritten).
+ * timers_ms8 (optional): total, factor_lo, solve_lo, residual_hi, add_hi, factor_hi, solve_hi, norm+convert. */
+typedef struct {
+    int64_t max_iterations;       /* Option::MaxIterations, default 30; < 0 -> default      */
+    double  tolerance;            /* Option::Tolerance, <= 0 -> eps * sqrt(n)               */
+    int     use_fallback_solver;  /* Option::UseFallbackSolver, default 1                   */
+    int     reserved[5];
+} sb200_mixed_options_t;
+int sb200_posv_mixed_d(sb200_matrix_t A, sb200_matrix_t B, sb200_matrix_t X, const sb200_mixed_options_t* mo,
+                       int* iter, int64_t* info, double* timers_ms8);
+int sb200_gesv_mixed_d(sb200_matrix_t A, int64_t* pivots, sb200_matrix_t B, sb200_matrix_t X,
+                       const sb200_mixed_options_t* mo, int* iter, int64_t* info, double* timers_ms8);
+
 #ifdef __cplusplus
 }
 #endif

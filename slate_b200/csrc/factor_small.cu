@@ -416,6 +416,15 @@ int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cuda
     return SB200_OK;
 }
 
+// the drivers (runtime.cu, solve.cu, getrf.cu) use these for every scalar type
+#define SB200_INST_FACTOR(T) \
+    template int trsm_colmajor<T>(bool, bool, int, bool, int, int, T, const T*, int, T* const*, int64_t, int, int, T*, cudaStream_t); \
+    template int potrf_tile_lower<T>(int, T*, int, int*, int, T*, cudaStream_t);
+SB200_INST_FACTOR(float)
+SB200_INST_FACTOR(double)
+SB200_INST_FACTOR(cuFloatComplex)
+SB200_INST_FACTOR(cuDoubleComplex)
+
 // double-precision entry points used by the runtime
 int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, double alpha,
                     const double* T, int ldt, double* const* dB, int64_t offB, int ldb, int batch,

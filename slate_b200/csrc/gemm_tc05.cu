@@ -110,6 +110,8 @@ gemm_tf32x3_kernel(const Tc05Params p)
     const int mb = b % MB; b /= MB;
     const int nbk = b % NB;
     const int t = b / NB;
+    // triangle-masked tile: a block that lies wholly above the diagonal has nothing to store
+    if (p.tri == 1 && mb * TC_BM + TC_BM - 1 < nbk * TC_BN) return;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -194,7 +196,7 @@ gemm_tf32x3_kernel(const Tc05Params p)
             #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int col = n0 + c0 + j;
-                if (row < p.m && col < p.n) {
+                if (row < p.m && col < p.n && (p.tri == 0 || row >= col)) {
                     float r = p.alpha * __uint_as_float(v[j]);
                     if (use_beta) r = fmaf(p.beta, cin[j], r);
                     C[row + int64_t(col) * p.ldc] = r;

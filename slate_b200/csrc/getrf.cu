@@ -19,20 +19,24 @@
 //   * Row interchanges of a whole panel are applied to a block-column range in ONE launch.
 //   * Column-major tiles throughout (the reference converts to row-major for its swap BLAS
 //     calls, src/getrf.cc:51-55); the fused swap kernel takes either layout.
+#include "runtime_internal.hh"
 #include "getrf_internal.hh"
-#include "gemm_dmma.cuh"
 #include <cooperative_groups.h>
 #include <cfloat>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 namespace cg = cooperative_groups;
 
 namespace sb200 {
 
-#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return int(e_); } while (0)
-#define SB_TRY(x) do { int s_ = (x); if (s_ != SB200_OK) return s_; } while (0)
+template <typename T> __device__ __forceinline__ T tiny_of();
+template <> __device__ __forceinline__ float  tiny_of<float>()  { return FLT_MIN; }
+template <> __device__ __forceinline__ double tiny_of<double>() { return DBL_MIN; }
+__device__ __forceinline__ float  fma_t(float a, float b, float c)    { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
 
 // ------------------------------------------------------------------------------------------
@@ -40,8 +44,9 @@ namespace sb200 {
 // piv_tile[jj]*nb + piv_off[jj]; applied in order (forward) or reversed.  One thread per matrix
 // column; `tiles[t + jt*ldt]` is tile t of the stack in block column jt.
 // ------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
-laswp_kernel(double* const* __restrict__ tiles, int64_t ldt, int mb, int nb, int ld, int colmajor,
+laswp_kernel(T* const* __restrict__ tiles, int64_t ldt, int mb, int nb, int ld, int colmajor,
              const int64_t* __restrict__ piv_tile, const int64_t* __restrict__ piv_off,
              int j0, int j1, int forward, int64_t col_lo, int64_t col_hi)
 {
@@ -53,7 +58,7 @@ laswp_kernel(double* const* __restrict__ tiles, int64_t ldt, int mb, int nb, int
     if (gc >= col_hi) return;
     const int64_t jt = gc / nb;
     const int cc = int(gc - jt * nb);
-    double* const* stack = tiles + jt * ldt;
+    T* const* stack = tiles + jt * ldt;
     const int64_t coff = colmajor ? int64_t(cc) * ld : cc;
     const int64_t rstr = colmajor ? 1 : ld;
     const int cnt = j1 - j0;
@@ -61,19 +66,20 @@ laswp_kernel(double* const* __restrict__ tiles, int64_t ldt, int mb, int nb, int
         const int e = forward ? s : cnt - 1 - s;
         const int r1 = j0 + e, r2 = s_piv[e];
         if (r1 == r2) continue;
-        double* p1 = stack[r1 / mb] + int64_t(r1 % mb) * rstr + coff;
-        double* p2 = stack[r2 / mb] + int64_t(r2 % mb) * rstr + coff;
-        const double t = *p1; *p1 = *p2; *p2 = t;
+        T* p1 = stack[r1 / mb] + int64_t(r1 % mb) * rstr + coff;
+        T* p2 = stack[r2 / mb] + int64_t(r2 % mb) * rstr + coff;
+        const T t = *p1; *p1 = *p2; *p2 = t;
     }
 }
 
-static int launch_laswp(double* const* tiles, int64_t ldt, int mb, int nb, int ld, int colmajor,
+template <typename T>
+int launch_laswp(T* const* tiles, int64_t ldt, int mb, int nb, int ld, int colmajor,
                         const int64_t* piv_tile, const int64_t* piv_off, int j0, int j1, int forward,
                         int64_t col_lo, int64_t col_hi, cudaStream_t s)
 {
     if (col_hi <= col_lo || j1 <= j0) return SB200_OK;
     const int64_t cols = col_hi - col_lo;
-    laswp_kernel<<<unsigned(ceil_div(cols, 256)), 256, size_t(j1 - j0) * sizeof(int), s>>>(
+    laswp_kernel<T><<<unsigned(ceil_div(cols, 256)), 256, size_t(j1 - j0) * sizeof(int), s>>>(
         tiles, ldt, mb, nb, ld, colmajor, piv_tile, piv_off, j0, j1, forward, col_lo, col_hi);
     return launch_status();
 }
@@ -82,11 +88,12 @@ static int launch_laswp(double* const* tiles, int64_t ldt, int mb, int nb, int l
 // Cooperative panel base block: columns [c0, c0+w) of the panel (tile stack `tiles`, panel rows
 // [c0, m_p) active), rows_per rows per CTA held in shared memory.
 // ------------------------------------------------------------------------------------------
+template <typename T>
 struct BaseArgs {
-    double* const* tiles;
+    T* const* tiles;
     int nb, m_p, c0, w, rows_per;
     int64_t* piv_tile; int64_t* piv_off;
-    double* gval; int* grow; double* gcand; double* gdiag;     // [2][G], [2][G], [2][G][PW], [2][PW]
+    T* gval; int* grow; T* gcand; T* gdiag;     // [2][G], [2][G], [2][G][PW], [2][PW]
     int* info; int info_base;
     int* rowmap;       // optional: rowmap[x] = panel row whose ORIGINAL content now sits at position x
     int kw_wide;       // > 0: the LAST CTA of the grid owns no rows and applies every interchange of this
@@ -94,13 +101,15 @@ struct BaseArgs {
                        // while the other CTAs go on factoring -- no laswp launches between blocks
 };
 
+template <typename T>
 __global__ void __launch_bounds__(PTHREADS)
-getrf_base_kernel(const BaseArgs a)
+getrf_base_kernel(const BaseArgs<T> a)
 {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ double blk[];                 // [w][RP]
-    __shared__ double s_prow[PW], s_drow[PW];
-    __shared__ double s_val[PTHREADS / 32];
+    extern __shared__ __align__(16) unsigned char blk_raw[];
+    T* blk = reinterpret_cast<T*>(blk_raw);          // [w][RP]
+    __shared__ T s_prow[PW], s_drow[PW];
+    __shared__ T s_val[PTHREADS / 32];
     __shared__ int    s_row[PTHREADS / 32];
     __shared__ int    s_p, s_w;
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -121,29 +130,29 @@ getrf_base_kernel(const BaseArgs a)
         const int d = a.c0 + j;                    // panel row of the diagonal entry
         const int par = j & 1;
         // ---- local candidate: first maximum of |a| over this CTA's rows below the diagonal
-        double best = -1.0;
+        T best = T(-1);
         int brow = INT_MAX;
         for (int lr = tid; lr < nr; lr += PTHREADS) {
             const int r = r_begin + lr;
             if (r > d) {
-                const double v = fabs(blk[j * RP + lr]);
+                const T v = fabs(blk[j * RP + lr]);
                 if (v > best) { best = v; brow = r; }      // rows ascend per thread: first max kept
             }
         }
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const T ov = __shfl_xor_sync(0xffffffffu, best, o);
             const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
             if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; }
         }
         if (lane == 0) { s_val[warp] = best; s_row[warp] = brow; }
         __syncthreads();
         if (warp == 0) {
-            best = lane < PTHREADS / 32 ? s_val[lane] : -1.0;
+            best = lane < PTHREADS / 32 ? s_val[lane] : T(-1);
             brow = lane < PTHREADS / 32 ? s_row[lane] : INT_MAX;
             #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const T ov = __shfl_xor_sync(0xffffffffu, best, o);
                 const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
                 if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; }
             }
@@ -160,22 +169,22 @@ getrf_base_kernel(const BaseArgs a)
 
         // ---- every CTA picks the same winner: diagonal first, then strictly larger candidates
         if (warp == 0) {
-            double bv = -1.0;
+            T bv = T(-1);
             int br = INT_MAX, bw = -1;
             for (int c = lane; c < G; c += 32) {
-                const double v = a.gval[par * G + c];
+                const T v = a.gval[par * G + c];
                 const int r = a.grow[par * G + c];
                 if (v > bv || (v == bv && r < br)) { bv = v; br = r; bw = c; }
             }
             #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const T ov = __shfl_xor_sync(0xffffffffu, bv, o);
                 const int orow = __shfl_xor_sync(0xffffffffu, br, o);
                 const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
                 if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; bw = ow; }
             }
             if (lane == 0) {
-                const double dv = fabs(a.gdiag[par * PW + j]);
+                const T dv = fabs(a.gdiag[par * PW + j]);
                 if (bv > dv) { s_p = br; s_w = bw; }        // strict: the diagonal wins ties (and NaN)
                 else         { s_p = d;  s_w = -1; }
             }
@@ -199,31 +208,31 @@ getrf_base_kernel(const BaseArgs a)
         if (a.kw_wide > 0 && b == G - 1 && p != d) {
             // thread t always handles panel columns t, t + PTHREADS, ...: the interchanges of one column
             // are applied in pivot order by one thread (rows d and p of later pivots may coincide)
-            double* rd_ = a.tiles[d / nb] + (d % nb);
-            double* rp_ = a.tiles[p / nb] + (p % nb);
+            T* rd_ = a.tiles[d / nb] + (d % nb);
+            T* rp_ = a.tiles[p / nb] + (p % nb);
             for (int c = tid; c < a.kw_wide; c += PTHREADS)
                 if (c < a.c0 || c >= a.c0 + a.w) {
-                    const double t0 = rd_[int64_t(c) * nb], t1 = rp_[int64_t(c) * nb];
+                    const T t0 = rd_[int64_t(c) * nb], t1 = rp_[int64_t(c) * nb];
                     rd_[int64_t(c) * nb] = t1;
                     rp_[int64_t(c) * nb] = t0;
                 }
         }
         __syncthreads();
-        const double pv = s_prow[j];
-        if (pv == 0.0) {
+        const T pv = s_prow[j];
+        if (pv == T(0)) {
             if (b == 0 && tid == 0 && *a.info == 0) *a.info = a.info_base + d + 1;
         }
         else {
-            const bool use_rcp = fabs(pv) >= DBL_MIN;
-            const double rcp = 1.0 / pv;
+            const bool use_rcp = fabs(pv) >= tiny_of<T>();
+            const T rcp = T(1) / pv;
             for (int lr = tid; lr < nr; lr += PTHREADS) {
                 const int r = r_begin + lr;
                 if (r > d) {
-                    double l = blk[j * RP + lr];
+                    T l = blk[j * RP + lr];
                     l = use_rcp ? l * rcp : l / pv;
                     blk[j * RP + lr] = l;
                     for (int c = j + 1; c < a.w; ++c)
-                        blk[c * RP + lr] = fma(-l, s_prow[c], blk[c * RP + lr]);
+                        blk[c * RP + lr] = fma_t(-l, s_prow[c], blk[c * RP + lr]);
                 }
             }
         }
@@ -253,8 +262,10 @@ int PanelScratch::init()
     W = reinterpret_cast<double*>(p);
     static thread_local bool attr_done[64] = {};
     if (! attr_done[dev & 63]) {
-        CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(PW * (PROWS_MAX | 1) * sizeof(double))));
+        CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(PW * (PROWS_MAX | 1) * sizeof(float))));
         attr_done[dev & 63] = true;
     }
     return SB200_OK;
@@ -272,8 +283,9 @@ static int panel_version()
 }
 
 namespace {
+template <typename T>
 struct PanelCtx {
-    double* const* stack; double* tile0; int ntile, nb, m_p, kw;
+    T* const* stack; T* tile0; int ntile, nb, m_p, kw;
     int64_t* piv_tile; int64_t* piv_off; int* dinfo; int info_base;
     PanelScratch* ps; cudaStream_t s; int* rowmap; PhaseTimer* pt;
 };
@@ -281,7 +293,8 @@ struct PanelCtx {
 
 // one cooperative launch: columns [c0, c0+w) over panel rows [c0, m_p), interchanges applied to all
 // kw panel columns by the extra (row-less) CTA
-static int panel_base_wide(const PanelCtx& x, int c0, int w)
+template <typename T>
+static int panel_base_wide(const PanelCtx<T>& x, int c0, int w)
 {
     const int active = x.m_p - c0;
     const int ctas = x.ps->max_ctas - 1;                       // one SM is kept for the interchange CTA
@@ -289,12 +302,13 @@ static int panel_base_wide(const PanelCtx& x, int c0, int w)
     rows_per = std::max(rows_per, PW);
     if (rows_per > PROWS_MAX) return SB200_ENOTSUP;
     const int G = int(ceil_div(active, rows_per));
-    BaseArgs a{x.stack, x.nb, x.m_p, c0, w, rows_per, x.piv_tile, x.piv_off,
-               x.ps->gval, x.ps->grow, x.ps->gcand, x.ps->gdiag, x.dinfo, x.info_base, x.rowmap, x.kw};
+    BaseArgs<T> a{x.stack, x.nb, x.m_p, c0, w, rows_per, x.piv_tile, x.piv_off,
+                  reinterpret_cast<T*>(x.ps->gval), x.ps->grow, reinterpret_cast<T*>(x.ps->gcand),
+                  reinterpret_cast<T*>(x.ps->gdiag), x.dinfo, x.info_base, x.rowmap, x.kw};
     void* args[] = {&a};
-    const size_t smem = size_t(w) * (rows_per | 1) * sizeof(double);
+    const size_t smem = size_t(w) * (rows_per | 1) * sizeof(T);
     x.pt->begin("pnl_base", x.s);
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel),
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel<T>),
                                                 dim3(G + 1), dim3(PTHREADS), args, smem, x.s);
     if (e != cudaSuccess) return int(e);
     SB_TRY(launch_status());
@@ -304,42 +318,43 @@ static int panel_base_wide(const PanelCtx& x, int c0, int w)
 
 // columns [cc, cc+n2) of the panel, given that columns [c0, c0+w1) are factored:
 //   U12 = L11^{-1} A12 (rows c0..c0+w1 of the top tile), then A22 -= L21 U12 on rows [c0+w1, m_p)
-static int panel_update(const PanelCtx& x, int c0, int w1, int cc, int n2)
+template <typename T>
+static int panel_update(const PanelCtx<T>& x, int c0, int w1, int cc, int n2)
 {
     if (n2 <= 0 || w1 <= 0) return SB200_OK;
     const int nb = x.nb;
     x.pt->begin("pnl_trsm", x.s);
-    SB_TRY(trsm_colmajor_d(true, true, 'N', true, w1, n2, 1.0, x.tile0 + c0 + int64_t(c0) * nb, nb,
-                           x.stack, c0 + int64_t(cc) * nb, nb, 1, x.ps->W, x.s));
+    SB_TRY(trsm_colmajor<T>(true, true, 'N', true, w1, n2, T(1), x.tile0 + c0 + int64_t(c0) * nb, nb,
+                           x.stack, c0 + int64_t(cc) * nb, nb, 1, reinterpret_cast<T*>(x.ps->W), x.s));
     x.pt->end(x.s);
     x.pt->begin("pnl_gemm", x.s);
-    const double* U12 = x.tile0 + c0 + int64_t(cc) * nb;
+    const T* U12 = x.tile0 + c0 + int64_t(cc) * nb;
     const int r0 = c0 + w1;                                   // first row of A22 (inside the top tile)
     const int top_rows = std::min(nb, x.m_p) - r0;
     if (top_rows > 0) {
-        GemmParamsD p{};
-        p.m = top_rows; p.n = n2; p.k = w1; p.alpha = -1.0; p.beta = 1.0; p.batch = 1;
+        GemmParamsT<T> p{};
+        p.m = top_rows; p.n = n2; p.k = w1; p.alpha = T(-1); p.beta = T(1); p.batch = 1;
         p.A0 = x.tile0 + r0 + int64_t(c0) * nb; p.lda = nb;
         p.B0 = U12; p.ldb = nb;
         p.C0 = x.tile0 + r0 + int64_t(cc) * nb; p.ldc = nb;
-        SB_TRY(launch_gemm_d('N', 'N', p, x.s));
+        SB_TRY(launch_gemm<T>('N', 'N', p, x.s));
     }
     const int full = (x.m_p % nb == 0) ? x.ntile - 1 : x.ntile - 2;      // full-height tiles below tile 0
     if (full > 0) {
-        GemmParamsD p{};
-        p.m = nb; p.n = n2; p.k = w1; p.alpha = -1.0; p.beta = 1.0; p.batch = full;
+        GemmParamsT<T> p{};
+        p.m = nb; p.n = n2; p.k = w1; p.alpha = T(-1); p.beta = T(1); p.batch = full;
         p.A = x.stack + 1; p.offA = int64_t(c0) * nb; p.lda = nb;
         p.B0 = U12; p.ldb = nb; p.strideB = 0;
         p.C = x.stack + 1; p.offC = int64_t(cc) * nb; p.ldc = nb;
-        SB_TRY(launch_gemm_d('N', 'N', p, x.s));
+        SB_TRY(launch_gemm<T>('N', 'N', p, x.s));
     }
     if (x.ntile > 1 && x.m_p % nb != 0) {
-        GemmParamsD p{};
-        p.m = x.m_p % nb; p.n = n2; p.k = w1; p.alpha = -1.0; p.beta = 1.0; p.batch = 1;
+        GemmParamsT<T> p{};
+        p.m = x.m_p % nb; p.n = n2; p.k = w1; p.alpha = T(-1); p.beta = T(1); p.batch = 1;
         p.A = x.stack + (x.ntile - 1); p.offA = int64_t(c0) * nb; p.lda = nb;
         p.B0 = U12; p.ldb = nb;
         p.C = x.stack + (x.ntile - 1); p.offC = int64_t(cc) * nb; p.ldc = nb;
-        SB_TRY(launch_gemm_d('N', 'N', p, x.s));
+        SB_TRY(launch_gemm<T>('N', 'N', p, x.s));
     }
     x.pt->end(x.s);
     return SB200_OK;
@@ -347,31 +362,34 @@ static int panel_update(const PanelCtx& x, int c0, int w1, int cc, int n2)
 
 // recursive LU of columns [c0, c0+w); on entry they carry every update of the columns left of c0 and
 // every interchange chosen so far; on return so do ALL panel columns (base kernels swap panel-wide)
-static int panel_recurse(const PanelCtx& x, int c0, int w)
+template <typename T>
+static int panel_recurse(const PanelCtx<T>& x, int c0, int w)
 {
-    if (w <= PW) return panel_base_wide(x, c0, w);
+    if (w <= PW) return panel_base_wide<T>(x, c0, w);
     int w1 = int(ceil_div(w / 2, PW)) * PW;
     if (w1 >= w) w1 = w - PW;
-    SB_TRY(panel_recurse(x, c0, w1));
-    SB_TRY(panel_update(x, c0, w1, c0 + w1, w - w1));
-    return panel_recurse(x, c0 + w1, w - w1);
+    SB_TRY(panel_recurse<T>(x, c0, w1));
+    SB_TRY(panel_update<T>(x, c0, w1, c0 + w1, w - w1));
+    return panel_recurse<T>(x, c0 + w1, w - w1);
 }
 
-static int getrf_panel_v2(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
+template <typename T>
+static int getrf_panel_v2(T* const* stack, T* tile0, int ntile, int nb, int m_p, int kw,
                           int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
                           PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph)
 {
     PhaseTimer off_timer;
     off_timer.on = false;
-    PanelCtx x{stack, tile0, ntile, nb, m_p, kw, piv_tile, piv_off, dinfo, info_base, &ps, s, rowmap,
+    PanelCtx<T> x{stack, tile0, ntile, nb, m_p, kw, piv_tile, piv_off, dinfo, info_base, &ps, s, rowmap,
                ph ? ph : &off_timer};
     const int diag_len = std::min(m_p, kw);
-    SB_TRY(panel_recurse(x, 0, diag_len));
+    SB_TRY(panel_recurse<T>(x, 0, diag_len));
     // wide last panel (m_p < kw): the columns right of the square part only get U = L^{-1} A
-    return panel_update(x, 0, diag_len, diag_len, kw - diag_len);
+    return panel_update<T>(x, 0, diag_len, diag_len, kw - diag_len);
 }
 
-static int getrf_panel_v1(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
+template <typename T>
+static int getrf_panel_v1(T* const* stack, T* tile0, int ntile, int nb, int m_p, int kw,
                   int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
                   PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph)
 {
@@ -386,91 +404,93 @@ static int getrf_panel_v1(double* const* stack, double* tile0, int ntile, int nb
         rows_per = std::max(rows_per, PW);
         if (rows_per > PROWS_MAX) return SB200_ENOTSUP;       // panel taller than 148 * 768 rows
         const int G = int(ceil_div(active, rows_per));
-        BaseArgs a{stack, nb, m_p, c0, w, rows_per, piv_tile, piv_off,
-                   ps.gval, ps.grow, ps.gcand, ps.gdiag, dinfo, info_base, rowmap};
+        BaseArgs<T> a{stack, nb, m_p, c0, w, rows_per, piv_tile, piv_off,
+                      reinterpret_cast<T*>(ps.gval), ps.grow, reinterpret_cast<T*>(ps.gcand),
+                      reinterpret_cast<T*>(ps.gdiag), dinfo, info_base, rowmap, 0};
         void* args[] = {&a};
-        const size_t smem = size_t(w) * (rows_per | 1) * sizeof(double);
+        const size_t smem = size_t(w) * (rows_per | 1) * sizeof(T);
         pt.begin("pnl_base", s);
-        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel),
+        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel<T>),
                                                     dim3(G), dim3(PTHREADS), args, smem, s);
         if (e != cudaSuccess) return int(e);
         SB_TRY(launch_status());
         pt.end(s);
         // interchanges of this block applied to the rest of the panel (left and right of the block)
         pt.begin("pnl_laswp", s);
-        SB_TRY(launch_laswp(stack, 0, nb, nb, nb, 1, piv_tile, piv_off, c0, c0 + w, 1, 0, c0, s));
-        SB_TRY(launch_laswp(stack, 0, nb, nb, nb, 1, piv_tile, piv_off, c0, c0 + w, 1, c0 + w, kw, s));
+        SB_TRY(launch_laswp<T>(stack, 0, nb, nb, nb, 1, piv_tile, piv_off, c0, c0 + w, 1, 0, c0, s));
+        SB_TRY(launch_laswp<T>(stack, 0, nb, nb, nb, 1, piv_tile, piv_off, c0, c0 + w, 1, c0 + w, kw, s));
         pt.end(s);
         const int rest = kw - c0 - w;
         if (rest <= 0) continue;
         // U12 = L11^{-1} A12  (top tile, rows c0..c0+w)
         pt.begin("pnl_trsm", s);
-        SB_TRY(trsm_colmajor_d(true, true, 'N', true, w, rest, 1.0, tile0 + c0 + int64_t(c0) * nb, nb,
-                               stack, c0 + int64_t(c0 + w) * nb, nb, 1, ps.W, s));
+        SB_TRY(trsm_colmajor<T>(true, true, 'N', true, w, rest, T(1), tile0 + c0 + int64_t(c0) * nb, nb,
+                               stack, c0 + int64_t(c0 + w) * nb, nb, 1, reinterpret_cast<T*>(ps.W), s));
         pt.end(s);
         pt.begin("pnl_gemm", s);
         // A22 -= L21 U12
-        const double* U12 = tile0 + c0 + int64_t(c0 + w) * nb;
+        const T* U12 = tile0 + c0 + int64_t(c0 + w) * nb;
         const int top_rows = std::min(nb, m_p) - (c0 + w);
         if (top_rows > 0) {
-            GemmParamsD p{};
-            p.m = top_rows; p.n = rest; p.k = w; p.alpha = -1.0; p.beta = 1.0; p.batch = 1;
+            GemmParamsT<T> p{};
+            p.m = top_rows; p.n = rest; p.k = w; p.alpha = T(-1); p.beta = T(1); p.batch = 1;
             p.A0 = tile0 + (c0 + w) + int64_t(c0) * nb; p.lda = nb;
             p.B0 = U12; p.ldb = nb;
             p.C0 = tile0 + (c0 + w) + int64_t(c0 + w) * nb; p.ldc = nb;
-            SB_TRY(launch_gemm_d('N', 'N', p, s));
+            SB_TRY(launch_gemm<T>('N', 'N', p, s));
         }
         const int full = (m_p % nb == 0) ? ntile - 1 : ntile - 2;      // full-height tiles below tile 0
         if (full > 0) {
-            GemmParamsD p{};
-            p.m = nb; p.n = rest; p.k = w; p.alpha = -1.0; p.beta = 1.0; p.batch = full;
+            GemmParamsT<T> p{};
+            p.m = nb; p.n = rest; p.k = w; p.alpha = T(-1); p.beta = T(1); p.batch = full;
             p.A = stack + 1; p.offA = int64_t(c0) * nb; p.lda = nb;
             p.B0 = U12; p.ldb = nb; p.strideB = 0;
             p.C = stack + 1; p.offC = int64_t(c0 + w) * nb; p.ldc = nb;
-            SB_TRY(launch_gemm_d('N', 'N', p, s));
+            SB_TRY(launch_gemm<T>('N', 'N', p, s));
         }
         if (ntile > 1 && m_p % nb != 0) {
-            GemmParamsD p{};
-            p.m = m_p % nb; p.n = rest; p.k = w; p.alpha = -1.0; p.beta = 1.0; p.batch = 1;
+            GemmParamsT<T> p{};
+            p.m = m_p % nb; p.n = rest; p.k = w; p.alpha = T(-1); p.beta = T(1); p.batch = 1;
             p.A = stack + (ntile - 1); p.offA = int64_t(c0) * nb; p.lda = nb;
             p.B0 = U12; p.ldb = nb;
             p.C = stack + (ntile - 1); p.offC = int64_t(c0 + w) * nb; p.ldc = nb;
-            SB_TRY(launch_gemm_d('N', 'N', p, s));
+            SB_TRY(launch_gemm<T>('N', 'N', p, s));
         }
         pt.end(s);
     }
     return SB200_OK;
 }
 
+template <typename T>
+int getrf_panel(T* const* stack, T* tile0, int ntile, int nb, int m_p, int kw,
+                int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
+                PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph)
+{
+    return (panel_version() == 1 ? getrf_panel_v1<T> : getrf_panel_v2<T>)(
+        stack, tile0, ntile, nb, m_p, kw, piv_tile, piv_off, dinfo, info_base, ps, s, rowmap, ph);
+}
+
 int getrf_panel_d(double* const* stack, double* tile0, int ntile, int nb, int m_p, int kw,
                   int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
                   PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph)
 {
-    return (panel_version() == 1 ? getrf_panel_v1 : getrf_panel_v2)(
-        stack, tile0, ntile, nb, m_p, kw, piv_tile, piv_off, dinfo, info_base, ps, s, rowmap, ph);
+    return getrf_panel<double>(stack, tile0, ntile, nb, m_p, kw, piv_tile, piv_off, dinfo, info_base, ps, s, rowmap, ph);
 }
 
 // ------------------------------------------------------------------------------------------
-// driver (single GPU in this round; the multi-GPU variant gathers the panel on the diagonal owner)
+// driver, one rank (the p x q variant in getrf_dist.cu gathers the panel on the diagonal owner).
+// T = double: the FP64 path.  T = float: the low-precision factorisation of gesv_mixed
+// (src/gesv_mixed.cc:171-176); with use_tc05 its trailing / lookahead GEMMs run on the tcgen05
+// FP32-emulated kernel, L(:,k) and U(k,:) being split-packed once per step.
 // ------------------------------------------------------------------------------------------
-struct GBatch { int m, n, k; std::vector<const double*> A, B; std::vector<double*> C; size_t off = 0; };
-
-static void gb_add(std::vector<GBatch>& v, int m, int n, int k, const double* A, const double* B, double* C)
-{
-    for (auto& b : v)
-        if (b.m == m && b.n == n && b.k == k) { b.A.push_back(A); b.B.push_back(B); b.C.push_back(C); return; }
-    v.push_back(GBatch{m, n, k, {A}, {B}, {C}, 0});
-}
-
-int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
+template <typename T>
+int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_tc05)
 {
     Grid& g = *A.g;
-    if (A.kind != 'G' || A.layout != 'C') return SB200_EINVAL;
-    // SB200_GETRF_DIST=1 runs the p x q algorithm on a single rank too (test hook: same code path
-    // as the multi-GPU runs, minus the NCCL calls)
-    const char* fd = getenv("SB200_GETRF_DIST");
-    const bool force_dist = fd && atoi(fd) != 0;
-    if (g.size() > 1 || force_dist) return getrf_driver_dist(A, pivots_out, info_out);
+    if (A.kind != 'G' || A.layout != 'C' || A.dtype != TypeChar<T>::value) return SB200_EINVAL;
+    constexpr bool is_float = std::is_same<T, float>::value;
+    if (use_tc05 && ! is_float) return SB200_EINVAL;
+    if (g.size() > 1) return SB200_ENOTSUP;
     CUDA_TRY(cudaDeviceSynchronize());
     const int64_t mt = A.mt, nt = A.nt, nb = A.nb;
     const int ld = int(nb);
@@ -478,198 +498,234 @@ int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
     const int64_t mn = std::min(A.m, A.n);
     if (mn == 0) { if (info_out) *info_out = 0; return SB200_OK; }
 
+    // packed operands of the tcgen05 path: L(i,k) in slot [k & 1][i], U(k,j) in slot [k & 1][j]
+    DevBuf packA, packB;
+    const size_t pa_bytes = use_tc05 ? tc05_packed_bytes('A', nb, nb) : 0;
+    const size_t pb_bytes = use_tc05 ? tc05_packed_bytes('B', nb, nb) : 0;
+    if (use_tc05) {
+        SB_TRY(packA.alloc(size_t(2) * mt * pa_bytes));
+        SB_TRY(packB.alloc(size_t(2) * nt * pb_bytes));
+    }
+    auto pkA = [&](int64_t i, int64_t k) { return packA.as<unsigned char>() + ((k & 1) * mt + i) * pa_bytes; };
+    auto pkB = [&](int64_t j, int64_t k) { return packB.as<unsigned char>() + ((k & 1) * nt + j) * pb_bytes; };
+
     // tile pointer tables: column-major (stacks of a block column) and row-major (block rows)
-    std::vector<double*> tbl(size_t(mt * nt)), tblT(size_t(mt * nt));
+    std::vector<T*> tbl(size_t(mt * nt)), tblT(size_t(mt * nt));
     for (int64_t j = 0; j < nt; ++j)
         for (int64_t i = 0; i < mt; ++i) {
-            tbl[size_t(i + j * mt)] = A.tile(i, j);
-            tblT[size_t(j + i * nt)] = A.tile(i, j);
+            tbl[size_t(i + j * mt)] = A.tile_as<T>(i, j);
+            tblT[size_t(j + i * nt)] = A.tile_as<T>(i, j);
         }
-    // per-step GEMM batches: lookahead column k+1 and trailing columns >= k+2
-    struct Step { std::vector<GBatch> la, tr; };
+    // per-step GEMM batches: lookahead column k+1 and trailing columns >= k+2; pack lists (tcgen05 path)
+    struct Step {
+        std::vector<Batch> la, tr;
+        std::vector<const void*> a_src, b_src;       // L(i,k), i > k (ragged last row at the end); U(k,j), j >= k+2 (ragged last col at the end)
+        std::vector<void*> a_dst, b_dst;
+        int a_full = 0, b_full = 0;
+        size_t a_src_off = 0, a_dst_off = 0, b_src_off = 0, b_dst_off = 0;
+    };
     std::vector<Step> steps(static_cast<size_t>(kt));
-    std::vector<const void*> hostptrs;
+    PlanBuffer pb;
     for (int64_t k = 0; k < kt; ++k) {
+        Step& s = steps[size_t(k)];
         const int kw = int(A.tile_nb(k));
         for (int64_t j = k + 1; j < nt; ++j)
-            for (int64_t i = k + 1; i < mt; ++i)
-                gb_add(j == k + 1 ? steps[k].la : steps[k].tr, int(A.tile_mb(i)), int(A.tile_nb(j)), kw,
-                       A.tile(i, k), A.tile(k, j), A.tile(i, j));
-        for (auto* lst : {&steps[k].la, &steps[k].tr})
-            for (auto& b : *lst) {
-                b.off = hostptrs.size();
-                hostptrs.insert(hostptrs.end(), b.A.begin(), b.A.end());
-                hostptrs.insert(hostptrs.end(), b.B.begin(), b.B.end());
-                hostptrs.insert(hostptrs.end(), b.C.begin(), b.C.end());
+            for (int64_t i = k + 1; i < mt; ++i) {
+                const void* a = use_tc05 ? static_cast<const void*>(pkA(i, k)) : A.tile_as<T>(i, k);
+                const void* b = use_tc05 ? static_cast<const void*>(pkB(j, k)) : A.tile_as<T>(k, j);
+                batch_add(j == k + 1 ? s.la : s.tr, int(A.tile_mb(i)), int(A.tile_nb(j)), kw, 0, a, b, A.tile_as<T>(i, j));
             }
+        if (use_tc05 && k + 1 < nt) {
+            for (int64_t i = k + 1; i < mt; ++i) {
+                s.a_src.push_back(A.tile_as<T>(i, k)); s.a_dst.push_back(pkA(i, k));
+                if (A.tile_mb(i) == nb) ++s.a_full;
+            }
+            for (int64_t j = k + 2; j < nt; ++j) {
+                s.b_src.push_back(A.tile_as<T>(k, j)); s.b_dst.push_back(pkB(j, k));
+                if (A.tile_nb(j) == nb) ++s.b_full;
+            }
+        }
+        pb.reserve(s.la);
+        pb.reserve(s.tr);
+        s.a_src_off = pb.push(s.a_src); s.a_dst_off = pb.push(s.a_dst);
+        s.b_src_off = pb.push(s.b_src); s.b_dst_off = pb.push(s.b_dst);
     }
-    void** dplan = nullptr; double** dtbl = nullptr; double** dtblT = nullptr;
-    int64_t* dpiv = nullptr; int* dinfo = nullptr; double* Wt = nullptr;
-    auto cleanup = [&] {
-        if (dplan) cudaFree(dplan); if (dtbl) cudaFree(dtbl); if (dtblT) cudaFree(dtblT);
-        if (dpiv) cudaFree(dpiv); if (dinfo) cudaFree(dinfo); if (Wt) cudaFree(Wt);
-    };
-    struct Guard { decltype(cleanup)& f; ~Guard() { f(); } } guard{cleanup};
-    CUDA_TRY(cudaMalloc(&dplan, std::max<size_t>(hostptrs.size(), 1) * sizeof(void*)));
-    CUDA_TRY(cudaMalloc(&dtbl, tbl.size() * sizeof(double*)));
-    CUDA_TRY(cudaMalloc(&dtblT, tblT.size() * sizeof(double*)));
-    CUDA_TRY(cudaMalloc(&dpiv, size_t(2 * kt * nb) * sizeof(int64_t)));
-    CUDA_TRY(cudaMalloc(&dinfo, sizeof(int)));
-    CUDA_TRY(cudaMalloc(&Wt, size_t(ceil_div(nb, 64)) * 64 * 64 * sizeof(double)));
-    int64_t* dpiv_tile = dpiv;
-    int64_t* dpiv_off = dpiv + kt * nb;
+    const size_t tbl_off = pb.push(tbl), tblT_off = pb.push(tblT);
+
+    DevBuf piv, dinfo, wt;
+    SB_TRY(piv.alloc(size_t(2 * kt * nb) * sizeof(int64_t)));
+    SB_TRY(dinfo.alloc(sizeof(int)));
+    SB_TRY(wt.alloc(size_t(ceil_div(nb, 64)) * 64 * 64 * sizeof(T)));
+    int64_t* dpiv_tile = piv.as<int64_t>();
+    int64_t* dpiv_off = dpiv_tile + kt * nb;
+    T* Wt = wt.as<T>();
 
     PanelScratch ps;
     SB_TRY(ps.init());
-    cudaStream_t P = nullptr, T = nullptr;
-    int lo, hi;
-    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CUDA_TRY(cudaStreamCreateWithPriority(&P, cudaStreamNonBlocking, hi));
-    CUDA_TRY(cudaStreamCreateWithPriority(&T, cudaStreamNonBlocking, lo));
-    std::vector<cudaEvent_t> ev(size_t(2 * kt));
-    for (auto& e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    std::vector<cudaEvent_t> tev, pev;
-    auto ptime = [&](cudaStream_t st) -> int {
-        cudaEvent_t e;
-        CUDA_TRY(cudaEventCreate(&e));
-        pev.push_back(e);
-        CUDA_TRY(cudaEventRecord(e, st));
-        return SB200_OK;
-    };
-    cudaEvent_t t0, t1;
-    CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
-    auto P_done = [&](int64_t k) { return ev[size_t(k)]; };
-    auto T_done = [&](int64_t k) { return ev[size_t(kt + k)]; };
-    int status = SB200_OK;
+    Streams st;
+    SB_TRY(st.init(size_t(2 * kt)));
+    cudaStream_t P = st.panel, T_ = st.trail;
+    auto P_done = [&](int64_t k) { return st.ev[size_t(k)]; };
+    auto T_done = [&](int64_t k) { return st.ev[size_t(kt + k)]; };
     double trail_flops = 0; int64_t trail_launches = 0;
     PhaseTimer ph;
+    SB_TRY(pb.upload(P));
+    T* const* dtbl = pb.at<T>(tbl_off);
+    T* const* dtblT = pb.at<T>(tblT_off);
 
-    auto run_batches = [&](const std::vector<GBatch>& bs, cudaStream_t s) -> int {
-        for (const auto& b : bs) {
-            GemmParamsD p{};
-            const size_t cnt = b.C.size();
-            p.A = reinterpret_cast<const double* const*>(dplan + b.off);
-            p.B = reinterpret_cast<const double* const*>(dplan + b.off + cnt);
-            p.C = reinterpret_cast<double* const*>(dplan + b.off + 2 * cnt);
-            p.m = b.m; p.n = b.n; p.k = b.k; p.lda = ld; p.ldb = ld; p.ldc = ld;
-            p.alpha = -1.0; p.beta = 1.0; p.batch = int(cnt);
-            SB_TRY(launch_gemm_d('N', 'N', p, s));
+    auto run_batches = [&](const std::vector<Batch>& bs, cudaStream_t s) -> int {
+        if constexpr (is_float) {
+            if (use_tc05) return launch_batches_tc05(bs, pb, -1.0f, 1.0f, ld, s);
         }
+        return launch_batches<T>(bs, pb, 'N', 'N', T(-1), T(1), ld, 0, s);
+    };
+    // split-pack `cnt` tiles (full-size ones first, then the ragged one) for one operand role
+    auto pack = [&](int role, size_t src_off, size_t dst_off, int cnt, int full, int rows_full, int rows_last,
+                    int kw, cudaStream_t s) -> int {
+        if constexpr (is_float) {
+            for (int part = 0; part < 2; ++part) {
+                const int c = part == 0 ? full : cnt - full;
+                if (c <= 0) continue;
+                const size_t o = part == 0 ? 0 : size_t(full);
+                Tc05PackParams q{};
+                q.X = reinterpret_cast<const float* const*>(pb.dev + src_off + o);
+                q.P = reinterpret_cast<void* const*>(pb.dev + dst_off + o);
+                q.rows = part == 0 ? rows_full : rows_last; q.k = kw;
+                if (role == 'A') { q.rs = 1; q.ks = ld; q.ru = TC_BM; }     // L(i,k): operand row = tile row
+                else             { q.rs = ld; q.ks = 1; q.ru = TC_BN; }     // U(k,j): operand row = tile column
+                q.batch = c;
+                SB_TRY(launch_tc05_pack(q, s));
+            }
+        }
+        (void) role; (void) src_off; (void) dst_off; (void) cnt; (void) full; (void) rows_full; (void) rows_last; (void) kw; (void) s;
         return SB200_OK;
     };
     // row-k solve U(k, j0..j1) = L_kk^{-1} A(k, j0..j1) on stream s with workspace W
-    auto row_trsm = [&](int64_t k, int64_t j0, int64_t j1, double* W, cudaStream_t s) -> int {
+    auto row_trsm = [&](int64_t k, int64_t j0, int64_t j1, T* W, cudaStream_t s) -> int {
         if (j1 <= j0) return SB200_OK;
         const int kw = int(std::min(A.tile_mb(k), A.tile_nb(k)));
         const int64_t jfull_end = (A.tile_nb(nt - 1) == nb) ? j1 : std::min(j1, nt - 1);
         if (jfull_end > j0)
-            SB_TRY(trsm_colmajor_d(true, true, 'N', true, kw, int(nb), 1.0, A.tile(k, k), ld,
-                                   dtblT + j0 + k * nt, 0, ld, int(jfull_end - j0), W, s));
+            SB_TRY(trsm_colmajor<T>(true, true, 'N', true, kw, int(nb), T(1), A.tile_as<T>(k, k), ld,
+                                    dtblT + j0 + k * nt, 0, ld, int(jfull_end - j0), W, s));
         if (jfull_end < j1)
-            SB_TRY(trsm_colmajor_d(true, true, 'N', true, kw, int(A.tile_nb(nt - 1)), 1.0, A.tile(k, k), ld,
-                                   dtblT + (nt - 1) + k * nt, 0, ld, 1, W, s));
+            SB_TRY(trsm_colmajor<T>(true, true, 'N', true, kw, int(A.tile_nb(nt - 1)), T(1), A.tile_as<T>(k, k), ld,
+                                    dtblT + (nt - 1) + k * nt, 0, ld, 1, W, s));
         return SB200_OK;
     };
 
-    auto body = [&]() -> int {
-        CUDA_TRY(cudaMemcpyAsync(dplan, hostptrs.data(), hostptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, P));
-        CUDA_TRY(cudaMemcpyAsync(dtbl, tbl.data(), tbl.size() * sizeof(double*), cudaMemcpyHostToDevice, P));
-        CUDA_TRY(cudaMemcpyAsync(dtblT, tblT.data(), tblT.size() * sizeof(double*), cudaMemcpyHostToDevice, P));
-        CUDA_TRY(cudaMemsetAsync(dinfo, 0, sizeof(int), P));
-        CUDA_TRY(cudaStreamSynchronize(P));
-        CUDA_TRY(cudaEventRecord(t0, P));
-        for (int64_t k = 0; k < kt; ++k) {
-            const int kw = int(A.tile_nb(k));
-            const int m_p = int(A.m - k * nb);
-            const int diag_len = std::min(m_p, kw);
-            int64_t* pt = dpiv_tile + k * nb;
-            int64_t* po = dpiv_off + k * nb;
-            double* const* stack_k = dtbl + k + k * mt;
-            // ---- panel k (column k already carries every earlier update: lookahead below)
-            SB_TRY(ptime(P));
-            SB_TRY(getrf_panel_d(stack_k, A.tile(k, k), int(mt - k), int(nb), m_p, kw, pt, po, dinfo, int(k * nb), ps, P,
-                                 nullptr, &ph));
-            SB_TRY(ptime(P));
-            CUDA_TRY(cudaEventRecord(P_done(k), P));
-            // ---- trailing update of columns >= k+2 and interchanges to the left, normal priority
-            CUDA_TRY(cudaStreamWaitEvent(T, P_done(k), 0));
-            SB_TRY(launch_laswp(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1, 0, k * nb, T));
-            if (k + 2 < nt) {
-                SB_TRY(launch_laswp(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1, (k + 2) * nb, A.n, T));
-                SB_TRY(row_trsm(k, k + 2, nt, Wt, T));
-                if (! steps[k].tr.empty()) {
-                    cudaEvent_t a0, a1;
-                    CUDA_TRY(cudaEventCreate(&a0)); CUDA_TRY(cudaEventCreate(&a1));
-                    tev.push_back(a0); tev.push_back(a1);
-                    CUDA_TRY(cudaEventRecord(a0, T));
-                    SB_TRY(run_batches(steps[k].tr, T));
-                    CUDA_TRY(cudaEventRecord(a1, T));
-                    for (const auto& b : steps[k].tr) trail_flops += 2.0 * b.m * b.n * b.k * double(b.C.size());
-                    trail_launches += int64_t(steps[k].tr.size());
-                }
-            }
-            CUDA_TRY(cudaEventRecord(T_done(k), T));
-            // ---- lookahead: bring column k+1 up to date on the panel stream
-            if (k + 1 < nt) {
-                if (k >= 1) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 1), 0));
-                ph.begin("la_swap_trsm", P);
-                SB_TRY(launch_laswp(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1,
-                                    (k + 1) * nb, std::min<int64_t>((k + 2) * nb, A.n), P));
-                SB_TRY(row_trsm(k, k + 1, k + 2, ps.W, P));
-                ph.end(P);
-                ph.begin("la_gemm", P);
-                SB_TRY(run_batches(steps[k].la, P));
-                ph.end(P);
+    CUDA_TRY(cudaMemsetAsync(dinfo.p, 0, sizeof(int), P));
+    CUDA_TRY(cudaStreamSynchronize(P));
+    CUDA_TRY(cudaEventRecord(st.t0, P));
+    for (int64_t k = 0; k < kt; ++k) {
+        Step& sk = steps[size_t(k)];
+        const int kw = int(A.tile_nb(k));
+        const int m_p = int(A.m - k * nb);
+        const int diag_len = std::min(m_p, kw);
+        int64_t* pt = dpiv_tile + k * nb;
+        int64_t* po = dpiv_off + k * nb;
+        T* const* stack_k = dtbl + k + k * mt;
+        // ---- panel k (column k already carries every earlier update: lookahead below)
+        SB_TRY(st.ptime(P));
+        SB_TRY(getrf_panel<T>(stack_k, A.tile_as<T>(k, k), int(mt - k), int(nb), m_p, kw, pt, po, dinfo.as<int>(),
+                              int(k * nb), ps, P, nullptr, &ph));
+        if (use_tc05 && ! sk.a_src.empty()) {
+            ph.begin("pack_L", P);
+            SB_TRY(pack('A', sk.a_src_off, sk.a_dst_off, int(sk.a_src.size()), sk.a_full, int(nb), int(A.tile_mb(mt - 1)), kw, P));
+            ph.end(P);
+        }
+        SB_TRY(st.ptime(P));
+        CUDA_TRY(cudaEventRecord(P_done(k), P));
+        // ---- trailing update of columns >= k+2 and interchanges to the left, normal priority
+        CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
+        SB_TRY(launch_laswp<T>(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1, 0, k * nb, T_));
+        if (k + 2 < nt) {
+            SB_TRY(launch_laswp<T>(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1, (k + 2) * nb, A.n, T_));
+            SB_TRY(row_trsm(k, k + 2, nt, Wt, T_));
+            if (use_tc05 && ! sk.b_src.empty())
+                SB_TRY(pack('B', sk.b_src_off, sk.b_dst_off, int(sk.b_src.size()), sk.b_full, int(nb), int(A.tile_nb(nt - 1)), kw, T_));
+            if (! sk.tr.empty()) {
+                SB_TRY(st.time_begin(T_));
+                SB_TRY(run_batches(sk.tr, T_));
+                SB_TRY(st.time_end(T_));
+                trail_flops += batches_flops(sk.tr, false);
+                trail_launches += int64_t(sk.tr.size());
             }
         }
-        CUDA_TRY(cudaStreamWaitEvent(P, T_done(kt - 1), 0));
-        CUDA_TRY(cudaEventRecord(t1, P));
-        CUDA_TRY(cudaStreamSynchronize(P));
-        CUDA_TRY(cudaStreamSynchronize(T));
-        return SB200_OK;
-    };
-    status = body();
-    ph.report("getrf", g.rank);
-    if (status == SB200_OK) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, t0, t1);
-        A.last_ms = ms;
-        double tms = 0;
-        for (size_t i = 0; i + 1 < tev.size(); i += 2) { float x = 0; if (cudaEventElapsedTime(&x, tev[i], tev[i + 1]) == cudaSuccess) tms += x; }
-        A.last_trail_ms = tms; A.last_trail_flops = trail_flops; A.last_trail_launches = trail_launches;
-        double pms = 0;
-        for (size_t i = 0; i + 1 < pev.size(); i += 2) { float x = 0; if (cudaEventElapsedTime(&x, pev[i], pev[i + 1]) == cudaSuccess) pms += x; }
-        A.last_panel_ms = pms;
-        int hinfo = 0;
-        cudaMemcpy(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost);
-        if (info_out) *info_out = hinfo;
-        if (pivots_out) {
-            std::vector<int64_t> ht(size_t(kt * nb)), ho(size_t(kt * nb));
-            cudaMemcpy(ht.data(), dpiv_tile, ht.size() * sizeof(int64_t), cudaMemcpyDeviceToHost);
-            cudaMemcpy(ho.data(), dpiv_off, ho.size() * sizeof(int64_t), cudaMemcpyDeviceToHost);
-            int64_t o = 0;
-            for (int64_t k = 0; k < kt; ++k) {
-                const int64_t dl = std::min(A.m - k * nb, A.tile_nb(k));
-                for (int64_t j = 0; j < dl && o < mn; ++j, ++o) {
-                    pivots_out[2 * o] = ht[size_t(k * nb + j)];
-                    pivots_out[2 * o + 1] = ho[size_t(k * nb + j)];
+        CUDA_TRY(cudaEventRecord(T_done(k), T_));
+        // ---- lookahead: bring column k+1 up to date on the panel stream
+        if (k + 1 < nt) {
+            if (k >= 1) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 1), 0));
+            ph.begin("la_swap_trsm", P);
+            SB_TRY(launch_laswp<T>(dtbl + k, mt, int(nb), int(nb), ld, 1, pt, po, 0, diag_len, 1,
+                                   (k + 1) * nb, std::min<int64_t>((k + 2) * nb, A.n), P));
+            SB_TRY(row_trsm(k, k + 1, k + 2, reinterpret_cast<T*>(ps.W), P));
+            if constexpr (is_float) {
+                if (use_tc05 && ! sk.la.empty()) {
+                    // U(k, k+1) packed on the panel stream into its own slot
+                    Tc05PackParams q{};
+                    q.X0 = A.tile_as<float>(k, k + 1); q.P0 = pkB(k + 1, k); q.strideX = 0; q.strideP = 0;
+                    q.rows = int(A.tile_nb(k + 1)); q.k = kw; q.rs = ld; q.ks = 1; q.ru = TC_BN; q.batch = 1;
+                    SB_TRY(launch_tc05_pack(q, P));
                 }
+            }
+            ph.end(P);
+            ph.begin("la_gemm", P);
+            SB_TRY(run_batches(sk.la, P));
+            ph.end(P);
+        }
+    }
+    CUDA_TRY(cudaStreamWaitEvent(P, T_done(kt - 1), 0));
+    CUDA_TRY(cudaEventRecord(st.t1, P));
+    CUDA_TRY(cudaStreamSynchronize(P));
+    CUDA_TRY(cudaStreamSynchronize(T_));
+    ph.report("getrf", g.rank);
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, st.t0, st.t1));
+    A.last_ms = ms;
+    A.last_trail_ms = st.timed_ms(); A.last_trail_flops = trail_flops; A.last_trail_launches = trail_launches;
+    A.last_panel_ms = st.panel_ms();
+    int hinfo = 0;
+    CUDA_TRY(cudaMemcpy(&hinfo, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (info_out) *info_out = hinfo;
+    if (pivots_out) {
+        std::vector<int64_t> ht(size_t(kt * nb)), ho(size_t(kt * nb));
+        CUDA_TRY(cudaMemcpy(ht.data(), dpiv_tile, ht.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(ho.data(), dpiv_off, ho.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        int64_t o = 0;
+        for (int64_t k = 0; k < kt; ++k) {
+            const int64_t dl = std::min(A.m - k * nb, A.tile_nb(k));
+            for (int64_t j = 0; j < dl && o < mn; ++j, ++o) {
+                pivots_out[2 * o] = ht[size_t(k * nb + j)];
+                pivots_out[2 * o + 1] = ho[size_t(k * nb + j)];
             }
         }
     }
-    for (auto e : ev) cudaEventDestroy(e);
-    for (auto e : tev) cudaEventDestroy(e);
-    for (auto e : pev) cudaEventDestroy(e);
-    cudaEventDestroy(t0); cudaEventDestroy(t1);
-    if (P) cudaStreamDestroy(P);
-    if (T) cudaStreamDestroy(T);
-    return status;
+    return SB200_OK;
 }
+
+int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
+{
+    // SB200_GETRF_DIST=1 runs the p x q algorithm on a single rank too (test hook: same code path
+    // as the multi-GPU runs, minus the NCCL calls)
+    const char* fd = getenv("SB200_GETRF_DIST");
+    const bool force_dist = fd && atoi(fd) != 0;
+    if (A.dtype != 'd') return SB200_EINVAL;
+    if (A.g->size() > 1 || force_dist) return getrf_driver_dist(A, pivots_out, info_out);
+    return getrf_driver_t<double>(A, pivots_out, info_out, false);
+}
+
+int getrf_driver_s(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_tc05)
+{
+    return getrf_driver_t<float>(A, pivots_out, info_out, use_tc05);
+}
+
+template int launch_laswp<double>(double* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);
+template int launch_laswp<float>(float* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);
 
 } // namespace sb200
 
 using namespace sb200;
-struct sb200_matrix_s { Matrix A; };
 
 extern "C" {
 
@@ -678,6 +734,22 @@ int sb200_getrf_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts
     (void) opts;     // inner blocking is fixed at 32, lookahead at 1, pivot threshold at 1.0
     if (! h) return SB200_EINVAL;
     return getrf_driver(h->A, pivots, info);
+}
+
+/* FP32 LU (1 x 1 grid): the low-precision factorisation of gesv_mixed.  sb200_getrf_tc05_s runs the
+ * trailing update on the tcgen05 FP32-emulated (3 x TF32) kernel. */
+int sb200_getrf_s(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
+{
+    (void) opts;
+    if (! h) return SB200_EINVAL;
+    return getrf_driver_s(h->A, pivots, info, false);
+}
+
+int sb200_getrf_tc05_s(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
+{
+    (void) opts;
+    if (! h) return SB200_EINVAL;
+    return getrf_driver_s(h->A, pivots, info, true);
 }
 
 int sb200_permute_rows_d(int layout, int forward, int64_t npiv,
@@ -689,8 +761,8 @@ int sb200_permute_rows_d(int layout, int forward, int64_t npiv,
     if (npiv == 0 || ncolblocks == 0 || ncols == 0) return SB200_OK;
     if (npiv > 0x7fffffff || tile_mb > 0x7fffffff || ld > 0x7fffffff) return SB200_EINVAL;
     // `ncols` columns per tile, block columns are `ncols` wide
-    return launch_laswp(dTiles, mt, int(tile_mb), int(ncols), int(ld), layout == 'C', d_piv_tile, d_piv_off,
-                        0, int(npiv), forward != 0, 0, ncolblocks * ncols, cudaStream_t(stream));
+    return launch_laswp<double>(dTiles, mt, int(tile_mb), int(ncols), int(ld), layout == 'C', d_piv_tile, d_piv_off,
+                                0, int(npiv), forward != 0, 0, ncolblocks * ncols, cudaStream_t(stream));
 }
 
 } // extern "C"

@@ -30,5 +30,13 @@ int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, doub
                     double* W, cudaStream_t stream);
 
 int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out);
+int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out);                      // FP64, any grid
+int getrf_driver_s(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_tc05);     // FP32, 1 x 1 grid
+
+// fused row interchanges of one panel over a block-column range (getrf.cu)
+template <typename T>
+int launch_laswp(T* const* tiles, int64_t ldt, int mb, int nb, int ld, int colmajor,
+                 const int64_t* piv_tile, const int64_t* piv_off, int j0, int j1, int forward,
+                 int64_t col_lo, int64_t col_hi, cudaStream_t s);
 
 } // namespace sb200

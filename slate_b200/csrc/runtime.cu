@@ -1,31 +1,18 @@
-// runtime.cu -- grid, tile matrix, generators, host<->device movement, potrf and gemm drivers.
-// See runtime.hh for the mapping to the reference.
-#include "runtime.hh"
-#include "gemm_dmma.cuh"
+// runtime.cu -- grid, tile matrix, generators, host<->device movement, and the potrf / gemm / herk
+// drivers for all four scalar types.  See runtime.hh for the mapping to the reference.
+#include "runtime_internal.hh"
 #include <algorithm>
 #include <climits>
 #include <cstdio>
 #include <cstring>
-#include <map>
-#include <tuple>
+#include <type_traits>
 
 namespace sb200 {
 
-// from factor_small.cu
-int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, double alpha,
-                    const double* T, int ldt, double* const* dB, int64_t offB, int ldb, int batch,
-                    double* W, cudaStream_t stream);
-int potrf_tile_lower_d(int n, double* A, int lda, int* dinfo, int info_base, double* W, cudaStream_t stream);
-
-#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return int(e_); } while (0)
-#define NCCL_TRY(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) { \
-    fprintf(stderr, "slate_b200: NCCL error %s at %s:%d\n", ncclGetErrorString(r_), __FILE__, __LINE__); \
-    return SB200_ENCCL; } } while (0)
-#define SB_TRY(x) do { int s_ = (x); if (s_ != SB200_OK) return s_; } while (0)
-
 // ------------------------------------------------------------------------------------------
 // Philox-2x64 test-matrix generator on the device, bit-identical to the reference's matgen
-// (matgen/random.cc:54-77 philox_2x64, :83-91 rand_to_real, generate_type_rand.hh:28-79).
+// (matgen/random.cc:54-77 philox_2x64, :83-91 rand_to_real, :96-112 generate_float: complex takes
+// (re, im) from the two Philox words; generate_type_rand.hh:28-79).
 // One thread per element of one tile; grid.y = local tile.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox_2x64(uint64_t& s0, uint64_t& s1, uint64_t key)
@@ -41,236 +28,179 @@ __device__ __forceinline__ void philox_2x64(uint64_t& s0, uint64_t& s1, uint64_t
     }
 }
 
-struct TileDesc { double* ptr; int64_t i0, j0; int mb, nbc; };
+struct TileDesc { void* ptr; int64_t i0, j0; int mb, nbc; };
 
+__device__ __forceinline__ double bits_to_real(uint64_t b, double) { return double(b >> 11) * (1.0 / 9007199254740992.0); }
+__device__ __forceinline__ float  bits_to_real(uint64_t b, float)  { return float(b >> 40) * (1.0f / 16777216.0f); }
+
+template <typename T> __device__ __forceinline__ T make_elem(uint64_t s0, uint64_t s1, typename RealOf<T>::type add);
+template <> __device__ __forceinline__ float  make_elem<float>(uint64_t s0, uint64_t, float add)   { return bits_to_real(s0, 0.f) + add; }
+template <> __device__ __forceinline__ double make_elem<double>(uint64_t s0, uint64_t, double add) { return bits_to_real(s0, 0.0) + add; }
+template <> __device__ __forceinline__ cuFloatComplex make_elem<cuFloatComplex>(uint64_t s0, uint64_t s1, float add)
+{
+    return make_cuFloatComplex(bits_to_real(s0, 0.f) + add, bits_to_real(s1, 0.f));
+}
+template <> __device__ __forceinline__ cuDoubleComplex make_elem<cuDoubleComplex>(uint64_t s0, uint64_t s1, double add)
+{
+    return make_cuDoubleComplex(bits_to_real(s0, 0.0) + add, bits_to_real(s1, 0.0));
+}
+
+template <typename T>
 __global__ void generate_kernel(const TileDesc* __restrict__ tiles, int ld, int64_t seed,
                                 int dominant, double diag_add)
 {
+    using R = typename RealOf<T>::type;
     const TileDesc t = tiles[blockIdx.y];
     const int total = t.mb * t.nbc;
+    T* __restrict__ out = static_cast<T*>(t.ptr);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int i = e % t.mb, j = e / t.mb;
         uint64_t s0 = uint64_t(t.i0 + i), s1 = uint64_t(t.j0 + j);
         philox_2x64(s0, s1, uint64_t(seed));
-        double v = double(s0 >> 11) * (1.0 / 9007199254740992.0);     // 53 bits -> [0, 1)
-        if (dominant && (t.i0 + i == t.j0 + j)) v += diag_add;
-        t.ptr[i + int64_t(j) * ld] = v;
+        const R add = (dominant && (t.i0 + i == t.j0 + j)) ? R(diag_add) : R(0);
+        out[i + int64_t(j) * ld] = make_elem<T>(s0, s1, add);
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// batches: tiles of one step grouped by (m, n, k, tri) -- the reference's "regions"
-// (src/internal/internal_batch.hh:169-347), built once per driver call for all steps.
-// ------------------------------------------------------------------------------------------
-struct Batch {
-    int m, n, k, tri;
-    std::vector<const double*> A, B;
-    std::vector<double*> C;
-    size_t off = 0;                 // offset (in pointers) of A | B | C blocks in the device plan
-};
-
-static void batch_add(std::vector<Batch>& v, int m, int n, int k, int tri,
-                      const double* A, const double* B, double* C)
+template <typename T>
+static int generate_t(Matrix& A, int kind_code, int64_t seed, cudaStream_t s)
 {
-    for (auto& b : v)
-        if (b.m == m && b.n == n && b.k == k && b.tri == tri) {
-            b.A.push_back(A); b.B.push_back(B); b.C.push_back(C);
-            return;
-        }
-    Batch b{m, n, k, tri, {A}, {B}, {C}, 0};
-    v.push_back(std::move(b));
+    std::vector<TileDesc> td;
+    for (int64_t j = A.g->pcol; j < A.nt; j += A.g->q)
+        for (int64_t i = A.g->prow; i < A.mt; i += A.g->p)
+            if (A.stored(i, j))
+                td.push_back({A.tile_as<T>(i, j), i * A.nb, j * A.nb, int(A.tile_mb(i)), int(A.tile_nb(j))});
+    if (td.empty()) return SB200_OK;
+    TileDesc* dtd = nullptr;
+    CUDA_TRY(cudaMalloc(&dtd, td.size() * sizeof(TileDesc)));
+    cudaError_t ce = cudaMemcpyAsync(dtd, td.data(), td.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s);
+    int status = ce == cudaSuccess ? SB200_OK : int(ce);
+    for (size_t o = 0; o < td.size() && status == SB200_OK; o += 32768) {
+        const unsigned cnt = unsigned(std::min<size_t>(32768, td.size() - o));
+        generate_kernel<T><<<dim3(32, cnt), 256, 0, s>>>(dtd + o, int(A.nb), seed, kind_code, double(A.n));
+        status = launch_status();
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(dtd);
+    return status;
 }
 
-struct PlanBuffer {
-    std::vector<const void*> host;
-    void** dev = nullptr;
-    size_t reserve(std::vector<Batch>& bs)
-    {
-        size_t first = host.size();
-        for (auto& b : bs) {
-            b.off = host.size();
-            host.insert(host.end(), b.A.begin(), b.A.end());
-            host.insert(host.end(), b.B.begin(), b.B.end());
-            host.insert(host.end(), b.C.begin(), b.C.end());
-        }
-        return first;
-    }
-    size_t push(const std::vector<double*>& v)
-    {
-        size_t o = host.size();
-        host.insert(host.end(), v.begin(), v.end());
-        return o;
-    }
-    int upload(cudaStream_t s)
-    {
-        if (host.empty()) return SB200_OK;
-        CUDA_TRY(cudaMalloc(&dev, host.size() * sizeof(void*)));
-        CUDA_TRY(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(void*), cudaMemcpyHostToDevice, s));
-        return SB200_OK;
-    }
-    ~PlanBuffer() { if (dev) cudaFree(dev); }
+// panel workspace slot of tile row i for step k (multi-rank): [k & 1][i % p][i / p]
+template <typename T>
+struct PanelWs {
+    T* base = nullptr; int p = 1; int64_t rows_max = 0, te = 0;
+    T* at(int64_t i, int64_t k) const { return base + ((k & 1) * p * rows_max + (i % p) * rows_max + i / p) * te; }
 };
 
-static int launch_batches(const std::vector<Batch>& bs, const PlanBuffer& pb, int opA, int opB,
-                          double alpha, double beta, int ld, cudaStream_t s)
+// every rank receives tiles (i, k), i >= i_first, of block column k of A: p grouped broadcasts of
+// ranges that are contiguous in the root's pool (the reference's listBcast to a row+column rank
+// set, include/slate/BaseMatrix.hh:1998-2140, widened to all ranks)
+template <typename T>
+static int bcast_block_column(Grid& g, Matrix& A, int64_t k, int64_t i_first, const PanelWs<T>& ws, cudaStream_t s)
 {
-    for (const auto& b : bs) {
-        GemmParamsD p{};
-        const size_t cnt = b.C.size();
-        p.A = reinterpret_cast<const double* const*>(pb.dev + b.off);
-        p.B = reinterpret_cast<const double* const*>(pb.dev + b.off + cnt);
-        p.C = reinterpret_cast<double* const*>(pb.dev + b.off + 2 * cnt);
-        p.m = b.m; p.n = b.n; p.k = b.k; p.lda = ld; p.ldb = ld; p.ldc = ld;
-        p.alpha = alpha; p.beta = beta; p.batch = int(cnt); p.tri = b.tri;
-        SB_TRY(launch_gemm_d(opA, opB, p, s));
+    const int64_t mt = A.mt, te = A.tile_elems();
+    NCCL_TRY(ncclGroupStart());
+    for (int r = 0; r < g.p; ++r) {
+        int64_t i0 = i_first + ((r - i_first) % g.p + g.p) % g.p;
+        if (i0 >= mt) continue;
+        const int64_t cnt = (mt - 1 - i0) / g.p + 1;
+        const int root = g.rank_of(i0, k);
+        const T* src = (g.rank == root) ? A.tile_as<T>(i0, k) : ws.at(i0, k);
+        NCCL_TRY(ncclBroadcast(src, ws.at(i0, k), size_t(cnt * te) * sizeof(T), ncclChar, root, g.world, s));
     }
+    NCCL_TRY(ncclGroupEnd());
     return SB200_OK;
 }
-
-static double batches_flops(const std::vector<Batch>& bs)
-{
-    double f = 0;
-    for (const auto& b : bs) {
-        // ALGORITHMIC flops: a triangle-masked (herk/syrk diagonal) tile counts n(n+1)k
-        // (blaspp/include/blas/flops.hh syrk), whatever the kernel computes above the diagonal
-        const double per = b.tri ? double(b.n) * (b.n + 1.0) * b.k : 2.0 * b.m * b.n * b.k;
-        f += per * double(b.C.size());
-    }
-    return f;
-}
-
-static int64_t batches_launches(const std::vector<Batch>& bs) { return int64_t(bs.size()); }
-
-struct Streams {
-    cudaStream_t panel = nullptr, trail = nullptr;
-    std::vector<cudaEvent_t> ev;
-    std::vector<cudaEvent_t> tev;          // timing event pairs around the trailing-update launches
-    std::vector<cudaEvent_t> pev;          // timing event pairs around the panel work of every step
-    int ptime(cudaStream_t s)
-    {
-        cudaEvent_t e;
-        CUDA_TRY(cudaEventCreate(&e));
-        pev.push_back(e);
-        CUDA_TRY(cudaEventRecord(e, s));
-        return SB200_OK;
-    }
-    double panel_ms()
-    {
-        double tot = 0;
-        for (size_t i = 0; i + 1 < pev.size(); i += 2) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, pev[i], pev[i + 1]) == cudaSuccess) tot += ms;
-        }
-        return tot;
-    }
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    int time_begin(cudaStream_t s)
-    {
-        cudaEvent_t e;
-        CUDA_TRY(cudaEventCreate(&e));
-        tev.push_back(e);
-        CUDA_TRY(cudaEventRecord(e, s));
-        return SB200_OK;
-    }
-    int time_end(cudaStream_t s) { return time_begin(s); }
-    double timed_ms()
-    {
-        double tot = 0;
-        for (size_t i = 0; i + 1 < tev.size(); i += 2) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, tev[i], tev[i + 1]) == cudaSuccess) tot += ms;
-        }
-        return tot;
-    }
-    int init(size_t nevents)
-    {
-        int lo, hi;
-        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&panel, cudaStreamNonBlocking, hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&trail, cudaStreamNonBlocking, lo));
-        ev.resize(nevents);
-        for (auto& e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreate(&t0));
-        CUDA_TRY(cudaEventCreate(&t1));
-        return SB200_OK;
-    }
-    ~Streams()
-    {
-        for (auto e : ev) if (e) cudaEventDestroy(e);
-        for (auto e : tev) if (e) cudaEventDestroy(e);
-        for (auto e : pev) if (e) cudaEventDestroy(e);
-        if (t0) cudaEventDestroy(t0);
-        if (t1) cudaEventDestroy(t1);
-        if (panel) cudaStreamDestroy(panel);
-        if (trail) cudaStreamDestroy(trail);
-    }
-};
-
-struct DevBuf {
-    void* p = nullptr;
-    int alloc(size_t bytes) { CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 16)); return SB200_OK; }
-    ~DevBuf() { if (p) cudaFree(p); }
-};
 
 // ------------------------------------------------------------------------------------------
 // potrf: right-looking tile Cholesky with lookahead 1, lower.
 // reference schedule: src/potrf.cc:84-195 (panel task = potrf + tileBcast + trsm + listBcastMT,
 // lookahead task = herk/gemm on column k+1, trailing task = herk on the rest).
+// use_tc05 (float only): the trailing / lookahead updates run on the tcgen05 FP32-emulated kernel
+// (gemm_tc05.cu); the factored panel is split-packed once per step (A-side and B-side units).
 // ------------------------------------------------------------------------------------------
-int potrf_driver(Matrix& A, int64_t* info_out)
+template <typename T>
+int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05)
 {
+    using R = typename RealOf<T>::type;
     Grid& g = *A.g;
-    if (A.kind != 'H' || A.layout != 'C' || A.m != A.n) return SB200_EINVAL;
+    if (A.kind != 'H' || A.layout != 'C' || A.m != A.n || A.dtype != TypeChar<T>::value) return SB200_EINVAL;
+    constexpr bool is_float = std::is_same<T, float>::value;
+    if (use_tc05 && ! is_float) return SB200_EINVAL;
     CUDA_TRY(cudaDeviceSynchronize());       // inputs may have been produced on any stream
     const int64_t nt = A.nt, nb = A.nb;
     const int ld = int(nb);
     const bool multi = g.size() > 1;
     const int64_t te = A.tile_elems();
     const int64_t rows_max = (A.mt + g.p - 1) / g.p;        // panel workspace slots per process row
+    const T one = from_real<T>(R(1)), minus_one = from_real<T>(R(-1));
+    const int opH = IsComplex<T>::value ? 'C' : 'T';
 
-    DevBuf ws, dbuf, work, dinfo;
+    DevBuf ws, dbuf, work, dinfo, packA, packB;
     if (multi) {
-        SB_TRY(ws.alloc(size_t(2) * g.p * rows_max * te * sizeof(double)));
-        SB_TRY(dbuf.alloc(size_t(2) * te * sizeof(double)));
+        SB_TRY(ws.alloc(size_t(2) * g.p * rows_max * te * sizeof(T)));
+        SB_TRY(dbuf.alloc(size_t(2) * te * sizeof(T)));
     }
-    SB_TRY(work.alloc(size_t(8) * 64 * 64 * sizeof(double) * 2));
+    SB_TRY(work.alloc(size_t(1 + ceil_div(nb, FACTOR_IB)) * FACTOR_IB * FACTOR_IB * sizeof(T)));
     SB_TRY(dinfo.alloc(sizeof(int)));
-    double* W_potrf = static_cast<double*>(work.p);
-    double* W_trsm  = W_potrf + 64 * 64;
+    T* W_potrf = work.as<T>();
+    T* W_trsm  = W_potrf + FACTOR_IB * FACTOR_IB;
+    PanelWs<T> pws{ws.as<T>(), g.p, rows_max, te};
 
-    auto pbuf = [&](int64_t i, int64_t k) -> double* {     // where step k's factored tile (i,k) is read from
-        if (! multi) return A.tile(i, k);
-        return static_cast<double*>(ws.p) + ((k & 1) * g.p * rows_max + (i % g.p) * rows_max + i / g.p) * te;
+    auto pbuf = [&](int64_t i, int64_t k) -> T* {     // where step k's factored tile (i,k) is read from
+        return multi ? pws.at(i, k) : A.tile_as<T>(i, k);
     };
+    // packed copies of panel tile i for step k (tcgen05 path): [k & 1][i]
+    const size_t pa_bytes = use_tc05 ? tc05_packed_bytes('A', nb, nb) : 0;
+    const size_t pb_bytes = use_tc05 ? tc05_packed_bytes('B', nb, nb) : 0;
+    if (use_tc05) {
+        SB_TRY(packA.alloc(size_t(2) * nt * pa_bytes));
+        SB_TRY(packB.alloc(size_t(2) * nt * pb_bytes));
+    }
+    auto pkA = [&](int64_t i, int64_t k) { return packA.as<unsigned char>() + ((k & 1) * nt + i) * pa_bytes; };
+    auto pkB = [&](int64_t i, int64_t k) { return packB.as<unsigned char>() + ((k & 1) * nt + i) * pb_bytes; };
 
     // ---- plan: every pointer batch of every step
     struct Step {
         std::vector<Batch> la, tr;           // lookahead column k+1 / trailing columns >= k+2
-        std::vector<double*> panel;          // local tiles (i,k), i > k, full height
-        std::vector<double*> panel_last;     // ragged last block row
-        size_t panel_off = 0, panel_last_off = 0;
+        std::vector<T*> panel;               // local tiles (i,k), i > k, full height
+        std::vector<T*> panel_last;          // ragged last block row
+        std::vector<const void*> pkA_src, pkB_src;   // tiles to pack (tcgen05 path), full height | last (ragged) at the end
+        std::vector<void*> pkA_dst, pkB_dst;
+        int pkA_full = 0, pkB_full = 0;      // how many of them are full-height tiles
+        size_t panel_off = 0, panel_last_off = 0, pkA_src_off = 0, pkA_dst_off = 0, pkB_src_off = 0, pkB_dst_off = 0;
     };
     std::vector<Step> steps(nt);
     PlanBuffer pb;
     for (int64_t k = 0; k < nt; ++k) {
         Step& s = steps[k];
         const int kw = int(A.tile_nb(k));
+        std::vector<char> needA(nt, 0), needB(nt, 0);
         for (int64_t j = k + 1; j < nt; ++j)
             for (int64_t i = j; i < nt; ++i) {
                 if (! A.is_local(i, j)) continue;
                 auto& dst = (j == k + 1) ? s.la : s.tr;
-                batch_add(dst, int(A.tile_mb(i)), int(A.tile_nb(j)), kw, i == j ? 1 : 0,
-                          pbuf(i, k), pbuf(j, k), A.tile(i, j));
+                const void* a = use_tc05 ? static_cast<const void*>(pkA(i, k)) : pbuf(i, k);
+                const void* b = use_tc05 ? static_cast<const void*>(pkB(j, k)) : pbuf(j, k);
+                batch_add(dst, int(A.tile_mb(i)), int(A.tile_nb(j)), kw, i == j ? 1 : 0, a, b, A.tile_as<T>(i, j));
+                needA[i] = 1; needB[j] = 1;
             }
         for (int64_t i = k + 1; i < nt; ++i)
             if (A.is_local(i, k)) {
-                if (A.tile_mb(i) == nb) s.panel.push_back(A.tile(i, k));
-                else                    s.panel_last.push_back(A.tile(i, k));
+                if (A.tile_mb(i) == nb) s.panel.push_back(A.tile_as<T>(i, k));
+                else                    s.panel_last.push_back(A.tile_as<T>(i, k));
+            }
+        if (use_tc05)
+            for (int64_t i = k + 1; i < nt; ++i) {          // tile nt-1 (possibly ragged) comes last
+                if (needA[i]) { s.pkA_src.push_back(pbuf(i, k)); s.pkA_dst.push_back(pkA(i, k)); if (A.tile_mb(i) == nb) ++s.pkA_full; }
+                if (needB[i]) { s.pkB_src.push_back(pbuf(i, k)); s.pkB_dst.push_back(pkB(i, k)); if (A.tile_mb(i) == nb) ++s.pkB_full; }
             }
         pb.reserve(s.la);
         pb.reserve(s.tr);
         s.panel_off = pb.push(s.panel);
         s.panel_last_off = pb.push(s.panel_last);
+        s.pkA_src_off = pb.push(s.pkA_src); s.pkA_dst_off = pb.push(s.pkA_dst);
+        s.pkB_src_off = pb.push(s.pkB_src); s.pkB_dst_off = pb.push(s.pkB_dst);
     }
 
     Streams st;
@@ -285,81 +215,106 @@ int potrf_driver(Matrix& A, int64_t* info_out)
     CUDA_TRY(cudaStreamSynchronize(st.panel));
     CUDA_TRY(cudaEventRecord(st.t0, st.panel));
 
+    auto update = [&](const std::vector<Batch>& bs, cudaStream_t s) -> int {
+        if constexpr (is_float) {
+            if (use_tc05) return launch_batches_tc05(bs, pb, -1.0f, 1.0f, ld, s);
+        }
+        return launch_batches<T>(bs, pb, 'N', opH, minus_one, one, ld, 1, s);
+    };
+    // split-pack the factored panel of step k for the tensor cores (both operand roles)
+    auto pack_panel = [&](Step& s, int kw, cudaStream_t P) -> int {
+        if constexpr (is_float) {
+            const int last_rows = int(A.tile_mb(nt - 1));
+            struct Side { int ru; size_t src, dst; int cnt, full; };
+            const Side sides[2] = {{TC_BM, s.pkA_src_off, s.pkA_dst_off, int(s.pkA_src.size()), s.pkA_full},
+                                   {TC_BN, s.pkB_src_off, s.pkB_dst_off, int(s.pkB_src.size()), s.pkB_full}};
+            for (const Side& sd : sides) {
+                for (int part = 0; part < 2; ++part) {
+                    const int cnt = part == 0 ? sd.full : sd.cnt - sd.full;
+                    if (cnt <= 0) continue;
+                    const size_t o = part == 0 ? 0 : size_t(sd.full);
+                    Tc05PackParams q{};
+                    q.X = reinterpret_cast<const float* const*>(pb.dev + sd.src + o);
+                    q.P = reinterpret_cast<void* const*>(pb.dev + sd.dst + o);
+                    q.rows = part == 0 ? int(nb) : last_rows; q.k = kw;
+                    q.rs = 1; q.ks = ld; q.ru = sd.ru; q.batch = cnt;
+                    SB_TRY(launch_tc05_pack(q, P));
+                }
+            }
+        }
+        (void) s; (void) kw; (void) P;
+        return SB200_OK;
+    };
+
     for (int64_t k = 0; k < nt; ++k) {
         Step& s = steps[k];
         const int kw = int(A.tile_nb(k));
         const int owner = g.rank_of(k, k);
         const bool in_col = (g.pcol == int(k % g.q));
-        cudaStream_t P = st.panel, T = st.trail;
+        cudaStream_t P = st.panel, T_ = st.trail;
 
         // -- lookahead update of column k by panel k-1 (after every older trailing update)
         if (k >= 1) {
             if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));
             ph.begin("la_update", P);
-            SB_TRY(launch_batches(steps[k - 1].la, pb, 'N', 'T', -1.0, 1.0, ld, P));
+            SB_TRY(update(steps[k - 1].la, P));
             ph.end(P);
         }
         // -- diagonal tile
         SB_TRY(st.ptime(P));
-        const double* Lkk = nullptr;
+        const T* Lkk = nullptr;
         ph.begin("potrf_tile", P);
         if (g.rank == owner)
-            SB_TRY(potrf_tile_lower_d(kw, A.tile(k, k), ld, static_cast<int*>(dinfo.p), int(k * nb), W_potrf, P));
+            SB_TRY(potrf_tile_lower<T>(kw, A.tile_as<T>(k, k), ld, dinfo.as<int>(), int(k * nb), W_potrf, P));
         ph.end(P);
         if (k + 1 < nt) {
             if (multi) {
-                double* db = static_cast<double*>(dbuf.p) + (k & 1) * te;
+                T* db = dbuf.as<T>() + (k & 1) * te;
                 if (in_col && g.p > 1) {
-                    const double* src = (g.rank == owner) ? A.tile(k, k) : db;
-                    NCCL_TRY(ncclBroadcast(src, db, size_t(te), ncclDouble, int(k % g.p), g.col_comm, P));
+                    const T* src = (g.rank == owner) ? A.tile_as<T>(k, k) : db;
+                    NCCL_TRY(ncclBroadcast(src, db, size_t(te) * sizeof(T), ncclChar, int(k % g.p), g.col_comm, P));
                     Lkk = db;
                 }
-                else if (in_col) Lkk = A.tile(k, k);
+                else if (in_col) Lkk = A.tile_as<T>(k, k);
             }
-            else Lkk = A.tile(k, k);
-            // -- panel solve A(i,k) <- A(i,k) L_kk^{-T}
+            else Lkk = A.tile_as<T>(k, k);
+            // -- panel solve A(i,k) <- A(i,k) L_kk^{-H}
             ph.begin("panel_trsm", P);
             if (in_col) {
                 if (! s.panel.empty())
-                    SB_TRY(trsm_colmajor_d(false, true, 'T', false, int(nb), kw, 1.0, Lkk, ld,
-                                           reinterpret_cast<double* const*>(pb.dev + s.panel_off), 0, ld,
-                                           int(s.panel.size()), W_trsm, P));
+                    SB_TRY(trsm_colmajor<T>(false, true, opH, false, int(nb), kw, one, Lkk, ld,
+                                            pb.at<T>(s.panel_off), 0, ld, int(s.panel.size()), W_trsm, P));
                 if (! s.panel_last.empty())
-                    SB_TRY(trsm_colmajor_d(false, true, 'T', false, int(A.tile_mb(nt - 1)), kw, 1.0, Lkk, ld,
-                                           reinterpret_cast<double* const*>(pb.dev + s.panel_last_off), 0, ld,
-                                           int(s.panel_last.size()), W_trsm, P));
+                    SB_TRY(trsm_colmajor<T>(false, true, opH, false, int(A.tile_mb(nt - 1)), kw, one, Lkk, ld,
+                                            pb.at<T>(s.panel_last_off), 0, ld, int(s.panel_last.size()), W_trsm, P));
             }
             ph.end(P);
             // -- panel broadcast: every rank receives the whole factored block column
             ph.begin("panel_bcast", P);
             if (multi) {
                 if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));   // ws[k&1] is free again
-                NCCL_TRY(ncclGroupStart());
-                for (int r = 0; r < g.p; ++r) {
-                    // tiles (i,k), i > k, i % p == r: contiguous in the root's pool
-                    int64_t i0 = k + 1 + ((r - (k + 1)) % g.p + g.p) % g.p;
-                    if (i0 >= nt) continue;
-                    const int64_t cnt = (nt - 1 - i0) / g.p + 1;
-                    const int root = g.rank_of(i0, k);
-                    const double* src = (g.rank == root) ? A.tile(i0, k) : pbuf(i0, k);
-                    NCCL_TRY(ncclBroadcast(src, pbuf(i0, k), size_t(cnt * te), ncclDouble, root, g.world, P));
-                }
-                NCCL_TRY(ncclGroupEnd());
+                SB_TRY(bcast_block_column<T>(g, A, k, k + 1, pws, P));
             }
             ph.end(P);
+            if (use_tc05) {
+                if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));   // pack[k&1] is free again
+                ph.begin("panel_pack", P);
+                SB_TRY(pack_panel(s, kw, P));
+                ph.end(P);
+            }
         }
         SB_TRY(st.ptime(P));
         CUDA_TRY(cudaEventRecord(P_done(k), P));
         // -- trailing update of columns >= k+2
-        CUDA_TRY(cudaStreamWaitEvent(T, P_done(k), 0));
+        CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
         if (! s.tr.empty()) {
-            SB_TRY(st.time_begin(T));
-            SB_TRY(launch_batches(s.tr, pb, 'N', 'T', -1.0, 1.0, ld, T));
-            SB_TRY(st.time_end(T));
-            trail_flops += batches_flops(s.tr);
-            trail_launches += batches_launches(s.tr);
+            SB_TRY(st.time_begin(T_));
+            SB_TRY(update(s.tr, T_));
+            SB_TRY(st.time_end(T_));
+            trail_flops += batches_flops(s.tr, IsComplex<T>::value);
+            trail_launches += int64_t(s.tr.size());
         }
-        CUDA_TRY(cudaEventRecord(T_done(k), T));
+        CUDA_TRY(cudaEventRecord(T_done(k), T_));
     }
     CUDA_TRY(cudaStreamWaitEvent(st.panel, T_done(nt - 1), 0));
     CUDA_TRY(cudaEventRecord(st.t1, st.panel));
@@ -396,11 +351,14 @@ int potrf_driver(Matrix& A, int64_t* info_out)
 // Step k: A(:,k) goes along process rows, B(k,:) down process columns (one step ahead of the
 // multiply, on the panel stream), then ONE batched launch updates every local C tile.
 // ------------------------------------------------------------------------------------------
-int gemm_driver(double alpha, Matrix& A, Matrix& B, double beta, Matrix& C)
+template <typename T>
+int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C)
 {
+    using R = typename RealOf<T>::type;
     Grid& g = *C.g;
     if (A.g != &g || B.g != &g) return SB200_EINVAL;
     if (A.kind != 'G' || B.kind != 'G' || C.kind != 'G') return SB200_EINVAL;
+    if (A.dtype != TypeChar<T>::value || B.dtype != A.dtype || C.dtype != A.dtype) return SB200_EINVAL;
     if (A.m != C.m || B.n != C.n || A.n != B.m || A.nb != C.nb || B.nb != C.nb) return SB200_EINVAL;
     const int64_t kt = A.nt, nb = C.nb, te = C.tile_elems();
     const int ld = int(nb);
@@ -409,16 +367,16 @@ int gemm_driver(double alpha, Matrix& A, Matrix& B, double beta, Matrix& C)
 
     DevBuf wsA, wsB;
     if (multi) {
-        SB_TRY(wsA.alloc(size_t(2) * C.mt_loc * te * sizeof(double)));
-        SB_TRY(wsB.alloc(size_t(2) * C.nt_loc * te * sizeof(double)));
+        SB_TRY(wsA.alloc(size_t(2) * C.mt_loc * te * sizeof(T)));
+        SB_TRY(wsB.alloc(size_t(2) * C.nt_loc * te * sizeof(T)));
     }
-    auto a_src = [&](int64_t i, int64_t k) -> double* {
-        if (! multi) return A.tile(i, k);
-        return static_cast<double*>(wsA.p) + ((k & 1) * C.mt_loc + (i - g.prow) / g.p) * te;
+    auto a_src = [&](int64_t i, int64_t k) -> T* {
+        if (! multi) return A.tile_as<T>(i, k);
+        return wsA.as<T>() + ((k & 1) * C.mt_loc + (i - g.prow) / g.p) * te;
     };
-    auto b_src = [&](int64_t k, int64_t j) -> double* {
-        if (! multi) return B.tile(k, j);
-        return static_cast<double*>(wsB.p) + ((k & 1) * C.nt_loc + (j - g.pcol) / g.q) * te;
+    auto b_src = [&](int64_t k, int64_t j) -> T* {
+        if (! multi) return B.tile_as<T>(k, j);
+        return wsB.as<T>() + ((k & 1) * C.nt_loc + (j - g.pcol) / g.q) * te;
     };
 
     std::vector<std::vector<Batch>> plan(kt);
@@ -427,7 +385,7 @@ int gemm_driver(double alpha, Matrix& A, Matrix& B, double beta, Matrix& C)
         for (int64_t j = g.pcol; j < C.nt; j += g.q)
             for (int64_t i = g.prow; i < C.mt; i += g.p)
                 batch_add(plan[k], int(C.tile_mb(i)), int(C.tile_nb(j)), int(A.tile_nb(k)), 0,
-                          a_src(i, k), b_src(k, j), C.tile(i, j));
+                          a_src(i, k), b_src(k, j), C.tile_as<T>(i, j));
         pb.reserve(plan[k]);
     }
     Streams st;
@@ -442,40 +400,40 @@ int gemm_driver(double alpha, Matrix& A, Matrix& B, double beta, Matrix& C)
     CUDA_TRY(cudaStreamWaitEvent(st.trail, st.t0, 0));
 
     for (int64_t k = 0; k < kt; ++k) {
-        cudaStream_t P = st.panel, T = st.trail;
+        cudaStream_t P = st.panel, T_ = st.trail;
         if (multi) {
             if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));
             NCCL_TRY(ncclGroupStart());
             if (C.mt_loc > 0 && g.q > 1) {
                 const int root = int(k % g.q);
-                const double* src = (g.pcol == root) ? A.tile(g.prow, k) : a_src(g.prow, k);
-                NCCL_TRY(ncclBroadcast(src, a_src(g.prow, k), size_t(C.mt_loc * te), ncclDouble, root, g.row_comm, P));
+                const T* src = (g.pcol == root) ? A.tile_as<T>(g.prow, k) : a_src(g.prow, k);
+                NCCL_TRY(ncclBroadcast(src, a_src(g.prow, k), size_t(C.mt_loc * te) * sizeof(T), ncclChar, root, g.row_comm, P));
             }
             if (g.p > 1) {
                 const int root = int(k % g.p);
                 for (int64_t j = g.pcol; j < C.nt; j += g.q) {
-                    const double* src = (g.prow == root) ? B.tile(k, j) : b_src(k, j);
-                    NCCL_TRY(ncclBroadcast(src, b_src(k, j), size_t(te), ncclDouble, root, g.col_comm, P));
+                    const T* src = (g.prow == root) ? B.tile_as<T>(k, j) : b_src(k, j);
+                    NCCL_TRY(ncclBroadcast(src, b_src(k, j), size_t(te) * sizeof(T), ncclChar, root, g.col_comm, P));
                 }
             }
             NCCL_TRY(ncclGroupEnd());
             // operands that did not need a broadcast are copied so that every tile is read from ws
             if (g.q == 1 && C.mt_loc > 0)
-                CUDA_TRY(cudaMemcpyAsync(a_src(g.prow, k), A.tile(g.prow, k), size_t(C.mt_loc * te) * sizeof(double),
+                CUDA_TRY(cudaMemcpyAsync(a_src(g.prow, k), A.tile_as<T>(g.prow, k), size_t(C.mt_loc * te) * sizeof(T),
                                          cudaMemcpyDeviceToDevice, P));
             if (g.p == 1)
                 for (int64_t j = g.pcol; j < C.nt; j += g.q)
-                    CUDA_TRY(cudaMemcpyAsync(b_src(k, j), B.tile(k, j), size_t(te) * sizeof(double),
+                    CUDA_TRY(cudaMemcpyAsync(b_src(k, j), B.tile_as<T>(k, j), size_t(te) * sizeof(T),
                                              cudaMemcpyDeviceToDevice, P));
             CUDA_TRY(cudaEventRecord(P_done(k), P));
-            CUDA_TRY(cudaStreamWaitEvent(T, P_done(k), 0));
+            CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
         }
-        SB_TRY(st.time_begin(T));
-        SB_TRY(launch_batches(plan[k], pb, 'N', 'N', alpha, k == 0 ? beta : 1.0, ld, T));
-        SB_TRY(st.time_end(T));
-        trail_flops += batches_flops(plan[k]);
-        trail_launches += batches_launches(plan[k]);
-        CUDA_TRY(cudaEventRecord(T_done(k), T));
+        SB_TRY(st.time_begin(T_));
+        SB_TRY(launch_batches<T>(plan[k], pb, 'N', 'N', alpha, k == 0 ? beta : from_real<T>(R(1)), ld, 0, T_));
+        SB_TRY(st.time_end(T_));
+        trail_flops += batches_flops(plan[k], IsComplex<T>::value);
+        trail_launches += int64_t(plan[k].size());
+        CUDA_TRY(cudaEventRecord(T_done(k), T_));
     }
     CUDA_TRY(cudaEventRecord(st.t1, st.trail));
     CUDA_TRY(cudaStreamSynchronize(st.trail));
@@ -489,12 +447,158 @@ int gemm_driver(double alpha, Matrix& A, Matrix& B, double beta, Matrix& C)
     return SB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// herk: C = alpha A A^H + beta C, C Hermitian (lower tiles), A general n x k
+// (reference: src/herk.cc:25-162 -> internal::herk<Devices>, src/internal/internal_herk.cc:355-536:
+// off-diagonal tiles by batched gemm, diagonal tiles by a per-tile herk loop).
+// Step kk: block column kk of A is broadcast to all ranks (one step ahead, panel stream), then ONE
+// batched launch per shape class updates every local lower tile, diagonal tiles triangle-masked.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int herk_driver(typename RealOf<T>::type alpha, Matrix& A, typename RealOf<T>::type beta, Matrix& C)
+{
+    using R = typename RealOf<T>::type;
+    Grid& g = *C.g;
+    if (A.g != &g || A.kind != 'G' || C.kind != 'H') return SB200_EINVAL;
+    if (A.dtype != TypeChar<T>::value || C.dtype != A.dtype) return SB200_EINVAL;
+    if (A.m != C.n || A.nb != C.nb) return SB200_EINVAL;
+    const int64_t kt = A.nt, nt = C.nt, nb = C.nb, te = C.tile_elems();
+    const int ld = int(nb);
+    const bool multi = g.size() > 1;
+    const int opH = IsComplex<T>::value ? 'C' : 'T';
+    CUDA_TRY(cudaDeviceSynchronize());
+
+    DevBuf ws;
+    const int64_t rows_max = (A.mt + g.p - 1) / g.p;
+    if (multi) SB_TRY(ws.alloc(size_t(2) * g.p * rows_max * te * sizeof(T)));
+    PanelWs<T> pws{ws.as<T>(), g.p, rows_max, te};
+    auto a_src = [&](int64_t i, int64_t k) -> T* { return multi ? pws.at(i, k) : A.tile_as<T>(i, k); };
+
+    std::vector<std::vector<Batch>> plan(kt);
+    PlanBuffer pb;
+    for (int64_t k = 0; k < kt; ++k) {
+        for (int64_t j = 0; j < nt; ++j)
+            for (int64_t i = j; i < nt; ++i)
+                if (C.is_local(i, j))
+                    batch_add(plan[k], int(C.tile_mb(i)), int(C.tile_nb(j)), int(A.tile_nb(k)), i == j ? 1 : 0,
+                              a_src(i, k), a_src(j, k), C.tile_as<T>(i, j));
+        pb.reserve(plan[k]);
+    }
+    Streams st;
+    double trail_flops = 0;
+    int64_t trail_launches = 0;
+    SB_TRY(st.init(size_t(2 * kt)));
+    auto P_done = [&](int64_t k) { return st.ev[k]; };
+    auto T_done = [&](int64_t k) { return st.ev[kt + k]; };
+    SB_TRY(pb.upload(st.panel));
+    CUDA_TRY(cudaStreamSynchronize(st.panel));
+    CUDA_TRY(cudaEventRecord(st.t0, st.panel));
+    CUDA_TRY(cudaStreamWaitEvent(st.trail, st.t0, 0));
+    for (int64_t k = 0; k < kt; ++k) {
+        cudaStream_t P = st.panel, T_ = st.trail;
+        if (multi) {
+            if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));
+            SB_TRY(bcast_block_column<T>(g, A, k, 0, pws, P));
+            CUDA_TRY(cudaEventRecord(P_done(k), P));
+            CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
+        }
+        SB_TRY(st.time_begin(T_));
+        SB_TRY(launch_batches<T>(plan[k], pb, 'N', opH, from_real<T>(alpha), from_real<T>(k == 0 ? beta : R(1)), ld, 1, T_));
+        SB_TRY(st.time_end(T_));
+        trail_flops += batches_flops(plan[k], IsComplex<T>::value);
+        trail_launches += int64_t(plan[k].size());
+        CUDA_TRY(cudaEventRecord(T_done(k), T_));
+    }
+    CUDA_TRY(cudaEventRecord(st.t1, st.trail));
+    CUDA_TRY(cudaStreamSynchronize(st.trail));
+    CUDA_TRY(cudaStreamSynchronize(st.panel));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, st.t0, st.t1));
+    C.last_ms = ms;
+    C.last_trail_ms = st.timed_ms();
+    C.last_trail_flops = trail_flops;
+    C.last_trail_launches = trail_launches;
+    return SB200_OK;
+}
+
+#define SB200_INST_DRIVERS(T) \
+    template int potrf_driver<T>(Matrix&, int64_t*, bool); \
+    template int gemm_driver<T>(T, Matrix&, Matrix&, T, Matrix&); \
+    template int herk_driver<T>(RealOf<T>::type, Matrix&, RealOf<T>::type, Matrix&);
+SB200_INST_DRIVERS(float)
+SB200_INST_DRIVERS(double)
+SB200_INST_DRIVERS(cuFloatComplex)
+SB200_INST_DRIVERS(cuDoubleComplex)
+
+int matrix_alloc(Grid& g, int dtype, int kind, int64_t m, int64_t n, int64_t nb, Matrix& A)
+{
+    A.g = &g; A.kind = kind; A.layout = 'C'; A.m = m; A.n = n; A.nb = nb;
+    A.dtype = dtype;
+    A.esize = dtype == 's' ? 4 : (dtype == 'd' || dtype == 'c') ? 8 : 16;
+    A.mt = ceil_div(m, nb); A.nt = ceil_div(n, nb);
+    A.mt_loc = A.mt > g.prow ? (A.mt - g.prow + g.p - 1) / g.p : 0;
+    A.nt_loc = A.nt > g.pcol ? (A.nt - g.pcol + g.q - 1) / g.q : 0;
+    A.col_start.assign(A.nt_loc + 1, 0);
+    int64_t cnt = 0;
+    for (int64_t jl = 0; jl < A.nt_loc; ++jl) {
+        A.col_start[jl] = cnt;
+        if (kind == 'G') cnt += A.mt_loc;
+        else {
+            const int64_t j = g.pcol + jl * g.q;
+            const int64_t il0 = A.first_local_row(j);
+            cnt += A.mt_loc > il0 ? A.mt_loc - il0 : 0;
+        }
+    }
+    A.col_start[A.nt_loc] = cnt;
+    A.ntiles_loc = cnt;
+    const size_t bytes = A.pool_bytes();
+    if (cudaMalloc(reinterpret_cast<void**>(&A.pool), bytes ? bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        A.pool = nullptr;
+        return SB200_ENOMEM;
+    }
+    return SB200_OK;
+}
+
+static int matrix_host_copy(Matrix& A, void* hA, int64_t lda, bool to_host, cudaStream_t s)
+{
+    if (lda < (A.m > 1 ? A.m : 1)) return SB200_EINVAL;
+    const size_t es = size_t(A.esize);
+    for (int64_t j = A.g->pcol; j < A.nt; j += A.g->q)
+        for (int64_t i = A.g->prow; i < A.mt; i += A.g->p) {
+            if (! A.stored(i, j)) continue;
+            char* d = reinterpret_cast<char*>(A.pool) + size_t(A.tile_index(i, j) * A.tile_elems()) * es;
+            char* hp = static_cast<char*>(hA) + size_t(i * A.nb + j * A.nb * lda) * es;
+            const size_t w = size_t(A.tile_mb(i)) * es, hgt = size_t(A.tile_nb(j));
+            if (to_host) CUDA_TRY(cudaMemcpy2DAsync(hp, size_t(lda) * es, d, size_t(A.nb) * es, w, hgt, cudaMemcpyDeviceToHost, s));
+            else         CUDA_TRY(cudaMemcpy2DAsync(d, size_t(A.nb) * es, hp, size_t(lda) * es, w, hgt, cudaMemcpyHostToDevice, s));
+        }
+    return SB200_OK;
+}
+
+// host-only description of the 2-D block-cyclic tile map (no GPU needed): used by the multi-rank
+// host logic and its CPU tests.  rank(i, j) = (i % p) + (j % q) * p (include/slate/func.hh:96-104).
+static int64_t local_tile_count(int kind, int p, int q, int rank, int64_t mt, int64_t nt)
+{
+    const int prow = rank % p, pcol = rank / p;
+    int64_t cnt = 0;
+    for (int64_t j = pcol; j < nt; j += q)
+        for (int64_t i = prow; i < mt; i += p)
+            if (kind == 'G' || i >= j) ++cnt;
+    return cnt;
+}
+
 } // namespace sb200
 
 using namespace sb200;
 
-struct sb200_grid_s   { Grid g; };
-struct sb200_matrix_s { Matrix A; };
+static inline float  cvs(float v) { return v; }
+static inline double cvs(double v) { return v; }
+static inline cuFloatComplex  cvs(sb200_c32 v) { return make_cuFloatComplex(v.re, v.im); }
+static inline cuDoubleComplex cvs(sb200_c64 v) { return make_cuDoubleComplex(v.re, v.im); }
+template <typename A> struct CuT { using type = A; };
+template <> struct CuT<sb200_c32> { using type = cuFloatComplex; };
+template <> struct CuT<sb200_c64> { using type = cuDoubleComplex; };
 
 extern "C" {
 
@@ -540,37 +644,34 @@ int sb200_grid_destroy(sb200_grid_t h)
     return SB200_OK;
 }
 
-int sb200_matrix_create_d(sb200_grid_t gh, int kind, int layout, int64_t m, int64_t n, int64_t nb,
-                          sb200_matrix_t* out)
+int sb200_tile_rank(int p, int q, int64_t i, int64_t j)
 {
-    if (! gh || ! out || (kind != 'G' && kind != 'H') || layout != 'C') return layout == 'R' ? SB200_ENOTSUP : SB200_EINVAL;
-    if (m < 0 || n < 0 || nb < 1 || (kind == 'H' && m != n)) return SB200_EINVAL;
-    auto* h = new sb200_matrix_s();
-    Matrix& A = h->A;
-    Grid& g = gh->g;
-    A.g = &g; A.kind = kind; A.layout = layout; A.m = m; A.n = n; A.nb = nb;
-    A.mt = ceil_div(m, nb); A.nt = ceil_div(n, nb);
-    A.mt_loc = A.mt > g.prow ? (A.mt - g.prow + g.p - 1) / g.p : 0;
-    A.nt_loc = A.nt > g.pcol ? (A.nt - g.pcol + g.q - 1) / g.q : 0;
-    A.col_start.resize(A.nt_loc + 1);
-    int64_t cnt = 0;
-    for (int64_t jl = 0; jl < A.nt_loc; ++jl) {
-        A.col_start[jl] = cnt;
-        if (kind == 'G') cnt += A.mt_loc;
-        else {
-            const int64_t j = g.pcol + jl * g.q;
-            const int64_t il0 = A.first_local_row(j);
-            cnt += A.mt_loc > il0 ? A.mt_loc - il0 : 0;
-        }
-    }
-    A.col_start[A.nt_loc] = cnt;
-    A.ntiles_loc = cnt;
-    const size_t bytes = size_t(cnt) * A.tile_elems() * sizeof(double);
-    if (cudaMalloc(reinterpret_cast<void**>(&A.pool), bytes ? bytes : 16) != cudaSuccess) {
-        cudaGetLastError(); delete h; return SB200_ENOMEM;
-    }
-    *out = h;
-    return SB200_OK;
+    if (p < 1 || q < 1 || i < 0 || j < 0) return -1;
+    return int(i % p) + int(j % q) * p;
+}
+
+int64_t sb200_local_tile_count(int kind, int p, int q, int rank, int64_t m, int64_t n, int64_t nb)
+{
+    if ((kind != 'G' && kind != 'H') || p < 1 || q < 1 || rank < 0 || rank >= p * q || m < 0 || n < 0 || nb < 1)
+        return -1;
+    return local_tile_count(kind, p, q, rank, ceil_div(m, nb), ceil_div(n, nb));
+}
+
+/* pool slot of tile (i, j) on its owner (local block column, then local block row; Hermitian: stored
+ * lower tiles only) -- the order of the packed host buffer of sb200_matrix_{from,to}_host_local */
+int64_t sb200_local_tile_index(int kind, int p, int q, int64_t m, int64_t n, int64_t nb, int64_t i, int64_t j)
+{
+    if ((kind != 'G' && kind != 'H') || p < 1 || q < 1 || nb < 1) return -1;
+    const int64_t mt = ceil_div(m, nb), nt = ceil_div(n, nb);
+    if (i < 0 || j < 0 || i >= mt || j >= nt || (kind == 'H' && i < j)) return -1;
+    const int prow = int(i % p), pcol = int(j % q);
+    int64_t idx = 0;
+    for (int64_t jj = pcol; jj < j; jj += q)
+        for (int64_t ii = prow; ii < mt; ii += p)
+            if (kind == 'G' || ii >= jj) ++idx;
+    for (int64_t ii = prow; ii < i; ii += p)
+        if (kind == 'G' || ii >= j) ++idx;
+    return idx;
 }
 
 int sb200_matrix_destroy(sb200_matrix_t h)
@@ -582,6 +683,7 @@ int sb200_matrix_destroy(sb200_matrix_t h)
 }
 
 int64_t sb200_matrix_local_tiles(sb200_matrix_t h) { return h ? h->A.ntiles_loc : 0; }
+int     sb200_matrix_dtype(sb200_matrix_t h) { return h ? h->A.dtype : 0; }
 double  sb200_last_driver_ms(sb200_matrix_t h) { return h ? h->A.last_ms : 0.0; }
 double  sb200_last_driver_panel_ms(sb200_matrix_t h) { return h ? h->A.last_panel_ms : 0.0; }
 
@@ -595,53 +697,14 @@ int sb200_last_driver_stats(sb200_matrix_t h, double* out4)
     return SB200_OK;
 }
 
-int sb200_matrix_generate_d(sb200_matrix_t h, int kind_code, int64_t seed, sb200_stream_t stream)
-{
-    if (! h || (kind_code != 0 && kind_code != 1)) return SB200_EINVAL;
-    Matrix& A = h->A;
-    std::vector<TileDesc> td;
-    for (int64_t j = A.g->pcol; j < A.nt; j += A.g->q)
-        for (int64_t i = A.g->prow; i < A.mt; i += A.g->p)
-            if (A.stored(i, j))
-                td.push_back({A.tile(i, j), i * A.nb, j * A.nb, int(A.tile_mb(i)), int(A.tile_nb(j))});
-    if (td.empty()) return SB200_OK;
-    TileDesc* dtd = nullptr;
-    CUDA_TRY(cudaMalloc(&dtd, td.size() * sizeof(TileDesc)));
-    cudaStream_t s = cudaStream_t(stream);
-    CUDA_TRY(cudaMemcpyAsync(dtd, td.data(), td.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s));
-    int status = SB200_OK;
-    for (size_t o = 0; o < td.size() && status == SB200_OK; o += 32768) {
-        const unsigned cnt = unsigned(std::min<size_t>(32768, td.size() - o));
-        generate_kernel<<<dim3(32, cnt), 256, 0, s>>>(dtd + o, int(A.nb), seed, kind_code, double(A.n));
-        status = launch_status();
-    }
-    cudaStreamSynchronize(s);
-    cudaFree(dtd);
-    return status;
-}
-
-static int matrix_host_copy(Matrix& A, double* hA, int64_t lda, bool to_host, cudaStream_t s)
-{
-    if (lda < (A.m > 1 ? A.m : 1)) return SB200_EINVAL;
-    for (int64_t j = A.g->pcol; j < A.nt; j += A.g->q)
-        for (int64_t i = A.g->prow; i < A.mt; i += A.g->p) {
-            if (! A.stored(i, j)) continue;
-            double* d = A.tile(i, j);
-            double* hp = hA + i * A.nb + j * A.nb * lda;
-            const size_t w = size_t(A.tile_mb(i)) * sizeof(double), hgt = size_t(A.tile_nb(j));
-            if (to_host) CUDA_TRY(cudaMemcpy2DAsync(hp, size_t(lda) * 8, d, size_t(A.nb) * 8, w, hgt, cudaMemcpyDeviceToHost, s));
-            else         CUDA_TRY(cudaMemcpy2DAsync(d, size_t(A.nb) * 8, hp, size_t(lda) * 8, w, hgt, cudaMemcpyHostToDevice, s));
-        }
-    return SB200_OK;
-}
-
-int sb200_matrix_from_host_d(sb200_matrix_t h, const double* hA, int64_t lda, sb200_stream_t stream)
+/* type-agnostic data movement (the matrix handle knows its element type) */
+int sb200_matrix_from_host(sb200_matrix_t h, const void* hA, int64_t lda, sb200_stream_t stream)
 {
     if (! h || ! hA) return SB200_EINVAL;
-    return matrix_host_copy(h->A, const_cast<double*>(hA), lda, false, cudaStream_t(stream));
+    return matrix_host_copy(h->A, const_cast<void*>(hA), lda, false, cudaStream_t(stream));
 }
 
-int sb200_matrix_to_host_d(sb200_matrix_t h, double* hA, int64_t lda, sb200_stream_t stream)
+int sb200_matrix_to_host(sb200_matrix_t h, void* hA, int64_t lda, sb200_stream_t stream)
 {
     if (! h || ! hA) return SB200_EINVAL;
     return matrix_host_copy(h->A, hA, lda, true, cudaStream_t(stream));
@@ -650,47 +713,97 @@ int sb200_matrix_to_host_d(sb200_matrix_t h, double* hA, int64_t lda, sb200_stre
 // local tiles <-> a packed host buffer in pool order (local block column, then local block row;
 // every tile nb*nb, ld = nb): the host-side layout a caller gets from Matrix::insertLocalTiles with
 // its own contiguous storage (include/slate/Matrix.hh:631-662).  One contiguous copy.
-int sb200_matrix_from_host_local_d(sb200_matrix_t h, const double* htiles, sb200_stream_t stream)
+int sb200_matrix_from_host_local(sb200_matrix_t h, const void* htiles, sb200_stream_t stream)
 {
     if (! h || ! htiles) return SB200_EINVAL;
-    Matrix& A = h->A;
-    CUDA_TRY(cudaMemcpyAsync(A.pool, htiles, size_t(A.ntiles_loc) * A.tile_elems() * sizeof(double),
-                             cudaMemcpyHostToDevice, cudaStream_t(stream)));
+    CUDA_TRY(cudaMemcpyAsync(h->A.pool, htiles, h->A.pool_bytes(), cudaMemcpyHostToDevice, cudaStream_t(stream)));
     return SB200_OK;
 }
 
-int sb200_matrix_to_host_local_d(sb200_matrix_t h, double* htiles, sb200_stream_t stream)
+int sb200_matrix_to_host_local(sb200_matrix_t h, void* htiles, sb200_stream_t stream)
 {
     if (! h || ! htiles) return SB200_EINVAL;
-    Matrix& A = h->A;
-    CUDA_TRY(cudaMemcpyAsync(htiles, A.pool, size_t(A.ntiles_loc) * A.tile_elems() * sizeof(double),
-                             cudaMemcpyDeviceToHost, cudaStream_t(stream)));
+    CUDA_TRY(cudaMemcpyAsync(htiles, h->A.pool, h->A.pool_bytes(), cudaMemcpyDeviceToHost, cudaStream_t(stream)));
     return SB200_OK;
 }
 
-int sb200_matrix_copy_d(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream)
+int sb200_matrix_copy(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream)
 {
     if (! dst || ! src) return SB200_EINVAL;
     Matrix& D = dst->A; Matrix& S = src->A;
-    if (D.g != S.g || D.kind != S.kind || D.m != S.m || D.n != S.n || D.nb != S.nb) return SB200_EINVAL;
-    CUDA_TRY(cudaMemcpyAsync(D.pool, S.pool, size_t(S.ntiles_loc) * S.tile_elems() * sizeof(double),
-                             cudaMemcpyDeviceToDevice, cudaStream_t(stream)));
+    if (D.g != S.g || D.kind != S.kind || D.m != S.m || D.n != S.n || D.nb != S.nb || D.dtype != S.dtype)
+        return SB200_EINVAL;
+    CUDA_TRY(cudaMemcpyAsync(D.pool, S.pool, S.pool_bytes(), cudaMemcpyDeviceToDevice, cudaStream_t(stream)));
     return SB200_OK;
 }
 
-int sb200_potrf_d(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info)
+int sb200_matrix_generate(sb200_matrix_t h, int kind_code, int64_t seed, sb200_stream_t stream)
 {
-    (void) opts;                       // lookahead is fixed at 1 (the reference default)
-    if (! h) return SB200_EINVAL;
-    return potrf_driver(h->A, info);
+    if (! h || (kind_code != 0 && kind_code != 1)) return SB200_EINVAL;
+    cudaStream_t s = cudaStream_t(stream);
+    switch (h->A.dtype) {
+        case 's': return generate_t<float>(h->A, kind_code, seed, s);
+        case 'd': return generate_t<double>(h->A, kind_code, seed, s);
+        case 'c': return generate_t<cuFloatComplex>(h->A, kind_code, seed, s);
+        case 'z': return generate_t<cuDoubleComplex>(h->A, kind_code, seed, s);
+    }
+    return SB200_EINVAL;
 }
 
-int sb200_gemm_d(double alpha, sb200_matrix_t A, sb200_matrix_t B, double beta, sb200_matrix_t C,
-                 const sb200_options_t* opts)
+/* the FP64 names of round 1 stay */
+int sb200_matrix_generate_d(sb200_matrix_t h, int kind_code, int64_t seed, sb200_stream_t stream)
+{ return (h && h->A.dtype == 'd') ? sb200_matrix_generate(h, kind_code, seed, stream) : SB200_EINVAL; }
+int sb200_matrix_from_host_d(sb200_matrix_t h, const double* hA, int64_t lda, sb200_stream_t stream)
+{ return (h && h->A.dtype == 'd') ? sb200_matrix_from_host(h, hA, lda, stream) : SB200_EINVAL; }
+int sb200_matrix_to_host_d(sb200_matrix_t h, double* hA, int64_t lda, sb200_stream_t stream)
+{ return (h && h->A.dtype == 'd') ? sb200_matrix_to_host(h, hA, lda, stream) : SB200_EINVAL; }
+int sb200_matrix_from_host_local_d(sb200_matrix_t h, const double* htiles, sb200_stream_t stream)
+{ return (h && h->A.dtype == 'd') ? sb200_matrix_from_host_local(h, htiles, stream) : SB200_EINVAL; }
+int sb200_matrix_to_host_local_d(sb200_matrix_t h, double* htiles, sb200_stream_t stream)
+{ return (h && h->A.dtype == 'd') ? sb200_matrix_to_host_local(h, htiles, stream) : SB200_EINVAL; }
+int sb200_matrix_copy_d(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream)
+{ return sb200_matrix_copy(dst, src, stream); }
+
+#define SB200_DEF_RUNTIME(X, T, R) \
+int sb200_matrix_create_##X(sb200_grid_t gh, int kind, int layout, int64_t m, int64_t n, int64_t nb, \
+                            sb200_matrix_t* out) \
+{ \
+    if (! gh || ! out || (kind != 'G' && kind != 'H') || layout != 'C') return layout == 'R' ? SB200_ENOTSUP : SB200_EINVAL; \
+    if (m < 0 || n < 0 || nb < 1 || (kind == 'H' && m != n)) return SB200_EINVAL; \
+    auto* h = new sb200_matrix_s(); \
+    const int st = matrix_alloc(gh->g, TypeChar<CuT<T>::type>::value, kind, m, n, nb, h->A); \
+    if (st != SB200_OK) { delete h; return st; } \
+    *out = h; \
+    return SB200_OK; \
+} \
+int sb200_potrf_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) \
+{ \
+    (void) opts;                       /* lookahead is fixed at 1 (the reference default) */ \
+    if (! h) return SB200_EINVAL; \
+    return potrf_driver<CuT<T>::type>(h->A, info, false); \
+} \
+int sb200_gemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, \
+                   const sb200_options_t* opts) \
+{ \
+    (void) opts; \
+    if (! A || ! B || ! C) return SB200_EINVAL; \
+    return gemm_driver<CuT<T>::type>(cvs(alpha), A->A, B->A, cvs(beta), C->A); \
+} \
+int sb200_herk_mat_##X(R alpha, sb200_matrix_t A, R beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    (void) opts; \
+    if (! A || ! C) return SB200_EINVAL; \
+    return herk_driver<CuT<T>::type>(alpha, A->A, beta, C->A); \
+}
+SB200_FOR_TYPES(SB200_DEF_RUNTIME)
+
+/* FP32 Cholesky whose trailing update runs on the tcgen05 FP32-emulated (3 x TF32) kernel:
+ * the low-precision factorisation of posv_mixed (src/posv_mixed.cc:171-176) */
+int sb200_potrf_tc05_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info)
 {
     (void) opts;
-    if (! A || ! B || ! C) return SB200_EINVAL;
-    return gemm_driver(alpha, A->A, B->A, beta, C->A);
+    if (! h) return SB200_EINVAL;
+    return potrf_driver<float>(h->A, info, true);
 }
 
 } // extern "C"

@@ -45,7 +45,9 @@ struct Matrix {
     int64_t mt_loc = 0, nt_loc = 0;          // local tile rows / cols
     std::vector<int64_t> col_start;          // tile index of the first stored tile of local col jl
     int64_t ntiles_loc = 0;
-    double* pool = nullptr;                  // ntiles_loc * nb*nb doubles, every tile ld = nb
+    int     dtype = 'd';                     // 's' float, 'd' double, 'c' complex<float>, 'z' complex<double>
+    int     esize = 8;                       // bytes per element
+    double* pool = nullptr;                  // ntiles_loc * nb*nb elements of `dtype` (typed double* for the FP64 drivers), every tile ld = nb
     double  last_ms = 0.0;                   // device time of the last driver call (CUDA events)
     double  last_trail_ms = 0.0;             // summed duration of its trailing-update GEMM launches
     double  last_trail_flops = 0.0;          // algorithmic flops of those launches
@@ -63,16 +65,29 @@ struct Matrix {
         int64_t il = (i0 - g->prow + g->p - 1) / g->p;
         return il < 0 ? 0 : il;
     }
-    // device pointer of local tile (i, j); caller guarantees is_local && stored
-    double* tile(int64_t i, int64_t j) const
+    // pool slot of local tile (i, j); caller guarantees is_local && stored
+    int64_t tile_index(int64_t i, int64_t j) const
     {
         const int64_t il = (i - g->prow) / g->p, jl = (j - g->pcol) / g->q;
-        int64_t idx;
-        if (kind == 'G') idx = col_start[jl] + il;
-        else             idx = col_start[jl] + (il - first_local_row(j));
-        return pool + idx * tile_elems();
+        if (kind == 'G') return col_start[jl] + il;
+        return col_start[jl] + (il - first_local_row(j));
     }
+    // device pointer of local tile (i, j) of an FP64 matrix
+    double* tile(int64_t i, int64_t j) const { return pool + tile_index(i, j) * tile_elems(); }
+    // ... of a matrix of element type T (sizeof(T) == esize)
+    template <typename T> T* tile_as(int64_t i, int64_t j) const
+    {
+        return reinterpret_cast<T*>(pool) + tile_index(i, j) * tile_elems();
+    }
+    size_t pool_bytes() const { return size_t(ntiles_loc) * size_t(tile_elems()) * size_t(esize); }
 };
+
+// element type <-> ABI type character
+template <typename T> struct TypeChar;
+template <> struct TypeChar<float>           { static constexpr int value = 's'; };
+template <> struct TypeChar<double>          { static constexpr int value = 'd'; };
+template <> struct TypeChar<cuFloatComplex>  { static constexpr int value = 'c'; };
+template <> struct TypeChar<cuDoubleComplex> { static constexpr int value = 'z'; };
 
 // Optional per-phase device timing of a driver call (SB200_PHASES=1): event pairs around named
 // phases of the panel / trailing streams, summed per phase and printed to stderr as one JSON line

@@ -1,0 +1,203 @@
+// runtime_internal.hh -- helpers shared by the drivers (runtime.cu, solve.cu, mixed.cu, getrf*.cu):
+// status macros, per-step pointer batches ("device regions"), the once-per-call plan buffer,
+// the two-stream/event scaffold, and the type-generic tile factor/solve entry points.
+#pragma once
+#include "runtime.hh"
+#include "gemm_dmma.cuh"
+#include "scalar_ops.cuh"
+#include "tc05.hh"
+#include <vector>
+#include <cstdio>
+
+namespace sb200 {
+
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return int(e_); } while (0)
+#define NCCL_TRY(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) { \
+    fprintf(stderr, "slate_b200: NCCL error %s at %s:%d\n", ncclGetErrorString(r_), __FILE__, __LINE__); \
+    return SB200_ENCCL; } } while (0)
+#define SB_TRY(x) do { int s_ = (x); if (s_ != SB200_OK) return s_; } while (0)
+
+// from factor_small.cu (explicitly instantiated there for float, double, cuFloatComplex, cuDoubleComplex)
+template <typename T>
+int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alpha,
+                  const T* Tm, int ldt, T* const* dB, int64_t offB, int ldb, int batch,
+                  T* W, cudaStream_t stream);
+template <typename T>
+int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cudaStream_t stream);
+constexpr int FACTOR_IB = 64;          // diagonal block of the tile factor / solve kernels
+
+template <typename T> struct IsComplex { static constexpr bool value = false; };
+template <> struct IsComplex<cuFloatComplex>  { static constexpr bool value = true; };
+template <> struct IsComplex<cuDoubleComplex> { static constexpr bool value = true; };
+
+// ------------------------------------------------------------------------------------------
+// batches: tiles of one step grouped by (m, n, k, tri) -- the reference's "regions"
+// (src/internal/internal_batch.hh:169-347), built once per driver call for all steps.
+// ------------------------------------------------------------------------------------------
+struct Batch {
+    int m, n, k, tri;
+    std::vector<const void*> A, B;
+    std::vector<void*> C;
+    size_t off = 0;                 // offset (in pointers) of A | B | C blocks in the device plan
+};
+
+inline void batch_add(std::vector<Batch>& v, int m, int n, int k, int tri,
+                      const void* A, const void* B, void* C)
+{
+    for (auto& b : v)
+        if (b.m == m && b.n == n && b.k == k && b.tri == tri) {
+            b.A.push_back(A); b.B.push_back(B); b.C.push_back(C);
+            return;
+        }
+    Batch b{m, n, k, tri, {A}, {B}, {C}, 0};
+    v.push_back(std::move(b));
+}
+
+struct PlanBuffer {
+    std::vector<const void*> host;
+    void** dev = nullptr;
+    size_t reserve(std::vector<Batch>& bs)
+    {
+        size_t first = host.size();
+        for (auto& b : bs) {
+            b.off = host.size();
+            host.insert(host.end(), b.A.begin(), b.A.end());
+            host.insert(host.end(), b.B.begin(), b.B.end());
+            host.insert(host.end(), b.C.begin(), b.C.end());
+        }
+        return first;
+    }
+    template <typename P> size_t push(const std::vector<P*>& v)
+    {
+        size_t o = host.size();
+        host.insert(host.end(), v.begin(), v.end());
+        return o;
+    }
+    int upload(cudaStream_t s)
+    {
+        if (host.empty()) return SB200_OK;
+        CUDA_TRY(cudaMalloc(&dev, host.size() * sizeof(void*)));
+        CUDA_TRY(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(void*), cudaMemcpyHostToDevice, s));
+        return SB200_OK;
+    }
+    template <typename T> T* const* at(size_t off) const { return reinterpret_cast<T* const*>(dev + off); }
+    ~PlanBuffer() { if (dev) cudaFree(dev); }
+};
+
+// one batched launch per shape class; herk != 0 forces the diagonal of triangle-masked complex tiles real
+template <typename T>
+inline int launch_batches(const std::vector<Batch>& bs, const PlanBuffer& pb, int opA, int opB,
+                          T alpha, T beta, int ld, int herk, cudaStream_t s)
+{
+    for (const auto& b : bs) {
+        GemmParamsT<T> p{};
+        const size_t cnt = b.C.size();
+        p.A = reinterpret_cast<const T* const*>(pb.dev + b.off);
+        p.B = reinterpret_cast<const T* const*>(pb.dev + b.off + cnt);
+        p.C = reinterpret_cast<T* const*>(pb.dev + b.off + 2 * cnt);
+        p.m = b.m; p.n = b.n; p.k = b.k; p.lda = ld; p.ldb = ld; p.ldc = ld;
+        p.alpha = alpha; p.beta = beta; p.batch = int(cnt); p.tri = b.tri;
+        p.herk = (herk && b.tri) ? 1 : 0;
+        SB_TRY(launch_gemm<T>(opA, opB, p, s));
+    }
+    return SB200_OK;
+}
+
+// same batches on the tcgen05 FP32-emulated kernel: A / B entries point at PACKED operands
+inline int launch_batches_tc05(const std::vector<Batch>& bs, const PlanBuffer& pb,
+                               float alpha, float beta, int ld, cudaStream_t s)
+{
+    for (const auto& b : bs) {
+        Tc05Params p{};
+        const size_t cnt = b.C.size();
+        p.Ap = reinterpret_cast<const void* const*>(pb.dev + b.off);
+        p.Bp = reinterpret_cast<const void* const*>(pb.dev + b.off + cnt);
+        p.C = reinterpret_cast<float* const*>(pb.dev + b.off + 2 * cnt);
+        p.m = b.m; p.n = b.n; p.k = b.k; p.ldc = ld;
+        p.alpha = alpha; p.beta = beta; p.batch = int(cnt); p.tri = b.tri;
+        SB_TRY(launch_tc05_gemm(p, s));
+    }
+    return SB200_OK;
+}
+
+inline double batches_flops(const std::vector<Batch>& bs, bool complex_)
+{
+    double f = 0;
+    for (const auto& b : bs) {
+        // ALGORITHMIC flops: a triangle-masked (herk/syrk diagonal) tile counts n(n+1)k
+        // (blaspp/include/blas/flops.hh syrk), whatever the kernel computes above the diagonal
+        const double per = b.tri ? double(b.n) * (b.n + 1.0) * b.k : 2.0 * b.m * b.n * b.k;
+        f += per * double(b.C.size());
+    }
+    return complex_ ? 4.0 * f : f;      // complex: 6 mul-flops + 2 add-flops per multiply-add (flops.hh:100-104)
+}
+
+struct Streams {
+    cudaStream_t panel = nullptr, trail = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> tev;          // timing event pairs around the trailing-update launches
+    std::vector<cudaEvent_t> pev;          // timing event pairs around the panel work of every step
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    static double sum_pairs(const std::vector<cudaEvent_t>& v)
+    {
+        double tot = 0;
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) tot += ms;
+        }
+        return tot;
+    }
+    static int stamp(std::vector<cudaEvent_t>& v, cudaStream_t s)
+    {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        v.push_back(e);
+        CUDA_TRY(cudaEventRecord(e, s));
+        return SB200_OK;
+    }
+    int ptime(cudaStream_t s) { return stamp(pev, s); }
+    int time_begin(cudaStream_t s) { return stamp(tev, s); }
+    int time_end(cudaStream_t s) { return stamp(tev, s); }
+    double panel_ms() { return sum_pairs(pev); }
+    double timed_ms() { return sum_pairs(tev); }
+    int init(size_t nevents)
+    {
+        int lo, hi;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&panel, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&trail, cudaStreamNonBlocking, lo));
+        ev.resize(nevents);
+        for (auto& e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreate(&t0));
+        CUDA_TRY(cudaEventCreate(&t1));
+        return SB200_OK;
+    }
+    ~Streams()
+    {
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+        for (auto e : tev) if (e) cudaEventDestroy(e);
+        for (auto e : pev) if (e) cudaEventDestroy(e);
+        if (t0) cudaEventDestroy(t0);
+        if (t1) cudaEventDestroy(t1);
+        if (panel) cudaStreamDestroy(panel);
+        if (trail) cudaStreamDestroy(trail);
+    }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    int alloc(size_t bytes) { CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 16)); return SB200_OK; }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+// drivers (runtime.cu)
+template <typename T> int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05);
+template <typename T> int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C);
+template <typename T> int herk_driver(typename RealOf<T>::type alpha, Matrix& A, typename RealOf<T>::type beta, Matrix& C);
+int matrix_alloc(Grid& g, int dtype, int kind, int64_t m, int64_t n, int64_t nb, Matrix& A);
+
+} // namespace sb200
+
+struct sb200_grid_s   { sb200::Grid g; };
+struct sb200_matrix_s { sb200::Matrix A; };

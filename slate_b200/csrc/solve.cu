@@ -1,0 +1,613 @@
+// solve.cu -- the solve path behind the factorisations and the
+// mixed-precision drivers that use it (BASELINE config 5).
+//
+// Reference:
+//   src/potrs.cc:54-77        potrs  = trsm(Left, L) ; trsm(Left, L^H)
+//   src/getrs.cc:25-66        getrs  = permuteRows(Forward) ; trsm(Left, L unit) ; trsm(Left, U)
+//   src/work/work_trsm.cc:24-387   the block-row sweep those trsm calls run (diagonal tile solve of
+//                             block row k, broadcast, gemm update of the remaining block rows)
+//   src/hemm.cc / src/hemmC.cc     R = alpha A X + beta R with A Hermitian (lower tiles stored)
+//   src/posv_mixed.cc:111-297, src/gesv_mixed.cc:106-300   factor in low precision, refine in high
+//   src/internal/internal_util.hh:121-138                  iterRefConverged
+//
+// B200-first: the low-precision factorisation is FP32 whose trailing update runs on the tcgen05
+// FP32-emulated (3 x TF32) kernel (gemm_tc05.cu); every sweep / product is a handful of batched
+// launches from a pointer plan built once per call; nothing is staged through the host.
+// This round the solve path runs on a 1 x 1 grid (one GPU); p x q grids return SB200_ENOTSUP.
+#include "runtime_internal.hh"
+#include "getrf_internal.hh"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+namespace sb200 {
+
+// ------------------------------------------------------------------------------------------ kernels
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) convert_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t count)
+{
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < count; e += int64_t(gridDim.x) * blockDim.x)
+        dst[e] = D(src[e]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_into_kernel(const T* __restrict__ r, T* __restrict__ x, int64_t count)
+{
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < count; e += int64_t(gridDim.x) * blockDim.x)
+        x[e] = add(x[e], r[e]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_kernel(T* __restrict__ x, T beta, int zero, int64_t count)
+{
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < count; e += int64_t(gridDim.x) * blockDim.x)
+        x[e] = zero ? zero_of<T>() : mul(beta, x[e]);
+}
+
+__device__ __forceinline__ double abs_d(float v)  { return fabs(double(v)); }
+__device__ __forceinline__ double abs_d(double v) { return fabs(v); }
+__device__ __forceinline__ double abs_d(cuFloatComplex v)  { return hypot(double(v.x), double(v.y)); }
+__device__ __forceinline__ double abs_d(cuDoubleComplex v) { return hypot(v.x, v.y); }
+
+static inline unsigned ew_grid(int64_t count) { return unsigned(std::min<int64_t>(ceil_div(std::max<int64_t>(count, 1), 256), 148 * 16)); }
+
+// full Hermitian copy of the diagonal tiles: out_k(r, c) = r >= c ? a_k(r, c) : conj(a_k(c, r)); complex diagonal real
+template <typename T>
+__global__ void __launch_bounds__(256) he_fill_kernel(const T* const* __restrict__ diag, T* __restrict__ out,
+                                                      int ld, int64_t te, int nfull, int nlast_rows, int ntiles)
+{
+    const int k = blockIdx.y;
+    const int n = (k == ntiles - 1) ? nlast_rows : nfull;
+    const T* __restrict__ a = diag[k];
+    T* __restrict__ o = out + int64_t(k) * te;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int r = e % n, c = e / n;
+        T v;
+        if (r > c)       v = a[r + int64_t(c) * ld];
+        else if (r < c)  v = conj_(a[c + int64_t(r) * ld]);
+        else             v = real_part_only(a[r + int64_t(c) * ld]);
+        o[r + int64_t(c) * ld] = v;
+    }
+}
+
+// out(x, c) = in(perm[x], c) over an m x n tile matrix on a 1 x 1 grid (tile (i, j) at pool + (j*mt + i)*te)
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                          const int* __restrict__ perm, int64_t m, int64_t n,
+                                                          int nb, int64_t mt)
+{
+    const int64_t te = int64_t(nb) * nb;
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < m * n; e += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t x = e % m, c = e / m;
+        const int64_t y = perm[x];
+        const int64_t jt = c / nb, cc = c % nb;
+        out[(jt * mt + x / nb) * te + (x % nb) + cc * nb] = in[(jt * mt + y / nb) * te + (y % nb) + cc * nb];
+    }
+}
+
+template <typename R> __device__ __forceinline__ R nan_max(R a, R b) { return (a > b || a != a) ? a : b; }
+
+// colNorms(Norm::Max): out[c] = max_r |X(r, c)|, NaN-propagating (src/cuda/device_genorm.cu:285-330 + colNorms)
+template <typename T>
+__global__ void __launch_bounds__(256) colmax_kernel(const T* __restrict__ X, double* __restrict__ out,
+                                                     int64_t m, int nb, int64_t mt)
+{
+    __shared__ double red[256];
+    const int64_t c = blockIdx.x, te = int64_t(nb) * nb;
+    const T* __restrict__ col = X + (c / nb) * mt * te + (c % nb) * nb;
+    double best = 0.0;
+    for (int64_t r = threadIdx.x; r < m; r += blockDim.x)
+        best = nan_max<double>(abs_d(col[(r / nb) * te + (r % nb)]), best);
+    red[threadIdx.x] = best;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (int(threadIdx.x) < o) red[threadIdx.x] = nan_max<double>(red[threadIdx.x + o], red[threadIdx.x]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = red[0];
+}
+
+// absolute row sums of block row i of a general (kind 'G') or Hermitian-lower (kind 'H') tile matrix on a
+// 1 x 1 grid: one CTA per block row, thread t owns row t of the block (norm(Norm::Inf, A), src/norm.cc)
+template <typename T>
+__global__ void __launch_bounds__(1024) rowsum_kernel(const T* __restrict__ pool, const int64_t* __restrict__ col_start,
+                                                      double* __restrict__ rowsum, int kind, int64_t m, int64_t n,
+                                                      int nb, int64_t mt, int64_t nt)
+{
+    extern __shared__ double acc[];              // nb partial sums (transposed part of the Hermitian case)
+    const int64_t i = blockIdx.x, te = int64_t(nb) * nb;
+    const int mb = int(min(int64_t(nb), m - i * nb));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int t = threadIdx.x; t < nb; t += blockDim.x) acc[t] = 0.0;
+    __syncthreads();
+    auto tile = [&](int64_t ti, int64_t tj) -> const T* {
+        return pool + (kind == 'G' ? (tj * mt + ti) : (col_start[tj] + (ti - tj))) * te;
+    };
+    // stored tiles of this block row: rows are contiguous across threads (coalesced)
+    const int64_t jend = (kind == 'G') ? nt : i + 1;
+    for (int t = threadIdx.x; t < mb; t += blockDim.x) {
+        double s = 0.0;
+        for (int64_t j = 0; j < jend; ++j) {
+            const T* a = tile(i, j);
+            const int w = int(min(int64_t(nb), n - j * nb));
+            const int cend = (kind == 'H' && j == i) ? t + 1 : w;         // diagonal tile: lower part, row t
+            for (int c = 0; c < cend; ++c) s += abs_d(a[t + int64_t(c) * nb]);
+        }
+        acc[t] += s;
+    }
+    __syncthreads();
+    if (kind == 'H') {
+        // transposed part: column t of the tiles below (and of the diagonal tile, strictly below the diagonal):
+        // one warp per column, lanes along the rows
+        for (int64_t k = i; k < mt; ++k) {
+            const T* a = tile(k, i);
+            const int rows = int(min(int64_t(nb), m - k * nb));
+            for (int t = warp; t < mb; t += nwarp) {
+                double s = 0.0;
+                const int r0 = (k == i) ? t + 1 : 0;
+                for (int r = r0 + lane; r < rows; r += 32) s += abs_d(a[r + int64_t(t) * nb]);
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) acc[t] += s;
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < mb; t += blockDim.x) rowsum[i * nb + t] = acc[t];
+}
+
+// ------------------------------------------------------------------------------------------ host helpers
+template <typename S, typename D>
+static int convert_pool(const Matrix& src, Matrix& dst, cudaStream_t s)
+{
+    const int64_t count = src.ntiles_loc * src.tile_elems();
+    if (dst.ntiles_loc != src.ntiles_loc || dst.nb != src.nb) return SB200_EINVAL;
+    if (count == 0) return SB200_OK;
+    convert_kernel<S, D><<<ew_grid(count), 256, 0, s>>>(reinterpret_cast<const S*>(src.pool), reinterpret_cast<D*>(dst.pool), count);
+    return launch_status();
+}
+
+template <typename T>
+static int add_pool(const Matrix& r, Matrix& x, cudaStream_t s)
+{
+    const int64_t count = x.ntiles_loc * x.tile_elems();
+    if (count == 0) return SB200_OK;
+    add_into_kernel<T><<<ew_grid(count), 256, 0, s>>>(reinterpret_cast<const T*>(r.pool), reinterpret_cast<T*>(x.pool), count);
+    return launch_status();
+}
+
+static int copy_pool(const Matrix& src, Matrix& dst, cudaStream_t s)
+{
+    if (src.pool_bytes() != dst.pool_bytes()) return SB200_EINVAL;
+    CUDA_TRY(cudaMemcpyAsync(dst.pool, src.pool, src.pool_bytes(), cudaMemcpyDeviceToDevice, s));
+    return SB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Block-row sweep  B <- op(T)^{-1} B,  T = the lower (or upper) triangle of the tile matrix A.
+// reference: work::trsm, src/work/work_trsm.cc:60-230 (Left; lower forward / upper backward sweep).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int tri_sweep(Matrix& A, bool lower, int op, bool unit, Matrix& B, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1 || B.g != A.g) return SB200_ENOTSUP;
+    if (A.m != A.n || B.m != A.n || A.nb != B.nb || B.kind != 'G') return SB200_EINVAL;
+    if (A.dtype != TypeChar<T>::value || B.dtype != A.dtype) return SB200_EINVAL;
+    const int64_t kt = A.nt, nb = A.nb, ntB = B.nt;
+    if (kt == 0 || ntB == 0) return SB200_OK;
+    const int ld = int(nb);
+    const bool trans = (op != 'N');
+    const bool forward = (lower != trans);                 // op(T) lower: forward substitution
+    if (A.kind == 'H' && ! lower) return SB200_EINVAL;     // only the lower tiles of a Hermitian matrix exist
+
+    struct Step { size_t full_off = 0, last_off = 0; int nfull = 0, nlast = 0; std::vector<Batch> upd; };
+    std::vector<Step> steps(static_cast<size_t>(kt));
+    PlanBuffer pb;
+    for (int64_t sidx = 0; sidx < kt; ++sidx) {
+        const int64_t k = forward ? sidx : kt - 1 - sidx;
+        Step& st = steps[size_t(sidx)];
+        std::vector<T*> full, last;
+        for (int64_t j = 0; j < ntB; ++j)
+            (B.tile_nb(j) == nb ? full : last).push_back(B.tile_as<T>(k, j));
+        const int64_t i0 = forward ? k + 1 : 0, i1 = forward ? kt : k;
+        for (int64_t i = i0; i < i1; ++i)
+            for (int64_t j = 0; j < ntB; ++j) {
+                const T* Mik = trans ? A.tile_as<T>(k, i) : A.tile_as<T>(i, k);
+                batch_add(st.upd, int(B.tile_mb(i)), int(B.tile_nb(j)), int(B.tile_mb(k)), 0, Mik,
+                          B.tile_as<T>(k, j), B.tile_as<T>(i, j));
+            }
+        st.nfull = int(full.size()); st.nlast = int(last.size());
+        st.full_off = pb.push(full); st.last_off = pb.push(last);
+        pb.reserve(st.upd);
+    }
+    DevBuf W;
+    SB_TRY(W.alloc(size_t(ceil_div(nb, FACTOR_IB)) * FACTOR_IB * FACTOR_IB * sizeof(T)));
+    SB_TRY(pb.upload(s));
+    const T one = from_real<T>(R(1)), minus_one = from_real<T>(R(-1));
+    for (int64_t sidx = 0; sidx < kt; ++sidx) {
+        const int64_t k = forward ? sidx : kt - 1 - sidx;
+        const Step& st = steps[size_t(sidx)];
+        const int mk = int(B.tile_mb(k));
+        if (st.nfull)
+            SB_TRY(trsm_colmajor<T>(true, lower, op, unit, mk, int(nb), one, A.tile_as<T>(k, k), ld,
+                                    pb.at<T>(st.full_off), 0, ld, st.nfull, W.as<T>(), s));
+        if (st.nlast)
+            SB_TRY(trsm_colmajor<T>(true, lower, op, unit, mk, int(B.tile_nb(ntB - 1)), one, A.tile_as<T>(k, k), ld,
+                                    pb.at<T>(st.last_off), 0, ld, st.nlast, W.as<T>(), s));
+        SB_TRY(launch_batches<T>(st.upd, pb, trans ? op : 'N', 'N', minus_one, one, ld, 0, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));       // the plan and W die with this frame
+    return SB200_OK;
+}
+
+template <typename T>
+int potrs_t(Matrix& A, Matrix& B, cudaStream_t s)
+{
+    if (A.kind != 'H') return SB200_EINVAL;
+    const int opH = IsComplex<T>::value ? 'C' : 'T';
+    SB_TRY(tri_sweep<T>(A, true, 'N', false, B, s));
+    return tri_sweep<T>(A, true, opH, false, B, s);
+}
+
+// pivots (host, (tileIndex, elementOffset) pairs per panel as slate::Pivots) -> forward row map:
+// row x of P*B is row perm[x] of B
+static void pivots_to_perm(const int64_t* piv, int64_t m, int64_t n, int64_t nb, std::vector<int>& perm)
+{
+    perm.resize(size_t(m));
+    std::iota(perm.begin(), perm.end(), 0);
+    const int64_t mn = std::min(m, n);
+    for (int64_t o = 0; o < mn; ++o) {
+        const int64_t k = o / nb;
+        const int64_t r2 = k * nb + piv[2 * o] * nb + piv[2 * o + 1];
+        if (r2 != o && r2 >= 0 && r2 < m) std::swap(perm[size_t(o)], perm[size_t(r2)]);
+    }
+}
+
+template <typename T>
+int getrs_t(Matrix& A, const int* dperm, Matrix& B, cudaStream_t s)
+{
+    if (A.kind != 'G' || A.g->size() > 1) return A.kind != 'G' ? SB200_EINVAL : SB200_ENOTSUP;
+    if (A.m != A.n || B.m != A.m || B.dtype != A.dtype) return SB200_EINVAL;
+    // B <- P B  (permuteRows Forward, src/getrs.cc:45-46), out of place through a copy of B
+    DevBuf tmp;
+    SB_TRY(tmp.alloc(B.pool_bytes()));
+    CUDA_TRY(cudaMemcpyAsync(tmp.p, B.pool, B.pool_bytes(), cudaMemcpyDeviceToDevice, s));
+    const int64_t cnt = B.m * B.n;
+    if (cnt > 0) {
+        gather_rows_kernel<T><<<ew_grid(cnt), 256, 0, s>>>(tmp.as<T>(), reinterpret_cast<T*>(B.pool), dperm,
+                                                           B.m, B.n, int(B.nb), B.mt);
+        SB_TRY(launch_status());
+    }
+    SB_TRY(tri_sweep<T>(A, true, 'N', true, B, s));         // L, unit diagonal
+    return tri_sweep<T>(A, false, 'N', false, B, s);        // U
+}
+
+// ------------------------------------------------------------------------------------------
+// hemm, Side::Left, lower storage: R = alpha A X + beta R  (src/hemmC.cc, Left/Lower case).
+// Step k adds block column k of the full Hermitian A: tiles below the diagonal as stored, tiles above
+// it as the conjugate transpose of row k's stored tiles, the diagonal tile from a filled-in copy.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int hemm_left_lower(T alpha, Matrix& A, Matrix& X, T beta, Matrix& Rm, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.kind != 'H' || X.kind != 'G' || Rm.kind != 'G' || X.m != A.n || Rm.m != A.n || X.n != Rm.n
+        || X.nb != A.nb || Rm.nb != A.nb) return SB200_EINVAL;
+    const int64_t nt = A.nt, nb = A.nb, ntB = X.nt, te = A.tile_elems();
+    if (nt == 0 || ntB == 0) return SB200_OK;
+    const int ld = int(nb);
+    const int opH = IsComplex<T>::value ? 'C' : 'T';
+    const T one = from_real<T>(R(1));
+
+    const int64_t count = Rm.ntiles_loc * te;
+    const bool beta_zero = is_zero(beta);
+    if (beta_zero || ! is_zero(sub(beta, one))) {
+        scale_kernel<T><<<ew_grid(count), 256, 0, s>>>(reinterpret_cast<T*>(Rm.pool), beta, beta_zero ? 1 : 0, count);
+        SB_TRY(launch_status());
+    }
+    DevBuf dfull;
+    SB_TRY(dfull.alloc(size_t(nt) * te * sizeof(T)));
+    struct Step { std::vector<Batch> below, above, diag; };
+    std::vector<Step> steps(static_cast<size_t>(nt));
+    std::vector<const T*> diag_ptrs;
+    PlanBuffer pb;
+    for (int64_t k = 0; k < nt; ++k) {
+        Step& st = steps[size_t(k)];
+        diag_ptrs.push_back(A.tile_as<T>(k, k));
+        for (int64_t j = 0; j < ntB; ++j) {
+            for (int64_t i = k + 1; i < nt; ++i)
+                batch_add(st.below, int(Rm.tile_mb(i)), int(Rm.tile_nb(j)), int(X.tile_mb(k)), 0,
+                          A.tile_as<T>(i, k), X.tile_as<T>(k, j), Rm.tile_as<T>(i, j));
+            for (int64_t i = 0; i < k; ++i)
+                batch_add(st.above, int(Rm.tile_mb(i)), int(Rm.tile_nb(j)), int(X.tile_mb(k)), 0,
+                          A.tile_as<T>(k, i), X.tile_as<T>(k, j), Rm.tile_as<T>(i, j));
+            batch_add(st.diag, int(Rm.tile_mb(k)), int(Rm.tile_nb(j)), int(X.tile_mb(k)), 0,
+                      dfull.as<T>() + k * te, X.tile_as<T>(k, j), Rm.tile_as<T>(k, j));
+        }
+        pb.reserve(st.below); pb.reserve(st.above); pb.reserve(st.diag);
+    }
+    const size_t diag_off = pb.push(diag_ptrs);
+    SB_TRY(pb.upload(s));
+    he_fill_kernel<T><<<dim3(64, unsigned(nt)), 256, 0, s>>>(pb.at<const T>(diag_off), dfull.as<T>(), ld, te,
+                                                            int(nb), int(A.tile_mb(nt - 1)), int(nt));
+    SB_TRY(launch_status());
+    for (int64_t k = 0; k < nt; ++k) {
+        const Step& st = steps[size_t(k)];
+        SB_TRY(launch_batches<T>(st.below, pb, 'N', 'N', alpha, one, ld, 0, s));
+        SB_TRY(launch_batches<T>(st.above, pb, opH, 'N', alpha, one, ld, 0, s));
+        SB_TRY(launch_batches<T>(st.diag, pb, 'N', 'N', alpha, one, ld, 0, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SB200_OK;
+}
+
+// norm(Norm::Inf, A): max absolute row sum; A general or Hermitian (lower tiles)
+template <typename T>
+int norm_inf(Matrix& A, double* out, cudaStream_t s)
+{
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    *out = 0.0;
+    if (A.m == 0 || A.n == 0) return SB200_OK;
+    DevBuf rs, cs;
+    SB_TRY(rs.alloc(size_t(A.m) * sizeof(double)));
+    SB_TRY(cs.alloc(A.col_start.size() * sizeof(int64_t)));
+    CUDA_TRY(cudaMemcpyAsync(cs.p, A.col_start.data(), A.col_start.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    const int threads = int(std::min<int64_t>(1024, std::max<int64_t>(32, ceil_div(A.nb, 32) * 32)));
+    rowsum_kernel<T><<<unsigned(A.mt), threads, size_t(A.nb) * sizeof(double), s>>>(
+        reinterpret_cast<const T*>(A.pool), cs.as<int64_t>(), rs.as<double>(), A.kind, A.m, A.n, int(A.nb), A.mt, A.nt);
+    SB_TRY(launch_status());
+    std::vector<double> h(static_cast<size_t>(A.m));
+    CUDA_TRY(cudaMemcpyAsync(h.data(), rs.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    double mx = 0.0;
+    for (double v : h) mx = (v > mx || v != v) ? v : mx;
+    *out = mx;
+    return SB200_OK;
+}
+
+template <typename T>
+static int col_norms_max(Matrix& X, std::vector<double>& out, double* dscratch, cudaStream_t s)
+{
+    out.assign(size_t(X.n), 0.0);
+    if (X.n == 0 || X.m == 0) return SB200_OK;
+    colmax_kernel<T><<<unsigned(X.n), 256, 0, s>>>(reinterpret_cast<const T*>(X.pool), dscratch, X.m, int(X.nb), X.mt);
+    SB_TRY(launch_status());
+    CUDA_TRY(cudaMemcpyAsync(out.data(), dscratch, out.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SB200_OK;
+}
+
+// src/internal/internal_util.hh:121-138
+static bool iter_ref_converged(const std::vector<double>& r, const std::vector<double>& x, double cte)
+{
+    for (size_t i = 0; i < x.size(); ++i)
+        if (r[i] > x[i] * cte) return false;
+    return true;
+}
+
+struct Clock {
+    std::chrono::steady_clock::time_point t;
+    void start() { cudaDeviceSynchronize(); t = std::chrono::steady_clock::now(); }
+    double stop() { cudaDeviceSynchronize(); return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); }
+};
+
+struct TmpMatrix {
+    Matrix M;
+    int like(const Matrix& o, int dtype) { return matrix_alloc(*o.g, dtype, o.kind, o.m, o.n, o.nb, M); }
+    ~TmpMatrix() { if (M.pool) cudaFree(M.pool); }
+};
+
+static bool mixed_use_tc05()
+{
+    const char* e = getenv("SB200_MIXED_TC05");
+    return ! (e && atoi(e) == 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// posv_mixed / gesv_mixed, double <- float (src/posv_mixed.cc:111-297, src/gesv_mixed.cc:106-300):
+// identical control flow, stopping rule and iter / info conventions.
+// timers_ms (optional, 8 doubles): total, factor_lo, solve_lo (summed), residual_hi (summed), add_hi (summed),
+// factor_hi (fallback), solve_hi (fallback), norm+convert
+// ------------------------------------------------------------------------------------------
+int solve_mixed_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B, Matrix& X,
+                  int64_t itermax, double tol, bool use_fallback, int* iter_out, int64_t* info_out, double* timers_ms)
+{
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.dtype != 'd' || B.dtype != 'd' || X.dtype != 'd') return SB200_EINVAL;
+    if (A.kind != (hermitian ? 'H' : 'G') || A.m != A.n || B.m != A.n || X.m != A.n || X.n != B.n
+        || B.nb != A.nb || X.nb != A.nb || B.kind != 'G' || X.kind != 'G') return SB200_EINVAL;
+    const double eps = std::numeric_limits<double>::epsilon();
+    if (tol <= 0) tol = eps * std::sqrt(double(A.m));
+    if (itermax < 0) itermax = 30;
+    double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    Clock total, c;
+    total.start();
+    cudaStream_t s = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    struct SG { cudaStream_t s; ~SG() { cudaStreamDestroy(s); } } sguard{s};
+
+    TmpMatrix Rm, A_lo, X_lo;
+    SB_TRY(Rm.like(B, 'd'));
+    SB_TRY(A_lo.like(A, 's'));
+    SB_TRY(X_lo.like(X, 's'));
+    DevBuf dnorm, dperm;
+    SB_TRY(dnorm.alloc(size_t(std::max<int64_t>(X.n, 1)) * sizeof(double)));
+    std::vector<double> cn_x, cn_r;
+    std::vector<int64_t> piv_lo(size_t(2 * std::max<int64_t>(A.m, 1)));
+    std::vector<int> perm;
+
+    c.start();
+    double Anorm = 0;
+    SB_TRY(norm_inf<double>(A, &Anorm, s));
+    const double cte = Anorm * tol;
+    SB_TRY((convert_pool<double, float>(B, X_lo.M, s)));
+    SB_TRY((convert_pool<double, float>(A, A_lo.M, s)));
+    tm[7] = c.stop();
+
+    bool converged = false;
+    int iter = 0;
+    int64_t info = 0;
+    const bool tc = mixed_use_tc05();
+    c.start();
+    if (hermitian) SB_TRY(potrf_driver<float>(A_lo.M, &info, tc));
+    else           SB_TRY(getrf_driver_s(A_lo.M, piv_lo.data(), &info, tc));
+    tm[1] = c.stop();
+
+    auto solve_lo = [&]() -> int {
+        c.start();
+        if (hermitian) SB_TRY(potrs_t<float>(A_lo.M, X_lo.M, s));
+        else           SB_TRY(getrs_t<float>(A_lo.M, dperm.as<int>(), X_lo.M, s));
+        tm[2] += c.stop();
+        return SB200_OK;
+    };
+    auto residual = [&]() -> int {          // R = B - A X
+        c.start();
+        SB_TRY(copy_pool(B, Rm.M, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (hermitian) SB_TRY(hemm_left_lower<double>(-1.0, A, X, 1.0, Rm.M, s));
+        else           SB_TRY(gemm_driver<double>(-1.0, A, X, 1.0, Rm.M));
+        tm[3] += c.stop();
+        SB_TRY(col_norms_max<double>(X, cn_x, dnorm.as<double>(), s));
+        SB_TRY(col_norms_max<double>(Rm.M, cn_r, dnorm.as<double>(), s));
+        return SB200_OK;
+    };
+
+    if (info != 0) iter = -3;
+    else {
+        if (! hermitian) {
+            pivots_to_perm(piv_lo.data(), A.m, A.n, A.nb, perm);
+            SB_TRY(dperm.alloc(perm.size() * sizeof(int)));
+            CUDA_TRY(cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+        SB_TRY(solve_lo());
+        SB_TRY((convert_pool<float, double>(X_lo.M, X, s)));
+        SB_TRY(residual());
+        if (iter_ref_converged(cn_r, cn_x, cte)) { iter = 0; converged = true; }
+        for (int64_t iiter = 0; iiter < itermax && ! converged; ++iiter) {
+            SB_TRY((convert_pool<double, float>(Rm.M, X_lo.M, s)));
+            SB_TRY(solve_lo());
+            c.start();
+            SB_TRY((convert_pool<float, double>(X_lo.M, Rm.M, s)));
+            SB_TRY(add_pool<double>(Rm.M, X, s));
+            tm[4] += c.stop();
+            SB_TRY(residual());
+            if (iter_ref_converged(cn_r, cn_x, cte)) { iter = int(iiter) + 1; converged = true; }
+        }
+    }
+    if (! converged) {
+        if (info == 0) iter = -int(itermax) - 1;
+        if (use_fallback) {
+            c.start();
+            if (hermitian) SB_TRY(potrf_driver<double>(A, &info, false));
+            else           SB_TRY(getrf_driver(A, pivots_out ? pivots_out : piv_lo.data(), &info));
+            tm[5] = c.stop();
+            c.start();
+            if (info == 0) {
+                SB_TRY(copy_pool(B, X, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                if (hermitian) SB_TRY(potrs_t<double>(A, X, s));
+                else {
+                    const int64_t* pv = pivots_out ? pivots_out : piv_lo.data();
+                    pivots_to_perm(pv, A.m, A.n, A.nb, perm);
+                    DevBuf dp;
+                    SB_TRY(dp.alloc(perm.size() * sizeof(int)));
+                    CUDA_TRY(cudaMemcpyAsync(dp.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+                    SB_TRY(getrs_t<double>(A, dp.as<int>(), X, s));
+                }
+            }
+            tm[6] = c.stop();
+        }
+    }
+    else if (pivots_out && ! hermitian)
+        memcpy(pivots_out, piv_lo.data(), size_t(2 * std::min(A.m, A.n)) * sizeof(int64_t));
+    tm[0] = total.stop();
+    X.last_ms = tm[0];
+    if (timers_ms) memcpy(timers_ms, tm, sizeof(tm));
+    if (iter_out) *iter_out = iter;
+    if (info_out) *info_out = info;
+    return SB200_OK;
+}
+
+} // namespace sb200
+
+using namespace sb200;
+
+template <typename A> struct CuS { using type = A; };
+template <> struct CuS<sb200_c32> { using type = cuFloatComplex; };
+template <> struct CuS<sb200_c64> { using type = cuDoubleComplex; };
+static inline float  cvv(float v) { return v; }
+static inline double cvv(double v) { return v; }
+static inline cuFloatComplex  cvv(sb200_c32 v) { return make_cuFloatComplex(v.re, v.im); }
+static inline cuDoubleComplex cvv(sb200_c64 v) { return make_cuDoubleComplex(v.re, v.im); }
+
+extern "C" {
+
+#define SB200_DEF_SOLVE(X, T, R) \
+int sb200_potrs_##X(sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts) \
+{ \
+    (void) opts; \
+    if (! A || ! B) return SB200_EINVAL; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return potrs_t<CuS<T>::type>(A->A, B->A, nullptr); \
+} \
+int sb200_hemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    (void) opts; \
+    if (! A || ! Xm || ! C) return SB200_EINVAL; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || Xm->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return hemm_left_lower<CuS<T>::type>(cvv(alpha), A->A, Xm->A, cvv(beta), C->A, nullptr); \
+} \
+int sb200_norm_inf_##X(sb200_matrix_t A, double* value) \
+{ \
+    if (! A || ! value) return SB200_EINVAL; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return norm_inf<CuS<T>::type>(A->A, value, nullptr); \
+}
+SB200_FOR_TYPES(SB200_DEF_SOLVE)
+
+static int getrs_any(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B)
+{
+    if (! A || ! B || ! pivots) return SB200_EINVAL;
+    if (A->A.g->size() > 1) return SB200_ENOTSUP;
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<int> perm;
+    pivots_to_perm(pivots, A->A.m, A->A.n, A->A.nb, perm);
+    DevBuf dp;
+    SB_TRY(dp.alloc(perm.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(dp.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (A->A.dtype == 'd') return getrs_t<double>(A->A, dp.as<int>(), B->A, nullptr);
+    if (A->A.dtype == 's') return getrs_t<float>(A->A, dp.as<int>(), B->A, nullptr);
+    return SB200_ENOTSUP;
+}
+
+int sb200_getrs_d(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts)
+{ (void) opts; return (A && A->A.dtype == 'd') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
+int sb200_getrs_s(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts)
+{ (void) opts; return (A && A->A.dtype == 's') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
+
+int sb200_posv_mixed_d(sb200_matrix_t A, sb200_matrix_t B, sb200_matrix_t Xm, const sb200_mixed_options_t* mo,
+                       int* iter, int64_t* info, double* timers_ms8)
+{
+    if (! A || ! B || ! Xm) return SB200_EINVAL;
+    return solve_mixed_d(true, A->A, nullptr, B->A, Xm->A, mo ? mo->max_iterations : 30, mo ? mo->tolerance : 0.0,
+                         mo ? mo->use_fallback_solver != 0 : true, iter, info, timers_ms8);
+}
+
+int sb200_gesv_mixed_d(sb200_matrix_t A, int64_t* pivots, sb200_matrix_t B, sb200_matrix_t Xm,
+                       const sb200_mixed_options_t* mo, int* iter, int64_t* info, double* timers_ms8)
+{
+    if (! A || ! B || ! Xm) return SB200_EINVAL;
+    return solve_mixed_d(false, A->A, pivots, B->A, Xm->A, mo ? mo->max_iterations : 30, mo ? mo->tolerance : 0.0,
+                         mo ? mo->use_fallback_solver != 0 : true, iter, info, timers_ms8);
+}
+
+} // extern "C"

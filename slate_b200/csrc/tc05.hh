@@ -18,6 +18,7 @@ struct Tc05Params {
     int m, n, k, ldc;
     float alpha, beta;
     int batch;
+    int tri;                    // 0 full, 1 keep lower (row >= col): herk/syrk diagonal tiles of the Cholesky update
 };
 
 // pack `batch` operands: element (r, kk) of operand t = X_t[r * rs + kk * ks], r < rows, kk < k
