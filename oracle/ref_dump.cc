@@ -14,7 +14,7 @@
 // produced them is tests/golden/make_golden.py).
 //
 // usage: ref_dump ROUTINE TYPE n nb seedA seedB seedC OUTPREFIX [key=value ...]
-//   ROUTINE  gen | gemm | herk | potrf | getrf | trsm | gesv_mixed | norms
+//   ROUTINE  gen | gemm | herk | potrf | getrf | trsm | gesv_mixed | posv_mixed | posv | gesv | hemm | norms
 //   TYPE     s | d | c | z
 //   keys     kind=rand|rand_dominant  la=1  ib=16  threads=N  dump=0|1  nrhs=10  pt=panel threads
 //            m= k= (gemm/herk rectangular)  uplo=l|u
@@ -273,6 +273,64 @@ int run(const Args& a)
             std::fprintf(stderr, "gesv_mixed needs type d or z\n");
             return 2;
         }
+    }
+    else if (a.routine == "posv_mixed" || a.routine == "posv") {
+        // Hermitian positive definite solve: posv = chol_factor + chol_solve_using_factor
+        // (test/test_posv.cc:205-232); posv_mixed = src/posv_mixed.cc
+        slate::HermitianMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        A.insertLocalTiles();
+        slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand_dominant"); p.seed = a.seedA;
+        p.cond_request = p.cond_actual = p.condD = NAN;
+        slate::generate_matrix(p, A);
+        auto B = make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
+        if (a.routine == "posv") {
+            auto t0 = tic();
+            info = slate::chol_factor(A, opts);
+            if (info == 0) slate::chol_solve_using_factor(A, B, opts);
+            seconds = toc(t0);
+            gflop = lapack::Gflop<T>::posv(n, nrhs);
+            if (dump) { auto d = to_dense(B); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
+        }
+        else if constexpr (std::is_same<real_t, double>::value) {
+            slate::Matrix<T> X(n, nrhs, nb, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+            X.insertLocalTiles();
+            auto t0 = tic();
+            info = slate::posv_mixed(A, B, X, iters, opts);
+            seconds = toc(t0);
+            gflop = lapack::Gflop<T>::posv(n, nrhs);
+            if (dump) { auto d = to_dense(X); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
+        }
+        else {
+            std::fprintf(stderr, "posv_mixed needs type d or z\n");
+            return 2;
+        }
+    }
+    else if (a.routine == "gesv") {
+        // lu_factor + lu_solve_using_factor (test/test_gesv.cc:225-260)
+        auto A = make_matrix<T>(n, n, nb, a.seedA, a.get("kind", "rand"));
+        auto B = make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
+        slate::Pivots pivots;
+        auto t0 = tic();
+        info = slate::lu_factor(A, pivots, opts);
+        if (info == 0) slate::lu_solve_using_factor(A, pivots, B, opts);
+        seconds = toc(t0);
+        gflop = lapack::Gflop<T>::gesv(n, nrhs);
+        if (dump) { auto d = to_dense(B); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
+    }
+    else if (a.routine == "hemm") {
+        // C = alpha A B + beta C, A Hermitian (lower), Side::Left (test/test_hemm.cc)
+        slate::HermitianMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        A.insertLocalTiles();
+        slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand"); p.seed = a.seedA;
+        p.cond_request = p.cond_actual = p.condD = NAN;
+        slate::generate_matrix(p, A);
+        auto B = make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
+        auto C = make_matrix<T>(n, nrhs, nb, a.seedC, "rand");
+        auto t0 = tic();
+        slate::hemm(slate::Side::Left, alpha, A, B, beta, C, opts);
+        seconds = toc(t0);
+        gflop = blas::Gflop<T>::hemm(slate::Side::Left, n, nrhs);
+        if (dump) { auto d = to_dense(C); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
     }
     else if (a.routine == "norms") {
         // max / one / inf / fro of a general rand matrix: slate::norm (src/norm.cc)

@@ -291,6 +291,120 @@ def trsm_tile(side: str, uplo: str, op: str, diag: str, alpha, T, B):
 
 
 # ----------------------------------------------------------------------------
+# solve path: block-row sweeps of work::trsm (src/work/work_trsm.cc:60-230), potrs
+# (src/potrs.cc:54-77), getrs (src/getrs.cc:25-66), hemm (src/hemmC.cc, Left/Lower) and the
+# Hermitian inf-norm (src/norm.cc -> internal_henorm.cc: row sums over the implied full matrix)
+# ----------------------------------------------------------------------------
+def tri_sweep(Tm, B, nb: int, lower: bool, op: str = "N", unit: bool = False):
+    """B <- op(T)^{-1} B, one diagonal-tile solve + gemm update of the remaining block rows per step."""
+    from scipy.linalg import solve_triangular
+    B = np.array(B, order="F", copy=True)
+    n = Tm.shape[0]
+    tl = _tiles(n, nb)
+    trans = op != "N"
+    M = Tm if not trans else (Tm.conj().T if op == "C" else Tm.T)      # op(T) as a math matrix
+    eff_lower = lower != trans
+    order = tl if eff_lower else tl[::-1]
+    for (k0, k1) in order:
+        B[k0:k1] = solve_triangular(M[k0:k1, k0:k1], B[k0:k1], lower=eff_lower, unit_diagonal=unit)
+        rows = [(i0, i1) for (i0, i1) in tl if (i0 > k0 if eff_lower else i0 < k0)]
+        for (i0, i1) in rows:
+            B[i0:i1] -= M[i0:i1, k0:k1] @ B[k0:k1]
+    return B
+
+
+def potrs(L, B, nb: int):
+    """Solve A X = B with A = L L^H (lower factor from potrf)."""
+    Y = tri_sweep(np.tril(L), B, nb, lower=True, op="N")
+    return tri_sweep(np.tril(L), Y, nb, lower=True, op="C")
+
+
+def getrs(LU, pivots, B, nb: int):
+    """Solve A X = B with P A = L U from getrf (pivots as slate::Pivots)."""
+    perm = pivots_to_perm(pivots, LU.shape[0], nb)
+    PB = np.asarray(B)[perm]
+    Y = tri_sweep(np.tril(LU, -1) + np.eye(LU.shape[0], dtype=LU.dtype), PB, nb, lower=True, unit=True)
+    return tri_sweep(np.triu(LU), Y, nb, lower=False)
+
+
+def he_full(A_lower):
+    """Full Hermitian matrix from its stored lower triangle (diagonal taken real)."""
+    L = np.tril(A_lower)
+    F = L + np.tril(L, -1).conj().T
+    if np.iscomplexobj(F):
+        d = np.arange(F.shape[0])
+        F[d, d] = F[d, d].real
+    return F
+
+
+def hemm(alpha, A_lower, B, beta, C, nb: int):
+    """C = alpha A B + beta C, A Hermitian given by its lower triangle; accumulated one block column
+    of A at a time (src/hemmC.cc: Left, Lower)."""
+    A = he_full(A_lower)
+    C = beta * np.array(C, order="F", copy=True)
+    for (k0, k1) in _tiles(A.shape[0], nb):
+        C += alpha * (A[:, k0:k1] @ B[k0:k1])
+    return C
+
+
+def norm_inf(A, hermitian_lower: bool = False):
+    F = he_full(A) if hermitian_lower else np.asarray(A)
+    return float(np.abs(F).sum(axis=1).max())
+
+
+def iter_ref_converged(colnorms_R, colnorms_X, cte) -> bool:       # src/internal/internal_util.hh:121-138
+    return not np.any(np.asarray(colnorms_R) > np.asarray(colnorms_X) * cte)
+
+
+def solve_mixed(A, B, nb: int, hermitian: bool, itermax: int = 30, tol=None, use_fallback: bool = True,
+                ib: int = 16):
+    """posv_mixed / gesv_mixed <double, float> (src/posv_mixed.cc:111-297, src/gesv_mixed.cc:106-300).
+    A: full matrix (gesv) or lower triangle (posv).  Returns (X, iter, info)."""
+    A = np.asarray(A, dtype=np.float64)
+    B = np.asarray(B, dtype=np.float64)
+    n = A.shape[0]
+    eps = np.finfo(np.float64).eps
+    tol = eps * np.sqrt(n) if tol is None else tol
+    Afull = he_full(A) if hermitian else A
+    cte = norm_inf(A, hermitian) * tol
+    A_lo = (np.tril(A) if hermitian else A).astype(np.float32)
+    if hermitian:
+        F_lo, info = potrf(he_full(A_lo), nb)
+        solve_lo = lambda R: potrs(F_lo, R.astype(np.float32), nb)
+    else:
+        F_lo, piv, info = getrf(A_lo, nb, ib)
+        solve_lo = lambda R: getrs(F_lo, piv, R.astype(np.float32), nb)
+    converged, it = False, 0
+    X = np.zeros_like(B)
+    if info != 0:
+        it = -3
+    else:
+        X = solve_lo(B).astype(np.float64)
+        R = B - Afull @ X
+        cm = lambda M: np.abs(M).max(axis=0)
+        if iter_ref_converged(cm(R), cm(X), cte):
+            converged = True
+        for iiter in range(itermax):
+            if converged:
+                break
+            X = X + solve_lo(R).astype(np.float64)
+            R = B - Afull @ X
+            if iter_ref_converged(cm(R), cm(X), cte):
+                it, converged = iiter + 1, True
+    if not converged:
+        if info == 0:
+            it = -itermax - 1
+        if use_fallback:
+            if hermitian:
+                F, info = potrf(Afull, nb)
+                X = potrs(F, B, nb) if info == 0 else X
+            else:
+                F, piv, info = getrf(A, nb, ib)
+                X = getrs(F, piv, B, nb) if info == 0 else X
+    return X, it, info
+
+
+# ----------------------------------------------------------------------------
 # memory-bound tile kernels (src/cuda/*.cu; include/slate/internal/device.hh:92-281)
 # ----------------------------------------------------------------------------
 def geadd(alpha, A, beta, B):            # device_geadd.cu:61-85

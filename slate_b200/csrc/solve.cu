@@ -457,6 +457,10 @@ int solve_mixed_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B, Mat
     if (hermitian) SB_TRY(potrf_driver<float>(A_lo.M, &info, tc));
     else           SB_TRY(getrf_driver_s(A_lo.M, piv_lo.data(), &info, tc));
     tm[1] = c.stop();
+    // the factorisation's device-side statistics are reported on X (sb200_last_driver_stats)
+    X.last_trail_ms = A_lo.M.last_trail_ms; X.last_trail_flops = A_lo.M.last_trail_flops;
+    X.last_trail_launches = A_lo.M.last_trail_launches; X.last_panel_ms = A_lo.M.last_panel_ms;
+    const double factor_device_ms = A_lo.M.last_ms;
 
     auto solve_lo = [&]() -> int {
         c.start();
@@ -528,6 +532,7 @@ int solve_mixed_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B, Mat
         memcpy(pivots_out, piv_lo.data(), size_t(2 * std::min(A.m, A.n)) * sizeof(int64_t));
     tm[0] = total.stop();
     X.last_ms = tm[0];
+    (void) factor_device_ms;
     if (timers_ms) memcpy(timers_ms, tm, sizeof(tm));
     if (iter_out) *iter_out = iter;
     if (info_out) *info_out = info;

@@ -16,7 +16,20 @@ import os
 
 import numpy as np
 
-from ._lib import lib, check, SB200Error, c_i64, c_int, c_dbl, c_ptr, _sig
+from ._lib import lib, check, SB200Error, c_i64, c_int, c_dbl, c_ptr, _sig, scalar, SCALAR_T, REAL_T
+
+NP_DTYPE = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
+_DTYPE_CHAR = {np.dtype(v): k for k, v in NP_DTYPE.items()}
+
+
+def dtype_char(dtype) -> str:
+    """'s' | 'd' | 'c' | 'z' for a numpy dtype / type character."""
+    if isinstance(dtype, str) and dtype in NP_DTYPE:
+        return dtype
+    try:
+        return _DTYPE_CHAR[np.dtype(dtype)]
+    except (KeyError, TypeError):
+        raise Exception_(f"unsupported element type {dtype!r}") from None
 
 
 class Exception_(SB200Error):
@@ -31,20 +44,42 @@ class _Options(ctypes.Structure):
 _grid_unique_id = _sig("sb200_grid_unique_id", [c_ptr])
 _grid_create = _sig("sb200_grid_create", [c_int, c_int, c_int, c_ptr, ctypes.POINTER(c_ptr)])
 _grid_destroy = _sig("sb200_grid_destroy", [c_ptr])
-_matrix_create = _sig("sb200_matrix_create_d", [c_ptr, c_int, c_int, c_i64, c_i64, c_i64, ctypes.POINTER(c_ptr)])
+class _MixedOptions(ctypes.Structure):
+    _fields_ = [("max_iterations", c_i64), ("tolerance", c_dbl), ("use_fallback_solver", c_int),
+                ("reserved", c_int * 5)]
+
+
+_OP = ctypes.POINTER(_Options)
+_matrix_create = {t: _sig(f"sb200_matrix_create_{t}", [c_ptr, c_int, c_int, c_i64, c_i64, c_i64, ctypes.POINTER(c_ptr)])
+                  for t in "sdcz"}
 _matrix_destroy = _sig("sb200_matrix_destroy", [c_ptr])
-_matrix_generate = _sig("sb200_matrix_generate_d", [c_ptr, c_int, c_i64, c_ptr])
-_matrix_from_host = _sig("sb200_matrix_from_host_d", [c_ptr, c_ptr, c_i64, c_ptr])
-_matrix_to_host = _sig("sb200_matrix_to_host_d", [c_ptr, c_ptr, c_i64, c_ptr])
-_matrix_from_host_local = _sig("sb200_matrix_from_host_local_d", [c_ptr, c_ptr, c_ptr])
-_matrix_to_host_local = _sig("sb200_matrix_to_host_local_d", [c_ptr, c_ptr, c_ptr])
+_matrix_generate = _sig("sb200_matrix_generate", [c_ptr, c_int, c_i64, c_ptr])
+_matrix_from_host = _sig("sb200_matrix_from_host", [c_ptr, c_ptr, c_i64, c_ptr])
+_matrix_to_host = _sig("sb200_matrix_to_host", [c_ptr, c_ptr, c_i64, c_ptr])
+_matrix_from_host_local = _sig("sb200_matrix_from_host_local", [c_ptr, c_ptr, c_ptr])
+_matrix_to_host_local = _sig("sb200_matrix_to_host_local", [c_ptr, c_ptr, c_ptr])
 _last_panel_ms = _sig("sb200_last_driver_panel_ms", [c_ptr], c_dbl)
-_matrix_copy = _sig("sb200_matrix_copy_d", [c_ptr, c_ptr, c_ptr])
+_matrix_copy = _sig("sb200_matrix_copy", [c_ptr, c_ptr, c_ptr])
 _matrix_local_tiles = _sig("sb200_matrix_local_tiles", [c_ptr], c_i64)
 _last_ms = _sig("sb200_last_driver_ms", [c_ptr], c_dbl)
-_potrf = _sig("sb200_potrf_d", [c_ptr, ctypes.POINTER(_Options), ctypes.POINTER(c_i64)])
-_gemm = _sig("sb200_gemm_d", [c_dbl, c_ptr, c_ptr, c_dbl, c_ptr, ctypes.POINTER(_Options)])
-_getrf = _sig("sb200_getrf_d", [c_ptr, ctypes.POINTER(c_i64), ctypes.POINTER(_Options), ctypes.POINTER(c_i64)])
+_potrf = {t: _sig(f"sb200_potrf_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64)]) for t in "sdcz"}
+_potrf["s_tc05"] = _sig("sb200_potrf_tc05_s", [c_ptr, _OP, ctypes.POINTER(c_i64)])
+_gemm = {t: _sig(f"sb200_gemm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+_herk = {t: _sig(f"sb200_herk_mat_{t}", [REAL_T[t], c_ptr, REAL_T[t], c_ptr, _OP]) for t in "sdcz"}
+_hemm = {t: _sig(f"sb200_hemm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+_potrs = {t: _sig(f"sb200_potrs_{t}", [c_ptr, c_ptr, _OP]) for t in "sdcz"}
+_norm_inf = {t: _sig(f"sb200_norm_inf_{t}", [c_ptr, ctypes.POINTER(c_dbl)]) for t in "sdcz"}
+_getrf = {"d": _sig("sb200_getrf_d", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)]),
+          "s": _sig("sb200_getrf_s", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)]),
+          "s_tc05": _sig("sb200_getrf_tc05_s", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)])}
+_getrs = {t: _sig(f"sb200_getrs_{t}", [c_ptr, ctypes.POINTER(c_i64), c_ptr, _OP]) for t in "sd"}
+_posv_mixed = _sig("sb200_posv_mixed_d", [c_ptr, c_ptr, c_ptr, ctypes.POINTER(_MixedOptions), ctypes.POINTER(c_int),
+                                          ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)])
+_gesv_mixed = _sig("sb200_gesv_mixed_d", [c_ptr, ctypes.POINTER(c_i64), c_ptr, c_ptr, ctypes.POINTER(_MixedOptions),
+                                          ctypes.POINTER(c_int), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)])
+tile_rank = _sig("sb200_tile_rank", [c_int, c_int, c_i64, c_i64])
+local_tile_count = _sig("sb200_local_tile_count", [c_int, c_int, c_int, c_int, c_i64, c_i64, c_i64], c_i64)
+local_tile_index = _sig("sb200_local_tile_index", [c_int, c_int, c_int, c_i64, c_i64, c_i64, c_i64, c_i64], c_i64)
 
 
 def _stream():
@@ -129,12 +164,14 @@ class Matrix:
     """General m-by-n tile matrix, nb-by-nb tiles, 2-D block-cyclic over the grid, resident in HBM."""
     _kind = "G"
 
-    def __init__(self, m: int, n: int, nb: int, grid: Grid | None = None):
+    def __init__(self, m: int, n: int, nb: int, grid: Grid | None = None, dtype="d"):
         self.grid = grid or default_grid()
         self.m, self.n, self.nb = int(m), int(n), int(nb)
+        self.t = dtype_char(dtype)
+        self.dtype = np.dtype(NP_DTYPE[self.t])
         h = c_ptr()
-        check(_matrix_create(self.grid._h, ord(self._kind), ord("C"), self.m, self.n, self.nb, ctypes.byref(h)),
-              "Matrix")
+        check(_matrix_create[self.t](self.grid._h, ord(self._kind), ord("C"), self.m, self.n, self.nb,
+                                     ctypes.byref(h)), "Matrix")
         self._h = h
 
     # -- data movement -------------------------------------------------------------------
@@ -149,7 +186,7 @@ class Matrix:
         """Copy locally-owned tiles from a host column-major (m, n) array of the GLOBAL matrix.
         `hA`: numpy F-ordered float64 array or a torch CPU tensor whose memory is column-major
         (i.e. a (n, m) row-major tensor); pinned memory makes the copy asynchronous."""
-        ptr, lda = _host_ptr(hA, self.m, self.n)
+        ptr, lda = _host_ptr(hA, self.m, self.n, self.dtype)
         check(_matrix_from_host(self._h, ptr, lda, _stream()), "from_host")
         if sync:
             import torch
@@ -159,8 +196,8 @@ class Matrix:
     def to_host(self, out=None):
         import torch
         if out is None:
-            out = np.zeros((self.m, self.n), dtype=np.float64, order="F")
-        ptr, lda = _host_ptr(out, self.m, self.n)
+            out = np.zeros((self.m, self.n), dtype=self.dtype, order="F")
+        ptr, lda = _host_ptr(out, self.m, self.n, self.dtype)
         check(_matrix_to_host(self._h, ptr, lda, _stream()), "to_host")
         torch.cuda.current_stream().synchronize()
         return out
@@ -186,9 +223,9 @@ class Matrix:
     def _check_local(self, t):
         import torch
         need = self.local_tiles * self.nb * self.nb
-        if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.dtype == torch.float64
+        if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.dtype == _torch_dtype(self.dtype)
                 and t.is_contiguous() and t.numel() == need):
-            raise Exception_(f"local tile buffer must be a contiguous float64 CPU tensor of {need} elements")
+            raise Exception_(f"local tile buffer must be a contiguous {self.dtype} CPU tensor of {need} elements")
 
     def copy_from(self, other: "Matrix"):
         check(_matrix_copy(self._h, other._h, _stream()), "copy")
@@ -223,48 +260,111 @@ class HermitianMatrix(Matrix):
     (slate::HermitianMatrix with Uplo::Lower, include/slate/HermitianMatrix.hh)."""
     _kind = "H"
 
-    def __init__(self, n: int, nb: int, grid: Grid | None = None, uplo: str = "L"):
+    def __init__(self, n: int, nb: int, grid: Grid | None = None, uplo: str = "L", dtype="d"):
         if uplo.upper()[0] != "L":
             raise Exception_("only Uplo::Lower storage is implemented")
-        super().__init__(n, n, nb, grid)
+        super().__init__(n, n, nb, grid, dtype)
 
 
-def _host_ptr(a, m, n):
+def _torch_dtype(dt):
+    import torch
+    return {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+            np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128}[np.dtype(dt)]
+
+
+def _host_ptr(a, m, n, dtype=np.float64):
+    dtype = np.dtype(dtype)
     try:
         import torch
         if isinstance(a, torch.Tensor):
-            if a.device.type != "cpu" or a.dtype != torch.float64 or not a.is_contiguous():
-                raise Exception_("host tensor must be a contiguous float64 CPU tensor")
+            if a.device.type != "cpu" or a.dtype != _torch_dtype(dtype) or not a.is_contiguous():
+                raise Exception_(f"host tensor must be a contiguous {dtype} CPU tensor")
             if tuple(a.shape) != (n, m):
                 raise Exception_(f"host tensor holding a column-major {m}x{n} matrix must have shape ({n}, {m})")
             return a.data_ptr(), max(m, 1)
     except ImportError:
         pass
-    if not isinstance(a, np.ndarray) or a.dtype != np.float64 or a.shape != (m, n) or not a.flags.f_contiguous:
-        raise Exception_(f"host array must be float64, shape ({m}, {n}), Fortran order")
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or a.shape != (m, n) or not a.flags.f_contiguous:
+        raise Exception_(f"host array must be {dtype}, shape ({m}, {n}), Fortran order")
     return a.ctypes.data, max(m, 1)
 
 
 # -- drivers ---------------------------------------------------------------------------------
-def gemm(alpha: float, A: Matrix, B: Matrix, beta: float, C: Matrix, opts: dict | None = None):
+def _same_type(*ms):
+    t = ms[0].t
+    for x in ms[1:]:
+        if x.t != t:
+            raise Exception_("operands must have the same element type")
+    return t
+
+
+def gemm(alpha, A: Matrix, B: Matrix, beta, C: Matrix, opts: dict | None = None):
     """C = alpha A B + beta C  (slate::gemm, src/gemm.cc:82-105 -> gemmC)."""
+    t = _same_type(A, B, C)
     o = _opts(opts)
-    check(_gemm(float(alpha), A._h, B._h, float(beta), C._h, ctypes.byref(o)), "gemm")
+    check(_gemm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "gemm")
 
 
 multiply = gemm     # simplified API name (include/slate/simplified_api.hh)
 
 
+def herk(alpha: float, A: Matrix, beta: float, C: "HermitianMatrix", opts: dict | None = None):
+    """C = alpha A A^H + beta C, C Hermitian (lower), alpha / beta real (slate::herk, src/herk.cc:25-162;
+    for real types this is syrk, as in the reference)."""
+    t = _same_type(A, C)
+    o = _opts(opts)
+    check(_herk[t](REAL_T[t](float(alpha)), A._h, REAL_T[t](float(beta)), C._h, ctypes.byref(o)), "herk")
+
+
+rank_k_update = herk
+
+
+def hemm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | None = None):
+    """C = alpha A B + beta C with A Hermitian, Side::Left (slate::hemm, src/hemmC.cc)."""
+    t = _same_type(A, B, C)
+    o = _opts(opts)
+    check(_hemm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "hemm")
+
+
+def norm_inf(A: Matrix) -> float:
+    """slate::norm(Norm::Inf, A) for a general or Hermitian matrix."""
+    v = c_dbl(0.0)
+    check(_norm_inf[A.t](A._h, ctypes.byref(v)), "norm")
+    return float(v.value)
+
+
 def potrf(A: HermitianMatrix, opts: dict | None = None) -> int:
     """Cholesky A = L L^H, lower (slate::potrf, src/potrf.cc:262-281).
-    Returns info: 0, or i > 0 if the leading minor of order i is not positive definite."""
+    Returns info: 0, or i > 0 if the leading minor of order i is not positive definite.
+    opts['tensor_core_fp32'] (float matrices only): run the trailing update on the tcgen05
+    FP32-emulated kernel, as posv_mixed does for its low-precision factorisation."""
     o = _opts(opts)
     info = c_i64(0)
-    check(_potrf(A._h, ctypes.byref(o), ctypes.byref(info)), "potrf")
+    key = A.t
+    if (opts or {}).get("tensor_core_fp32"):
+        if A.t != "s":
+            raise Exception_("tensor_core_fp32 applies to float matrices")
+        key = "s_tc05"
+    check(_potrf[key](A._h, ctypes.byref(o), ctypes.byref(info)), "potrf")
     return int(info.value)
 
 
 chol_factor = potrf
+
+
+def potrs(A: HermitianMatrix, B: Matrix, opts: dict | None = None):
+    """Solve A X = B with the Cholesky factor from potrf; B is overwritten by X (slate::potrs, src/potrs.cc)."""
+    t = _same_type(A, B)
+    o = _opts(opts)
+    check(_potrs[t](A._h, B._h, ctypes.byref(o)), "potrs")
+
+
+chol_solve_using_factor = potrs
+
+
+def _pivots_flat(pivots):
+    flat = [v for blk in pivots for pr in blk for v in pr]
+    return (c_i64 * max(len(flat), 1))(*flat)
 
 
 def getrf(A: Matrix, opts: dict | None = None):
@@ -275,7 +375,14 @@ def getrf(A: Matrix, opts: dict | None = None):
     info = c_i64(0)
     mn = min(A.m, A.n)
     flat = (c_i64 * (2 * max(mn, 1)))()
-    check(_getrf(A._h, flat, ctypes.byref(o), ctypes.byref(info)), "getrf")
+    key = A.t
+    if (opts or {}).get("tensor_core_fp32"):
+        if A.t != "s":
+            raise Exception_("tensor_core_fp32 applies to float matrices")
+        key = "s_tc05"
+    if key not in _getrf:
+        raise Exception_(f"getrf is implemented for float and double, not {A.dtype}")
+    check(_getrf[key](A._h, flat, ctypes.byref(o), ctypes.byref(info)), "getrf")
     piv = np.frombuffer(flat, dtype=np.int64)[: 2 * mn].reshape(-1, 2)
     nb = A.nb
     pivots = [[(int(t), int(off)) for t, off in piv[k0:min(k0 + nb, mn)]] for k0 in range(0, mn, nb)]
@@ -283,3 +390,48 @@ def getrf(A: Matrix, opts: dict | None = None):
 
 
 lu_factor = getrf
+
+
+def getrs(A: Matrix, pivots, B: Matrix, opts: dict | None = None):
+    """Solve A X = B with the LU factors and pivots from getrf; B is overwritten (slate::getrs, src/getrs.cc)."""
+    t = _same_type(A, B)
+    if t not in _getrs:
+        raise Exception_(f"getrs is implemented for float and double, not {A.dtype}")
+    o = _opts(opts)
+    check(_getrs[t](A._h, _pivots_flat(pivots), B._h, ctypes.byref(o)), "getrs")
+
+
+lu_solve_using_factor = getrs
+
+MIXED_TIMERS = ("total", "factor_lo", "solve_lo", "residual_hi", "add_hi", "factor_hi", "solve_hi", "norm_convert")
+
+
+def _mixed_opts(opts):
+    mo = _MixedOptions()
+    mo.max_iterations = int((opts or {}).get("max_iterations", 30))
+    mo.tolerance = float((opts or {}).get("tolerance", 0.0))
+    mo.use_fallback_solver = int(bool((opts or {}).get("use_fallback_solver", True)))
+    return mo
+
+
+def posv_mixed(A: HermitianMatrix, B: Matrix, X: Matrix, opts: dict | None = None):
+    """Mixed-precision Cholesky solve (slate::posv_mixed<double,float>, src/posv_mixed.cc:111-297).
+    Returns (info, iter, timers_ms): iter as the reference (>= 0 refinement steps, -3 low-precision
+    factor failed, -(max_iterations+1) not converged -> FP64 fallback, which overwrites A)."""
+    mo = _mixed_opts(opts)
+    it, info, tm = c_int(0), c_i64(0), (c_dbl * 8)()
+    check(_posv_mixed(A._h, B._h, X._h, ctypes.byref(mo), ctypes.byref(it), ctypes.byref(info), tm), "posv_mixed")
+    return int(info.value), int(it.value), dict(zip(MIXED_TIMERS, list(tm)))
+
+
+def gesv_mixed(A: Matrix, B: Matrix, X: Matrix, opts: dict | None = None):
+    """Mixed-precision LU solve (slate::gesv_mixed<double,float>, src/gesv_mixed.cc:106-300).
+    Returns (info, iter, pivots, timers_ms)."""
+    mo = _mixed_opts(opts)
+    it, info, tm = c_int(0), c_i64(0), (c_dbl * 8)()
+    mn = min(A.m, A.n)
+    flat = (c_i64 * (2 * max(mn, 1)))()
+    check(_gesv_mixed(A._h, flat, B._h, X._h, ctypes.byref(mo), ctypes.byref(it), ctypes.byref(info), tm), "gesv_mixed")
+    piv = np.frombuffer(flat, dtype=np.int64)[: 2 * mn].reshape(-1, 2)
+    pivots = [[(int(t), int(off)) for t, off in piv[k0:min(k0 + A.nb, mn)]] for k0 in range(0, mn, A.nb)]
+    return int(info.value), int(it.value), pivots, dict(zip(MIXED_TIMERS, list(tm)))

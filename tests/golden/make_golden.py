@@ -15,6 +15,11 @@ generator fixture pins that), only outputs:
   trsm_d.npz             Left/Lower/NoTrans/NonUnit solve, m=256 n=128 nb=64
   norms_d.npz            max/one/inf/fro of rand 200x136
   gesv_mixed_d.npz       solution + iteration count, n=256 nb=64
+  posv_mixed_d.npz       the same for the Cholesky mixed solver (rand_dominant), n=256 nb=64
+  posv_d.npz, posv_z.npz chol_factor + chol_solve_using_factor solution, n=300 nb=128 / n=192 nb=64 nrhs=70
+  gesv_d.npz             lu_factor + lu_solve_using_factor solution, n=300 nb=128
+  hemm_z.npz             C = alpha A B + beta C, A Hermitian lower, n=192 nb=64 nrhs=70
+  potrf_z.npz            complex Cholesky factor, n=192 nb=64
 
 Usage (in the build container, where /root/reference exists):  python tests/golden/make_golden.py
 """
@@ -73,6 +78,20 @@ def main():
     f, meta = run("gesv_mixed", "d", 256, 64)
     np.savez_compressed(os.path.join(OUT, "gesv_mixed_d.npz"), out=f["out"].reshape(256, 10, order="F"),
                         iters=meta["iters"], info=meta["info"])
+    # solve path and Hermitian mixed solver (round-1 widening)
+    f, meta = run("posv_mixed", "d", 256, 64)
+    np.savez_compressed(os.path.join(OUT, "posv_mixed_d.npz"), out=f["out"].reshape(256, 10, order="F"),
+                        iters=meta["iters"], info=meta["info"])
+    f, meta = run("posv", "d", 300, 128)
+    np.savez_compressed(os.path.join(OUT, "posv_d.npz"), out=f["out"].reshape(300, 10, order="F"), info=meta["info"])
+    f, meta = run("posv", "z", 192, 64, nrhs=70)
+    np.savez_compressed(os.path.join(OUT, "posv_z.npz"), out=f["out"].reshape(192, 70, order="F"), info=meta["info"])
+    f, meta = run("gesv", "d", 300, 128, ib=16, pt=1)
+    np.savez_compressed(os.path.join(OUT, "gesv_d.npz"), out=f["out"].reshape(300, 10, order="F"), info=meta["info"])
+    f, _ = run("hemm", "z", 192, 64, nrhs=70)
+    np.savez_compressed(os.path.join(OUT, "hemm_z.npz"), out=f["out"].reshape(192, 70, order="F"))
+    f, meta = run("potrf", "z", 192, 64)
+    np.savez_compressed(os.path.join(OUT, "potrf_z.npz"), out=f["out"].reshape(192, 192, order="F"), info=meta["info"])
     print("golden fixtures written to", OUT)
 
 

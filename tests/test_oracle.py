@@ -158,3 +158,85 @@ def test_live_reference_agrees_when_built(ref_dump, tmp_path):
     G = o.generate("rand_dominant", 200, 200, 11)
     L, info = o.potrf(np.tril(G) + np.tril(G, -1).T, 64)
     assert info == 0 and np.abs(L - np.tril(ref)).max() <= 16 * EPS * np.abs(ref).max()
+
+
+# ---------------------------------------------------------------------------- solve path / mixed solvers
+def test_posv_matches_reference(golden_dir):
+    g = load(golden_dir, "posv_d")
+    n, nb = 300, 128
+    G = o.generate("rand_dominant", n, n, 42); B = o.generate("rand", n, 10, 43)
+    L, info = o.potrf(o.he_full(G), nb)
+    X = o.potrs(L, B, nb)
+    assert info == int(g["info"]) == 0
+    assert np.abs(X - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+    assert o.solve_residual(o.he_full(G), X, B) <= 25 * EPS
+
+
+def test_posv_complex_matches_reference(golden_dir):
+    g = load(golden_dir, "posv_z")
+    n, nb = 192, 64
+    G = o.generate("rand_dominant", n, n, 42, np.complex128); B = o.generate("rand", n, 70, 43, np.complex128)
+    L, info = o.potrf(o.he_full(G), nb)
+    gz = load(golden_dir, "potrf_z")
+    assert info == int(gz["info"]) == 0
+    assert np.abs(L - np.tril(gz["out"])).max() <= 64 * EPS * np.abs(gz["out"]).max()
+    X = o.potrs(L, B, nb)
+    assert np.abs(X - g["out"]).max() <= 256 * EPS * np.abs(g["out"]).max()
+
+
+def test_gesv_matches_reference(golden_dir):
+    g = load(golden_dir, "gesv_d")
+    n, nb = 300, 128
+    A = o.generate("rand", n, n, 42); B = o.generate("rand", n, 10, 43)
+    LU, piv, info = o.getrf(A, nb, 16)
+    X = o.getrs(LU, piv, B, nb)
+    assert info == int(g["info"]) == 0
+    assert np.abs(X - g["out"]).max() <= 1e-10 * np.abs(g["out"]).max()
+    assert o.solve_residual(A, X, B) <= 25 * EPS
+
+
+def test_hemm_matches_reference(golden_dir):
+    g = load(golden_dir, "hemm_z")
+    n, nb, nrhs = 192, 64, 70
+    A = o.generate("rand", n, n, 42, np.complex128)
+    B = o.generate("rand", n, nrhs, 43, np.complex128); C = o.generate("rand", n, nrhs, 44, np.complex128)
+    out = o.hemm(ALPHA, A, B, BETA, C, nb)
+    assert np.abs(out - g["out"]).max() <= 8 * np.sqrt(n) * EPS * np.abs(g["out"]).max()
+
+
+def test_posv_mixed_matches_reference(golden_dir):
+    """Same control flow as src/posv_mixed.cc: same iteration count on the seeded system, same solution to FP64
+    refinement accuracy."""
+    g = load(golden_dir, "posv_mixed_d")
+    n, nb = 256, 64
+    G = o.generate("rand_dominant", n, n, 42); B = o.generate("rand", n, 10, 43)
+    X, it, info = o.solve_mixed(G, B, nb, hermitian=True)
+    assert info == int(g["info"]) == 0
+    assert it == int(g["iters"])
+    assert np.abs(X - g["out"]).max() <= 1e-13 * np.abs(g["out"]).max()
+    assert o.solve_residual(o.he_full(G), X, B) <= 25 * EPS
+
+
+def test_gesv_mixed_matches_reference(golden_dir):
+    g = load(golden_dir, "gesv_mixed_d")
+    n, nb = 256, 64
+    A = o.generate("rand", n, n, 42); B = o.generate("rand", n, 10, 43)
+    X, it, info = o.solve_mixed(A, B, nb, hermitian=False)
+    assert info == int(g["info"]) == 0
+    assert it == int(g["iters"])
+    assert np.abs(X - g["out"]).max() <= 1e-11 * np.abs(g["out"]).max()
+
+
+def test_mixed_fallback_and_failure_codes():
+    """iter = -3 when the low-precision factorisation fails, -(itermax+1) when refinement does not converge."""
+    n, nb = 96, 32
+    rng = np.random.default_rng(3)
+    Q = rng.random((n, n))
+    S = Q @ Q.T + n * np.eye(n)
+    S[5, 5] = -1.0                                           # not positive definite: potrf info = 6
+    X, it, info = o.solve_mixed(np.tril(S), rng.random((n, 3)), nb, hermitian=True, use_fallback=False)
+    assert it == -3 and info == 6
+    A = o.generate("rand", n, n, 1)
+    X, it, info = o.solve_mixed(A, rng.random((n, 3)), nb, hermitian=False, itermax=0, tol=1e-30, use_fallback=True)
+    assert it == -1 and info == 0
+    assert o.solve_residual(A, X, (A @ X)) <= 25 * EPS       # fallback solved in FP64
