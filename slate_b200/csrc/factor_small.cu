@@ -94,17 +94,25 @@ potrf_diag_kernel(T* __restrict__ A, int lda, int nv, T* __restrict__ Winv,
 // written to W + b*IB*IB (ld = IB), zero in the other triangle, padded with identity when the
 // last block is ragged.  lower != 0: T lower triangular; unit != 0: unit diagonal.
 // ---------------------------------------------------------------------------------------------
+// Batched form (gridDim.y > 1): tile y is Tarr[y], its blocks go to W + y * gridDim.x * IB * IB; the LAST tile
+// (y == gridDim.y - 1) has na_last rows, the others na.  Blocks wholly outside a ragged tile become identity.
 template <typename T>
 __global__ void __launch_bounds__(256)
-trtri_diag_kernel(const T* __restrict__ Tm, int ldt, int na, int lower, int unit, T* __restrict__ W)
+trtri_diag_kernel(const T* __restrict__ Tm, int ldt, int na, int lower, int unit, T* __restrict__ W,
+                  const T* const* __restrict__ Tarr = nullptr, int na_last = 0)
 {
     using R = typename RealOf<T>::type;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     T (*L)[IB + 1] = reinterpret_cast<T (*)[IB + 1]>(smem_dyn);   // always handled as LOWER:
     T (*X)[IB + 1] = L + IB;                                       // upper blocks are transposed in
     const int b = blockIdx.x, tid = threadIdx.x;
+    if (Tarr) {
+        Tm = Tarr[blockIdx.y];
+        W += int64_t(blockIdx.y) * gridDim.x * IB * IB;
+        if (blockIdx.y == gridDim.y - 1) na = na_last;
+    }
     const int o = b * IB;
-    const int nv = min(IB, na - o);
+    const int nv = max(0, min(IB, na - o));
     for (int e = tid; e < IB * IB; e += 256) {
         const int i = e % IB, j = e / IB;
         T v = (i == j) ? from_real<T>(R(1)) : zero_of<T>();
@@ -231,14 +239,20 @@ potrf_diag_fast_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv,
 // fast trtri of the diagonal IB-blocks (real types): same contract as trtri_diag_kernel
 template <typename R>
 __global__ void __launch_bounds__(IB, 1)
-trtri_diag_fast_kernel(const R* __restrict__ Tm, int ldt, int na, int lower, int unit, R* __restrict__ W)
+trtri_diag_fast_kernel(const R* __restrict__ Tm, int ldt, int na, int lower, int unit, R* __restrict__ W,
+                       const R* const* __restrict__ Tarr = nullptr, int na_last = 0)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     R* Ls = reinterpret_cast<R*>(smem_dyn);
     R* rd = Ls + IB * (IB + 1);
     const int b = blockIdx.x, tid = threadIdx.x;
+    if (Tarr) {
+        Tm = Tarr[blockIdx.y];
+        W += int64_t(blockIdx.y) * gridDim.x * IB * IB;
+        if (blockIdx.y == gridDim.y - 1) na = na_last;
+    }
     const int o = b * IB;
-    const int nv = min(IB, na - o);
+    const int nv = max(0, min(IB, na - o));
     // always handled as LOWER: upper blocks are transposed in.  Thread = row i of the lower block.
     #pragma unroll 8
     for (int j = 0; j < IB; ++j) {
@@ -279,6 +293,21 @@ static int launch_trtri_diag(int nblk, const T* Tm, int ldt, int na, int lower, 
         trtri_diag_fast_kernel<T><<<nblk, IB, fast_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
     else
         trtri_diag_kernel<T><<<nblk, 256, small_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
+    return launch_status();
+}
+
+// inverted diagonal IB-blocks of `ntiles` triangular tiles in ONE launch: W[tile][block][IB*IB], nblk = ceil(na / IB)
+// blocks per tile (the last tile has na_last <= na rows)
+template <typename T>
+static int launch_trtri_diag_batched(int ntiles, const T* const* Tarr, int ldt, int na, int na_last, int lower, int unit,
+                                     T* W, cudaStream_t stream)
+{
+    const int nblk = int(ceil_div(na, IB));
+    if (ntiles <= 0 || nblk <= 0) return SB200_OK;
+    if constexpr (IsRealType<T>::value)
+        trtri_diag_fast_kernel<T><<<dim3(nblk, ntiles), IB, fast_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
+    else
+        trtri_diag_kernel<T><<<dim3(nblk, ntiles), 256, small_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
     return launch_status();
 }
 
@@ -415,6 +444,160 @@ int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cuda
     }
     return SB200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Triangular tile solve for FEW right-hand sides (the solve path: potrs / getrs with nrhs ~ 10;
+// reference call site work::trsm -> internal::trsm, src/work/work_trsm.cc:60-230).
+// Same arithmetic as trsm_colmajor (block substitution with the inverted IB x IB diagonal blocks),
+// but the whole na x na triangle is walked inside ONE CTA per <= TS_NC columns of one B tile, instead
+// of 2 GEMM launches per diagonal block: the solve path is a chain of nt dependent tile solves, so
+// launch latency, not bandwidth, is what it pays for.
+//   mode 0: lower, NoTrans   (forward;  right-looking: thread-per-row axpy updates, coalesced down T's columns)
+//   mode 1: lower, Trans/Conj (backward; left-looking: warp-per-row dot products down T's columns)
+//   mode 2: upper, NoTrans   (backward; right-looking)
+// Winv: the nblk inverted diagonal blocks of T (IB x IB dense each, from the trtri kernels).
+// ---------------------------------------------------------------------------------------------
+constexpr int TS_NC = 8;            // right-hand-side columns per CTA
+constexpr int TS_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(TS_THREADS)
+trsm_small_kernel(const T* __restrict__ Tm, int ldt, const T* __restrict__ Winv, T* const* __restrict__ Barr,
+                  int64_t offB, int ldb, int na, int n, int mode, int conj)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    T* Xs = reinterpret_cast<T*>(smem_dyn);          // [TS_NC][na]   the right-hand sides / solution
+    T* V  = Xs + size_t(TS_NC) * na;                 // [TS_NC][IB]   block staging
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = blockIdx.x * TS_NC;
+    const int nc = min(TS_NC, n - c0);
+    T* __restrict__ B = Barr[blockIdx.y] + offB + int64_t(c0) * ldb;
+    const int nblk = (na + IB - 1) / IB;
+
+    for (int e = tid; e < TS_NC * na; e += TS_THREADS) {
+        const int c = e / na, r = e - c * na;
+        Xs[e] = (c < nc) ? B[r + int64_t(c) * ldb] : zero_of<T>();
+    }
+    __syncthreads();
+
+    for (int s = 0; s < nblk; ++s) {
+        const int b = (mode == 0) ? s : nblk - 1 - s;
+        const int o = b * IB, nv = min(IB, na - o);
+        const T* __restrict__ Wb = Winv + int64_t(b) * IB * IB;
+        if (mode == 1) {
+            // v(r, :) = x(o + r, :) - sum_{i >= o + nv} op(T)(o + r, i) x(i, :),  op(T)(o + r, i) = [conj] T(i, o + r)
+            for (int r = warp; r < nv; r += TS_THREADS / 32) {
+                const T* __restrict__ col = Tm + int64_t(o + r) * ldt;
+                T acc[TS_NC];
+                #pragma unroll
+                for (int c = 0; c < TS_NC; ++c) acc[c] = zero_of<T>();
+                for (int i = o + nv + lane; i < na; i += 32) {
+                    T t = col[i];
+                    if (conj) t = conj_(t);
+                    #pragma unroll
+                    for (int c = 0; c < TS_NC; ++c) fma_acc(acc[c], t, Xs[c * na + i]);
+                }
+                #pragma unroll
+                for (int c = 0; c < TS_NC; ++c) {
+                    T v = acc[c];
+                    #pragma unroll
+                    for (int sh = 16; sh > 0; sh >>= 1) v = add(v, shfl_xor_t(v, sh));
+                    if (lane == 0) V[c * IB + r] = sub(Xs[c * na + o + r], v);
+                }
+            }
+        }
+        else {
+            for (int e = tid; e < TS_NC * nv; e += TS_THREADS) {
+                const int c = e / nv, r = e - c * nv;
+                V[c * IB + r] = Xs[c * na + o + r];
+            }
+        }
+        __syncthreads();
+        // y = op(Winv_b) v  (Winv_b is dense IB x IB with zeros in the other triangle)
+        for (int e = tid; e < TS_NC * nv; e += TS_THREADS) {
+            const int c = e / nv, r = e - c * nv;
+            T y = zero_of<T>();
+            if (mode == 1) {
+                for (int q = r; q < nv; ++q) {           // op(W)(r, q) = [conj] W(q, r), W lower
+                    T w = Wb[q + r * IB];
+                    if (conj) w = conj_(w);
+                    fma_acc(y, w, V[c * IB + q]);
+                }
+            }
+            else if (mode == 0) { for (int q = 0; q <= r; ++q) fma_acc(y, Wb[r + q * IB], V[c * IB + q]); }
+            else                { for (int q = r; q < nv; ++q) fma_acc(y, Wb[r + q * IB], V[c * IB + q]); }
+            Xs[c * na + o + r] = y;
+        }
+        __syncthreads();
+        if (mode != 1) {
+            // right-looking: x(i, :) -= T(i, o : o + nv) y  for the rows not solved yet
+            const int i_lo = (mode == 0) ? o + nv : 0, i_hi = (mode == 0) ? na : o;
+            for (int i = i_lo + tid; i < i_hi; i += TS_THREADS) {
+                T acc[TS_NC];
+                #pragma unroll
+                for (int c = 0; c < TS_NC; ++c) acc[c] = zero_of<T>();
+                const T* __restrict__ row = Tm + i + int64_t(o) * ldt;
+                #pragma unroll 8
+                for (int q = 0; q < nv; ++q) {
+                    const T t = row[int64_t(q) * ldt];
+                    #pragma unroll
+                    for (int c = 0; c < TS_NC; ++c) fma_acc(acc[c], t, Xs[c * na + o + q]);
+                }
+                #pragma unroll
+                for (int c = 0; c < TS_NC; ++c) Xs[c * na + i] = sub(Xs[c * na + i], acc[c]);
+            }
+            __syncthreads();
+        }
+    }
+    for (int e = tid; e < nc * na; e += TS_THREADS) {
+        const int c = e / na, r = e - c * na;
+        B[r + int64_t(c) * ldb] = Xs[e];
+    }
+}
+
+template <typename T> constexpr size_t ts_smem(int na) { return (size_t(TS_NC) * na + size_t(TS_NC) * IB) * sizeof(T); }
+
+// Inverted diagonal blocks of every diagonal tile of a sweep, one launch (see launch_trtri_diag_batched).
+template <typename T>
+int trtri_diag_all(int ntiles, const T* const* Tarr, int ldt, int na, int na_last, bool lower, bool unit, T* W, cudaStream_t stream)
+{
+    small_kernels_init<T>();
+    return launch_trtri_diag_batched<T>(ntiles, Tarr, ldt, na, na_last, lower ? 1 : 0, unit ? 1 : 0, W, stream);
+}
+
+// B_t <- op(T)^{-1} B_t for `batch` tiles of n columns (left side).  Returns SB200_ENOTSUP when the case is not
+// served by the small kernel (upper + transposed, or a triangle too tall for shared memory): callers fall back to
+// trsm_colmajor.
+template <typename T>
+int trsm_small(bool lower, int op, int na, int n, const T* Tm, int ldt, const T* Winv, T* const* dB, int64_t offB,
+               int ldb, int batch, cudaStream_t stream)
+{
+    if (na <= 0 || n <= 0 || batch <= 0) return SB200_OK;
+    const bool trans = (op != 'N');
+    if (! lower && trans) return SB200_ENOTSUP;
+    const size_t smem = ts_smem<T>(na);
+    if (smem > 200 * 1024) return SB200_ENOTSUP;
+    static thread_local size_t attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_set[dev & 63] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(trsm_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(200 * 1024));
+        if (e != cudaSuccess) return int(e);
+        attr_set[dev & 63] = 200 * 1024;
+    }
+    const int mode = lower ? (trans ? 1 : 0) : 2;
+    trsm_small_kernel<T><<<dim3(unsigned(ceil_div(n, TS_NC)), unsigned(batch)), TS_THREADS, smem, stream>>>(
+        Tm, ldt, Winv, dB, offB, ldb, na, n, mode, op == 'C' ? 1 : 0);
+    return launch_status();
+}
+
+#define SB200_INST_SMALL(T) \
+    template int trtri_diag_all<T>(int, const T* const*, int, int, int, bool, bool, T*, cudaStream_t); \
+    template int trsm_small<T>(bool, int, int, int, const T*, int, const T*, T* const*, int64_t, int, int, cudaStream_t);
+SB200_INST_SMALL(float)
+SB200_INST_SMALL(double)
+SB200_INST_SMALL(cuFloatComplex)
+SB200_INST_SMALL(cuDoubleComplex)
 
 // the drivers (runtime.cu, solve.cu, getrf.cu) use these for every scalar type
 #define SB200_INST_FACTOR(T) \

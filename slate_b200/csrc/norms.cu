@@ -40,6 +40,23 @@ template <typename R> __device__ inline void add_sumsq(R& scale, R& sumsq, R abs
     if (scale < absx) { const R r = scale / absx; sumsq = R(1) + sumsq * r * r; scale = absx; }
     else              { const R r = absx / scale; sumsq += r * r; }
 }
+// per-thread streaming variant: `inv` caches 1 / scale so that the common case (|x| <= scale) is one
+// multiply and one FMA; the division only happens when the running maximum changes.  The value kept is
+// the same (scale, sumsq) pair up to rounding of x / scale vs x * (1 / scale).
+__device__ inline float  fma_r(float a, float b, float c)    { return fmaf(a, b, c); }
+__device__ inline double fma_r(double a, double b, double c) { return ::fma(a, b, c); }
+template <typename R> struct SumSq {
+    R scale = R(0), sumsq = R(1), inv = R(0);
+    __device__ inline void add(R absx)
+    {
+        if (absx != absx) { scale = absx; return; }             // NaN poisons the result
+        if (scale != scale) return;
+        if (absx == R(0)) return;
+        if (scale < absx) { const R r = scale / absx; sumsq = R(1) + sumsq * r * r; scale = absx; inv = R(1) / absx; }
+        else              { const R r = absx * inv; sumsq = fma_r(r, r, sumsq); }
+    }
+};
+
 template <typename R> __device__ inline void combine_sumsq(R& scale, R& sumsq, R scale2, R sumsq2)
 {
     if (scale2 != scale2) { scale = scale2; return; }
@@ -100,19 +117,31 @@ norm_kernel(int mode, NormCfg cfg, int m, int n, const T* const* A, int64_t lda,
     constexpr int NW = NORM_THREADS / 32;
     __shared__ R red[2 * NW];
 
+    constexpr int UN = 4;                       // independent loads in flight per lane (HBM latency hiding)
     if (mode == 'M' || mode == 'F') {
-        R vmax = 0, scale = 0, sumsq = 1;
+        R vmax = 0;
+        SumSq<R> ss;
         for (int j = warp; j < n; j += NW) {
-            for (int i = lane; i < m; i += 32) {
-                if (! in_shape(cfg, i, j)) continue;
-                const R v = elem_abs(cfg, a, lda, i, j);
-                if (mode == 'M') vmax = max_nan(vmax, v);
-                else {
-                    add_sumsq(scale, sumsq, v);
-                    if (cfg.sym && i != j) add_sumsq(scale, sumsq, v);     // mirrored entry
+            for (int i0 = lane; i0 < m; i0 += 32 * UN) {
+                R v[UN]; bool ok[UN];
+                #pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int i = i0 + 32 * u;
+                    ok[u] = i < m && in_shape(cfg, i, j);
+                    v[u] = ok[u] ? elem_abs(cfg, a, lda, i, j) : R(0);
+                }
+                #pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    if (! ok[u]) continue;
+                    if (mode == 'M') vmax = max_nan(vmax, v[u]);
+                    else {
+                        ss.add(v[u]);
+                        if (cfg.sym && i0 + 32 * u != j) ss.add(v[u]);     // mirrored entry
+                    }
                 }
             }
         }
+        R scale = ss.scale, sumsq = ss.sumsq;
         if (mode == 'M') {
             vmax = warp_max_nan(vmax);
             if (lane == 0) red[warp] = vmax;
@@ -144,10 +173,17 @@ norm_kernel(int mode, NormCfg cfg, int m, int n, const T* const* A, int64_t lda,
         // column pass: one warp per column
         for (int j = warp; j < n; j += NW) {
             R acc = 0;
-            for (int i = lane; i < m; i += 32) {
-                if (! in_shape(cfg, i, j)) continue;
-                const R v = elem_abs(cfg, a, lda, i, j);
-                acc = (mode == 'C') ? max_nan(acc, v) : acc + v;
+            for (int i0 = lane; i0 < m; i0 += 32 * UN) {
+                R v[UN]; bool ok[UN];
+                #pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int i = i0 + 32 * u;
+                    ok[u] = i < m && in_shape(cfg, i, j);
+                    v[u] = ok[u] ? elem_abs(cfg, a, lda, i, j) : R(0);
+                }
+                #pragma unroll
+                for (int u = 0; u < UN; ++u)
+                    if (ok[u]) acc = (mode == 'C') ? max_nan(acc, v[u]) : acc + v[u];
             }
             acc = (mode == 'C') ? warp_max_nan(acc) : warp_sum(acc);
             if (lane == 0) out[j] = acc;
@@ -158,10 +194,16 @@ norm_kernel(int mode, NormCfg cfg, int m, int n, const T* const* A, int64_t lda,
         // row pass: one thread per row (coalesced across the CTA), deterministic order in j
         for (int i = tid; i < m; i += NORM_THREADS) {
             R acc = 0;
-            for (int j = 0; j < n; ++j) {
-                if (! in_shape(cfg, i, j)) continue;
-                if (mode == 'O' && i == j) continue;            // sym: diagonal already in the column sum
-                acc += elem_abs(cfg, a, lda, i, j);
+            for (int j0 = 0; j0 < n; j0 += UN) {
+                R v[UN]; bool ok[UN];
+                #pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int j = j0 + u;
+                    ok[u] = j < n && in_shape(cfg, i, j) && ! (mode == 'O' && i == j);   // sym: diagonal already in the column sum
+                    v[u] = ok[u] ? elem_abs(cfg, a, lda, i, j) : R(0);
+                }
+                #pragma unroll
+                for (int u = 0; u < UN; ++u) if (ok[u]) acc += v[u];
             }
             if (mode == 'I') out[i] = acc;
             else if (mode == 'B') out[n + i] = acc;

@@ -24,6 +24,13 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
                   T* W, cudaStream_t stream);
 template <typename T>
 int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cudaStream_t stream);
+// small-nrhs solve path (factor_small.cu): inverted diagonal blocks of all diagonal tiles in one launch, and the
+// one-CTA-per-8-columns tile solve; trsm_small returns SB200_ENOTSUP for cases it does not serve
+template <typename T>
+int trtri_diag_all(int ntiles, const T* const* Tarr, int ldt, int na, int na_last, bool lower, bool unit, T* W, cudaStream_t stream);
+template <typename T>
+int trsm_small(bool lower, int op, int na, int n, const T* Tm, int ldt, const T* Winv, T* const* dB, int64_t offB,
+               int ldb, int batch, cudaStream_t stream);
 constexpr int FACTOR_IB = 64;          // diagonal block of the tile factor / solve kernels
 
 template <typename T> struct IsComplex { static constexpr bool value = false; };

@@ -65,6 +65,19 @@ __host__ __device__ inline double div_real(double a, double r) { return a / r; }
 __host__ __device__ inline cuFloatComplex  div_real(cuFloatComplex a, float r) { return make_cuFloatComplex(a.x / r, a.y / r); }
 __host__ __device__ inline cuDoubleComplex div_real(cuDoubleComplex a, double r) { return make_cuDoubleComplex(a.x / r, a.y / r); }
 
+#ifdef __CUDACC__
+__device__ inline float  shfl_xor_t(float v, int m)  { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ inline double shfl_xor_t(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ inline cuFloatComplex shfl_xor_t(cuFloatComplex v, int m)
+{
+    return make_cuFloatComplex(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ inline cuDoubleComplex shfl_xor_t(cuDoubleComplex v, int m)
+{
+    return make_cuDoubleComplex(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+#endif
+
 // acc += a * b
 __device__ inline void fma_acc(float& acc, float a, float b) { acc = fmaf(a, b, acc); }
 __device__ inline void fma_acc(double& acc, double a, double b) { acc = fma(a, b, acc); }

@@ -224,20 +224,38 @@ int tri_sweep(Matrix& A, bool lower, int op, bool unit, Matrix& B, cudaStream_t 
         st.full_off = pb.push(full); st.last_off = pb.push(last);
         pb.reserve(st.upd);
     }
+    // few right-hand sides: the diagonal-tile solve of every step is ONE small kernel (trsm_small) fed by the
+    // inverted diagonal blocks of all diagonal tiles, computed up front in one launch; otherwise the GEMM-based
+    // block substitution (trsm_colmajor).  Same arithmetic either way.
+    const int nblk = int(ceil_div(nb, FACTOR_IB));
+    const bool small = B.n <= 64 && (lower || ! trans)
+                       && (size_t(8) * nb + 8 * FACTOR_IB) * sizeof(T) <= size_t(200) * 1024;
+    std::vector<const T*> diag;
+    for (int64_t k = 0; k < kt; ++k) diag.push_back(A.tile_as<T>(k, k));
+    const size_t diag_off = pb.push(diag);
     DevBuf W;
-    SB_TRY(W.alloc(size_t(ceil_div(nb, FACTOR_IB)) * FACTOR_IB * FACTOR_IB * sizeof(T)));
+    SB_TRY(W.alloc(size_t(small ? kt : 1) * nblk * FACTOR_IB * FACTOR_IB * sizeof(T)));
     SB_TRY(pb.upload(s));
+    if (small)
+        SB_TRY(trtri_diag_all<T>(int(kt), pb.at<const T>(diag_off), ld, int(nb), int(A.tile_mb(kt - 1)), lower, unit,
+                                 W.as<T>(), s));
     const T one = from_real<T>(R(1)), minus_one = from_real<T>(R(-1));
     for (int64_t sidx = 0; sidx < kt; ++sidx) {
         const int64_t k = forward ? sidx : kt - 1 - sidx;
         const Step& st = steps[size_t(sidx)];
         const int mk = int(B.tile_mb(k));
-        if (st.nfull)
-            SB_TRY(trsm_colmajor<T>(true, lower, op, unit, mk, int(nb), one, A.tile_as<T>(k, k), ld,
-                                    pb.at<T>(st.full_off), 0, ld, st.nfull, W.as<T>(), s));
-        if (st.nlast)
-            SB_TRY(trsm_colmajor<T>(true, lower, op, unit, mk, int(B.tile_nb(ntB - 1)), one, A.tile_as<T>(k, k), ld,
-                                    pb.at<T>(st.last_off), 0, ld, st.nlast, W.as<T>(), s));
+        const T* Wk = W.as<T>() + (small ? k : 0) * int64_t(nblk) * FACTOR_IB * FACTOR_IB;
+        for (int part = 0; part < 2; ++part) {
+            const int cnt = part == 0 ? st.nfull : st.nlast;
+            if (cnt == 0) continue;
+            const int width = part == 0 ? int(nb) : int(B.tile_nb(ntB - 1));
+            T* const* ptrs = pb.at<T>(part == 0 ? st.full_off : st.last_off);
+            if (small)
+                SB_TRY(trsm_small<T>(lower, op, mk, width, A.tile_as<T>(k, k), ld, Wk, ptrs, 0, ld, cnt, s));
+            else
+                SB_TRY(trsm_colmajor<T>(true, lower, op, unit, mk, width, one, A.tile_as<T>(k, k), ld, ptrs, 0, ld, cnt,
+                                        W.as<T>(), s));
+        }
         SB_TRY(launch_batches<T>(st.upd, pb, trans ? op : 'N', 'N', minus_one, one, ld, 0, s));
     }
     CUDA_TRY(cudaStreamSynchronize(s));       // the plan and W die with this frame

@@ -339,3 +339,35 @@ def test_solve_path_rejects_multi_rank_and_type_mismatch(sl):
         sl.potrs(A, Bs)
     with pytest.raises(sl.SB200Error):
         sl.posv_mixed(A, sl.Matrix(64, 4, 16), sl.Matrix(64, 4, 32))
+
+
+# ---------------------------------------------------------------------------- small-nrhs solve kernel (trsm_small)
+@pytest.mark.parametrize("t,n,nb,nrhs", [("d", 1000, 128, 5), ("z", 520, 128, 10), ("s", 1024, 256, 10), ("c", 300, 64, 3),
+                                         ("d", 1536, 512, 64), ("d", 200, 512, 9), ("z", 1100, 512, 8)])
+def test_potrs_small_rhs_kernel_all_types_and_ragged(sl, t, n, nb, nrhs):
+    """nrhs <= 64 takes the one-launch-per-step tile solve (all three sweeps it serves: lower N, lower C, and --
+    through getrs below -- upper N), ragged last tiles and every scalar type; vs the oracle's block sweeps."""
+    hi = np.complex128 if t in "cz" else np.float64
+    A = sl.HermitianMatrix(n, nb, dtype=t).generate("rand_dominant", 42)
+    B = sl.Matrix(n, nrhs, nb, dtype=t).generate("rand", 43)
+    assert sl.potrf(A) == 0
+    L = np.tril(A.to_host()).astype(hi)
+    sl.potrs(A, B)
+    Xo = o.potrs(L, o.generate("rand", n, nrhs, 43, NP[t]).astype(hi), nb)
+    assert np.abs(B.to_host() - Xo).max() <= 200 * TOL[t] * np.abs(Xo).max()
+
+
+@pytest.mark.parametrize("t,n,nb,nrhs", [("d", 700, 128, 7), ("s", 1024, 256, 10), ("d", 1536, 512, 33), ("d", 300, 512, 2)])
+def test_getrs_small_rhs_kernel(sl, t, n, nb, nrhs):
+    A = sl.Matrix(n, n, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(n, nrhs, nb, dtype=t).generate("rand", 43)
+    piv, info = sl.getrf(A)
+    assert info == 0
+    LU = A.to_host().astype(np.float64)
+    sl.getrs(A, piv, B)
+    Xo = o.getrs(LU, piv, o.generate("rand", n, nrhs, 43, NP[t]).astype(np.float64), nb)
+    tol = 1e-9 if t == "d" else 0.5           # forward error ~ cond(A) eps (sanity only in FP32); the tester residual is the sharp check:
+    X = B.to_host().astype(np.float64)
+    assert np.abs(X - Xo).max() <= tol * np.abs(Xo).max()
+    a = o.generate("rand", n, n, 42, NP[t]).astype(np.float64); b = o.generate("rand", n, nrhs, 43, NP[t]).astype(np.float64)
+    assert o.solve_residual(a, X, b) <= 25 * TOL[t]
