@@ -32,6 +32,9 @@ template <typename T>
 int trsm_small(bool lower, int op, int na, int n, const T* Tm, int ldt, const T* Winv, T* const* dB, int64_t offB,
                int ldb, int batch, cudaStream_t stream);
 constexpr int FACTOR_IB = 64;          // diagonal block of the tile factor / solve kernels
+// skinny right operand (n <= 16): HBM-bound streaming kernel instead of a tensor-core tile kernel (gemm_skinny.cu)
+template <typename T> bool gemm_skinny_applies(int opB, const GemmParamsT<T>& p);
+template <typename T> int launch_gemm_skinny(int opA, const GemmParamsT<T>& p, cudaStream_t stream);
 
 template <typename T> struct IsComplex { static constexpr bool value = false; };
 template <> struct IsComplex<cuFloatComplex>  { static constexpr bool value = true; };
@@ -105,7 +108,8 @@ inline int launch_batches(const std::vector<Batch>& bs, const PlanBuffer& pb, in
         p.m = b.m; p.n = b.n; p.k = b.k; p.lda = ld; p.ldb = ld; p.ldc = ld;
         p.alpha = alpha; p.beta = beta; p.batch = int(cnt); p.tri = b.tri;
         p.herk = (herk && b.tri) ? 1 : 0;
-        SB_TRY(launch_gemm<T>(opA, opB, p, s));
+        if (gemm_skinny_applies<T>(opB, p)) SB_TRY(launch_gemm_skinny<T>(opA, p, s));
+        else                                SB_TRY(launch_gemm<T>(opA, opB, p, s));
     }
     return SB200_OK;
 }

@@ -228,7 +228,8 @@ int tri_sweep(Matrix& A, bool lower, int op, bool unit, Matrix& B, cudaStream_t 
     // inverted diagonal blocks of all diagonal tiles, computed up front in one launch; otherwise the GEMM-based
     // block substitution (trsm_colmajor).  Same arithmetic either way.
     const int nblk = int(ceil_div(nb, FACTOR_IB));
-    const bool small = B.n <= 64 && (lower || ! trans)
+    static const bool small_on = [] { const char* e = getenv("SB200_TRSM_SMALL"); return ! (e && atoi(e) == 0); }();
+    const bool small = small_on && B.n <= 64 && (lower || ! trans)
                        && (size_t(8) * nb + 8 * FACTOR_IB) * sizeof(T) <= size_t(200) * 1024;
     std::vector<const T*> diag;
     for (int64_t k = 0; k < kt; ++k) diag.push_back(A.tile_as<T>(k, k));
