@@ -21,8 +21,15 @@ EPS = np.finfo(np.float64).eps
 
 def gather(M, m, n):
     """Global matrix on every rank: each rank contributes its own tiles, the rest is zero."""
-    h = np.zeros((m, n), order="F")
+    h = np.zeros((m, n), dtype=M.dtype, order="F")
     M.to_host(h)
+    if np.iscomplexobj(h):
+        parts = []
+        for comp in (h.real, h.imag):
+            t = torch.from_numpy(np.ascontiguousarray(comp.T)).cuda()
+            dist.all_reduce(t)
+            parts.append(t.cpu().numpy().T)
+        return np.asfortranarray(parts[0] + 1j * parts[1])
     t = torch.from_numpy(np.ascontiguousarray(h.T)).cuda()
     dist.all_reduce(t)
     return np.asfortranarray(t.cpu().numpy().T)
@@ -76,6 +83,39 @@ def main():
                 good = e <= 64 * EPS and o.gemm_check(3.1, a, b, 2.7, c, C) <= 3 * EPS
                 print(f"grid {p}x{q} gemm n={n} nb={nb}: err={e:.2e} {'ok' if good else 'FAILED'}", flush=True)
                 ok &= good
+            # ---- round-1 widening on the grid: complex herk / potrf / gemm, FP32 potrf on the tcgen05 kernel
+            if n != 2048:
+                k = n // 2
+                Az = sl.Matrix(n, k, nb, grid, "z").generate("rand", 5)
+                Cz = sl.HermitianMatrix(n, nb, grid, dtype="z").generate("rand", 6)
+                sl.herk(-1.0, Az, 2.0, Cz)
+                out = np.tril(gather(Cz, n, n))
+                Hz = sl.HermitianMatrix(n, nb, grid, dtype="z").generate("rand_dominant", 42)
+                iz = sl.potrf(Hz)
+                Lz = np.tril(gather(Hz, n, n))
+                Bz = sl.Matrix(k, n, nb, grid, "z").generate("rand", 7)
+                Gz = sl.Matrix(n, n, nb, grid, "z").generate("rand", 8)
+                sl.gemm(3.1 + 1.4j, Az, Bz, 2.7 + 1.7j, Gz)
+                gz = gather(Gz, n, n)
+                Hs = sl.HermitianMatrix(n, nb, grid, dtype="s").generate("rand_dominant", 42)
+                i_s = sl.potrf(Hs, {"tensor_core_fp32": True})
+                Ls = np.tril(gather(Hs, n, n)).astype(np.float64)
+                if rank == 0:
+                    a = o.generate("rand", n, k, 5, np.complex128)
+                    ref = np.tril(o.herk(-1.0, a, 2.0, o.generate("rand", n, n, 6, np.complex128), nb))
+                    e1 = np.abs(out - ref).max() / np.abs(ref).max()
+                    Lo, _ = o.potrf(o.he_full(o.generate("rand_dominant", n, n, 42, np.complex128)), nb)
+                    e2 = np.abs(Lz - Lo).max() / np.abs(Lo).max()
+                    refg = o.gemm(3.1 + 1.4j, a, o.generate("rand", k, n, 7, np.complex128), 2.7 + 1.7j,
+                                  o.generate("rand", n, n, 8, np.complex128), nb)
+                    e3 = np.abs(gz - refg).max() / np.abs(refg).max()
+                    Lso, _ = o.potrf(o.he_full(o.generate("rand_dominant", n, n, 42, np.float32).astype(np.float64)), nb)
+                    e4 = np.abs(Ls - Lso).max() / np.abs(Lso).max()
+                    good = (e1 <= 256 * EPS and e2 <= 64 * EPS and iz == 0 and e3 <= 256 * EPS
+                            and i_s == 0 and e4 <= 64 * float(np.finfo(np.float32).eps))
+                    print(f"grid {p}x{q} n={n} nb={nb}: zherk err={e1:.2e} zpotrf err={e2:.2e} zgemm err={e3:.2e} "
+                          f"spotrf(tcgen05) err={e4:.2e} {'ok' if good else 'FAILED'}", flush=True)
+                    ok &= good
             dist.barrier()
         grid.close()
     t = torch.tensor([1 if ok else 0], device="cuda")

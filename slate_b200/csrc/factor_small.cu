@@ -468,6 +468,7 @@ trsm_small_kernel(const T* __restrict__ Tm, int ldt, const T* __restrict__ Winv,
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     T* Xs = reinterpret_cast<T*>(smem_dyn);          // [TS_NC][na]   the right-hand sides / solution
     T* V  = Xs + size_t(TS_NC) * na;                 // [TS_NC][IB]   block staging
+    T* Ws = V + TS_NC * IB;                          // [IB][IB]      inverted diagonal block of this step
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c0 = blockIdx.x * TS_NC;
     const int nc = min(TS_NC, n - c0);
@@ -483,7 +484,12 @@ trsm_small_kernel(const T* __restrict__ Tm, int ldt, const T* __restrict__ Winv,
     for (int s = 0; s < nblk; ++s) {
         const int b = (mode == 0) ? s : nblk - 1 - s;
         const int o = b * IB, nv = min(IB, na - o);
-        const T* __restrict__ Wb = Winv + int64_t(b) * IB * IB;
+        {   // stage the inverted diagonal block (independent coalesced loads: one memory round trip)
+            const T* __restrict__ Wg = Winv + int64_t(b) * IB * IB;
+            #pragma unroll
+            for (int e = 0; e < IB * IB / TS_THREADS; ++e) Ws[tid + e * TS_THREADS] = Wg[tid + e * TS_THREADS];
+        }
+        const T* Wb = Ws;
         if (mode == 1) {
             // v(r, :) = x(o + r, :) - sum_{i >= o + nv} op(T)(o + r, i) x(i, :),  op(T)(o + r, i) = [conj] T(i, o + r)
             for (int r = warp; r < nv; r += TS_THREADS / 32) {
@@ -491,11 +497,17 @@ trsm_small_kernel(const T* __restrict__ Tm, int ldt, const T* __restrict__ Winv,
                 T acc[TS_NC];
                 #pragma unroll
                 for (int c = 0; c < TS_NC; ++c) acc[c] = zero_of<T>();
-                for (int i = o + nv + lane; i < na; i += 32) {
-                    T t = col[i];
-                    if (conj) t = conj_(t);
+                for (int i = o + nv + lane; i < na; i += 32 * 4) {
+                    T t[4];
                     #pragma unroll
-                    for (int c = 0; c < TS_NC; ++c) fma_acc(acc[c], t, Xs[c * na + i]);
+                    for (int u = 0; u < 4; ++u) t[u] = (i + 32 * u < na) ? col[i + 32 * u] : zero_of<T>();
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (i + 32 * u >= na) continue;
+                        const T tv = conj ? conj_(t[u]) : t[u];
+                        #pragma unroll
+                        for (int c = 0; c < TS_NC; ++c) fma_acc(acc[c], tv, Xs[c * na + i + 32 * u]);
+                    }
                 }
                 #pragma unroll
                 for (int c = 0; c < TS_NC; ++c) {
@@ -537,11 +549,16 @@ trsm_small_kernel(const T* __restrict__ Tm, int ldt, const T* __restrict__ Winv,
                 #pragma unroll
                 for (int c = 0; c < TS_NC; ++c) acc[c] = zero_of<T>();
                 const T* __restrict__ row = Tm + i + int64_t(o) * ldt;
-                #pragma unroll 8
-                for (int q = 0; q < nv; ++q) {
-                    const T t = row[int64_t(q) * ldt];
+                for (int q0 = 0; q0 < nv; q0 += 16) {
+                    T t[16];
                     #pragma unroll
-                    for (int c = 0; c < TS_NC; ++c) fma_acc(acc[c], t, Xs[c * na + o + q]);
+                    for (int u = 0; u < 16; ++u) t[u] = (q0 + u < nv) ? row[int64_t(q0 + u) * ldt] : zero_of<T>();
+                    #pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        if (q0 + u >= nv) continue;
+                        #pragma unroll
+                        for (int c = 0; c < TS_NC; ++c) fma_acc(acc[c], t[u], Xs[c * na + o + q0 + u]);
+                    }
                 }
                 #pragma unroll
                 for (int c = 0; c < TS_NC; ++c) Xs[c * na + i] = sub(Xs[c * na + i], acc[c]);
@@ -555,7 +572,7 @@ trsm_small_kernel(const T* __restrict__ Tm, int ldt, const T* __restrict__ Winv,
     }
 }
 
-template <typename T> constexpr size_t ts_smem(int na) { return (size_t(TS_NC) * na + size_t(TS_NC) * IB) * sizeof(T); }
+template <typename T> constexpr size_t ts_smem(int na) { return (size_t(TS_NC) * na + size_t(TS_NC) * IB + size_t(IB) * IB) * sizeof(T); }
 
 // Inverted diagonal blocks of every diagonal tile of a sweep, one launch (see launch_trtri_diag_batched).
 template <typename T>

@@ -53,11 +53,16 @@ gemm_skinny_kernel(const GemmParamsT<T> p, int opA)
             __syncthreads();
             if (live) {
                 const T* __restrict__ arow = A + row + int64_t(k0) * p.lda;
-                #pragma unroll 4
-                for (int kk = ks; kk < kc; kk += 4) {
-                    const T a = arow[int64_t(kk) * p.lda];
+                for (int kk = ks; kk < kc; kk += 4 * 8) {          // 8 independent loads per round trip
+                    T a[8];
                     #pragma unroll
-                    for (int c = 0; c < SK_NC; ++c) fma_acc(acc[c], a, Bs[c][kk]);
+                    for (int u = 0; u < 8; ++u) a[u] = (kk + 4 * u < kc) ? arow[int64_t(kk + 4 * u) * p.lda] : zero_of<T>();
+                    #pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (kk + 4 * u >= kc) continue;
+                        #pragma unroll
+                        for (int c = 0; c < SK_NC; ++c) fma_acc(acc[c], a[u], Bs[c][kk + 4 * u]);
+                    }
                 }
             }
         }
@@ -100,11 +105,15 @@ gemm_skinny_kernel(const GemmParamsT<T> p, int opA)
             const int row = i0 + warp + (SK_THREADS / 32) * j;
             if (row >= p.m) continue;                                     // warp-uniform
             const T* __restrict__ acol = A + k0 + int64_t(row) * p.lda;
-            for (int kk = lane; kk < kc; kk += 32) {
-                T a = acol[kk];
-                if (cj) a = conj_(a);
+            T a[SK_KCH / 32];                                     // the whole chunk of this row: 4 loads in flight
+            #pragma unroll
+            for (int u = 0; u < SK_KCH / 32; ++u) a[u] = (lane + 32 * u < kc) ? acol[lane + 32 * u] : zero_of<T>();
+            #pragma unroll
+            for (int u = 0; u < SK_KCH / 32; ++u) {
+                if (lane + 32 * u >= kc) continue;
+                const T av = cj ? conj_(a[u]) : a[u];
                 #pragma unroll
-                for (int c = 0; c < SK_NC; ++c) fma_acc(res[j][c], a, Bs[c][kk]);
+                for (int c = 0; c < SK_NC; ++c) fma_acc(res[j][c], av, Bs[c][lane + 32 * u]);
             }
         }
     }

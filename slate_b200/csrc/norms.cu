@@ -101,6 +101,17 @@ __device__ inline typename RealOf<T>::type elem_abs(const NormCfg& c, const T* a
     return abs_(a[i + j * lda]);
 }
 
+// |a_ij| as the norm counts it, from an ALREADY LOADED value (the loads themselves stay unconditional /
+// predicated only on the bounds, so that the compiler issues UN of them back to back)
+template <typename T>
+__device__ inline typename RealOf<T>::type abs_loaded(const NormCfg& c, T raw, int i, int j)
+{
+    using R = typename RealOf<T>::type;
+    if (i == j && c.unit) return R(1);
+    if (i == j && c.herm) return abs_real(raw);
+    return abs_(raw);
+}
+
 constexpr int NORM_THREADS = 512;
 
 // mode: 'M' max, 'O' one (column sums [+ row part for sym]), 'I' inf (row sums), 'F' fro,
@@ -117,26 +128,27 @@ norm_kernel(int mode, NormCfg cfg, int m, int n, const T* const* A, int64_t lda,
     constexpr int NW = NORM_THREADS / 32;
     __shared__ R red[2 * NW];
 
-    constexpr int UN = 4;                       // independent loads in flight per lane (HBM latency hiding)
+    constexpr int UN = 8;                       // independent loads in flight per lane (HBM latency hiding)
     if (mode == 'M' || mode == 'F') {
         R vmax = 0;
         SumSq<R> ss;
         for (int j = warp; j < n; j += NW) {
             for (int i0 = lane; i0 < m; i0 += 32 * UN) {
-                R v[UN]; bool ok[UN];
+                T raw[UN];
                 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
                     const int i = i0 + 32 * u;
-                    ok[u] = i < m && in_shape(cfg, i, j);
-                    v[u] = ok[u] ? elem_abs(cfg, a, lda, i, j) : R(0);
+                    raw[u] = (i < m) ? a[i + int64_t(j) * lda] : zero_of<T>();
                 }
                 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
-                    if (! ok[u]) continue;
-                    if (mode == 'M') vmax = max_nan(vmax, v[u]);
+                    const int i = i0 + 32 * u;
+                    if (i >= m || ! in_shape(cfg, i, j)) continue;
+                    const R v = abs_loaded(cfg, raw[u], i, j);
+                    if (mode == 'M') vmax = max_nan(vmax, v);
                     else {
-                        ss.add(v[u]);
-                        if (cfg.sym && i0 + 32 * u != j) ss.add(v[u]);     // mirrored entry
+                        ss.add(v);
+                        if (cfg.sym && i != j) ss.add(v);     // mirrored entry
                     }
                 }
             }
@@ -174,16 +186,19 @@ norm_kernel(int mode, NormCfg cfg, int m, int n, const T* const* A, int64_t lda,
         for (int j = warp; j < n; j += NW) {
             R acc = 0;
             for (int i0 = lane; i0 < m; i0 += 32 * UN) {
-                R v[UN]; bool ok[UN];
+                T raw[UN];
                 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
                     const int i = i0 + 32 * u;
-                    ok[u] = i < m && in_shape(cfg, i, j);
-                    v[u] = ok[u] ? elem_abs(cfg, a, lda, i, j) : R(0);
+                    raw[u] = (i < m) ? a[i + int64_t(j) * lda] : zero_of<T>();
                 }
                 #pragma unroll
-                for (int u = 0; u < UN; ++u)
-                    if (ok[u]) acc = (mode == 'C') ? max_nan(acc, v[u]) : acc + v[u];
+                for (int u = 0; u < UN; ++u) {
+                    const int i = i0 + 32 * u;
+                    if (i >= m || ! in_shape(cfg, i, j)) continue;
+                    const R v = abs_loaded(cfg, raw[u], i, j);
+                    acc = (mode == 'C') ? max_nan(acc, v) : acc + v;
+                }
             }
             acc = (mode == 'C') ? warp_max_nan(acc) : warp_sum(acc);
             if (lane == 0) out[j] = acc;
@@ -195,15 +210,18 @@ norm_kernel(int mode, NormCfg cfg, int m, int n, const T* const* A, int64_t lda,
         for (int i = tid; i < m; i += NORM_THREADS) {
             R acc = 0;
             for (int j0 = 0; j0 < n; j0 += UN) {
-                R v[UN]; bool ok[UN];
+                T raw[UN];
                 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
                     const int j = j0 + u;
-                    ok[u] = j < n && in_shape(cfg, i, j) && ! (mode == 'O' && i == j);   // sym: diagonal already in the column sum
-                    v[u] = ok[u] ? elem_abs(cfg, a, lda, i, j) : R(0);
+                    raw[u] = (j < n) ? a[i + int64_t(j) * lda] : zero_of<T>();
                 }
                 #pragma unroll
-                for (int u = 0; u < UN; ++u) if (ok[u]) acc += v[u];
+                for (int u = 0; u < UN; ++u) {
+                    const int j = j0 + u;
+                    if (j >= n || ! in_shape(cfg, i, j) || (mode == 'O' && i == j)) continue;   // sym: diagonal already in the column sum
+                    acc += abs_loaded(cfg, raw[u], i, j);
+                }
             }
             if (mode == 'I') out[i] = acc;
             else if (mode == 'B') out[n + i] = acc;

@@ -127,6 +127,7 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05)
     if (A.kind != 'H' || A.layout != 'C' || A.m != A.n || A.dtype != TypeChar<T>::value) return SB200_EINVAL;
     constexpr bool is_float = std::is_same<T, float>::value;
     if (use_tc05 && ! is_float) return SB200_EINVAL;
+    if (A.n == 0) { if (info_out) *info_out = 0; return SB200_OK; }       // quick return (LAPACK: n == 0)
     CUDA_TRY(cudaDeviceSynchronize());       // inputs may have been produced on any stream
     const int64_t nt = A.nt, nb = A.nb;
     const int ld = int(nb);
@@ -363,6 +364,7 @@ int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C)
     const int64_t kt = A.nt, nb = C.nb, te = C.tile_elems();
     const int ld = int(nb);
     const bool multi = g.size() > 1;
+    if (C.m == 0 || C.n == 0 || kt == 0) return (C.m == 0 || C.n == 0) ? SB200_OK : SB200_ENOTSUP;   // k == 0 not served
     CUDA_TRY(cudaDeviceSynchronize());       // inputs may have been produced on any stream
 
     DevBuf wsA, wsB;
@@ -466,6 +468,7 @@ int herk_driver(typename RealOf<T>::type alpha, Matrix& A, typename RealOf<T>::t
     const int ld = int(nb);
     const bool multi = g.size() > 1;
     const int opH = IsComplex<T>::value ? 'C' : 'T';
+    if (C.n == 0 || kt == 0) return C.n == 0 ? SB200_OK : SB200_ENOTSUP;    // k == 0 (C <- beta C only) is not served
     CUDA_TRY(cudaDeviceSynchronize());
 
     DevBuf ws;

@@ -230,7 +230,7 @@ int tri_sweep(Matrix& A, bool lower, int op, bool unit, Matrix& B, cudaStream_t 
     const int nblk = int(ceil_div(nb, FACTOR_IB));
     static const bool small_on = [] { const char* e = getenv("SB200_TRSM_SMALL"); return ! (e && atoi(e) == 0); }();
     const bool small = small_on && B.n <= 64 && (lower || ! trans)
-                       && (size_t(8) * nb + 8 * FACTOR_IB) * sizeof(T) <= size_t(200) * 1024;
+                       && (size_t(8) * nb + 8 * FACTOR_IB + FACTOR_IB * FACTOR_IB) * sizeof(T) <= size_t(200) * 1024;
     std::vector<const T*> diag;
     for (int64_t k = 0; k < kt; ++k) diag.push_back(A.tile_as<T>(k, k));
     const size_t diag_off = pb.push(diag);

@@ -371,3 +371,21 @@ def test_getrs_small_rhs_kernel(sl, t, n, nb, nrhs):
     assert np.abs(X - Xo).max() <= tol * np.abs(Xo).max()
     a = o.generate("rand", n, n, 42, NP[t]).astype(np.float64); b = o.generate("rand", n, nrhs, 43, NP[t]).astype(np.float64)
     assert o.solve_residual(a, X, b) <= 25 * TOL[t]
+
+
+def test_empty_problems_are_quick_returns(sl):
+    """n == 0 / nrhs == 0: LAPACK-style quick returns, no launches that index an empty plan."""
+    A = sl.HermitianMatrix(0, 64)
+    assert sl.potrf(A) == 0
+    B0 = sl.Matrix(0, 0, 64)
+    sl.potrs(A, B0)
+    sl.gemm(1.0, sl.Matrix(0, 0, 64), sl.Matrix(0, 0, 64), 1.0, sl.Matrix(0, 0, 64))
+    n, nb = 256, 64
+    H = sl.HermitianMatrix(n, nb).generate("rand_dominant", 1)
+    assert sl.potrf(H) == 0
+    Bn = sl.Matrix(n, 0, nb)
+    sl.potrs(H, Bn)
+    G = sl.Matrix(n, n, nb).generate("rand", 1)
+    piv, info = sl.getrf(G)
+    sl.getrs(G, piv, Bn)
+    assert sl.Matrix(0, 0, 64).to_host().shape == (0, 0)
