@@ -53,9 +53,10 @@ def default_n(routine: str, ngpus: int) -> int:
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period: float = 0.2):
         super().__init__(daemon=True)
         self.index = index
+        self.period = period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._halt = threading.Event()
@@ -76,7 +77,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(self.period)
 
     def stop(self):
         self._halt.set()
@@ -319,7 +320,7 @@ def run_extra(args):
         torch.cuda.synchronize()
 
     al, be = 3.141592653589793 + 1.414213562373095j, 2.718281828459045 + 1.732050807568877j
-    timers = {}
+    timers, phase_log = {}, []
     if routine == "zgemm":
         Am = sl.Matrix(n, n, nb, grid, "z").generate("rand", 42)
         Bm = sl.Matrix(n, n, nb, grid, "z").generate("rand", 43)
@@ -352,16 +353,18 @@ def run_extra(args):
             if r[0] != 0 or r[1] < 0:
                 raise SystemExit(f"{routine}: info={r[0]} iter={r[1]} (refinement did not converge)")
             timers.update(r[-1]); timers["iter"] = r[1]
+            phase_log.append(dict(r[-1]))
         kernel = "gemm_tf32x3_kernel (tcgen05 kind::tf32 x3, FP32-emulated trailing update of the low-precision factor)"
 
     stats = (c_dbl * 4)()
     lib.sb200_last_driver_stats.argtypes = [c_ptr, ctypes.POINTER(c_dbl)]
-    for _ in range(max(args.warmup, 3) if not mixed else 1):
+    for _ in range(max(args.warmup, 3) if not mixed else 2):
         run()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler = ClockSampler(local_rank, period=1.0 if mixed else 0.2); sampler.start()
     launches0 = lib.sb200_launch_count()
     barrier(); w0 = time.perf_counter()
     step_ms, trail_ms, trail_flops, trail_launches = [], 0.0, 0.0, 0.0
+    del phase_log[:]
     for _ in range(args.steps):
         run()
         check(lib.sb200_last_driver_stats(out._h, stats))
@@ -369,6 +372,7 @@ def run_extra(args):
     barrier(); w1 = time.perf_counter()
     launches = lib.sb200_launch_count() - launches0
     clocks = sampler.stop()
+    timed_phases = {k: sum(p[k] for p in phase_log) / len(phase_log) for k in phase_log[0]} if phase_log else {}
     t = torch.tensor([sum(step_ms) / len(step_ms), (w1 - w0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -453,8 +457,10 @@ def run_extra(args):
                        "l2": "operands (GiBs) are far larger than the 126 MB L2; no explicit flush"},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         }
+        line["step_ms"] = step_ms
         if mixed:
-            line["phases_ms"] = timers
+            timed_phases["iter"] = timers.get("iter")
+            line["phases_ms"] = timed_phases        # mean over the timed steps (reference timer names)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
