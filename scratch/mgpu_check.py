@@ -46,7 +46,10 @@ def main():
     ok = True
     for (p, q) in shapes:
         grid = sl.Grid.from_torch_distributed(p, q)
-        for (n, nb) in [(1024, 128), (1000, 128), (2048, 256)]:
+        sizes = [(1024, 128), (1000, 128), (2048, 256)]
+        if os.environ.get("MGPU_SIZES"):
+            sizes = [tuple(int(x) for x in a.split("x")) for a in os.environ["MGPU_SIZES"].split(",")]
+        for (n, nb) in sizes:
             # ---- getrf
             A = sl.Matrix(n, n, nb, grid).generate("rand", 42)
             piv, info = sl.getrf(A)
