@@ -475,7 +475,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--routine", default="potrf", choices=["potrf", "getrf", "gemm"] + EXTRA_ROUTINES)
     ap.add_argument("--nrhs", type=int, default=10)
-    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=0,
+                    help="matrix size (use --size under torchrun, whose own parser claims the prefix --n)")
     ap.add_argument("--nb", type=int, default=512)
     ap.add_argument("--ref-n", type=int, default=8192, help="bounded sample size for the CPU reference legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -12,6 +12,6 @@ echo "[$((SECONDS-T0)) s] check"
 timeout 150 $TR --master-port 29512 bench.py --gpus 2 --routine potrf --steps 2 --warmup 3 --no-e2e > $OUT/mgpu2_bench_potrf.json 2> $OUT/mgpu2_bench_potrf.err
 echo "bench potrf exit $?"; tail -1 $OUT/mgpu2_bench_potrf.json | cut -c1-400; tail -3 $OUT/mgpu2_bench_potrf.err
 echo "[$((SECONDS-T0)) s] potrf"
-timeout 150 $TR --master-port 29513 bench.py --gpus 2 --routine zherk --n 16384 --steps 2 --no-e2e > $OUT/mgpu2_bench_zherk.json 2> $OUT/mgpu2_bench_zherk.err
+timeout 150 $TR --master-port 29513 bench.py --gpus 2 --routine zherk --size 32768 --steps 2 --no-e2e > $OUT/mgpu2_bench_zherk.json 2> $OUT/mgpu2_bench_zherk.err
 echo "bench zherk exit $?"; tail -1 $OUT/mgpu2_bench_zherk.json | cut -c1-400; tail -3 $OUT/mgpu2_bench_zherk.err
 echo "[$((SECONDS-T0)) s] zherk"

@@ -460,21 +460,42 @@ int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cuda
 constexpr int TS_NC = 8;            // right-hand-side columns per CTA
 constexpr int TS_THREADS = 256;
 
+// 16-byte global loads of `n16` consecutive chunks into a register array of T
+__device__ __forceinline__ void ld16(const float* p, float* o)   { const float4 v = *reinterpret_cast<const float4*>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void ld16(const double* p, double* o) { const double2 v = *reinterpret_cast<const double2*>(p); o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void ld16(const cuFloatComplex* p, cuFloatComplex* o)
+{
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = make_cuFloatComplex(v.x, v.y); o[1] = make_cuFloatComplex(v.z, v.w);
+}
+__device__ __forceinline__ void ld16(const cuDoubleComplex* p, cuDoubleComplex* o) { o[0] = *p; }
+
 template <typename T>
 __global__ void __launch_bounds__(TS_THREADS)
 trsm_small_kernel(const T* __restrict__ Tm, int ldt, const T* __restrict__ Winv, T* const* __restrict__ Barr,
                   int64_t offB, int ldb, int na, int n, int mode, int conj)
 {
+    constexpr int QB = sizeof(T) <= 8 ? 32 : 16;         // loads in flight per thread in the update
+    constexpr int PER16 = 16 / int(sizeof(T));           // elements per 16-byte load
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     T* Xs = reinterpret_cast<T*>(smem_dyn);          // [TS_NC][na]   the right-hand sides / solution
     T* V  = Xs + size_t(TS_NC) * na;                 // [TS_NC][IB]   block staging
     T* Ws = V + TS_NC * IB;                          // [IB][IB]      inverted diagonal block of this step
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int c0 = blockIdx.x * TS_NC;
     const int nc = min(TS_NC, n - c0);
     T* __restrict__ B = Barr[blockIdx.y] + offB + int64_t(c0) * ldb;
     const int nblk = (na + IB - 1) / IB;
 
+    {   // pull the stored triangle of T towards L2 in one go: the walk below is a chain of dependent round trips
+        constexpr int PER_LINE = 128 / int(sizeof(T));
+        const int lines_per_col = (na + PER_LINE - 1) / PER_LINE;
+        for (int e = tid; e < lines_per_col * na; e += TS_THREADS) {
+            const int col = e / lines_per_col, r0 = (e - col * lines_per_col) * PER_LINE;
+            const bool need = (mode == 2) ? (r0 <= col) : (r0 + PER_LINE > col);
+            if (need) asm volatile("prefetch.global.L2 [%0];" :: "l"(Tm + r0 + int64_t(col) * ldt));
+        }
+    }
     for (int e = tid; e < TS_NC * na; e += TS_THREADS) {
         const int c = e / na, r = e - c * na;
         Xs[e] = (c < nc) ? B[r + int64_t(c) * ldb] : zero_of<T>();
@@ -489,40 +510,9 @@ trsm_small_kernel(const T* __restrict__ Tm, int ldt, const T* __restrict__ Winv,
             #pragma unroll
             for (int e = 0; e < IB * IB / TS_THREADS; ++e) Ws[tid + e * TS_THREADS] = Wg[tid + e * TS_THREADS];
         }
-        const T* Wb = Ws;
-        if (mode == 1) {
-            // v(r, :) = x(o + r, :) - sum_{i >= o + nv} op(T)(o + r, i) x(i, :),  op(T)(o + r, i) = [conj] T(i, o + r)
-            for (int r = warp; r < nv; r += TS_THREADS / 32) {
-                const T* __restrict__ col = Tm + int64_t(o + r) * ldt;
-                T acc[TS_NC];
-                #pragma unroll
-                for (int c = 0; c < TS_NC; ++c) acc[c] = zero_of<T>();
-                for (int i = o + nv + lane; i < na; i += 32 * 4) {
-                    T t[4];
-                    #pragma unroll
-                    for (int u = 0; u < 4; ++u) t[u] = (i + 32 * u < na) ? col[i + 32 * u] : zero_of<T>();
-                    #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (i + 32 * u >= na) continue;
-                        const T tv = conj ? conj_(t[u]) : t[u];
-                        #pragma unroll
-                        for (int c = 0; c < TS_NC; ++c) fma_acc(acc[c], tv, Xs[c * na + i + 32 * u]);
-                    }
-                }
-                #pragma unroll
-                for (int c = 0; c < TS_NC; ++c) {
-                    T v = acc[c];
-                    #pragma unroll
-                    for (int sh = 16; sh > 0; sh >>= 1) v = add(v, shfl_xor_t(v, sh));
-                    if (lane == 0) V[c * IB + r] = sub(Xs[c * na + o + r], v);
-                }
-            }
-        }
-        else {
-            for (int e = tid; e < TS_NC * nv; e += TS_THREADS) {
-                const int c = e / nv, r = e - c * nv;
-                V[c * IB + r] = Xs[c * na + o + r];
-            }
+        for (int e = tid; e < TS_NC * nv; e += TS_THREADS) {
+            const int c = e / nv, r = e - c * nv;
+            V[c * IB + r] = Xs[c * na + o + r];
         }
         __syncthreads();
         // y = op(Winv_b) v  (Winv_b is dense IB x IB with zeros in the other triangle)
@@ -531,40 +521,70 @@ trsm_small_kernel(const T* __restrict__ Tm, int ldt, const T* __restrict__ Winv,
             T y = zero_of<T>();
             if (mode == 1) {
                 for (int q = r; q < nv; ++q) {           // op(W)(r, q) = [conj] W(q, r), W lower
-                    T w = Wb[q + r * IB];
+                    T w = Ws[q + r * IB];
                     if (conj) w = conj_(w);
                     fma_acc(y, w, V[c * IB + q]);
                 }
             }
-            else if (mode == 0) { for (int q = 0; q <= r; ++q) fma_acc(y, Wb[r + q * IB], V[c * IB + q]); }
-            else                { for (int q = r; q < nv; ++q) fma_acc(y, Wb[r + q * IB], V[c * IB + q]); }
+            else if (mode == 0) { for (int q = 0; q <= r; ++q) fma_acc(y, Ws[r + q * IB], V[c * IB + q]); }
+            else                { for (int q = r; q < nv; ++q) fma_acc(y, Ws[r + q * IB], V[c * IB + q]); }
             Xs[c * na + o + r] = y;
         }
         __syncthreads();
-        if (mode != 1) {
-            // right-looking: x(i, :) -= T(i, o : o + nv) y  for the rows not solved yet
-            const int i_lo = (mode == 0) ? o + nv : 0, i_hi = (mode == 0) ? na : o;
-            for (int i = i_lo + tid; i < i_hi; i += TS_THREADS) {
-                T acc[TS_NC];
-                #pragma unroll
-                for (int c = 0; c < TS_NC; ++c) acc[c] = zero_of<T>();
+        // right-looking update of the rows not solved yet:  x(i, :) -= op(T)(i, o : o + nv) y
+        //   mode 0 / 2: op(T)(i, o + q) = T(i, o + q): thread-per-row, coalesced down T's columns
+        //   mode 1    : op(T)(i, o + q) = [conj] T(o + q, i): thread-per-row reads a CONTIGUOUS segment of column i
+        const int i_lo = (mode == 0) ? o + nv : 0, i_hi = (mode == 0) ? na : o;
+        for (int i = i_lo + tid; i < i_hi; i += TS_THREADS) {
+            T acc[TS_NC];
+            #pragma unroll
+            for (int c = 0; c < TS_NC; ++c) acc[c] = zero_of<T>();
+            if (mode != 1) {
                 const T* __restrict__ row = Tm + i + int64_t(o) * ldt;
-                for (int q0 = 0; q0 < nv; q0 += 16) {
-                    T t[16];
+                for (int q0 = 0; q0 < nv; q0 += QB) {
+                    T t[QB];
                     #pragma unroll
-                    for (int u = 0; u < 16; ++u) t[u] = (q0 + u < nv) ? row[int64_t(q0 + u) * ldt] : zero_of<T>();
+                    for (int u = 0; u < QB; ++u) t[u] = (q0 + u < nv) ? row[int64_t(q0 + u) * ldt] : zero_of<T>();
                     #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
+                    for (int u = 0; u < QB; ++u) {
                         if (q0 + u >= nv) continue;
                         #pragma unroll
                         for (int c = 0; c < TS_NC; ++c) fma_acc(acc[c], t[u], Xs[c * na + o + q0 + u]);
                     }
                 }
-                #pragma unroll
-                for (int c = 0; c < TS_NC; ++c) Xs[c * na + i] = sub(Xs[c * na + i], acc[c]);
             }
-            __syncthreads();
+            else {
+                const T* __restrict__ seg = Tm + o + int64_t(i) * ldt;
+                const bool vec = (nv % PER16 == 0) && ((reinterpret_cast<uintptr_t>(seg) & 15) == 0);
+                for (int q0 = 0; q0 < nv; q0 += QB) {
+                    T t[QB];
+                    if (vec) {
+                        #pragma unroll
+                        for (int u = 0; u < QB; u += PER16) {
+                            if (q0 + u < nv) ld16(seg + q0 + u, t + u);
+                            else { 
+                                #pragma unroll
+                                for (int w = 0; w < PER16; ++w) t[u + w] = zero_of<T>();
+                            }
+                        }
+                    }
+                    else {
+                        #pragma unroll
+                        for (int u = 0; u < QB; ++u) t[u] = (q0 + u < nv) ? seg[q0 + u] : zero_of<T>();
+                    }
+                    #pragma unroll
+                    for (int u = 0; u < QB; ++u) {
+                        if (q0 + u >= nv) continue;
+                        const T tv = conj ? conj_(t[u]) : t[u];
+                        #pragma unroll
+                        for (int c = 0; c < TS_NC; ++c) fma_acc(acc[c], tv, Xs[c * na + o + q0 + u]);
+                    }
+                }
+            }
+            #pragma unroll
+            for (int c = 0; c < TS_NC; ++c) Xs[c * na + i] = sub(Xs[c * na + i], acc[c]);
         }
+        __syncthreads();
     }
     for (int e = tid; e < nc * na; e += TS_THREADS) {
         const int c = e / na, r = e - c * na;
