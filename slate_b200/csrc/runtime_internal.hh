@@ -207,6 +207,10 @@ template <typename T> int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc
 template <typename T> int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C);
 template <typename T> int herk_driver(typename RealOf<T>::type alpha, Matrix& A, typename RealOf<T>::type beta, Matrix& C);
 int matrix_alloc(Grid& g, int dtype, int kind, int64_t m, int64_t n, int64_t nb, Matrix& A);
+// solve path on a p x q grid with replicated right-hand sides (solve_dist.cu; float / double)
+template <typename T> int potrs_dist(Matrix& A, Matrix& B, cudaStream_t s);
+int posv_mixed_dist_d(Matrix& A, Matrix& B, Matrix& Xm, int64_t itermax, double tol, bool use_fallback,
+                      int* iter_out, int64_t* info_out, double* timers_ms);
 
 } // namespace sb200
 

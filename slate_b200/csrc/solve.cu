@@ -267,6 +267,10 @@ template <typename T>
 int potrs_t(Matrix& A, Matrix& B, cudaStream_t s)
 {
     if (A.kind != 'H') return SB200_EINVAL;
+    if (A.g->size() > 1) {
+        if constexpr (IsComplex<T>::value) return SB200_ENOTSUP;
+        else return potrs_dist<T>(A, B, s);
+    }
     const int opH = IsComplex<T>::value ? 'C' : 'T';
     SB_TRY(tri_sweep<T>(A, true, 'N', false, B, s));
     return tri_sweep<T>(A, true, opH, false, B, s);
@@ -436,7 +440,11 @@ static bool mixed_use_tc05()
 int solve_mixed_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B, Matrix& X,
                   int64_t itermax, double tol, bool use_fallback, int* iter_out, int64_t* info_out, double* timers_ms)
 {
-    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.g->size() > 1) {
+        // p x q grid: replicated right-hand sides (solve_dist.cu); the LU variant needs the FP32 p x q getrf (next)
+        if (! hermitian) return SB200_ENOTSUP;
+        return posv_mixed_dist_d(A, B, X, itermax, tol, use_fallback, iter_out, info_out, timers_ms);
+    }
     if (A.dtype != 'd' || B.dtype != 'd' || X.dtype != 'd') return SB200_EINVAL;
     if (A.kind != (hermitian ? 'H' : 'G') || A.m != A.n || B.m != A.n || X.m != A.n || X.n != B.n
         || B.nb != A.nb || X.nb != A.nb || B.kind != 'G' || X.kind != 'G') return SB200_EINVAL;
