@@ -119,6 +119,30 @@ def main():
                     print(f"grid {p}x{q} n={n} nb={nb}: zherk err={e1:.2e} zpotrf err={e2:.2e} zgemm err={e3:.2e} "
                           f"spotrf(tcgen05) err={e4:.2e} {'ok' if good else 'FAILED'}", flush=True)
                     ok &= good
+            # ---- solve path on the grid (replicated right-hand sides, solve_dist.cu): potrs and posv_mixed
+            if os.environ.get("MGPU_SOLVE", "1") != "0":
+                Hd = sl.HermitianMatrix(n, nb, grid).generate("rand_dominant", 42)
+                Bd = sl.Matrix(n, 10, nb, grid).generate("rand", 43)
+                assert sl.potrf(Hd) == 0
+                sl.potrs(Hd, Bd)
+                xs = gather(Bd, n, 10)
+                Hm = sl.HermitianMatrix(n, nb, grid).generate("rand_dominant", 42)
+                Bm = sl.Matrix(n, 10, nb, grid).generate("rand", 43)
+                Xm = sl.Matrix(n, 10, nb, grid)
+                minfo, mit, _ = sl.posv_mixed(Hm, Bm, Xm)
+                xm = gather(Xm, n, 10)
+                if rank == 0:
+                    G = o.generate("rand_dominant", n, n, 42); b = o.generate("rand", n, 10, 43)
+                    Lo, _ = o.potrf(o.he_full(G), nb)
+                    xo = o.potrs(Lo, b, nb)
+                    e1 = np.abs(xs - xo).max() / np.abs(xo).max()
+                    xmo, ito, _ = o.solve_mixed(G, b, nb, hermitian=True)
+                    e2 = np.abs(xm - xmo).max() / np.abs(xmo).max()
+                    r2 = o.solve_residual(o.he_full(G), xm, b)
+                    good = e1 <= 200 * EPS and minfo == 0 and abs(mit - ito) <= 1 and e2 <= 1e-12 and r2 <= 25 * EPS
+                    print(f"grid {p}x{q} n={n} nb={nb}: potrs err={e1:.2e}; posv_mixed iter={mit} (oracle {ito}) err={e2:.2e} "
+                          f"resid={r2:.2e} {'ok' if good else 'FAILED'}", flush=True)
+                    ok &= good
             dist.barrier()
         grid.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
