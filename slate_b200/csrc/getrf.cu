@@ -717,8 +717,15 @@ int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out)
 
 int getrf_driver_s(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_tc05)
 {
+    const char* fd = getenv("SB200_GETRF_DIST");
+    const bool force_dist = fd && atoi(fd) != 0;
+    if (A.dtype != 's') return SB200_EINVAL;
+    if (A.g->size() > 1 || force_dist) return getrf_driver_dist_s(A, pivots_out, info_out, use_tc05);
     return getrf_driver_t<float>(A, pivots_out, info_out, use_tc05);
 }
+
+template int getrf_panel<double>(double* const*, double*, int, int, int, int, int64_t*, int64_t*, int*, int, PanelScratch&, cudaStream_t, int*, PhaseTimer*);
+template int getrf_panel<float>(float* const*, float*, int, int, int, int, int64_t*, int64_t*, int*, int, PanelScratch&, cudaStream_t, int*, PhaseTimer*);
 
 template int launch_laswp<double>(double* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);
 template int launch_laswp<float>(float* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);

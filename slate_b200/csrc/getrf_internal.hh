@@ -30,6 +30,12 @@ int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, doub
                     double* W, cudaStream_t stream);
 
 int getrf_driver_dist(Matrix& A, int64_t* pivots_out, int64_t* info_out);
+int getrf_driver_dist_s(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_tc05);     // FP32, p x q grid
+// type-generic panel (getrf.cu; float and double)
+template <typename T>
+int getrf_panel(T* const* stack, T* tile0, int ntile, int nb, int m_p, int kw,
+                int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
+                PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph);
 int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out);                      // FP64, any grid
 int getrf_driver_s(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_tc05);     // FP32, 1 x 1 grid
 
