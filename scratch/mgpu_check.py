@@ -131,6 +131,17 @@ def main():
                 Xm = sl.Matrix(n, 10, nb, grid)
                 minfo, mit, _ = sl.posv_mixed(Hm, Bm, Xm)
                 xm = gather(Xm, n, 10)
+                Gm = sl.Matrix(n, n, nb, grid).generate("rand", 42)
+                Bg = sl.Matrix(n, 10, nb, grid).generate("rand", 43)
+                Xg = sl.Matrix(n, 10, nb, grid)
+                ginfo, git, _gp, _ = sl.gesv_mixed(Gm, Bg, Xg)
+                xg = gather(Xg, n, 10)
+                if rank == 0:
+                    ag = o.generate("rand", n, n, 42)
+                    rg = o.solve_residual(ag, xg, o.generate("rand", n, 10, 43))
+                    goodg = ginfo == 0 and 0 <= git <= 30 and rg <= 25 * EPS
+                    print(f"grid {p}x{q} n={n} nb={nb}: gesv_mixed iter={git} resid={rg:.2e} {'ok' if goodg else 'FAILED'}", flush=True)
+                    ok &= goodg
                 if rank == 0:
                     G = o.generate("rand_dominant", n, n, 42); b = o.generate("rand", n, 10, 43)
                     Lo, _ = o.potrf(o.he_full(G), nb)

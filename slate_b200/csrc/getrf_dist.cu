@@ -26,7 +26,8 @@
 // The driver is a template over float / double.  T = float is the low-precision factorisation of gesv_mixed on
 // the grid; with use_tc05 its trailing / lookahead GEMMs run on the tcgen05 FP32-emulated kernel, the panel
 // workspace tiles (A role) and the U slots (B role) being split-packed once per step.
-// STATUS of T = float: written in round 1 after the GPU budget was spent -- compiled, not yet run.
+// STATUS of T = float: validated on ONE GPU through the test hook SB200_GETRF_DIST=1 (the p x q algorithm minus the
+// NCCL calls: FP32 LU tests with and without the tcgen05 update, gesv_mixed on top of it); not yet run on a grid.
 #include "runtime_internal.hh"
 #include "getrf_internal.hh"
 #include <algorithm>

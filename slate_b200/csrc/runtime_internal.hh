@@ -209,8 +209,9 @@ template <typename T> int herk_driver(typename RealOf<T>::type alpha, Matrix& A,
 int matrix_alloc(Grid& g, int dtype, int kind, int64_t m, int64_t n, int64_t nb, Matrix& A);
 // solve path on a p x q grid with replicated right-hand sides (solve_dist.cu; float / double)
 template <typename T> int potrs_dist(Matrix& A, Matrix& B, cudaStream_t s);
-int posv_mixed_dist_d(Matrix& A, Matrix& B, Matrix& Xm, int64_t itermax, double tol, bool use_fallback,
-                      int* iter_out, int64_t* info_out, double* timers_ms);
+template <typename T> int getrs_dist(Matrix& A, const int64_t* pivots, Matrix& B, cudaStream_t s);
+int solve_mixed_dist_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B, Matrix& Xm, int64_t itermax, double tol,
+                       bool use_fallback, int* iter_out, int64_t* info_out, double* timers_ms);
 
 } // namespace sb200
 

@@ -159,6 +159,13 @@ __global__ void __launch_bounds__(1024) rowsum_kernel(const T* __restrict__ pool
     for (int t = threadIdx.x; t < mb; t += blockDim.x) rowsum[i * nb + t] = acc[t];
 }
 
+// SB200_DIST_SOLVE=2: run the p x q solve path (solve_dist.cu) on a 1 x 1 grid too -- test hook, same code minus NCCL
+static bool force_dist_solve()
+{
+    const char* e = getenv("SB200_DIST_SOLVE");
+    return e && atoi(e) == 2;
+}
+
 // ------------------------------------------------------------------------------------------ host helpers
 template <typename S, typename D>
 static int convert_pool(const Matrix& src, Matrix& dst, cudaStream_t s)
@@ -267,7 +274,7 @@ template <typename T>
 int potrs_t(Matrix& A, Matrix& B, cudaStream_t s)
 {
     if (A.kind != 'H') return SB200_EINVAL;
-    if (A.g->size() > 1) {
+    if (A.g->size() > 1 || (force_dist_solve() && ! IsComplex<T>::value && B.nt <= 1)) {
         if constexpr (IsComplex<T>::value) return SB200_ENOTSUP;
         else return potrs_dist<T>(A, B, s);
     }
@@ -440,10 +447,9 @@ static bool mixed_use_tc05()
 int solve_mixed_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B, Matrix& X,
                   int64_t itermax, double tol, bool use_fallback, int* iter_out, int64_t* info_out, double* timers_ms)
 {
-    if (A.g->size() > 1) {
-        // p x q grid: replicated right-hand sides (solve_dist.cu); the LU variant needs the FP32 p x q getrf (next)
-        if (! hermitian) return SB200_ENOTSUP;
-        return posv_mixed_dist_d(A, B, X, itermax, tol, use_fallback, iter_out, info_out, timers_ms);
+    if (A.g->size() > 1 || (force_dist_solve() && B.nt <= 1)) {
+        // p x q grid: replicated right-hand sides (solve_dist.cu)
+        return solve_mixed_dist_d(hermitian, A, pivots_out, B, X, itermax, tol, use_fallback, iter_out, info_out, timers_ms);
     }
     if (A.dtype != 'd' || B.dtype != 'd' || X.dtype != 'd') return SB200_EINVAL;
     if (A.kind != (hermitian ? 'H' : 'G') || A.m != A.n || B.m != A.n || X.m != A.n || X.n != B.n
@@ -609,8 +615,12 @@ SB200_FOR_TYPES(SB200_DEF_SOLVE)
 static int getrs_any(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B)
 {
     if (! A || ! B || ! pivots) return SB200_EINVAL;
-    if (A->A.g->size() > 1) return SB200_ENOTSUP;
     CUDA_TRY(cudaDeviceSynchronize());
+    if (A->A.g->size() > 1 || (force_dist_solve() && B->A.nt <= 1)) {
+        if (A->A.dtype == 'd') return getrs_dist<double>(A->A, pivots, B->A, nullptr);
+        if (A->A.dtype == 's') return getrs_dist<float>(A->A, pivots, B->A, nullptr);
+        return SB200_ENOTSUP;
+    }
     std::vector<int> perm;
     pivots_to_perm(pivots, A->A.m, A->A.n, A->A.nb, perm);
     DevBuf dp;

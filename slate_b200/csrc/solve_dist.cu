@@ -19,6 +19,7 @@
 // grid.  Reached only when the grid has more than one rank (the 1 x 1 path in solve.cu
 // is the validated one); SB200_DIST_SOLVE=0 restores SB200_ENOTSUP.
 #include "runtime_internal.hh"
+#include "getrf_internal.hh"
 #include <algorithm>
 #include <array>
 #include <chrono>
@@ -138,7 +139,7 @@ int gather_rep(Matrix& B, RepVec<T>& X, cudaStream_t s)
     for (int64_t i = g.prow; i < B.mt; i += g.p)
         if (B.is_local(i, 0))
             CUDA_TRY(cudaMemcpyAsync(X.blk(i), B.tile_as<T>(i, 0), size_t(X.nb) * X.nrhs * sizeof(T), cudaMemcpyDeviceToDevice, s));
-    NCCL_TRY(ncclAllReduce(X.base, X.base, X.elems(), NcclType<T>::value, ncclSum, g.world, s));
+    if (g.size() > 1) NCCL_TRY(ncclAllReduce(X.base, X.base, X.elems(), NcclType<T>::value, ncclSum, g.world, s));
     return SB200_OK;
 }
 
@@ -248,7 +249,7 @@ int sweep_dist(Matrix& A, bool lower, int op, bool unit, RepVec<T>& X, cudaStrea
             }
             else SB_TRY(st_small);
         }
-        NCCL_TRY(ncclBroadcast(X.blk(i), X.blk(i), size_t(blk_elems), NcclType<T>::value, owner, g.world, s));
+        if (g.size() > 1) NCCL_TRY(ncclBroadcast(X.blk(i), X.blk(i), size_t(blk_elems), NcclType<T>::value, owner, g.world, s));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     return SB200_OK;
@@ -308,7 +309,7 @@ int residual_dist(Matrix& A, const RepVec<T>& Bv, const RepVec<T>& X, RepVec<T>&
         SB_TRY(launch_batches<T>(st.above, pb, 'T', 'N', T(-1), T(1), ld, 0, s));
         SB_TRY(launch_batches<T>(st.diag, pb, 'N', 'N', T(-1), T(1), ld, 0, s));
     }
-    NCCL_TRY(ncclAllReduce(R.base, R.base, R.elems(), NcclType<T>::value, ncclSum, g.world, s));
+    if (g.size() > 1) NCCL_TRY(ncclAllReduce(R.base, R.base, R.elems(), NcclType<T>::value, ncclSum, g.world, s));
     rv_axpby_kernel<T><<<rv_grid(int64_t(R.elems())), 256, 0, s>>>(Bv.base, T(1), R.base, R.base, int64_t(R.elems()));
     SB_TRY(launch_status());
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -368,7 +369,7 @@ int norm_inf_dist_d(Matrix& A, double* out, cudaStream_t s)
     DevBuf red;
     SB_TRY(red.alloc(rowsum.size() * sizeof(double)));
     CUDA_TRY(cudaMemcpyAsync(red.p, rowsum.data(), rowsum.size() * sizeof(double), cudaMemcpyHostToDevice, s));
-    NCCL_TRY(ncclAllReduce(red.p, red.p, rowsum.size(), ncclDouble, ncclSum, g.world, s));
+    if (g.size() > 1) NCCL_TRY(ncclAllReduce(red.p, red.p, rowsum.size(), ncclDouble, ncclSum, g.world, s));
     CUDA_TRY(cudaMemcpyAsync(rowsum.data(), red.p, rowsum.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     double mx = 0.0;
@@ -420,12 +421,76 @@ int potrs_dist(Matrix& A, Matrix& B, cudaStream_t s)
 template int potrs_dist<float>(Matrix&, Matrix&, cudaStream_t);
 template int potrs_dist<double>(Matrix&, Matrix&, cudaStream_t);
 
-// posv_mixed<double, float> on a p x q grid (same control flow as solve_mixed_d in solve.cu / src/posv_mixed.cc)
-int posv_mixed_dist_d(Matrix& A, Matrix& B, Matrix& Xm, int64_t itermax, double tol, bool use_fallback,
-                      int* iter_out, int64_t* info_out, double* timers_ms)
+// getrs on a p x q grid (B: one tile column); pivots as returned by getrf (host)
+template <typename T>
+int getrs_dist(Matrix& A, const int64_t* pivots, Matrix& B, cudaStream_t s);
+
+// row gather on a replicated block vector: out(x, :) = in(perm[x], :)   (permuteRows Forward of getrs, src/getrs.cc:45-46)
+template <typename T>
+__global__ void __launch_bounds__(256) rv_gather_rows_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                             const int* __restrict__ perm, int64_t m, int nb, int nrhs)
+{
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < m * nrhs; e += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t x = e % m, c = e / m, y = perm[x];
+        out[(x / nb) * int64_t(nb) * nrhs + (x % nb) + c * nb] = in[(y / nb) * int64_t(nb) * nrhs + (y % nb) + c * nb];
+    }
+}
+
+static void pivots_to_perm_h(const int64_t* piv, int64_t m, int64_t n, int64_t nb, std::vector<int>& perm)
+{
+    perm.resize(size_t(m));
+    for (int64_t i = 0; i < m; ++i) perm[size_t(i)] = int(i);
+    const int64_t mn = std::min(m, n);
+    for (int64_t o = 0; o < mn; ++o) {
+        const int64_t r2 = (o / nb) * nb + piv[2 * o] * nb + piv[2 * o + 1];
+        if (r2 != o && r2 >= 0 && r2 < m) std::swap(perm[size_t(o)], perm[size_t(r2)]);
+    }
+}
+
+// X <- A^{-1} X from the LU factors: row gather with the composed permutation, unit-L sweep, U sweep
+template <typename T>
+static int getrs_rep(Matrix& A, const int* dperm, RepVec<T>& X, RepVec<T>& tmp, cudaStream_t s)
+{
+    const int64_t cnt = X.m * X.nrhs;
+    if (cnt > 0) {
+        CUDA_TRY(cudaMemcpyAsync(tmp.base, X.base, X.elems() * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        rv_gather_rows_kernel<T><<<rv_grid(cnt), 256, 0, s>>>(tmp.base, X.base, dperm, X.m, int(X.nb), X.nrhs);
+        SB_TRY(launch_status());
+    }
+    SB_TRY(sweep_dist<T>(A, true, 'N', true, X, s));
+    return sweep_dist<T>(A, false, 'N', false, X, s);
+}
+
+template <typename T>
+int getrs_dist(Matrix& A, const int64_t* pivots, Matrix& B, cudaStream_t s)
 {
     if (! dist_solve_enabled()) return SB200_ENOTSUP;
-    if (A.dtype != 'd' || B.dtype != 'd' || Xm.dtype != 'd' || A.kind != 'H') return SB200_EINVAL;
+    if (A.kind != 'G' || A.m != A.n || B.kind != 'G' || B.m != A.n || B.nb != A.nb || B.g != A.g) return SB200_EINVAL;
+    if (B.nt > 1) return SB200_ENOTSUP;
+    if (B.nt == 0 || A.nt == 0) return SB200_OK;
+    std::vector<int> perm;
+    pivots_to_perm_h(pivots, A.m, A.n, A.nb, perm);
+    DevBuf dp;
+    SB_TRY(dp.alloc(perm.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(dp.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    RepVec<T> X, tmp;
+    SB_TRY(X.alloc(B.m, B.nb, int(B.n))); SB_TRY(tmp.alloc(B.m, B.nb, int(B.n)));
+    SB_TRY(gather_rep<T>(B, X, s));
+    SB_TRY(getrs_rep<T>(A, dp.as<int>(), X, tmp, s));
+    SB_TRY(scatter_rep<T>(X, B, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SB200_OK;
+}
+template int getrs_dist<float>(Matrix&, const int64_t*, Matrix&, cudaStream_t);
+template int getrs_dist<double>(Matrix&, const int64_t*, Matrix&, cudaStream_t);
+
+// posv_mixed / gesv_mixed <double, float> on a p x q grid (same control flow as solve_mixed_d in solve.cu /
+// src/posv_mixed.cc:111-297, src/gesv_mixed.cc:106-300)
+int solve_mixed_dist_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B, Matrix& Xm, int64_t itermax, double tol,
+                       bool use_fallback, int* iter_out, int64_t* info_out, double* timers_ms)
+{
+    if (! dist_solve_enabled()) return SB200_ENOTSUP;
+    if (A.dtype != 'd' || B.dtype != 'd' || Xm.dtype != 'd' || A.kind != (hermitian ? 'H' : 'G') || A.m != A.n) return SB200_EINVAL;
     if (B.m != A.n || Xm.m != A.n || Xm.n != B.n || B.nb != A.nb || Xm.nb != A.nb || B.g != A.g || Xm.g != A.g) return SB200_EINVAL;
     if (B.nt > 1) return SB200_ENOTSUP;
     const double eps = std::numeric_limits<double>::epsilon();
@@ -441,11 +506,15 @@ int posv_mixed_dist_d(Matrix& A, Matrix& B, Matrix& Xm, int64_t itermax, double 
 
     Matrix A_lo;
     struct MG { Matrix& M; ~MG() { if (M.pool) cudaFree(M.pool); } } mguard{A_lo};
-    SB_TRY(matrix_alloc(*A.g, 's', 'H', A.m, A.n, A.nb, A_lo));
-    RepVec<double> Bv, Xv, Rv;
-    RepVec<float> Xlo;
+    SB_TRY(matrix_alloc(*A.g, 's', A.kind, A.m, A.n, A.nb, A_lo));
+    RepVec<double> Bv, Xv, Rv, Tv;
+    RepVec<float> Xlo, Tlo;
     SB_TRY(Bv.alloc(B.m, B.nb, nrhs)); SB_TRY(Xv.alloc(B.m, B.nb, nrhs)); SB_TRY(Rv.alloc(B.m, B.nb, nrhs));
     SB_TRY(Xlo.alloc(B.m, B.nb, nrhs));
+    if (! hermitian) { SB_TRY(Tv.alloc(B.m, B.nb, nrhs)); SB_TRY(Tlo.alloc(B.m, B.nb, nrhs)); }
+    std::vector<int64_t> piv_lo(size_t(2 * std::max<int64_t>(A.m, 1)));
+    std::vector<int> perm;
+    DevBuf dperm;
     DevBuf dnorm;
     SB_TRY(dnorm.alloc(size_t(std::max(nrhs, 1)) * sizeof(double)));
     std::vector<double> cn_x, cn_r;
@@ -470,15 +539,27 @@ int posv_mixed_dist_d(Matrix& A, Matrix& B, Matrix& Xm, int64_t itermax, double 
     const char* e = getenv("SB200_MIXED_TC05");
     const bool tc = ! (e && atoi(e) == 0);
     c.start();
-    SB_TRY(potrf_driver<float>(A_lo, &info, tc));
+    if (hermitian) SB_TRY(potrf_driver<float>(A_lo, &info, tc));
+    else           SB_TRY(getrf_driver_dist_s(A_lo, piv_lo.data(), &info, tc));
     tm[1] = c.stop();
+    auto upload_perm = [&](const int64_t* pv) -> int {
+        pivots_to_perm_h(pv, A.m, A.n, A.nb, perm);
+        if (! dperm.p) SB_TRY(dperm.alloc(perm.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return SB200_OK;
+    };
+    if (! hermitian && info == 0) SB_TRY(upload_perm(piv_lo.data()));
     Xm.last_trail_ms = A_lo.last_trail_ms; Xm.last_trail_flops = A_lo.last_trail_flops;
     Xm.last_trail_launches = A_lo.last_trail_launches; Xm.last_panel_ms = A_lo.last_panel_ms;
 
     auto solve_lo = [&]() -> int {            // Xlo <- A_lo^{-1} Xlo
         c.start();
-        SB_TRY(sweep_dist<float>(A_lo, true, 'N', false, Xlo, s));
-        SB_TRY(sweep_dist<float>(A_lo, true, 'T', false, Xlo, s));
+        if (hermitian) {
+            SB_TRY(sweep_dist<float>(A_lo, true, 'N', false, Xlo, s));
+            SB_TRY(sweep_dist<float>(A_lo, true, 'T', false, Xlo, s));
+        }
+        else SB_TRY(getrs_rep<float>(A_lo, dperm.as<int>(), Xlo, Tlo, s));
         tm[2] += c.stop();
         return SB200_OK;
     };
@@ -515,17 +596,27 @@ int posv_mixed_dist_d(Matrix& A, Matrix& B, Matrix& Xm, int64_t itermax, double 
         if (info == 0) iter = -int(itermax) - 1;
         if (use_fallback) {
             c.start();
-            SB_TRY(potrf_driver<double>(A, &info, false));
+            int64_t* pv = pivots_out ? pivots_out : piv_lo.data();
+            if (hermitian) SB_TRY(potrf_driver<double>(A, &info, false));
+            else           SB_TRY(getrf_driver(A, pv, &info));
             tm[5] = c.stop();
             c.start();
             if (info == 0) {
                 CUDA_TRY(cudaMemcpyAsync(Xv.base, Bv.base, Xv.elems() * sizeof(double), cudaMemcpyDeviceToDevice, s));
-                SB_TRY(sweep_dist<double>(A, true, 'N', false, Xv, s));
-                SB_TRY(sweep_dist<double>(A, true, 'T', false, Xv, s));
+                if (hermitian) {
+                    SB_TRY(sweep_dist<double>(A, true, 'N', false, Xv, s));
+                    SB_TRY(sweep_dist<double>(A, true, 'T', false, Xv, s));
+                }
+                else {
+                    SB_TRY(upload_perm(pv));
+                    SB_TRY(getrs_rep<double>(A, dperm.as<int>(), Xv, Tv, s));
+                }
             }
             tm[6] = c.stop();
         }
     }
+    if (converged && pivots_out && ! hermitian)
+        memcpy(pivots_out, piv_lo.data(), size_t(2 * std::min(A.m, A.n)) * sizeof(int64_t));
     SB_TRY(scatter_rep<double>(Xv, Xm, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     tm[0] = total.stop();
