@@ -13,6 +13,7 @@
 // conditioning of the IB x IB diagonal blocks only.
 #include "gemm_dmma.cuh"
 #include "scalar_ops.cuh"
+#include <cstdlib>
 
 namespace sb200 {
 
@@ -189,7 +190,10 @@ __device__ __forceinline__ void store_inverse(R* __restrict__ Xs, const R (&x)[I
     }
 }
 
-template <typename R>
+// RSQ (opt-in, SB200_DIAG_RSQRT=1): one rsqrt per column instead of two divisions and a square root -- the
+// dependent chain of software FP64 divisions is what this kernel's 109 us are made of;
+// L_ij = a_ij * rinv, update with (a_ij * rinv^2), diag = d * rinv: <= 2-3 ulp from the divided form.
+template <typename R, bool RSQ = false>
 __global__ void __launch_bounds__(IB, 1)
 potrf_diag_fast_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv,
                        int* __restrict__ info, int info_base)
@@ -211,12 +215,22 @@ potrf_diag_fast_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv,
         __syncthreads();
         const R d = Ls[j * IB + j];
         if (fail == 0 && !(d > R(0))) fail = j + 1;          // also catches NaN; uniform over the CTA
+        if constexpr (RSQ) {
+            const R rinv = rsqrt(d);
+            const R w = a[j] * (rinv * rinv);
+            #pragma unroll
+            for (int c = j + 1; c < IB; ++c) a[c] = fma(-w, Ls[j * IB + c], a[c]);
+            a[j] = (i == j) ? d * rinv : a[j] * rinv;
+            if (i == j) rdiag = rinv;
+        }
+        else {
         const R w = a[j] / d;
         #pragma unroll
         for (int c = j + 1; c < IB; ++c) a[c] = fma(-w, Ls[j * IB + c], a[c]);
         const R r = sqrt(d);
         a[j] = (i == j) ? r : a[j] / r;
         if (i == j) rdiag = R(1) / r;
+        }
     }
     if (fail) {
         if (i == 0 && *info == 0) *info = info_base + fail;
@@ -279,8 +293,11 @@ template <> struct IsRealType<double> { static constexpr bool value = true; };
 template <typename T>
 static int launch_potrf_diag(T* A, int lda, int nv, T* Winv, int* info, int info_base, cudaStream_t stream)
 {
-    if constexpr (IsRealType<T>::value)
-        potrf_diag_fast_kernel<T><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+    if constexpr (IsRealType<T>::value) {
+        static const bool rsq = [] { const char* e = getenv("SB200_DIAG_RSQRT"); return e && atoi(e) != 0; }();
+        if (rsq) potrf_diag_fast_kernel<T, true><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+        else     potrf_diag_fast_kernel<T, false><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+    }
     else
         potrf_diag_kernel<T><<<1, 256, small_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
     return launch_status();
@@ -321,7 +338,8 @@ static void small_kernels_init()
     cudaFuncSetAttribute(potrf_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem<T>()));
     cudaFuncSetAttribute(trtri_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(small_smem<T>()));
     if constexpr (IsRealType<T>::value) {
-        cudaFuncSetAttribute(potrf_diag_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
+        cudaFuncSetAttribute(potrf_diag_fast_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
+        cudaFuncSetAttribute(potrf_diag_fast_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
         cudaFuncSetAttribute(trtri_diag_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
     }
     done[dev & 63] = true;
