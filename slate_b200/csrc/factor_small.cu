@@ -250,6 +250,111 @@ potrf_diag_fast_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv,
     store_inverse<R>(Ls, x, i, Winv, false);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-synchronous variant of the diagonal-block Cholesky (opt-in: SB200_DIAG_WARP=1; round-2 candidate,
+// written after round 1's GPU budget was spent, NOT yet run).  Same contract as potrf_diag_fast_kernel.
+// The 64 x 64 block is handled as 2 x 2 blocks of 32: a 32 x 32 Cholesky lives entirely in ONE warp
+// (thread = row, the pivot and the normalised column travel by shuffles: no shared memory, no block
+// barrier on the 32-step chain), and each column costs one rsqrt instead of two divisions and a sqrt.
+//   warp 0: L11 = chol(A11)                                   (shuffles)
+//   warp 1: L21 = A21 L11^-T (rows independent), A22 -= L21 L21^T (L21 via shared memory), L22 = chol(A22)
+// Two block barriers in total; then the inverse exactly as in the fast kernel.
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ int chol32_warp(R (&a)[IB], int c0, int lane, R& rdiag)
+{
+    // in-warp Cholesky of the 32 x 32 block whose row `lane` sits in a[c0 .. c0 + 32); returns the first failing
+    // column + 1 (warp-uniform) or 0.  On return a[c0 + j] = L(lane, j) for j <= lane; rdiag = 1 / L(lane, lane).
+    int fail = 0;
+    #pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const R d = __shfl_sync(0xffffffffu, a[c0 + j], j);
+        if (fail == 0 && !(d > R(0))) fail = j + 1;
+        const R rinv = rsqrt(d);
+        const R lj = (lane == j) ? d * rinv : a[c0 + j] * rinv;          // L(lane, j) for lane >= j
+        a[c0 + j] = lj;
+        if (lane == j) rdiag = rinv;
+        #pragma unroll
+        for (int c = j + 1; c < 32; ++c) {
+            const R lc = __shfl_sync(0xffffffffu, lj, c);                // L(c, j)
+            a[c0 + c] = fma(-lj, lc, a[c0 + c]);                         // meaningful for lane >= c
+        }
+    }
+    return fail;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(IB, 1)
+potrf_diag_warp_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv,
+                       int* __restrict__ info, int info_base)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    R* Ls = reinterpret_cast<R*>(smem_dyn);        // [IB*(IB+1)]: L columns (stride IB), later padded staging
+    R* rd = Ls + IB * (IB + 1);                    // [IB] reciprocal diagonal
+    __shared__ int s_fail;
+    const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+    if (*info != 0) return;                        // an earlier block already failed: leave the tile alone
+    if (i == 0) s_fail = 0;
+    R a[IB];
+    #pragma unroll
+    for (int c = 0; c < IB; ++c)
+        a[c] = (i < nv && c < nv) ? (c <= i ? A[i + int64_t(c) * lda] : R(0)) : (i == c ? R(1) : R(0));
+    R rdiag = R(1);
+    __syncthreads();
+    if (warp == 0) {
+        const int f = chol32_warp<R>(a, 0, lane, rdiag);
+        if (f && lane == 0) s_fail = f;
+        #pragma unroll
+        for (int c = 0; c < 32; ++c) Ls[c * IB + i] = a[c];              // L11, column-major (rows 0..31)
+        rd[i] = rdiag;
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (i == 0 && *info == 0) *info = info_base + s_fail;
+        return;
+    }
+    if (warp == 1) {
+        // L21 row: forward substitution against L11 (column-oriented: after l_j is known, update the later entries)
+        #pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const R lj = a[j] * rd[j];
+            a[j] = lj;
+            #pragma unroll
+            for (int c = j + 1; c < 32; ++c) a[c] = fma(-lj, Ls[j * IB + c], a[c]);      // L11(c, j)
+        }
+        // park L21 in shared memory (rows 32..63 of the same column-major array), then A22 -= L21 L21^T (lower part)
+        #pragma unroll
+        for (int c = 0; c < 32; ++c) Ls[c * IB + i] = a[c];
+        __syncwarp();
+        #pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            R acc = a[32 + c];
+            #pragma unroll
+            for (int q = 0; q < 32; ++q) acc = fma(-a[q], Ls[q * IB + 32 + c], acc);      // L21(i, q) * L21(32 + c, q)
+            a[32 + c] = acc;                                                              // meaningful for c <= lane
+        }
+        const int f = chol32_warp<R>(a, 32, lane, rdiag);
+        if (f && lane == 0) s_fail = 32 + f;
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (i == 0 && *info == 0) *info = info_base + s_fail;
+        return;
+    }
+    #pragma unroll
+    for (int c = 0; c < IB; ++c)
+        if (c <= i && i < nv) A[i + int64_t(c) * lda] = a[c];
+    // L (final) into shared memory for the inverse; rows above the diagonal are never read
+    __syncthreads();
+    #pragma unroll
+    for (int c = 0; c < IB; ++c) Ls[c * IB + i] = a[c];
+    rd[i] = rdiag;
+    __syncthreads();
+    R x[IB];
+    inv_lower_column<R>(Ls, rd, i, x);
+    store_inverse<R>(Ls, x, i, Winv, false);
+}
+
 // fast trtri of the diagonal IB-blocks (real types): same contract as trtri_diag_kernel
 template <typename R>
 __global__ void __launch_bounds__(IB, 1)
@@ -295,7 +400,9 @@ static int launch_potrf_diag(T* A, int lda, int nv, T* Winv, int* info, int info
 {
     if constexpr (IsRealType<T>::value) {
         static const bool rsq = [] { const char* e = getenv("SB200_DIAG_RSQRT"); return e && atoi(e) != 0; }();
-        if (rsq) potrf_diag_fast_kernel<T, true><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+        static const bool wrp = [] { const char* e = getenv("SB200_DIAG_WARP"); return e && atoi(e) != 0; }();
+        if (wrp)      potrf_diag_warp_kernel<T><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+        else if (rsq) potrf_diag_fast_kernel<T, true><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
         else     potrf_diag_fast_kernel<T, false><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
     }
     else
@@ -340,6 +447,7 @@ static void small_kernels_init()
     if constexpr (IsRealType<T>::value) {
         cudaFuncSetAttribute(potrf_diag_fast_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
         cudaFuncSetAttribute(potrf_diag_fast_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
+        cudaFuncSetAttribute(potrf_diag_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
         cudaFuncSetAttribute(trtri_diag_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
     }
     done[dev & 63] = true;
