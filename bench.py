@@ -302,14 +302,15 @@ def run_extra(args):
     if routine == "tileops":
         return run_tileops(args, sl, lib, torch)
     mixed = routine in ("posv_mixed", "gesv_mixed")
-    if mixed and world > 1:
-        raise SystemExit("bench.py: the mixed-precision solve path runs on a 1 x 1 grid this round")
+    if mixed and world > 1 and os.environ.get("SB200_RUN_UNVALIDATED") != "1":
+        raise SystemExit("bench.py: the mixed-precision solve path on a p x q grid (csrc/solve_dist.cu) has not been validated "
+                         "on GPUs yet; set SB200_RUN_UNVALIDATED=1 to run it")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     n = args.n or ({"zgemm": 16384, "zherk": 16384, "zpotrf": 24576, "posv_mixed": 32768, "gesv_mixed": 32768}[routine]
-                   if world == 1 else {"zgemm": 40960, "zherk": 40960, "zpotrf": 40960}[routine])
+                   if world == 1 else {"zgemm": 40960, "zherk": 40960, "zpotrf": 40960, "posv_mixed": 65536, "gesv_mixed": 65536}[routine])
     grid = sl.Grid.from_torch_distributed() if world > 1 else sl.Grid()
     st = torch.cuda.current_stream().cuda_stream
 
