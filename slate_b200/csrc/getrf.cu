@@ -99,6 +99,8 @@ struct BaseArgs {
     int kw_wide;       // > 0: the LAST CTA of the grid owns no rows and applies every interchange of this
                        // block to the panel columns outside [c0, c0+w) (all kw_wide columns of the panel)
                        // while the other CTAs go on factoring -- no laswp launches between blocks
+    unsigned* bar;     // opt-in (SB200_PANEL_BARRIER=1, round-2 candidate): arrival counter of a hand-rolled grid
+                       // barrier (zeroed before the launch) used instead of cooperative-groups grid.sync()
 };
 
 template <typename T>
@@ -165,7 +167,19 @@ getrf_base_kernel(const BaseArgs<T> a)
             if (d >= r_begin && d < r_end) a.gdiag[par * PW + tid] = blk[tid * RP + (d - r_begin)];
         }
         __threadfence();
-        grid.sync();
+        if (a.bar) {
+            // one arrival per CTA per column; released when all gridDim.x CTAs of this launch have arrived j + 1 times
+            __syncthreads();
+            if (tid == 0) {
+                atomicAdd(a.bar, 1u);
+                const unsigned target = unsigned(j + 1) * gridDim.x;
+                unsigned seen;
+                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.bar) : "memory"); } while (seen < target);
+            }
+            __syncthreads();
+            __threadfence();          // every thread orders its reads of the other CTAs' candidates after the release it waited for
+        }
+        else grid.sync();
 
         // ---- every CTA picks the same winner: diagonal first, then strictly larger candidates
         if (warp == 0) {
@@ -252,14 +266,16 @@ int PanelScratch::init()
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     max_ctas = sms;
     const size_t G = size_t(sms);
-    const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8;
+    const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8 + 64;
     CUDA_TRY(cudaMalloc(&raw, bytes));
     char* p = static_cast<char*>(raw);
     gval = reinterpret_cast<double*>(p); p += 2 * G * 8;
     grow = reinterpret_cast<int*>(p);    p += 2 * G * 8;
     gcand = reinterpret_cast<double*>(p); p += 2 * G * PW * 8;
     gdiag = reinterpret_cast<double*>(p); p += 2 * PW * 8;
-    W = reinterpret_cast<double*>(p);
+    W = reinterpret_cast<double*>(p); p += 16 * 64 * 64 * 8;
+    bar = reinterpret_cast<unsigned*>(p);
+    { const char* e = getenv("SB200_PANEL_BARRIER"); use_bar = e && atoi(e) != 0; }
     static thread_local bool attr_done[64] = {};
     if (! attr_done[dev & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -304,7 +320,9 @@ static int panel_base_wide(const PanelCtx<T>& x, int c0, int w)
     const int G = int(ceil_div(active, rows_per));
     BaseArgs<T> a{x.stack, x.nb, x.m_p, c0, w, rows_per, x.piv_tile, x.piv_off,
                   reinterpret_cast<T*>(x.ps->gval), x.ps->grow, reinterpret_cast<T*>(x.ps->gcand),
-                  reinterpret_cast<T*>(x.ps->gdiag), x.dinfo, x.info_base, x.rowmap, x.kw};
+                  reinterpret_cast<T*>(x.ps->gdiag), x.dinfo, x.info_base, x.rowmap, x.kw,
+                  x.ps->use_bar ? x.ps->bar : nullptr};
+    if (x.ps->use_bar) CUDA_TRY(cudaMemsetAsync(x.ps->bar, 0, sizeof(unsigned), x.s));
     void* args[] = {&a};
     const size_t smem = size_t(w) * (rows_per | 1) * sizeof(T);
     x.pt->begin("pnl_base", x.s);
@@ -406,7 +424,8 @@ static int getrf_panel_v1(T* const* stack, T* tile0, int ntile, int nb, int m_p,
         const int G = int(ceil_div(active, rows_per));
         BaseArgs<T> a{stack, nb, m_p, c0, w, rows_per, piv_tile, piv_off,
                       reinterpret_cast<T*>(ps.gval), ps.grow, reinterpret_cast<T*>(ps.gcand),
-                      reinterpret_cast<T*>(ps.gdiag), dinfo, info_base, rowmap, 0};
+                      reinterpret_cast<T*>(ps.gdiag), dinfo, info_base, rowmap, 0, ps.use_bar ? ps.bar : nullptr};
+        if (ps.use_bar) CUDA_TRY(cudaMemsetAsync(ps.bar, 0, sizeof(unsigned), s));
         void* args[] = {&a};
         const size_t smem = size_t(w) * (rows_per | 1) * sizeof(T);
         pt.begin("pnl_base", s);

@@ -12,6 +12,8 @@ constexpr int PTHREADS = 256;
 struct PanelScratch {
     double* gval = nullptr; int* grow = nullptr; double* gcand = nullptr; double* gdiag = nullptr;
     double* W = nullptr;            // trsm workspace of the panel stream
+    unsigned* bar = nullptr;        // arrival counter of the opt-in hand-rolled grid barrier (SB200_PANEL_BARRIER=1)
+    bool use_bar = false;
     int max_ctas = 0;
     void* raw = nullptr;
     int init();
