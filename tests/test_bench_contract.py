@@ -1,0 +1,65 @@
+"""CPU tests of the bench.py JSON contract: the committed bench lines (profiles/) carry every key the driver and the
+judge read, and the reference arm (`--impl reference`, the unmodified reference's HostTask path timed on host cores)
+prints a well-formed line here, without a GPU."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "clocks", "roofline", "e2e", "gpu_launches"]
+
+
+def _lines(pattern):
+    out = []
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", pattern))):
+        txt = [l for l in open(f).read().splitlines() if l.startswith("{")]
+        if txt:
+            out.append((os.path.basename(f), json.loads(txt[-1])))
+    return out
+
+
+@pytest.mark.parametrize("name,line", _lines("r01[c-e]_bench_*_1gpu.json") + _lines("r01e_bench_*_2gpu.json"),
+                         ids=lambda x: x if isinstance(x, str) else "")
+def test_committed_bench_lines_follow_the_contract(name, line):
+    for k in BASE_KEYS:
+        assert k in line, f"{name}: missing {k}"
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["value"] > 0 and line["ms_per_step"] > 0 and line["gpu_launches"] > 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"]))
+    r = line["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] in ("hbm", "tensor")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    if line["e2e"] is not None:                     # the tile-kernel line has no host-buffer variant
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] < line["value"] * 1.001 + 1e-9 \
+            or line["config"].get("routine") in ("posv_mixed", "gesv_mixed")
+    if line["n_gpus"] == 1 and line.get("cpu_baseline"):
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
+        assert line["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_default_line_is_the_baseline_config():
+    lines = dict(_lines("r01c_bench_potrf_1gpu.json"))
+    line = lines["r01c_bench_potrf_1gpu.json"]
+    assert line["metric"] == "dpotrf TFLOP/s" and line["dtype"] == "f64"
+    assert line["config"]["n"] == 32768 and line["config"]["nb"] == 512        # BASELINE.json configs[1]
+    assert line["cpu_baseline"]["kind"] == "reference"
+
+
+def test_reference_arm_prints_a_wellformed_line(ref_dump):
+    if ref_dump is None:
+        pytest.skip("oracle/_ref not built in this environment")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--ref-n", "1024",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "dpotrf TFLOP/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
