@@ -375,6 +375,9 @@ int sb200_gemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_ma
 int sb200_herk_mat_##X(R alpha, sb200_matrix_t A, R beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* A = L L^H, lower                             slate::potrf (src/potrf.cc:22-210) */ \
 int sb200_potrf_##X(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info); \
+/* the same, streaming every finished block column into the packed host buffer `htiles` (order and size of \
+ * sb200_matrix_to_host_local; pinned memory makes the copies overlap the factorisation) */ \
+int sb200_potrf_to_host_local_##X(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info, void* htiles); \
 /* B <- A^{-1} B from the Cholesky factor       slate::potrs (src/potrs.cc:54-77); 1 x 1 grid this round */ \
 int sb200_potrs_##X(sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
 /* C = alpha A X + beta C, A Hermitian lower, Side::Left   slate::hemm (src/hemmC.cc); 1 x 1 grid */ \

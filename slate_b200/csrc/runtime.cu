@@ -120,7 +120,7 @@ static int bcast_block_column(Grid& g, Matrix& A, int64_t k, int64_t i_first, co
 // (gemm_tc05.cu); the factored panel is split-packed once per step (A-side and B-side units).
 // ------------------------------------------------------------------------------------------
 template <typename T>
-int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05)
+int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out)
 {
     using R = typename RealOf<T>::type;
     Grid& g = *A.g;
@@ -207,6 +207,11 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05)
     Streams st;
     PhaseTimer ph;
     SB_TRY(st.init(size_t(2 * nt)));
+    // optional: every block column is copied to the caller's packed host buffer (pool order, as to_host_local) as soon
+    // as it is final (after P_done(k)), on a copy stream, overlapping the rest of the factorisation
+    cudaStream_t copy = nullptr;
+    struct CopyGuard { cudaStream_t& s; ~CopyGuard() { if (s) cudaStreamDestroy(s); } } copy_guard{copy};
+    if (host_out) CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
     double trail_flops = 0;
     int64_t trail_launches = 0;
     auto P_done = [&](int64_t k) { return st.ev[k]; };
@@ -306,6 +311,14 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05)
         }
         SB_TRY(st.ptime(P));
         CUDA_TRY(cudaEventRecord(P_done(k), P));
+        if (host_out && in_col) {
+            const int64_t jl = (k - g.pcol) / g.q;
+            const size_t o = size_t(A.col_start[jl]) * te * sizeof(T), bytes = size_t(A.col_start[jl + 1] - A.col_start[jl]) * te * sizeof(T);
+            CUDA_TRY(cudaStreamWaitEvent(copy, P_done(k), 0));
+            if (bytes)
+                CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(host_out) + o, reinterpret_cast<char*>(A.pool) + o, bytes,
+                                         cudaMemcpyDeviceToHost, copy));
+        }
         // -- trailing update of columns >= k+2
         CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
         if (! s.tr.empty()) {
@@ -323,6 +336,7 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05)
     CUDA_TRY(cudaMemcpyAsync(&hinfo, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st.panel));
     CUDA_TRY(cudaStreamSynchronize(st.panel));
     CUDA_TRY(cudaStreamSynchronize(st.trail));
+    if (copy) CUDA_TRY(cudaStreamSynchronize(copy));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, st.t0, st.t1));
     A.last_ms = ms;
@@ -525,7 +539,7 @@ int herk_driver(typename RealOf<T>::type alpha, Matrix& A, typename RealOf<T>::t
 }
 
 #define SB200_INST_DRIVERS(T) \
-    template int potrf_driver<T>(Matrix&, int64_t*, bool); \
+    template int potrf_driver<T>(Matrix&, int64_t*, bool, void*); \
     template int gemm_driver<T>(T, Matrix&, Matrix&, T, Matrix&); \
     template int herk_driver<T>(RealOf<T>::type, Matrix&, RealOf<T>::type, Matrix&);
 SB200_INST_DRIVERS(float)
@@ -783,7 +797,14 @@ int sb200_potrf_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info
 { \
     (void) opts;                       /* lookahead is fixed at 1 (the reference default) */ \
     if (! h) return SB200_EINVAL; \
-    return potrf_driver<CuT<T>::type>(h->A, info, false); \
+    return potrf_driver<CuT<T>::type>(h->A, info, false, nullptr); \
+} \
+/* potrf whose result streams to the packed host buffer (sb200_matrix_to_host_local order) while it factors */ \
+int sb200_potrf_to_host_local_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info, void* htiles) \
+{ \
+    (void) opts; \
+    if (! h || ! htiles) return SB200_EINVAL; \
+    return potrf_driver<CuT<T>::type>(h->A, info, false, htiles); \
 } \
 int sb200_gemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, \
                    const sb200_options_t* opts) \
@@ -806,7 +827,7 @@ int sb200_potrf_tc05_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* i
 {
     (void) opts;
     if (! h) return SB200_EINVAL;
-    return potrf_driver<float>(h->A, info, true);
+    return potrf_driver<float>(h->A, info, true, nullptr);
 }
 
 } // extern "C"

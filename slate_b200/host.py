@@ -64,6 +64,7 @@ _matrix_local_tiles = _sig("sb200_matrix_local_tiles", [c_ptr], c_i64)
 _last_ms = _sig("sb200_last_driver_ms", [c_ptr], c_dbl)
 _potrf = {t: _sig(f"sb200_potrf_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64)]) for t in "sdcz"}
 _potrf["s_tc05"] = _sig("sb200_potrf_tc05_s", [c_ptr, _OP, ctypes.POINTER(c_i64)])
+_potrf_to_host = {t: _sig(f"sb200_potrf_to_host_local_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64), c_ptr]) for t in "sdcz"}
 _gemm = {t: _sig(f"sb200_gemm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
 _herk = {t: _sig(f"sb200_herk_mat_{t}", [REAL_T[t], c_ptr, REAL_T[t], c_ptr, _OP]) for t in "sdcz"}
 _hemm = {t: _sig(f"sb200_hemm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
@@ -333,8 +334,10 @@ def norm_inf(A: Matrix) -> float:
     return float(v.value)
 
 
-def potrf(A: HermitianMatrix, opts: dict | None = None) -> int:
+def potrf(A: HermitianMatrix, opts: dict | None = None, out_local=None) -> int:
     """Cholesky A = L L^H, lower (slate::potrf, src/potrf.cc:262-281).
+    out_local (optional): packed host tile buffer as for Matrix.to_host_local; every finished block column is copied
+    into it while the factorisation runs (pinned memory: the D2H overlaps the trailing updates).
     Returns info: 0, or i > 0 if the leading minor of order i is not positive definite.
     opts['tensor_core_fp32'] (float matrices only): run the trailing update on the tcgen05
     FP32-emulated kernel, as posv_mixed does for its low-precision factorisation."""
@@ -345,6 +348,12 @@ def potrf(A: HermitianMatrix, opts: dict | None = None) -> int:
         if A.t != "s":
             raise Exception_("tensor_core_fp32 applies to float matrices")
         key = "s_tc05"
+    if out_local is not None:
+        if key == "s_tc05":
+            raise Exception_("out_local is not combined with tensor_core_fp32")
+        A._check_local(out_local)
+        check(_potrf_to_host[A.t](A._h, ctypes.byref(o), ctypes.byref(info), out_local.data_ptr()), "potrf")
+        return int(info.value)
     check(_potrf[key](A._h, ctypes.byref(o), ctypes.byref(info)), "potrf")
     return int(info.value)
 

@@ -65,3 +65,16 @@ def test_mixed_solvers_replicated_rhs_path(sl, monkeypatch, routine, n, nb):
     x = X.to_host()
     assert np.abs(x - xo).max() <= 1e-10 * np.abs(xo).max()
     assert o.solve_residual(o.he_full(a) if herm else a, x, b) <= 25 * EPS
+
+
+def test_potrf_streams_finished_columns_to_host(sl):
+    """potrf(out_local=...) (D2H of every block column as soon as it is final, overlapped with the trailing updates)
+    must deliver exactly what to_host_local delivers afterwards."""
+    import torch
+    n, nb = 2048, 256
+    A = sl.HermitianMatrix(n, nb).generate("rand_dominant", 42)
+    out = torch.empty(A.local_tiles * nb * nb, dtype=torch.float64).pin_memory()
+    ref = torch.empty_like(out)
+    assert sl.potrf(A, out_local=out) == 0
+    A.to_host_local(ref)
+    assert torch.equal(out, ref)
