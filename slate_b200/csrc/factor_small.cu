@@ -14,8 +14,13 @@
 #include "gemm_dmma.cuh"
 #include "scalar_ops.cuh"
 #include <cstdlib>
+#include <type_traits>
 
 namespace sb200 {
+
+// potrf_tile_fused.cu (opt-in one-launch tile Cholesky, SB200_TILE_FUSED); declared again in runtime_internal.hh
+constexpr int FUSED_NOT_TAKEN_ = -1000001;
+int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream);
 
 constexpr int IB = 64;
 template <typename T> constexpr size_t small_smem() { return 2 * IB * (IB + 1) * sizeof(T); }
@@ -550,6 +555,16 @@ template <typename T>
 int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cudaStream_t stream)
 {
     int st;
+    if constexpr (std::is_same<T, double>::value) {
+        // opt-in (round-2 candidate, not yet run): the whole tile in one launch (potrf_tile_fused.cu); read per call
+        // so that a test can switch it
+        const char* e = getenv("SB200_TILE_FUSED");
+        const int fused = e ? atoi(e) : 0;
+        if (fused > 0 && n > IB) {
+            st = potrf_tile_fused_d(n, A, lda, dinfo, info_base, fused, stream);
+            if (st != FUSED_NOT_TAKEN_) return st;
+        }
+    }
     small_kernels_init<T>();
     for (int jo = 0; jo < n; jo += IB) {
         const int jv = min(IB, n - jo);

@@ -1,0 +1,352 @@
+// potrf_tile_fused.cu -- the lower Cholesky of ONE diagonal tile (n <= 1024) in ONE launch.
+// OPT-IN (SB200_TILE_FUSED=1 | 2); round-2 candidate written after round 1's GPU budget was spent: compiled,
+// desk-checked, NOT yet run on a GPU.  The default path (potrf_tile_lower in factor_small.cu) is unchanged.
+//
+// Why (profiles/r01e_launches_potrf_n2048_per_grid.txt): the diagonal tile of every potrf
+// step (reference: internal::potrf<Devices> -> cusolverDn?potrf, src/internal/internal_potrf.cc:57-81) is
+// 8 x (64-block Cholesky kernel + 2 small GEMM launches) = 24 dependent launches, 1.3 ms uncontended and 1.9 ms
+// next to the trailing update; at 8 GPUs that chain (128 tiles at n = 65536) is longer than the trailing update.
+//
+// Design: one CTA per 64-row block, LEFT-looking, rows pipelined through release/acquire flags in global memory
+// (no grid barrier, no cooperative launch: a CTA only ever waits for CTAs with a smaller index):
+//   CTA r, for b = 0 .. r-1:   S = A(r,b) - sum_{c<b} L(r,c) L(b,c)^T     needs row b complete   (rowcnt[b] >= b)
+//                              L(r,b) = S inv(L(b,b))^T                    needs W_b = inv(L(b,b)) (diagf[b])
+//                              publish rowcnt[r] = b + 1
+//   then                       D = A(r,r) - sum_{c<r} L(r,c) L(r,c)^T ;  L(r,r) = chol(D) ;  W_r = inv(L(r,r)) ;
+//                              publish diagf[r]
+// The only work between "W_{r-1} published" and "W_r published" is one 64^3 product for L(r,r-1), one for its
+// contribution to D, the 64 x 64 Cholesky and the inverse: everything else of row r (S for b = r-1 and the part of D
+// that does not involve L(r,r-1)) is computed while CTA r-1 factors its diagonal block.
+// Products run on the FP64 tensor-core MMA (DMMA.8x8x4, fragment conventions of gemm_dmma.cuh), operands staged
+// through padded shared memory; the 64 x 64 Cholesky + inverse are the register kernels of factor_small.cu
+// (one row / one column per thread) on two warps with a named barrier.
+// Failure (block not positive definite): info = info_base + column + 1 as the default path; the failing CTA
+// publishes FAILED on its flags and every later CTA leaves on seeing it.
+#include "common.cuh"
+#include "runtime_internal.hh"
+#include <cstdlib>
+
+namespace sb200 {
+
+namespace {
+
+constexpr int FB = 64;              // block size (== IB of factor_small.cu)
+constexpr int FLD = FB + 4;         // padded shared leading dimension: conflict-free DMMA fragment loads
+constexpr int FT = 128;             // threads per CTA: 4 warps, 2 x 2 warp tiles of 32 x 32.  128 x <= 255 registers and
+                                    // 104 KB of shared memory leave room for ONE trailing-update CTA on the same SM, so a
+                                    // tile CTA needs a single CTA slot to free up, not a whole SM
+constexpr int FNJ = 4;              // 8-column DMMA blocks per warp tile
+constexpr int FMAXB = 16;           // at most 16 row blocks (n <= 1024)
+constexpr unsigned F_FAILED = 0x40000000u;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// barrier among the first 64 threads (warps 0 and 1) only
+__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+// all FT threads: wait until *p >= target (FAILED is larger than any target); returns the value seen
+__device__ __forceinline__ unsigned wait_flag(const unsigned* p, unsigned target, unsigned* s_v)
+{
+    if (threadIdx.x == 0) {
+        unsigned v;
+        while ((v = ld_acquire_u32(p)) < target) __nanosleep(40);
+        *s_v = v;
+    }
+    __syncthreads();
+    const unsigned v = *s_v;
+    __syncthreads();
+    return v;
+}
+
+// dst[k * FLD + i] = src[i + k * lds] for i < rv (rows beyond rv are zero-filled), 64 x 64, L2 loads
+__device__ __forceinline__ void load_block(double* __restrict__ dst, const double* src, int lds, int rv)
+{
+    const int i = threadIdx.x & (FB - 1), k0 = threadIdx.x >> 6;          // k0 in {0, 1}
+    #pragma unroll
+    for (int half = 0; half < 2; ++half) {                                 // 2 x 16 loads in flight per thread
+        double v[FB / 4];
+        #pragma unroll
+        for (int t = 0; t < FB / 4; ++t) {
+            const int k = k0 + 2 * (half * (FB / 4) + t);
+            v[t] = (i < rv) ? __ldcg(src + i + int64_t(k) * lds) : 0.0;
+        }
+        #pragma unroll
+        for (int t = 0; t < FB / 4; ++t) dst[(k0 + 2 * (half * (FB / 4) + t)) * FLD + i] = v[t];
+    }
+}
+
+// acc(row, col) += sum_k X(row, k) Y(col, k) over one 64 x 64 x 64 block; Xs[k * FLD + row], Ys[k * FLD + col]
+__device__ __forceinline__ void mma_block(double (&acc)[4][FNJ][2], const double* __restrict__ Xs, const double* __restrict__ Ys,
+                                          int wm, int wn, int lr, int lc)
+{
+    const double* cA = Xs + lc * FLD + wm + lr;
+    const double* cB = Ys + lc * FLD + wn + lr;
+    #pragma unroll 4
+    for (int k4 = 0; k4 < FB / 4; ++k4) {
+        double a[4], b[FNJ];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = cA[k4 * 4 * FLD + i * 8];
+        #pragma unroll
+        for (int j = 0; j < FNJ; ++j) b[j] = cB[k4 * 4 * FLD + j * 8];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+            #pragma unroll
+            for (int j = 0; j < FNJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
+__device__ __forceinline__ void zero_acc(double (&acc)[4][FNJ][2])
+{
+    #pragma unroll
+    for (int i = 0; i < 4; ++i)
+        #pragma unroll
+        for (int j = 0; j < FNJ; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+}
+
+// X = inv(L), thread j owns column j (same arithmetic as inv_lower_column of factor_small.cu)
+__device__ __forceinline__ void inv_column64(const double* __restrict__ Ls, const double* __restrict__ rd, int j, double (&x)[FB])
+{
+    #pragma unroll
+    for (int k = 0; k < FB; ++k) x[k] = (k == j) ? 1.0 : 0.0;
+    #pragma unroll
+    for (int i = 0; i < FB; ++i) {
+        x[i] *= rd[i];
+        const double xi = x[i];
+        #pragma unroll
+        for (int k = i + 1; k < FB; ++k) x[k] = fma(-Ls[i * FB + k], xi, x[k]);
+    }
+}
+
+template <bool RSQ>
+__global__ void __launch_bounds__(FT, 1)
+potrf_tile_fused_kernel(double* __restrict__ A, int lda, int n, int* __restrict__ info, int info_base,
+                        double* __restrict__ Wg, unsigned* __restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    double* Xs = reinterpret_cast<double*>(smem_dyn);      // operand X / Cholesky columns + staging
+    double* Ys = Xs + FB * FLD;                            // operand Y / W_b
+    double* Cs = Ys + FB * FLD;                            // S (operand of the solve) / D (input of the Cholesky)
+    __shared__ unsigned s_v;
+    __shared__ int s_fail;
+    unsigned* rowcnt = flags;                              // rowcnt[r] = number of final blocks L(r, 0 .. cnt-1)
+    unsigned* diagf = flags + FMAXB;                       // diagf[r]  = 1 once L(r,r) and W_r are final
+
+    const int r = blockIdx.x, nblk = gridDim.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lc = lane & 3;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+    const int rv = min(FB, n - r * FB);                    // valid rows (= columns of the diagonal block) of this row block
+    double* Arow = A + r * FB;                             // row block r, column 0
+
+    if (*reinterpret_cast<volatile int*>(info) != 0) {     // an earlier tile / block already failed: leave the tile alone
+        if (tid == 0) { st_release_u32(&rowcnt[r], F_FAILED); st_release_u32(&diagf[r], F_FAILED); }
+        return;
+    }
+    if (tid == 0) s_fail = 0;
+
+    double acc[4][FNJ][2], accD[4][FNJ][2];
+    zero_acc(accD);
+
+    for (int b = 0; b < r; ++b) {
+        // ---- S = A(r,b) - sum_{c<b} L(r,c) L(b,c)^T
+        if (b > 0) {
+            const unsigned v = wait_flag(&rowcnt[b], unsigned(b), &s_v);
+            if (v & F_FAILED) { if (tid == 0) { st_release_u32(&rowcnt[r], F_FAILED); st_release_u32(&diagf[r], F_FAILED); } return; }
+        }
+        zero_acc(acc);
+        for (int c = 0; c < b; ++c) {
+            load_block(Xs, Arow + int64_t(c) * FB * lda, lda, rv);                 // L(r,c): written by this CTA
+            load_block(Ys, A + b * FB + int64_t(c) * FB * lda, lda, FB);           // L(b,c): final (rowcnt[b] >= b)
+            __syncthreads();
+            mma_block(acc, Xs, Ys, wm, wn, lr, lc);
+            __syncthreads();
+        }
+        const double* Ab0 = Arow + int64_t(b) * FB * lda;                         // A(r,b) as given
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+            #pragma unroll
+            for (int j = 0; j < FNJ; ++j)
+                #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row = wm + i * 8 + lr, col = wn + j * 8 + 2 * lc + h;
+                    const double o = (row < rv) ? __ldcg(Ab0 + row + int64_t(col) * lda) : 0.0;
+                    Cs[col * FLD + row] = o - acc[i][j][h];                       // rows >= rv: 0 - 0
+                }
+        if (b == r - 1) {
+            // the part of D that does not need L(r,r-1), while CTA r-1 is still factoring its diagonal block
+            for (int c = 0; c < b; ++c) {
+                load_block(Xs, Arow + int64_t(c) * FB * lda, lda, rv);
+                __syncthreads();
+                mma_block(accD, Xs, Xs, wm, wn, lr, lc);
+                __syncthreads();
+            }
+        }
+        // ---- L(r,b) = S W_b^T
+        {
+            const unsigned v = wait_flag(&diagf[b], 1u, &s_v);
+            if (v & F_FAILED) { if (tid == 0) { st_release_u32(&rowcnt[r], F_FAILED); st_release_u32(&diagf[r], F_FAILED); } return; }
+        }
+        load_block(Ys, Wg + int64_t(b) * FB * FB, FB, FB);
+        __syncthreads();                                                           // Cs and Ys complete
+        zero_acc(acc);
+        mma_block(acc, Cs, Ys, wm, wn, lr, lc);
+        {
+            double* Ab = Arow + int64_t(b) * FB * lda;
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+                #pragma unroll
+                for (int j = 0; j < FNJ; ++j)
+                    #pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int row = wm + i * 8 + lr, col = wn + j * 8 + 2 * lc + h;
+                        if (row < rv) Ab[row + int64_t(col) * lda] = acc[i][j][h];
+                        if (b == r - 1) Xs[col * FLD + row] = acc[i][j][h];        // operand of the last update of D
+                    }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_u32(&rowcnt[r], unsigned(b + 1));
+        if (b == r - 1) mma_block(accD, Xs, Xs, wm, wn, lr, lc);
+    }
+
+    // ---- D = A(r,r) - sum_c L(r,c) L(r,c)^T, identity-padded to 64 x 64 (only the lower triangle is used)
+    {
+        const double* Ad = Arow + int64_t(r) * FB * lda;
+        __syncthreads();                                   // everybody is done with Xs as an operand; Cs free
+        #pragma unroll
+        for (int i = 0; i < 4; ++i)
+            #pragma unroll
+            for (int j = 0; j < FNJ; ++j)
+                #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row = wm + i * 8 + lr, col = wn + j * 8 + 2 * lc + h;
+                    double v;
+                    if (row < rv && col < rv) v = (col <= row) ? __ldcg(Ad + row + int64_t(col) * lda) - accD[i][j][h] : 0.0;
+                    else                      v = (row == col) ? 1.0 : 0.0;
+                    Cs[col * FLD + row] = v;
+                }
+        __syncthreads();
+    }
+
+    // ---- 64 x 64 Cholesky + inverse on warps 0 and 1 (thread = row / column); the other warps wait below
+    if (tid < FB) {
+        double* Ls = Xs;                                   // [FB * (FB + 1)] columns (stride FB), later padded staging
+        double* rd = Ls + FB * (FB + 1);                   // [FB] reciprocal diagonal      (FB*(FB+1) + FB <= FB*FLD)
+        const int i = tid;
+        double a[FB];
+        #pragma unroll
+        for (int c = 0; c < FB; ++c) a[c] = Cs[c * FLD + i];
+        int fail = 0;
+        double rdiag = 1.0;
+        #pragma unroll
+        for (int j = 0; j < FB; ++j) {
+            Ls[j * FB + i] = a[j];
+            bar64();
+            const double d = Ls[j * FB + j];
+            if (fail == 0 && !(d > 0.0)) fail = j + 1;     // also catches NaN; uniform over the 64 threads
+            if constexpr (RSQ) {
+                const double rinv = rsqrt(d);
+                const double w = a[j] * (rinv * rinv);
+                #pragma unroll
+                for (int c = j + 1; c < FB; ++c) a[c] = fma(-w, Ls[j * FB + c], a[c]);
+                a[j] = (i == j) ? d * rinv : a[j] * rinv;
+                if (i == j) rdiag = rinv;
+            }
+            else {
+                const double w = a[j] / d;
+                #pragma unroll
+                for (int c = j + 1; c < FB; ++c) a[c] = fma(-w, Ls[j * FB + c], a[c]);
+                const double rt = sqrt(d);
+                a[j] = (i == j) ? rt : a[j] / rt;
+                if (i == j) rdiag = 1.0 / rt;
+            }
+        }
+        if (fail) {
+            if (i == 0) {
+                if (*reinterpret_cast<volatile int*>(info) == 0) *info = info_base + r * FB + fail;
+                s_fail = fail;
+            }
+        }
+        else {
+            double* Ad = Arow + int64_t(r) * FB * lda;
+            #pragma unroll
+            for (int c = 0; c < FB; ++c)
+                if (c <= i && i < rv) Ad[i + int64_t(c) * lda] = a[c];
+            if (r + 1 < nblk) {                            // W_r is only needed by the rows below
+                bar64();
+                #pragma unroll
+                for (int c = 0; c < FB; ++c) Ls[c * FB + i] = a[c];
+                rd[i] = rdiag;
+                bar64();
+                double x[FB];
+                inv_column64(Ls, rd, i, x);
+                bar64();                                   // everybody is done reading Ls (aliased by the staging)
+                #pragma unroll
+                for (int q = 0; q < FB; ++q) Ls[q * (FB + 1) + i] = x[q];          // staging[q][column i]
+                bar64();
+                double* W = Wg + int64_t(r) * FB * FB;
+                #pragma unroll 8
+                for (int j = 0; j < FB; ++j) W[i + j * FB] = Ls[i * (FB + 1) + j]; // W(i, j), coalesced over i
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned f = s_fail ? F_FAILED : 1u;
+        if (s_fail) st_release_u32(&rowcnt[r], F_FAILED);
+        st_release_u32(&diagf[r], f);
+    }
+}
+
+constexpr size_t fused_smem() { return size_t(3) * FB * FLD * sizeof(double); }
+
+} // namespace
+
+// returns FUSED_NOT_TAKEN when the variant does not apply (the caller then runs the default path)
+int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream)
+{
+    const int nblk = int(ceil_div(n, FB));
+    if (nblk < 2 || nblk > FMAXB) return FUSED_NOT_TAKEN;
+    static thread_local bool attr_done[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (! attr_done[dev & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(potrf_tile_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem())));
+        CUDA_TRY(cudaFuncSetAttribute(potrf_tile_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem())));
+        // keep freed stream-ordered allocations in the pool (the workspace below is allocated per launch)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        attr_done[dev & 63] = true;
+    }
+    // stream-ordered workspace: the inverted diagonal blocks W_0 .. W_{nblk-2} and the flags
+    const size_t wbytes = size_t(nblk) * FB * FB * sizeof(double);
+    void* ws = nullptr;
+    CUDA_TRY(cudaMallocAsync(&ws, wbytes + 2 * FMAXB * sizeof(unsigned), stream));
+    unsigned* flags = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + wbytes);
+    cudaError_t e = cudaMemsetAsync(flags, 0, 2 * FMAXB * sizeof(unsigned), stream);
+    int st = (e == cudaSuccess) ? SB200_OK : int(e);
+    if (st == SB200_OK) {
+        if (variant == 2)
+            potrf_tile_fused_kernel<true><<<nblk, FT, fused_smem(), stream>>>(A, lda, n, dinfo, info_base, static_cast<double*>(ws), flags);
+        else
+            potrf_tile_fused_kernel<false><<<nblk, FT, fused_smem(), stream>>>(A, lda, n, dinfo, info_base, static_cast<double*>(ws), flags);
+        st = launch_status();
+    }
+    cudaFreeAsync(ws, stream);
+    return st;
+}
+
+} // namespace sb200

@@ -32,6 +32,10 @@ template <typename T>
 int trsm_small(bool lower, int op, int na, int n, const T* Tm, int ldt, const T* Winv, T* const* dB, int64_t offB,
                int ldb, int batch, cudaStream_t stream);
 constexpr int FACTOR_IB = 64;          // diagonal block of the tile factor / solve kernels
+// opt-in one-launch tile Cholesky (potrf_tile_fused.cu; SB200_TILE_FUSED=1: divided form, 2: rsqrt form);
+// returns FUSED_NOT_TAKEN when it does not apply
+constexpr int FUSED_NOT_TAKEN = -1000001;
+int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream);
 // skinny right operand (n <= 16): HBM-bound streaming kernel instead of a tensor-core tile kernel (gemm_skinny.cu)
 template <typename T> bool gemm_skinny_applies(int opB, const GemmParamsT<T>& p);
 template <typename T> int launch_gemm_skinny(int opA, const GemmParamsT<T>& p, cudaStream_t stream);
