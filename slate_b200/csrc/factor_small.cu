@@ -21,6 +21,12 @@ namespace sb200 {
 // potrf_tile_fused.cu (opt-in one-launch tile Cholesky, SB200_TILE_FUSED); declared again in runtime_internal.hh
 constexpr int FUSED_NOT_TAKEN_ = -1000001;
 int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream);
+int potrf_tile_fused_s(int n, float* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream);
+// opt-in one-launch panel solve B <- alpha B L^{-T} (SB200_TRSM_FUSED=1), W = inverted diagonal blocks
+int trsm_rlt_fused_d(int m, int na, double alpha, const double* Tm, int ldt, const double* W, double* const* dB,
+                     int64_t offB, int ldb, int batch, cudaStream_t stream);
+int trsm_rlt_fused_s(int m, int na, float alpha, const float* Tm, int ldt, const float* W, float* const* dB,
+                     int64_t offB, int ldb, int batch, cudaStream_t stream);
 
 constexpr int IB = 64;
 template <typename T> constexpr size_t small_smem() { return 2 * IB * (IB + 1) * sizeof(T); }
@@ -497,6 +503,15 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
     small_kernels_init<T>();
     int st = launch_trtri_diag<T>(nblk, Tm, ldt, na, lower ? 1 : 0, unit ? 1 : 0, W, stream);
     if (st) return st;
+    if constexpr (IsRealType<T>::value) {
+        // opt-in (round-2 candidate, not yet run): the Cholesky panel solve (Right, Lower, Trans, NonUnit) in one
+        // launch after the inverses (potrf_tile_fused.cu); read per call so that a test can switch it
+        const char* e = getenv("SB200_TRSM_FUSED");
+        if (e && atoi(e) != 0 && ! left && lower && op != 'N' && ! unit && na > IB) {
+            if constexpr (std::is_same<T, double>::value) return trsm_rlt_fused_d(m, na, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
+            else                                          return trsm_rlt_fused_s(m, na, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
+        }
+    }
     const bool trans = (op != 'N');
     const bool eff_lower = (lower != trans);        // op(T) as a math matrix
     const int opT = trans ? op : 'N';          // 'C' conjugates (complex)
@@ -555,13 +570,14 @@ template <typename T>
 int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cudaStream_t stream)
 {
     int st;
-    if constexpr (std::is_same<T, double>::value) {
+    if constexpr (IsRealType<T>::value) {
         // opt-in (round-2 candidate, not yet run): the whole tile in one launch (potrf_tile_fused.cu); read per call
         // so that a test can switch it
         const char* e = getenv("SB200_TILE_FUSED");
         const int fused = e ? atoi(e) : 0;
         if (fused > 0 && n > IB) {
-            st = potrf_tile_fused_d(n, A, lda, dinfo, info_base, fused, stream);
+            if constexpr (std::is_same<T, double>::value) st = potrf_tile_fused_d(n, A, lda, dinfo, info_base, fused, stream);
+            else                                          st = potrf_tile_fused_s(n, A, lda, dinfo, info_base, fused, stream);
             if (st != FUSED_NOT_TAKEN_) return st;
         }
     }

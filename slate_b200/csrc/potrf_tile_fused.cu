@@ -17,7 +17,8 @@
 // The only work between "W_{r-1} published" and "W_r published" is one 64^3 product for L(r,r-1), one for its
 // contribution to D, the 64 x 64 Cholesky and the inverse: everything else of row r (S for b = r-1 and the part of D
 // that does not involve L(r,r-1)) is computed while CTA r-1 factors its diagonal block.
-// Products run on the FP64 tensor-core MMA (DMMA.8x8x4, fragment conventions of gemm_dmma.cuh), operands staged
+// FP64 products run on the FP64 tensor-core MMA (DMMA.8x8x4, fragment conventions of gemm_dmma.cuh), FP32 products
+// (the FP32 factorisation of posv_mixed) on FP32 FMAs with a 4 x 8 register tile per thread; operands are staged
 // through padded shared memory; the 64 x 64 Cholesky + inverse are the register kernels of factor_small.cu
 // (one row / one column per thread) on two warps with a named barrier.
 // Failure (block not positive definite): info = info_base + column + 1 as the default path; the failing CTA
@@ -32,10 +33,9 @@ namespace {
 
 constexpr int FB = 64;              // block size (== IB of factor_small.cu)
 constexpr int FLD = FB + 4;         // padded shared leading dimension: conflict-free DMMA fragment loads
-constexpr int FT = 128;             // threads per CTA: 4 warps, 2 x 2 warp tiles of 32 x 32.  128 x <= 255 registers and
+constexpr int FT = 128;             // threads per CTA (4 warps).  128 x <= 255 registers and
                                     // 104 KB of shared memory leave room for ONE trailing-update CTA on the same SM, so a
                                     // tile CTA needs a single CTA slot to free up, not a whole SM
-constexpr int FNJ = 4;              // 8-column DMMA blocks per warp tile
 constexpr int FMAXB = 16;           // at most 16 row blocks (n <= 1024)
 constexpr unsigned F_FAILED = 0x40000000u;
 
@@ -67,84 +67,125 @@ __device__ __forceinline__ unsigned wait_flag(const unsigned* p, unsigned target
 }
 
 // dst[k * FLD + i] = src[i + k * lds] for i < rv (rows beyond rv are zero-filled), 64 x 64, L2 loads
-__device__ __forceinline__ void load_block(double* __restrict__ dst, const double* src, int lds, int rv)
+template <typename R>
+__device__ __forceinline__ void load_block(R* __restrict__ dst, const R* src, int lds, int rv)
 {
     const int i = threadIdx.x & (FB - 1), k0 = threadIdx.x >> 6;          // k0 in {0, 1}
     #pragma unroll
     for (int half = 0; half < 2; ++half) {                                 // 2 x 16 loads in flight per thread
-        double v[FB / 4];
+        R v[FB / 4];
         #pragma unroll
         for (int t = 0; t < FB / 4; ++t) {
             const int k = k0 + 2 * (half * (FB / 4) + t);
-            v[t] = (i < rv) ? __ldcg(src + i + int64_t(k) * lds) : 0.0;
+            v[t] = (i < rv) ? __ldcg(src + i + int64_t(k) * lds) : R(0);
         }
         #pragma unroll
         for (int t = 0; t < FB / 4; ++t) dst[(k0 + 2 * (half * (FB / 4) + t)) * FLD + i] = v[t];
     }
 }
 
-// acc(row, col) += sum_k X(row, k) Y(col, k) over one 64 x 64 x 64 block; Xs[k * FLD + row], Ys[k * FLD + col]
-__device__ __forceinline__ void mma_block(double (&acc)[4][FNJ][2], const double* __restrict__ Xs, const double* __restrict__ Ys,
-                                          int wm, int wn, int lr, int lc)
-{
-    const double* cA = Xs + lc * FLD + wm + lr;
-    const double* cB = Ys + lc * FLD + wn + lr;
-    #pragma unroll 4
-    for (int k4 = 0; k4 < FB / 4; ++k4) {
-        double a[4], b[FNJ];
-        #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = cA[k4 * 4 * FLD + i * 8];
-        #pragma unroll
-        for (int j = 0; j < FNJ; ++j) b[j] = cB[k4 * 4 * FLD + j * 8];
-        #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            #pragma unroll
-            for (int j = 0; j < FNJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-}
+// The 64 x 64 x 64 product micro-kernel of a 128-thread CTA: acc(row, col) += sum_k X(row, k) Y(col, k) with
+// Xs[k * FLD + row], Ys[k * FLD + col]; 32 accumulators per thread, element e of thread `tid` is (row(e), col(e)).
+template <typename R> struct Prod;
 
-__device__ __forceinline__ void zero_acc(double (&acc)[4][FNJ][2])
+template <> struct Prod<double> {          // DMMA.8x8x4: 4 warps, 2 x 2 warp tiles of 32 x 32 (4 x 4 MMA tiles)
+    int wm, wn, lr, lc;
+    __device__ __forceinline__ explicit Prod(int tid)
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        lr = lane >> 2; lc = lane & 3; wm = (warp & 1) * 32; wn = (warp >> 1) * 32;
+    }
+    // e = (i * 4 + j) * 2 + h
+    __device__ __forceinline__ int row(int e) const { return wm + (e >> 3) * 8 + lr; }
+    __device__ __forceinline__ int col(int e) const { return wn + ((e >> 1) & 3) * 8 + 2 * lc + (e & 1); }
+    __device__ __forceinline__ void mma(double (&acc)[32], const double* __restrict__ Xs, const double* __restrict__ Ys) const
+    {
+        const double* cA = Xs + lc * FLD + wm + lr;
+        const double* cB = Ys + lc * FLD + wn + lr;
+        #pragma unroll 4
+        for (int k4 = 0; k4 < FB / 4; ++k4) {
+            double a[4], b[4];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = cA[k4 * 4 * FLD + i * 8];
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = cB[k4 * 4 * FLD + j * 8];
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[(i * 4 + j) * 2], acc[(i * 4 + j) * 2 + 1], a[i], b[j]);
+        }
+    }
+};
+
+template <> struct Prod<float> {           // FP32 FMA: thread (tx, ty) of 16 x 8 owns rows 4 tx .. +3, columns 8 ty .. +7
+    int tx, ty;
+    __device__ __forceinline__ explicit Prod(int tid) { tx = tid & 15; ty = tid >> 4; }
+    // e = i * 8 + j
+    __device__ __forceinline__ int row(int e) const { return tx * 4 + (e >> 3); }
+    __device__ __forceinline__ int col(int e) const { return ty * 8 + (e & 7); }
+    __device__ __forceinline__ void mma(float (&acc)[32], const float* __restrict__ Xs, const float* __restrict__ Ys) const
+    {
+        const float* cA = Xs + tx * 4;
+        const float* cB = Ys + ty * 8;
+        #pragma unroll 8
+        for (int k = 0; k < FB; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(cA + k * FLD);
+            const float4 b0 = *reinterpret_cast<const float4*>(cB + k * FLD);
+            const float4 b1 = *reinterpret_cast<const float4*>(cB + k * FLD + 4);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            #pragma unroll
+            for (int i = 0; i < 4; ++i)
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fmaf(a[i], b[j], acc[i * 8 + j]);
+        }
+    }
+};
+
+template <typename R>
+__device__ __forceinline__ void zero_acc(R (&acc)[32])
 {
     #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        #pragma unroll
-        for (int j = 0; j < FNJ; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int e = 0; e < 32; ++e) acc[e] = R(0);
 }
+
+__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
+__device__ __forceinline__ float  rsqrt_t(float x)  { return rsqrtf(x); }
 
 // X = inv(L), thread j owns column j (same arithmetic as inv_lower_column of factor_small.cu)
-__device__ __forceinline__ void inv_column64(const double* __restrict__ Ls, const double* __restrict__ rd, int j, double (&x)[FB])
+template <typename R>
+__device__ __forceinline__ void inv_column64(const R* __restrict__ Ls, const R* __restrict__ rd, int j, R (&x)[FB])
 {
     #pragma unroll
-    for (int k = 0; k < FB; ++k) x[k] = (k == j) ? 1.0 : 0.0;
+    for (int k = 0; k < FB; ++k) x[k] = (k == j) ? R(1) : R(0);
     #pragma unroll
     for (int i = 0; i < FB; ++i) {
         x[i] *= rd[i];
-        const double xi = x[i];
+        const R xi = x[i];
         #pragma unroll
         for (int k = i + 1; k < FB; ++k) x[k] = fma(-Ls[i * FB + k], xi, x[k]);
     }
 }
 
-template <bool RSQ>
+template <typename R, bool RSQ>
 __global__ void __launch_bounds__(FT, 1)
-potrf_tile_fused_kernel(double* __restrict__ A, int lda, int n, int* __restrict__ info, int info_base,
-                        double* __restrict__ Wg, unsigned* __restrict__ flags)
+potrf_tile_fused_kernel(R* __restrict__ A, int lda, int n, int* __restrict__ info, int info_base,
+                        R* __restrict__ Wg, unsigned* __restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    double* Xs = reinterpret_cast<double*>(smem_dyn);      // operand X / Cholesky columns + staging
-    double* Ys = Xs + FB * FLD;                            // operand Y / W_b
-    double* Cs = Ys + FB * FLD;                            // S (operand of the solve) / D (input of the Cholesky)
+    R* Xs = reinterpret_cast<R*>(smem_dyn);                // operand X / Cholesky columns + staging
+    R* Ys = Xs + FB * FLD;                                 // operand Y / W_b
+    R* Cs = Ys + FB * FLD;                                 // S (operand of the solve) / D (input of the Cholesky)
     __shared__ unsigned s_v;
     __shared__ int s_fail;
     unsigned* rowcnt = flags;                              // rowcnt[r] = number of final blocks L(r, 0 .. cnt-1)
     unsigned* diagf = flags + FMAXB;                       // diagf[r]  = 1 once L(r,r) and W_r are final
 
     const int r = blockIdx.x, nblk = gridDim.x;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int lr = lane >> 2, lc = lane & 3;
-    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+    const int tid = threadIdx.x;
+    const Prod<R> pr(tid);
     const int rv = min(FB, n - r * FB);                    // valid rows (= columns of the diagonal block) of this row block
-    double* Arow = A + r * FB;                             // row block r, column 0
+    R* Arow = A + r * FB;                                  // row block r, column 0
 
     if (*reinterpret_cast<volatile int*>(info) != 0) {     // an earlier tile / block already failed: leave the tile alone
         if (tid == 0) { st_release_u32(&rowcnt[r], F_FAILED); st_release_u32(&diagf[r], F_FAILED); }
@@ -152,7 +193,7 @@ potrf_tile_fused_kernel(double* __restrict__ A, int lda, int n, int* __restrict_
     }
     if (tid == 0) s_fail = 0;
 
-    double acc[4][FNJ][2], accD[4][FNJ][2];
+    R acc[32], accD[32];
     zero_acc(accD);
 
     for (int b = 0; b < r; ++b) {
@@ -163,29 +204,25 @@ potrf_tile_fused_kernel(double* __restrict__ A, int lda, int n, int* __restrict_
         }
         zero_acc(acc);
         for (int c = 0; c < b; ++c) {
-            load_block(Xs, Arow + int64_t(c) * FB * lda, lda, rv);                 // L(r,c): written by this CTA
-            load_block(Ys, A + b * FB + int64_t(c) * FB * lda, lda, FB);           // L(b,c): final (rowcnt[b] >= b)
+            load_block<R>(Xs, Arow + int64_t(c) * FB * lda, lda, rv);              // L(r,c): written by this CTA
+            load_block<R>(Ys, A + b * FB + int64_t(c) * FB * lda, lda, FB);        // L(b,c): final (rowcnt[b] >= b)
             __syncthreads();
-            mma_block(acc, Xs, Ys, wm, wn, lr, lc);
+            pr.mma(acc, Xs, Ys);
             __syncthreads();
         }
-        const double* Ab0 = Arow + int64_t(b) * FB * lda;                         // A(r,b) as given
+        R* Ab = Arow + int64_t(b) * FB * lda;                                     // A(r,b) as given, L(r,b) on return
         #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            #pragma unroll
-            for (int j = 0; j < FNJ; ++j)
-                #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int row = wm + i * 8 + lr, col = wn + j * 8 + 2 * lc + h;
-                    const double o = (row < rv) ? __ldcg(Ab0 + row + int64_t(col) * lda) : 0.0;
-                    Cs[col * FLD + row] = o - acc[i][j][h];                       // rows >= rv: 0 - 0
-                }
+        for (int e = 0; e < 32; ++e) {
+            const int row = pr.row(e), col = pr.col(e);
+            const R o = (row < rv) ? __ldcg(Ab + row + int64_t(col) * lda) : R(0);
+            Cs[col * FLD + row] = o - acc[e];                                     // rows >= rv: 0 - 0
+        }
         if (b == r - 1) {
             // the part of D that does not need L(r,r-1), while CTA r-1 is still factoring its diagonal block
             for (int c = 0; c < b; ++c) {
-                load_block(Xs, Arow + int64_t(c) * FB * lda, lda, rv);
+                load_block<R>(Xs, Arow + int64_t(c) * FB * lda, lda, rv);
                 __syncthreads();
-                mma_block(accD, Xs, Xs, wm, wn, lr, lc);
+                pr.mma(accD, Xs, Xs);
                 __syncthreads();
             }
         }
@@ -194,79 +231,68 @@ potrf_tile_fused_kernel(double* __restrict__ A, int lda, int n, int* __restrict_
             const unsigned v = wait_flag(&diagf[b], 1u, &s_v);
             if (v & F_FAILED) { if (tid == 0) { st_release_u32(&rowcnt[r], F_FAILED); st_release_u32(&diagf[r], F_FAILED); } return; }
         }
-        load_block(Ys, Wg + int64_t(b) * FB * FB, FB, FB);
+        load_block<R>(Ys, Wg + int64_t(b) * FB * FB, FB, FB);
         __syncthreads();                                                           // Cs and Ys complete
         zero_acc(acc);
-        mma_block(acc, Cs, Ys, wm, wn, lr, lc);
-        {
-            double* Ab = Arow + int64_t(b) * FB * lda;
-            #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                #pragma unroll
-                for (int j = 0; j < FNJ; ++j)
-                    #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int row = wm + i * 8 + lr, col = wn + j * 8 + 2 * lc + h;
-                        if (row < rv) Ab[row + int64_t(col) * lda] = acc[i][j][h];
-                        if (b == r - 1) Xs[col * FLD + row] = acc[i][j][h];        // operand of the last update of D
-                    }
+        pr.mma(acc, Cs, Ys);
+        #pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int row = pr.row(e), col = pr.col(e);
+            if (row < rv) Ab[row + int64_t(col) * lda] = acc[e];
+            if (b == r - 1) Xs[col * FLD + row] = acc[e];                          // operand of the last update of D
         }
         __threadfence();
         __syncthreads();
         if (tid == 0) st_release_u32(&rowcnt[r], unsigned(b + 1));
-        if (b == r - 1) mma_block(accD, Xs, Xs, wm, wn, lr, lc);
+        if (b == r - 1) pr.mma(accD, Xs, Xs);
     }
 
     // ---- D = A(r,r) - sum_c L(r,c) L(r,c)^T, identity-padded to 64 x 64 (only the lower triangle is used)
     {
-        const double* Ad = Arow + int64_t(r) * FB * lda;
+        const R* Ad = Arow + int64_t(r) * FB * lda;
         __syncthreads();                                   // everybody is done with Xs as an operand; Cs free
         #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            #pragma unroll
-            for (int j = 0; j < FNJ; ++j)
-                #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int row = wm + i * 8 + lr, col = wn + j * 8 + 2 * lc + h;
-                    double v;
-                    if (row < rv && col < rv) v = (col <= row) ? __ldcg(Ad + row + int64_t(col) * lda) - accD[i][j][h] : 0.0;
-                    else                      v = (row == col) ? 1.0 : 0.0;
-                    Cs[col * FLD + row] = v;
-                }
+        for (int e = 0; e < 32; ++e) {
+            const int row = pr.row(e), col = pr.col(e);
+            R v;
+            if (row < rv && col < rv) v = (col <= row) ? __ldcg(Ad + row + int64_t(col) * lda) - accD[e] : R(0);
+            else                      v = (row == col) ? R(1) : R(0);
+            Cs[col * FLD + row] = v;
+        }
         __syncthreads();
     }
 
     // ---- 64 x 64 Cholesky + inverse on warps 0 and 1 (thread = row / column); the other warps wait below
     if (tid < FB) {
-        double* Ls = Xs;                                   // [FB * (FB + 1)] columns (stride FB), later padded staging
-        double* rd = Ls + FB * (FB + 1);                   // [FB] reciprocal diagonal      (FB*(FB+1) + FB <= FB*FLD)
+        R* Ls = Xs;                                        // [FB * (FB + 1)] columns (stride FB), later padded staging
+        R* rd = Ls + FB * (FB + 1);                        // [FB] reciprocal diagonal      (FB*(FB+1) + FB <= FB*FLD)
         const int i = tid;
-        double a[FB];
+        R a[FB];
         #pragma unroll
         for (int c = 0; c < FB; ++c) a[c] = Cs[c * FLD + i];
         int fail = 0;
-        double rdiag = 1.0;
+        R rdiag = R(1);
         #pragma unroll
         for (int j = 0; j < FB; ++j) {
             Ls[j * FB + i] = a[j];
             bar64();
-            const double d = Ls[j * FB + j];
-            if (fail == 0 && !(d > 0.0)) fail = j + 1;     // also catches NaN; uniform over the 64 threads
+            const R d = Ls[j * FB + j];
+            if (fail == 0 && !(d > R(0))) fail = j + 1;    // also catches NaN; uniform over the 64 threads
             if constexpr (RSQ) {
-                const double rinv = rsqrt(d);
-                const double w = a[j] * (rinv * rinv);
+                const R rinv = rsqrt_t(d);
+                const R w = a[j] * (rinv * rinv);
                 #pragma unroll
                 for (int c = j + 1; c < FB; ++c) a[c] = fma(-w, Ls[j * FB + c], a[c]);
                 a[j] = (i == j) ? d * rinv : a[j] * rinv;
                 if (i == j) rdiag = rinv;
             }
             else {
-                const double w = a[j] / d;
+                const R w = a[j] / d;
                 #pragma unroll
                 for (int c = j + 1; c < FB; ++c) a[c] = fma(-w, Ls[j * FB + c], a[c]);
-                const double rt = sqrt(d);
+                const R rt = sqrt(d);
                 a[j] = (i == j) ? rt : a[j] / rt;
-                if (i == j) rdiag = 1.0 / rt;
+                if (i == j) rdiag = R(1) / rt;
             }
         }
         if (fail) {
@@ -276,7 +302,7 @@ potrf_tile_fused_kernel(double* __restrict__ A, int lda, int n, int* __restrict_
             }
         }
         else {
-            double* Ad = Arow + int64_t(r) * FB * lda;
+            R* Ad = Arow + int64_t(r) * FB * lda;
             #pragma unroll
             for (int c = 0; c < FB; ++c)
                 if (c <= i && i < rv) Ad[i + int64_t(c) * lda] = a[c];
@@ -286,13 +312,13 @@ potrf_tile_fused_kernel(double* __restrict__ A, int lda, int n, int* __restrict_
                 for (int c = 0; c < FB; ++c) Ls[c * FB + i] = a[c];
                 rd[i] = rdiag;
                 bar64();
-                double x[FB];
-                inv_column64(Ls, rd, i, x);
+                R x[FB];
+                inv_column64<R>(Ls, rd, i, x);
                 bar64();                                   // everybody is done reading Ls (aliased by the staging)
                 #pragma unroll
                 for (int q = 0; q < FB; ++q) Ls[q * (FB + 1) + i] = x[q];          // staging[q][column i]
                 bar64();
-                double* W = Wg + int64_t(r) * FB * FB;
+                R* W = Wg + int64_t(r) * FB * FB;
                 #pragma unroll 8
                 for (int j = 0; j < FB; ++j) W[i + j * FB] = Ls[i * (FB + 1) + j]; // W(i, j), coalesced over i
             }
@@ -307,12 +333,66 @@ potrf_tile_fused_kernel(double* __restrict__ A, int lda, int n, int* __restrict_
     }
 }
 
-constexpr size_t fused_smem() { return size_t(3) * FB * FLD * sizeof(double); }
+// ---------------------------------------------------------------------------------------------
+// Panel solve of the Cholesky step in ONE launch (opt-in, SB200_TRSM_FUSED=1; round-2 candidate, not yet run):
+//   B_t <- alpha B_t L^{-T}      (Right, Lower, Trans, NonUnit;  reference: internal::trsm<Devices>,
+//                                 src/internal/internal_trsm.cc:132-262 -> cublas?trsmBatched)
+// The rows of B are independent, so one CTA takes 64 rows of one B tile through the whole block substitution
+//   for j = 0 .. nblk-1:   X_j = (alpha B_j - sum_{c<j} X_c L(j,c)^T) W_j^T,      W_j = inv(L(j,j)) from trtri_diag
+// with the product micro-kernel of the tile Cholesky above -- the default path (trsm_colmajor) is the same
+// arithmetic as 2 launches per 64-column block (16 dependent launches for nb = 512).
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(FT, 1)
+trsm_rlt_fused_kernel(int m, int na, R alpha, const R* __restrict__ Tm, int ldt, const R* __restrict__ W,
+                      R* const* __restrict__ dB, int64_t offB, int ldb)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    R* Xs = reinterpret_cast<R*>(smem_dyn);
+    R* Ys = Xs + FB * FLD;
+    R* Cs = Ys + FB * FLD;
+    const int tid = threadIdx.x;
+    const Prod<R> pr(tid);
+    const int r0 = blockIdx.x * FB;                        // first row of this CTA inside the tile
+    const int rv = min(FB, m - r0);
+    if (rv <= 0) return;
+    R* Brow = dB[blockIdx.y] + offB + r0;
+    const int nblk = (na + FB - 1) / FB;
+    R acc[32];
+    for (int j = 0; j < nblk; ++j) {
+        const int jv = min(FB, na - j * FB);
+        zero_acc(acc);
+        for (int c = 0; c < j; ++c) {
+            load_block<R>(Xs, Brow + int64_t(c) * FB * ldb, ldb, rv);              // X_c: written by this CTA
+            load_block<R>(Ys, Tm + j * FB + int64_t(c) * FB * ldt, ldt, jv);       // L(j,c), rows >= jv zero
+            __syncthreads();
+            pr.mma(acc, Xs, Ys);
+            __syncthreads();
+        }
+        R* Bj = Brow + int64_t(j) * FB * ldb;
+        #pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int row = pr.row(e), col = pr.col(e);
+            const R o = (row < rv && col < jv) ? __ldcg(Bj + row + int64_t(col) * ldb) : R(0);
+            Cs[col * FLD + row] = alpha * o - acc[e];
+        }
+        load_block<R>(Ys, W + int64_t(j) * FB * FB, FB, FB);                       // W_j (identity-padded by trtri_diag)
+        __syncthreads();
+        zero_acc(acc);
+        pr.mma(acc, Cs, Ys);
+        #pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int row = pr.row(e), col = pr.col(e);
+            if (row < rv && col < jv) Bj[row + int64_t(col) * ldb] = acc[e];
+        }
+        __syncthreads();                                   // X_j visible to the whole CTA (global), Cs / Ys free
+    }
+}
 
-} // namespace
+template <typename R> constexpr size_t fused_smem() { return size_t(3) * FB * FLD * sizeof(R); }
 
-// returns FUSED_NOT_TAKEN when the variant does not apply (the caller then runs the default path)
-int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream)
+template <typename R>
+int potrf_tile_fused_t(int n, R* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream)
 {
     const int nblk = int(ceil_div(n, FB));
     if (nblk < 2 || nblk > FMAXB) return FUSED_NOT_TAKEN;
@@ -320,8 +400,8 @@ int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (! attr_done[dev & 63]) {
-        CUDA_TRY(cudaFuncSetAttribute(potrf_tile_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem())));
-        CUDA_TRY(cudaFuncSetAttribute(potrf_tile_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem())));
+        CUDA_TRY(cudaFuncSetAttribute(potrf_tile_fused_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem<R>())));
+        CUDA_TRY(cudaFuncSetAttribute(potrf_tile_fused_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem<R>())));
         // keep freed stream-ordered allocations in the pool (the workspace below is allocated per launch)
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -332,7 +412,7 @@ int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int
         attr_done[dev & 63] = true;
     }
     // stream-ordered workspace: the inverted diagonal blocks W_0 .. W_{nblk-2} and the flags
-    const size_t wbytes = size_t(nblk) * FB * FB * sizeof(double);
+    const size_t wbytes = size_t(nblk) * FB * FB * sizeof(R);
     void* ws = nullptr;
     CUDA_TRY(cudaMallocAsync(&ws, wbytes + 2 * FMAXB * sizeof(unsigned), stream));
     unsigned* flags = reinterpret_cast<unsigned*>(static_cast<char*>(ws) + wbytes);
@@ -340,13 +420,55 @@ int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int
     int st = (e == cudaSuccess) ? SB200_OK : int(e);
     if (st == SB200_OK) {
         if (variant == 2)
-            potrf_tile_fused_kernel<true><<<nblk, FT, fused_smem(), stream>>>(A, lda, n, dinfo, info_base, static_cast<double*>(ws), flags);
+            potrf_tile_fused_kernel<R, true><<<nblk, FT, fused_smem<R>(), stream>>>(A, lda, n, dinfo, info_base, static_cast<R*>(ws), flags);
         else
-            potrf_tile_fused_kernel<false><<<nblk, FT, fused_smem(), stream>>>(A, lda, n, dinfo, info_base, static_cast<double*>(ws), flags);
+            potrf_tile_fused_kernel<R, false><<<nblk, FT, fused_smem<R>(), stream>>>(A, lda, n, dinfo, info_base, static_cast<R*>(ws), flags);
         st = launch_status();
     }
     cudaFreeAsync(ws, stream);
     return st;
+}
+
+
+// B_t <- alpha B_t L^{-T} for `batch` m x na tiles; W = inverted diagonal 64-blocks of L (trtri_diag layout)
+template <typename R>
+int trsm_rlt_fused_t(int m, int na, R alpha, const R* Tm, int ldt, const R* W, R* const* dB, int64_t offB, int ldb,
+                     int batch, cudaStream_t stream)
+{
+    if (m <= 0 || na <= 0 || batch <= 0) return SB200_OK;
+    static thread_local bool attr_done[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (! attr_done[dev & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(trsm_rlt_fused_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem<R>())));
+        attr_done[dev & 63] = true;
+    }
+    const dim3 grid(unsigned(ceil_div(m, FB)), unsigned(batch));
+    trsm_rlt_fused_kernel<R><<<grid, FT, fused_smem<R>(), stream>>>(m, na, alpha, Tm, ldt, W, dB, offB, ldb);
+    return launch_status();
+}
+
+} // namespace
+
+// return FUSED_NOT_TAKEN when the variant does not apply (the caller then runs the default path)
+int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream)
+{
+    return potrf_tile_fused_t<double>(n, A, lda, dinfo, info_base, variant, stream);
+}
+int potrf_tile_fused_s(int n, float* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream)
+{
+    return potrf_tile_fused_t<float>(n, A, lda, dinfo, info_base, variant, stream);
+}
+
+int trsm_rlt_fused_d(int m, int na, double alpha, const double* Tm, int ldt, const double* W, double* const* dB,
+                     int64_t offB, int ldb, int batch, cudaStream_t stream)
+{
+    return trsm_rlt_fused_t<double>(m, na, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
+}
+int trsm_rlt_fused_s(int m, int na, float alpha, const float* Tm, int ldt, const float* W, float* const* dB,
+                     int64_t offB, int ldb, int batch, cudaStream_t stream)
+{
+    return trsm_rlt_fused_t<float>(m, na, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
 }
 
 } // namespace sb200

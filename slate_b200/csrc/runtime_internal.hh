@@ -36,6 +36,7 @@ constexpr int FACTOR_IB = 64;          // diagonal block of the tile factor / so
 // returns FUSED_NOT_TAKEN when it does not apply
 constexpr int FUSED_NOT_TAKEN = -1000001;
 int potrf_tile_fused_d(int n, double* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream);
+int potrf_tile_fused_s(int n, float* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream);
 // skinny right operand (n <= 16): HBM-bound streaming kernel instead of a tensor-core tile kernel (gemm_skinny.cu)
 template <typename T> bool gemm_skinny_applies(int opB, const GemmParamsT<T>& p);
 template <typename T> int launch_gemm_skinny(int opA, const GemmParamsT<T>& p, cudaStream_t stream);

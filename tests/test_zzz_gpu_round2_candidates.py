@@ -2,6 +2,8 @@
 
 * SB200_TILE_FUSED=1|2 -- one-launch tile Cholesky (slate_b200/csrc/potrf_tile_fused.cu), through the C ABI
   (`sb200_potrf_tile_d`, the lapack::potrf seam: src/internal/internal_potrf.cc:57-81) and through the driver.
+* SB200_TRSM_FUSED=1 -- one-launch Cholesky panel solve B <- alpha B L^-T (same file), through `sb200_trsm_batched_*`
+  (the blas::batch::trsm seam: src/internal/internal_trsm.cc:132-262) and through the driver.
 
 Written after round 1's GPU budget was spent: SKIPPED unless SB200_RUN_UNVALIDATED=1 (round 2: run, fix, drop the guard,
 then make the winner the default)."""
@@ -26,30 +28,32 @@ def sl():
     return sl_
 
 
-def _potrf_tile(A, n, lda=None):
-    from tests.gpu_util import DevTiles, dev_zeros, fn, stream, sync, c_int, c_i64, c_ptr
+def _potrf_tile(A, n, lda=None, t="d"):
+    from tests.gpu_util import DevTiles, dev_zeros, fn, stream, sync, c_int, c_i64, c_ptr, NP
     lda = lda or n
-    buf = np.full((lda, n), 7.25)
+    buf = np.full((lda, n), 7.25, dtype=NP[t])
     buf[:n, :] = A
     dA = DevTiles([buf])
     info = dev_zeros(1, np.int32)
-    f = fn("sb200_potrf_tile_d", [c_int, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr])
+    f = fn(f"sb200_potrf_tile_{t}", [c_int, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr])
     assert f(ord("L"), n, dA.t[0].data_ptr(), lda, info.data_ptr(), None, stream()) == 0
     sync()
     return dA.get()[0], int(info.cpu()[0])
 
 
+@pytest.mark.parametrize("t", ["d", "s"])
 @pytest.mark.parametrize("variant", ["1", "2"])
 @pytest.mark.parametrize("n,lda", [(128, 128), (512, 512), (448, 512), (500, 500), (130, 136), (1000, 1024), (1024, 1024), (65, 65)])
-def test_fused_tile_cholesky_vs_lapack(monkeypatch, variant, n, lda):
+def test_fused_tile_cholesky_vs_lapack(monkeypatch, variant, n, lda, t):
     monkeypatch.setenv("SB200_TILE_FUSED", variant)
     rng = np.random.default_rng(5)
     G = rng.random((n, n))
-    A = G @ G.T + n * np.eye(n)
-    out, info = _potrf_tile(A, n, lda)
+    A = (G @ G.T + n * np.eye(n)).astype(np.float64 if t == "d" else np.float32)
+    out, info = _potrf_tile(A, n, lda, t)
     assert info == 0
-    ref = np.linalg.cholesky(A)
-    assert np.abs(np.tril(out[:n, :]) - ref).max() <= 50 * EPS * np.abs(ref).max()
+    ref = np.linalg.cholesky(A.astype(np.float64))
+    eps = EPS if t == "d" else float(np.finfo(np.float32).eps)
+    assert np.abs(np.tril(out[:n, :]) - ref).max() <= 50 * eps * np.abs(ref).max()
     assert np.array_equal(np.triu(out[:n, :], 1), np.triu(A, 1))          # strict upper triangle untouched
     assert np.all(out[n:, :] == 7.25)                                    # rows beyond n (lda > n) untouched
 
@@ -103,3 +107,54 @@ def test_potrf_driver_with_fused_tile_info(sl, monkeypatch):
     S[700, 700] = -1.0
     A = sl.HermitianMatrix(n, nb); A.from_host(np.asfortranarray(S))
     assert sl.potrf(A) == 701
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+@pytest.mark.parametrize("n,nb", [(2048, 512), (1000, 128)])
+def test_posv_mixed_with_fused_tile(sl, monkeypatch, variant, n, nb):
+    """The FP32 factorisation of posv_mixed takes the FP32 instance of the fused tile kernel."""
+    monkeypatch.setenv("SB200_TILE_FUSED", variant)
+    A = sl.HermitianMatrix(n, nb).generate("rand_dominant", 42)
+    B = sl.Matrix(n, 10, nb).generate("rand", 43)
+    X = sl.Matrix(n, 10, nb)
+    info, it, _ = sl.posv_mixed(A, B, X)
+    assert info == 0 and 0 <= it <= 30
+    a = o.generate("rand_dominant", n, n, 42); b = o.generate("rand", n, 10, 43)
+    assert o.solve_residual(o.he_full(a), X.to_host(), b) <= 25 * EPS            # test/test_posv.cc:336-342
+
+
+@pytest.mark.parametrize("t", ["d", "s"])
+@pytest.mark.parametrize("m,n", [(512, 512), (300, 512), (512, 448), (100, 130), (64, 500), (1, 65), (512, 1024)])
+def test_fused_panel_trsm_right_lower_trans(monkeypatch, t, m, n):
+    """Right / Lower / Trans / NonUnit (the potrf panel solve) through the C ABI, vs the oracle's tile solve; the layout
+    'R' call of the same routine is the Left / Upper / NoTrans problem on the transposed storage and must agree too."""
+    from tests.gpu_util import DevTiles, fn, scal, stream, rng_tiles, NP, SC, c_int, c_i64, c_ptr
+    monkeypatch.setenv("SB200_TRSM_FUSED", "1")
+    rng = np.random.default_rng(4)
+    batch = 3
+    T = (rng.random((n, n)) / n + np.eye(n) * (1 + rng.random(n))).astype(NP[t])
+    B = rng_tiles(rng, batch, m, n, t)
+    alpha = 0.7
+    ref = [o.trsm_tile("R", "L", "T", "N", alpha, T.astype(np.float64), b.astype(np.float64)) for b in B]
+    dT, dB = DevTiles([T]), DevTiles(B)
+    f = fn(f"sb200_trsm_batched_{t}", [c_int] * 5 + [c_i64, c_i64, SC[t], c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr])
+    assert f(ord("C"), ord("R"), ord("L"), ord("T"), ord("N"), m, n, scal(t, alpha), dT.t[0].data_ptr(), n,
+             dB.p, m, batch, None, stream()) == 0
+    eps = EPS if t == "d" else float(np.finfo(np.float32).eps)
+    for x, r in zip(dB.get(), ref):
+        assert np.abs(x - r).max() <= 200 * eps * np.abs(r).max()
+
+
+@pytest.mark.parametrize("n,nb", [(2048, 512), (1100, 512), (1000, 256)])
+def test_potrf_driver_with_fused_tile_and_panel_solve(sl, monkeypatch, n, nb):
+    monkeypatch.setenv("SB200_TILE_FUSED", "1")
+    monkeypatch.setenv("SB200_TRSM_FUSED", "1")
+    A = sl.HermitianMatrix(n, nb).generate("rand_dominant", 11)
+    assert sl.potrf(A) == 0
+    L = np.tril(A.to_host())
+    G = o.generate("rand_dominant", n, n, 11)
+    Af = np.tril(G) + np.tril(G, -1).T
+    Lo, info = o.potrf(Af, nb)
+    assert info == 0
+    assert np.abs(L - Lo).max() <= 64 * EPS * np.abs(Lo).max()
+    assert np.abs(L @ L.T - Af).max() <= 64 * EPS * np.abs(Af).max()
