@@ -27,6 +27,11 @@ int trsm_rlt_fused_d(int m, int na, double alpha, const double* Tm, int ldt, con
                      int64_t offB, int ldb, int batch, cudaStream_t stream);
 int trsm_rlt_fused_s(int m, int na, float alpha, const float* Tm, int ldt, const float* W, float* const* dB,
                      int64_t offB, int ldb, int batch, cudaStream_t stream);
+// opt-in one-launch LU row solve B <- alpha L^{-1} B (SB200_TRSM_FUSED bit 1)
+int trsm_lln_fused_d(int na, int n, double alpha, const double* Tm, int ldt, const double* W, double* const* dB,
+                     int64_t offB, int ldb, int batch, cudaStream_t stream);
+int trsm_lln_fused_s(int na, int n, float alpha, const float* Tm, int ldt, const float* W, float* const* dB,
+                     int64_t offB, int ldb, int batch, cudaStream_t stream);
 
 constexpr int IB = 64;
 template <typename T> constexpr size_t small_smem() { return 2 * IB * (IB + 1) * sizeof(T); }
@@ -504,12 +509,19 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
     int st = launch_trtri_diag<T>(nblk, Tm, ldt, na, lower ? 1 : 0, unit ? 1 : 0, W, stream);
     if (st) return st;
     if constexpr (IsRealType<T>::value) {
-        // opt-in (round-2 candidate, not yet run): the Cholesky panel solve (Right, Lower, Trans, NonUnit) in one
-        // launch after the inverses (potrf_tile_fused.cu); read per call so that a test can switch it
+        // opt-in (round-2 candidates, not yet run; potrf_tile_fused.cu): one launch after the inverses for
+        //   bit 0: the Cholesky panel solve (Right, Lower, Trans, NonUnit)
+        //   bit 1: the LU row solve (Left, Lower, NoTrans, Unit / NonUnit)
+        // read per call so that a test can switch it
         const char* e = getenv("SB200_TRSM_FUSED");
-        if (e && atoi(e) != 0 && ! left && lower && op != 'N' && ! unit && na > IB) {
+        const int fused = e ? atoi(e) : 0;
+        if ((fused & 1) && ! left && lower && op != 'N' && ! unit && na > IB) {
             if constexpr (std::is_same<T, double>::value) return trsm_rlt_fused_d(m, na, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
             else                                          return trsm_rlt_fused_s(m, na, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
+        }
+        if ((fused & 2) && left && lower && op == 'N' && na > IB) {
+            if constexpr (std::is_same<T, double>::value) return trsm_lln_fused_d(na, n, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
+            else                                          return trsm_lln_fused_s(na, n, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
         }
     }
     const bool trans = (op != 'N');

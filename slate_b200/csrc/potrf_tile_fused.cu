@@ -389,6 +389,78 @@ trsm_rlt_fused_kernel(int m, int na, R alpha, const R* __restrict__ Tm, int ldt,
     }
 }
 
+// dst[k * FLD + j] = src[k + j * lds] for j < cv (columns beyond cv are zero-filled): the 64 x 64 block is stored
+// transposed, so that an operand which is contiguous along k in memory gets the [k][column] layout the product wants
+template <typename R>
+__device__ __forceinline__ void load_block_t(R* __restrict__ dst, const R* src, int lds, int cv)
+{
+    const int k = threadIdx.x & (FB - 1), j0 = threadIdx.x >> 6;          // j0 in {0, 1}
+    #pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        R v[FB / 4];
+        #pragma unroll
+        for (int t = 0; t < FB / 4; ++t) {
+            const int j = j0 + 2 * (half * (FB / 4) + t);
+            v[t] = (j < cv) ? __ldcg(src + k + int64_t(j) * lds) : R(0);
+        }
+        #pragma unroll
+        for (int t = 0; t < FB / 4; ++t) dst[k * FLD + j0 + 2 * (half * (FB / 4) + t)] = v[t];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row solve of the LU step in ONE launch (opt-in, SB200_TRSM_FUSED bit 1; round-2 candidate, not yet run):
+//   B_t <- alpha L^{-1} B_t      (Left, Lower, NoTrans, Unit or NonUnit: the diagonal only enters through W)
+// The columns of B are independent: one CTA takes 64 columns of one B tile through
+//   for j = 0 .. nblk-1:   X_j = W_j (alpha B_j - sum_{c<j} L(j,c) X_c)
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(FT, 1)
+trsm_lln_fused_kernel(int na, int n, R alpha, const R* __restrict__ Tm, int ldt, const R* __restrict__ W,
+                      R* const* __restrict__ dB, int64_t offB, int ldb)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    R* Xs = reinterpret_cast<R*>(smem_dyn);
+    R* Ys = Xs + FB * FLD;
+    R* Cs = Ys + FB * FLD;
+    const int tid = threadIdx.x;
+    const Prod<R> pr(tid);
+    const int c0 = blockIdx.x * FB;                        // first column of this CTA inside the tile
+    const int cv = min(FB, n - c0);
+    if (cv <= 0) return;
+    R* Bcol = dB[blockIdx.y] + offB + int64_t(c0) * ldb;
+    const int nblk = (na + FB - 1) / FB;
+    R acc[32];
+    for (int j = 0; j < nblk; ++j) {
+        const int jv = min(FB, na - j * FB);
+        zero_acc(acc);
+        for (int c = 0; c < j; ++c) {
+            load_block<R>(Xs, Tm + j * FB + int64_t(c) * FB * ldt, ldt, jv);       // L(j,c)(row, k), rows >= jv zero
+            load_block_t<R>(Ys, Bcol + c * FB, ldb, cv);                          // X_c(k, col): written by this CTA
+            __syncthreads();
+            pr.mma(acc, Xs, Ys);
+            __syncthreads();
+        }
+        R* Bj = Bcol + j * FB;
+        #pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int row = pr.row(e), col = pr.col(e);
+            const R o = (row < jv && col < cv) ? __ldcg(Bj + row + int64_t(col) * ldb) : R(0);
+            Cs[row * FLD + col] = alpha * o - acc[e];                             // S(k = row, col)
+        }
+        load_block<R>(Xs, W + int64_t(j) * FB * FB, FB, FB);                       // W_j(row, k)
+        __syncthreads();
+        zero_acc(acc);
+        pr.mma(acc, Xs, Cs);
+        #pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int row = pr.row(e), col = pr.col(e);
+            if (row < jv && col < cv) Bj[row + int64_t(col) * ldb] = acc[e];
+        }
+        __syncthreads();
+    }
+}
+
 template <typename R> constexpr size_t fused_smem() { return size_t(3) * FB * FLD * sizeof(R); }
 
 template <typename R>
@@ -448,6 +520,24 @@ int trsm_rlt_fused_t(int m, int na, R alpha, const R* Tm, int ldt, const R* W, R
     return launch_status();
 }
 
+// B_t <- alpha L^{-1} B_t for `batch` na x n tiles; W = inverted diagonal 64-blocks of L (unit or not: trtri_diag)
+template <typename R>
+int trsm_lln_fused_t(int na, int n, R alpha, const R* Tm, int ldt, const R* W, R* const* dB, int64_t offB, int ldb,
+                     int batch, cudaStream_t stream)
+{
+    if (n <= 0 || na <= 0 || batch <= 0) return SB200_OK;
+    static thread_local bool attr_done[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (! attr_done[dev & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(trsm_lln_fused_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem<R>())));
+        attr_done[dev & 63] = true;
+    }
+    const dim3 grid(unsigned(ceil_div(n, FB)), unsigned(batch));
+    trsm_lln_fused_kernel<R><<<grid, FT, fused_smem<R>(), stream>>>(na, n, alpha, Tm, ldt, W, dB, offB, ldb);
+    return launch_status();
+}
+
 } // namespace
 
 // return FUSED_NOT_TAKEN when the variant does not apply (the caller then runs the default path)
@@ -469,6 +559,16 @@ int trsm_rlt_fused_s(int m, int na, float alpha, const float* Tm, int ldt, const
                      int64_t offB, int ldb, int batch, cudaStream_t stream)
 {
     return trsm_rlt_fused_t<float>(m, na, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
+}
+int trsm_lln_fused_d(int na, int n, double alpha, const double* Tm, int ldt, const double* W, double* const* dB,
+                     int64_t offB, int ldb, int batch, cudaStream_t stream)
+{
+    return trsm_lln_fused_t<double>(na, n, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
+}
+int trsm_lln_fused_s(int na, int n, float alpha, const float* Tm, int ldt, const float* W, float* const* dB,
+                     int64_t offB, int ldb, int batch, cudaStream_t stream)
+{
+    return trsm_lln_fused_t<float>(na, n, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
 }
 
 } // namespace sb200

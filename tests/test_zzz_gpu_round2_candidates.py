@@ -2,8 +2,9 @@
 
 * SB200_TILE_FUSED=1|2 -- one-launch tile Cholesky (slate_b200/csrc/potrf_tile_fused.cu), through the C ABI
   (`sb200_potrf_tile_d`, the lapack::potrf seam: src/internal/internal_potrf.cc:57-81) and through the driver.
-* SB200_TRSM_FUSED=1 -- one-launch Cholesky panel solve B <- alpha B L^-T (same file), through `sb200_trsm_batched_*`
-  (the blas::batch::trsm seam: src/internal/internal_trsm.cc:132-262) and through the driver.
+* SB200_TRSM_FUSED bit 0 -- one-launch Cholesky panel solve B <- alpha B L^-T, bit 1 -- one-launch LU row solve
+  B <- alpha L^-1 B (same file), through `sb200_trsm_batched_*` (the blas::batch::trsm seam:
+  src/internal/internal_trsm.cc:132-262) and through the drivers.
 
 Written after round 1's GPU budget was spent: SKIPPED unless SB200_RUN_UNVALIDATED=1 (round 2: run, fix, drop the guard,
 then make the winner the default)."""
@@ -158,3 +159,51 @@ def test_potrf_driver_with_fused_tile_and_panel_solve(sl, monkeypatch, n, nb):
     assert info == 0
     assert np.abs(L - Lo).max() <= 64 * EPS * np.abs(Lo).max()
     assert np.abs(L @ L.T - Af).max() <= 64 * EPS * np.abs(Af).max()
+
+
+@pytest.mark.parametrize("t", ["d", "s"])
+@pytest.mark.parametrize("diag", ["U", "N"])
+@pytest.mark.parametrize("m,n", [(512, 512), (512, 300), (448, 512), (130, 100), (500, 64), (65, 1), (1024, 512), (256, 700)])
+def test_fused_row_trsm_left_lower_notrans(monkeypatch, t, diag, m, n):
+    """Left / Lower / NoTrans (the LU row solve U(k,j) = L_kk^-1 A(k,j), unit diagonal in getrf) through the C ABI."""
+    from tests.gpu_util import DevTiles, fn, scal, stream, rng_tiles, NP, SC, c_int, c_i64, c_ptr
+    monkeypatch.setenv("SB200_TRSM_FUSED", "2")
+    rng = np.random.default_rng(4)
+    batch = 3
+    T = (rng.random((m, m)) / m + np.eye(m) * (1 + rng.random(m))).astype(NP[t])
+    B = rng_tiles(rng, batch, m, n, t)
+    alpha = 0.7
+    ref = [o.trsm_tile("L", "L", "N", diag, alpha, T.astype(np.float64), b.astype(np.float64)) for b in B]
+    dT, dB = DevTiles([T]), DevTiles(B)
+    f = fn(f"sb200_trsm_batched_{t}", [c_int] * 5 + [c_i64, c_i64, SC[t], c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr])
+    assert f(ord("C"), ord("L"), ord("L"), ord("N"), ord(diag), m, n, scal(t, alpha), dT.t[0].data_ptr(), m,
+             dB.p, m, batch, None, stream()) == 0
+    eps = EPS if t == "d" else float(np.finfo(np.float32).eps)
+    for x, r in zip(dB.get(), ref):
+        assert np.abs(x - r).max() <= 200 * eps * np.abs(r).max()
+
+
+@pytest.mark.parametrize("dist", ["0", "1"])
+@pytest.mark.parametrize("m,n,nb", [(1024, 1024, 256), (2048, 2048, 512), (700, 300, 128), (300, 700, 128), (1100, 1100, 512)])
+def test_getrf_with_fused_row_solve_identical_pivots(sl, monkeypatch, m, n, nb, dist):
+    monkeypatch.setenv("SB200_TRSM_FUSED", "2")
+    monkeypatch.setenv("SB200_GETRF_DIST", dist)
+    A = sl.Matrix(m, n, nb).generate("rand", 42)
+    piv, info = sl.getrf(A)
+    A0 = o.generate("rand", m, n, 42)
+    LUo, pivo, info_o = o.getrf(A0, nb, 32)
+    assert info == info_o == 0
+    assert piv == pivo, "pivot vectors differ from the oracle's"
+    assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
+
+
+def test_gesv_mixed_with_all_fused_candidates(sl, monkeypatch):
+    monkeypatch.setenv("SB200_TRSM_FUSED", "3")
+    monkeypatch.setenv("SB200_TILE_FUSED", "1")
+    n, nb = 2048, 512
+    A = sl.Matrix(n, n, nb).generate("rand", 42)
+    B = sl.Matrix(n, 10, nb).generate("rand", 43)
+    X = sl.Matrix(n, 10, nb)
+    info, it, piv, tm = sl.gesv_mixed(A, B, X)
+    assert info == 0 and 0 <= it <= 30
+    assert o.solve_residual(o.generate("rand", n, n, 42), X.to_host(), o.generate("rand", n, 10, 43)) <= 25 * EPS
