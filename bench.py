@@ -606,8 +606,16 @@ def main():
         e2e_ms = []
         # opt-in (round-2 candidate, not yet run): D2H of finished block columns overlapped inside the driver
         overlap_d2h = routine == "potrf" and os.environ.get("SB200_E2E_OVERLAP") == "1"
+        # opt-in (round-2 candidate, not yet run; one rank): the input streams in by chunks of block columns as well
+        overlap_both = routine == "potrf" and world == 1 and os.environ.get("SB200_E2E_OVERLAP") == "2"
         for it in range(1 + args.steps):
             barrier(); t0 = time.perf_counter()
+            if overlap_both:
+                sl.potrf(A, in_local=host, out_local=res)
+                barrier(); t1 = time.perf_counter()
+                if it >= 1:
+                    e2e_ms.append((t1 - t0) * 1e3)
+                continue
             A.from_host_local(host, sync=False)
             if overlap_d2h:
                 sl.potrf(A, out_local=res)          # finished block columns stream to the host while it factors

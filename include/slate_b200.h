@@ -378,6 +378,10 @@ int sb200_potrf_##X(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info
 /* the same, streaming every finished block column into the packed host buffer `htiles` (order and size of \
  * sb200_matrix_to_host_local; pinned memory makes the copies overlap the factorisation) */ \
 int sb200_potrf_to_host_local_##X(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info, void* htiles); \
+/* the same with the INPUT streaming in as well: the matrix is read from the packed host buffer `htiles_in` (layout of \
+ * sb200_matrix_from_host_local) in chunks of block columns while earlier chunks are being factored; `htiles_out` may \
+ * be NULL (the factor then stays on the device only).  One rank; bitwise the same factor as sb200_potrf. */ \
+int sb200_potrf_stream_##X(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info, const void* htiles_in, void* htiles_out); \
 /* B <- A^{-1} B from the Cholesky factor       slate::potrs (src/potrs.cc:54-77); 1 x 1 grid this round */ \
 int sb200_potrs_##X(sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
 /* C = alpha A X + beta C, A Hermitian lower, Side::Left   slate::hemm (src/hemmC.cc); 1 x 1 grid */ \

@@ -120,7 +120,7 @@ static int bcast_block_column(Grid& g, Matrix& A, int64_t k, int64_t i_first, co
 // (gemm_tc05.cu); the factored panel is split-packed once per step (A-side and B-side units).
 // ------------------------------------------------------------------------------------------
 template <typename T>
-int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out)
+int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, const void* host_in)
 {
     using R = typename RealOf<T>::type;
     Grid& g = *A.g;
@@ -136,6 +136,24 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out)
     const int64_t rows_max = (A.mt + g.p - 1) / g.p;        // panel workspace slots per process row
     const T one = from_real<T>(R(1)), minus_one = from_real<T>(R(-1));
     const int opH = IsComplex<T>::value ? 'C' : 'T';
+    // Streaming input (opt-in, host_in != nullptr; one rank, no tcgen05 path): the matrix arrives from the caller's
+    // packed host buffer in CHUNKS of block columns on a copy stream while the factorisation runs.  Inside a chunk the
+    // schedule below is unchanged (its updates only touch columns of the chunk); when the next chunk has arrived it
+    // first receives the updates of every finished step, one batched launch per step in step order, so every tile
+    // sees exactly the same sequence of updates as without streaming (bitwise identical factor).
+    const bool stream_in = host_in != nullptr;
+    if (stream_in && (multi || use_tc05)) return SB200_ENOTSUP;
+    std::vector<int64_t> cb{0};                              // chunk c = block columns [cb[c], cb[c+1])
+    if (stream_in) {
+        const char* e = getenv("SB200_STREAM_CHUNK");
+        const int64_t cw = std::max<int64_t>(1, e ? atoll(e) : 8);
+        for (int64_t c = std::min<int64_t>(nt, std::max<int64_t>(1, cw / 2)); c < nt; c += cw) cb.push_back(c);   // small first chunk
+    }
+    cb.push_back(nt);
+    const int nchunk = int(cb.size()) - 1;
+    std::vector<int> chunk_of(nt, 0);
+    for (int c = 0; c < nchunk; ++c)
+        for (int64_t j = cb[c]; j < cb[c + 1]; ++j) chunk_of[j] = c;
 
     DevBuf ws, dbuf, work, dinfo, packA, packB;
     if (multi) {
@@ -163,7 +181,8 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out)
 
     // ---- plan: every pointer batch of every step
     struct Step {
-        std::vector<Batch> la, tr;           // lookahead column k+1 / trailing columns >= k+2
+        std::vector<Batch> la, tr;           // lookahead column k+1 / trailing columns >= k+2 (inside the chunk of k)
+        std::vector<std::vector<Batch>> catchup;    // streaming input: this step's update of the columns of each later chunk
         std::vector<T*> panel;               // local tiles (i,k), i > k, full height
         std::vector<T*> panel_last;          // ragged last block row
         std::vector<const void*> pkA_src, pkB_src;   // tiles to pack (tcgen05 path), full height | last (ragged) at the end
@@ -177,10 +196,11 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out)
         Step& s = steps[k];
         const int kw = int(A.tile_nb(k));
         std::vector<char> needA(nt, 0), needB(nt, 0);
+        s.catchup.resize(nchunk);
         for (int64_t j = k + 1; j < nt; ++j)
             for (int64_t i = j; i < nt; ++i) {
                 if (! A.is_local(i, j)) continue;
-                auto& dst = (j == k + 1) ? s.la : s.tr;
+                auto& dst = (chunk_of[j] > chunk_of[k]) ? s.catchup[chunk_of[j]] : (j == k + 1) ? s.la : s.tr;
                 const void* a = use_tc05 ? static_cast<const void*>(pkA(i, k)) : pbuf(i, k);
                 const void* b = use_tc05 ? static_cast<const void*>(pkB(j, k)) : pbuf(j, k);
                 batch_add(dst, int(A.tile_mb(i)), int(A.tile_nb(j)), kw, i == j ? 1 : 0, a, b, A.tile_as<T>(i, j));
@@ -198,6 +218,7 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out)
             }
         pb.reserve(s.la);
         pb.reserve(s.tr);
+        for (auto& cu : s.catchup) pb.reserve(cu);
         s.panel_off = pb.push(s.panel);
         s.panel_last_off = pb.push(s.panel_last);
         s.pkA_src_off = pb.push(s.pkA_src); s.pkA_dst_off = pb.push(s.pkA_dst);
@@ -206,7 +227,7 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out)
 
     Streams st;
     PhaseTimer ph;
-    SB_TRY(st.init(size_t(2 * nt)));
+    SB_TRY(st.init(size_t(2 * nt + 2 * nchunk)));
     // optional: every block column is copied to the caller's packed host buffer (pool order, as to_host_local) as soon
     // as it is final (after P_done(k)), on a copy stream, overlapping the rest of the factorisation
     cudaStream_t copy = nullptr;
@@ -216,10 +237,27 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out)
     int64_t trail_launches = 0;
     auto P_done = [&](int64_t k) { return st.ev[k]; };
     auto T_done = [&](int64_t k) { return st.ev[nt + k]; };
+    auto H_in   = [&](int c) { return st.ev[2 * nt + c]; };              // chunk c has arrived from the host
+    auto C_done = [&](int c) { return st.ev[2 * nt + nchunk + c]; };     // chunk c carries every earlier step's update
+    cudaStream_t copy_in = nullptr;
+    struct CopyGuard2 { cudaStream_t& s; ~CopyGuard2() { if (s) cudaStreamDestroy(s); } } copy_in_guard{copy_in};
+    if (stream_in) CUDA_TRY(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
     SB_TRY(pb.upload(st.panel));
     CUDA_TRY(cudaMemsetAsync(dinfo.p, 0, sizeof(int), st.panel));
     CUDA_TRY(cudaStreamSynchronize(st.panel));
     CUDA_TRY(cudaEventRecord(st.t0, st.panel));
+    if (stream_in) {
+        // one rank: local block column jl == block column j; chunks are contiguous ranges of the pool
+        CUDA_TRY(cudaStreamWaitEvent(copy_in, st.t0, 0));
+        for (int c = 0; c < nchunk; ++c) {
+            const size_t o = size_t(A.col_start[cb[c]]) * te * sizeof(T);
+            const size_t bytes = size_t(A.col_start[cb[c + 1]] - A.col_start[cb[c]]) * te * sizeof(T);
+            if (bytes)
+                CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(A.pool) + o, static_cast<const char*>(host_in) + o, bytes,
+                                         cudaMemcpyHostToDevice, copy_in));
+            CUDA_TRY(cudaEventRecord(H_in(c), copy_in));
+        }
+    }
 
     auto update = [&](const std::vector<Batch>& bs, cudaStream_t s) -> int {
         if constexpr (is_float) {
@@ -259,8 +297,28 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out)
         const bool in_col = (g.pcol == int(k % g.q));
         cudaStream_t P = st.panel, T_ = st.trail;
 
+        // -- streaming input: first step of a chunk -- wait for its arrival, then bring it up to date
+        if (stream_in && k == cb[chunk_of[k]]) {
+            const int c = chunk_of[k];
+            CUDA_TRY(cudaStreamWaitEvent(T_, H_in(c), 0));
+            CUDA_TRY(cudaStreamWaitEvent(P, H_in(c), 0));
+            if (c > 0) {
+                CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k - 1), 0));          // every panel < k is final
+                for (int64_t kk = 0; kk < k; ++kk) {
+                    const auto& cu = steps[kk].catchup[c];
+                    if (cu.empty()) continue;
+                    SB_TRY(st.time_begin(T_));
+                    SB_TRY(update(cu, T_));
+                    SB_TRY(st.time_end(T_));
+                    trail_flops += batches_flops(cu, IsComplex<T>::value);
+                    trail_launches += int64_t(cu.size());
+                }
+                CUDA_TRY(cudaEventRecord(C_done(c), T_));
+                CUDA_TRY(cudaStreamWaitEvent(P, C_done(c), 0));
+            }
+        }
         // -- lookahead update of column k by panel k-1 (after every older trailing update)
-        if (k >= 1) {
+        if (k >= 1 && ! (stream_in && steps[k - 1].la.empty())) {     // (streaming: the first column of a chunk was updated by the catch-up)
             if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));
             ph.begin("la_update", P);
             SB_TRY(update(steps[k - 1].la, P));
@@ -539,7 +597,7 @@ int herk_driver(typename RealOf<T>::type alpha, Matrix& A, typename RealOf<T>::t
 }
 
 #define SB200_INST_DRIVERS(T) \
-    template int potrf_driver<T>(Matrix&, int64_t*, bool, void*); \
+    template int potrf_driver<T>(Matrix&, int64_t*, bool, void*, const void*); \
     template int gemm_driver<T>(T, Matrix&, Matrix&, T, Matrix&); \
     template int herk_driver<T>(RealOf<T>::type, Matrix&, RealOf<T>::type, Matrix&);
 SB200_INST_DRIVERS(float)
@@ -797,14 +855,21 @@ int sb200_potrf_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info
 { \
     (void) opts;                       /* lookahead is fixed at 1 (the reference default) */ \
     if (! h) return SB200_EINVAL; \
-    return potrf_driver<CuT<T>::type>(h->A, info, false, nullptr); \
+    return potrf_driver<CuT<T>::type>(h->A, info, false, nullptr, nullptr); \
 } \
 /* potrf whose result streams to the packed host buffer (sb200_matrix_to_host_local order) while it factors */ \
 int sb200_potrf_to_host_local_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info, void* htiles) \
 { \
     (void) opts; \
     if (! h || ! htiles) return SB200_EINVAL; \
-    return potrf_driver<CuT<T>::type>(h->A, info, false, htiles); \
+    return potrf_driver<CuT<T>::type>(h->A, info, false, htiles, nullptr); \
+} \
+/* potrf whose INPUT also streams from a packed host buffer (chunks of block columns) while it factors; one rank */ \
+int sb200_potrf_stream_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info, const void* htiles_in, void* htiles_out) \
+{ \
+    (void) opts; \
+    if (! h || ! htiles_in) return SB200_EINVAL; \
+    return potrf_driver<CuT<T>::type>(h->A, info, false, htiles_out, htiles_in); \
 } \
 int sb200_gemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, \
                    const sb200_options_t* opts) \
@@ -827,7 +892,7 @@ int sb200_potrf_tc05_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* i
 {
     (void) opts;
     if (! h) return SB200_EINVAL;
-    return potrf_driver<float>(h->A, info, true, nullptr);
+    return potrf_driver<float>(h->A, info, true, nullptr, nullptr);
 }
 
 } // extern "C"

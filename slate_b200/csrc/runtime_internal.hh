@@ -208,7 +208,8 @@ struct DevBuf {
 };
 
 // drivers (runtime.cu)
-template <typename T> int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out = nullptr);
+template <typename T> int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out = nullptr,
+                                        const void* host_in = nullptr);
 template <typename T> int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C);
 template <typename T> int herk_driver(typename RealOf<T>::type alpha, Matrix& A, typename RealOf<T>::type beta, Matrix& C);
 int matrix_alloc(Grid& g, int dtype, int kind, int64_t m, int64_t n, int64_t nb, Matrix& A);

@@ -65,6 +65,7 @@ _last_ms = _sig("sb200_last_driver_ms", [c_ptr], c_dbl)
 _potrf = {t: _sig(f"sb200_potrf_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64)]) for t in "sdcz"}
 _potrf["s_tc05"] = _sig("sb200_potrf_tc05_s", [c_ptr, _OP, ctypes.POINTER(c_i64)])
 _potrf_to_host = {t: _sig(f"sb200_potrf_to_host_local_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64), c_ptr]) for t in "sdcz"}
+_potrf_stream = {t: _sig(f"sb200_potrf_stream_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64), c_ptr, c_ptr]) for t in "sdcz"}
 _gemm = {t: _sig(f"sb200_gemm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
 _herk = {t: _sig(f"sb200_herk_mat_{t}", [REAL_T[t], c_ptr, REAL_T[t], c_ptr, _OP]) for t in "sdcz"}
 _hemm = {t: _sig(f"sb200_hemm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
@@ -334,10 +335,12 @@ def norm_inf(A: Matrix) -> float:
     return float(v.value)
 
 
-def potrf(A: HermitianMatrix, opts: dict | None = None, out_local=None) -> int:
+def potrf(A: HermitianMatrix, opts: dict | None = None, out_local=None, in_local=None) -> int:
     """Cholesky A = L L^H, lower (slate::potrf, src/potrf.cc:262-281).
     out_local (optional): packed host tile buffer as for Matrix.to_host_local; every finished block column is copied
     into it while the factorisation runs (pinned memory: the D2H overlaps the trailing updates).
+    in_local (optional, one rank): packed host tile buffer as for Matrix.from_host_local; the matrix streams in by
+    chunks of block columns while earlier chunks are factored (bitwise the same factor).
     Returns info: 0, or i > 0 if the leading minor of order i is not positive definite.
     opts['tensor_core_fp32'] (float matrices only): run the trailing update on the tcgen05
     FP32-emulated kernel, as posv_mixed does for its low-precision factorisation."""
@@ -348,6 +351,15 @@ def potrf(A: HermitianMatrix, opts: dict | None = None, out_local=None) -> int:
         if A.t != "s":
             raise Exception_("tensor_core_fp32 applies to float matrices")
         key = "s_tc05"
+    if in_local is not None:
+        if key == "s_tc05":
+            raise Exception_("in_local is not combined with tensor_core_fp32")
+        A._check_local(in_local)
+        if out_local is not None:
+            A._check_local(out_local)
+        check(_potrf_stream[A.t](A._h, ctypes.byref(o), ctypes.byref(info), in_local.data_ptr(),
+                                 out_local.data_ptr() if out_local is not None else None), "potrf")
+        return int(info.value)
     if out_local is not None:
         if key == "s_tc05":
             raise Exception_("out_local is not combined with tensor_core_fp32")
