@@ -1,0 +1,44 @@
+#!/usr/bin/env bash
+# Round 2, FIRST GPU call (N = 1, ~6-8 min of box time): validate everything written after round 1's GPU budget was
+# spent, then measure every candidate against the default path.  Nothing here changes defaults.
+#   gpurun --timeout 900 -- 'bash scratch/gpu_r2_call1.sh'
+set -uo pipefail
+OUT=gpurun_out; mkdir -p $OUT
+T0=$SECONDS
+stamp() { echo "[$((SECONDS-T0)) s] $*" | tee -a $OUT/r2c1_timeline.txt; }
+stamp start
+# 1. smoke + the guarded candidate tests (each file separately so that one failure does not hide the others)
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/r2c1_smoke.log 2>&1; tail -2 $OUT/r2c1_smoke.log
+stamp smoke
+for f in test_zzz_gpu_round2_candidates test_zzz_gpu_dist_solve; do
+  SB200_RUN_UNVALIDATED=1 timeout 420 python -m pytest tests/$f.py -m gpu -q --timeout 120 -n 4 > $OUT/r2c1_$f.log 2>&1
+  echo "pytest exit $?" >> $OUT/r2c1_$f.log; tail -25 $OUT/r2c1_$f.log | cut -c1-240
+  stamp $f
+done
+# 2. latched switches: the existing parity tests under each of them (fresh process per switch)
+for sw in SB200_DIAG_RSQRT SB200_DIAG_WARP SB200_PANEL_BARRIER; do
+  env $sw=1 timeout 300 python -m pytest tests/test_zz_gpu_panel_variants.py tests/test_gpu_drivers.py -m gpu -q --timeout 120 -n 4 \
+      > $OUT/r2c1_switch_$sw.log 2>&1
+  echo "pytest exit $?" >> $OUT/r2c1_switch_$sw.log; tail -6 $OUT/r2c1_switch_$sw.log | cut -c1-240
+  stamp $sw
+done
+# 3. timings of every variant (one fresh process each), phases on stderr
+for r in potrf getrf posv_mixed; do
+  timeout 900 python scratch/perf_variants.py $r 32768 512 > $OUT/r2c1_perf_$r.log 2> $OUT/r2c1_perf_$r.err
+  cat $OUT/r2c1_perf_$r.log | cut -c1-300
+  stamp perf_$r
+done
+# 4. e2e of the default bench with the overlap modes (0 = none, 1 = D2H streamed, 2 = H2D + D2H streamed)
+for m in 0 1 2; do
+  SB200_E2E_OVERLAP=$m timeout 300 python bench.py --steps 3 --warmup 3 > $OUT/r2c1_bench_e2e$m.json 2> $OUT/r2c1_bench_e2e$m.err
+  grep -o '"e2e": {[^}]*}' $OUT/r2c1_bench_e2e$m.json | cut -c1-200
+  stamp bench_e2e$m
+done
+# 5. N = 1 at the metric's size (n = 65536 fits one B200: 16 GiB of lower tiles)
+timeout 400 python bench.py --routine potrf --size 65536 --steps 2 --warmup 3 --no-e2e > $OUT/r2c1_bench_potrf_n65536.json 2> $OUT/r2c1_bench_potrf_n65536.err
+tail -1 $OUT/r2c1_bench_potrf_n65536.json | cut -c1-300; tail -3 $OUT/r2c1_bench_potrf_n65536.err
+stamp bench_n65536
+# 6. refreshed launch list of the default bench command (profiles/r01_launches_potrf_summary.txt predates the fast diagonal kernels)
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/r2c1_launches_potrf.csv \
+    python bench.py --steps 1 --warmup 1 --no-e2e --size 8192 > $OUT/r2c1_ncu_launches.log 2>&1
+stamp ncu_launches

@@ -1,0 +1,14 @@
+"""CPU check (no GPU) of the index arithmetic of the opt-in fused tile kernels (slate_b200/csrc/potrf_tile_fused.cu):
+scratch/emulate_fused.py transcribes the loaders, the DMMA / FP32 product micro-kernels and the three block algorithms
+thread by thread into numpy and compares them with dense references (ragged sizes included)."""
+import importlib.util
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fused_kernels_index_arithmetic_emulation():
+    spec = importlib.util.spec_from_file_location("emulate_fused", os.path.join(ROOT, "scratch", "emulate_fused.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
