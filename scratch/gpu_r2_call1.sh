@@ -16,14 +16,14 @@ for f in test_zzz_gpu_round2_candidates test_zzz_gpu_dist_solve; do
   stamp $f
 done
 # 2. latched switches: the existing parity tests under each of them (fresh process per switch)
-for sw in SB200_DIAG_RSQRT SB200_DIAG_WARP SB200_PANEL_BARRIER; do
+for sw in SB200_DIAG_RSQRT SB200_DIAG_WARP SB200_PANEL_BARRIER SB200_PANEL_LL; do
   env $sw=1 timeout 300 python -m pytest tests/test_zz_gpu_panel_variants.py tests/test_gpu_drivers.py -m gpu -q --timeout 120 -n 4 \
       > $OUT/r2c1_switch_$sw.log 2>&1
   echo "pytest exit $?" >> $OUT/r2c1_switch_$sw.log; tail -6 $OUT/r2c1_switch_$sw.log | cut -c1-240
   stamp $sw
 done
 # 3. timings of every variant (one fresh process each), phases on stderr
-for r in potrf getrf posv_mixed; do
+for r in potrf getrf posv_mixed gesv_mixed; do
   timeout 900 python scratch/perf_variants.py $r 32768 512 > $OUT/r2c1_perf_$r.log 2> $OUT/r2c1_perf_$r.err
   cat $OUT/r2c1_perf_$r.log | cut -c1-300
   stamp perf_$r

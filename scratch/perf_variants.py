@@ -19,10 +19,14 @@ POTRF = [("default", {}),
          ("tile_rsqrt+trsm_fused", {"SB200_TILE_FUSED": "2", "SB200_TRSM_FUSED": "1"})]
 GETRF = [("default", {}),
          ("panel_barrier", {"SB200_PANEL_BARRIER": "1"}),
+         ("panel_ll", {"SB200_PANEL_LL": "1"}),
+         ("panel_ll+row_trsm_fused", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "2"}),
          ("row_trsm_fused", {"SB200_TRSM_FUSED": "2"}),
          ("barrier+row_trsm_fused", {"SB200_PANEL_BARRIER": "1", "SB200_TRSM_FUSED": "2"})]
 MIXED = [("default", {}),
          ("tile+trsm_fused", {"SB200_TILE_FUSED": "1", "SB200_TRSM_FUSED": "3"})]
+GMIXED = [("default", {}),
+          ("panel_ll+row_trsm_fused", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "2"})]
 
 
 def one(routine, n, nb):
@@ -38,6 +42,11 @@ def one(routine, n, nb):
         fl = 2 * n ** 3 / 3 - n * n / 2 + 5 * n / 6
         A0 = sl.Matrix(n, n, nb).generate("rand", 42); A = sl.Matrix(n, n, nb)
         fn = lambda: sl.getrf(A)
+    elif routine == "gesv_mixed":
+        fl = 2 * n ** 3 / 3
+        A0 = sl.Matrix(n, n, nb).generate("rand", 42); A = sl.Matrix(n, n, nb)
+        B = sl.Matrix(n, 10, nb).generate("rand", 43); X = sl.Matrix(n, 10, nb)
+        fn = lambda: sl.gesv_mixed(A, B, X)
     else:                                                   # posv_mixed: the FP32 factor is the chain there
         fl = n ** 3 / 3
         A0 = sl.HermitianMatrix(n, nb).generate("rand_dominant", 42); A = sl.HermitianMatrix(n, nb)
@@ -52,12 +61,13 @@ def one(routine, n, nb):
         ev0.record()
         out = fn()
         ev1.record(); torch.cuda.synchronize()
-        ms = A.last_driver_ms if routine != "posv_mixed" else ev0.elapsed_time(ev1)
+        mixed = routine in ("posv_mixed", "gesv_mixed")
+        ms = A.last_driver_ms if not mixed else ev0.elapsed_time(ev1)
         best = min(best, ms)
-        if routine == "posv_mixed":
-            tms = out[2]
+        if mixed:
+            tms = out[-1]
     print(json.dumps({"routine": routine, "n": n, "nb": nb, "best_ms": round(best, 2), "tflops": round(fl / best / 1e9, 2),
-                      "panel_ms": round(A.last_panel_ms, 1) if routine != "posv_mixed" else None, "timers": tms,
+                      "panel_ms": round(A.last_panel_ms, 1) if not mixed else None, "timers": tms,
                       "env": {k: v for k, v in os.environ.items() if k.startswith("SB200_") and k != "SB200_PHASES"}}), flush=True)
 
 
@@ -68,7 +78,7 @@ if __name__ == "__main__":
     routine = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
     nb = int(sys.argv[3]) if len(sys.argv) > 3 else 512
-    for tag, env in {"potrf": POTRF, "getrf": GETRF, "posv_mixed": MIXED}[routine]:
+    for tag, env in {"potrf": POTRF, "getrf": GETRF, "posv_mixed": MIXED, "gesv_mixed": GMIXED}[routine]:
         e = dict(os.environ); e.update(env)
         print(f"## {routine} {tag}", flush=True)
         sys.stderr.write(f"## {routine} {tag}\n"); sys.stderr.flush()

@@ -14,6 +14,10 @@ struct PanelScratch {
     double* W = nullptr;            // trsm workspace of the panel stream
     unsigned* bar = nullptr;        // arrival counter of the opt-in hand-rolled grid barrier (SB200_PANEL_BARRIER=1)
     bool use_bar = false;
+    unsigned long long* ll = nullptr;   // exchange buffers of the opt-in flag-in-data base kernel (SB200_PANEL_LL=1)
+    unsigned gen_base = 0;              // generation tag of the next launch's first column, minus 1
+    bool use_ll = false;
+    size_t ll_bytes = 0;
     int max_ctas = 0;
     void* raw = nullptr;
     int init();

@@ -9,6 +9,10 @@
 * `potrf(A, in_local=..., out_local=...)` -- input AND output stream between pinned host memory and the device in chunks
   of block columns while the factorisation runs (`sb200_potrf_stream_*`, csrc/runtime.cu): bitwise the default factor.
 
+* SB200_PANEL_LL=1 -- LU panel base kernel whose per-column exchange (candidates, diagonal row, winner's row) travels as
+  {data | generation tag} 8-byte words instead of stores + fence + grid barrier (csrc/getrf.cu, getrf_base_ll_kernel):
+  identical pivots and factors.
+
 Written after round 1's GPU budget was spent: SKIPPED unless SB200_RUN_UNVALIDATED=1 (round 2: run, fix, drop the guard,
 then make the winner the default)."""
 import os
@@ -245,3 +249,66 @@ def test_potrf_streaming_reports_info(sl):
     A.to_host_local(hin)
     B = sl.HermitianMatrix(n, nb)
     assert sl.potrf(B, in_local=hin) == 701
+
+
+@pytest.mark.parametrize("dist", ["0", "1"])
+@pytest.mark.parametrize("panel", ["1", "2"])
+@pytest.mark.parametrize("m,n,nb", [(1024, 1024, 256), (700, 700, 128), (2048, 2048, 512), (700, 300, 128), (300, 700, 128),
+                                    (1100, 1100, 512)])
+def test_getrf_ll_panel_identical_pivots(sl, m, n, nb, panel, dist, monkeypatch):
+    monkeypatch.setenv("SB200_PANEL_LL", "1")
+    monkeypatch.setenv("SB200_PANEL", panel)
+    monkeypatch.setenv("SB200_GETRF_DIST", dist)
+    A = sl.Matrix(m, n, nb).generate("rand", 42)
+    piv, info = sl.getrf(A)
+    A0 = o.generate("rand", m, n, 42)
+    LUo, pivo, info_o = o.getrf(A0, nb, 32)
+    assert info == info_o == 0
+    assert piv == pivo, "pivot vectors differ from the oracle's"
+    assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
+
+
+@pytest.mark.parametrize("panel", ["1", "2"])
+def test_getrf_ll_panel_zero_column_and_ties(sl, panel, monkeypatch):
+    monkeypatch.setenv("SB200_PANEL_LL", "1")
+    monkeypatch.setenv("SB200_PANEL", panel)
+    n, nb = 256, 64
+    A0 = o.generate("rand", n, n, 3); A0[:, 100] = 0.0
+    A = sl.Matrix(n, n, nb); A.from_host(np.asfortranarray(A0))
+    _, info = sl.getrf(A)
+    assert info == o.getrf(A0, nb, 32)[2] == 101
+    # equal magnitudes everywhere: the first (lowest) row must win every tie, as in the reference's scan order
+    rng = np.random.default_rng(2)
+    S = np.sign(rng.random((n, n)) - 0.5) + 2 * np.eye(n) * 0          # entries +-1
+    B = sl.Matrix(n, n, nb); B.from_host(np.asfortranarray(S))
+    piv, info = sl.getrf(B)
+    LUo, pivo, info_o = o.getrf(S, nb, 32)
+    assert info == info_o
+    assert piv == pivo
+
+
+def test_getrf_ll_panel_tall_many_ctas_and_same_bits_as_default(sl, monkeypatch):
+    """m_p = 8192 rows: 11 + 1 CTAs exchange through the tagged words; the factor must be BITWISE the default kernel's
+    (same pivots => same arithmetic in the same order)."""
+    import torch
+    n, nb = 8192, 512
+    A = sl.Matrix(n, n, nb).generate("rand", 42)
+    piv0, info0 = sl.getrf(A)
+    h0 = torch.empty(A.local_tiles * nb * nb, dtype=torch.float64).pin_memory(); A.to_host_local(h0)
+    monkeypatch.setenv("SB200_PANEL_LL", "1")
+    B = sl.Matrix(n, n, nb).generate("rand", 42)
+    piv1, info1 = sl.getrf(B)
+    h1 = torch.empty(B.local_tiles * nb * nb, dtype=torch.float64).pin_memory(); B.to_host_local(h1)
+    assert info0 == info1 == 0 and piv0 == piv1
+    assert torch.equal(h0.view(torch.uint8), h1.view(torch.uint8))
+
+
+def test_gesv_mixed_with_ll_panel(sl, monkeypatch):
+    monkeypatch.setenv("SB200_PANEL_LL", "1")
+    n, nb = 2048, 512
+    A = sl.Matrix(n, n, nb).generate("rand", 42)
+    B = sl.Matrix(n, 10, nb).generate("rand", 43)
+    X = sl.Matrix(n, 10, nb)
+    info, it, piv, tm = sl.gesv_mixed(A, B, X)
+    assert info == 0 and 0 <= it <= 30
+    assert o.solve_residual(o.generate("rand", n, n, 42), X.to_host(), o.generate("rand", n, 10, 43)) <= 25 * EPS
