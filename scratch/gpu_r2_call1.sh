@@ -10,14 +10,26 @@ stamp start
 # 1. smoke + the guarded candidate tests (each file separately so that one failure does not hide the others)
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/r2c1_smoke.log 2>&1; tail -2 $OUT/r2c1_smoke.log
 stamp smoke
-for f in test_zzz_gpu_round2_candidates test_zzz_gpu_dist_solve; do
-  SB200_RUN_UNVALIDATED=1 timeout 420 python -m pytest tests/$f.py -m gpu -q --timeout 120 -n 4 > $OUT/r2c1_$f.log 2>&1
-  echo "pytest exit $?" >> $OUT/r2c1_$f.log; tail -25 $OUT/r2c1_$f.log | cut -c1-240
-  stamp $f
-done
+# groups in order of increasing risk of a hang (spin-wait protocols last); --timeout-method=thread makes pytest-timeout
+# os._exit() a worker that is stuck inside a CUDA call, and the outer timeout -k kills whatever is left
+PT="python -m pytest -m gpu -q --timeout 90 --timeout-method=thread -n 4"
+C=tests/test_zzz_gpu_round2_candidates.py
+run_group() {   # name, pytest args...
+  local name=$1; shift
+  SB200_RUN_UNVALIDATED=1 timeout -k 10 400 $PT "$@" > $OUT/r2c1_$name.log 2>&1
+  echo "pytest exit $?" >> $OUT/r2c1_$name.log; tail -12 $OUT/r2c1_$name.log | cut -c1-240
+  stamp $name
+}
+run_group dist_solve tests/test_zzz_gpu_dist_solve.py
+run_group streaming  $C -k "streaming"
+run_group trsm_fused $C -k "fused_panel_trsm or fused_row_trsm or fused_row_solve"
+run_group tile_fused $C -k "fused_tile"
+run_group panel_ll   $C -k "ll_panel"
+run_group all_fused  $C -k "all_fused or tile_and_panel_solve"
+nvidia-smi --query-gpu=utilization.gpu,memory.used --format=csv,noheader | tee -a $OUT/r2c1_timeline.txt   # nothing may be left running
 # 2. latched switches: the existing parity tests under each of them (fresh process per switch)
 for sw in SB200_DIAG_RSQRT SB200_DIAG_WARP SB200_PANEL_BARRIER SB200_PANEL_LL; do
-  env $sw=1 timeout 300 python -m pytest tests/test_zz_gpu_panel_variants.py tests/test_gpu_drivers.py -m gpu -q --timeout 120 -n 4 \
+  env $sw=1 timeout -k 10 300 python -m pytest tests/test_zz_gpu_panel_variants.py tests/test_gpu_drivers.py -m gpu -q --timeout 90 --timeout-method=thread -n 4 \
       > $OUT/r2c1_switch_$sw.log 2>&1
   echo "pytest exit $?" >> $OUT/r2c1_switch_$sw.log; tail -6 $OUT/r2c1_switch_$sw.log | cut -c1-240
   stamp $sw
