@@ -123,6 +123,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// Watchdog for the spin-wait protocols between CTAs (flags of the fused tile Cholesky, tagged words and the arrival
+// counter of the LU base kernels): a wait that lasts seconds is a protocol bug, and a kernel that spins forever takes
+// the GPU down with it, so trap instead (the launch then fails with a CUDA error the host sees).
+// 2^33 cycles = 4.4 s at 1.965 GHz; a legitimate wait is at most the time for a co-scheduled CTA to get an SM slot.
+__device__ __forceinline__ void spin_watchdog(long long t0)
+{
+    if (clock64() - t0 > (1LL << 33)) __trap();
+}
 #endif // __CUDACC__
 
 } // namespace sb200

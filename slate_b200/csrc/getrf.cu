@@ -182,7 +182,8 @@ getrf_base_kernel(const BaseArgs<T> a)
                 atomicAdd(a.bar, 1u);
                 const unsigned target = unsigned(j + 1) * gridDim.x;
                 unsigned seen;
-                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.bar) : "memory"); } while (seen < target);
+                const long long t0 = clock64();
+                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.bar) : "memory"); spin_watchdog(t0); } while (seen < target);
             }
             __syncthreads();
             __threadfence();          // every thread orders its reads of the other CTAs' candidates after the release it waited for
@@ -299,7 +300,12 @@ __device__ __forceinline__ unsigned long long ll_load(const unsigned long long* 
 __device__ __forceinline__ double ll_wait_double(const unsigned long long* p, unsigned gen)
 {
     unsigned long long lo, hi;
-    do { lo = ll_load(p); hi = ll_load(p + 1); } while (unsigned(lo >> 32) != gen || unsigned(hi >> 32) != gen);
+    const long long t0 = clock64();
+    for (;;) {
+        lo = ll_load(p); hi = ll_load(p + 1);
+        if (unsigned(lo >> 32) == gen && unsigned(hi >> 32) == gen) break;
+        spin_watchdog(t0);
+    }
     return __hiloint2double(int(unsigned(hi)), int(unsigned(lo)));
 }
 __device__ __forceinline__ void ll_store_double(unsigned long long* p, double v, unsigned gen)
@@ -389,8 +395,12 @@ getrf_base_ll_kernel(const LLArgs<T> q)
         for (int c = tid; c < G; c += PTHREADS) {               // G <= PTHREADS - 32 in practice: one record per thread
             const unsigned long long* r = rec + (size_t(par) * G + c) * 4;
             unsigned long long w0, w1, w2;
-            do { w0 = ll_load(r); w1 = ll_load(r + 1); w2 = ll_load(r + 2); }
-            while (unsigned(w0 >> 32) != gen || unsigned(w1 >> 32) != gen || unsigned(w2 >> 32) != gen);
+            const long long t0 = clock64();
+            for (;;) {
+                w0 = ll_load(r); w1 = ll_load(r + 1); w2 = ll_load(r + 2);
+                if (unsigned(w0 >> 32) == gen && unsigned(w1 >> 32) == gen && unsigned(w2 >> 32) == gen) break;
+                spin_watchdog(t0);
+            }
             const double v = __hiloint2double(int(unsigned(w1)), int(unsigned(w0)));
             const int rr = int(unsigned(w2));
             if (v > bv || (v == bv && rr < br)) { bv = v; br = rr; bw = c; }

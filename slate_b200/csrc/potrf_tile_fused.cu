@@ -57,7 +57,8 @@ __device__ __forceinline__ unsigned wait_flag(const unsigned* p, unsigned target
 {
     if (threadIdx.x == 0) {
         unsigned v;
-        while ((v = ld_acquire_u32(p)) < target) __nanosleep(40);
+        const long long t0 = clock64();
+        while ((v = ld_acquire_u32(p)) < target) { __nanosleep(40); spin_watchdog(t0); }
         *s_v = v;
     }
     __syncthreads();
