@@ -21,12 +21,14 @@ GETRF = [("default", {}),
          ("panel_barrier", {"SB200_PANEL_BARRIER": "1"}),
          ("panel_ll", {"SB200_PANEL_LL": "1"}),
          ("panel_ll+row_trsm_fused", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "2"}),
+         ("small_trsm_direct", {"SB200_TRSM_FUSED": "4"}),
+         ("panel_ll+all_row_solves", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6"}),
          ("row_trsm_fused", {"SB200_TRSM_FUSED": "2"}),
          ("barrier+row_trsm_fused", {"SB200_PANEL_BARRIER": "1", "SB200_TRSM_FUSED": "2"})]
 MIXED = [("default", {}),
          ("tile+trsm_fused", {"SB200_TILE_FUSED": "1", "SB200_TRSM_FUSED": "3"})]
 GMIXED = [("default", {}),
-          ("panel_ll+row_trsm_fused", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "2"})]
+          ("panel_ll+all_row_solves", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6"})]
 
 
 def one(routine, n, nb):

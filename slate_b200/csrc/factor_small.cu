@@ -27,6 +27,11 @@ int trsm_rlt_fused_d(int m, int na, double alpha, const double* Tm, int ldt, con
                      int64_t offB, int ldb, int batch, cudaStream_t stream);
 int trsm_rlt_fused_s(int m, int na, float alpha, const float* Tm, int ldt, const float* W, float* const* dB,
                      int64_t offB, int ldb, int batch, cudaStream_t stream);
+// opt-in direct substitution for a small triangle, na <= 64 (SB200_TRSM_FUSED bit 2)
+int trsm_lln_small_d(int na, int n, double alpha, bool unit, const double* Tm, int ldt, double* const* dB, int64_t offB,
+                     int ldb, int batch, cudaStream_t stream);
+int trsm_lln_small_s(int na, int n, float alpha, bool unit, const float* Tm, int ldt, float* const* dB, int64_t offB,
+                     int ldb, int batch, cudaStream_t stream);
 // opt-in one-launch LU row solve B <- alpha L^{-1} B (SB200_TRSM_FUSED bit 1)
 int trsm_lln_fused_d(int na, int n, double alpha, const double* Tm, int ldt, const double* W, double* const* dB,
                      int64_t offB, int ldb, int batch, cudaStream_t stream);
@@ -506,12 +511,21 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
     const int na = left ? m : n;
     const int nblk = int(ceil_div(na, IB));
     small_kernels_init<T>();
+    if constexpr (IsRealType<T>::value) {
+        // opt-in (round-2 candidate, not yet run): bit 2 = a small triangle (na <= 64: the U12 solves inside the LU panel)
+        // by direct substitution in one launch, no inversion kernel
+        const char* e = getenv("SB200_TRSM_FUSED");
+        if (e && (atoi(e) & 4) && left && lower && op == 'N' && na <= IB) {
+            if constexpr (std::is_same<T, double>::value) return trsm_lln_small_d(na, n, alpha, unit, Tm, ldt, dB, offB, ldb, batch, stream);
+            else                                          return trsm_lln_small_s(na, n, alpha, unit, Tm, ldt, dB, offB, ldb, batch, stream);
+        }
+    }
     int st = launch_trtri_diag<T>(nblk, Tm, ldt, na, lower ? 1 : 0, unit ? 1 : 0, W, stream);
     if (st) return st;
     if constexpr (IsRealType<T>::value) {
         // opt-in (round-2 candidates, not yet run; potrf_tile_fused.cu): one launch after the inverses for
         //   bit 0: the Cholesky panel solve (Right, Lower, Trans, NonUnit)
-        //   bit 1: the LU row solve (Left, Lower, NoTrans, Unit / NonUnit)
+        //   bit 1: the LU row solve (Left, Lower, NoTrans, Unit / NonUnit)      (bit 2: see above)
         // read per call so that a test can switch it
         const char* e = getenv("SB200_TRSM_FUSED");
         const int fused = e ? atoi(e) : 0;

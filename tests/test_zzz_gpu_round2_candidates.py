@@ -312,3 +312,39 @@ def test_gesv_mixed_with_ll_panel(sl, monkeypatch):
     info, it, piv, tm = sl.gesv_mixed(A, B, X)
     assert info == 0 and 0 <= it <= 30
     assert o.solve_residual(o.generate("rand", n, n, 42), X.to_host(), o.generate("rand", n, 10, 43)) <= 25 * EPS
+
+
+@pytest.mark.parametrize("t", ["d", "s"])
+@pytest.mark.parametrize("diag", ["U", "N"])
+@pytest.mark.parametrize("m,n", [(32, 32), (64, 64), (20, 100), (64, 300), (32, 1), (33, 512), (1, 7)])
+def test_fused_row_trsm_small_triangle_direct_substitution(monkeypatch, t, diag, m, n):
+    """SB200_TRSM_FUSED bit 2: na <= 64 (the U12 solves inside the recursive LU panel) by direct substitution."""
+    from tests.gpu_util import DevTiles, fn, scal, stream, rng_tiles, NP, SC, c_int, c_i64, c_ptr
+    monkeypatch.setenv("SB200_TRSM_FUSED", "4")
+    rng = np.random.default_rng(4)
+    batch = 2
+    T = (rng.random((m, m)) / m + np.eye(m) * (1 + rng.random(m))).astype(NP[t])
+    B = rng_tiles(rng, batch, m, n, t)
+    alpha = 0.7
+    ref = [o.trsm_tile("L", "L", "N", diag, alpha, T.astype(np.float64), b.astype(np.float64)) for b in B]
+    dT, dB = DevTiles([T]), DevTiles(B)
+    f = fn(f"sb200_trsm_batched_{t}", [c_int] * 5 + [c_i64, c_i64, SC[t], c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr])
+    assert f(ord("C"), ord("L"), ord("L"), ord("N"), ord(diag), m, n, scal(t, alpha), dT.t[0].data_ptr(), m,
+             dB.p, m, batch, None, stream()) == 0
+    eps = EPS if t == "d" else float(np.finfo(np.float32).eps)
+    for x, r in zip(dB.get(), ref):
+        assert np.abs(x - r).max() <= 200 * eps * np.abs(r).max()
+
+
+@pytest.mark.parametrize("panel", ["1", "2"])
+@pytest.mark.parametrize("m,n,nb", [(1024, 1024, 256), (2048, 2048, 512), (700, 300, 128), (1100, 1100, 512)])
+def test_getrf_with_all_row_solve_candidates_identical_pivots(sl, monkeypatch, m, n, nb, panel):
+    monkeypatch.setenv("SB200_TRSM_FUSED", "6")
+    monkeypatch.setenv("SB200_PANEL", panel)
+    A = sl.Matrix(m, n, nb).generate("rand", 42)
+    piv, info = sl.getrf(A)
+    A0 = o.generate("rand", m, n, 42)
+    LUo, pivo, info_o = o.getrf(A0, nb, 32)
+    assert info == info_o == 0
+    assert piv == pivo, "pivot vectors differ from the oracle's"
+    assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
