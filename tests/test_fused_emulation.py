@@ -12,3 +12,12 @@ def test_fused_kernels_index_arithmetic_emulation():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.main()
+
+
+def test_panel_ll_protocol_emulation():
+    """scratch/emulate_panel_ll.py: the tagged-slot exchange of getrf_base_ll_kernel (double-buffered by column parity, no
+    barrier) run by G threads with shuffled interleavings: no deadlock, pivots / factors of plain partial pivoting."""
+    spec = importlib.util.spec_from_file_location("emulate_panel_ll", os.path.join(ROOT, "scratch", "emulate_panel_ll.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
