@@ -42,6 +42,13 @@ def flops(routine: str, n: int) -> float:
     raise ValueError(routine)
 
 
+def _switches() -> dict:
+    """Library switches in effect (SB200_* environment): empty for the default paths, so that a line measured with an
+    opt-in candidate turned on says so."""
+    return {k: v for k, v in sorted(os.environ.items())
+            if k.startswith("SB200_") and k not in ("SB200_PHASES", "SB200_REFERENCE", "SB200_RUN_UNVALIDATED")}
+
+
 def default_n(routine: str, ngpus: int) -> int:
     # N = 1: the single-GPU configuration BASELINE.json names (configs[1], n = 32768);
     # N > 1: the n the headline metric is quoted on (n = 65536), fixed total work for N = 2, 4, 8.
@@ -455,7 +462,8 @@ def run_extra(args):
             "config": {"workload": f"{name} n={n} nb={nb}" + (f" nrhs={nrhs}" if mixed else "")
                                    + f", {grid.p}x{grid.q} block-cyclic grid over {world} B200",
                        "routine": routine, "n": n, "nb": nb, "grid": [grid.p, grid.q],
-                       "l2": "operands (GiBs) are far larger than the 126 MB L2; no explicit flush"},
+                       "l2": "operands (GiBs) are far larger than the 126 MB L2; no explicit flush",
+                       "switches": _switches()},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         }
         line["step_ms"] = step_ms
@@ -659,7 +667,8 @@ def main():
             "data": "synthetic (reference matgen: Philox-2x64 rand_dominant/rand, seed 42, generated on device)",
             "config": {"workload": f"d{routine} n={n} nb={nb} lookahead=1, {p}x{q} block-cyclic grid over {world} B200",
                        "routine": routine, "n": n, "nb": nb, "grid": [p, q],
-                       "l2": "inputs (>= 4 GiB per step) are far larger than the 126 MB L2; no explicit flush"},
+                       "l2": "inputs (>= 4 GiB per step) are far larger than the 126 MB L2; no explicit flush",
+                       "switches": _switches()},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches),
         }
