@@ -196,11 +196,13 @@ SB200_FOR_TYPES(SB200_DECL_POTRF)
  * (piv_tile[i], piv_off[i]) -- the reference's Pivot{tileIndex, elementOffset}
  * (include/slate/types.hh:84-105) -- applied in order i = 0..npiv-1 (forward) or reversed.
  * ------------------------------------------------------------------------- */
-int sb200_permute_rows_d(int layout, int forward, int64_t npiv,
-                         const int64_t* d_piv_tile, const int64_t* d_piv_off,
-                         double* const* dTiles, int64_t mt, int64_t ncolblocks,
-                         int64_t tile_mb, int64_t ncols, int64_t ld,
-                         sb200_stream_t stream);
+#define SB200_DECL_PERMUTE_ROWS(X, T, R) \
+int sb200_permute_rows_##X(int layout, int forward, int64_t npiv, \
+                           const int64_t* d_piv_tile, const int64_t* d_piv_off, \
+                           T* const* dTiles, int64_t mt, int64_t ncolblocks, \
+                           int64_t tile_mb, int64_t ncols, int64_t ld, \
+                           sb200_stream_t stream);
+SB200_FOR_TYPES(SB200_DECL_PERMUTE_ROWS)
 
 /* ---------------------------------------------------------------------------
  * Seam 2: memory-bound tile kernels (slate::device::*, include/slate/internal/device.hh:92-281).

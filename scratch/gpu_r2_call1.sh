@@ -21,7 +21,7 @@ run_group() {   # name, pytest args...
   stamp $name
 }
 run_group dist_solve tests/test_zzz_gpu_dist_solve.py
-run_group streaming  $C -k "streaming"
+run_group streaming  $C -k "streaming or permute_rows"
 run_group trsm_fused $C -k "fused_panel_trsm or fused_row_trsm or fused_row_solve or row_solve_candidates"
 run_group tile_fused $C -k "fused_tile"
 run_group panel_ll   $C -k "ll_panel"

@@ -1001,6 +1001,8 @@ template int getrf_panel<float>(float* const*, float*, int, int, int, int, int64
 
 template int launch_laswp<double>(double* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);
 template int launch_laswp<float>(float* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);
+template int launch_laswp<cuFloatComplex>(cuFloatComplex* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);
+template int launch_laswp<cuDoubleComplex>(cuDoubleComplex* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);
 
 } // namespace sb200
 
@@ -1031,17 +1033,23 @@ int sb200_getrf_tc05_s(sb200_matrix_t h, int64_t* pivots, const sb200_options_t*
     return getrf_driver_s(h->A, pivots, info, true);
 }
 
-int sb200_permute_rows_d(int layout, int forward, int64_t npiv,
-                         const int64_t* d_piv_tile, const int64_t* d_piv_off,
-                         double* const* dTiles, int64_t mt, int64_t ncolblocks,
-                         int64_t tile_mb, int64_t ncols, int64_t ld, sb200_stream_t stream)
-{
-    if (! valid_layout(layout) || npiv < 0 || mt < 1 || ncolblocks < 0 || tile_mb < 1 || ncols < 0) return SB200_EINVAL;
-    if (npiv == 0 || ncolblocks == 0 || ncols == 0) return SB200_OK;
-    if (npiv > 0x7fffffff || tile_mb > 0x7fffffff || ld > 0x7fffffff) return SB200_EINVAL;
-    // `ncols` columns per tile, block columns are `ncols` wide
-    return launch_laswp<double>(dTiles, mt, int(tile_mb), int(ncols), int(ld), layout == 'C', d_piv_tile, d_piv_off,
-                                0, int(npiv), forward != 0, 0, ncolblocks * ncols, cudaStream_t(stream));
+// one body for the four scalar types: pure data movement (sb200_permute_rows_{s,d,c,z})
+#define SB200_DEF_PERMUTE_ROWS(X, T, CT) \
+int sb200_permute_rows_##X(int layout, int forward, int64_t npiv, \
+                           const int64_t* d_piv_tile, const int64_t* d_piv_off, \
+                           T* const* dTiles, int64_t mt, int64_t ncolblocks, \
+                           int64_t tile_mb, int64_t ncols, int64_t ld, sb200_stream_t stream) \
+{ \
+    if (! valid_layout(layout) || npiv < 0 || mt < 1 || ncolblocks < 0 || tile_mb < 1 || ncols < 0) return SB200_EINVAL; \
+    if (npiv == 0 || ncolblocks == 0 || ncols == 0) return SB200_OK; \
+    if (npiv > 0x7fffffff || tile_mb > 0x7fffffff || ld > 0x7fffffff) return SB200_EINVAL; \
+    /* `ncols` columns per tile, block columns are `ncols` wide */ \
+    return launch_laswp<CT>(reinterpret_cast<CT* const*>(dTiles), mt, int(tile_mb), int(ncols), int(ld), layout == 'C', \
+                            d_piv_tile, d_piv_off, 0, int(npiv), forward != 0, 0, ncolblocks * ncols, cudaStream_t(stream)); \
 }
+SB200_DEF_PERMUTE_ROWS(s, float, float)
+SB200_DEF_PERMUTE_ROWS(d, double, double)
+SB200_DEF_PERMUTE_ROWS(c, sb200_c32, cuFloatComplex)
+SB200_DEF_PERMUTE_ROWS(z, sb200_c64, cuDoubleComplex)
 
 } // extern "C"

@@ -348,3 +348,42 @@ def test_getrf_with_all_row_solve_candidates_identical_pivots(sl, monkeypatch, m
     assert info == info_o == 0
     assert piv == pivo, "pivot vectors differ from the oracle's"
     assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
+
+
+@pytest.mark.parametrize("t", ["s", "c", "z"])
+@pytest.mark.parametrize("layout", ["C", "R"])
+def test_permute_rows_other_types(t, layout):
+    """sb200_permute_rows_{s,c,z}: the same launch_laswp template as the validated _d entry (internal_swap.cc:674-688)."""
+    import torch
+    from tests.gpu_util import DevTiles, fn, stream, NP, c_int, c_i64, c_ptr
+    rng = np.random.default_rng(6)
+    mt, ncb, mb, nc = 3, 2, 32, 24
+    M = rng.random((mt * mb, ncb * nc))
+    if t in "cz":
+        M = M + 1j * rng.random(M.shape)
+    M = M.astype(NP[t])
+    npiv = mb
+    piv = [(int(rng.integers(0, mt)), int(rng.integers(0, mb))) for _ in range(npiv)]
+    piv = [(ti, off) if ti * mb + off >= j else (0, j) for j, (ti, off) in enumerate(piv)]
+    ref = M.copy()
+    for j in range(npiv):
+        r2 = piv[j][0] * mb + piv[j][1]
+        ref[[j, r2]] = ref[[r2, j]]
+    tiles = []
+    for jb in range(ncb):
+        for tb in range(mt):
+            blk = M[tb * mb:(tb + 1) * mb, jb * nc:(jb + 1) * nc]
+            tiles.append(np.asfortranarray(blk if layout == "C" else blk.T))
+    d = DevTiles(tiles)
+    pt = torch.tensor([p[0] for p in piv], dtype=torch.int64, device="cuda")
+    po = torch.tensor([p[1] for p in piv], dtype=torch.int64, device="cuda")
+    f = fn(f"sb200_permute_rows_{t}", [c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr])
+    ld = mb if layout == "C" else nc
+    assert f(ord(layout), 1, npiv, pt.data_ptr(), po.data_ptr(), d.p, mt, ncb, mb, nc, ld, stream()) == 0
+    out = d.get()
+    got = np.zeros_like(M)
+    for jb in range(ncb):
+        for tb in range(mt):
+            blk = out[tb + jb * mt]
+            got[tb * mb:(tb + 1) * mb, jb * nc:(jb + 1) * nc] = blk if layout == "C" else blk.T
+    assert np.array_equal(got, ref)
