@@ -79,6 +79,50 @@ def load_block_t(dst, mem, src, lds, cv):
                 dst[k * FLD + j] = mem[src + k + j * lds] if j < cv else 0.0
 
 
+def chol64_smem(As, Ls, rd, NT, LD, rsq):
+    """diag64.cuh: chol64_smem, thread by thread; phases separated by the kernel's barriers"""
+    TC = NT // 16
+    fail = 0
+    for j in range(64):
+        d = As[j * LD + j]
+        if fail == 0 and not d > 0:
+            fail = j + 1
+        if rsq:
+            rinv = 1.0 / np.sqrt(d); diag = d * rinv
+        else:
+            diag = np.sqrt(d); rinv = 1.0 / diag
+        for tid in range(NT):                                   # scale phase
+            for r in range(j + tid, 64, NT):
+                Ls[j * LD + r] = diag if r == j else As[j * LD + r] * rinv
+            if tid == 0:
+                rd[j] = rinv
+        for tid in range(NT):                                   # update phase
+            tr, tc = tid & 15, tid >> 4
+            for c in range(j + 1 + tc, 64, TC):
+                lc = Ls[j * LD + c]
+                for r in range(c + tr, 64, 16):
+                    As[c * LD + r] -= Ls[j * LD + r] * lc
+    return fail
+
+
+def inv64_smem(Ls, rd, Xs, NT, LD):
+    TC = NT // 16
+    for tid in range(NT):
+        for e in range(tid, 64 * 64, NT):
+            r, c = e & 63, e >> 6
+            Xs[c * LD + r] = 1.0 if r == c else 0.0
+    for i in range(64):
+        for tid in range(NT):
+            if tid <= i:
+                Xs[tid * LD + i] *= rd[i]
+        for tid in range(NT):
+            tr, tc = tid & 15, tid >> 4
+            for j in range(tc, i + 1, TC):
+                xij = Xs[j * LD + i]
+                for r in range(i + 1 + tr, 64, 16):
+                    Xs[j * LD + r] -= Ls[i * LD + r] * xij
+
+
 def make(prec):
     P = ProdD if prec == "d" else ProdS
     mma = mma_d if prec == "d" else mma_s
@@ -132,16 +176,16 @@ def potrf_tile(A, n, lda, prec):
                 else:
                     v = 1.0 if row == col else 0.0
                 Cs[col * FLD + row] = v
-        D = np.array([[Cs[c * FLD + i] for c in range(FB)] for i in range(FB)])      # D[i][c], lower part meaningful
-        D = np.tril(D) + np.tril(D, -1).T
-        L = np.linalg.cholesky(D)
-        for i in range(rv):
-            for c in range(i + 1):
-                A[Ad + i + c * lda] = L[i, c]
-        Wr = np.linalg.inv(L)
-        for i in range(FB):
-            for j in range(FB):
-                W[r * FB * FB + i + j * FB] = Wr[i, j]
+        rd = np.zeros(FB)
+        fail = chol64_smem(Cs, Xs, rd, FT, FLD, False)            # D in Cs -> L in Xs
+        assert fail == 0
+        for e in range(FB * FB):
+            row, col = e & (FB - 1), e >> 6
+            if col <= row and row < rv:
+                A[Ad + row + col * lda] = Xs[col * FLD + row]
+        inv64_smem(Xs, rd, Ys, FT, FLD)
+        for e in range(FB * FB):
+            W[r * FB * FB + e] = Ys[(e >> 6) * FLD + (e & (FB - 1))]
 
 
 def trsm_rlt(B, m, na, ldb, alpha, T, ldt, prec):
@@ -231,6 +275,28 @@ def trsm_lln(B, na, n, ldb, alpha, T, ldt, unit, prec):
 
 def main():
     rng = np.random.default_rng(1)
+    # stand-alone multi-warp diagonal kernels (256 threads, LD = 65): L and the full inverse, both forms of the pivot
+    for rsq in (False, True):
+        G = rng.random((64, 64)); S = G @ G.T + 64 * np.eye(64)
+        LD = 65
+        As = np.zeros(64 * LD); Ls = np.zeros(64 * LD); rd = np.zeros(64); Xs = np.full(64 * LD, 3.0)
+        for c in range(64):
+            for r in range(64):
+                As[c * LD + r] = S[r, c] if c <= r else 0.0
+        assert chol64_smem(As, Ls, rd, 256, LD, rsq) == 0
+        L = np.array([[Ls[c * LD + r] if c <= r else 0.0 for c in range(64)] for r in range(64)])
+        ref = np.linalg.cholesky(S)
+        assert np.abs(L - ref).max() < 1e-13 * np.abs(ref).max()
+        inv64_smem(Ls, rd, Xs, 256, LD)
+        X = np.array([[Xs[c * LD + r] for c in range(64)] for r in range(64)])
+        assert np.abs(X - np.linalg.inv(ref)).max() < 1e-12 * np.abs(X).max() and (np.triu(X, 1) == 0).all()
+    S = np.eye(64); S[40, 40] = -1.0
+    As = np.zeros(64 * 65)
+    for c in range(64):
+        for r in range(c, 64):
+            As[c * 65 + r] = S[r, c]
+    assert chol64_smem(As, np.zeros(64 * 65), np.zeros(64), 256, 65, False) == 41
+    print("chol64_smem / inv64_smem (multi-warp diagonal block): OK")
     for prec in ("d", "s"):
         # every (row, col) of the 64 x 64 block is owned by exactly one accumulator
         pr, _ = make(prec)

@@ -21,6 +21,7 @@ run_group() {   # name, pytest args...
   stamp $name
 }
 run_group dist_solve tests/test_zzz_gpu_dist_solve.py
+run_group diag_mw    $C -k "diag_mw"
 run_group streaming  $C -k "streaming or permute_rows"
 run_group trsm_fused $C -k "fused_panel_trsm or fused_row_trsm or fused_row_solve or row_solve_candidates"
 run_group tile_fused $C -k "fused_tile"
@@ -54,3 +55,14 @@ stamp bench_n65536
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/r2c1_launches_potrf.csv \
     python bench.py --steps 1 --warmup 1 --no-e2e --size 8192 > $OUT/r2c1_ncu_launches.log 2>&1
 stamp ncu_launches
+# 7. per-launch durations of the candidates themselves (one pass, no replay): potrf n=2048 (4 diagonal tiles) with the fused
+#    tile + panel solve, getrf n=4096 with the LL panel + fused row solves
+SB200_DIAG_MW=1 SB200_TILE_FUSED=1 SB200_TRSM_FUSED=1 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file $OUT/r2c1_launches_potrf2048_fused.csv python scratch/prof_potrf_small.py > $OUT/r2c1_ncu_fused.log 2>&1
+SB200_DIAG_MW=1 SB200_PANEL_LL=1 SB200_TRSM_FUSED=6 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file $OUT/r2c1_launches_getrf4096_ll.csv python scratch/prof_getrf_small.py > $OUT/r2c1_ncu_ll.log 2>&1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file $OUT/r2c1_launches_getrf4096_default.csv python scratch/prof_getrf_small.py > $OUT/r2c1_ncu_getrf_default.log 2>&1
+python scratch/launch_summary.py $OUT/r2c1_launches_potrf.csv $OUT/r2c1_launches_potrf2048_fused.csv $OUT/r2c1_launches_getrf4096_ll.csv \
+    $OUT/r2c1_launches_getrf4096_default.csv > $OUT/r2c1_launch_summaries.txt 2>&1; head -60 $OUT/r2c1_launch_summaries.txt
+stamp ncu_candidates

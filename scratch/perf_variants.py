@@ -12,23 +12,29 @@ sys.path.insert(0, ROOT)
 POTRF = [("default", {}),
          ("diag_rsqrt", {"SB200_DIAG_RSQRT": "1"}),
          ("diag_warp", {"SB200_DIAG_WARP": "1"}),
+         ("diag_mw", {"SB200_DIAG_MW": "1"}),
+         ("diag_mw_rsqrt", {"SB200_DIAG_MW": "2"}),
+         ("diag_mw+trsm_fused", {"SB200_DIAG_MW": "1", "SB200_TRSM_FUSED": "1"}),
          ("tile_fused", {"SB200_TILE_FUSED": "1"}),
          ("tile_fused_rsqrt", {"SB200_TILE_FUSED": "2"}),
          ("trsm_fused", {"SB200_TRSM_FUSED": "1"}),
          ("tile+trsm_fused", {"SB200_TILE_FUSED": "1", "SB200_TRSM_FUSED": "1"}),
          ("tile_rsqrt+trsm_fused", {"SB200_TILE_FUSED": "2", "SB200_TRSM_FUSED": "1"})]
 GETRF = [("default", {}),
+         ("diag_mw", {"SB200_DIAG_MW": "1"}),
          ("panel_barrier", {"SB200_PANEL_BARRIER": "1"}),
          ("panel_ll", {"SB200_PANEL_LL": "1"}),
          ("panel_ll+row_trsm_fused", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "2"}),
          ("small_trsm_direct", {"SB200_TRSM_FUSED": "4"}),
          ("panel_ll+all_row_solves", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6"}),
+         ("panel_ll+all_row_solves+diag_mw", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1"}),
          ("row_trsm_fused", {"SB200_TRSM_FUSED": "2"}),
          ("barrier+row_trsm_fused", {"SB200_PANEL_BARRIER": "1", "SB200_TRSM_FUSED": "2"})]
 MIXED = [("default", {}),
-         ("tile+trsm_fused", {"SB200_TILE_FUSED": "1", "SB200_TRSM_FUSED": "3"})]
+         ("diag_mw", {"SB200_DIAG_MW": "1"}),
+         ("tile+trsm_fused+diag_mw", {"SB200_TILE_FUSED": "1", "SB200_TRSM_FUSED": "3", "SB200_DIAG_MW": "1"})]
 GMIXED = [("default", {}),
-          ("panel_ll+all_row_solves", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6"})]
+          ("panel_ll+all_row_solves+diag_mw", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1"})]
 
 
 def one(routine, n, nb):

@@ -13,6 +13,7 @@
 // conditioning of the IB x IB diagonal blocks only.
 #include "gemm_dmma.cuh"
 #include "scalar_ops.cuh"
+#include "diag64.cuh"
 #include <cstdlib>
 #include <type_traits>
 
@@ -412,6 +413,90 @@ trtri_diag_fast_kernel(const R* __restrict__ Tm, int ldt, int na, int lower, int
     store_inverse<R>(Ls, x, tid, W + int64_t(b) * IB * IB, lower == 0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-warp variants of the two diagonal-block kernels (opt-in: SB200_DIAG_MW=1 | 2; round-2 candidates, not yet
+// run): same contracts as potrf_diag_fast_kernel / trtri_diag_fast_kernel, the 64 x 64 block lives in shared memory
+// and all 256 threads work on it with rolled loops (diag64.cuh explains why: the register kernels above run at
+// 15-19 cycles per instruction).
+// ---------------------------------------------------------------------------------------------
+constexpr int MW_THREADS = 256;
+constexpr int MW_LD = IB + 1;
+template <typename R> constexpr size_t mw_smem() { return (size_t(2) * IB * MW_LD + IB) * sizeof(R); }
+
+template <typename R, bool RSQ>
+__global__ void __launch_bounds__(MW_THREADS)
+potrf_diag_mw_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv, int* __restrict__ info, int info_base)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    R* As = reinterpret_cast<R*>(smem_dyn);        // work matrix, later the inverse
+    R* Ls = As + IB * MW_LD;                       // L
+    R* rd = Ls + IB * MW_LD;                       // reciprocal diagonal
+    const int tid = threadIdx.x;
+    if (*info != 0) return;                        // an earlier block already failed: leave the tile alone
+    for (int e = tid; e < IB * IB; e += MW_THREADS) {
+        const int r = e % IB, c = e / IB;
+        As[c * MW_LD + r] = (r < nv && c < nv) ? (c <= r ? A[r + int64_t(c) * lda] : R(0)) : (r == c ? R(1) : R(0));
+    }
+    __syncthreads();
+    const int fail = chol64_smem<R, MW_THREADS, MW_LD, RSQ>(As, Ls, rd, tid);
+    if (fail) {
+        if (tid == 0 && *info == 0) *info = info_base + fail;
+        return;
+    }
+    for (int e = tid; e < IB * IB; e += MW_THREADS) {
+        const int r = e % IB, c = e / IB;
+        if (c <= r && r < nv) A[r + int64_t(c) * lda] = Ls[c * MW_LD + r];
+    }
+    inv64_smem<R, MW_THREADS, MW_LD>(Ls, rd, As, tid);
+    for (int e = tid; e < IB * IB; e += MW_THREADS) Winv[e] = As[(e / IB) * MW_LD + (e % IB)];      // W[i + j*IB] = X_ij
+}
+
+template <typename R>
+__global__ void __launch_bounds__(MW_THREADS)
+trtri_diag_mw_kernel(const R* __restrict__ Tm, int ldt, int na, int lower, int unit, R* __restrict__ W,
+                     const R* const* __restrict__ Tarr = nullptr, int na_last = 0)
+{
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    R* Xs = reinterpret_cast<R*>(smem_dyn);
+    R* Ls = Xs + IB * MW_LD;
+    R* rd = Ls + IB * MW_LD;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (Tarr) {
+        Tm = Tarr[blockIdx.y];
+        W += int64_t(blockIdx.y) * gridDim.x * IB * IB;
+        if (blockIdx.y == gridDim.y - 1) na = na_last;
+    }
+    const int o = b * IB;
+    const int nv = max(0, min(IB, na - o));
+    // always handled as LOWER: upper blocks are transposed in
+    for (int e = tid; e < IB * IB; e += MW_THREADS) {
+        const int i = e % IB, j = e / IB;              // for an upper block the transposing read is strided: 32 KB, once
+        R v = (i == j) ? R(1) : R(0);
+        if (i < nv && j < nv) {
+            if (i > j)                v = lower ? Tm[o + i + int64_t(o + j) * ldt] : Tm[o + j + int64_t(o + i) * ldt];
+            else if (i == j && !unit) v = Tm[o + i + int64_t(o + j) * ldt];
+        }
+        Ls[j * MW_LD + i] = v;
+        if (i == j) rd[i] = R(1) / v;
+    }
+    __syncthreads();
+    inv64_smem<R, MW_THREADS, MW_LD>(Ls, rd, Xs, tid);
+    R* Wb = W + int64_t(b) * IB * IB;
+    // inverse of the transpose = transpose of the inverse
+    for (int e = tid; e < IB * IB; e += MW_THREADS) {
+        const int i = e % IB, j = e / IB;
+        Wb[e] = lower ? Xs[j * MW_LD + i] : Xs[i * MW_LD + j];
+    }
+}
+
+// SB200_DIAG_MW (read per call so that a test can switch it): 0 = register kernels, 1 = multi-warp (sqrt + reciprocal),
+// 2 = multi-warp with one rsqrt per column
+static int diag_mw_mode()
+{
+    const char* e = getenv("SB200_DIAG_MW");
+    return e ? atoi(e) : 0;
+}
+
 template <typename T> struct IsRealType { static constexpr bool value = false; };
 template <> struct IsRealType<float>  { static constexpr bool value = true; };
 template <> struct IsRealType<double> { static constexpr bool value = true; };
@@ -420,6 +505,12 @@ template <typename T>
 static int launch_potrf_diag(T* A, int lda, int nv, T* Winv, int* info, int info_base, cudaStream_t stream)
 {
     if constexpr (IsRealType<T>::value) {
+        const int mw = diag_mw_mode();
+        if (mw > 0) {
+            if (mw == 2) potrf_diag_mw_kernel<T, true><<<1, MW_THREADS, mw_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+            else         potrf_diag_mw_kernel<T, false><<<1, MW_THREADS, mw_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+            return launch_status();
+        }
         static const bool rsq = [] { const char* e = getenv("SB200_DIAG_RSQRT"); return e && atoi(e) != 0; }();
         static const bool wrp = [] { const char* e = getenv("SB200_DIAG_WARP"); return e && atoi(e) != 0; }();
         if (wrp)      potrf_diag_warp_kernel<T><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
@@ -434,8 +525,10 @@ static int launch_potrf_diag(T* A, int lda, int nv, T* Winv, int* info, int info
 template <typename T>
 static int launch_trtri_diag(int nblk, const T* Tm, int ldt, int na, int lower, int unit, T* W, cudaStream_t stream)
 {
-    if constexpr (IsRealType<T>::value)
-        trtri_diag_fast_kernel<T><<<nblk, IB, fast_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
+    if constexpr (IsRealType<T>::value) {
+        if (diag_mw_mode() > 0) trtri_diag_mw_kernel<T><<<nblk, MW_THREADS, mw_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
+        else                    trtri_diag_fast_kernel<T><<<nblk, IB, fast_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
+    }
     else
         trtri_diag_kernel<T><<<nblk, 256, small_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
     return launch_status();
@@ -449,8 +542,12 @@ static int launch_trtri_diag_batched(int ntiles, const T* const* Tarr, int ldt, 
 {
     const int nblk = int(ceil_div(na, IB));
     if (ntiles <= 0 || nblk <= 0) return SB200_OK;
-    if constexpr (IsRealType<T>::value)
-        trtri_diag_fast_kernel<T><<<dim3(nblk, ntiles), IB, fast_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
+    if constexpr (IsRealType<T>::value) {
+        if (diag_mw_mode() > 0)
+            trtri_diag_mw_kernel<T><<<dim3(nblk, ntiles), MW_THREADS, mw_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
+        else
+            trtri_diag_fast_kernel<T><<<dim3(nblk, ntiles), IB, fast_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
+    }
     else
         trtri_diag_kernel<T><<<dim3(nblk, ntiles), 256, small_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
     return launch_status();
@@ -470,6 +567,9 @@ static void small_kernels_init()
         cudaFuncSetAttribute(potrf_diag_fast_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
         cudaFuncSetAttribute(potrf_diag_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
         cudaFuncSetAttribute(trtri_diag_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
+        cudaFuncSetAttribute(potrf_diag_mw_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mw_smem<T>()));
+        cudaFuncSetAttribute(potrf_diag_mw_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mw_smem<T>()));
+        cudaFuncSetAttribute(trtri_diag_mw_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mw_smem<T>()));
     }
     done[dev & 63] = true;
 }

@@ -19,11 +19,11 @@
 // that does not involve L(r,r-1)) is computed while CTA r-1 factors its diagonal block.
 // FP64 products run on the FP64 tensor-core MMA (DMMA.8x8x4, fragment conventions of gemm_dmma.cuh), FP32 products
 // (the FP32 factorisation of posv_mixed) on FP32 FMAs with a 4 x 8 register tile per thread; operands are staged
-// through padded shared memory; the 64 x 64 Cholesky + inverse are the register kernels of factor_small.cu
-// (one row / one column per thread) on two warps with a named barrier.
+// through padded shared memory; the 64 x 64 Cholesky + inverse run in shared memory on all threads (diag64.cuh).
 // Failure (block not positive definite): info = info_base + column + 1 as the default path; the failing CTA
 // publishes FAILED on its flags and every later CTA leaves on seeing it.
 #include "common.cuh"
+#include "diag64.cuh"
 #include "runtime_internal.hh"
 #include <cstdlib>
 
@@ -49,8 +49,6 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-// barrier among the first 64 threads (warps 0 and 1) only
-__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
 // all FT threads: wait until *p >= target (FAILED is larger than any target); returns the value seen
 __device__ __forceinline__ unsigned wait_flag(const unsigned* p, unsigned target, unsigned* s_v)
@@ -150,24 +148,6 @@ __device__ __forceinline__ void zero_acc(R (&acc)[32])
     for (int e = 0; e < 32; ++e) acc[e] = R(0);
 }
 
-__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
-__device__ __forceinline__ float  rsqrt_t(float x)  { return rsqrtf(x); }
-
-// X = inv(L), thread j owns column j (same arithmetic as inv_lower_column of factor_small.cu)
-template <typename R>
-__device__ __forceinline__ void inv_column64(const R* __restrict__ Ls, const R* __restrict__ rd, int j, R (&x)[FB])
-{
-    #pragma unroll
-    for (int k = 0; k < FB; ++k) x[k] = (k == j) ? R(1) : R(0);
-    #pragma unroll
-    for (int i = 0; i < FB; ++i) {
-        x[i] *= rd[i];
-        const R xi = x[i];
-        #pragma unroll
-        for (int k = i + 1; k < FB; ++k) x[k] = fma(-Ls[i * FB + k], xi, x[k]);
-    }
-}
-
 template <typename R, bool RSQ>
 __global__ void __launch_bounds__(FT, 1)
 potrf_tile_fused_kernel(R* __restrict__ A, int lda, int n, int* __restrict__ info, int info_base,
@@ -178,7 +158,6 @@ potrf_tile_fused_kernel(R* __restrict__ A, int lda, int n, int* __restrict__ inf
     R* Ys = Xs + FB * FLD;                                 // operand Y / W_b
     R* Cs = Ys + FB * FLD;                                 // S (operand of the solve) / D (input of the Cholesky)
     __shared__ unsigned s_v;
-    __shared__ int s_fail;
     unsigned* rowcnt = flags;                              // rowcnt[r] = number of final blocks L(r, 0 .. cnt-1)
     unsigned* diagf = flags + FMAXB;                       // diagf[r]  = 1 once L(r,r) and W_r are final
 
@@ -192,7 +171,6 @@ potrf_tile_fused_kernel(R* __restrict__ A, int lda, int n, int* __restrict__ inf
         if (tid == 0) { st_release_u32(&rowcnt[r], F_FAILED); st_release_u32(&diagf[r], F_FAILED); }
         return;
     }
-    if (tid == 0) s_fail = 0;
 
     R acc[32], accD[32];
     zero_acc(accD);
@@ -263,74 +241,31 @@ potrf_tile_fused_kernel(R* __restrict__ A, int lda, int n, int* __restrict__ inf
         __syncthreads();
     }
 
-    // ---- 64 x 64 Cholesky + inverse on warps 0 and 1 (thread = row / column); the other warps wait below
-    if (tid < FB) {
-        R* Ls = Xs;                                        // [FB * (FB + 1)] columns (stride FB), later padded staging
-        R* rd = Ls + FB * (FB + 1);                        // [FB] reciprocal diagonal      (FB*(FB+1) + FB <= FB*FLD)
-        const int i = tid;
-        R a[FB];
-        #pragma unroll
-        for (int c = 0; c < FB; ++c) a[c] = Cs[c * FLD + i];
-        int fail = 0;
-        R rdiag = R(1);
-        #pragma unroll
-        for (int j = 0; j < FB; ++j) {
-            Ls[j * FB + i] = a[j];
-            bar64();
-            const R d = Ls[j * FB + j];
-            if (fail == 0 && !(d > R(0))) fail = j + 1;    // also catches NaN; uniform over the 64 threads
-            if constexpr (RSQ) {
-                const R rinv = rsqrt_t(d);
-                const R w = a[j] * (rinv * rinv);
-                #pragma unroll
-                for (int c = j + 1; c < FB; ++c) a[c] = fma(-w, Ls[j * FB + c], a[c]);
-                a[j] = (i == j) ? d * rinv : a[j] * rinv;
-                if (i == j) rdiag = rinv;
-            }
-            else {
-                const R w = a[j] / d;
-                #pragma unroll
-                for (int c = j + 1; c < FB; ++c) a[c] = fma(-w, Ls[j * FB + c], a[c]);
-                const R rt = sqrt(d);
-                a[j] = (i == j) ? rt : a[j] / rt;
-                if (i == j) rdiag = R(1) / rt;
-            }
+    // ---- 64 x 64 Cholesky + inverse in shared memory, all threads (diag64.cuh): D is in Cs, L goes to Xs, W_r to Ys
+    R* rd = Cs + FB * FLD;                                 // [FB] reciprocal diagonal (extra FB elements of shared memory)
+    const int fail = chol64_smem<R, FT, FLD, RSQ>(Cs, Xs, rd, tid);
+    if (fail) {
+        if (tid == 0) {
+            if (*reinterpret_cast<volatile int*>(info) == 0) *info = info_base + r * FB + fail;
+            st_release_u32(&rowcnt[r], F_FAILED);
+            st_release_u32(&diagf[r], F_FAILED);
         }
-        if (fail) {
-            if (i == 0) {
-                if (*reinterpret_cast<volatile int*>(info) == 0) *info = info_base + r * FB + fail;
-                s_fail = fail;
-            }
-        }
-        else {
-            R* Ad = Arow + int64_t(r) * FB * lda;
-            #pragma unroll
-            for (int c = 0; c < FB; ++c)
-                if (c <= i && i < rv) Ad[i + int64_t(c) * lda] = a[c];
-            if (r + 1 < nblk) {                            // W_r is only needed by the rows below
-                bar64();
-                #pragma unroll
-                for (int c = 0; c < FB; ++c) Ls[c * FB + i] = a[c];
-                rd[i] = rdiag;
-                bar64();
-                R x[FB];
-                inv_column64<R>(Ls, rd, i, x);
-                bar64();                                   // everybody is done reading Ls (aliased by the staging)
-                #pragma unroll
-                for (int q = 0; q < FB; ++q) Ls[q * (FB + 1) + i] = x[q];          // staging[q][column i]
-                bar64();
-                R* W = Wg + int64_t(r) * FB * FB;
-                #pragma unroll 8
-                for (int j = 0; j < FB; ++j) W[i + j * FB] = Ls[i * (FB + 1) + j]; // W(i, j), coalesced over i
-            }
+        return;
+    }
+    {
+        R* Ad = Arow + int64_t(r) * FB * lda;
+        for (int e = tid; e < FB * FB; e += FT) {
+            const int row = e & (FB - 1), col = e >> 6;
+            if (col <= row && row < rv) Ad[row + int64_t(col) * lda] = Xs[col * FLD + row];
         }
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned f = s_fail ? F_FAILED : 1u;
-        if (s_fail) st_release_u32(&rowcnt[r], F_FAILED);
-        st_release_u32(&diagf[r], f);
+    if (r + 1 < nblk) {                                    // W_r is only needed by the rows below
+        inv64_smem<R, FT, FLD>(Xs, rd, Ys, tid);
+        R* W = Wg + int64_t(r) * FB * FB;
+        for (int e = tid; e < FB * FB; e += FT) W[e] = Ys[(e >> 6) * FLD + (e & (FB - 1))];       // W(i, j) at i + j * FB
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_u32(&diagf[r], 1u);
     }
 }
 
@@ -518,7 +453,7 @@ trsm_lln_small_kernel(int na, int n, R alpha, int unit, const R* __restrict__ Tm
     }
 }
 
-template <typename R> constexpr size_t fused_smem() { return size_t(3) * FB * FLD * sizeof(R); }
+template <typename R> constexpr size_t fused_smem() { return (size_t(3) * FB * FLD + FB) * sizeof(R); }
 
 template <typename R>
 int potrf_tile_fused_t(int n, R* A, int lda, int* dinfo, int info_base, int variant, cudaStream_t stream)
