@@ -123,6 +123,36 @@ def inv64_smem(Ls, rd, Xs, NT, LD):
                     Xs[j * LD + r] -= Ls[i * LD + r] * xij
 
 
+def trsm_lln_small(B, na, n, ldb, alpha, T, ldt, unit, NT=256):
+    """potrf_tile_fused.cu: trsm_lln_small_kernel (one CTA per 64 columns), phases separated by its barriers"""
+    for c0 in range(0, n, 64):
+        cv = min(64, n - c0)
+        Ls = np.zeros(64 * 65); Bs = np.zeros(64 * 65)
+        for e in range(na * na):
+            i, k = e % na, e // na
+            if i > k:
+                Ls[k * 65 + i] = T[i + k * ldt]
+            elif i == k:
+                Ls[k * 65 + i] = 1.0 if unit else 1.0 / T[i + k * ldt]
+        for e in range(na * cv):
+            i, c = e % na, e // na
+            Bs[c * 65 + i] = alpha * B[i + (c0 + c) * ldb]
+        for k in range(na):
+            if not unit:
+                for tid in range(NT):
+                    if tid < cv:
+                        Bs[tid * 65 + k] *= Ls[k * 65 + k]
+            for tid in range(NT):
+                ti, tcol = tid & 15, tid >> 4
+                for c in range(tcol, cv, NT // 16):
+                    xk = Bs[c * 65 + k]
+                    for i in range(k + 1 + ti, na, 16):
+                        Bs[c * 65 + i] -= Ls[k * 65 + i] * xk
+        for e in range(na * cv):
+            i, c = e % na, e // na
+            B[i + (c0 + c) * ldb] = Bs[c * 65 + i]
+
+
 def make(prec):
     P = ProdD if prec == "d" else ProdS
     mma = mma_d if prec == "d" else mma_s
@@ -297,6 +327,15 @@ def main():
             As[c * 65 + r] = S[r, c]
     assert chol64_smem(As, np.zeros(64 * 65), np.zeros(64), 256, 65, False) == 41
     print("chol64_smem / inv64_smem (multi-warp diagonal block): OK")
+    for na, n, unit in ((32, 32, True), (64, 100, False), (20, 7, True), (33, 130, False)):
+        T = rng.random((na, na)) / na + np.eye(na) * (1 + rng.random(na))
+        Bm = rng.random((na, n))
+        flat = Bm.flatten(order="F")
+        trsm_lln_small(flat, na, n, na, 0.7, T.flatten(order="F"), na, unit)
+        Lm = np.tril(T, -1) + (np.eye(na) if unit else np.diag(np.diag(T)))
+        ref = 0.7 * np.linalg.solve(Lm, Bm)
+        assert np.abs(flat.reshape((na, n), order="F") - ref).max() < 1e-13 * np.abs(ref).max(), (na, n, unit)
+    print("trsm_lln_small_kernel (direct substitution, small triangle): OK")
     for prec in ("d", "s"):
         # every (row, col) of the 64 x 64 block is owned by exactly one accumulator
         pr, _ = make(prec)

@@ -401,55 +401,49 @@ trsm_lln_fused_kernel(int na, int n, R alpha, const R* __restrict__ Tm, int ldt,
 // Left / Lower / NoTrans solve with a SMALL triangle (na <= 64) by direct substitution, one launch
 // (opt-in, SB200_TRSM_FUSED bit 2; round-2 candidate, not yet run): the U12 = L11^-1 A12 steps inside the recursive
 // LU panel (w1 = 32 or 64; 12 of the 15 updates of an nb = 512 panel) are today an inversion kernel with a 64-step
-// dependent chain (~35 us) plus a GEMM launch.  Here: thread = one column of B held in registers, L broadcast from
-// shared memory, axpy-form substitution (the dependent chain is na FMAs); B goes through shared memory transposed so
-// that global accesses are coalesced.
+// dependent chain (~35 us) plus a GEMM launch.  Here: L and a 64-column slab of B in shared memory, axpy-form
+// substitution with rolled loops on 256 threads (one barrier per row of the triangle, two if the diagonal is not unit).
 // ---------------------------------------------------------------------------------------------
-constexpr int SL_COLS = 64;         // columns of B per CTA = threads per CTA
+constexpr int SL_COLS = 64;         // columns of B per CTA
+constexpr int SL_THREADS = 256;     // rolled loops over shared memory, 8 warps (see diag64.cuh for why not thread-per-column)
 
-template <typename R, int NA>
-__global__ void __launch_bounds__(SL_COLS)
+template <typename R>
+__global__ void __launch_bounds__(SL_THREADS)
 trsm_lln_small_kernel(int na, int n, R alpha, int unit, const R* __restrict__ Tm, int ldt,
                       R* const* __restrict__ dB, int64_t offB, int ldb)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    R* Ls = reinterpret_cast<R*>(smem_dyn);        // Ls[k * (NA + 1) + i] = L(i, k)
-    R* Bs = Ls + NA * (NA + 1);                    // Bs[i * (SL_COLS + 1) + c] = B(i, c0 + c)
+    R* Ls = reinterpret_cast<R*>(smem_dyn);        // Ls[k * 65 + i] = L(i, k), i > k;  Ls[k * 65 + k] = 1 / L(k, k) (1 if unit)
+    R* Bs = Ls + 64 * 65;                          // Bs[c * 65 + i] = B(i, c0 + c)
     const int tid = threadIdx.x;
     const int c0 = blockIdx.x * SL_COLS;
     const int cv = min(SL_COLS, n - c0);
     R* B = dB[blockIdx.y] + offB + int64_t(c0) * ldb;
-    for (int e = tid; e < na * na; e += SL_COLS) {
+    for (int e = tid; e < na * na; e += SL_THREADS) {
         const int i = e % na, k = e / na;
-        Ls[k * (NA + 1) + i] = (i > k) ? Tm[i + int64_t(k) * ldt] : (i == k ? (unit ? R(1) : Tm[i + int64_t(k) * ldt]) : R(0));
+        if (i > k)       Ls[k * 65 + i] = Tm[i + int64_t(k) * ldt];
+        else if (i == k) Ls[k * 65 + i] = unit ? R(1) : R(1) / Tm[i + int64_t(k) * ldt];
     }
-    for (int e = tid; e < na * cv; e += SL_COLS) {
+    for (int e = tid; e < na * cv; e += SL_THREADS) {
         const int i = e % na, c = e / na;
-        Bs[i * (SL_COLS + 1) + c] = alpha * B[i + int64_t(c) * ldb];
+        Bs[c * 65 + i] = alpha * B[i + int64_t(c) * ldb];
     }
     __syncthreads();
-    if (tid < cv) {
-        R x[NA];
-        #pragma unroll
-        for (int i = 0; i < NA; ++i) x[i] = (i < na) ? Bs[i * (SL_COLS + 1) + tid] : R(0);
-        #pragma unroll
-        for (int k = 0; k < NA; ++k) {
-            if (k < na) {
-                if (! unit) x[k] = x[k] / Ls[k * (NA + 1) + k];
-                const R xk = x[k];
-                #pragma unroll
-                for (int i = k + 1; i < NA; ++i)
-                    if (i < na) x[i] = fma(-Ls[k * (NA + 1) + i], xk, x[i]);
-            }
+    const int ti = tid & 15, tcol = tid >> 4;      // 16 threads along the rows, 16 along the columns
+    for (int k = 0; k < na; ++k) {
+        if (! unit) {
+            if (tid < cv) Bs[tid * 65 + k] *= Ls[k * 65 + k];           // x_k = b_k / L(k,k)
+            __syncthreads();
         }
-        #pragma unroll
-        for (int i = 0; i < NA; ++i)
-            if (i < na) Bs[i * (SL_COLS + 1) + tid] = x[i];
+        for (int c = tcol; c < cv; c += SL_THREADS / 16) {
+            const R xk = Bs[c * 65 + k];
+            for (int i = k + 1 + ti; i < na; i += 16) Bs[c * 65 + i] = fma(-Ls[k * 65 + i], xk, Bs[c * 65 + i]);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int e = tid; e < na * cv; e += SL_COLS) {
+    for (int e = tid; e < na * cv; e += SL_THREADS) {
         const int i = e % na, c = e / na;
-        B[i + int64_t(c) * ldb] = Bs[i * (SL_COLS + 1) + c];
+        B[i + int64_t(c) * ldb] = Bs[c * 65 + i];
     }
 }
 
@@ -537,17 +531,15 @@ int trsm_lln_small_t(int na, int n, R alpha, bool unit, const R* Tm, int ldt, R*
     if (n <= 0 || na <= 0 || batch <= 0) return SB200_OK;
     if (na > 64) return SB200_EINVAL;
     const dim3 grid(unsigned(ceil_div(n, SL_COLS)), unsigned(batch));
-    constexpr size_t smem32 = (size_t(32) * 33 + size_t(32) * (SL_COLS + 1)) * sizeof(R);
-    constexpr size_t smem64 = (size_t(64) * 65 + size_t(64) * (SL_COLS + 1)) * sizeof(R);
+    constexpr size_t smem = size_t(2) * 64 * 65 * sizeof(R);
     static thread_local bool attr_done[64] = {};
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (! attr_done[dev & 63]) {
-        CUDA_TRY(cudaFuncSetAttribute(trsm_lln_small_kernel<R, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem64)));
+        CUDA_TRY(cudaFuncSetAttribute(trsm_lln_small_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         attr_done[dev & 63] = true;
     }
-    if (na <= 32) trsm_lln_small_kernel<R, 32><<<grid, SL_COLS, smem32, stream>>>(na, n, alpha, unit ? 1 : 0, Tm, ldt, dB, offB, ldb);
-    else          trsm_lln_small_kernel<R, 64><<<grid, SL_COLS, smem64, stream>>>(na, n, alpha, unit ? 1 : 0, Tm, ldt, dB, offB, ldb);
+    trsm_lln_small_kernel<R><<<grid, SL_THREADS, smem, stream>>>(na, n, alpha, unit ? 1 : 0, Tm, ldt, dB, offB, ldb);
     return launch_status();
 }
 
