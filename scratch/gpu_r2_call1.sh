@@ -22,7 +22,7 @@ run_group() {   # name, pytest args...
 }
 run_group dist_solve tests/test_zzz_gpu_dist_solve.py
 run_group diag_mw    $C -k "diag_mw"
-run_group streaming  $C -k "streaming or permute_rows"
+run_group streaming  $C -k "streaming or permute_rows or transposed_b"
 run_group trsm_fused $C -k "fused_panel_trsm or fused_row_trsm or fused_row_solve or row_solve_candidates"
 run_group tile_fused $C -k "fused_tile"
 run_group panel_ll   $C -k "ll_panel"
@@ -36,6 +36,8 @@ for sw in SB200_DIAG_RSQRT SB200_DIAG_WARP SB200_PANEL_BARRIER SB200_PANEL_LL; d
   stamp $sw
 done
 # 3. timings of every variant (one fresh process each), phases on stderr
+timeout 300 python scratch/perf_variants.py gemm 16384 512 > $OUT/r2c1_perf_gemm.log 2> $OUT/r2c1_perf_gemm.err; cat $OUT/r2c1_perf_gemm.log | cut -c1-300
+stamp perf_gemm
 for r in potrf getrf posv_mixed gesv_mixed; do
   timeout 900 python scratch/perf_variants.py $r 32768 512 > $OUT/r2c1_perf_$r.log 2> $OUT/r2c1_perf_$r.err
   cat $OUT/r2c1_perf_$r.log | cut -c1-300

@@ -33,6 +33,7 @@ GETRF = [("default", {}),
 MIXED = [("default", {}),
          ("diag_mw", {"SB200_DIAG_MW": "1"}),
          ("tile+trsm_fused+diag_mw", {"SB200_TILE_FUSED": "1", "SB200_TRSM_FUSED": "3", "SB200_DIAG_MW": "1"})]
+GEMM = [("default", {}), ("transposed_B_panel", {"SB200_GEMM_BT": "1"})]
 GMIXED = [("default", {}),
           ("panel_ll+all_row_solves+diag_mw", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1"})]
 
@@ -50,6 +51,11 @@ def one(routine, n, nb):
         fl = 2 * n ** 3 / 3 - n * n / 2 + 5 * n / 6
         A0 = sl.Matrix(n, n, nb).generate("rand", 42); A = sl.Matrix(n, n, nb)
         fn = lambda: sl.getrf(A)
+    elif routine == "gemm":
+        fl = 2.0 * n ** 3
+        A0 = sl.Matrix(n, n, nb).generate("rand", 3); A = sl.Matrix(n, n, nb)
+        Ga = sl.Matrix(n, n, nb).generate("rand", 1); Gb = sl.Matrix(n, n, nb).generate("rand", 2)
+        fn = lambda: sl.gemm(3.1, Ga, Gb, 2.7, A)
     elif routine == "gesv_mixed":
         fl = 2 * n ** 3 / 3
         A0 = sl.Matrix(n, n, nb).generate("rand", 42); A = sl.Matrix(n, n, nb)
@@ -86,7 +92,7 @@ if __name__ == "__main__":
     routine = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
     nb = int(sys.argv[3]) if len(sys.argv) > 3 else 512
-    for tag, env in {"potrf": POTRF, "getrf": GETRF, "posv_mixed": MIXED, "gesv_mixed": GMIXED}[routine]:
+    for tag, env in {"potrf": POTRF, "getrf": GETRF, "gemm": GEMM, "posv_mixed": MIXED, "gesv_mixed": GMIXED}[routine]:
         e = dict(os.environ); e.update(env)
         print(f"## {routine} {tag}", flush=True)
         sys.stderr.write(f"## {routine} {tag}\n"); sys.stderr.flush()

@@ -453,14 +453,42 @@ int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C)
         return wsB.as<T>() + ((k & 1) * C.nt_loc + (j - g.pcol) / g.q) * te;
     };
 
+    // opt-in (SB200_GEMM_BT=1, double only; round-2 candidate, not yet run): the B row panel of every step is transposed
+    // once (tile kernels, HBM-bound, ~50 us per step) so that the multiply runs as 'N','T' -- both operands staged by TMA
+    // bulk copies, the variant the potrf trailing update runs at 0.91 of the DMMA peak -- instead of 'N','N', whose
+    // K-major B operand goes through 16-byte cp.async (0.85 measured for dgemm).  Same products in the same order:
+    // bitwise the same C.
+    bool use_bt = false;
+    if constexpr (std::is_same<T, double>::value) {
+        const char* e = getenv("SB200_GEMM_BT");
+        use_bt = e && atoi(e) != 0;
+    }
+    DevBuf wsBt;
+    if (use_bt) SB_TRY(wsBt.alloc(size_t(2) * std::max<int64_t>(C.nt_loc, 1) * te * sizeof(T)));
+    auto bt_src = [&](int64_t k, int64_t j) -> T* {
+        return wsBt.as<T>() + ((k & 1) * C.nt_loc + (j - g.pcol) / g.q) * te;
+    };
+    struct BtStep { std::vector<const T*> src_full, src_last; std::vector<T*> dst_full, dst_last;
+                    size_t src_full_off = 0, dst_full_off = 0, src_last_off = 0, dst_last_off = 0; };
+    std::vector<BtStep> bts(use_bt ? size_t(kt) : 0);
+
     std::vector<std::vector<Batch>> plan(kt);
     PlanBuffer pb;
     for (int64_t k = 0; k < kt; ++k) {
         for (int64_t j = g.pcol; j < C.nt; j += g.q)
             for (int64_t i = g.prow; i < C.mt; i += g.p)
                 batch_add(plan[k], int(C.tile_mb(i)), int(C.tile_nb(j)), int(A.tile_nb(k)), 0,
-                          a_src(i, k), b_src(k, j), C.tile_as<T>(i, j));
+                          a_src(i, k), use_bt ? bt_src(k, j) : b_src(k, j), C.tile_as<T>(i, j));
         pb.reserve(plan[k]);
+        if (use_bt) {
+            BtStep& b = bts[size_t(k)];
+            for (int64_t j = g.pcol; j < C.nt; j += g.q) {
+                if (C.tile_nb(j) == nb) { b.src_full.push_back(b_src(k, j)); b.dst_full.push_back(bt_src(k, j)); }
+                else                    { b.src_last.push_back(b_src(k, j)); b.dst_last.push_back(bt_src(k, j)); }
+            }
+            b.src_full_off = pb.push(b.src_full); b.dst_full_off = pb.push(b.dst_full);
+            b.src_last_off = pb.push(b.src_last); b.dst_last_off = pb.push(b.dst_last);
+        }
     }
     Streams st;
     double trail_flops = 0;
@@ -499,11 +527,29 @@ int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C)
                 for (int64_t j = g.pcol; j < C.nt; j += g.q)
                     CUDA_TRY(cudaMemcpyAsync(b_src(k, j), B.tile_as<T>(k, j), size_t(te) * sizeof(T),
                                              cudaMemcpyDeviceToDevice, P));
-            CUDA_TRY(cudaEventRecord(P_done(k), P));
-            CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
+            if (! use_bt) {
+                CUDA_TRY(cudaEventRecord(P_done(k), P));
+                CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
+            }
+        }
+        if constexpr (std::is_same<T, double>::value) {
+            if (use_bt) {
+                // Bt(j,k) = B(k,j)^T for the local block columns j, on the panel stream, one step ahead of the multiply
+                if (! multi && k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));      // slot [k & 1] is free again
+                const BtStep& b = bts[size_t(k)];
+                const int kb = int(A.tile_nb(k));
+                if (! b.src_full.empty())
+                    SB_TRY(sb200_transpose_batched_d(0, kb, nb, pb.at<const double>(b.src_full_off), ld,
+                                                     pb.at<double>(b.dst_full_off), ld, int64_t(b.src_full.size()), P));
+                if (! b.src_last.empty())
+                    SB_TRY(sb200_transpose_batched_d(0, kb, C.tile_nb(C.nt - 1), pb.at<const double>(b.src_last_off), ld,
+                                                     pb.at<double>(b.dst_last_off), ld, int64_t(b.src_last.size()), P));
+                CUDA_TRY(cudaEventRecord(P_done(k), P));
+                CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
+            }
         }
         SB_TRY(st.time_begin(T_));
-        SB_TRY(launch_batches<T>(plan[k], pb, 'N', 'N', alpha, k == 0 ? beta : from_real<T>(R(1)), ld, 0, T_));
+        SB_TRY(launch_batches<T>(plan[k], pb, 'N', use_bt ? 'T' : 'N', alpha, k == 0 ? beta : from_real<T>(R(1)), ld, 0, T_));
         SB_TRY(st.time_end(T_));
         trail_flops += batches_flops(plan[k], IsComplex<T>::value);
         trail_launches += int64_t(plan[k].size());

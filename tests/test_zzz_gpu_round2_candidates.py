@@ -16,6 +16,9 @@
 * SB200_DIAG_MW=1|2 -- multi-warp shared-memory versions of the 64 x 64 diagonal-block Cholesky / triangular inverse
   (csrc/diag64.cuh; the register kernels run at 15-19 cycles per instruction), behind every potrf tile and every trsm.
 
+* SB200_GEMM_BT=1 -- dgemm (SUMMA) with the B row panel transposed once per step so that the multiply runs as 'N','T'
+  (both operands through TMA bulk copies): bitwise the default C.
+
 Written after round 1's GPU budget was spent: SKIPPED unless SB200_RUN_UNVALIDATED=1 (round 2: run, fix, drop the guard,
 then make the winner the default)."""
 import os
@@ -460,3 +463,23 @@ def test_diag_mw_drivers(sl, monkeypatch, mode):
     LUo, pivo, info_o = o.getrf(o.generate("rand", n, n, 42), nb, 32)
     assert info == info_o == 0 and piv == pivo
     assert np.abs(M.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
+
+
+@pytest.mark.parametrize("m,n,k,nb", [(1024, 1024, 1024, 256), (700, 900, 500, 128), (2048, 1536, 1024, 512), (300, 200, 100, 512)])
+def test_gemm_transposed_b_panel_is_bitwise_the_default(sl, monkeypatch, m, n, k, nb):
+    import torch
+
+    def run():
+        A = sl.Matrix(m, k, nb).generate("rand", 1)
+        B = sl.Matrix(k, n, nb).generate("rand", 2)
+        C = sl.Matrix(m, n, nb).generate("rand", 3)
+        sl.gemm(3.1, A, B, 2.7, C)
+        return C.to_host()
+
+    monkeypatch.delenv("SB200_GEMM_BT", raising=False)
+    c0 = run()
+    monkeypatch.setenv("SB200_GEMM_BT", "1")
+    c1 = run()
+    assert np.array_equal(c0, c1)
+    a, b, c = (o.generate("rand", *shape, seed) for shape, seed in (((m, k), 1), ((k, n), 2), ((m, n), 3)))
+    assert o.gemm_check(3.1, a, b, 2.7, c, c1) <= 3 * EPS
