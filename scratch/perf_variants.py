@@ -26,8 +26,10 @@ GETRF = [("default", {}),
          ("panel_ll", {"SB200_PANEL_LL": "1"}),
          ("panel_ll+row_trsm_fused", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "2"}),
          ("small_trsm_direct", {"SB200_TRSM_FUSED": "4"}),
+         ("transposed_U_row", {"SB200_GEMM_BT": "1"}),
          ("panel_ll+all_row_solves", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6"}),
          ("panel_ll+all_row_solves+diag_mw", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1"}),
+         ("everything", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1", "SB200_GEMM_BT": "1"}),
          ("row_trsm_fused", {"SB200_TRSM_FUSED": "2"}),
          ("barrier+row_trsm_fused", {"SB200_PANEL_BARRIER": "1", "SB200_TRSM_FUSED": "2"})]
 MIXED = [("default", {}),

@@ -788,8 +788,24 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
             tbl[size_t(i + j * mt)] = A.tile_as<T>(i, j);
             tblT[size_t(j + i * nt)] = A.tile_as<T>(i, j);
         }
+    // opt-in (SB200_GEMM_BT=1, double, not the tcgen05 path; round-2 candidate, not yet run): the row U(k, k+2:) is
+    // transposed once per step after its solve, so that the trailing update runs as 'N','T' (both operands staged by TMA
+    // bulk copies: the variant of the potrf trailing update, 0.91 of the DMMA peak) instead of 'N','N' (K-major B through
+    // 16-byte cp.async; 0.80 measured here).  Same products in the same order: bitwise the same factor.
+    bool use_bt = false;
+    if constexpr (std::is_same<T, double>::value) {
+        const char* e = getenv("SB200_GEMM_BT");
+        use_bt = e && atoi(e) != 0 && ! use_tc05;
+    }
+    DevBuf wsUt;
+    const int64_t te_ = nb * nb;
+    if (use_bt) SB_TRY(wsUt.alloc(size_t(2) * nt * te_ * sizeof(T)));
+    auto ut = [&](int64_t k, int64_t j) -> T* { return wsUt.as<T>() + ((k & 1) * nt + j) * te_; };
     // per-step GEMM batches: lookahead column k+1 and trailing columns >= k+2; pack lists (tcgen05 path)
     struct Step {
+        std::vector<const T*> ut_src_full, ut_src_last;     // U(k,j), j >= k+2 (use_bt)
+        std::vector<T*> ut_dst_full, ut_dst_last;
+        size_t ut_src_full_off = 0, ut_dst_full_off = 0, ut_src_last_off = 0, ut_dst_last_off = 0;
         std::vector<Batch> la, tr;
         std::vector<const void*> a_src, b_src;       // L(i,k), i > k (ragged last row at the end); U(k,j), j >= k+2 (ragged last col at the end)
         std::vector<void*> a_dst, b_dst;
@@ -804,9 +820,17 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
         for (int64_t j = k + 1; j < nt; ++j)
             for (int64_t i = k + 1; i < mt; ++i) {
                 const void* a = use_tc05 ? static_cast<const void*>(pkA(i, k)) : A.tile_as<T>(i, k);
-                const void* b = use_tc05 ? static_cast<const void*>(pkB(j, k)) : A.tile_as<T>(k, j);
+                const void* b = use_tc05 ? static_cast<const void*>(pkB(j, k))
+                              : (use_bt && j >= k + 2) ? static_cast<const void*>(ut(k, j)) : A.tile_as<T>(k, j);
                 batch_add(j == k + 1 ? s.la : s.tr, int(A.tile_mb(i)), int(A.tile_nb(j)), kw, 0, a, b, A.tile_as<T>(i, j));
             }
+        if (use_bt && k + 1 < mt)
+            for (int64_t j = k + 2; j < nt; ++j) {
+                if (A.tile_nb(j) == nb) { s.ut_src_full.push_back(A.tile_as<T>(k, j)); s.ut_dst_full.push_back(ut(k, j)); }
+                else                    { s.ut_src_last.push_back(A.tile_as<T>(k, j)); s.ut_dst_last.push_back(ut(k, j)); }
+            }
+        s.ut_src_full_off = pb.push(s.ut_src_full); s.ut_dst_full_off = pb.push(s.ut_dst_full);
+        s.ut_src_last_off = pb.push(s.ut_src_last); s.ut_dst_last_off = pb.push(s.ut_dst_last);
         if (use_tc05 && k + 1 < nt) {
             for (int64_t i = k + 1; i < mt; ++i) {
                 s.a_src.push_back(A.tile_as<T>(i, k)); s.a_dst.push_back(pkA(i, k));
@@ -845,11 +869,11 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
     T* const* dtbl = pb.at<T>(tbl_off);
     T* const* dtblT = pb.at<T>(tblT_off);
 
-    auto run_batches = [&](const std::vector<Batch>& bs, cudaStream_t s) -> int {
+    auto run_batches = [&](const std::vector<Batch>& bs, cudaStream_t s, bool b_transposed = false) -> int {
         if constexpr (is_float) {
             if (use_tc05) return launch_batches_tc05(bs, pb, -1.0f, 1.0f, ld, s);
         }
-        return launch_batches<T>(bs, pb, 'N', 'N', T(-1), T(1), ld, 0, s);
+        return launch_batches<T>(bs, pb, 'N', b_transposed ? 'T' : 'N', T(-1), T(1), ld, 0, s);
     };
     // split-pack `cnt` tiles (full-size ones first, then the ragged one) for one operand role
     auto pack = [&](int role, size_t src_off, size_t dst_off, int cnt, int full, int rows_full, int rows_last,
@@ -916,9 +940,19 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
             SB_TRY(row_trsm(k, k + 2, nt, Wt, T_));
             if (use_tc05 && ! sk.b_src.empty())
                 SB_TRY(pack('B', sk.b_src_off, sk.b_dst_off, int(sk.b_src.size()), sk.b_full, int(nb), int(A.tile_nb(nt - 1)), kw, T_));
+            if constexpr (std::is_same<T, double>::value) {
+                if (use_bt) {
+                    if (! sk.ut_src_full.empty())
+                        SB_TRY(sb200_transpose_batched_d(0, kw, nb, pb.at<const double>(sk.ut_src_full_off), ld,
+                                                         pb.at<double>(sk.ut_dst_full_off), ld, int64_t(sk.ut_src_full.size()), T_));
+                    if (! sk.ut_src_last.empty())
+                        SB_TRY(sb200_transpose_batched_d(0, kw, A.tile_nb(nt - 1), pb.at<const double>(sk.ut_src_last_off), ld,
+                                                         pb.at<double>(sk.ut_dst_last_off), ld, int64_t(sk.ut_src_last.size()), T_));
+                }
+            }
             if (! sk.tr.empty()) {
                 SB_TRY(st.time_begin(T_));
-                SB_TRY(run_batches(sk.tr, T_));
+                SB_TRY(run_batches(sk.tr, T_, use_bt));
                 SB_TRY(st.time_end(T_));
                 trail_flops += batches_flops(sk.tr, false);
                 trail_launches += int64_t(sk.tr.size());

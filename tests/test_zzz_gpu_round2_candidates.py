@@ -483,3 +483,18 @@ def test_gemm_transposed_b_panel_is_bitwise_the_default(sl, monkeypatch, m, n, k
     assert np.array_equal(c0, c1)
     a, b, c = (o.generate("rand", *shape, seed) for shape, seed in (((m, k), 1), ((k, n), 2), ((m, n), 3)))
     assert o.gemm_check(3.1, a, b, 2.7, c, c1) <= 3 * EPS
+
+
+@pytest.mark.parametrize("m,n,nb", [(2048, 2048, 512), (1100, 1100, 256), (700, 1000, 128), (1000, 700, 128)])
+def test_getrf_transposed_u_row_is_bitwise_the_default(sl, monkeypatch, m, n, nb):
+    def run():
+        A = sl.Matrix(m, n, nb).generate("rand", 42)
+        piv, info = sl.getrf(A)
+        return piv, info, A.to_host()
+
+    monkeypatch.delenv("SB200_GEMM_BT", raising=False)
+    p0, i0, a0 = run()
+    monkeypatch.setenv("SB200_GEMM_BT", "1")
+    p1, i1, a1 = run()
+    assert i0 == i1 == 0 and p0 == p1
+    assert np.array_equal(a0, a1)
