@@ -252,20 +252,20 @@ potrf_tile_fused_kernel(R* __restrict__ A, int lda, int n, int* __restrict__ inf
         }
         return;
     }
-    {
-        R* Ad = Arow + int64_t(r) * FB * lda;
-        for (int e = tid; e < FB * FB; e += FT) {
-            const int row = e & (FB - 1), col = e >> 6;
-            if (col <= row && row < rv) Ad[row + int64_t(col) * lda] = Xs[col * FLD + row];
-        }
-    }
-    if (r + 1 < nblk) {                                    // W_r is only needed by the rows below
+    if (r + 1 < nblk) {                                    // W_r first: the rows below are waiting for it
         inv64_smem<R, FT, FLD>(Xs, rd, Ys, tid);
         R* W = Wg + int64_t(r) * FB * FB;
         for (int e = tid; e < FB * FB; e += FT) W[e] = Ys[(e >> 6) * FLD + (e & (FB - 1))];       // W(i, j) at i + j * FB
         __threadfence();
         __syncthreads();
         if (tid == 0) st_release_u32(&diagf[r], 1u);
+    }
+    {
+        R* Ad = Arow + int64_t(r) * FB * lda;              // L(r,r) itself is only read after the kernel
+        for (int e = tid; e < FB * FB; e += FT) {
+            const int row = e & (FB - 1), col = e >> 6;
+            if (col <= row && row < rv) Ad[row + int64_t(col) * lda] = Xs[col * FLD + row];
+        }
     }
 }
 
