@@ -179,6 +179,15 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
     SB_TRY(pws.alloc(size_t(2) * mt * te * sizeof(T)));
     SB_TRY(uws.alloc(size_t(std::max(nt_loc, 1)) * te * sizeof(T)));
     SB_TRY(ula.alloc(size_t(te) * sizeof(T)));
+    // opt-in (SB200_GEMM_BT=1, double, not the tcgen05 path; round-2 candidate, not yet run): transposed copies of the U
+    // slots, written once per step after the row solve, so that the trailing update runs as 'N','T' (see getrf.cu)
+    bool use_bt = false;
+    if constexpr (std::is_same<T, double>::value) {
+        const char* e = getenv("SB200_GEMM_BT");
+        use_bt = e && atoi(e) != 0 && ! use_tc05;
+    }
+    DBuf uwsT;
+    if (use_bt) SB_TRY(uwsT.alloc(size_t(std::max(nt_loc, 1)) * te * sizeof(T)));
     SB_TRY(gmine.alloc(size_t(std::max(nt_loc, 1)) * te * sizeof(T)));
     SB_TRY(oldtop.alloc(size_t(std::max(nt_loc, 1)) * te * sizeof(T)));
     SB_TRY(gmineP.alloc(size_t(te) * sizeof(T)));
@@ -218,7 +227,7 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
         for (int64_t j = k + 1; j < nt; ++j) {
             if (int(j % q) != pcol) continue;
             const int64_t jl = (j - pcol) / q;
-            const T* Bop = (j == k + 1) ? ula.as<T>() : uws.as<T>() + jl * te;
+            const T* Bop = (j == k + 1) ? ula.as<T>() : (use_bt ? uwsT.as<T>() : uws.as<T>()) + jl * te;
             for (int64_t i = k + 1; i < mt; ++i) {
                 if (int(i % p) != prow) continue;
                 batch_add(j == k + 1 ? steps[k].la : steps[k].tr, int(A.tile_mb(i)), int(A.tile_nb(j)), kw, 0,
@@ -249,6 +258,17 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
                 if (int(j % q) == pcol) {
                     const int64_t jl = (j - pcol) / q;
                     src.push_back(uws.as<T>() + jl * te); dst.push_back(pkB.as<unsigned char>() + jl * pb_bytes);
+                    ++steps[k].b_cnt; if (A.tile_nb(j) == nb) ++steps[k].b_full;
+                }
+            steps[k].b_src = hp.size(); hp.insert(hp.end(), src.begin(), src.end());
+            steps[k].b_dst = hp.size(); hp.insert(hp.end(), dst.begin(), dst.end());
+        }
+        if (use_bt && k + 1 < mt) {                       // U slots of the trailing columns -> their transposes (full-size first)
+            std::vector<const void*> src; std::vector<void*> dst;
+            for (int64_t j = k + 2; j < nt; ++j)
+                if (int(j % q) == pcol) {
+                    const int64_t jl = (j - pcol) / q;
+                    src.push_back(uws.as<T>() + jl * te); dst.push_back(uwsT.as<T>() + jl * te);
                     ++steps[k].b_cnt; if (A.tile_nb(j) == nb) ++steps[k].b_full;
                 }
             steps[k].b_src = hp.size(); hp.insert(hp.end(), src.begin(), src.end());
@@ -294,11 +314,11 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
     PlanBuffer pbv;                      // non-owning view of the device plan for the shared batch launchers
     struct PbvGuard { PlanBuffer& v; ~PbvGuard() { v.dev = nullptr; } } pbv_guard{pbv};
     pbv.dev = dplan;
-    auto run_batches = [&](const std::vector<Batch>& bs, cudaStream_t s) -> int {
+    auto run_batches = [&](const std::vector<Batch>& bs, cudaStream_t s, bool b_transposed = false) -> int {
         if constexpr (is_float) {
             if (use_tc05) return launch_batches_tc05(bs, pbv, -1.0f, 1.0f, ld, s);
         }
-        return launch_batches<T>(bs, pbv, 'N', 'N', T(-1), T(1), ld, 0, s);
+        return launch_batches<T>(bs, pbv, 'N', b_transposed ? 'T' : 'N', T(-1), T(1), ld, 0, s);
     };
     // split-pack `cnt` operands given by device pointer arrays (tcgen05 path)
     auto pack = [&](int role, const void* const* src, void* const* dst, int cnt, int rows, int kdim, cudaStream_t s) -> int {
@@ -460,12 +480,24 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
                 SB_TRY(pack('B', src, dst, sk.b_full, int(nb), kw, T_));
                 SB_TRY(pack('B', src + sk.b_full, dst + sk.b_full, sk.b_cnt - sk.b_full, int(A.tile_nb(nt - 1)), kw, T_));
             }
+            if constexpr (std::is_same<T, double>::value) {
+                if (use_bt && steps[k].b_cnt > 0) {
+                    const Step& sk = steps[k];
+                    const double* const* src = reinterpret_cast<const double* const*>(dplan + sk.b_src);
+                    double* const* dst = reinterpret_cast<double* const*>(dplan + sk.b_dst);
+                    if (sk.b_full > 0)
+                        SB_TRY(sb200_transpose_batched_d(0, kw, nb, src, ld, dst, ld, sk.b_full, T_));
+                    if (sk.b_cnt > sk.b_full)
+                        SB_TRY(sb200_transpose_batched_d(0, kw, A.tile_nb(nt - 1), src + sk.b_full, ld, dst + sk.b_full, ld,
+                                                         sk.b_cnt - sk.b_full, T_));
+                }
+            }
             if (! steps[k].tr.empty()) {
                 cudaEvent_t a0, a1;
                 CUDA_TRY(cudaEventCreate(&a0)); CUDA_TRY(cudaEventCreate(&a1));
                 tev.push_back(a0); tev.push_back(a1);
                 CUDA_TRY(cudaEventRecord(a0, T_));
-                SB_TRY(run_batches(steps[k].tr, T_));
+                SB_TRY(run_batches(steps[k].tr, T_, use_bt));
                 CUDA_TRY(cudaEventRecord(a1, T_));
                 for (const auto& b : steps[k].tr) trail_flops += 2.0 * b.m * b.n * b.k * double(b.C.size());
                 trail_launches += int64_t(steps[k].tr.size());

@@ -485,8 +485,11 @@ def test_gemm_transposed_b_panel_is_bitwise_the_default(sl, monkeypatch, m, n, k
     assert o.gemm_check(3.1, a, b, 2.7, c, c1) <= 3 * EPS
 
 
+@pytest.mark.parametrize("dist", ["0", "1"])
 @pytest.mark.parametrize("m,n,nb", [(2048, 2048, 512), (1100, 1100, 256), (700, 1000, 128), (1000, 700, 128)])
-def test_getrf_transposed_u_row_is_bitwise_the_default(sl, monkeypatch, m, n, nb):
+def test_getrf_transposed_u_row_is_bitwise_the_default(sl, monkeypatch, m, n, nb, dist):
+    monkeypatch.setenv("SB200_GETRF_DIST", dist)            # 1 = the p x q driver (getrf_dist.cu) on one rank
+
     def run():
         A = sl.Matrix(m, n, nb).generate("rand", 42)
         piv, info = sl.getrf(A)
