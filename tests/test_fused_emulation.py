@@ -21,3 +21,13 @@ def test_panel_ll_protocol_emulation():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.main()
+
+
+def test_streaming_potrf_schedule_model():
+    """scratch/emulate_stream_potrf.py: the stream / event schedule of potrf with streaming input (chunks, catch-up updates)
+    executed in random event-respecting interleavings gives bitwise the right-looking factor and never touches a chunk
+    before its arrival."""
+    spec = importlib.util.spec_from_file_location("emulate_stream_potrf", os.path.join(ROOT, "scratch", "emulate_stream_potrf.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
