@@ -31,3 +31,12 @@ def test_streaming_potrf_schedule_model():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.main()
+
+
+def test_fused_tile_flag_protocol_emulation():
+    """scratch/emulate_tile_flags.py: the rowcnt / diagf release-acquire pipeline of potrf_tile_fused_kernel with one thread
+    per CTA started in shuffled order: no deadlock, LAPACK's factor, first failing minor, FAILED propagation."""
+    spec = importlib.util.spec_from_file_location("emulate_tile_flags", os.path.join(ROOT, "scratch", "emulate_tile_flags.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
