@@ -6,7 +6,7 @@ set -o pipefail
 OUT=gpurun_out; mkdir -p $OUT
 T0=$SECONDS
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-ALL="SB200_DIAG_MW=1 SB200_TILE_FUSED=1 SB200_TRSM_FUSED=7 SB200_PANEL_LL=1 SB200_GEMM_BT=1"
+ALL="SB200_DIAG_MW=1 SB200_TILE_FUSED=1 SB200_TRSM_FUSED=7 SB200_PANEL_LL=1 SB200_GEMM_BT=1 SB200_PANEL_SKINNY=1"
 MGPU_SIZES="1000x128,1024x256" timeout 300 $TR --master-port 29521 scratch/mgpu_check.py 1x2 2x1 > $OUT/r2m_check_default.log 2>&1
 echo "mgpu_check exit $?" >> $OUT/r2m_check_default.log; grep -E "grid|MGPU|exit|Error|error|FAIL" $OUT/r2m_check_default.log | tail -30
 echo "[$((SECONDS-T0)) s] check default"

@@ -27,9 +27,10 @@ GETRF = [("default", {}),
          ("panel_ll+row_trsm_fused", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "2"}),
          ("small_trsm_direct", {"SB200_TRSM_FUSED": "4"}),
          ("transposed_U_row", {"SB200_GEMM_BT": "1"}),
+         ("skinny_panel_update", {"SB200_PANEL_SKINNY": "1"}),
          ("panel_ll+all_row_solves", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6"}),
          ("panel_ll+all_row_solves+diag_mw", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1"}),
-         ("everything", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1", "SB200_GEMM_BT": "1"}),
+         ("everything", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1", "SB200_GEMM_BT": "1", "SB200_PANEL_SKINNY": "1"}),
          ("row_trsm_fused", {"SB200_TRSM_FUSED": "2"}),
          ("barrier+row_trsm_fused", {"SB200_PANEL_BARRIER": "1", "SB200_TRSM_FUSED": "2"})]
 MIXED = [("default", {}),
@@ -37,7 +38,7 @@ MIXED = [("default", {}),
          ("tile+trsm_fused+diag_mw", {"SB200_TILE_FUSED": "1", "SB200_TRSM_FUSED": "3", "SB200_DIAG_MW": "1"})]
 GEMM = [("default", {}), ("transposed_B_panel", {"SB200_GEMM_BT": "1"})]
 GMIXED = [("default", {}),
-          ("panel_ll+all_row_solves+diag_mw", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1"})]
+          ("panel_ll+all_row_solves+diag_mw+skinny", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1", "SB200_PANEL_SKINNY": "1"})]
 
 
 def one(routine, n, nb):

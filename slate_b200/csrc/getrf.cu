@@ -591,6 +591,55 @@ static int panel_base_wide(const PanelCtx<T>& x, int c0, int w)
     return SB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Skinny panel update (opt-in: SB200_PANEL_SKINNY=1; round-2 candidate, not yet run):
+//   A22(r, cc + c) -= sum_k L21(r, c0 + k) U12(k, c)      for every panel row r >= r0,  w1 <= 64,  n2 <= 64
+// in ONE launch over the whole tile stack.  12 of the 15 updates of an nb = 512 panel have w1, n2 <= 64; today each is
+// three launches of the tensor-core tile GEMM (top partial tile, full tiles, ragged last tile: ~17 us each, fixed
+// cost), although the work is 2 m_p w1 n2 flop on data that sits in L2.  Thread = one panel row (loads coalesced down
+// the tile columns), U12 broadcast from shared memory, the row's n2 results in registers.  Sums run over k in
+// increasing order with FMAs from zero and C - acc at the end, as the tile GEMM does.
+// ------------------------------------------------------------------------------------------
+constexpr int PSK_ROWS = 128;
+template <typename T, int N2T>
+__global__ void __launch_bounds__(PSK_ROWS)
+panel_update_skinny_kernel(T* const* __restrict__ tiles, int nb, int m_p, int r0, int c0, int w1, int cc, int n2)
+{
+    __shared__ T Us[64 * N2T];                       // Us[k * N2T + c] = U12(k, c), zero beyond n2
+    const int tid = threadIdx.x;
+    const T* top = tiles[0];
+    for (int e = tid; e < w1 * N2T; e += PSK_ROWS) {
+        const int k = e / N2T, c = e - k * N2T;
+        Us[e] = (c < n2) ? top[(c0 + k) + int64_t(cc + c) * nb] : T(0);
+    }
+    __syncthreads();
+    const int r = r0 + blockIdx.x * PSK_ROWS + tid;
+    if (r >= m_p) return;
+    T* row = tiles[r / nb] + (r % nb);
+    T acc[N2T];
+    #pragma unroll
+    for (int c = 0; c < N2T; ++c) acc[c] = T(0);
+    #pragma unroll 2
+    for (int k = 0; k < w1; ++k) {
+        const T l = row[int64_t(c0 + k) * nb];
+        #pragma unroll
+        for (int c = 0; c < N2T; ++c) acc[c] = fma_t(l, Us[k * N2T + c], acc[c]);
+    }
+    #pragma unroll
+    for (int c = 0; c < N2T; ++c)
+        if (c < n2) { T* p = row + int64_t(cc + c) * nb; *p = *p - acc[c]; }
+}
+
+template <typename T>
+static int launch_panel_update_skinny(T* const* stack, int nb, int m_p, int r0, int c0, int w1, int cc, int n2, cudaStream_t s)
+{
+    if (m_p <= r0) return SB200_OK;
+    const unsigned grid = unsigned(ceil_div(m_p - r0, PSK_ROWS));
+    if (n2 <= 32) panel_update_skinny_kernel<T, 32><<<grid, PSK_ROWS, 0, s>>>(stack, nb, m_p, r0, c0, w1, cc, n2);
+    else          panel_update_skinny_kernel<T, 64><<<grid, PSK_ROWS, 0, s>>>(stack, nb, m_p, r0, c0, w1, cc, n2);
+    return launch_status();
+}
+
 // columns [cc, cc+n2) of the panel, given that columns [c0, c0+w1) are factored:
 //   U12 = L11^{-1} A12 (rows c0..c0+w1 of the top tile), then A22 -= L21 U12 on rows [c0+w1, m_p)
 template <typename T>
@@ -605,6 +654,14 @@ static int panel_update(const PanelCtx<T>& x, int c0, int w1, int cc, int n2)
     x.pt->begin("pnl_gemm", x.s);
     const T* U12 = x.tile0 + c0 + int64_t(cc) * nb;
     const int r0 = c0 + w1;                                   // first row of A22 (inside the top tile)
+    {
+        const char* e = getenv("SB200_PANEL_SKINNY");         // opt-in (round-2 candidate, not yet run), read per call
+        if (e && atoi(e) != 0 && w1 <= 64 && n2 <= 64) {
+            SB_TRY(launch_panel_update_skinny<T>(x.stack, nb, x.m_p, r0, c0, w1, cc, n2, x.s));
+            x.pt->end(x.s);
+            return SB200_OK;
+        }
+    }
     const int top_rows = std::min(nb, x.m_p) - r0;
     if (top_rows > 0) {
         GemmParamsT<T> p{};

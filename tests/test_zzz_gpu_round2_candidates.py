@@ -19,6 +19,9 @@
 * SB200_GEMM_BT=1 -- dgemm (SUMMA) with the B row panel transposed once per step so that the multiply runs as 'N','T'
   (both operands through TMA bulk copies): bitwise the default C.
 
+* SB200_PANEL_SKINNY=1 -- the w1, n2 <= 64 updates inside the recursive LU panel as ONE row-per-thread launch over the
+  tile stack instead of three tile-GEMM launches (csrc/getrf.cu, panel_update_skinny_kernel).
+
 Written after round 1's GPU budget was spent: SKIPPED unless SB200_RUN_UNVALIDATED=1 (round 2: run, fix, drop the guard,
 then make the winner the default)."""
 import os
@@ -501,3 +504,28 @@ def test_getrf_transposed_u_row_is_bitwise_the_default(sl, monkeypatch, m, n, nb
     p1, i1, a1 = run()
     assert i0 == i1 == 0 and p0 == p1
     assert np.array_equal(a0, a1)
+
+
+@pytest.mark.parametrize("t", ["d", "s"])
+@pytest.mark.parametrize("dist", ["0", "1"])
+@pytest.mark.parametrize("m,n,nb", [(2048, 2048, 512), (1100, 1100, 256), (700, 300, 128), (300, 700, 128), (8192, 512, 512)])
+def test_getrf_skinny_panel_update(sl, monkeypatch, m, n, nb, dist, t):
+    if t == "s" and dist == "1":
+        pytest.skip("the FP32 p x q driver is covered through gesv_mixed")
+    monkeypatch.setenv("SB200_GETRF_DIST", dist)
+
+    def run():
+        A = sl.Matrix(m, n, nb, dtype=t).generate("rand", 42)
+        piv, info = sl.getrf(A)
+        return piv, info, A.to_host()
+
+    monkeypatch.delenv("SB200_PANEL_SKINNY", raising=False)
+    p0, i0, a0 = run()
+    monkeypatch.setenv("SB200_PANEL_SKINNY", "1")
+    p1, i1, a1 = run()
+    assert i0 == i1 == 0 and p0 == p1, "pivots differ from the default path"
+    tol = 1e-13 if t == "d" else 1e-5
+    assert np.abs(a1.astype(np.float64) - a0.astype(np.float64)).max() <= tol * np.abs(a0).max()
+    if t == "d" and m * n <= 2048 * 2048:
+        LUo, pivo, info_o = o.getrf(o.generate("rand", m, n, 42), nb, 32)
+        assert p1 == pivo and np.abs(a1 - LUo).max() <= 1e-11 * np.abs(LUo).max()
