@@ -375,6 +375,8 @@ int sb200_matrix_create_##X(sb200_grid_t g, int kind, int layout, int64_t m, int
 int sb200_gemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* C = alpha A A^H + beta C, C Hermitian lower  slate::herk (src/herk.cc:25-162; real types: syrk) */ \
 int sb200_herk_mat_##X(R alpha, sb200_matrix_t A, R beta, sb200_matrix_t C, const sb200_options_t* opts); \
+/* C = alpha A B^H + conj(alpha) B A^H + beta C, C Hermitian lower   slate::her2k (src/her2k.cc:27-170; real types: syr2k) */ \
+int sb200_her2k_mat_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, R beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* A = L L^H, lower                             slate::potrf (src/potrf.cc:22-210) */ \
 int sb200_potrf_##X(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info); \
 /* the same, streaming every finished block column into the packed host buffer `htiles` (order and size of \

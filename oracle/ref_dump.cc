@@ -332,6 +332,26 @@ int run(const Args& a)
         gflop = blas::Gflop<T>::hemm(slate::Side::Left, n, nrhs);
         if (dump) { auto d = to_dense(C); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
     }
+    else if (a.routine == "her2k") {
+        // C = alpha A B^H + conj(alpha) B A^H + beta C, C Hermitian lower (test/test_her2k.cc; slate::her2k, src/her2k.cc)
+        int64_t k = a.geti("k", n);
+        auto A = make_matrix<T>(n, k, nb, a.seedA, "rand");
+        auto B = make_matrix<T>(n, k, nb, a.seedB, "rand");
+        slate::HermitianMatrix<T> C(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        C.insertLocalTiles();
+        slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedC;
+        p.cond_request = p.cond_actual = p.condD = NAN;
+        slate::generate_matrix(p, C);
+        real_t rb = std::real(beta);
+        auto t0 = tic();
+        slate::her2k(alpha, A, B, rb, C, opts);
+        seconds = toc(t0);
+        gflop = blas::Gflop<T>::her2k(n, k);
+        if (dump) {
+            auto d = tz_to_dense<slate::HermitianMatrix<T>, T>(C, true);
+            write_raw(a.prefix + ".out.bin", d.data(), d.size());
+        }
+    }
     else if (a.routine == "norms") {
         // max / one / inf / fro of a general rand matrix: slate::norm (src/norm.cc)
         int64_t m = a.geti("m", n);

@@ -327,6 +327,34 @@ def getrs(LU, pivots, B, nb: int):
     return tri_sweep(np.triu(LU), Y, nb, lower=False)
 
 
+# ----------------------------------------------------------------------------
+# her2k: lower C = alpha A B^H + conj(alpha) B A^H + beta C (src/her2k.cc:27-170; internal_her2k.cc):
+# one block column k of A and B per step, diagonal tiles by tile her2k (stored triangle, real diagonal),
+# off-diagonal tiles by two gemms.  Real types: syr2k.
+# ----------------------------------------------------------------------------
+def her2k(alpha, A, B, beta, C, nb: int):
+    C = np.array(C, order="F", copy=True)
+    n = C.shape[0]
+    for idx, (k0, k1) in enumerate(_tiles(A.shape[1], nb)):
+        b = beta if idx == 0 else 1.0
+        for (j0, j1) in _tiles(n, nb):
+            for (i0, i1) in _tiles(n, nb):
+                if i0 < j0:
+                    continue
+                upd = (alpha * (A[i0:i1, k0:k1] @ B[j0:j1, k0:k1].conj().T)
+                       + np.conj(alpha) * (B[i0:i1, k0:k1] @ A[j0:j1, k0:k1].conj().T) + b * C[i0:i1, j0:j1])
+                if i0 == j0:
+                    mask = np.tril(np.ones_like(upd, dtype=bool))
+                    blk = C[i0:i1, j0:j1]
+                    blk[mask] = upd[mask]
+                    if np.iscomplexobj(blk):
+                        di = np.arange(blk.shape[0])
+                        blk[di, di] = blk[di, di].real
+                else:
+                    C[i0:i1, j0:j1] = upd
+    return C
+
+
 def he_full(A_lower):
     """Full Hermitian matrix from its stored lower triangle (diagonal taken real)."""
     L = np.tril(A_lower)

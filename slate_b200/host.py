@@ -68,6 +68,7 @@ _potrf_to_host = {t: _sig(f"sb200_potrf_to_host_local_{t}", [c_ptr, _OP, ctypes.
 _potrf_stream = {t: _sig(f"sb200_potrf_stream_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64), c_ptr, c_ptr]) for t in "sdcz"}
 _gemm = {t: _sig(f"sb200_gemm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
 _herk = {t: _sig(f"sb200_herk_mat_{t}", [REAL_T[t], c_ptr, REAL_T[t], c_ptr, _OP]) for t in "sdcz"}
+_her2k = {t: _sig(f"sb200_her2k_mat_{t}", [SCALAR_T[t], c_ptr, c_ptr, REAL_T[t], c_ptr, _OP]) for t in "sdcz"}
 _hemm = {t: _sig(f"sb200_hemm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
 _potrs = {t: _sig(f"sb200_potrs_{t}", [c_ptr, c_ptr, _OP]) for t in "sdcz"}
 _norm_inf = {t: _sig(f"sb200_norm_inf_{t}", [c_ptr, ctypes.POINTER(c_dbl)]) for t in "sdcz"}
@@ -319,6 +320,17 @@ def herk(alpha: float, A: Matrix, beta: float, C: "HermitianMatrix", opts: dict 
 
 
 rank_k_update = herk
+
+
+def her2k(alpha, A: Matrix, B: Matrix, beta: float, C: "HermitianMatrix", opts: dict | None = None):
+    """C = alpha A B^H + conj(alpha) B A^H + beta C, C Hermitian (lower), beta real (slate::her2k, src/her2k.cc:27-170;
+    for real types this is syr2k)."""
+    t = _same_type(A, B, C)
+    o = _opts(opts)
+    check(_her2k[t](scalar(t, alpha), A._h, B._h, REAL_T[t](float(beta)), C._h, ctypes.byref(o)), "her2k")
+
+
+rank_2k_update = her2k
 
 
 def hemm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | None = None):

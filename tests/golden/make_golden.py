@@ -20,6 +20,7 @@ generator fixture pins that), only outputs:
   gesv_d.npz             lu_factor + lu_solve_using_factor solution, n=300 nb=128
   hemm_z.npz             C = alpha A B + beta C, A Hermitian lower, n=192 nb=64 nrhs=70
   potrf_z.npz            complex Cholesky factor, n=192 nb=64
+  her2k_d.npz, her2k_z.npz  C = alpha A B^H + conj(alpha) B A^H + beta C lower, n=200 k=100 nb=64 (ragged tiles)
 
 Usage (in the build container, where /root/reference exists):  python tests/golden/make_golden.py
 """
@@ -92,8 +93,11 @@ def main():
     np.savez_compressed(os.path.join(OUT, "hemm_z.npz"), out=f["out"].reshape(192, 70, order="F"))
     f, meta = run("potrf", "z", 192, 64)
     np.savez_compressed(os.path.join(OUT, "potrf_z.npz"), out=f["out"].reshape(192, 192, order="F"), info=meta["info"])
+    # section 8(f) item 3 widening: her2k / syr2k
+    for t in "dz":
+        f, _ = run("her2k", t, 200, 64, k=100)
+        np.savez_compressed(os.path.join(OUT, f"her2k_{t}.npz"), out=f["out"].reshape(200, 200, order="F"))
     print("golden fixtures written to", OUT)
-
 
 if __name__ == "__main__":
     main()

@@ -93,6 +93,19 @@ def test_herk_matches_reference(golden_dir, t, dtype):
     assert np.abs(out - ref).max() <= 64 * EPS * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("t,dtype", [("d", np.float64), ("z", np.complex128)])
+def test_her2k_matches_reference(golden_dir, t, dtype):
+    g = load(golden_dir, f"her2k_{t}")
+    n, k, nb = 200, 100, 64
+    A = o.generate("rand", n, k, 42, dtype)
+    B = o.generate("rand", n, k, 43, dtype)
+    C = np.tril(o.generate("rand", n, n, 44, dtype))
+    al = ALPHA if t == "z" else ALPHA.real
+    out = np.tril(o.her2k(al, A, B, BETA.real, C, nb))
+    ref = np.tril(g["out"])
+    assert np.abs(out - ref).max() <= 64 * EPS * np.abs(ref).max()
+
+
 def test_trsm_matches_reference(golden_dir):
     g = load(golden_dir, "trsm_d")
     m, n = 256, 128

@@ -22,6 +22,9 @@
 * SB200_PANEL_SKINNY=1 -- the w1, n2 <= 64 updates inside the recursive LU panel as ONE row-per-thread launch over the
   tile stack instead of three tile-GEMM launches (csrc/getrf.cu, panel_update_skinny_kernel).
 
+* `her2k`: C = alpha A B^H + conj(alpha) B A^H + beta C on the herk skeleton (two batched launches
+  per step), against the reference's golden output and the oracle.
+
 Written after round 1's GPU budget was spent: SKIPPED unless SB200_RUN_UNVALIDATED=1 (round 2: run, fix, drop the guard,
 then make the winner the default)."""
 import os
@@ -529,3 +532,38 @@ def test_getrf_skinny_panel_update(sl, monkeypatch, m, n, nb, dist, t):
     if t == "d" and m * n <= 2048 * 2048:
         LUo, pivo, info_o = o.getrf(o.generate("rand", m, n, 42), nb, 32)
         assert p1 == pivo and np.abs(a1 - LUo).max() <= 1e-11 * np.abs(LUo).max()
+
+
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+def test_her2k_matches_reference_golden_and_oracle(sl, golden_dir, t):
+    """golden her2k_{d,z}.npz were written by the unmodified reference (slate::her2k, HostTask); s / c against the oracle"""
+    from tests.gpu_util import NP
+    n, k, nb = 200, 100, 64
+    al = (3.141592653589793 + 1.414213562373095j) if t in "cz" else 3.141592653589793
+    be = 2.718281828459045
+    A = sl.Matrix(n, k, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(n, k, nb, dtype=t).generate("rand", 43)
+    C = sl.HermitianMatrix(n, nb, dtype=t).generate("rand", 44)
+    sl.her2k(al, A, B, be, C)
+    out = np.tril(C.to_host())
+    a, b, c = (o.generate("rand", *shape, seed, NP[t]) for shape, seed in (((n, k), 42), ((n, k), 43), ((n, n), 44)))
+    wide = np.complex128 if t in "cz" else np.float64
+    ref = np.tril(o.her2k(al, a.astype(wide), b.astype(wide), be, np.tril(c).astype(wide), nb))
+    eps = EPS if t in "dz" else float(np.finfo(np.float32).eps)
+    assert np.abs(out - ref).max() <= 64 * eps * np.abs(ref).max()
+    if t in "dz":
+        g = np.load(os.path.join(golden_dir, f"her2k_{t}.npz"))
+        assert np.abs(out - np.tril(g["out"])).max() <= 64 * EPS * np.abs(g["out"]).max()
+    if t in "cz":
+        assert np.all(np.diag(out).imag == 0)
+
+
+def test_her2k_larger_and_ragged(sl):
+    n, k, nb = 1100, 700, 256
+    A = sl.Matrix(n, k, nb).generate("rand", 1)
+    B = sl.Matrix(n, k, nb).generate("rand", 2)
+    C = sl.HermitianMatrix(n, nb).generate("rand", 3)
+    sl.her2k(0.5, A, B, 1.5, C)
+    a, b, c = o.generate("rand", n, k, 1), o.generate("rand", n, k, 2), np.tril(o.generate("rand", n, n, 3))
+    ref = np.tril(0.5 * (a @ b.T) + 0.5 * (b @ a.T) + 1.5 * (c + np.tril(c, -1).T))
+    assert np.abs(np.tril(C.to_host()) - ref).max() <= 3 * np.sqrt(2 * k) * EPS * 4 * np.abs(ref).max()
