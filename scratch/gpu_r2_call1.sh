@@ -41,6 +41,9 @@ sec_switches() {
   done
 }
 sec_perf() {
+  # 3a. kernel-level timings of the chain pieces (potrf tile, panel / row / small solves), every per-call switch
+  timeout 300 python scratch/bench_tile.py 512 32 > $OUT/r2c1_bench_tile.log 2> $OUT/r2c1_bench_tile.err; cat $OUT/r2c1_bench_tile.log | cut -c1-200
+  stamp bench_tile
   # 3. timings of every variant (one fresh process each), phases on stderr
   timeout 300 python scratch/perf_variants.py gemm 16384 512 > $OUT/r2c1_perf_gemm.log 2> $OUT/r2c1_perf_gemm.err; cat $OUT/r2c1_perf_gemm.log | cut -c1-300
   stamp perf_gemm
