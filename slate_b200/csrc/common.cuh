@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuComplex.h>
 #include <stdint.h>
+#include <cstdlib>
 #include <atomic>
 #include "../../include/slate_b200.h"
 
@@ -24,6 +25,22 @@ inline int launch_status()
 }
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------- opt-in switches
+// Defaults of the round-2 candidates in ONE place (all 0 = off until they have run on a B200; flip here once
+// validated).  The environment variable of the same name overrides the default; every site reads it per call.
+struct Switch { const char* env; int dflt; };
+constexpr Switch SW_DIAG_MW      {"SB200_DIAG_MW", 0};        // multi-warp 64 x 64 Cholesky / inverse (diag64.cuh): 1 | 2 (rsqrt)
+constexpr Switch SW_TILE_FUSED   {"SB200_TILE_FUSED", 0};     // one-launch tile Cholesky: 1 | 2 (rsqrt)
+constexpr Switch SW_TRSM_FUSED   {"SB200_TRSM_FUSED", 0};     // bit 0 panel solve, bit 1 row solve, bit 2 small-triangle solve
+constexpr Switch SW_PANEL_LL     {"SB200_PANEL_LL", 0};       // LU base kernel with tagged-word exchange
+constexpr Switch SW_PANEL_SKINNY {"SB200_PANEL_SKINNY", 0};   // one-launch skinny update inside the LU panel
+constexpr Switch SW_GEMM_BT      {"SB200_GEMM_BT", 0};        // transposed B panel / U row: 'N','T' multiply
+inline int switch_value(const Switch& s)
+{
+    const char* e = getenv(s.env);
+    return e ? atoi(e) : s.dflt;
+}
 
 inline bool valid_op(int op)       { return op == 'N' || op == 'T' || op == 'C'; }
 inline bool valid_layout(int l)    { return l == 'C' || l == 'R'; }

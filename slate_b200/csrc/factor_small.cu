@@ -493,8 +493,7 @@ trtri_diag_mw_kernel(const R* __restrict__ Tm, int ldt, int na, int lower, int u
 // 2 = multi-warp with one rsqrt per column
 static int diag_mw_mode()
 {
-    const char* e = getenv("SB200_DIAG_MW");
-    return e ? atoi(e) : 0;
+    return switch_value(SW_DIAG_MW);
 }
 
 template <typename T> struct IsRealType { static constexpr bool value = false; };
@@ -614,8 +613,7 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
     if constexpr (IsRealType<T>::value) {
         // opt-in (round-2 candidate, not yet run): bit 2 = a small triangle (na <= 64: the U12 solves inside the LU panel)
         // by direct substitution in one launch, no inversion kernel
-        const char* e = getenv("SB200_TRSM_FUSED");
-        if (e && (atoi(e) & 4) && left && lower && op == 'N' && na <= IB) {
+        if ((switch_value(SW_TRSM_FUSED) & 4) && left && lower && op == 'N' && na <= IB) {
             if constexpr (std::is_same<T, double>::value) return trsm_lln_small_d(na, n, alpha, unit, Tm, ldt, dB, offB, ldb, batch, stream);
             else                                          return trsm_lln_small_s(na, n, alpha, unit, Tm, ldt, dB, offB, ldb, batch, stream);
         }
@@ -627,8 +625,7 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
         //   bit 0: the Cholesky panel solve (Right, Lower, Trans, NonUnit)
         //   bit 1: the LU row solve (Left, Lower, NoTrans, Unit / NonUnit)      (bit 2: see above)
         // read per call so that a test can switch it
-        const char* e = getenv("SB200_TRSM_FUSED");
-        const int fused = e ? atoi(e) : 0;
+        const int fused = switch_value(SW_TRSM_FUSED);
         if ((fused & 1) && ! left && lower && op != 'N' && ! unit && na > IB) {
             if constexpr (std::is_same<T, double>::value) return trsm_rlt_fused_d(m, na, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
             else                                          return trsm_rlt_fused_s(m, na, alpha, Tm, ldt, W, dB, offB, ldb, batch, stream);
@@ -699,8 +696,7 @@ int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cuda
     if constexpr (IsRealType<T>::value) {
         // opt-in (round-2 candidate, not yet run): the whole tile in one launch (potrf_tile_fused.cu); read per call
         // so that a test can switch it
-        const char* e = getenv("SB200_TILE_FUSED");
-        const int fused = e ? atoi(e) : 0;
+        const int fused = switch_value(SW_TILE_FUSED);
         if (fused > 0 && n > IB) {
             if constexpr (std::is_same<T, double>::value) st = potrf_tile_fused_d(n, A, lda, dinfo, info_base, fused, stream);
             else                                          st = potrf_tile_fused_s(n, A, lda, dinfo, info_base, fused, stream);

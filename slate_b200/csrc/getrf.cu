@@ -506,7 +506,7 @@ int PanelScratch::init()
     bar = reinterpret_cast<unsigned*>(p); p += 64;
     ll = reinterpret_cast<unsigned long long*>(p);
     { const char* e = getenv("SB200_PANEL_BARRIER"); use_bar = e && atoi(e) != 0; }
-    { const char* e = getenv("SB200_PANEL_LL"); use_ll = e && atoi(e) != 0; }
+    use_ll = switch_value(SW_PANEL_LL) != 0;
     if (use_ll) CUDA_TRY(cudaMemset(ll, 0, ll_bytes));          // tag 0 is never used by a launch
     gen_base = 0;
     static thread_local bool attr_done[64] = {};
@@ -655,8 +655,8 @@ static int panel_update(const PanelCtx<T>& x, int c0, int w1, int cc, int n2)
     const T* U12 = x.tile0 + c0 + int64_t(cc) * nb;
     const int r0 = c0 + w1;                                   // first row of A22 (inside the top tile)
     {
-        const char* e = getenv("SB200_PANEL_SKINNY");         // opt-in (round-2 candidate, not yet run), read per call
-        if (e && atoi(e) != 0 && w1 <= 64 && n2 <= 64) {
+        // opt-in (round-2 candidate, not yet run), read per call
+        if (switch_value(SW_PANEL_SKINNY) != 0 && w1 <= 64 && n2 <= 64) {
             SB_TRY(launch_panel_update_skinny<T>(x.stack, nb, x.m_p, r0, c0, w1, cc, n2, x.s));
             x.pt->end(x.s);
             return SB200_OK;
@@ -851,8 +851,7 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
     // 16-byte cp.async; 0.80 measured here).  Same products in the same order: bitwise the same factor.
     bool use_bt = false;
     if constexpr (std::is_same<T, double>::value) {
-        const char* e = getenv("SB200_GEMM_BT");
-        use_bt = e && atoi(e) != 0 && ! use_tc05;
+        use_bt = switch_value(SW_GEMM_BT) != 0 && ! use_tc05;
     }
     DevBuf wsUt;
     const int64_t te_ = nb * nb;

@@ -183,8 +183,7 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
     // slots, written once per step after the row solve, so that the trailing update runs as 'N','T' (see getrf.cu)
     bool use_bt = false;
     if constexpr (std::is_same<T, double>::value) {
-        const char* e = getenv("SB200_GEMM_BT");
-        use_bt = e && atoi(e) != 0 && ! use_tc05;
+        use_bt = switch_value(SW_GEMM_BT) != 0 && ! use_tc05;
     }
     DBuf uwsT;
     if (use_bt) SB_TRY(uwsT.alloc(size_t(std::max(nt_loc, 1)) * te * sizeof(T)));

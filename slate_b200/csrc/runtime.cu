@@ -460,8 +460,7 @@ int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C)
     // bitwise the same C.
     bool use_bt = false;
     if constexpr (std::is_same<T, double>::value) {
-        const char* e = getenv("SB200_GEMM_BT");
-        use_bt = e && atoi(e) != 0;
+        use_bt = switch_value(SW_GEMM_BT) != 0;
     }
     DevBuf wsBt;
     if (use_bt) SB_TRY(wsBt.alloc(size_t(2) * std::max<int64_t>(C.nt_loc, 1) * te * sizeof(T)));
