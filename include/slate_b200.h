@@ -361,6 +361,13 @@ int sb200_matrix_to_host(sb200_matrix_t A, void* hA, int64_t lda, sb200_stream_t
 int sb200_matrix_from_host_local(sb200_matrix_t A, const void* htiles, sb200_stream_t stream);
 int sb200_matrix_to_host_local(sb200_matrix_t A, void* htiles, sb200_stream_t stream);
 int sb200_matrix_copy(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream);
+/* ScaLAPACK-style local arrays (Matrix::fromScaLAPACK, include/slate/Matrix.hh:75-99): `local` is this rank's
+ * column-major local array (leading dimension lld >= local rows) of the 2-D block-cyclic distribution with square
+ * nb x nb blocks on the matrix's p x q grid (column-major rank order): tile (i, j) sits at local offset
+ * ((i / p) * nb, (j / q) * nb).  Gathers the locally owned (stored) tiles into the HBM tile pool / scatters them
+ * back; on_device != 0: `local` is device memory. */
+int sb200_matrix_from_scalapack(sb200_matrix_t A, const void* local, int64_t lld, int on_device, sb200_stream_t stream);
+int sb200_matrix_to_scalapack(sb200_matrix_t A, void* local, int64_t lld, int on_device, sb200_stream_t stream);
 
 /* host-only description of the 2-D block-cyclic tile map (no GPU needed):
  * tileRank (include/slate/func.hh:96-104, GridOrder::Col), the number of tiles a rank stores, and the

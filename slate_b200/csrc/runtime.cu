@@ -787,6 +787,34 @@ static int matrix_host_copy(Matrix& A, void* hA, int64_t lda, bool to_host, cuda
     return SB200_OK;
 }
 
+// ScaLAPACK-style local array <-> local tiles (reference: Matrix::fromScaLAPACK,
+// include/slate/Matrix.hh:75-99 + BaseMatrix::tileLayoutConvert for the strided tiles).  The caller's local array is
+// column-major with leading dimension lld and holds this rank's blocks of the 2-D block-cyclic distribution packed
+// as ScaLAPACK does: tile (i, j) at local offset ((i / p) * nb, (j / q) * nb).  The reference views the user's memory
+// in place (strided tiles, ld = lld) and converts per tile when a kernel needs contiguous storage; here the tiles
+// are gathered once into the contiguous HBM pool (one 2-D copy per tile on the caller's stream) and scattered back
+// by the inverse call.  `on_device`: the local array is device memory (device-to-device copies) or host memory.
+static int matrix_scalapack_copy(Matrix& A, void* local, int64_t lld, bool on_device, bool to_local, cudaStream_t s)
+{
+    int64_t rows_loc = 0;                                  // ScaLAPACK numroc: rows of the local array
+    for (int64_t i = A.g->prow; i < A.mt; i += A.g->p) rows_loc += A.tile_mb(i);
+    if (lld < std::max<int64_t>(rows_loc, 1)) return SB200_EINVAL;
+    const size_t es = size_t(A.esize);
+    const cudaMemcpyKind k_in = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind k_out = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int64_t j = A.g->pcol; j < A.nt; j += A.g->q)
+        for (int64_t i = A.g->prow; i < A.mt; i += A.g->p) {
+            if (! A.stored(i, j)) continue;
+            char* d = reinterpret_cast<char*>(A.pool) + size_t(A.tile_index(i, j) * A.tile_elems()) * es;
+            const int64_t il = i / A.g->p, jl = j / A.g->q;
+            char* lp = static_cast<char*>(local) + size_t(il * A.nb + jl * A.nb * lld) * es;
+            const size_t w = size_t(A.tile_mb(i)) * es, hgt = size_t(A.tile_nb(j));
+            if (to_local) CUDA_TRY(cudaMemcpy2DAsync(lp, size_t(lld) * es, d, size_t(A.nb) * es, w, hgt, k_out, s));
+            else          CUDA_TRY(cudaMemcpy2DAsync(d, size_t(A.nb) * es, lp, size_t(lld) * es, w, hgt, k_in, s));
+        }
+    return SB200_OK;
+}
+
 // host-only description of the 2-D block-cyclic tile map (no GPU needed): used by the multi-rank
 // host logic and its CPU tests.  rank(i, j) = (i % p) + (j % q) * p (include/slate/func.hh:96-104).
 static int64_t local_tile_count(int kind, int p, int q, int rank, int64_t mt, int64_t nt)
@@ -936,6 +964,18 @@ int sb200_matrix_to_host_local(sb200_matrix_t h, void* htiles, sb200_stream_t st
     if (! h || ! htiles) return SB200_EINVAL;
     CUDA_TRY(cudaMemcpyAsync(htiles, h->A.pool, h->A.pool_bytes(), cudaMemcpyDeviceToHost, cudaStream_t(stream)));
     return SB200_OK;
+}
+
+int sb200_matrix_from_scalapack(sb200_matrix_t h, const void* local, int64_t lld, int on_device, sb200_stream_t stream)
+{
+    if (! h || ! local) return SB200_EINVAL;
+    return matrix_scalapack_copy(h->A, const_cast<void*>(local), lld, on_device != 0, false, cudaStream_t(stream));
+}
+
+int sb200_matrix_to_scalapack(sb200_matrix_t h, void* local, int64_t lld, int on_device, sb200_stream_t stream)
+{
+    if (! h || ! local) return SB200_EINVAL;
+    return matrix_scalapack_copy(h->A, local, lld, on_device != 0, true, cudaStream_t(stream));
 }
 
 int sb200_matrix_copy(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream)

@@ -61,6 +61,8 @@ _matrix_to_host_local = _sig("sb200_matrix_to_host_local", [c_ptr, c_ptr, c_ptr]
 _last_panel_ms = _sig("sb200_last_driver_panel_ms", [c_ptr], c_dbl)
 _matrix_copy = _sig("sb200_matrix_copy", [c_ptr, c_ptr, c_ptr])
 _matrix_local_tiles = _sig("sb200_matrix_local_tiles", [c_ptr], c_i64)
+_matrix_from_scalapack = _sig("sb200_matrix_from_scalapack", [c_ptr, c_ptr, c_i64, c_int, c_ptr])
+_matrix_to_scalapack = _sig("sb200_matrix_to_scalapack", [c_ptr, c_ptr, c_i64, c_int, c_ptr])
 _last_ms = _sig("sb200_last_driver_ms", [c_ptr], c_dbl)
 _potrf = {t: _sig(f"sb200_potrf_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64)]) for t in "sdcz"}
 _potrf["s_tc05"] = _sig("sb200_potrf_tc05_s", [c_ptr, _OP, ctypes.POINTER(c_i64)])
@@ -222,6 +224,33 @@ class Matrix:
             import torch
             torch.cuda.current_stream().synchronize()
         return htiles
+
+    def from_scalapack(self, local, lld: int | None = None, sync: bool = True):
+        """Gather this rank's tiles from a ScaLAPACK-style local array (Matrix::fromScaLAPACK, include/slate/Matrix.hh:75-99):
+        `local` is a torch tensor (CPU or CUDA) holding the column-major local array, leading dimension lld."""
+        lld = self._check_scalapack(local, lld)
+        check(_matrix_from_scalapack(self._h, local.data_ptr(), lld, 1 if local.is_cuda else 0, _stream()), "from_scalapack")
+        if sync:
+            import torch
+            torch.cuda.current_stream().synchronize()
+        return self
+
+    def to_scalapack(self, local, lld: int | None = None, sync: bool = True):
+        lld = self._check_scalapack(local, lld)
+        check(_matrix_to_scalapack(self._h, local.data_ptr(), lld, 1 if local.is_cuda else 0, _stream()), "to_scalapack")
+        if sync:
+            import torch
+            torch.cuda.current_stream().synchronize()
+        return local
+
+    def _check_scalapack(self, t, lld):
+        import torch
+        if not (isinstance(t, torch.Tensor) and t.dtype == _torch_dtype(self.dtype) and t.is_contiguous() and t.dim() == 2):
+            raise Exception_("local array must be a contiguous 2-D torch tensor [local columns][lld] of the matrix type")
+        lld = int(lld if lld is not None else t.shape[1])            # row-major [cols][lld] == column-major lld x cols
+        if lld > t.shape[1]:
+            raise Exception_("lld exceeds the local array")
+        return lld
 
     def _check_local(self, t):
         import torch
