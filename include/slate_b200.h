@@ -336,6 +336,9 @@ int sb200_potrf_d(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
 /* P A = L U, partial pivoting       (slate::getrf, src/getrf.cc).  pivots: host array of
  * 2*min(m,n) int64 (tileIndex, elementOffset) pairs relative to each panel, as slate::Pivots. */
 int sb200_getrf_d(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
+/* LU without pivoting (slate::getrf_nopiv, src/getrf_nopiv.cc:  A = L U, unit lower L); info = first zero pivot + 1 */
+int sb200_getrf_nopiv_d(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
+int sb200_getrf_nopiv_s(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
 /* device time of the last driver call on this matrix, milliseconds (CUDA events) */
 double sb200_last_driver_ms(sb200_matrix_t A);
 /* summed device time of the panel-stream critical work (diagonal factor / LU panel + solve +

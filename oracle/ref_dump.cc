@@ -231,6 +231,15 @@ int run(const Args& a)
             write_raw(a.prefix + ".piv.bin", flat.data(), flat.size());
         }
     }
+    else if (a.routine == "getrf_nopiv") {
+        // LU without pivoting (slate::getrf_nopiv, src/getrf_nopiv.cc); the tester uses a diagonally dominant matrix
+        auto A = make_matrix<T>(n, n, nb, a.seedA, a.get("kind", "rand_dominant"));
+        auto t0 = tic();
+        info = slate::getrf_nopiv(A, opts);
+        seconds = toc(t0);
+        gflop = lapack::Gflop<T>::getrf(n, n);
+        if (dump) { auto d = to_dense(A); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
+    }
     else if (a.routine == "trsm") {
         // Left/Lower/NoTrans/NonUnit solve  A X = alpha B, A = rand_dominant lower triangle
         int64_t m = a.geti("m", n);   // A is m x m, B is m x n

@@ -328,6 +328,31 @@ def getrs(LU, pivots, B, nb: int):
 
 
 # ----------------------------------------------------------------------------
+# getrf_nopiv: A = L U without pivoting (src/getrf_nopiv.cc:25-190; internal_getrf_nopiv.cc + Tile_getrf_nopiv.hh):
+# per step the diagonal tile is factored (ib-blocked, no search), the column below is solved against U_kk, the row to
+# the right against L_kk, the rest updated.  The factors of LU without pivoting are unique, so the blocking only
+# changes rounding; this restatement is the tile-level right-looking form.  info = first zero pivot + 1.
+# ----------------------------------------------------------------------------
+def getrf_nopiv(A, nb: int):
+    A = np.array(A, order="F", copy=True)
+    m, n = A.shape
+    info = 0
+    for (k0, k1) in _tiles(min(m, n), nb):
+        for j in range(k0, k1):                                   # diagonal tile (and, equivalently, the column below it)
+            piv = A[j, j]
+            if piv == 0:
+                info = info or j + 1
+                continue
+            A[j + 1:, j] /= piv
+            A[j + 1:, j + 1:k1] -= np.outer(A[j + 1:, j], A[j, j + 1:k1])
+        if k1 < n:
+            L = np.tril(A[k0:k1, k0:k1], -1) + np.eye(k1 - k0)
+            A[k0:k1, k1:] = np.linalg.solve(L, A[k0:k1, k1:])
+            A[k1:, k1:] -= A[k1:, k0:k1] @ A[k0:k1, k1:]
+    return A, info
+
+
+# ----------------------------------------------------------------------------
 # her2k: lower C = alpha A B^H + conj(alpha) B A^H + beta C (src/her2k.cc:27-170; internal_her2k.cc):
 # one block column k of A and B per step, diagonal tiles by tile her2k (stored triangle, real diagonal),
 # off-diagonal tiles by two gemms.  Real types: syr2k.

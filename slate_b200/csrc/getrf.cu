@@ -111,7 +111,10 @@ struct LLArgs {
     unsigned gen_base;        // getrf_base_ll_kernel; column j of this launch is tagged gen_base + j + 1
 };
 
-template <typename T>
+// NOPIV = true (getrf_nopiv, src/getrf_nopiv.cc): no candidate is ever proposed, so the diagonal entry is the pivot of
+// every column and the interchange logic below degenerates to the identity; everything else (the diagonal row's
+// broadcast, zero-pivot info, scaling, rank-1 update) is the same code.  SURVEY section 8(f) item 2.
+template <typename T, bool NOPIV = false>
 __global__ void __launch_bounds__(PTHREADS)
 getrf_base_kernel(const BaseArgs<T> a)
 {
@@ -142,12 +145,14 @@ getrf_base_kernel(const BaseArgs<T> a)
         // ---- local candidate: first maximum of |a| over this CTA's rows below the diagonal
         T best = T(-1);
         int brow = INT_MAX;
+        if constexpr (! NOPIV) {
         for (int lr = tid; lr < nr; lr += PTHREADS) {
             const int r = r_begin + lr;
             if (r > d) {
                 const T v = fabs(blk[j * RP + lr]);
                 if (v > best) { best = v; brow = r; }      // rows ascend per thread: first max kept
             }
+        }
         }
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -487,6 +492,10 @@ getrf_base_ll_kernel(const LLArgs<T> q)
         }
 }
 
+// set by the getrf_nopiv entry points around their driver call (the drivers construct their PanelScratch on the
+// calling thread); read once per driver call by PanelScratch::init
+static thread_local bool g_getrf_nopiv = false;
+
 int PanelScratch::init()
 {
     int dev = 0, sms = 0;
@@ -507,6 +516,7 @@ int PanelScratch::init()
     ll = reinterpret_cast<unsigned long long*>(p);
     { const char* e = getenv("SB200_PANEL_BARRIER"); use_bar = e && atoi(e) != 0; }
     use_ll = switch_value(SW_PANEL_LL) != 0;
+    nopiv = g_getrf_nopiv;
     if (use_ll) CUDA_TRY(cudaMemset(ll, 0, ll_bytes));          // tag 0 is never used by a launch
     gen_base = 0;
     static thread_local bool attr_done[64] = {};
@@ -514,6 +524,10 @@ int PanelScratch::init()
         CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(PW * (PROWS_MAX | 1) * sizeof(double))));
         CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(PW * (PROWS_MAX | 1) * sizeof(float))));
+        CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(PW * (PROWS_MAX | 1) * sizeof(double))));
+        CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(PW * (PROWS_MAX | 1) * sizeof(float))));
         CUDA_TRY(cudaFuncSetAttribute(getrf_base_ll_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(PW * (PROWS_MAX | 1) * sizeof(double))));
@@ -541,7 +555,11 @@ template <typename T>
 static int launch_base(BaseArgs<T>& a, int grid, size_t smem, PanelScratch& ps, cudaStream_t s)
 {
     cudaError_t e;
-    if (ps.use_ll) {
+    if (ps.nopiv) {                                             // getrf_nopiv: the barrier kernel without a pivot search
+        void* args[] = {&a};
+        e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel<T, true>), dim3(grid), dim3(PTHREADS), args, smem, s);
+    }
+    else if (ps.use_ll) {
         if (ps.gen_base > 0xF0000000u) {                        // tags about to wrap: start over from clean slots
             CUDA_TRY(cudaMemsetAsync(ps.ll, 0, ps.ll_bytes, s));
             ps.gen_base = 0;
@@ -1099,6 +1117,18 @@ template int launch_laswp<cuDoubleComplex>(cuDoubleComplex* const*, int64_t, int
 using namespace sb200;
 
 extern "C" {
+
+/* LU without pivoting (slate::getrf_nopiv, src/getrf_nopiv.cc): the getrf drivers with the pivot search switched off.
+ * STATUS: written after round 1's GPU budget was spent, not yet run (guarded test). */
+static int getrf_nopiv_any(sb200_matrix_t h, int64_t* info, bool is_float)
+{
+    if (! h) return SB200_EINVAL;
+    struct Guard { Guard() { g_getrf_nopiv = true; } ~Guard() { g_getrf_nopiv = false; } } guard;
+    std::vector<int64_t> piv(size_t(2 * std::max<int64_t>(std::min(h->A.m, h->A.n), 1)));
+    return is_float ? getrf_driver_s(h->A, piv.data(), info, false) : getrf_driver(h->A, piv.data(), info);
+}
+int sb200_getrf_nopiv_d(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { (void) opts; return getrf_nopiv_any(h, info, false); }
+int sb200_getrf_nopiv_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { (void) opts; return getrf_nopiv_any(h, info, true); }
 
 int sb200_getrf_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
 {

@@ -17,6 +17,7 @@ struct PanelScratch {
     unsigned long long* ll = nullptr;   // exchange buffers of the opt-in flag-in-data base kernel (SB200_PANEL_LL=1)
     unsigned gen_base = 0;              // generation tag of the next launch's first column, minus 1
     bool use_ll = false;
+    bool nopiv = false;                 // getrf_nopiv: base kernel without the pivot search
     size_t ll_bytes = 0;
     int max_ctas = 0;
     void* raw = nullptr;

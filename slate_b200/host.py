@@ -454,6 +454,22 @@ def getrf(A: Matrix, opts: dict | None = None):
 lu_factor = getrf
 
 
+_getrf_nopiv = {t: _sig(f"sb200_getrf_nopiv_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64)]) for t in "sd"}
+
+
+def getrf_nopiv(A: Matrix, opts: dict | None = None) -> int:
+    """LU without pivoting A = L U (slate::getrf_nopiv, src/getrf_nopiv.cc).  Returns info (first zero pivot + 1, or 0)."""
+    if A.t not in _getrf_nopiv:
+        raise Exception_(f"getrf_nopiv is implemented for float and double, not {A.dtype}")
+    o = _opts(opts)
+    info = c_i64(0)
+    check(_getrf_nopiv[A.t](A._h, ctypes.byref(o), ctypes.byref(info)), "getrf_nopiv")
+    return int(info.value)
+
+
+lu_factor_nopiv = getrf_nopiv
+
+
 def getrs(A: Matrix, pivots, B: Matrix, opts: dict | None = None):
     """Solve A X = B with the LU factors and pivots from getrf; B is overwritten (slate::getrs, src/getrs.cc)."""
     t = _same_type(A, B)

@@ -106,6 +106,20 @@ def test_her2k_matches_reference(golden_dir, t, dtype):
     assert np.abs(out - ref).max() <= 64 * EPS * np.abs(ref).max()
 
 
+def test_getrf_nopiv_matches_reference(golden_dir):
+    g = load(golden_dir, "getrf_nopiv_d")
+    n, nb = 300, 128
+    A = o.generate("rand_dominant", n, n, 42)
+    LU, info = o.getrf_nopiv(A, nb)
+    assert info == int(g["info"]) == 0
+    assert np.abs(LU - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+    L = np.tril(LU, -1) + np.eye(n); U = np.triu(LU)
+    assert np.abs(L @ U - A).max() <= 64 * EPS * np.abs(A).max()
+    Z = A.copy(); Z[:, 5] = 0.0; Z[5, 5] = 0.0; Z[5:, 5] = 0.0            # exact zero pivot at column 5 after elimination
+    Z[:5, 5] = 0.0
+    assert o.getrf_nopiv(Z, nb)[1] == 6
+
+
 def test_trsm_matches_reference(golden_dir):
     g = load(golden_dir, "trsm_d")
     m, n = 256, 128

@@ -27,6 +27,8 @@
 
 * `Matrix.from_scalapack / to_scalapack`: ScaLAPACK-style local array <-> HBM tile pool.
 
+* `getrf_nopiv`: the getrf drivers with the pivot search compiled out of the base kernel.
+
 Written after round 1's GPU budget was spent: SKIPPED unless SB200_RUN_UNVALIDATED=1 (round 2: run, fix, drop the guard,
 then make the winner the default)."""
 import os
@@ -600,3 +602,31 @@ def test_scalapack_local_array_round_trip(sl, kind, m, n, nb, on_device):
     else:
         assert np.array_equal(bk, G)
     assert np.all(back.cpu().numpy()[:, m:] == -1.0)                 # the padding rows of the local array are untouched
+
+
+@pytest.mark.parametrize("dist", ["0", "1"])
+@pytest.mark.parametrize("n,nb", [(300, 128), (1024, 256), (2048, 512)])
+def test_getrf_nopiv_matches_reference_golden_and_oracle(sl, golden_dir, monkeypatch, n, nb, dist):
+    monkeypatch.setenv("SB200_GETRF_DIST", dist)
+    A = sl.Matrix(n, n, nb).generate("rand_dominant", 42)
+    assert sl.getrf_nopiv(A) == 0
+    LU = A.to_host()
+    A0 = o.generate("rand_dominant", n, n, 42)
+    LUo, info = o.getrf_nopiv(A0, nb)
+    assert info == 0
+    assert np.abs(LU - LUo).max() <= 64 * EPS * np.abs(LUo).max()
+    L = np.tril(LU, -1) + np.eye(n); U = np.triu(LU)
+    assert np.abs(L @ U - A0).max() <= 64 * EPS * np.abs(A0).max()
+    if (n, nb) == (300, 128):
+        g = np.load(os.path.join(golden_dir, "getrf_nopiv_d.npz"))          # written by the unmodified reference
+        assert np.abs(LU - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+
+
+def test_getrf_nopiv_zero_pivot_info_and_pivoting_is_back_afterwards(sl):
+    n, nb = 256, 64
+    Z = o.generate("rand_dominant", n, n, 3); Z[:, 100] = 0.0
+    A = sl.Matrix(n, n, nb); A.from_host(np.asfortranarray(Z))
+    assert sl.getrf_nopiv(A) == o.getrf_nopiv(Z, nb)[1] == 101
+    B = sl.Matrix(n, n, nb).generate("rand", 42)                             # the switch is per call: getrf pivots again
+    piv, info = sl.getrf(B)
+    assert info == 0 and piv == o.getrf(o.generate("rand", n, n, 42), nb, 32)[1]
