@@ -22,6 +22,10 @@
 // through padded shared memory; the 64 x 64 Cholesky + inverse run in shared memory on all threads (diag64.cuh).
 // Failure (block not positive definite): info = info_base + column + 1 as the default path; the failing CTA
 // publishes FAILED on its flags and every later CTA leaves on seeing it.
+//
+// The same product micro-kernels serve the other opt-in one-launch kernels further down (SB200_TRSM_FUSED):
+// trsm_rlt_fused_kernel (Cholesky panel solve), trsm_lln_fused_kernel (LU row solve), trsm_lln_small_kernel (small
+// triangle, direct substitution).  CPU transcriptions of all of them: scratch/emulate_fused.py.
 #include "common.cuh"
 #include "diag64.cuh"
 #include "runtime_internal.hh"
