@@ -387,6 +387,10 @@ int sb200_gemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_ma
 int sb200_herk_mat_##X(R alpha, sb200_matrix_t A, R beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* C = alpha A B^H + conj(alpha) B A^H + beta C, C Hermitian lower   slate::her2k (src/her2k.cc:27-170; real types: syr2k) */ \
 int sb200_her2k_mat_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, R beta, sb200_matrix_t C, const sb200_options_t* opts); \
+/* (complex-)symmetric rank-k / rank-2k updates, no conjugation, C symmetric lower (kind 'H' storage: lower tiles) \
+ * slate::syrk (src/syrk.cc), slate::syr2k (src/syr2k.cc); for real types the same as herk / her2k */ \
+int sb200_syrk_mat_##X(T alpha, sb200_matrix_t A, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
+int sb200_syr2k_mat_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* A = L L^H, lower                             slate::potrf (src/potrf.cc:22-210) */ \
 int sb200_potrf_##X(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info); \
 /* the same, streaming every finished block column into the packed host buffer `htiles` (order and size of \

@@ -361,6 +361,27 @@ int run(const Args& a)
             write_raw(a.prefix + ".out.bin", d.data(), d.size());
         }
     }
+    else if (a.routine == "syrk" || a.routine == "syr2k") {
+        // complex-symmetric rank-k / rank-2k updates (no conjugation; slate::syrk, src/syrk.cc; slate::syr2k, src/syr2k.cc):
+        // C = alpha A A^T + beta C   /   C = alpha A B^T + alpha B A^T + beta C,  C symmetric lower, alpha / beta scalar_t
+        int64_t k = a.geti("k", n);
+        auto A = make_matrix<T>(n, k, nb, a.seedA, "rand");
+        auto B = make_matrix<T>(n, k, nb, a.seedB, "rand");
+        slate::SymmetricMatrix<T> C(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        C.insertLocalTiles();
+        slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedC;
+        p.cond_request = p.cond_actual = p.condD = NAN;
+        slate::generate_matrix(p, C);
+        auto t0 = tic();
+        if (a.routine == "syrk") slate::syrk(alpha, A, beta, C, opts);
+        else                     slate::syr2k(alpha, A, B, beta, C, opts);
+        seconds = toc(t0);
+        gflop = a.routine == "syrk" ? blas::Gflop<T>::syrk(n, k) : blas::Gflop<T>::syr2k(n, k);
+        if (dump) {
+            auto d = tz_to_dense<slate::SymmetricMatrix<T>, T>(C, true);
+            write_raw(a.prefix + ".out.bin", d.data(), d.size());
+        }
+    }
     else if (a.routine == "norms") {
         // max / one / inf / fro of a general rand matrix: slate::norm (src/norm.cc)
         int64_t m = a.geti("m", n);

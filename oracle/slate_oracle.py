@@ -380,6 +380,47 @@ def her2k(alpha, A, B, beta, C, nb: int):
     return C
 
 
+# ----------------------------------------------------------------------------
+# syrk / syr2k for complex-symmetric C (no conjugation; src/syrk.cc, src/syr2k.cc): alpha, beta are full scalars and
+# the diagonal stays complex.  (For real types they coincide with herk / her2k.)
+# ----------------------------------------------------------------------------
+def syrk(alpha, A, beta, C, nb: int):
+    C = np.array(C, order="F", copy=True)
+    n = C.shape[0]
+    for idx, (k0, k1) in enumerate(_tiles(A.shape[1], nb)):
+        b = beta if idx == 0 else 1.0
+        for (j0, j1) in _tiles(n, nb):
+            for (i0, i1) in _tiles(n, nb):
+                if i0 < j0:
+                    continue
+                upd = alpha * (A[i0:i1, k0:k1] @ A[j0:j1, k0:k1].T) + b * C[i0:i1, j0:j1]
+                if i0 == j0:
+                    mask = np.tril(np.ones_like(upd, dtype=bool))
+                    C[i0:i1, j0:j1][mask] = upd[mask]
+                else:
+                    C[i0:i1, j0:j1] = upd
+    return C
+
+
+def syr2k(alpha, A, B, beta, C, nb: int):
+    C = np.array(C, order="F", copy=True)
+    n = C.shape[0]
+    for idx, (k0, k1) in enumerate(_tiles(A.shape[1], nb)):
+        b = beta if idx == 0 else 1.0
+        for (j0, j1) in _tiles(n, nb):
+            for (i0, i1) in _tiles(n, nb):
+                if i0 < j0:
+                    continue
+                upd = (alpha * (A[i0:i1, k0:k1] @ B[j0:j1, k0:k1].T) + alpha * (B[i0:i1, k0:k1] @ A[j0:j1, k0:k1].T)
+                       + b * C[i0:i1, j0:j1])
+                if i0 == j0:
+                    mask = np.tril(np.ones_like(upd, dtype=bool))
+                    C[i0:i1, j0:j1][mask] = upd[mask]
+                else:
+                    C[i0:i1, j0:j1] = upd
+    return C
+
+
 def he_full(A_lower):
     """Full Hermitian matrix from its stored lower triangle (diagonal taken real)."""
     L = np.tril(A_lower)

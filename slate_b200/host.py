@@ -361,6 +361,23 @@ def her2k(alpha, A: Matrix, B: Matrix, beta: float, C: "HermitianMatrix", opts: 
 
 rank_2k_update = her2k
 
+_syrk = {t: _sig(f"sb200_syrk_mat_{t}", [SCALAR_T[t], c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+_syr2k = {t: _sig(f"sb200_syr2k_mat_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+
+
+def syrk(alpha, A: Matrix, beta, C: "HermitianMatrix", opts: dict | None = None):
+    """C = alpha A A^T + beta C, C symmetric (lower tiles), no conjugation (slate::syrk, src/syrk.cc)."""
+    t = _same_type(A, C)
+    o = _opts(opts)
+    check(_syrk[t](scalar(t, alpha), A._h, scalar(t, beta), C._h, ctypes.byref(o)), "syrk")
+
+
+def syr2k(alpha, A: Matrix, B: Matrix, beta, C: "HermitianMatrix", opts: dict | None = None):
+    """C = alpha A B^T + alpha B A^T + beta C, C symmetric (lower tiles), no conjugation (slate::syr2k, src/syr2k.cc)."""
+    t = _same_type(A, B, C)
+    o = _opts(opts)
+    check(_syr2k[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "syr2k")
+
 
 def hemm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | None = None):
     """C = alpha A B + beta C with A Hermitian, Side::Left (slate::hemm, src/hemmC.cc)."""

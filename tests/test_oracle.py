@@ -106,6 +106,18 @@ def test_her2k_matches_reference(golden_dir, t, dtype):
     assert np.abs(out - ref).max() <= 64 * EPS * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("routine", ["syrk", "syr2k"])
+def test_complex_symmetric_rank_updates_match_reference(golden_dir, routine):
+    g = load(golden_dir, f"{routine}_z")
+    n, k, nb = 200, 100, 64
+    A = o.generate("rand", n, k, 42, np.complex128)
+    B = o.generate("rand", n, k, 43, np.complex128)
+    C = np.tril(o.generate("rand", n, n, 44, np.complex128))
+    out = o.syrk(ALPHA, A, BETA, C, nb) if routine == "syrk" else o.syr2k(ALPHA, A, B, BETA, C, nb)
+    ref = np.tril(g["out"])
+    assert np.abs(np.tril(out) - ref).max() <= 64 * EPS * np.abs(ref).max()
+
+
 def test_getrf_nopiv_matches_reference(golden_dir):
     g = load(golden_dir, "getrf_nopiv_d")
     n, nb = 300, 128

@@ -630,3 +630,29 @@ def test_getrf_nopiv_zero_pivot_info_and_pivoting_is_back_afterwards(sl):
     B = sl.Matrix(n, n, nb).generate("rand", 42)                             # the switch is per call: getrf pivots again
     piv, info = sl.getrf(B)
     assert info == 0 and piv == o.getrf(o.generate("rand", n, n, 42), nb, 32)[1]
+
+
+@pytest.mark.parametrize("t", ["z", "c", "d"])
+@pytest.mark.parametrize("routine", ["syrk", "syr2k"])
+def test_symmetric_rank_updates_match_reference_golden_and_oracle(sl, golden_dir, routine, t):
+    """complex-symmetric syrk / syr2k (no conjugation, complex diagonal kept); golden {syrk,syr2k}_z.npz from the reference"""
+    from tests.gpu_util import NP
+    n, k, nb = 200, 100, 64
+    al = (3.141592653589793 + 1.414213562373095j) if t in "cz" else 3.141592653589793
+    be = (2.718281828459045 + 1.732050807568877j) if t in "cz" else 2.718281828459045
+    A = sl.Matrix(n, k, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(n, k, nb, dtype=t).generate("rand", 43)
+    C = sl.HermitianMatrix(n, nb, dtype=t).generate("rand", 44)
+    if routine == "syrk":
+        sl.syrk(al, A, be, C)
+    else:
+        sl.syr2k(al, A, B, be, C)
+    out = np.tril(C.to_host())
+    wide = np.complex128 if t in "cz" else np.float64
+    a, b, c = (o.generate("rand", *shape, seed, NP[t]).astype(wide) for shape, seed in (((n, k), 42), ((n, k), 43), ((n, n), 44)))
+    ref = np.tril(o.syrk(al, a, be, np.tril(c), nb) if routine == "syrk" else o.syr2k(al, a, b, be, np.tril(c), nb))
+    eps = EPS if t in "dz" else float(np.finfo(np.float32).eps)
+    assert np.abs(out - ref).max() <= 64 * eps * np.abs(ref).max()
+    if t == "z":
+        g = np.load(os.path.join(golden_dir, f"{routine}_z.npz"))
+        assert np.abs(out - np.tril(g["out"])).max() <= 64 * EPS * np.abs(g["out"]).max()
