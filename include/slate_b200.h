@@ -404,6 +404,8 @@ int sb200_potrf_stream_##X(sb200_matrix_t A, const sb200_options_t* opts, int64_
 int sb200_potrs_##X(sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
 /* C = alpha A X + beta C, A Hermitian lower, Side::Left   slate::hemm (src/hemmC.cc); 1 x 1 grid */ \
 int sb200_hemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
+/* C = alpha A X + beta C, A (complex-)symmetric lower, Side::Left, no conjugation   slate::symm (src/symm.cc); 1 x 1 grid */ \
+int sb200_symm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t X, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* norm(Norm::Inf, A), A general or Hermitian   slate::norm (src/norm.cc); 1 x 1 grid */ \
 int sb200_norm_inf_##X(sb200_matrix_t A, double* value);
 SB200_FOR_TYPES(SB200_DECL_RUNTIME)

@@ -382,6 +382,21 @@ int run(const Args& a)
             write_raw(a.prefix + ".out.bin", d.data(), d.size());
         }
     }
+    else if (a.routine == "symm") {
+        // C = alpha A B + beta C, A complex-symmetric (lower), Side::Left (test/test_symm.cc; slate::symm, src/symm.cc)
+        slate::SymmetricMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        A.insertLocalTiles();
+        slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand"); p.seed = a.seedA;
+        p.cond_request = p.cond_actual = p.condD = NAN;
+        slate::generate_matrix(p, A);
+        auto B = make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
+        auto C = make_matrix<T>(n, nrhs, nb, a.seedC, "rand");
+        auto t0 = tic();
+        slate::symm(slate::Side::Left, alpha, A, B, beta, C, opts);
+        seconds = toc(t0);
+        gflop = blas::Gflop<T>::symm(slate::Side::Left, n, nrhs);
+        if (dump) { auto d = to_dense(C); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
+    }
     else if (a.routine == "norms") {
         // max / one / inf / fro of a general rand matrix: slate::norm (src/norm.cc)
         int64_t m = a.geti("m", n);

@@ -441,6 +441,22 @@ def hemm(alpha, A_lower, B, beta, C, nb: int):
     return C
 
 
+def sy_full(A_lower):
+    """Full (complex-)symmetric matrix from its stored lower triangle (no conjugation, diagonal as stored)."""
+    L = np.tril(A_lower)
+    return L + np.tril(L, -1).T
+
+
+def symm(alpha, A_lower, B, beta, C, nb: int):
+    """C = alpha A B + beta C, A symmetric given by its lower triangle; one block column of A per step (src/symm.cc:
+    Left, Lower)."""
+    A = sy_full(A_lower)
+    C = beta * np.array(C, order="F", copy=True)
+    for (k0, k1) in _tiles(A.shape[0], nb):
+        C += alpha * (A[:, k0:k1] @ B[k0:k1])
+    return C
+
+
 def norm_inf(A, hermitian_lower: bool = False):
     F = he_full(A) if hermitian_lower else np.asarray(A)
     return float(np.abs(F).sum(axis=1).max())

@@ -73,6 +73,21 @@ __global__ void __launch_bounds__(256) he_fill_kernel(const T* const* __restrict
     }
 }
 
+// full SYMMETRIC copy of the diagonal tiles (complex-symmetric symm): out_k(r, c) = r >= c ? a_k(r, c) : a_k(c, r)
+template <typename T>
+__global__ void __launch_bounds__(256) sy_fill_kernel(const T* const* __restrict__ diag, T* __restrict__ out,
+                                                      int ld, int64_t te, int nfull, int nlast_rows, int ntiles)
+{
+    const int k = blockIdx.y;
+    const int n = (k == ntiles - 1) ? nlast_rows : nfull;
+    const T* __restrict__ a = diag[k];
+    T* __restrict__ o = out + int64_t(k) * te;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int r = e % n, c = e / n;
+        o[r + int64_t(c) * ld] = (r >= c) ? a[r + int64_t(c) * ld] : a[c + int64_t(r) * ld];
+    }
+}
+
 // out(x, c) = in(perm[x], c) over an m x n tile matrix on a 1 x 1 grid (tile (i, j) at pool + (j*mt + i)*te)
 template <typename T>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ in, T* __restrict__ out,
@@ -376,6 +391,66 @@ int hemm_left_lower(T alpha, Matrix& A, Matrix& X, T beta, Matrix& Rm, cudaStrea
     return SB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// symm, Side::Left, lower storage: R = alpha A X + beta R with A (complex-)SYMMETRIC (src/symm.cc, Left/Lower case):
+// hemm_left_lower without the conjugation (tiles above the diagonal are plain transposes, the diagonal stays complex).
+// SURVEY section 8(f) item 3.  STATUS: written after round 1's GPU budget was spent; oracle pinned to the reference's
+// golden output on the CPU side, NOT yet run on a GPU (guarded test).  1 x 1 grid as hemm.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int symm_left_lower(T alpha, Matrix& A, Matrix& X, T beta, Matrix& Rm, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.kind != 'H' || X.kind != 'G' || Rm.kind != 'G' || X.m != A.n || Rm.m != A.n || X.n != Rm.n
+        || X.nb != A.nb || Rm.nb != A.nb) return SB200_EINVAL;
+    const int64_t nt = A.nt, nb = A.nb, ntB = X.nt, te = A.tile_elems();
+    if (nt == 0 || ntB == 0) return SB200_OK;
+    const int ld = int(nb);
+    const T one = from_real<T>(R(1));
+
+    const int64_t count = Rm.ntiles_loc * te;
+    const bool beta_zero = is_zero(beta);
+    if (beta_zero || ! is_zero(sub(beta, one))) {
+        scale_kernel<T><<<ew_grid(count), 256, 0, s>>>(reinterpret_cast<T*>(Rm.pool), beta, beta_zero ? 1 : 0, count);
+        SB_TRY(launch_status());
+    }
+    DevBuf dfull;
+    SB_TRY(dfull.alloc(size_t(nt) * te * sizeof(T)));
+    struct Step { std::vector<Batch> below, above, diag; };
+    std::vector<Step> steps(static_cast<size_t>(nt));
+    std::vector<const T*> diag_ptrs;
+    PlanBuffer pb;
+    for (int64_t k = 0; k < nt; ++k) {
+        Step& st = steps[size_t(k)];
+        diag_ptrs.push_back(A.tile_as<T>(k, k));
+        for (int64_t j = 0; j < ntB; ++j) {
+            for (int64_t i = k + 1; i < nt; ++i)
+                batch_add(st.below, int(Rm.tile_mb(i)), int(Rm.tile_nb(j)), int(X.tile_mb(k)), 0,
+                          A.tile_as<T>(i, k), X.tile_as<T>(k, j), Rm.tile_as<T>(i, j));
+            for (int64_t i = 0; i < k; ++i)
+                batch_add(st.above, int(Rm.tile_mb(i)), int(Rm.tile_nb(j)), int(X.tile_mb(k)), 0,
+                          A.tile_as<T>(k, i), X.tile_as<T>(k, j), Rm.tile_as<T>(i, j));
+            batch_add(st.diag, int(Rm.tile_mb(k)), int(Rm.tile_nb(j)), int(X.tile_mb(k)), 0,
+                      dfull.as<T>() + k * te, X.tile_as<T>(k, j), Rm.tile_as<T>(k, j));
+        }
+        pb.reserve(st.below); pb.reserve(st.above); pb.reserve(st.diag);
+    }
+    const size_t diag_off = pb.push(diag_ptrs);
+    SB_TRY(pb.upload(s));
+    sy_fill_kernel<T><<<dim3(64, unsigned(nt)), 256, 0, s>>>(pb.at<const T>(diag_off), dfull.as<T>(), ld, te,
+                                                            int(nb), int(A.tile_mb(nt - 1)), int(nt));
+    SB_TRY(launch_status());
+    for (int64_t k = 0; k < nt; ++k) {
+        const Step& st = steps[size_t(k)];
+        SB_TRY(launch_batches<T>(st.below, pb, 'N', 'N', alpha, one, ld, 0, s));
+        SB_TRY(launch_batches<T>(st.above, pb, 'T', 'N', alpha, one, ld, 0, s));
+        SB_TRY(launch_batches<T>(st.diag, pb, 'N', 'N', alpha, one, ld, 0, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SB200_OK;
+}
+
 // norm(Norm::Inf, A): max absolute row sum; A general or Hermitian (lower tiles)
 template <typename T>
 int norm_inf(Matrix& A, double* out, cudaStream_t s)
@@ -602,6 +677,14 @@ int sb200_hemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_m
     if (A->A.dtype != TypeChar<CuS<T>::type>::value || Xm->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
     CUDA_TRY(cudaDeviceSynchronize()); \
     return hemm_left_lower<CuS<T>::type>(cvv(alpha), A->A, Xm->A, cvv(beta), C->A, nullptr); \
+} \
+int sb200_symm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    (void) opts; \
+    if (! A || ! Xm || ! C) return SB200_EINVAL; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || Xm->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return symm_left_lower<CuS<T>::type>(cvv(alpha), A->A, Xm->A, cvv(beta), C->A, nullptr); \
 } \
 int sb200_norm_inf_##X(sb200_matrix_t A, double* value) \
 { \

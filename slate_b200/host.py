@@ -386,6 +386,16 @@ def hemm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | N
     check(_hemm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "hemm")
 
 
+_symm = {t: _sig(f"sb200_symm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+
+
+def symm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | None = None):
+    """C = alpha A B + beta C with A (complex-)symmetric (lower tiles), Side::Left, no conjugation (slate::symm, src/symm.cc)."""
+    t = _same_type(A, B, C)
+    o = _opts(opts)
+    check(_symm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "symm")
+
+
 def norm_inf(A: Matrix) -> float:
     """slate::norm(Norm::Inf, A) for a general or Hermitian matrix."""
     v = c_dbl(0.0)

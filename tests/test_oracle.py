@@ -118,6 +118,16 @@ def test_complex_symmetric_rank_updates_match_reference(golden_dir, routine):
     assert np.abs(np.tril(out) - ref).max() <= 64 * EPS * np.abs(ref).max()
 
 
+def test_symm_matches_reference(golden_dir):
+    g = load(golden_dir, "symm_z")
+    n, nb, nrhs = 192, 64, 70
+    A = np.tril(o.generate("rand", n, n, 42, np.complex128))
+    B = o.generate("rand", n, nrhs, 43, np.complex128)
+    C = o.generate("rand", n, nrhs, 44, np.complex128)
+    out = o.symm(ALPHA, A, B, BETA, C, nb)
+    assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+
+
 def test_getrf_nopiv_matches_reference(golden_dir):
     g = load(golden_dir, "getrf_nopiv_d")
     n, nb = 300, 128

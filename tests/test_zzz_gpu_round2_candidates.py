@@ -656,3 +656,25 @@ def test_symmetric_rank_updates_match_reference_golden_and_oracle(sl, golden_dir
     if t == "z":
         g = np.load(os.path.join(golden_dir, f"{routine}_z.npz"))
         assert np.abs(out - np.tril(g["out"])).max() <= 64 * EPS * np.abs(g["out"]).max()
+
+
+@pytest.mark.parametrize("t", ["z", "c", "d"])
+def test_symm_matches_reference_golden_and_oracle(sl, golden_dir, t):
+    from tests.gpu_util import NP
+    n, nb, nrhs = 192, 64, 70
+    al = (3.141592653589793 + 1.414213562373095j) if t in "cz" else 3.141592653589793
+    be = (2.718281828459045 + 1.732050807568877j) if t in "cz" else 2.718281828459045
+    A = sl.HermitianMatrix(n, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(n, nrhs, nb, dtype=t).generate("rand", 43)
+    C = sl.Matrix(n, nrhs, nb, dtype=t).generate("rand", 44)
+    sl.symm(al, A, B, be, C)
+    wide = np.complex128 if t in "cz" else np.float64
+    a = np.tril(o.generate("rand", n, n, 42, NP[t])).astype(wide)
+    b, c = (o.generate("rand", n, nrhs, seed, NP[t]).astype(wide) for seed in (43, 44))
+    ref = o.symm(al, a, b, be, c, nb)
+    eps = EPS if t in "dz" else float(np.finfo(np.float32).eps)
+    out = C.to_host()
+    assert np.abs(out - ref).max() <= 64 * eps * np.abs(ref).max()
+    if t == "z":
+        g = np.load(os.path.join(golden_dir, "symm_z.npz"))
+        assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
