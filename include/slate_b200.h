@@ -406,6 +406,9 @@ int sb200_potrs_##X(sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* o
 int sb200_hemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* C = alpha A X + beta C, A (complex-)symmetric lower, Side::Left, no conjugation   slate::symm (src/symm.cc); 1 x 1 grid */ \
 int sb200_symm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t X, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
+/* B = alpha A B, A lower triangular (lower tiles of a kind 'H' matrix), side 'L', uplo 'L', op 'N', diag 'N' | 'U' \
+ * slate::trmm (src/trmm.cc); other side / uplo / op: SB200_ENOTSUP; 1 x 1 grid */ \
+int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
 /* norm(Norm::Inf, A), A general or Hermitian   slate::norm (src/norm.cc); 1 x 1 grid */ \
 int sb200_norm_inf_##X(sb200_matrix_t A, double* value);
 SB200_FOR_TYPES(SB200_DECL_RUNTIME)

@@ -382,6 +382,23 @@ int run(const Args& a)
             write_raw(a.prefix + ".out.bin", d.data(), d.size());
         }
     }
+    else if (a.routine == "trmm") {
+        // B = alpha A B, A lower triangular (rand), Side::Left, NoTrans (test/test_trmm.cc; slate::trmm, src/trmm.cc)
+        int64_t m = a.geti("m", n);   // A is m x m, B is m x n
+        bool unit = a.get("diag", "n") == "u";
+        slate::TriangularMatrix<T> A(slate::Uplo::Lower, unit ? slate::Diag::Unit : slate::Diag::NonUnit, m, nb,
+                                     slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        A.insertLocalTiles();
+        slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedA;
+        p.cond_request = p.cond_actual = p.condD = NAN;
+        slate::generate_matrix(p, A);
+        auto B = make_matrix<T>(m, n, nb, a.seedB, "rand");
+        auto t0 = tic();
+        slate::trmm(slate::Side::Left, alpha, A, B, opts);
+        seconds = toc(t0);
+        gflop = blas::Gflop<T>::trmm(slate::Side::Left, m, n);
+        if (dump) { auto d = to_dense(B); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
+    }
     else if (a.routine == "symm") {
         // C = alpha A B + beta C, A complex-symmetric (lower), Side::Left (test/test_symm.cc; slate::symm, src/symm.cc)
         slate::SymmetricMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);

@@ -457,6 +457,24 @@ def symm(alpha, A_lower, B, beta, C, nb: int):
     return C
 
 
+def trmm(alpha, A_lower, B, nb: int, unit: bool = False):
+    """B <- alpha A B, A lower triangular, Side::Left, NoTrans (src/trmm.cc -> work::trmm, src/work/work_trmm.cc): block
+    row i of the result = alpha (A_ii B_i + sum_{k<i} A_ik B_k) from the ORIGINAL B, computed bottom-up in place."""
+    A = np.tril(A_lower).astype(np.result_type(A_lower, B), copy=True)
+    if unit:
+        np.fill_diagonal(A, 1.0)
+    B = np.array(B, order="F", copy=True)
+    tiles = _tiles(A.shape[0], nb)
+    for (i0, i1) in reversed(tiles):
+        acc = A[i0:i1, i0:i1] @ B[i0:i1]
+        for (k0, k1) in tiles:
+            if k0 >= i0:
+                break
+            acc += A[i0:i1, k0:k1] @ B[k0:k1]
+        B[i0:i1] = alpha * acc
+    return B
+
+
 def norm_inf(A, hermitian_lower: bool = False):
     F = he_full(A) if hermitian_lower else np.asarray(A)
     return float(np.abs(F).sum(axis=1).max())

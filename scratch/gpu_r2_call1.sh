@@ -24,7 +24,7 @@ sec_tests() {
   }
   run_group dist_solve tests/test_zzz_gpu_dist_solve.py
   run_group diag_mw    $C -k "diag_mw"
-  run_group streaming  $C -k "streaming or permute_rows or transposed or skinny_panel or her2k or scalapack or nopiv or symmetric_rank or symm_matches"
+  run_group streaming  $C -k "streaming or permute_rows or transposed or skinny_panel or her2k or scalapack or nopiv or symmetric_rank or symm_matches or trmm"
   run_group trsm_fused $C -k "fused_panel_trsm or fused_row_trsm or fused_row_solve or row_solve_candidates"
   run_group tile_fused $C -k "fused_tile"
   run_group panel_ll   $C -k "ll_panel"

@@ -88,6 +88,26 @@ __global__ void __launch_bounds__(256) sy_fill_kernel(const T* const* __restrict
     }
 }
 
+// lower-triangular copy of the diagonal tiles (trmm): out_k(r, c) = a_k(r, c) below the diagonal, the diagonal itself
+// (1 if unit), exact zeros above
+template <typename T>
+__global__ void __launch_bounds__(256) tr_fill_kernel(const T* const* __restrict__ diag, T* __restrict__ out,
+                                                      int ld, int64_t te, int nfull, int nlast_rows, int ntiles, int unit)
+{
+    using R = typename RealOf<T>::type;
+    const int k = blockIdx.y;
+    const int n = (k == ntiles - 1) ? nlast_rows : nfull;
+    const T* __restrict__ a = diag[k];
+    T* __restrict__ o = out + int64_t(k) * te;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int r = e % n, c = e / n;
+        T v = zero_of<T>();
+        if (r > c)       v = a[r + int64_t(c) * ld];
+        else if (r == c) v = unit ? from_real<T>(R(1)) : a[r + int64_t(c) * ld];
+        o[r + int64_t(c) * ld] = v;
+    }
+}
+
 // out(x, c) = in(perm[x], c) over an m x n tile matrix on a 1 x 1 grid (tile (i, j) at pool + (j*mt + i)*te)
 template <typename T>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ in, T* __restrict__ out,
@@ -451,6 +471,59 @@ int symm_left_lower(T alpha, Matrix& A, Matrix& X, T beta, Matrix& Rm, cudaStrea
     return SB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// trmm, Side::Left, Lower, NoTrans: B <- alpha A B with A lower triangular (src/trmm.cc -> work::trmm,
+// src/work/work_trmm.cc).  In place, right-looking from the bottom: for k = nt-1 .. 0
+//     B(i, :) += alpha A(i, k) B(k, :)   for i > k        (one batched launch; B(k, :) is still the original block row)
+//     B(k, :)  = alpha tril(A(k, k)) B(k, :)              (through a one-block-row workspace: the tile product cannot alias)
+// SURVEY section 8(f) item 3.  STATUS: written after round 1's GPU budget was spent; oracle pinned to the reference's
+// golden output on the CPU side, NOT yet run on a GPU (guarded test).  1 x 1 grid; other side / uplo / op: ENOTSUP.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int trmm_left_lower(T alpha, Matrix& A, Matrix& B, bool unit, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.kind != 'H' || B.kind != 'G' || B.m != A.n || B.nb != A.nb) return SB200_EINVAL;
+    const int64_t nt = A.nt, nb = A.nb, ntB = B.nt, te = A.tile_elems();
+    if (nt == 0 || ntB == 0) return SB200_OK;
+    const int ld = int(nb);
+    const T one = from_real<T>(R(1)), zero = zero_of<T>();
+    DevBuf dtri, wrow;
+    SB_TRY(dtri.alloc(size_t(nt) * te * sizeof(T)));
+    SB_TRY(wrow.alloc(size_t(ntB) * te * sizeof(T)));
+    struct Step { std::vector<Batch> below, diag; };
+    std::vector<Step> steps(static_cast<size_t>(nt));
+    std::vector<const T*> diag_ptrs;
+    PlanBuffer pb;
+    for (int64_t k = 0; k < nt; ++k) {
+        Step& st = steps[size_t(k)];
+        diag_ptrs.push_back(A.tile_as<T>(k, k));
+        for (int64_t j = 0; j < ntB; ++j) {
+            for (int64_t i = k + 1; i < nt; ++i)
+                batch_add(st.below, int(B.tile_mb(i)), int(B.tile_nb(j)), int(B.tile_mb(k)), 0,
+                          A.tile_as<T>(i, k), B.tile_as<T>(k, j), B.tile_as<T>(i, j));
+            batch_add(st.diag, int(B.tile_mb(k)), int(B.tile_nb(j)), int(B.tile_mb(k)), 0,
+                      dtri.as<T>() + k * te, B.tile_as<T>(k, j), wrow.as<T>() + j * te);
+        }
+        pb.reserve(st.below); pb.reserve(st.diag);
+    }
+    const size_t diag_off = pb.push(diag_ptrs);
+    SB_TRY(pb.upload(s));
+    tr_fill_kernel<T><<<dim3(64, unsigned(nt)), 256, 0, s>>>(pb.at<const T>(diag_off), dtri.as<T>(), ld, te,
+                                                            int(nb), int(A.tile_mb(nt - 1)), int(nt), unit ? 1 : 0);
+    SB_TRY(launch_status());
+    for (int64_t k = nt - 1; k >= 0; --k) {
+        const Step& st = steps[size_t(k)];
+        SB_TRY(launch_batches<T>(st.below, pb, 'N', 'N', alpha, one, ld, 0, s));
+        SB_TRY(launch_batches<T>(st.diag, pb, 'N', 'N', alpha, zero, ld, 0, s));
+        for (int64_t j = 0; j < ntB; ++j)
+            CUDA_TRY(cudaMemcpyAsync(B.tile_as<T>(k, j), wrow.as<T>() + j * te, size_t(te) * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SB200_OK;
+}
+
 // norm(Norm::Inf, A): max absolute row sum; A general or Hermitian (lower tiles)
 template <typename T>
 int norm_inf(Matrix& A, double* out, cudaStream_t s)
@@ -685,6 +758,16 @@ int sb200_symm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_m
     if (A->A.dtype != TypeChar<CuS<T>::type>::value || Xm->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
     CUDA_TRY(cudaDeviceSynchronize()); \
     return symm_left_lower<CuS<T>::type>(cvv(alpha), A->A, Xm->A, cvv(beta), C->A, nullptr); \
+} \
+int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts) \
+{ \
+    (void) opts; \
+    if (! A || ! B) return SB200_EINVAL; \
+    if (! valid_side(side) || ! valid_uplo(uplo) || ! valid_op(op) || ! valid_diag(diag)) return SB200_EINVAL; \
+    if (side != 'L' || uplo != 'L' || op != 'N') return SB200_ENOTSUP; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || B->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return trmm_left_lower<CuS<T>::type>(cvv(alpha), A->A, B->A, diag == 'U', nullptr); \
 } \
 int sb200_norm_inf_##X(sb200_matrix_t A, double* value) \
 { \

@@ -396,6 +396,17 @@ def symm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | N
     check(_symm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "symm")
 
 
+_trmm = {t: _sig(f"sb200_trmm_{t}", [c_int, c_int, c_int, c_int, SCALAR_T[t], c_ptr, c_ptr, _OP]) for t in "sdcz"}
+
+
+def trmm(alpha, A: "HermitianMatrix", B: Matrix, side: str = "L", uplo: str = "L", op: str = "N", diag: str = "N",
+         opts: dict | None = None):
+    """B = alpha A B with A lower triangular (the lower tiles of A), Side::Left, NoTrans (slate::trmm, src/trmm.cc)."""
+    t = _same_type(A, B)
+    o = _opts(opts)
+    check(_trmm[t](ord(side), ord(uplo), ord(op), ord(diag), scalar(t, alpha), A._h, B._h, ctypes.byref(o)), "trmm")
+
+
 def norm_inf(A: Matrix) -> float:
     """slate::norm(Norm::Inf, A) for a general or Hermitian matrix."""
     v = c_dbl(0.0)

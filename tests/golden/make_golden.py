@@ -20,6 +20,7 @@ generator fixture pins that), only outputs:
   gesv_d.npz             lu_factor + lu_solve_using_factor solution, n=300 nb=128
   hemm_z.npz             C = alpha A B + beta C, A Hermitian lower, n=192 nb=64 nrhs=70
   potrf_z.npz            complex Cholesky factor, n=192 nb=64
+  trmm_d.npz             B = alpha A B, A lower triangular (rand), Left/NoTrans/NonUnit, m=200 n=70 nb=64
   symm_z.npz             C = alpha A B + beta C, A complex-symmetric lower, n=192 nb=64 nrhs=70
   syrk_z.npz, syr2k_z.npz   complex-symmetric rank-k / rank-2k updates (no conjugation), n=200 k=100 nb=64
   getrf_nopiv_d.npz      LU without pivoting, rand_dominant, n=300 nb=128 (ragged)
@@ -100,6 +101,8 @@ def main():
     for t in "dz":
         f, _ = run("her2k", t, 200, 64, k=100)
         np.savez_compressed(os.path.join(OUT, f"her2k_{t}.npz"), out=f["out"].reshape(200, 200, order="F"))
+    f, _ = run("trmm", "d", 70, 64, m=200)
+    np.savez_compressed(os.path.join(OUT, "trmm_d.npz"), out=f["out"].reshape(200, 70, order="F"))
     f, _ = run("symm", "z", 192, 64, nrhs=70)
     np.savez_compressed(os.path.join(OUT, "symm_z.npz"), out=f["out"].reshape(192, 70, order="F"))
     f, _ = run("syrk", "z", 200, 64, k=100)

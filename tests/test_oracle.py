@@ -118,6 +118,15 @@ def test_complex_symmetric_rank_updates_match_reference(golden_dir, routine):
     assert np.abs(np.tril(out) - ref).max() <= 64 * EPS * np.abs(ref).max()
 
 
+def test_trmm_matches_reference(golden_dir):
+    g = load(golden_dir, "trmm_d")
+    m, n, nb = 200, 70, 64
+    A = np.tril(o.generate("rand", m, m, 42))
+    B = o.generate("rand", m, n, 43)
+    out = o.trmm(ALPHA.real, A, B, nb)
+    assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+
+
 def test_symm_matches_reference(golden_dir):
     g = load(golden_dir, "symm_z")
     n, nb, nrhs = 192, 64, 70

@@ -678,3 +678,32 @@ def test_symm_matches_reference_golden_and_oracle(sl, golden_dir, t):
     if t == "z":
         g = np.load(os.path.join(golden_dir, "symm_z.npz"))
         assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+
+
+@pytest.mark.parametrize("t", ["d", "z", "s"])
+@pytest.mark.parametrize("diag", ["N", "U"])
+@pytest.mark.parametrize("m,n,nb", [(200, 70, 64), (512, 512, 128), (300, 1000, 256)])
+def test_trmm_left_lower_matches_oracle_and_reference_golden(sl, golden_dir, t, diag, m, n, nb):
+    from tests.gpu_util import NP
+    al = (3.141592653589793 + 1.414213562373095j) if t == "z" else 3.141592653589793
+    A = sl.HermitianMatrix(m, nb, dtype=t).generate("rand", 42)             # its lower tiles are the triangle
+    B = sl.Matrix(m, n, nb, dtype=t).generate("rand", 43)
+    sl.trmm(al, A, B, diag=diag)
+    wide = np.complex128 if t == "z" else np.float64
+    a = np.tril(o.generate("rand", m, m, 42, NP[t])).astype(wide)
+    b = o.generate("rand", m, n, 43, NP[t]).astype(wide)
+    ref = o.trmm(al, a, b, nb, unit=(diag == "U"))
+    eps = EPS if t in "dz" else float(np.finfo(np.float32).eps)
+    out = B.to_host()
+    assert np.abs(out - ref).max() <= 3 * np.sqrt(m) * eps * 4 * np.abs(ref).max()
+    if (t, diag, m, n, nb) == ("d", "N", 200, 70, 64):
+        g = np.load(os.path.join(golden_dir, "trmm_d.npz"))                  # written by the unmodified reference
+        assert np.abs(out - g["out"]).max() <= 3 * np.sqrt(m) * EPS * 4 * np.abs(g["out"]).max()
+
+
+def test_trmm_unsupported_variants_say_so(sl):
+    A = sl.HermitianMatrix(64, 32); B = sl.Matrix(64, 8, 32)
+    with pytest.raises(sl.SB200Error):
+        sl.trmm(1.0, A, B, side="R")
+    with pytest.raises(sl.SB200Error):
+        sl.trmm(1.0, A, B, op="T")
