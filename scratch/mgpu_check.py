@@ -119,6 +119,38 @@ def main():
                     print(f"grid {p}x{q} n={n} nb={nb}: zherk err={e1:.2e} zpotrf err={e2:.2e} zgemm err={e3:.2e} "
                           f"spotrf(tcgen05) err={e4:.2e} {'ok' if good else 'FAILED'}", flush=True)
                     ok &= good
+            # ---- SURVEY 8(f) items 2-3 on the grid (written after round 1's GPU budget was spent): her2k, complex-symmetric
+            #      syrk / syr2k, getrf_nopiv.  MGPU_WIDEN=0 skips them.
+            if os.environ.get("MGPU_WIDEN", "1") != "0" and n != 2048:
+                k = n // 2
+                al, be = 3.1 + 1.4j, 2.7 + 1.7j
+                Az = sl.Matrix(n, k, nb, grid, "z").generate("rand", 5)
+                Bz = sl.Matrix(n, k, nb, grid, "z").generate("rand", 9)
+                outs = []
+                for name in ("her2k", "syrk", "syr2k"):
+                    Cz = sl.HermitianMatrix(n, nb, grid, dtype="z").generate("rand", 6)
+                    if name == "her2k":
+                        sl.her2k(al, Az, Bz, 2.0, Cz)
+                    elif name == "syrk":
+                        sl.syrk(al, Az, be, Cz)
+                    else:
+                        sl.syr2k(al, Az, Bz, be, Cz)
+                    outs.append(np.tril(gather(Cz, n, n)))
+                Gn = sl.Matrix(n, n, nb, grid).generate("rand_dominant", 42)
+                inp = sl.getrf_nopiv(Gn)
+                lun = gather(Gn, n, n)
+                if rank == 0:
+                    a, b = o.generate("rand", n, k, 5, np.complex128), o.generate("rand", n, k, 9, np.complex128)
+                    c = np.tril(o.generate("rand", n, n, 6, np.complex128))
+                    refs = [np.tril(o.her2k(al, a, b, 2.0, c, nb)), np.tril(o.syrk(al, a, be, c, nb)),
+                            np.tril(o.syr2k(al, a, b, be, c, nb))]
+                    errs = [np.abs(x - r).max() / np.abs(r).max() for x, r in zip(outs, refs)]
+                    LUo, info_o = o.getrf_nopiv(o.generate("rand_dominant", n, n, 42), nb)
+                    en = np.abs(lun - LUo).max() / np.abs(LUo).max()
+                    good = all(e <= 256 * EPS for e in errs) and en <= 64 * EPS and inp == info_o == 0
+                    print(f"grid {p}x{q} n={n} nb={nb}: zher2k err={errs[0]:.2e} zsyrk err={errs[1]:.2e} zsyr2k err={errs[2]:.2e} "
+                          f"getrf_nopiv err={en:.2e} {'ok' if good else 'FAILED'}", flush=True)
+                    ok &= good
             # ---- solve path on the grid (replicated right-hand sides, solve_dist.cu): potrs and posv_mixed
             if os.environ.get("MGPU_SOLVE", "1") != "0":
                 Hd = sl.HermitianMatrix(n, nb, grid).generate("rand_dominant", 42)
