@@ -13,7 +13,7 @@ port=29530
 check() {  # tag [env...]
   local tag=$1; shift
   port=$((port + 1))
-  env "$@" MGPU_SIZES="2048x256" timeout 300 $TR --master-port $port scratch/mgpu_check.py 2x4 > $OUT/r2g8_check_$tag.log 2>&1
+  env "$@" MGPU_WIDEN=0 MGPU_SIZES="2048x256" timeout 300 $TR --master-port $port scratch/mgpu_check.py 2x4 > $OUT/r2g8_check_$tag.log 2>&1
   echo "mgpu_check $tag exit $?" | tee -a $OUT/r2g8_check_$tag.log; grep -E "grid|MGPU|Error|error|FAIL" $OUT/r2g8_check_$tag.log | tail -20
   echo "[$((SECONDS-T0)) s] check $tag"
 }
