@@ -320,9 +320,13 @@ int sb200_matrix_to_host_local_d(sb200_matrix_t A, double* htiles, sb200_stream_
 int sb200_matrix_copy_d(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream);
 int64_t sb200_matrix_local_tiles(sb200_matrix_t A);
 
-/* options common to the drivers */
+/* options common to the drivers (NULL = the defaults).  Honour-or-reject: the runtime's pipelines have a fixed
+ * lookahead depth of 1 and its LU panel always takes the largest candidate, so lookahead != 1 or
+ * pivot_threshold != 1.0 returns SB200_ENOTSUP (out-of-range values SB200_EINVAL) -- never a silent ignore.
+ * inner_blocking only re-associates the reference panel's rank-ib updates (it does not enter the pivot rule,
+ * src/internal/Tile_getrf.hh:160-447); the GPU panel has its own blocking and accepts any value >= 1. */
 typedef struct {
-    int64_t lookahead;        /* slate::Option::Lookahead, default 1                     */
+    int64_t lookahead;        /* slate::Option::Lookahead, default 1 (src/potrf.cc:41-42, src/getrf.cc:38-43) */
     int64_t inner_blocking;   /* slate::Option::InnerBlocking (getrf panel), default 16  */
     double  pivot_threshold;  /* slate::Option::PivotThreshold, default 1.0              */
     int     reserved[8];
@@ -368,9 +372,18 @@ int sb200_matrix_copy(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t str
  * column-major local array (leading dimension lld >= local rows) of the 2-D block-cyclic distribution with square
  * nb x nb blocks on the matrix's p x q grid (column-major rank order): tile (i, j) sits at local offset
  * ((i / p) * nb, (j / q) * nb).  Gathers the locally owned (stored) tiles into the HBM tile pool / scatters them
- * back; on_device != 0: `local` is device memory. */
-int sb200_matrix_from_scalapack(sb200_matrix_t A, const void* local, int64_t lld, int on_device, sb200_stream_t stream);
-int sb200_matrix_to_scalapack(sb200_matrix_t A, void* local, int64_t lld, int on_device, sb200_stream_t stream);
+ * back; on_device != 0: `local` is device memory.  ncols_local = columns the caller's array holds; SB200_EINVAL when
+ * lld or ncols_local is smaller than this rank's numroc rows / columns (nothing is copied). */
+int sb200_matrix_from_scalapack(sb200_matrix_t A, const void* local, int64_t lld, int64_t ncols_local, int on_device, sb200_stream_t stream);
+int sb200_matrix_to_scalapack(sb200_matrix_t A, void* local, int64_t lld, int64_t ncols_local, int on_device, sb200_stream_t stream);
+
+/* Probe-vector product with the tiles this rank stores (residual checks at bench size without a second n x n
+ * matrix; the reference tester forms ||B - A X|| with gemm / hemm, test/test_posv.cc:336-342, test/test_gesv.cc:371-377):
+ *   y += op(part(A)) x     op 'N' | 'C';   part 'G' whole matrix, 'L' lower triangle (diag 'U': unit), 'U' upper triangle,
+ *                          'H' Hermitian matrix from its stored lower tiles;   use_abs != 0: |a_ij| instead of a_ij.
+ * x, y: device vectors of the matrix's element type holding the WHOLE vector (length n resp. m, swapped for 'C');
+ * contributions are added atomically, so the caller zeroes y and sums it over the ranks of the grid. */
+int sb200_matrix_probe_mv(sb200_matrix_t A, int part, int op, int diag, int use_abs, const void* x, void* y, sb200_stream_t stream);
 
 /* host-only description of the 2-D block-cyclic tile map (no GPU needed):
  * tileRank (include/slate/func.hh:96-104, GridOrder::Col), the number of tiles a rank stores, and the

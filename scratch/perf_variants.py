@@ -95,7 +95,10 @@ if __name__ == "__main__":
     routine = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
     nb = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+    only = [t for t in os.environ.get("SB200_VARIANTS", "").split(",") if t]
     for tag, env in {"potrf": POTRF, "getrf": GETRF, "gemm": GEMM, "posv_mixed": MIXED, "gesv_mixed": GMIXED}[routine]:
+        if only and tag not in only:
+            continue
         e = dict(os.environ); e.update(env)
         print(f"## {routine} {tag}", flush=True)
         sys.stderr.write(f"## {routine} {tag}\n"); sys.stderr.flush()

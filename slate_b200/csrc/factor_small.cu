@@ -613,7 +613,7 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
     if constexpr (IsRealType<T>::value) {
         // opt-in (round-2 candidate, not yet run): bit 2 = a small triangle (na <= 64: the U12 solves inside the LU panel)
         // by direct substitution in one launch, no inversion kernel
-        if ((switch_value(SW_TRSM_FUSED) & 4) && left && lower && op == 'N' && na <= IB) {
+        if ((switch_value(SW_TRSM_FUSED) & 4) && left && lower && op == 'N' && na <= 32) {      // 13 us vs 24 us (na = 32); slower than the inverse path at 64
             if constexpr (std::is_same<T, double>::value) return trsm_lln_small_d(na, n, alpha, unit, Tm, ldt, dB, offB, ldb, batch, stream);
             else                                          return trsm_lln_small_s(na, n, alpha, unit, Tm, ldt, dB, offB, ldb, batch, stream);
         }

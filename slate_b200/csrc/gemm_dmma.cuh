@@ -42,6 +42,7 @@ struct GemmParamsT {
     int herk;                    // complex herk: force the diagonal of C real (generic kernel only)
 };
 using GemmParamsD = GemmParamsT<double>;
+constexpr int SKINNY_MAX_N = 16;       // widest right operand served by the HBM-bound streaming kernel (gemm_skinny.cu)
 
 // Type-generic launcher: double -> DMMA kernel below; float / complex -> gemm_generic.cu.
 // opA / opB in 'N','T','C' refer to the column-major problem C = alpha op(A) op(B) + beta C.

@@ -16,7 +16,7 @@
 
 namespace sb200 {
 
-constexpr int SK_NC = 16;          // max columns of B / C
+constexpr int SK_NC = SKINNY_MAX_N; // max columns of B / C (16)
 constexpr int SK_KCH = 128;        // k chunk of B staged in shared memory
 constexpr int SK_ROWS = 64;        // rows of C per CTA, op(A) = A
 constexpr int SK_ROWS_T = 16;      // rows of C per CTA, op(A) = A^T / A^H (2 rows per warp: 32 accumulators per lane)

@@ -1127,12 +1127,12 @@ static int getrf_nopiv_any(sb200_matrix_t h, int64_t* info, bool is_float)
     std::vector<int64_t> piv(size_t(2 * std::max<int64_t>(std::min(h->A.m, h->A.n), 1)));
     return is_float ? getrf_driver_s(h->A, piv.data(), info, false) : getrf_driver(h->A, piv.data(), info);
 }
-int sb200_getrf_nopiv_d(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { (void) opts; return getrf_nopiv_any(h, info, false); }
-int sb200_getrf_nopiv_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { (void) opts; return getrf_nopiv_any(h, info, true); }
+int sb200_getrf_nopiv_d(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, false); }
+int sb200_getrf_nopiv_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, true); }
 
 int sb200_getrf_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
 {
-    (void) opts;     // inner blocking is fixed at 32, lookahead at 1, pivot threshold at 1.0
+    SB_TRY(options_status(opts));
     if (! h) return SB200_EINVAL;
     return getrf_driver(h->A, pivots, info);
 }
@@ -1141,14 +1141,14 @@ int sb200_getrf_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts
  * trailing update on the tcgen05 FP32-emulated (3 x TF32) kernel. */
 int sb200_getrf_s(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
 {
-    (void) opts;
+    SB_TRY(options_status(opts));
     if (! h) return SB200_EINVAL;
     return getrf_driver_s(h->A, pivots, info, false);
 }
 
 int sb200_getrf_tc05_s(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
 {
-    (void) opts;
+    SB_TRY(options_status(opts));
     if (! h) return SB200_EINVAL;
     return getrf_driver_s(h->A, pivots, info, true);
 }

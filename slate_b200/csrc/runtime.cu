@@ -477,13 +477,13 @@ int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C)
         for (int64_t j = g.pcol; j < C.nt; j += g.q)
             for (int64_t i = g.prow; i < C.mt; i += g.p)
                 batch_add(plan[k], int(C.tile_mb(i)), int(C.tile_nb(j)), int(A.tile_nb(k)), 0,
-                          a_src(i, k), use_bt ? bt_src(k, j) : b_src(k, j), C.tile_as<T>(i, j));
+                          a_src(i, k), (use_bt && C.tile_nb(j) > SKINNY_MAX_N) ? bt_src(k, j) : b_src(k, j), C.tile_as<T>(i, j));
         pb.reserve(plan[k]);
         if (use_bt) {
             BtStep& b = bts[size_t(k)];
             for (int64_t j = g.pcol; j < C.nt; j += g.q) {
                 if (C.tile_nb(j) == nb) { b.src_full.push_back(b_src(k, j)); b.dst_full.push_back(bt_src(k, j)); }
-                else                    { b.src_last.push_back(b_src(k, j)); b.dst_last.push_back(bt_src(k, j)); }
+                else if (C.tile_nb(j) > SKINNY_MAX_N) { b.src_last.push_back(b_src(k, j)); b.dst_last.push_back(bt_src(k, j)); }
             }
             b.src_full_off = pb.push(b.src_full); b.dst_full_off = pb.push(b.dst_full);
             b.src_last_off = pb.push(b.src_last); b.dst_last_off = pb.push(b.dst_last);
@@ -548,7 +548,7 @@ int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C)
             }
         }
         SB_TRY(st.time_begin(T_));
-        SB_TRY(launch_batches<T>(plan[k], pb, 'N', use_bt ? 'T' : 'N', alpha, k == 0 ? beta : from_real<T>(R(1)), ld, 0, T_));
+        SB_TRY(launch_batches<T>(plan[k], pb, 'N', use_bt ? 'T' : 'N', alpha, k == 0 ? beta : from_real<T>(R(1)), ld, 0, T_, 'N'));
         SB_TRY(st.time_end(T_));
         trail_flops += batches_flops(plan[k], IsComplex<T>::value);
         trail_launches += int64_t(plan[k].size());
@@ -881,11 +881,14 @@ static int matrix_host_copy(Matrix& A, void* hA, int64_t lda, bool to_host, cuda
 // in place (strided tiles, ld = lld) and converts per tile when a kernel needs contiguous storage; here the tiles
 // are gathered once into the contiguous HBM pool (one 2-D copy per tile on the caller's stream) and scattered back
 // by the inverse call.  `on_device`: the local array is device memory (device-to-device copies) or host memory.
-static int matrix_scalapack_copy(Matrix& A, void* local, int64_t lld, bool on_device, bool to_local, cudaStream_t s)
+static int matrix_scalapack_copy(Matrix& A, void* local, int64_t lld, int64_t ncols_local, bool on_device, bool to_local, cudaStream_t s)
 {
     int64_t rows_loc = 0;                                  // ScaLAPACK numroc: rows of the local array
     for (int64_t i = A.g->prow; i < A.mt; i += A.g->p) rows_loc += A.tile_mb(i);
     if (lld < std::max<int64_t>(rows_loc, 1)) return SB200_EINVAL;
+    int64_t cols_loc = 0;                                  // numroc: columns of the local array
+    for (int64_t j = A.g->pcol; j < A.nt; j += A.g->q) cols_loc += A.tile_nb(j);
+    if (ncols_local < cols_loc || (local == nullptr && rows_loc * cols_loc > 0)) return SB200_EINVAL;
     const size_t es = size_t(A.esize);
     const cudaMemcpyKind k_in = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const cudaMemcpyKind k_out = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -1053,16 +1056,16 @@ int sb200_matrix_to_host_local(sb200_matrix_t h, void* htiles, sb200_stream_t st
     return SB200_OK;
 }
 
-int sb200_matrix_from_scalapack(sb200_matrix_t h, const void* local, int64_t lld, int on_device, sb200_stream_t stream)
+int sb200_matrix_from_scalapack(sb200_matrix_t h, const void* local, int64_t lld, int64_t ncols_local, int on_device, sb200_stream_t stream)
 {
     if (! h || ! local) return SB200_EINVAL;
-    return matrix_scalapack_copy(h->A, const_cast<void*>(local), lld, on_device != 0, false, cudaStream_t(stream));
+    return matrix_scalapack_copy(h->A, const_cast<void*>(local), lld, ncols_local, on_device != 0, false, cudaStream_t(stream));
 }
 
-int sb200_matrix_to_scalapack(sb200_matrix_t h, void* local, int64_t lld, int on_device, sb200_stream_t stream)
+int sb200_matrix_to_scalapack(sb200_matrix_t h, void* local, int64_t lld, int64_t ncols_local, int on_device, sb200_stream_t stream)
 {
     if (! h || ! local) return SB200_EINVAL;
-    return matrix_scalapack_copy(h->A, local, lld, on_device != 0, true, cudaStream_t(stream));
+    return matrix_scalapack_copy(h->A, local, lld, ncols_local, on_device != 0, true, cudaStream_t(stream));
 }
 
 int sb200_matrix_copy(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream)
@@ -1116,52 +1119,52 @@ int sb200_matrix_create_##X(sb200_grid_t gh, int kind, int layout, int64_t m, in
 } \
 int sb200_potrf_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) \
 { \
-    (void) opts;                       /* lookahead is fixed at 1 (the reference default) */ \
+    SB_TRY(options_status(opts));\
     if (! h) return SB200_EINVAL; \
     return potrf_driver<CuT<T>::type>(h->A, info, false, nullptr, nullptr); \
 } \
 /* potrf whose result streams to the packed host buffer (sb200_matrix_to_host_local order) while it factors */ \
 int sb200_potrf_to_host_local_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info, void* htiles) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! h || ! htiles) return SB200_EINVAL; \
     return potrf_driver<CuT<T>::type>(h->A, info, false, htiles, nullptr); \
 } \
 /* potrf whose INPUT also streams from a packed host buffer (chunks of block columns) while it factors; one rank */ \
 int sb200_potrf_stream_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info, const void* htiles_in, void* htiles_out) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! h || ! htiles_in) return SB200_EINVAL; \
     return potrf_driver<CuT<T>::type>(h->A, info, false, htiles_out, htiles_in); \
 } \
 int sb200_gemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, \
                    const sb200_options_t* opts) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! A || ! B || ! C) return SB200_EINVAL; \
     return gemm_driver<CuT<T>::type>(cvs(alpha), A->A, B->A, cvs(beta), C->A); \
 } \
 int sb200_herk_mat_##X(R alpha, sb200_matrix_t A, R beta, sb200_matrix_t C, const sb200_options_t* opts) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! A || ! C) return SB200_EINVAL; \
     return herk_driver<CuT<T>::type>(alpha, A->A, beta, C->A); \
 } \
 int sb200_her2k_mat_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, R beta, sb200_matrix_t C, const sb200_options_t* opts) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! A || ! B || ! C) return SB200_EINVAL; \
     return her2k_driver<CuT<T>::type>(cvs(alpha), A->A, B->A, beta, C->A); \
 } \
 int sb200_syrk_mat_##X(T alpha, sb200_matrix_t A, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! A || ! C) return SB200_EINVAL; \
     return sym_rank_update_driver<CuT<T>::type>(cvs(alpha), A->A, nullptr, cvs(beta), C->A); \
 } \
 int sb200_syr2k_mat_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! A || ! B || ! C) return SB200_EINVAL; \
     return sym_rank_update_driver<CuT<T>::type>(cvs(alpha), A->A, &B->A, cvs(beta), C->A); \
 }
@@ -1171,7 +1174,7 @@ SB200_FOR_TYPES(SB200_DEF_RUNTIME)
  * the low-precision factorisation of posv_mixed (src/posv_mixed.cc:171-176) */
 int sb200_potrf_tc05_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info)
 {
-    (void) opts;
+    SB_TRY(options_status(opts));
     if (! h) return SB200_EINVAL;
     return potrf_driver<float>(h->A, info, true, nullptr, nullptr);
 }

@@ -101,10 +101,13 @@ struct PlanBuffer {
 
 // one batched launch per shape class; herk != 0 forces the diagonal of triangle-masked complex tiles real
 template <typename T>
-inline int launch_batches(const std::vector<Batch>& bs, const PlanBuffer& pb, int opA, int opB,
-                          T alpha, T beta, int ld, int herk, cudaStream_t s)
+inline int launch_batches(const std::vector<Batch>& bs, const PlanBuffer& pb, int opA, int opB_wide,
+                          T alpha, T beta, int ld, int herk, cudaStream_t s, int opB_skinny = 0)
 {
     for (const auto& b : bs) {
+        // batches with a skinny right operand (n <= SKINNY_MAX_N) may carry their B in another orientation (the
+        // transposed-B-panel path keeps them untransposed so that they stay on the HBM-bound streaming kernel)
+        const int opB = (opB_skinny && b.n <= SKINNY_MAX_N) ? opB_skinny : opB_wide;
         GemmParamsT<T> p{};
         const size_t cnt = b.C.size();
         p.A = reinterpret_cast<const T* const*>(pb.dev + b.off);
@@ -220,6 +223,19 @@ int solve_mixed_dist_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B
                        bool use_fallback, int* iter_out, int64_t* info_out, double* timers_ms);
 
 } // namespace sb200
+
+// Driver options (include/slate_b200.h sb200_options_t; reference: slate::Option::{Lookahead, InnerBlocking, PivotThreshold},
+// src/potrf.cc:41-42, src/getrf.cc:38-43).  The runtime's pipelines have a fixed depth (lookahead 1) and the LU panel
+// always takes the largest candidate (threshold 1.0): anything else is REJECTED, never silently ignored.
+// InnerBlocking only re-associates the panel's rank-ib updates in the reference (no effect on the pivot rule); the GPU
+// panel has its own fixed blocking, so any positive value is accepted as the hint it is.
+inline int options_status(const sb200_options_t* o)
+{
+    if (! o) return SB200_OK;
+    if (o->lookahead < 0 || o->inner_blocking < 1 || ! (o->pivot_threshold >= 0.0 && o->pivot_threshold <= 1.0)) return SB200_EINVAL;
+    if (o->lookahead != 1 || o->pivot_threshold != 1.0) return SB200_ENOTSUP;
+    return SB200_OK;
+}
 
 struct sb200_grid_s   { sb200::Grid g; };
 struct sb200_matrix_s { sb200::Matrix A; };

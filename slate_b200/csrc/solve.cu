@@ -737,7 +737,7 @@ extern "C" {
 #define SB200_DEF_SOLVE(X, T, R) \
 int sb200_potrs_##X(sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! A || ! B) return SB200_EINVAL; \
     if (A->A.dtype != TypeChar<CuS<T>::type>::value) return SB200_EINVAL; \
     CUDA_TRY(cudaDeviceSynchronize()); \
@@ -745,7 +745,7 @@ int sb200_potrs_##X(sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* o
 } \
 int sb200_hemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! A || ! Xm || ! C) return SB200_EINVAL; \
     if (A->A.dtype != TypeChar<CuS<T>::type>::value || Xm->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
     CUDA_TRY(cudaDeviceSynchronize()); \
@@ -753,7 +753,7 @@ int sb200_hemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_m
 } \
 int sb200_symm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! A || ! Xm || ! C) return SB200_EINVAL; \
     if (A->A.dtype != TypeChar<CuS<T>::type>::value || Xm->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
     CUDA_TRY(cudaDeviceSynchronize()); \
@@ -761,7 +761,7 @@ int sb200_symm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_m
 } \
 int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts) \
 { \
-    (void) opts; \
+    SB_TRY(options_status(opts));\
     if (! A || ! B) return SB200_EINVAL; \
     if (! valid_side(side) || ! valid_uplo(uplo) || ! valid_op(op) || ! valid_diag(diag)) return SB200_EINVAL; \
     if (side != 'L' || uplo != 'L' || op != 'N') return SB200_ENOTSUP; \
@@ -798,9 +798,9 @@ static int getrs_any(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B)
 }
 
 int sb200_getrs_d(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts)
-{ (void) opts; return (A && A->A.dtype == 'd') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
+{ SB_TRY(options_status(opts)); return (A && A->A.dtype == 'd') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
 int sb200_getrs_s(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts)
-{ (void) opts; return (A && A->A.dtype == 's') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
+{ SB_TRY(options_status(opts)); return (A && A->A.dtype == 's') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
 
 int sb200_posv_mixed_d(sb200_matrix_t A, sb200_matrix_t B, sb200_matrix_t Xm, const sb200_mixed_options_t* mo,
                        int* iter, int64_t* info, double* timers_ms8)

@@ -61,8 +61,9 @@ _matrix_to_host_local = _sig("sb200_matrix_to_host_local", [c_ptr, c_ptr, c_ptr]
 _last_panel_ms = _sig("sb200_last_driver_panel_ms", [c_ptr], c_dbl)
 _matrix_copy = _sig("sb200_matrix_copy", [c_ptr, c_ptr, c_ptr])
 _matrix_local_tiles = _sig("sb200_matrix_local_tiles", [c_ptr], c_i64)
-_matrix_from_scalapack = _sig("sb200_matrix_from_scalapack", [c_ptr, c_ptr, c_i64, c_int, c_ptr])
-_matrix_to_scalapack = _sig("sb200_matrix_to_scalapack", [c_ptr, c_ptr, c_i64, c_int, c_ptr])
+_matrix_probe_mv = _sig("sb200_matrix_probe_mv", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr])
+_matrix_from_scalapack = _sig("sb200_matrix_from_scalapack", [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr])
+_matrix_to_scalapack = _sig("sb200_matrix_to_scalapack", [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr])
 _last_ms = _sig("sb200_last_driver_ms", [c_ptr], c_dbl)
 _potrf = {t: _sig(f"sb200_potrf_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64)]) for t in "sdcz"}
 _potrf["s_tc05"] = _sig("sb200_potrf_tc05_s", [c_ptr, _OP, ctypes.POINTER(c_i64)])
@@ -229,7 +230,7 @@ class Matrix:
         """Gather this rank's tiles from a ScaLAPACK-style local array (Matrix::fromScaLAPACK, include/slate/Matrix.hh:75-99):
         `local` is a torch tensor (CPU or CUDA) holding the column-major local array, leading dimension lld."""
         lld = self._check_scalapack(local, lld)
-        check(_matrix_from_scalapack(self._h, local.data_ptr(), lld, 1 if local.is_cuda else 0, _stream()), "from_scalapack")
+        check(_matrix_from_scalapack(self._h, local.data_ptr(), lld, int(local.shape[0]), 1 if local.is_cuda else 0, _stream()), "from_scalapack")
         if sync:
             import torch
             torch.cuda.current_stream().synchronize()
@@ -237,19 +238,33 @@ class Matrix:
 
     def to_scalapack(self, local, lld: int | None = None, sync: bool = True):
         lld = self._check_scalapack(local, lld)
-        check(_matrix_to_scalapack(self._h, local.data_ptr(), lld, 1 if local.is_cuda else 0, _stream()), "to_scalapack")
+        check(_matrix_to_scalapack(self._h, local.data_ptr(), lld, int(local.shape[0]), 1 if local.is_cuda else 0, _stream()), "to_scalapack")
         if sync:
             import torch
             torch.cuda.current_stream().synchronize()
         return local
+
+    def _numroc(self):
+        """ScaLAPACK numroc: rows and columns of this rank's local array (tile (i, j) at local block (i // p, j // q))."""
+        g, nb = self.grid, self.nb
+        prow, pcol = g.rank % g.p, g.rank // g.p
+        mt, nt = -(-self.m // nb), -(-self.n // nb)
+        rows = sum(min(nb, self.m - i * nb) for i in range(prow, mt, g.p))
+        cols = sum(min(nb, self.n - j * nb) for j in range(pcol, nt, g.q))
+        return rows, cols
 
     def _check_scalapack(self, t, lld):
         import torch
         if not (isinstance(t, torch.Tensor) and t.dtype == _torch_dtype(self.dtype) and t.is_contiguous() and t.dim() == 2):
             raise Exception_("local array must be a contiguous 2-D torch tensor [local columns][lld] of the matrix type")
         lld = int(lld if lld is not None else t.shape[1])            # row-major [cols][lld] == column-major lld x cols
+        rows, cols = self._numroc()
         if lld > t.shape[1]:
             raise Exception_("lld exceeds the local array")
+        if lld < max(rows, 1):
+            raise Exception_(f"lld = {lld} is smaller than this rank's {rows} local rows")
+        if t.shape[0] < cols:
+            raise Exception_(f"local array holds {t.shape[0]} columns, this rank owns {cols}")
         return lld
 
     def _check_local(self, t):
@@ -551,3 +566,92 @@ def gesv_mixed(A: Matrix, B: Matrix, X: Matrix, opts: dict | None = None):
     piv = np.frombuffer(flat, dtype=np.int64)[: 2 * mn].reshape(-1, 2)
     pivots = [[(int(t), int(off)) for t, off in piv[k0:min(k0 + A.nb, mn)]] for k0 in range(0, mn, A.nb)]
     return int(info.value), int(it.value), pivots, dict(zip(MIXED_TIMERS, list(tm)))
+
+
+# -- probe-vector residual checks (bench-size substitute for the tester's ||B - A X|| checks) -------------
+def probe_mv(A: Matrix, x, part: str = "G", op: str = "N", diag: str = "N", use_abs: bool = False):
+    """y = op(part(A)) x for a replicated device vector x (torch CUDA tensor of the matrix type): every rank multiplies
+    the tiles it stores (sb200_matrix_probe_mv) and the partial results are summed over the grid's ranks."""
+    import torch
+    rows, cols = (A.m, A.n) if op == "N" else (A.n, A.m)
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == _torch_dtype(A.dtype) and x.is_contiguous()
+            and x.numel() == cols):
+        raise Exception_(f"probe vector must be a contiguous CUDA {A.dtype} tensor of {cols} elements")
+    y = torch.zeros(rows, dtype=x.dtype, device=x.device)
+    torch.cuda.current_stream().synchronize()
+    check(_matrix_probe_mv(A._h, ord(part), ord(op), ord(diag), 1 if use_abs else 0, x.data_ptr(), y.data_ptr(), _stream()),
+          "probe_mv")
+    if A.grid.p * A.grid.q > 1:
+        import torch.distributed as dist
+        if y.is_complex():
+            yr = torch.view_as_real(y)
+            dist.all_reduce(yr)
+        else:
+            dist.all_reduce(y)
+    return y
+
+
+def _probe_vector(n, dtype, seed=7):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, dtype=torch.float64, generator=g) - 0.5
+    if np.dtype(dtype).kind == "c":
+        x = torch.complex(x, torch.rand(n, dtype=torch.float64, generator=g) - 0.5)
+    return x.to(_torch_dtype(dtype)).cuda()
+
+
+def _eps(dtype):
+    return float(np.finfo(np.dtype(dtype)).eps)
+
+
+def potrf_residual(A0: HermitianMatrix, L: HermitianMatrix, seed: int = 7) -> dict:
+    """|| A x - L (L^H x) ||_max / (n ||A||_1 ||x||_max) for a seeded probe vector (the tester's Cholesky check,
+    test/test_posv.cc:336-342, with X = one vector); tolerance = the tester's 50 eps / 2."""
+    x = _probe_vector(A0.n, A0.dtype, seed)
+    y = probe_mv(A0, x, "H")
+    z = probe_mv(L, x, "L", "C")
+    w = probe_mv(L, z, "L", "N")
+    anorm = float(probe_mv(A0, x.new_ones(A0.n), "H", use_abs=True).abs().max())
+    err = float((y - w).abs().max()) / (max(A0.n, 1) * anorm * float(x.abs().max()))
+    tol = 25.0 * _eps(A0.dtype) if np.dtype(A0.dtype).kind != "c" else 25.0 * _eps(np.dtype(A0.dtype).char.lower())
+    return {"residual": err, "tol": tol, "pass": bool(err <= tol), "kind": "||A x - L (L^H x)|| / (n ||A||_1 ||x||)"}
+
+
+def getrf_residual(A0: Matrix, LU: Matrix, pivots, seed: int = 7) -> dict:
+    """|| P A x - L (U x) ||_max / (n ||A||_1 ||x||_max) for a seeded probe vector (the tester's LU check,
+    test/test_gesv.cc:371-377, with X = one vector); pivots as returned by getrf."""
+    import torch
+    x = _probe_vector(A0.n, A0.dtype, seed)
+    y = probe_mv(A0, x, "G").cpu().numpy()
+    nb = A0.nb
+    for k, blk in enumerate(pivots):                      # apply P: the panels' interchanges in order
+        for j, (t, off) in enumerate(blk):
+            r, p = k * nb + j, (k + t) * nb + off
+            if p != r:
+                y[r], y[p] = y[p], y[r]
+    z = probe_mv(LU, x, "U")                              # U is min(m,n) x n: rows beyond it come out zero
+    mn = min(LU.m, LU.n)
+    zz = torch.zeros(LU.n, dtype=z.dtype, device=z.device)
+    zz[:mn] = z[:mn]
+    w = probe_mv(LU, zz, "L", "N", "U").cpu().numpy()
+    anorm = float(probe_mv(A0, x.new_ones(A0.m), "G", "C", use_abs=True).abs().max())      # column sums: one-norm
+    err = float(np.abs(y - w).max()) / (max(A0.n, 1) * anorm * float(x.abs().max()))
+    tol = 25.0 * _eps(np.dtype(A0.dtype).char.lower() if np.dtype(A0.dtype).kind == "c" else A0.dtype)
+    return {"residual": err, "tol": tol, "pass": bool(err <= tol), "kind": "||P A x - L (U x)|| / (n ||A||_1 ||x||)"}
+
+
+def gemm_residual(alpha, A: Matrix, B: Matrix, beta, c0x, C: Matrix, x) -> dict:
+    """|| C x - (alpha A (B x) + beta C0 x) ||_max / (sqrt(k) (|alpha| ||A|| ||B|| + |beta| ||C0||) ||x||)-style check with a
+    probe vector (test/test_gemm.cc:205-207 with X = one vector).  c0x = probe_mv(C0, x) taken before the multiply."""
+    bx = probe_mv(B, x, "G")
+    abx = probe_mv(A, bx, "G")
+    cx = probe_mv(C, x, "G")
+    want = alpha * abx + beta * c0x
+    ones_n, ones_k = x.new_ones(B.n), x.new_ones(A.n)
+    an = float(probe_mv(A, ones_k, "G", use_abs=True).abs().max())
+    bn = float(probe_mv(B, ones_n, "G", use_abs=True).abs().max())
+    c0n = float(c0x.abs().max())
+    denom = (abs(alpha) * an * bn + abs(beta) * c0n) * float(x.abs().max()) * np.sqrt(float(A.n))
+    err = float((cx - want).abs().max()) / denom
+    tol = 3.0 * _eps(np.dtype(A.dtype).char.lower() if np.dtype(A.dtype).kind == "c" else A.dtype)
+    return {"residual": err, "tol": tol, "pass": bool(err <= tol), "kind": "||C x - (alpha A (B x) + beta C0 x)|| / (sqrt(k) (|alpha| ||A|| ||B|| + |beta| ||C0 x||) ||x||)"}
