@@ -8,10 +8,13 @@ A "step" is ONE full factorisation (default routine: dpotrf, Cholesky) of a fres
 matrix that is already resident in HBM when the timed region starts (`value`), and the same
 through the public API from pinned HOST buffers, H2D + D2H inside the timed region (`e2e`).
 
-N = 1 workload: BASELINE.json configs[1]  "dpotrf n=32768 nb=512 on 1 B200".
-N > 1: the same routine at the n the headline metric is quoted on (n = 65536, fixed total work
-for N = 2, 4, 8 -> "strong"), 2-D block-cyclic over a p x q grid of N ranks (one process per
-GPU, NCCL panel broadcast).  The metric is a rate (TFLOP/s), so N = 1 at n = 32768 is comparable.
+Workload at every N: the n the headline metric is quoted on (BASELINE.json: dpotrf/dgetrf/dgemm at
+n = 65536 on 1/2/4/8 B200; it fits one GPU), nb = 512, 2-D block-cyclic over a p x q grid of N ranks
+(one process per GPU, NCCL panel broadcasts) -> fixed total work, "scaling": "strong".  The default
+run times dpotrf as the line's `value` and dgetrf / dgemm at the same n as `also` sub-records, each
+with an untimed probe-vector residual `check` (the tester's tolerances).  BASELINE configs[1]
+(n = 32768) is `--size 32768`.  `value` is wall clock between barriers (driver entry to return, the
+restore copy of the input included and reported); `device_ms_per_step` is the in-driver event time.
 
 Prints exactly one JSON line on rank 0.
 """
@@ -19,6 +22,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -50,38 +54,73 @@ def _switches() -> dict:
 
 
 def default_n(routine: str, ngpus: int) -> int:
-    # N = 1: the single-GPU configuration BASELINE.json names (configs[1], n = 32768);
-    # N > 1: the n the headline metric is quoted on (n = 65536), fixed total work for N = 2, 4, 8.
-    if routine == "gemm":
-        return 16384 if ngpus == 1 else 32768
-    return 32768 if ngpus == 1 else 65536
+    # the n the headline metric is quoted on (BASELINE.json: "dpotrf/dgetrf/dgemm TFLOP/s at n=65536, 1/2/4/8 B200"),
+    # the SAME at every N, so "scaling": "strong" is literally true.  n = 65536 fits one B200 (potrf: 2 x 17 GB, getrf:
+    # 2 x 34 GB, gemm: 3 x 34 GB of the 180 GB); BASELINE configs[1] (n = 32768) is `--size 32768`.
+    return 65536
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region.  In-process NVML (nvidia_ml_py) queries: spawning
+    `nvidia-smi` five times a second was measured (r2b) to stall the CUDA API calls of the launch loop by 40-280 ms per
+    step.  Falls back to `nvidia-smi` once a second when NVML cannot be loaded."""
 
-    def __init__(self, index: int, period: float = 0.2):
+    def __init__(self, index: int, period: float = 0.25):
         super().__init__(daemon=True)
         self.index = index
         self.period = period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._halt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [x for x in vis.split(",") if x.strip() != ""]
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+            self.period = max(period, 1.0)
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for nm, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                        ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        self.samples.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for nm, v in zip(names, f[2:]):
+            if v.lower().startswith("active"):
+                self.reasons.add(nm)
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for nm, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(nm)
+                if self._nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
             self._halt.wait(self.period)
@@ -91,7 +130,7 @@ class ClockSampler(threading.Thread):
         self.join(timeout=10)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+                "reasons": sorted(self.reasons), "samples": len(s), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def cpu_reference_run(routine: str, n: int, nb: int, threads: int):
@@ -142,13 +181,21 @@ def run_reference(args):
         return 0
     else:
         val = flops(args.routine, n) / (ms * 1e-3) / 1e12
-    sample = f"d{args.routine} n={n} nb={args.nb} Target::HostTask (OpenMP tasks + OpenBLAS), {threads} threads"
+    n_full = args.n or default_n(args.routine, args.gpus)
+    p = int(math.floor(math.sqrt(args.gpus)))
+    while args.gpus % p:
+        p -= 1
+    q = args.gpus // p
+    sample = (f"d{args.routine} n={n} nb={args.nb} Target::HostTask (OpenMP tasks + OpenBLAS), {threads} host threads: a bounded "
+              f"sample of the n={n_full} workload (same generator, seed and tile size; the full size takes minutes per step "
+              f"on the host) -- the metric is a rate")
     line = {
         "impl": "reference", "metric": f"d{args.routine} TFLOP/s", "value": val, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (reference matgen Philox rand/rand_dominant, seed 42)",
-        "config": {"workload": sample, "routine": args.routine, "n": n, "nb": args.nb},
+        "config": workload_config(args.routine, n_full, args.nb, p, q, args.gpus),
+        "sample_n": n,
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -476,6 +523,172 @@ def run_extra(args):
     return 0
 
 
+def _barrier(torch, dist, world):
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(torch, dist, world, vals):
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+GEMM_VARIANT = {"potrf": "NT", "getrf": "NT", "gemm": "NT"}     # the gemm_dmma_kernel variant each routine's update runs
+
+
+def measured_traffic(routine):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the trailing-update kernel, from the committed
+    `ncu --set full` capture of the variant THIS routine runs (profiles/gemm_dram_bytes_per_launch.json); None if that
+    variant was never captured."""
+    try:
+        d = json.load(open(os.path.join(HERE, "profiles", "gemm_dram_bytes_per_launch.json")))
+        v = d.get("variants", {}).get(f"{routine}:{GEMM_VARIANT[routine]}")
+        return (v or {}).get("dram_bytes_per_launch"), (v or {}).get("algorithmic_bytes_per_launch"), (v or {}).get("source")
+    except Exception:
+        return None, None, None
+
+
+def run_factor_bench(routine, n, nb, grid, world, steps, warmup, env, with_clocks=False, local_rank=0):
+    """One routine at one size: warm-up, K timed steps bracketed by barrier + synchronize (wall clock, max over ranks;
+    the restore copy of the input is inside the bracket and reported), device-event times from the driver, the trailing
+    kernel's roofline numbers, and an untimed probe-vector residual check of the last result."""
+    import ctypes
+    torch, dist, sl, lib, check_, c_dbl, c_ptr = (env[k] for k in ("torch", "dist", "sl", "lib", "check", "c_dbl", "c_ptr"))
+    al, be = 3.141592653589793, 2.718281828459045
+    pivots = [None]
+    if routine == "potrf":
+        A0 = sl.HermitianMatrix(n, nb, grid).generate("rand_dominant", 42)
+        A = sl.HermitianMatrix(n, nb, grid)
+        run = lambda: sl.potrf(A)
+        restore = lambda: A.copy_from(A0)
+        mats = [A0, A]
+    elif routine == "getrf":
+        A0 = sl.Matrix(n, n, nb, grid).generate("rand", 42)
+        A = sl.Matrix(n, n, nb, grid)
+
+        def run():
+            pivots[0], info = sl.getrf(A)
+            return info
+        restore = lambda: A.copy_from(A0)
+        mats = [A0, A]
+    else:
+        Am = sl.Matrix(n, n, nb, grid).generate("rand", 42)
+        Bm = sl.Matrix(n, n, nb, grid).generate("rand", 43)
+        A = sl.Matrix(n, n, nb, grid).generate("rand", 44)
+        A0 = None
+        run = lambda: (sl.gemm(al, Am, Bm, be, A), 0)[1]
+        restore = lambda: None          # C keeps accumulating (alpha A B + beta C); the check below runs on a fresh C
+        mats = [Am, Bm, A]
+    out = A
+    stats = (c_dbl * 4)()
+    lib.sb200_last_driver_stats.argtypes = [c_ptr, ctypes.POINTER(c_dbl)]
+    for _ in range(warmup):
+        restore(); info = run()
+        if info != 0:
+            raise SystemExit(f"bench.py: {routine} returned info={info}")
+    sampler = None
+    if with_clocks:
+        sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = lib.sb200_launch_count()
+    dev_ms, trail_ms, trail_flops, trail_launches, panel_ms = [], 0.0, 0.0, 0.0, 0.0
+    _barrier(torch, dist, world); w0 = time.perf_counter()
+    for _ in range(steps):
+        restore(); run()
+        check_(lib.sb200_last_driver_stats(out._h, stats))
+        dev_ms.append(stats[0]); trail_ms += stats[1]; trail_flops += stats[2]; trail_launches += stats[3]
+        panel_ms += out.last_panel_ms
+    _barrier(torch, dist, world); w1 = time.perf_counter()
+    launches = lib.sb200_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    # restore cost (inside the bracket above), measured once
+    _barrier(torch, dist, world); r0 = time.perf_counter(); restore(); _barrier(torch, dist, world)
+    restore_ms = (time.perf_counter() - r0) * 1e3
+    wall_ms, device_ms, restore_ms = _max_over_ranks(torch, dist, world, [(w1 - w0) * 1e3 / steps, sum(dev_ms) / len(dev_ms), restore_ms])
+    fl = flops(routine, n)
+    rec = {"value": fl / (wall_ms * 1e-3) / 1e12, "ms_per_step": wall_ms, "device_ms_per_step": device_ms,
+           "restore_ms_per_step": restore_ms if routine != "gemm" else 0.0, "steps": steps, "warmup": warmup, "n": n, "nb": nb,
+           "trail_ms_per_step": trail_ms / steps, "trail_flops_per_step": trail_flops / steps,
+           "trail_launches": int(trail_launches), "panel_stream_ms_per_step": panel_ms / steps,
+           "gpu_launches": int(launches), "clocks": clocks}
+    # ---- untimed check of a fresh result (probe-vector residual; tolerance = the tester's)
+    if routine == "potrf":
+        restore(); run()
+        rec["check"] = sl.potrf_residual(A0, A)
+    elif routine == "getrf":
+        restore(); run()
+        rec["check"] = sl.getrf_residual(A0, A, pivots[0])
+    else:
+        A.generate("rand", 44)
+        x = sl._probe_vector(n, A.dtype, 5)
+        c0x = sl.probe_mv(A, x, "G")
+        run()
+        rec["check"] = sl.gemm_residual(al, Am, Bm, be, c0x, A, x)
+    return rec, mats, (A0, A)
+
+
+def e2e_potrf(n, nb, grid, world, steps, env, mats):
+    """The same metric through the public API with HOST buffers: pinned host tiles -> device -> potrf -> host, all inside
+    the timed region (wall clock between barriers, max over ranks).  Mode 2 (one rank): the input streams in by chunks
+    of block columns and finished block columns stream out while the factorisation runs (sl.potrf(in_local=, out_local=));
+    mode 1: the output streams out; mode 0: copy, factor, copy."""
+    torch, dist, sl = env["torch"], env["dist"], env["sl"]
+    A0, A = mats
+    mode = os.environ.get("SB200_E2E_OVERLAP")
+    mode = int(mode) if mode is not None else (2 if world == 1 else 1)
+    nelem = A.local_tiles * nb * nb
+    host = torch.empty(nelem, dtype=torch.float64).pin_memory()
+    res = torch.empty(nelem, dtype=torch.float64).pin_memory()
+    A0.to_host_local(host)            # setup (untimed): host copy of the seeded input
+    e2e_ms = []
+    for it in range(1 + steps):
+        _barrier(torch, dist, world); t0 = time.perf_counter()
+        if mode == 2 and world == 1:
+            info = sl.potrf(A, in_local=host, out_local=res)
+        else:
+            A.from_host_local(host, sync=False)
+            if mode == 1:
+                info = sl.potrf(A, out_local=res)
+            else:
+                info = sl.potrf(A)
+                A.to_host_local(res)
+        _barrier(torch, dist, world); t1 = time.perf_counter()
+        if info != 0:
+            raise SystemExit(f"bench.py: e2e potrf returned info={info}")
+        if it >= 1:
+            e2e_ms.append((t1 - t0) * 1e3)
+    # the streamed result is the factor the resident path produces (bitwise on one rank)
+    ok = None
+    if world == 1:
+        A.copy_from(A0); sl.potrf(A)
+        chk = torch.empty(nelem, dtype=torch.float64).pin_memory()
+        A.to_host_local(chk)
+        ok = bool(torch.equal(chk, res))
+        del chk
+    te = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
+    tb = torch.tensor([float(nelem * 8)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+    em, nbytes = float(te[0]), float(tb[0])
+    del host, res
+    return {"value": flops("potrf", n) / (em * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": em,
+            "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes), "overlap_mode": mode,
+            "matches_resident_result": ok,
+            "note": "pinned host tiles -> device -> potrf -> pinned host tiles on every rank, copies inside the timed region "
+                    "(mode 2: input and output stream by block columns while the factorisation runs; 1: output streams; 0: serial); "
+                    "bytes summed over ranks, time = max over ranks"}
+
+
+def workload_config(routine, n, nb, p, q, world):
+    return {"workload": f"d{routine} n={n} nb={nb} lookahead=1, {p}x{q} block-cyclic grid over {world} B200",
+            "routine": routine, "n": n, "nb": nb, "grid": [p, q],
+            "l2": "operands (>= 16 GiB per step) are far larger than the 126 MB L2; no explicit flush"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -487,9 +700,11 @@ def main():
     ap.add_argument("--n", "--size", dest="n", type=int, default=0,
                     help="matrix size (use --size under torchrun, whose own parser claims the prefix --n)")
     ap.add_argument("--nb", type=int, default=512)
-    ap.add_argument("--ref-n", type=int, default=8192, help="bounded sample size for the CPU reference legs")
+    ap.add_argument("--ref-n", type=int, default=16384, help="bounded sample size for the CPU reference legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the dgetrf / dgemm sub-records of the default run")
+    ap.add_argument("--also-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -497,7 +712,6 @@ def main():
         return run_extra(args)
 
     import ctypes
-    import numpy as np
     import torch
     import torch.distributed as dist
     import slate_b200.host as sl
@@ -517,134 +731,53 @@ def main():
     n = args.n or default_n(routine, world)
     grid = sl.Grid.from_torch_distributed() if world > 1 else sl.Grid()
     st = torch.cuda.current_stream().cuda_stream
+    env = {"torch": torch, "dist": dist, "sl": sl, "lib": lib, "check": check, "c_dbl": c_dbl, "c_ptr": c_ptr}
+    warmup = max(args.warmup, 3)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    rec, mats, pair = run_factor_bench(routine, n, nb, grid, world, args.steps, warmup, env, True, local_rank)
+    peak = fp64_peak_probe(lib, st)
+    peak = _max_over_ranks(torch, dist, world, [peak])[0]
 
-    # ---- operands (resident in HBM before the timed region); a pristine copy restores the input
-    if routine == "potrf":
-        A0 = sl.HermitianMatrix(n, nb, grid).generate("rand_dominant", 42)
-        A = sl.HermitianMatrix(n, nb, grid)
-        run = lambda: sl.potrf(A)
-        restore = lambda: A.copy_from(A0)
-        out = A
-    elif routine == "getrf":
-        A0 = sl.Matrix(n, n, nb, grid).generate("rand", 42)
-        A = sl.Matrix(n, n, nb, grid)
-        run = lambda: sl.getrf(A)[1]
-        restore = lambda: A.copy_from(A0)
-        out = A
-    else:
-        Am = sl.Matrix(n, n, nb, grid).generate("rand", 42)
-        Bm = sl.Matrix(n, n, nb, grid).generate("rand", 43)
-        A0 = sl.Matrix(n, n, nb, grid).generate("rand", 44)
-        A = sl.Matrix(n, n, nb, grid)
-        run = lambda: (sl.gemm(3.141592653589793, Am, Bm, 2.718281828459045, A), 0)[1]
-        restore = lambda: A.copy_from(A0)
-        out = A
-
-    stats = (c_dbl * 4)()
-    lib.sb200_last_driver_stats.argtypes = [c_ptr, ctypes.POINTER(c_dbl)]
-
-    for _ in range(max(args.warmup, 3)):
-        restore(); info = run()
-        if info != 0:
-            raise SystemExit(f"bench.py: {routine} returned info={info}")
-
-    # ---- timed region: K steps, device time by CUDA events inside the driver (on its own
-    #      streams), bracketed by barrier + synchronize; max over ranks
-    sampler = ClockSampler(local_rank); sampler.start()
-    launches0 = lib.sb200_launch_count()
-    barrier(); w0 = time.perf_counter()
-    step_ms, trail_ms, trail_flops, trail_launches, panel_ms = [], 0.0, 0.0, 0.0, 0.0
-    for _ in range(args.steps):
-        restore(); run()
-        check(lib.sb200_last_driver_stats(out._h, stats))
-        step_ms.append(stats[0]); trail_ms += stats[1]; trail_flops += stats[2]; trail_launches += stats[3]
-        panel_ms += out.last_panel_ms
-    barrier(); w1 = time.perf_counter()
-    launches = lib.sb200_launch_count() - launches0
-    clocks = sampler.stop()
-    t = torch.tensor([sum(step_ms) / len(step_ms), (w1 - w0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step, wall_ms_per_step = float(t[0]), float(t[1])
-    fl = flops(routine, n)
-    value = fl / (ms_per_step * 1e-3) / 1e12
-
-    # ---- FP64 tensor peak measured in this run (MEASURED_PEAKS.json has no FP64 figure)
-    lib.sb200_fp64_peak_probe.argtypes = [c_int, c_int, c_int, c_ptr, ctypes.POINTER(c_dbl), c_ptr]
-    scratch = torch.zeros(16, dtype=torch.float64, device="cuda")
-    pf = c_dbl(0)
-    lib.sb200_fp64_peak_probe(0, 2000, 4, scratch.data_ptr(), ctypes.byref(pf), st)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); lib.sb200_fp64_peak_probe(0, 40000, 4, scratch.data_ptr(), ctypes.byref(pf), st); e1.record()
-    torch.cuda.synchronize()
-    peak = pf.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
-    achieved = trail_flops / (trail_ms * 1e-3) / 1e12 if trail_ms > 0 else 0.0
-    traffic = None
-    tfile = os.path.join(HERE, "profiles", "gemm_dram_bytes_per_launch.json")
-    if os.path.exists(tfile):
-        try:
-            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel (trailing-update batched tile GEMM/HERK, FP64 DMMA)",
+    def roofline_of(r, rt):
+        achieved = r["trail_flops_per_step"] / (r["trail_ms_per_step"] * 1e-3) / 1e12 if r["trail_ms_per_step"] > 0 else 0.0
+        traffic, alg_bytes, tsrc = measured_traffic(rt)
+        return {"bound": "tensor", "kernel": f"gemm_dmma_kernel<{GEMM_VARIANT[rt]}> (trailing-update batched tile GEMM/HERK, FP64 DMMA)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic,
+                "traffic": traffic, "algorithmic_bytes": alg_bytes, "traffic_source": tsrc,
                 "peak_source": "FP64 DMMA.8x8x4 probe measured live in this run (sb200_fp64_peak_probe); "
                                "MEASURED_PEAKS.json carries no FP64 figure",
-                "launches_timed": int(trail_launches),
-                "trailing_ms_per_step": trail_ms / args.steps, "panel_stream_ms_per_step": panel_ms / args.steps,
-                "whole_step_frac_of_peak": value / (world * peak) if peak else None}
+                "launches_timed": r["trail_launches"], "trailing_ms_per_step": r["trail_ms_per_step"],
+                "panel_stream_ms_per_step": r["panel_stream_ms_per_step"],
+                "whole_step_frac_of_peak": r["value"] / (world * peak) if peak else None}
 
-    # ---- e2e: public API with HOST buffers (pinned), H2D + driver + D2H inside the timed region.
-    #      Every rank moves ITS tiles (packed local tile storage, as Matrix::insertLocalTiles hands
-    #      SLATE caller-owned memory); wall clock between barriers, max over ranks.
+    roofline = roofline_of(rec, routine)
+
+    # ---- e2e (potrf): public API with HOST buffers, copies inside the timed region
     e2e = None
-    if not args.no_e2e:
-        nelem = out.local_tiles * nb * nb
-        host = torch.empty(nelem, dtype=torch.float64).pin_memory()
-        res = torch.empty(nelem, dtype=torch.float64).pin_memory()
-        A0.to_host_local(host)            # setup (untimed): host copy of the seeded input
-        e2e_ms = []
-        # opt-in (round-2 candidate, not yet run): D2H of finished block columns overlapped inside the driver
-        overlap_d2h = routine == "potrf" and os.environ.get("SB200_E2E_OVERLAP") == "1"
-        # opt-in (round-2 candidate, not yet run; one rank): the input streams in by chunks of block columns as well
-        overlap_both = routine == "potrf" and world == 1 and os.environ.get("SB200_E2E_OVERLAP") == "2"
-        for it in range(1 + args.steps):
-            barrier(); t0 = time.perf_counter()
-            if overlap_both:
-                sl.potrf(A, in_local=host, out_local=res)
-                barrier(); t1 = time.perf_counter()
-                if it >= 1:
-                    e2e_ms.append((t1 - t0) * 1e3)
-                continue
-            A.from_host_local(host, sync=False)
-            if overlap_d2h:
-                sl.potrf(A, out_local=res)          # finished block columns stream to the host while it factors
-            else:
-                run()
-                A.to_host_local(res)
-            barrier(); t1 = time.perf_counter()
-            if it >= 1:
-                e2e_ms.append((t1 - t0) * 1e3)
-        te = torch.tensor([sum(e2e_ms) / len(e2e_ms), float(nelem * 8)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            tmax = te.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = te.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            em, nbytes = float(tmax[0]), float(tsum[1])
-        else:
-            em, nbytes = float(te[0]), float(te[1])
-        e2e = {"value": fl / (em * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": em,
-               "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes),
-               "note": "pinned host tiles -> Matrix.from_host_local -> driver -> Matrix.to_host_local on every rank; "
-                       "bytes summed over ranks, time = max over ranks"}
-        del host, res
+    if not args.no_e2e and routine == "potrf":
+        e2e = e2e_potrf(n, nb, grid, world, min(args.steps, 3), env, pair)
+    elif not args.no_e2e:
+        e2e = {"value": None, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "the end-to-end leg is measured on the default routine (potrf)"}
+    for m in mats:
+        m.close()
+    del mats, pair
+    torch.cuda.empty_cache()
+
+    # ---- the metric's other two routines at the same n, timed in the same run (fewer steps)
+    also = {}
+    if routine == "potrf" and not args.no_also:
+        for rt in ("getrf", "gemm"):
+            r2, m2, _ = run_factor_bench(rt, n, nb, grid, world, max(1, min(args.also_steps, args.steps)), 1, env)
+            for m in m2:
+                m.close()
+            del m2, _
+            torch.cuda.empty_cache()
+            also["d" + rt] = {"value": r2["value"], "unit": "TFLOP/s", "ms_per_step": r2["ms_per_step"],
+                              "device_ms_per_step": r2["device_ms_per_step"], "steps": r2["steps"], "warmup": r2["warmup"],
+                              "frac_of_aggregate_peak": r2["value"] / (world * peak) if peak else None,
+                              "roofline": roofline_of(r2, rt), "check": r2["check"], "gpu_launches": r2["gpu_launches"],
+                              "config": workload_config(rt, n, nb, grid.p, grid.q, world)}
 
     # ---- CPU baseline: reference HostTask on this box's cores, bounded sample (rank 0, N = 1)
     cpu = None
@@ -653,24 +786,23 @@ def main():
             threads = os.cpu_count() or 1
             secs, kind = cpu_reference_run(routine, args.ref_n, nb, threads)
             cpu = {"value": flops(routine, args.ref_n) / secs / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": kind,
-                   "sample": f"d{routine} n={args.ref_n} nb={nb} Target::HostTask, one run, {secs:.2f} s"}
+                   "sample": f"d{routine} n={args.ref_n} nb={nb} Target::HostTask (the workload's generator and tile size at a "
+                             f"bounded n), one run, {secs:.2f} s"}
         except Exception as ex:   # noqa: BLE001
             cpu = {"value": None, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
 
     if rank == 0:
-        p, q = grid.p, grid.q
+        cfg = workload_config(routine, n, nb, grid.p, grid.q, world)
         line = {
-            "metric": f"d{routine} TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "wall_ms_per_step": wall_ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "metric": f"d{routine} TFLOP/s", "value": rec["value"], "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": rec["ms_per_step"],
+            "device_ms_per_step": rec["device_ms_per_step"], "restore_ms_per_step": rec["restore_ms_per_step"],
+            "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (reference matgen: Philox-2x64 rand_dominant/rand, seed 42, generated on device)",
-            "config": {"workload": f"d{routine} n={n} nb={nb} lookahead=1, {p}x{q} block-cyclic grid over {world} B200",
-                       "routine": routine, "n": n, "nb": nb, "grid": [p, q],
-                       "l2": "inputs (>= 4 GiB per step) are far larger than the 126 MB L2; no explicit flush",
-                       "switches": _switches()},
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches),
+            "config": cfg, "switches": _switches(), "frac_of_aggregate_peak": rec["value"] / (world * peak) if peak else None,
+            "clocks": rec["clocks"], "roofline": roofline, "check": rec["check"], "also": also,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": rec["gpu_launches"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:

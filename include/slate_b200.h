@@ -320,9 +320,12 @@ int sb200_matrix_to_host_local_d(sb200_matrix_t A, double* htiles, sb200_stream_
 int sb200_matrix_copy_d(sb200_matrix_t dst, sb200_matrix_t src, sb200_stream_t stream);
 int64_t sb200_matrix_local_tiles(sb200_matrix_t A);
 
-/* options common to the drivers (NULL = the defaults).  Honour-or-reject: the runtime's pipelines have a fixed
- * lookahead depth of 1 and its LU panel always takes the largest candidate, so lookahead != 1 or
- * pivot_threshold != 1.0 returns SB200_ENOTSUP (out-of-range values SB200_EINVAL) -- never a silent ignore.
+/* options common to the drivers (NULL = the defaults).  Honour-or-reject, never a silent ignore:
+ *   lookahead: sb200_potrf_* honours 1 .. 8 (depth of its lookahead stream; 0 or NULL options = the library's tuned depth;
+ *              the factor is bitwise independent of it); every other driver has a fixed depth of 1 and returns
+ *              SB200_ENOTSUP for lookahead > 1;
+ *   pivot_threshold: the LU panel always takes the largest candidate; != 1.0 returns SB200_ENOTSUP;
+ *   out-of-range values return SB200_EINVAL.
  * inner_blocking only re-associates the reference panel's rank-ib updates (it does not enter the pivot rule,
  * src/internal/Tile_getrf.hh:160-447); the GPU panel has its own blocking and accepts any value >= 1. */
 typedef struct {

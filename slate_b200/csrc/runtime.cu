@@ -85,11 +85,11 @@ static int generate_t(Matrix& A, int kind_code, int64_t seed, cudaStream_t s)
     return status;
 }
 
-// panel workspace slot of tile row i for step k (multi-rank): [k & 1][i % p][i / p]
+// panel workspace slot of tile row i for step k (multi-rank): [k % depth][i % p][i / p]
 template <typename T>
 struct PanelWs {
-    T* base = nullptr; int p = 1; int64_t rows_max = 0, te = 0;
-    T* at(int64_t i, int64_t k) const { return base + ((k & 1) * p * rows_max + (i % p) * rows_max + i / p) * te; }
+    T* base = nullptr; int p = 1; int64_t rows_max = 0, te = 0; int depth = 2;
+    T* at(int64_t i, int64_t k) const { return base + ((k % depth) * p * rows_max + (i % p) * rows_max + i / p) * te; }
 };
 
 // every rank receives tiles (i, k), i >= i_first, of block column k of A: p grouped broadcasts of
@@ -113,14 +113,25 @@ static int bcast_block_column(Grid& g, Matrix& A, int64_t k, int64_t i_first, co
 }
 
 // ------------------------------------------------------------------------------------------
-// potrf: right-looking tile Cholesky with lookahead 1, lower.
-// reference schedule: src/potrf.cc:84-195 (panel task = potrf + tileBcast + trsm + listBcastMT,
-// lookahead task = herk/gemm on column k+1, trailing task = herk on the rest).
-// use_tc05 (float only): the trailing / lookahead updates run on the tcgen05 FP32-emulated kernel
-// (gemm_tc05.cu); the factored panel is split-packed once per step (A-side and B-side units).
+// potrf: right-looking tile Cholesky, lower, lookahead depth L (slate::Option::Lookahead, default 1).
+// reference schedule: src/potrf.cc:84-195 (panel task = potrf + tileBcast + trsm + listBcastMT, one lookahead task per
+// column k+1 .. k+L = herk/gemm on that column, trailing task = herk on the rest).
+//
+// Three streams ordered by events; the host never blocks inside the step loop:
+//   chain  (highest priority): [update of the diagonal tile (k,k) by panel k-1] -> potrf(k,k) -> L_kk down the process
+//           column -> panel solve -> panel broadcast.  The diagonal tile is updated FIRST and alone, so that its
+//           factorisation overlaps the update of the rest of column k on the lookahead stream ("critical tile first").
+//   look   (high priority): after panel k: columns k+1 .. k+L, one batched launch each (column k+1 without its
+//           diagonal tile), in order of urgency.
+//   trail  (low priority):  columns > k+L, one batched launch per shape class.
+// Every tile still receives its updates in step order, so the factor is bitwise independent of L.
+// Panel workspaces (multi-rank), packed panels (tcgen05 path) are rings of L+1 slots: the chain may run L+1 steps ahead of
+// the trailing stream, which is exactly what the data dependencies allow.
+// use_tc05 (float only): the updates run on the tcgen05 FP32-emulated kernel (gemm_tc05.cu); the factored panel is
+// split-packed once per step (A-side and B-side units).
 // ------------------------------------------------------------------------------------------
 template <typename T>
-int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, const void* host_in)
+int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, const void* host_in, int lookahead)
 {
     using R = typename RealOf<T>::type;
     Grid& g = *A.g;
@@ -136,11 +147,14 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
     const int64_t rows_max = (A.mt + g.p - 1) / g.p;        // panel workspace slots per process row
     const T one = from_real<T>(R(1)), minus_one = from_real<T>(R(-1));
     const int opH = IsComplex<T>::value ? 'C' : 'T';
-    // Streaming input (opt-in, host_in != nullptr; one rank, no tcgen05 path): the matrix arrives from the caller's
-    // packed host buffer in CHUNKS of block columns on a copy stream while the factorisation runs.  Inside a chunk the
-    // schedule below is unchanged (its updates only touch columns of the chunk); when the next chunk has arrived it
-    // first receives the updates of every finished step, one batched launch per step in step order, so every tile
-    // sees exactly the same sequence of updates as without streaming (bitwise identical factor).
+    if (lookahead <= 0) { const char* e = getenv("SB200_LOOKAHEAD"); lookahead = e ? atoi(e) : POTRF_DEFAULT_LOOKAHEAD; }
+    const int L = int(std::min<int64_t>(std::max(lookahead, 1), MAX_LOOKAHEAD));
+    const int NBUF = L + 1;                                  // ring of panel workspaces / packed panels
+    // Streaming input (host_in != nullptr; one rank, no tcgen05 path): the matrix arrives from the caller's packed host
+    // buffer in CHUNKS of block columns on a copy stream while the factorisation runs.  Inside a chunk the schedule is
+    // unchanged (its updates only touch columns of the chunk); when the next chunk has arrived it first receives the
+    // updates of every finished step, one batched launch per step in step order, so every tile sees exactly the same
+    // sequence of updates as without streaming (bitwise identical factor).
     const bool stream_in = host_in != nullptr;
     if (stream_in && (multi || use_tc05)) return SB200_ENOTSUP;
     std::vector<int64_t> cb{0};                              // chunk c = block columns [cb[c], cb[c+1])
@@ -157,31 +171,33 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
 
     DevBuf ws, dbuf, work, dinfo, packA, packB;
     if (multi) {
-        SB_TRY(ws.alloc(size_t(2) * g.p * rows_max * te * sizeof(T)));
+        SB_TRY(ws.alloc(size_t(NBUF) * g.p * rows_max * te * sizeof(T)));
         SB_TRY(dbuf.alloc(size_t(2) * te * sizeof(T)));
     }
     SB_TRY(work.alloc(size_t(1 + ceil_div(nb, FACTOR_IB)) * FACTOR_IB * FACTOR_IB * sizeof(T)));
     SB_TRY(dinfo.alloc(sizeof(int)));
     T* W_potrf = work.as<T>();
     T* W_trsm  = W_potrf + FACTOR_IB * FACTOR_IB;
-    PanelWs<T> pws{ws.as<T>(), g.p, rows_max, te};
+    PanelWs<T> pws{ws.as<T>(), g.p, rows_max, te, NBUF};
 
     auto pbuf = [&](int64_t i, int64_t k) -> T* {     // where step k's factored tile (i,k) is read from
         return multi ? pws.at(i, k) : A.tile_as<T>(i, k);
     };
-    // packed copies of panel tile i for step k (tcgen05 path): [k & 1][i]
+    // packed copies of panel tile i for step k (tcgen05 path): [k % NBUF][i]
     const size_t pa_bytes = use_tc05 ? tc05_packed_bytes('A', nb, nb) : 0;
     const size_t pb_bytes = use_tc05 ? tc05_packed_bytes('B', nb, nb) : 0;
     if (use_tc05) {
-        SB_TRY(packA.alloc(size_t(2) * nt * pa_bytes));
-        SB_TRY(packB.alloc(size_t(2) * nt * pb_bytes));
+        SB_TRY(packA.alloc(size_t(NBUF) * nt * pa_bytes));
+        SB_TRY(packB.alloc(size_t(NBUF) * nt * pb_bytes));
     }
-    auto pkA = [&](int64_t i, int64_t k) { return packA.as<unsigned char>() + ((k & 1) * nt + i) * pa_bytes; };
-    auto pkB = [&](int64_t i, int64_t k) { return packB.as<unsigned char>() + ((k & 1) * nt + i) * pb_bytes; };
+    auto pkA = [&](int64_t i, int64_t k) { return packA.as<unsigned char>() + ((k % NBUF) * nt + i) * pa_bytes; };
+    auto pkB = [&](int64_t i, int64_t k) { return packB.as<unsigned char>() + ((k % NBUF) * nt + i) * pb_bytes; };
 
     // ---- plan: every pointer batch of every step
     struct Step {
-        std::vector<Batch> la, tr;           // lookahead column k+1 / trailing columns >= k+2 (inside the chunk of k)
+        std::vector<Batch> diag;             // tile (k+1, k+1) alone (chain stream)
+        std::vector<std::vector<Batch>> la;  // la[d-1]: column k+d, d = 1 .. L (column k+1 without its diagonal tile)
+        std::vector<Batch> tr;               // columns > k+L (inside the chunk of k)
         std::vector<std::vector<Batch>> catchup;    // streaming input: this step's update of the columns of each later chunk
         std::vector<T*> panel;               // local tiles (i,k), i > k, full height
         std::vector<T*> panel_last;          // ragged last block row
@@ -197,10 +213,13 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
         const int kw = int(A.tile_nb(k));
         std::vector<char> needA(nt, 0), needB(nt, 0);
         s.catchup.resize(nchunk);
+        s.la.resize(L);
         for (int64_t j = k + 1; j < nt; ++j)
             for (int64_t i = j; i < nt; ++i) {
                 if (! A.is_local(i, j)) continue;
-                auto& dst = (chunk_of[j] > chunk_of[k]) ? s.catchup[chunk_of[j]] : (j == k + 1) ? s.la : s.tr;
+                auto& dst = (chunk_of[j] > chunk_of[k]) ? s.catchup[chunk_of[j]]
+                          : (j == k + 1 && i == j) ? s.diag
+                          : (j - k <= L) ? s.la[size_t(j - k - 1)] : s.tr;
                 const void* a = use_tc05 ? static_cast<const void*>(pkA(i, k)) : pbuf(i, k);
                 const void* b = use_tc05 ? static_cast<const void*>(pkB(j, k)) : pbuf(j, k);
                 batch_add(dst, int(A.tile_mb(i)), int(A.tile_nb(j)), kw, i == j ? 1 : 0, a, b, A.tile_as<T>(i, j));
@@ -216,7 +235,8 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
                 if (needA[i]) { s.pkA_src.push_back(pbuf(i, k)); s.pkA_dst.push_back(pkA(i, k)); if (A.tile_mb(i) == nb) ++s.pkA_full; }
                 if (needB[i]) { s.pkB_src.push_back(pbuf(i, k)); s.pkB_dst.push_back(pkB(i, k)); if (A.tile_mb(i) == nb) ++s.pkB_full; }
             }
-        pb.reserve(s.la);
+        pb.reserve(s.diag);
+        for (auto& b : s.la) pb.reserve(b);
         pb.reserve(s.tr);
         for (auto& cu : s.catchup) pb.reserve(cu);
         s.panel_off = pb.push(s.panel);
@@ -227,7 +247,7 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
 
     Streams st;
     PhaseTimer ph;
-    SB_TRY(st.init(size_t(2 * nt + 2 * nchunk)));
+    SB_TRY(st.init(size_t((2 + L) * nt + 2 * nchunk)));
     // optional: every block column is copied to the caller's packed host buffer (pool order, as to_host_local) as soon
     // as it is final (after P_done(k)), on a copy stream, overlapping the rest of the factorisation
     cudaStream_t copy = nullptr;
@@ -237,8 +257,9 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
     int64_t trail_launches = 0;
     auto P_done = [&](int64_t k) { return st.ev[k]; };
     auto T_done = [&](int64_t k) { return st.ev[nt + k]; };
-    auto H_in   = [&](int c) { return st.ev[2 * nt + c]; };              // chunk c has arrived from the host
-    auto C_done = [&](int c) { return st.ev[2 * nt + nchunk + c]; };     // chunk c carries every earlier step's update
+    auto LA_done = [&](int64_t k, int d) { return st.ev[2 * nt + k * L + (d - 1)]; };    // column k+d carries panel k's update
+    auto H_in   = [&](int c) { return st.ev[(2 + L) * nt + c]; };              // chunk c has arrived from the host
+    auto C_done = [&](int c) { return st.ev[(2 + L) * nt + nchunk + c]; };     // chunk c carries every earlier step's update
     cudaStream_t copy_in = nullptr;
     struct CopyGuard2 { cudaStream_t& s; ~CopyGuard2() { if (s) cudaStreamDestroy(s); } } copy_in_guard{copy_in};
     if (stream_in) CUDA_TRY(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
@@ -264,6 +285,15 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
             if (use_tc05) return launch_batches_tc05(bs, pb, -1.0f, 1.0f, ld, s);
         }
         return launch_batches<T>(bs, pb, 'N', opH, minus_one, one, ld, 1, s);
+    };
+    auto timed_update = [&](const std::vector<Batch>& bs, cudaStream_t s) -> int {      // counted in the roofline numbers
+        if (bs.empty()) return SB200_OK;
+        SB_TRY(st.time_begin(s));
+        SB_TRY(update(bs, s));
+        SB_TRY(st.time_end(s));
+        trail_flops += batches_flops(bs, IsComplex<T>::value);
+        trail_launches += int64_t(bs.size());
+        return SB200_OK;
     };
     // split-pack the factored panel of step k for the tensor cores (both operand roles)
     auto pack_panel = [&](Step& s, int kw, cudaStream_t P) -> int {
@@ -295,7 +325,7 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
         const int kw = int(A.tile_nb(k));
         const int owner = g.rank_of(k, k);
         const bool in_col = (g.pcol == int(k % g.q));
-        cudaStream_t P = st.panel, T_ = st.trail;
+        cudaStream_t P = st.panel, LA_ = st.look, T_ = st.trail;
 
         // -- streaming input: first step of a chunk -- wait for its arrival, then bring it up to date
         if (stream_in && k == cb[chunk_of[k]]) {
@@ -304,28 +334,23 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
             CUDA_TRY(cudaStreamWaitEvent(P, H_in(c), 0));
             if (c > 0) {
                 CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k - 1), 0));          // every panel < k is final
-                for (int64_t kk = 0; kk < k; ++kk) {
-                    const auto& cu = steps[kk].catchup[c];
-                    if (cu.empty()) continue;
-                    SB_TRY(st.time_begin(T_));
-                    SB_TRY(update(cu, T_));
-                    SB_TRY(st.time_end(T_));
-                    trail_flops += batches_flops(cu, IsComplex<T>::value);
-                    trail_launches += int64_t(cu.size());
-                }
+                for (int64_t kk = 0; kk < k; ++kk) SB_TRY(timed_update(steps[kk].catchup[c], T_));
                 CUDA_TRY(cudaEventRecord(C_done(c), T_));
                 CUDA_TRY(cudaStreamWaitEvent(P, C_done(c), 0));
+                CUDA_TRY(cudaStreamWaitEvent(LA_, C_done(c), 0));
             }
         }
-        // -- lookahead update of column k by panel k-1 (after every older trailing update)
-        if (k >= 1 && ! (stream_in && steps[k - 1].la.empty())) {     // (streaming: the first column of a chunk was updated by the catch-up)
-            if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));
-            ph.begin("la_update", P);
-            SB_TRY(update(steps[k - 1].la, P));
+        SB_TRY(st.ptime(P));
+        // -- chain: diagonal tile (k,k) <- panel k-1, first and alone.  Its earlier updates: panels <= k-1-L on the
+        //    trailing stream, panels k-L .. k-2 on the lookahead stream (the last of them is LA(k-2, 2))
+        if (k >= 1 && ! steps[k - 1].diag.empty()) {
+            if (k - 1 - L >= 0) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 1 - L), 0));
+            if (L >= 2 && k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, LA_done(k - 2, 2), 0));
+            ph.begin("diag_update", P);
+            SB_TRY(update(steps[k - 1].diag, P));
             ph.end(P);
         }
         // -- diagonal tile
-        SB_TRY(st.ptime(P));
         const T* Lkk = nullptr;
         ph.begin("potrf_tile", P);
         if (g.rank == owner)
@@ -342,7 +367,8 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
                 else if (in_col) Lkk = A.tile_as<T>(k, k);
             }
             else Lkk = A.tile_as<T>(k, k);
-            // -- panel solve A(i,k) <- A(i,k) L_kk^{-H}
+            // -- panel solve A(i,k) <- A(i,k) L_kk^{-H}: the rest of column k must carry panel k-1's update
+            if (k >= 1) CUDA_TRY(cudaStreamWaitEvent(P, LA_done(k - 1, 1), 0));
             ph.begin("panel_trsm", P);
             if (in_col) {
                 if (! s.panel.empty())
@@ -353,15 +379,16 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
                                             pb.at<T>(s.panel_last_off), 0, ld, int(s.panel_last.size()), W_trsm, P));
             }
             ph.end(P);
+            // -- ring slot k % NBUF is free once every reader of panel k-NBUF is done
+            if ((multi || use_tc05) && k >= NBUF) {
+                CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - NBUF), 0));
+                CUDA_TRY(cudaStreamWaitEvent(P, LA_done(k - NBUF, L), 0));
+            }
             // -- panel broadcast: every rank receives the whole factored block column
             ph.begin("panel_bcast", P);
-            if (multi) {
-                if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));   // ws[k&1] is free again
-                SB_TRY(bcast_block_column<T>(g, A, k, k + 1, pws, P));
-            }
+            if (multi) SB_TRY(bcast_block_column<T>(g, A, k, k + 1, pws, P));
             ph.end(P);
             if (use_tc05) {
-                if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(P, T_done(k - 2), 0));   // pack[k&1] is free again
                 ph.begin("panel_pack", P);
                 SB_TRY(pack_panel(s, kw, P));
                 ph.end(P);
@@ -377,22 +404,29 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
                 CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(host_out) + o, reinterpret_cast<char*>(A.pool) + o, bytes,
                                          cudaMemcpyDeviceToHost, copy));
         }
-        // -- trailing update of columns >= k+2
-        CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
-        if (! s.tr.empty()) {
-            SB_TRY(st.time_begin(T_));
-            SB_TRY(update(s.tr, T_));
-            SB_TRY(st.time_end(T_));
-            trail_flops += batches_flops(s.tr, IsComplex<T>::value);
-            trail_launches += int64_t(s.tr.size());
+        // -- lookahead columns k+1 .. k+L by panel k (column k+L was last touched by the trailing update of step k-1)
+        CUDA_TRY(cudaStreamWaitEvent(LA_, P_done(k), 0));
+        for (int d = 1; d <= L; ++d) {
+            if (d == L && k >= 1) CUDA_TRY(cudaStreamWaitEvent(LA_, T_done(k - 1), 0));
+            if (! s.la[size_t(d - 1)].empty()) {
+                ph.begin("la_update", LA_);
+                SB_TRY(timed_update(s.la[size_t(d - 1)], LA_));
+                ph.end(LA_);
+            }
+            CUDA_TRY(cudaEventRecord(LA_done(k, d), LA_));
         }
+        // -- trailing update of columns > k+L
+        CUDA_TRY(cudaStreamWaitEvent(T_, P_done(k), 0));
+        SB_TRY(timed_update(s.tr, T_));
         CUDA_TRY(cudaEventRecord(T_done(k), T_));
     }
     CUDA_TRY(cudaStreamWaitEvent(st.panel, T_done(nt - 1), 0));
+    CUDA_TRY(cudaStreamWaitEvent(st.panel, LA_done(nt - 1, L), 0));
     CUDA_TRY(cudaEventRecord(st.t1, st.panel));
     int hinfo = 0;
     CUDA_TRY(cudaMemcpyAsync(&hinfo, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st.panel));
     CUDA_TRY(cudaStreamSynchronize(st.panel));
+    CUDA_TRY(cudaStreamSynchronize(st.look));
     CUDA_TRY(cudaStreamSynchronize(st.trail));
     if (copy) CUDA_TRY(cudaStreamSynchronize(copy));
     float ms = 0;
@@ -818,7 +852,7 @@ int sym_rank_update_driver(T alpha, Matrix& A, Matrix* B, T beta, Matrix& C)
 }
 
 #define SB200_INST_DRIVERS(T) \
-    template int potrf_driver<T>(Matrix&, int64_t*, bool, void*, const void*); \
+    template int potrf_driver<T>(Matrix&, int64_t*, bool, void*, const void*, int); \
     template int gemm_driver<T>(T, Matrix&, Matrix&, T, Matrix&); \
     template int herk_driver<T>(RealOf<T>::type, Matrix&, RealOf<T>::type, Matrix&); \
     template int her2k_driver<T>(T, Matrix&, Matrix&, RealOf<T>::type, Matrix&); \
@@ -1119,23 +1153,23 @@ int sb200_matrix_create_##X(sb200_grid_t gh, int kind, int layout, int64_t m, in
 } \
 int sb200_potrf_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) \
 { \
-    SB_TRY(options_status(opts));\
+    SB_TRY(options_status(opts, MAX_LOOKAHEAD)); \
     if (! h) return SB200_EINVAL; \
-    return potrf_driver<CuT<T>::type>(h->A, info, false, nullptr, nullptr); \
+    return potrf_driver<CuT<T>::type>(h->A, info, false, nullptr, nullptr, opts ? int(opts->lookahead) : 0); \
 } \
 /* potrf whose result streams to the packed host buffer (sb200_matrix_to_host_local order) while it factors */ \
 int sb200_potrf_to_host_local_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info, void* htiles) \
 { \
-    SB_TRY(options_status(opts));\
+    SB_TRY(options_status(opts, MAX_LOOKAHEAD)); \
     if (! h || ! htiles) return SB200_EINVAL; \
-    return potrf_driver<CuT<T>::type>(h->A, info, false, htiles, nullptr); \
+    return potrf_driver<CuT<T>::type>(h->A, info, false, htiles, nullptr, opts ? int(opts->lookahead) : 0); \
 } \
 /* potrf whose INPUT also streams from a packed host buffer (chunks of block columns) while it factors; one rank */ \
 int sb200_potrf_stream_##X(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info, const void* htiles_in, void* htiles_out) \
 { \
-    SB_TRY(options_status(opts));\
+    SB_TRY(options_status(opts, MAX_LOOKAHEAD)); \
     if (! h || ! htiles_in) return SB200_EINVAL; \
-    return potrf_driver<CuT<T>::type>(h->A, info, false, htiles_out, htiles_in); \
+    return potrf_driver<CuT<T>::type>(h->A, info, false, htiles_out, htiles_in, opts ? int(opts->lookahead) : 0); \
 } \
 int sb200_gemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, \
                    const sb200_options_t* opts) \
@@ -1174,9 +1208,9 @@ SB200_FOR_TYPES(SB200_DEF_RUNTIME)
  * the low-precision factorisation of posv_mixed (src/posv_mixed.cc:171-176) */
 int sb200_potrf_tc05_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info)
 {
-    SB_TRY(options_status(opts));
+    SB_TRY(options_status(opts, MAX_LOOKAHEAD));
     if (! h) return SB200_EINVAL;
-    return potrf_driver<float>(h->A, info, true, nullptr, nullptr);
+    return potrf_driver<float>(h->A, info, true, nullptr, nullptr, opts ? int(opts->lookahead) : 0);
 }
 
 } // extern "C"

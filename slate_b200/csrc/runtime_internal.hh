@@ -152,7 +152,7 @@ inline double batches_flops(const std::vector<Batch>& bs, bool complex_)
 }
 
 struct Streams {
-    cudaStream_t panel = nullptr, trail = nullptr;
+    cudaStream_t panel = nullptr, look = nullptr, trail = nullptr;     // chain (highest priority) | lookahead columns | trailing update
     std::vector<cudaEvent_t> ev;
     std::vector<cudaEvent_t> tev;          // timing event pairs around the trailing-update launches
     std::vector<cudaEvent_t> pev;          // timing event pairs around the panel work of every step
@@ -184,6 +184,7 @@ struct Streams {
         int lo, hi;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&panel, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&look, cudaStreamNonBlocking, hi < lo - 1 ? hi + 1 : hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&trail, cudaStreamNonBlocking, lo));
         ev.resize(nevents);
         for (auto& e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -199,6 +200,7 @@ struct Streams {
         if (t0) cudaEventDestroy(t0);
         if (t1) cudaEventDestroy(t1);
         if (panel) cudaStreamDestroy(panel);
+        if (look) cudaStreamDestroy(look);
         if (trail) cudaStreamDestroy(trail);
     }
 };
@@ -211,8 +213,10 @@ struct DevBuf {
 };
 
 // drivers (runtime.cu)
+// lookahead <= 0: the library default (SB200_LOOKAHEAD or POTRF_DEFAULT_LOOKAHEAD)
+constexpr int POTRF_DEFAULT_LOOKAHEAD = 2, MAX_LOOKAHEAD = 8;
 template <typename T> int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out = nullptr,
-                                        const void* host_in = nullptr);
+                                        const void* host_in = nullptr, int lookahead = 0);
 template <typename T> int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C);
 template <typename T> int herk_driver(typename RealOf<T>::type alpha, Matrix& A, typename RealOf<T>::type beta, Matrix& C);
 int matrix_alloc(Grid& g, int dtype, int kind, int64_t m, int64_t n, int64_t nb, Matrix& A);
@@ -225,15 +229,18 @@ int solve_mixed_dist_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B
 } // namespace sb200
 
 // Driver options (include/slate_b200.h sb200_options_t; reference: slate::Option::{Lookahead, InnerBlocking, PivotThreshold},
-// src/potrf.cc:41-42, src/getrf.cc:38-43).  The runtime's pipelines have a fixed depth (lookahead 1) and the LU panel
-// always takes the largest candidate (threshold 1.0): anything else is REJECTED, never silently ignored.
+// src/potrf.cc:41-42, src/getrf.cc:38-43).  potrf honours Lookahead 1 .. MAX_LOOKAHEAD (depth of its lookahead stream); the
+// other pipelines have a fixed depth of 1 and the LU panel always takes the largest candidate (threshold 1.0):
+// anything else is REJECTED, never silently ignored.
 // InnerBlocking only re-associates the panel's rank-ib updates in the reference (no effect on the pivot rule); the GPU
 // panel has its own fixed blocking, so any positive value is accepted as the hint it is.
-inline int options_status(const sb200_options_t* o)
+inline int options_status(const sb200_options_t* o, int max_lookahead = 1)
 {
     if (! o) return SB200_OK;
     if (o->lookahead < 0 || o->inner_blocking < 1 || ! (o->pivot_threshold >= 0.0 && o->pivot_threshold <= 1.0)) return SB200_EINVAL;
-    if (o->lookahead != 1 || o->pivot_threshold != 1.0) return SB200_ENOTSUP;
+    // lookahead 0 = the library's own depth (the result does not depend on the depth; only the overlap does)
+    if (o->lookahead > max_lookahead || o->pivot_threshold != 1.0) return SB200_ENOTSUP;
+    if (max_lookahead == 1 && o->lookahead > 1) return SB200_ENOTSUP;
     return SB200_OK;
 }
 

@@ -94,6 +94,8 @@ def _stream():
 
 
 def _opts(opts):
+    """sb200_options_t for the caller's dict; keys the caller does not give take the reference's defaults, except
+    `lookahead` of potrf, where 0 = the library's tuned depth (see _potrf_opts)."""
     o = _Options()
     o.lookahead = int((opts or {}).get("lookahead", 1))
     o.inner_blocking = int((opts or {}).get("inner_blocking", 16))
@@ -439,6 +441,8 @@ def potrf(A: HermitianMatrix, opts: dict | None = None, out_local=None, in_local
     opts['tensor_core_fp32'] (float matrices only): run the trailing update on the tcgen05
     FP32-emulated kernel, as posv_mixed does for its low-precision factorisation."""
     o = _opts(opts)
+    if "lookahead" not in (opts or {}):
+        o.lookahead = 0                     # the library's tuned depth (csrc/runtime_internal.hh POTRF_DEFAULT_LOOKAHEAD)
     info = c_i64(0)
     key = A.t
     if (opts or {}).get("tensor_core_fp32"):
