@@ -358,6 +358,11 @@ int sb200_last_driver_stats(sb200_matrix_t A, double* out4);
  * kind 0 = DMMA.8x8x4, 1 = DFMA; launches ctas_per_sm x SMs CTAs; *flops = work of the launch. */
 int sb200_fp64_peak_probe(int kind, int iters, int ctas_per_sm, double* d_scratch, double* flops,
                           sb200_stream_t stream);
+/* SM partition of the factorisation drivers (csrc/sm_partition.cu): with SB200_CHAIN_SMS = c > 0 (default: 4 on a
+ * multi-rank grid, 0 on one rank) the panel chain -- the diagonal-tile factor the reference runs through
+ * cusolverDn?potrf (src/internal/internal_potrf.cc:57-81) -- gets c whole SMs of its own (CUDA green context) and
+ * every other stream the remaining ones.  Reports the split the device grants; SB200_ENOTSUP if it cannot. */
+int sb200_sm_partition_probe(int chain_sms, int* sm_chain, int* sm_rest);
 
 /* ---------------------------------------------------------------------------
  * Round-1 widening of the host runtime: all four scalar types, herk, the solve path and the

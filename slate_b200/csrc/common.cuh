@@ -34,6 +34,7 @@ constexpr Switch SW_DIAG_MW      {"SB200_DIAG_MW", 0};        // multi-warp 64 x
 constexpr Switch SW_TILE_FUSED   {"SB200_TILE_FUSED", 0};     // one-launch tile Cholesky: 1 | 2 (rsqrt)
 constexpr Switch SW_TRSM_FUSED   {"SB200_TRSM_FUSED", 7};     // bit 0 panel solve, bit 1 row solve, bit 2 small-triangle (<= 32) solve: measured r2a, on
 constexpr Switch SW_PANEL_LL     {"SB200_PANEL_LL", 0};       // LU base kernel with tagged-word exchange
+constexpr Switch SW_PANEL_V3     {"SB200_PANEL_V3", 1};       // LU base kernel with one exchange round per column (getrf_base_v3.cu)
 constexpr Switch SW_PANEL_SKINNY {"SB200_PANEL_SKINNY", 0};   // one-launch skinny update inside the LU panel
 constexpr Switch SW_GEMM_BT      {"SB200_GEMM_BT", 1};        // transposed B panel / U row: 'N','T' multiply (measured r2a: dgemm 30.5 -> 35.3 TF/s), on
 inline int switch_value(const Switch& s)

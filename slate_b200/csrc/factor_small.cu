@@ -690,13 +690,15 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
 
 // lower Cholesky of one n x n tile, blocked by IB; W >= IB*IB elements
 template <typename T>
-int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cudaStream_t stream)
+int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cudaStream_t stream, int fused_dflt)
 {
     int st;
     if constexpr (IsRealType<T>::value) {
-        // opt-in (round-2 candidate, not yet run): the whole tile in one launch (potrf_tile_fused.cu); read per call
-        // so that a test can switch it
-        const int fused = switch_value(SW_TILE_FUSED);
+        // the whole tile in one launch (potrf_tile_fused.cu): 0.67 ms against 0.57 ms for the launch chain below on an
+        // idle device, but 0.69 ms against 1.1 ms on the chain's own SM partition (fused_dflt = 1 from the driver,
+        // profiles/r02d_greenctx_chain_partition.jsonl); the environment switch overrides, read per call
+        const char* fe = getenv(SW_TILE_FUSED.env);
+        const int fused = fe ? atoi(fe) : (fused_dflt >= 0 ? fused_dflt : SW_TILE_FUSED.dflt);
         if (fused > 0 && n > IB) {
             if constexpr (std::is_same<T, double>::value) st = potrf_tile_fused_d(n, A, lda, dinfo, info_base, fused, stream);
             else                                          st = potrf_tile_fused_s(n, A, lda, dinfo, info_base, fused, stream);
@@ -918,7 +920,7 @@ SB200_INST_SMALL(cuDoubleComplex)
 // the drivers (runtime.cu, solve.cu, getrf.cu) use these for every scalar type
 #define SB200_INST_FACTOR(T) \
     template int trsm_colmajor<T>(bool, bool, int, bool, int, int, T, const T*, int, T* const*, int64_t, int, int, T*, cudaStream_t); \
-    template int potrf_tile_lower<T>(int, T*, int, int*, int, T*, cudaStream_t);
+    template int potrf_tile_lower<T>(int, T*, int, int*, int, T*, cudaStream_t, int);
 SB200_INST_FACTOR(float)
 SB200_INST_FACTOR(double)
 SB200_INST_FACTOR(cuFloatComplex)
@@ -933,7 +935,7 @@ int trsm_colmajor_d(bool left, bool lower, int op, bool unit, int m, int n, doub
 }
 int potrf_tile_lower_d(int n, double* A, int lda, int* dinfo, int info_base, double* W, cudaStream_t stream)
 {
-    return potrf_tile_lower<double>(n, A, lda, dinfo, info_base, W, stream);
+    return potrf_tile_lower<double>(n, A, lda, dinfo, info_base, W, stream, -1);
 }
 
 template <typename T>
@@ -979,7 +981,7 @@ static int potrf_tile_t(int uplo, int64_t n, T* dA, int64_t lda, int* dinfo, voi
         W = static_cast<T*>(device_scratch(size_t(IB) * IB * sizeof(T)));
         if (! W) return SB200_ENOMEM;
     }
-    return potrf_tile_lower<T>(int(n), dA, int(lda), dinfo, 0, W, stream);
+    return potrf_tile_lower<T>(int(n), dA, int(lda), dinfo, 0, W, stream, -1);
 }
 
 template <typename A> struct Cu { using type = A; };

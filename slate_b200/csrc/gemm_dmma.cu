@@ -29,15 +29,9 @@ static int launch_variant(const GemmParamsD& p, cudaStream_t stream)
     return launch_status();
 }
 
-int launch_gemm_d_persist(int opA, int opB, const GemmParamsD& p, cudaStream_t stream);     // gemm_dmma_persist.cu
-
 int launch_gemm_d(int opA, int opB, GemmParamsD p, cudaStream_t stream)
 {
     if (p.m <= 0 || p.n <= 0 || p.batch <= 0) return SB200_OK;
-    {
-        const int st = launch_gemm_d_persist(opA, opB, p, stream);      // opt-in (SB200_GEMM_PERSIST)
-        if (st != -1000000) return st;                                  // PERSIST_NOT_TAKEN
-    }
     const bool ak = (opA != 'N');     // op(A) = A^T: k contiguous
     const bool bk = (opB == 'N');     // op(B) = B  : k contiguous
     static const int cfg_sel = [] { const char* e = getenv("SB200_GEMM_CFG"); return e ? atoi(e) : 0; }();

@@ -504,7 +504,8 @@ int PanelScratch::init()
     max_ctas = sms;
     const size_t G = size_t(sms);
     ll_bytes = (2 * G * 4 + 2 * G * PW * 2 + 2 * PW * 2) * sizeof(unsigned long long);
-    const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8 + 64 + ll_bytes;
+    const size_t v3_bytes = base_v3_scratch_bytes(sms);
+    const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8 + 64 + ll_bytes + 16 + v3_bytes;
     CUDA_TRY(cudaMalloc(&raw, bytes));
     char* p = static_cast<char*>(raw);
     gval = reinterpret_cast<double*>(p); p += 2 * G * 8;
@@ -513,10 +514,18 @@ int PanelScratch::init()
     gdiag = reinterpret_cast<double*>(p); p += 2 * PW * 8;
     W = reinterpret_cast<double*>(p); p += 16 * 64 * 64 * 8;
     bar = reinterpret_cast<unsigned*>(p); p += 64;
-    ll = reinterpret_cast<unsigned long long*>(p);
+    ll = reinterpret_cast<unsigned long long*>(p); p += ll_bytes;
+    p = static_cast<char*>(raw) + (size_t(p - static_cast<char*>(raw)) + 15) / 16 * 16;      // 16-byte vector accesses
+    v3_buf = reinterpret_cast<unsigned long long*>(p);
     { const char* e = getenv("SB200_PANEL_BARRIER"); use_bar = e && atoi(e) != 0; }
     use_ll = switch_value(SW_PANEL_LL) != 0;
     nopiv = g_getrf_nopiv;
+    use_v3 = ! nopiv && ! use_ll && ! use_bar && switch_value(SW_PANEL_V3) != 0;
+    if (use_v3) {
+        CUDA_TRY(cudaMemset(v3_buf, 0, v3_bytes));             // tag 0 is never used by a launch
+        SB_TRY(base_v3_init());
+    }
+    v3_gen = 0;
     if (use_ll) CUDA_TRY(cudaMemset(ll, 0, ll_bytes));          // tag 0 is never used by a launch
     gen_base = 0;
     static thread_local bool attr_done[64] = {};
@@ -591,6 +600,13 @@ struct PanelCtx {
 template <typename T>
 static int panel_base_wide(const PanelCtx<T>& x, int c0, int w)
 {
+    if (x.ps->use_v3) {
+        x.pt->begin("pnl_base", x.s);
+        SB_TRY(launch_base_v3<T>(x.stack, x.nb, x.m_p, c0, w, x.kw, x.piv_tile, x.piv_off, x.dinfo, x.info_base,
+                                 x.rowmap, *x.ps, x.s));
+        x.pt->end(x.s);
+        return SB200_OK;
+    }
     const int active = x.m_p - c0;
     const int ctas = x.ps->max_ctas - 1;                       // one SM is kept for the interchange CTA
     int rows_per = std::max(int(ceil_div(active, ctas)), std::min(active, PROWS_MAX));

@@ -7,6 +7,7 @@ namespace sb200 {
 constexpr int PW = 32;            // panel base-block width (the tester's ib 32)
 constexpr int PROWS_MAX = 768;    // rows of the block one CTA keeps in shared memory
 constexpr int PTHREADS = 256;
+constexpr int V3_NWIDE = 4;       // interchange CTAs of the one-round base kernel (getrf_base_v3.cu)
 
 // scratch of the cooperative panel kernel (per driver call)
 struct PanelScratch {
@@ -18,6 +19,9 @@ struct PanelScratch {
     unsigned gen_base = 0;              // generation tag of the next launch's first column, minus 1
     bool use_ll = false;
     bool nopiv = false;                 // getrf_nopiv: base kernel without the pivot search
+    unsigned long long* v3_buf = nullptr;   // per-column exchange records of getrf_base_v3_kernel (getrf_base_v3.cu)
+    unsigned v3_gen = 0;
+    bool use_v3 = false;
     size_t ll_bytes = 0;
     int max_ctas = 0;
     void* raw = nullptr;
@@ -45,6 +49,13 @@ int getrf_panel(T* const* stack, T* tile0, int ntile, int nb, int m_p, int kw,
                 PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph);
 int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out);                      // FP64, any grid
 int getrf_driver_s(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_tc05);     // FP32, 1 x 1 grid
+
+// one-round base block (getrf_base_v3.cu)
+size_t base_v3_scratch_bytes(int max_ctas);
+int base_v3_init();
+template <typename T>
+int launch_base_v3(T* const* stack, int nb, int m_p, int c0, int w, int kw, int64_t* piv_tile, int64_t* piv_off,
+                   int* dinfo, int info_base, int* rowmap, PanelScratch& ps, cudaStream_t s);
 
 // fused row interchanges of one panel over a block-column range (getrf.cu)
 template <typename T>

@@ -247,7 +247,12 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
 
     Streams st;
     PhaseTimer ph;
-    SB_TRY(st.init(size_t((2 + L) * nt + 2 * nchunk)));
+    // the diagonal-tile factor runs on its own few SMs when the chain is what bounds the step (multi-rank grids: the
+    // trailing update shrinks with 1 / (p q), the chain does not); on one rank the trailing update is 7x the chain
+    // and keeps all 148 SMs.  SB200_CHAIN_SMS overrides (0 = priority streams only).
+    const int chain_sms = [&] { const char* e = getenv("SB200_CHAIN_SMS"); return e ? atoi(e) : (multi ? 4 : 0); }();
+    SB_TRY(st.init(size_t((2 + L) * nt + 2 * nchunk), chain_sms));
+    const int tile_fused_dflt = st.own_chain ? 1 : -1;
     // optional: every block column is copied to the caller's packed host buffer (pool order, as to_host_local) as soon
     // as it is final (after P_done(k)), on a copy stream, overlapping the rest of the factorisation
     cudaStream_t copy = nullptr;
@@ -352,10 +357,13 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
         }
         // -- diagonal tile
         const T* Lkk = nullptr;
-        ph.begin("potrf_tile", P);
-        if (g.rank == owner)
-            SB_TRY(potrf_tile_lower<T>(kw, A.tile_as<T>(k, k), ld, dinfo.as<int>(), int(k * nb), W_potrf, P));
-        ph.end(P);
+        if (g.rank == owner) {
+            SB_TRY(st.hop(P, st.chain));
+            ph.begin("potrf_tile", st.chain);
+            SB_TRY(potrf_tile_lower<T>(kw, A.tile_as<T>(k, k), ld, dinfo.as<int>(), int(k * nb), W_potrf, st.chain, tile_fused_dflt));
+            ph.end(st.chain);
+            SB_TRY(st.hop(st.chain, P));
+        }
         if (k + 1 < nt) {
             if (multi) {
                 T* db = dbuf.as<T>() + (k & 1) * te;

@@ -2,6 +2,7 @@
 // status macros, per-step pointer batches ("device regions"), the once-per-call plan buffer,
 // the two-stream/event scaffold, and the type-generic tile factor/solve entry points.
 #pragma once
+#include <cuda_profiler_api.h>
 #include "runtime.hh"
 #include "gemm_dmma.cuh"
 #include "scalar_ops.cuh"
@@ -23,7 +24,7 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
                   const T* Tm, int ldt, T* const* dB, int64_t offB, int ldb, int batch,
                   T* W, cudaStream_t stream);
 template <typename T>
-int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cudaStream_t stream);
+int potrf_tile_lower(int n, T* A, int lda, int* dinfo, int info_base, T* W, cudaStream_t stream, int fused_dflt = -1);
 // small-nrhs solve path (factor_small.cu): inverted diagonal blocks of all diagonal tiles in one launch, and the
 // one-CTA-per-8-columns tile solve; trsm_small returns SB200_ENOTSUP for cases it does not serve
 template <typename T>
@@ -153,6 +154,11 @@ inline double batches_flops(const std::vector<Batch>& bs, bool complex_)
 
 struct Streams {
     cudaStream_t panel = nullptr, look = nullptr, trail = nullptr;     // chain (highest priority) | lookahead columns | trailing update
+    cudaStream_t chain = nullptr;          // == panel, or a stream on its own SM partition (init with chain_sms > 0)
+    bool own_chain = false;
+    int chain_sm_count = 0;
+    cudaEvent_t hop_ev[2] = {nullptr, nullptr};
+    int hop_next = 0;
     std::vector<cudaEvent_t> ev;
     std::vector<cudaEvent_t> tev;          // timing event pairs around the trailing-update launches
     std::vector<cudaEvent_t> pev;          // timing event pairs around the panel work of every step
@@ -175,23 +181,25 @@ struct Streams {
         return SB200_OK;
     }
     int ptime(cudaStream_t s) { return stamp(pev, s); }
-    int time_begin(cudaStream_t s) { return stamp(tev, s); }
-    int time_end(cudaStream_t s) { return stamp(tev, s); }
+    // SB200_NCU_TIMED=i: the timed (trailing-update) launch groups i .. i+3 of a driver call sit inside a
+    // cudaProfilerStart/Stop window, so that `ncu --profile-from-start off` captures exactly the kernels the
+    // roofline is quoted on and not the small launches of the panel chain that share their name.
+    int ncu_pick = -2, ncu_seen = 0;
+    int time_begin(cudaStream_t s)
+    {
+        if (ncu_pick == -2) { const char* e = getenv("SB200_NCU_TIMED"); ncu_pick = e ? atoi(e) : -1; }
+        if (ncu_pick >= 0 && ncu_seen == ncu_pick) cudaProfilerStart();
+        return stamp(tev, s);
+    }
+    int time_end(cudaStream_t s)
+    {
+        if (ncu_pick >= 0 && ++ncu_seen == ncu_pick + 4) cudaProfilerStop();
+        return stamp(tev, s);
+    }
     double panel_ms() { return sum_pairs(pev); }
     double timed_ms() { return sum_pairs(tev); }
-    int init(size_t nevents)
-    {
-        int lo, hi;
-        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&panel, cudaStreamNonBlocking, hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&look, cudaStreamNonBlocking, hi < lo - 1 ? hi + 1 : hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&trail, cudaStreamNonBlocking, lo));
-        ev.resize(nevents);
-        for (auto& e : ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreate(&t0));
-        CUDA_TRY(cudaEventCreate(&t1));
-        return SB200_OK;
-    }
+    int init(size_t nevents, int chain_sms = 0);          // sm_partition.cu
+    int hop(cudaStream_t from, cudaStream_t to);          // event edge from -> to (no-op when they are the same stream)
     ~Streams()
     {
         for (auto e : ev) if (e) cudaEventDestroy(e);
@@ -199,6 +207,8 @@ struct Streams {
         for (auto e : pev) if (e) cudaEventDestroy(e);
         if (t0) cudaEventDestroy(t0);
         if (t1) cudaEventDestroy(t1);
+        for (auto e : hop_ev) if (e) cudaEventDestroy(e);
+        if (own_chain && chain) cudaStreamDestroy(chain);
         if (panel) cudaStreamDestroy(panel);
         if (look) cudaStreamDestroy(look);
         if (trail) cudaStreamDestroy(trail);

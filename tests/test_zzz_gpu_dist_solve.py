@@ -1,9 +1,8 @@
 """GPU tests of the p x q solve path (slate_b200/csrc/solve_dist.cu: replicated right-hand sides) through the single-rank
 test hook SB200_DIST_SOLVE=2 (same code path as on a grid, minus the NCCL calls).
 
-The code was written after round 1's GPU budget was spent, so these tests have not run on a GPU yet: they are SKIPPED
-unless SB200_RUN_UNVALIDATED=1 (round 2: run them, fix, then drop the guard).  The multi-rank check itself lives in
-scratch/mgpu_check.py (potrs / posv_mixed on 1x2 and 2x1 grids)."""
+Validated on a B200 in round 2 (gpurun call r2b: all green; profiles/r02b_pytest_gpu_tail.txt).  The multi-rank check
+itself lives in scratch/mgpu_check.py (potrs / posv_mixed on 1x2 and 2x1 grids)."""
 import os
 
 import numpy as np
@@ -11,9 +10,7 @@ import pytest
 
 from oracle import slate_oracle as o
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SB200_RUN_UNVALIDATED") != "1",
-                                 reason="p x q solve path not yet validated on a GPU; set SB200_RUN_UNVALIDATED=1")]
+pytestmark = [pytest.mark.gpu]
 EPS = float(np.finfo(np.float64).eps)
 
 

@@ -29,8 +29,8 @@
 
 * `getrf_nopiv`: the getrf drivers with the pivot search compiled out of the base kernel.
 
-Written after round 1's GPU budget was spent: SKIPPED unless SB200_RUN_UNVALIDATED=1 (round 2: run, fix, drop the guard,
-then make the winner the default)."""
+Validated on a B200 in round 2 (gpurun call r2b: 357 passed; profiles/r02b_pytest_gpu_tail.txt); the winners are the
+defaults in csrc/common.cuh (SW_* table)."""
 import os
 
 import numpy as np
@@ -38,9 +38,7 @@ import pytest
 
 from oracle import slate_oracle as o
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SB200_RUN_UNVALIDATED") != "1",
-                                 reason="round-2 candidate not yet validated on a GPU; set SB200_RUN_UNVALIDATED=1")]
+pytestmark = [pytest.mark.gpu]
 EPS = float(np.finfo(np.float64).eps)
 
 
