@@ -26,6 +26,8 @@
 #include "getrf_internal.hh"
 #include <cfloat>
 #include <climits>
+#include <cstdio>
+#include <vector>
 
 namespace sb200 {
 
@@ -92,7 +94,9 @@ struct V3Args {
     unsigned long long* drow;                 // [PW][2 PW]     diagonal row of column j (published by CTA 0)
     unsigned long long* pivrec;               // [PW]           pivot row of column j (published by CTA 0)
     unsigned gen_base; int gmax;
+    long long* trace;                         // debug (SB200_V3_TRACE=1): [G][8] cycles per phase, thread 0 of every row CTA
 };
+#define V3_MARK(k) do { if (a.trace && tid == 0) { const long long t_ = clock64(); tr_acc[k] += t_ - tr_last; tr_last = t_; } } while (0)
 
 template <typename T>
 __global__ void __launch_bounds__(PTHREADS)
@@ -131,6 +135,7 @@ getrf_base_v3_kernel(const V3Args<T> a)
         return;
     }
 
+    long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tr_last = clock64();
     const int RP = a.rows_per | 1;
     const int r_begin = a.c0 + b * a.rows_per;
     const int r_end = min(r_begin + a.rows_per, a.m_p);
@@ -143,6 +148,7 @@ getrf_base_v3_kernel(const V3Args<T> a)
         }
     __syncthreads();
 
+    V3_MARK(0);                                     // slab load
     // candidate of the first column; later ones come out of the rank-1 update
     double best = -1.0;
     int brow = INT_MAX;
@@ -187,6 +193,7 @@ getrf_base_v3_kernel(const V3Args<T> a)
             else if (b == 0 && lane < w)
                 v3_store_double(a.drow + (size_t(j) * PW + lane) * 2, double(blk[lane * RP + (d - r_begin)]), gen);
         }
+        V3_MARK(1);                                 // candidate reduce + publish
         // ---- gather: thread c polls the header of CTA c; the last warp polls the diagonal row
         double bv = -1.0;
         int br = INT_MAX, bw = -1;
@@ -205,6 +212,7 @@ getrf_base_v3_kernel(const V3Args<T> a)
         }
         if (warp == NWARP - 1 && lane < w)
             s_drow[lane] = T(v3_wait_double(a.drow + (size_t(j) * PW + lane) * 2, gen));
+        V3_MARK(2);                                 // header poll (thread 0: the header of CTA 0)
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -227,6 +235,7 @@ getrf_base_v3_kernel(const V3Args<T> a)
         bv = __shfl_sync(0xffffffffu, bv, 0);
         br = __shfl_sync(0xffffffffu, br, 0);
         bw = __shfl_sync(0xffffffffu, bw, 0);
+        V3_MARK(3);                                 // gather reduce (waits for the slowest poller of this CTA)
         // ---- every CTA picks the same winner: strictly larger than the diagonal, or the diagonal (ties, NaN)
         const double dv = double(fabs(s_drow[j]));
         const int p = (bv > dv) ? br : d;
@@ -239,11 +248,13 @@ getrf_base_v3_kernel(const V3Args<T> a)
             v3_store(a.pivrec + j, unsigned(p), gen);
         }
         __syncthreads();
+        V3_MARK(4);                                 // winner's row
         if (p != d && tid < w) {
             if (p >= r_begin && p < r_end) blk[tid * RP + (p - r_begin)] = s_drow[tid];
             if (b == 0) blk[tid * RP + (d - r_begin)] = s_prow[tid];
         }
         __syncthreads();
+        V3_MARK(5);                                 // swap
         // ---- scale + rank-1 update of rows below the diagonal; the next column's candidate falls out of it
         const T pv = s_prow[j];
         best = -1.0; brow = INT_MAX;
@@ -280,6 +291,7 @@ getrf_base_v3_kernel(const V3Args<T> a)
                 }
             }
         }
+        V3_MARK(6);                                 // update
         // (the barrier at the top of the next column orders these writes before anybody reads them)
     }
     __syncthreads();
@@ -288,6 +300,198 @@ getrf_base_v3_kernel(const V3Args<T> a)
             const int r = r_begin + lr;
             a.tiles[r / nb][(r % nb) + int64_t(a.c0 + c) * nb] = blk[c * RP + lr];
         }
+    V3_MARK(7);                                     // slab store
+    if (a.trace && tid == 0)
+        for (int k = 0; k < 8; ++k) a.trace[b * 8 + k] = tr_acc[k];
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Register-resident variant (the default for panels of <= (#SMs - NWIDE) x 512 rows): ONE row per thread, its <= 32
+// block columns in registers, the column loop fully unrolled so that every register index is static.
+// Why (v3 phase trace, profiles/r02f_v3_phase_trace.txt): with the block in shared memory the rank-1 update of one
+// column re-reads and re-writes the whole remaining slab -- 3 700 of the 12 300 cycles per column, bound by shared-memory
+// bandwidth -- and loading / storing the slab costs another 2 300 per column; the exchange itself has a floor of
+// 1 500-1 900 cycles (profiles/r02g_allgather_floor.txt).  In registers the update is <= 31 DFMAs per thread.
+// Same protocol, same pivot rule, same arithmetic as above.
+// ------------------------------------------------------------------------------------------
+constexpr int V4_THREADS = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(V4_THREADS, 1)
+getrf_base_v4_kernel(const V3Args<T> a)
+{
+    __shared__ __align__(16) T s_prow[PW];
+    __shared__ __align__(16) T s_drow[PW];
+    constexpr int NWARP = V4_THREADS / 32;
+    __shared__ double s_val[NWARP];
+    __shared__ int    s_row[NWARP];
+    __shared__ double g_val[NWARP];
+    __shared__ int    g_row[NWARP], g_cta[NWARP];
+    const int G = a.G, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = a.nb, w = a.w;
+
+    if (b >= G) {
+        // ---- interchange CTAs: follow the pivot sequence, swap rows d and p in every panel column outside the block
+        const int wi = b - G, nw = int(gridDim.x) - G;
+        const int outside = a.kw_wide - w;
+        for (int j = 0; j < w; ++j) {
+            const int d = a.c0 + j;
+            const int p = int(v3_wait_word(a.pivrec + j, a.gen_base + unsigned(j) + 1u));
+            if (p == d) continue;
+            T* rd_ = a.tiles[d / nb] + (d % nb);
+            T* rp_ = a.tiles[p / nb] + (p % nb);
+            for (int ci = wi * V4_THREADS + tid; ci < outside; ci += nw * V4_THREADS) {
+                const int c = ci < a.c0 ? ci : ci + w;
+                const T t0 = rd_[int64_t(c) * nb], t1 = rp_[int64_t(c) * nb];
+                rd_[int64_t(c) * nb] = t1;
+                rp_[int64_t(c) * nb] = t0;
+            }
+            if (a.rowmap && wi == 0 && tid == 0) { const int t = a.rowmap[d]; a.rowmap[d] = a.rowmap[p]; a.rowmap[p] = t; }
+        }
+        return;
+    }
+
+    const int r = a.c0 + b * a.rows_per + tid;                 // this thread's panel row
+    const bool have = tid < a.rows_per && r < a.m_p;
+    T* rowp = have ? a.tiles[r / nb] + (r % nb) + int64_t(a.c0) * nb : nullptr;
+    T x[PW];
+    #pragma unroll
+    for (int c = 0; c < PW; ++c) x[c] = (have && c < w) ? rowp[int64_t(c) * nb] : T(0);
+
+    double best = (have && r > a.c0) ? double(fabs(x[0])) : -1.0;
+    int brow = (have && r > a.c0) ? r : INT_MAX;
+
+    #pragma unroll
+    for (int j = 0; j < PW; ++j) {
+        if (j < w) {
+            const int d = a.c0 + j;
+            const unsigned gen = a.gen_base + unsigned(j) + 1u;
+            unsigned long long* slot = a.rec + size_t(j) * a.gmax * V3_REC;
+            // ---- this CTA's candidate: warp, then block
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+                if (v3_better(ov, orow, best, brow)) { best = ov; brow = orow; }
+            }
+            if (lane == 0) { s_val[warp] = best; s_row[warp] = brow; }
+            __syncthreads();
+            best = lane < NWARP ? s_val[lane] : -1.0;
+            brow = lane < NWARP ? s_row[lane] : INT_MAX;
+            #pragma unroll
+            for (int o = NWARP / 2; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+                if (v3_better(ov, orow, best, brow)) { best = ov; brow = orow; }
+            }
+            best = __shfl_sync(0xffffffffu, best, 0);
+            brow = __shfl_sync(0xffffffffu, brow, 0);
+            // ---- publish: the owner of the candidate row sends header + row, the owner of row d the diagonal row
+            {
+                unsigned long long* R = slot + size_t(b) * V3_REC;
+                if (brow == INT_MAX ? tid == 0 : (have && r == brow)) {
+                    if (brow != INT_MAX) {
+                        #pragma unroll
+                        for (int c = 0; c < PW; ++c) v3_store_double(R + V3_HDR + 2 * c, double(x[c]), gen);
+                    }
+                    v3_store_double(R, best, gen);
+                    v3_store(R + 2, unsigned(brow), gen);
+                }
+                if (b == 0 && tid == j) {
+                    #pragma unroll
+                    for (int c = 0; c < PW; ++c) v3_store_double(a.drow + (size_t(j) * PW + c) * 2, double(x[c]), gen);
+                }
+            }
+            // ---- gather: thread c polls the header of CTA c; the last warp polls the diagonal row
+            double bv = -1.0;
+            int br = INT_MAX, bw = -1;
+            if (tid < G) {
+                const unsigned long long* R = slot + size_t(tid) * V3_REC;
+                unsigned long long w0, w1, w2, w3;
+                const long long t0 = clock64();
+                for (;;) {
+                    v3_load2(R, w0, w1); v3_load2(R + 2, w2, w3);
+                    if (unsigned(w0 >> 32) == gen && unsigned(w1 >> 32) == gen && unsigned(w2 >> 32) == gen) break;
+                    spin_watchdog(t0);
+                }
+                bv = __hiloint2double(int(unsigned(w1)), int(unsigned(w0)));
+                br = int(unsigned(w2));
+                bw = tid;
+            }
+            if (warp == NWARP - 1)
+                s_drow[lane] = T(v3_wait_double(a.drow + (size_t(j) * PW + lane) * 2, gen));
+            if (warp * 32 < G) {
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int orow = __shfl_xor_sync(0xffffffffu, br, o);
+                    const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                    if (v3_better(ov, orow, bv, br)) { bv = ov; br = orow; bw = ow; }
+                }
+            }
+            if (lane == 0) { g_val[warp] = bv; g_row[warp] = br; g_cta[warp] = bw; }
+            __syncthreads();
+            bv = lane < NWARP ? g_val[lane] : -1.0;
+            br = lane < NWARP ? g_row[lane] : INT_MAX;
+            bw = lane < NWARP ? g_cta[lane] : -1;
+            #pragma unroll
+            for (int o = NWARP / 2; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, br, o);
+                const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                if (v3_better(ov, orow, bv, br)) { bv = ov; br = orow; bw = ow; }
+            }
+            bv = __shfl_sync(0xffffffffu, bv, 0);
+            br = __shfl_sync(0xffffffffu, br, 0);
+            bw = __shfl_sync(0xffffffffu, bw, 0);
+            // ---- every CTA picks the same winner: strictly larger than the diagonal, or the diagonal (ties, NaN)
+            const double dv = double(fabs(s_drow[j]));
+            const int p = (bv > dv) ? br : d;
+            if (warp == 0)
+                s_prow[lane] = (p == d) ? s_drow[lane]
+                                        : T(v3_wait_double(slot + size_t(bw) * V3_REC + V3_HDR + 2 * lane, gen));
+            if (b == 0 && tid == 2 * 32) {
+                a.piv_tile[d] = p / nb;
+                a.piv_off[d] = p % nb;
+                v3_store(a.pivrec + j, unsigned(p), gen);
+            }
+            __syncthreads();
+            // ---- interchange (registers of the two owning threads), scale, rank-1 update
+            if (p != d) {
+                if (have && r == p) {
+                    #pragma unroll
+                    for (int c = 0; c < PW; ++c) x[c] = s_drow[c];
+                }
+                if (b == 0 && tid == j) {
+                    #pragma unroll
+                    for (int c = 0; c < PW; ++c) x[c] = s_prow[c];
+                }
+            }
+            const T pv = s_prow[j];
+            if (pv == T(0)) {
+                if (b == 0 && tid == 0 && *a.info == 0) *a.info = a.info_base + d + 1;
+            }
+            else if (have && r > d) {
+                const bool use_rcp = fabs(pv) >= v3_tiny<T>();
+                const T rcp = T(1) / pv;
+                const T l = use_rcp ? x[j] * rcp : x[j] / pv;
+                x[j] = l;
+                #pragma unroll
+                for (int c = j + 1; c < PW; ++c) x[c] = v3_fma(-l, s_prow[c], x[c]);
+            }
+            if (j + 1 < PW) {
+                const bool cand = have && r > d + 1;
+                best = cand ? double(fabs(x[j + 1 < PW ? j + 1 : j])) : -1.0;
+                brow = cand ? r : INT_MAX;
+            }
+        }
+    }
+    if (have) {
+        #pragma unroll
+        for (int c = 0; c < PW; ++c)
+            if (c < w) rowp[int64_t(c) * nb] = x[c];
+    }
 }
 
 } // namespace
@@ -319,7 +523,9 @@ int launch_base_v3(T* const* stack, int nb, int m_p, int c0, int w, int kw, int6
 {
     const int active = m_p - c0;
     const int ctas = ps.max_ctas - V3_NWIDE;
-    int rows_per = std::max(int(ceil_div(active, ctas)), std::min(active, PROWS_MAX));
+    static const int v4_sel = [] { const char* e = getenv("SB200_PANEL_V4"); return e ? atoi(e) : 1; }();
+    const bool v4 = v4_sel != 0 && active <= ctas * V4_THREADS;     // register-resident rows: <= 512 rows per CTA
+    int rows_per = v4 ? V4_THREADS : std::max(int(ceil_div(active, ctas)), std::min(active, PROWS_MAX));
     rows_per = std::max(rows_per, PW);
     if (rows_per > PROWS_MAX) return SB200_ENOTSUP;
     const int G = int(ceil_div(active, rows_per));
@@ -336,11 +542,28 @@ int launch_base_v3(T* const* stack, int nb, int m_p, int c0, int w, int kw, int6
     a.pivrec = a.drow + size_t(PW) * 2 * PW;
     a.gen_base = ps.v3_gen; a.gmax = ps.max_ctas;
     ps.v3_gen += unsigned(PW);
-    const size_t smem = size_t(w) * (rows_per | 1) * sizeof(T);
+    const size_t smem = v4 ? 0 : size_t(w) * (rows_per | 1) * sizeof(T);
+    static const bool trace_on = [] { const char* e = getenv("SB200_V3_TRACE"); return e && atoi(e) != 0; }();
+    long long* dtrace = nullptr;
+    if (trace_on && ! v4) { CUDA_TRY(cudaMalloc(&dtrace, size_t(G) * 8 * sizeof(long long))); a.trace = dtrace; }
     void* args[] = {&a};
-    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_v3_kernel<T>),
-                                                      dim3(G + V3_NWIDE), dim3(PTHREADS), args, smem, s);
+    const cudaError_t e = v4
+        ? cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_v4_kernel<T>), dim3(G + V3_NWIDE), dim3(V4_THREADS), args, 0, s)
+        : cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_v3_kernel<T>), dim3(G + V3_NWIDE), dim3(PTHREADS), args, smem, s);
     if (e != cudaSuccess) return int(e);
+    if (trace_on && ! v4) {
+        // debug: cycles per phase (thread 0 of the first, a middle and the last row CTA), summed over the w columns
+        std::vector<long long> h(size_t(G) * 8);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaMemcpy(h.data(), dtrace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(dtrace);
+        static int printed = 0;
+        if (printed++ < 40)
+            for (int c : {0, G / 2, G - 1})
+                fprintf(stderr, "{\"v3_trace\": 1, \"m\": %d, \"c0\": %d, \"w\": %d, \"G\": %d, \"cta\": %d, \"load\": %lld, \"cand\": %lld, "
+                        "\"poll\": %lld, \"greduce\": %lld, \"winrow\": %lld, \"swap\": %lld, \"update\": %lld, \"store\": %lld}\n",
+                        m_p, c0, w, G, c, h[c * 8 + 0], h[c * 8 + 1], h[c * 8 + 2], h[c * 8 + 3], h[c * 8 + 4], h[c * 8 + 5], h[c * 8 + 6], h[c * 8 + 7]);
+    }
     return launch_status();
 }
 
