@@ -356,9 +356,6 @@ def run_extra(args):
     if routine == "tileops":
         return run_tileops(args, sl, lib, torch)
     mixed = routine in ("posv_mixed", "gesv_mixed")
-    if mixed and world > 1 and os.environ.get("SB200_RUN_UNVALIDATED") != "1":
-        raise SystemExit("bench.py: the mixed-precision solve path on a p x q grid (csrc/solve_dist.cu) has not been validated "
-                         "on GPUs yet; set SB200_RUN_UNVALIDATED=1 to run it")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world != args.gpus:
