@@ -435,17 +435,17 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
             }
             ph.begin("bcast", P);
             if (multi) {
-                NCCL_TRY(ncclGroupStart());
+                std::vector<BcastItem> items;
                 for (int r = 0; r < p; ++r) {
                     if (count_rows(r, k) == 0) continue;
                     T* dstp = pws_tile(first_row(r, k), k);
                     const T* srcp = (g.rank == root && r == kp) ? A.tile_as<T>(first_row(r, k), k) : dstp;
-                    NCCL_TRY(ncclBroadcast(srcp, dstp, size_t(count_rows(r, k) * te), nccl_t, root, g.world, P));
+                    items.push_back({srcp, dstp, size_t(count_rows(r, k) * te) * sizeof(T), root});
                 }
-                NCCL_TRY(ncclBroadcast(perm, perm, size_t(3 * ntop) * sizeof(int), ncclChar, root, g.world, P));
-                NCCL_TRY(ncclBroadcast(pt, pt, size_t(ntop) * sizeof(int64_t), ncclChar, root, g.world, P));
-                NCCL_TRY(ncclBroadcast(po, po, size_t(ntop) * sizeof(int64_t), ncclChar, root, g.world, P));
-                NCCL_TRY(ncclGroupEnd());
+                items.push_back({perm, perm, size_t(3 * ntop) * sizeof(int), root});
+                items.push_back({pt, pt, size_t(ntop) * sizeof(int64_t), root});
+                items.push_back({po, po, size_t(ntop) * sizeof(int64_t), root});
+                SB_TRY(bcast_many(g, items, P));
                 // the other owners of panel tiles take their factored tiles back from the workspace
                 if (pcol == kq && g.rank != root && count_rows(prow, k) > 0)
                     CUDA_TRY(cudaMemcpyAsync(A.tile_as<T>(first_row(prow, k), k), pws_tile(first_row(prow, k), k),

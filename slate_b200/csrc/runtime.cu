@@ -92,24 +92,69 @@ struct PanelWs {
     T* at(int64_t i, int64_t k) const { return base + ((k % depth) * p * rows_max + (i % p) * rows_max + i / p) * te; }
 };
 
-// every rank receives tiles (i, k), i >= i_first, of block column k of A: p grouped broadcasts of
-// ranges that are contiguous in the root's pool (the reference's listBcast to a row+column rank
-// set, include/slate/BaseMatrix.hh:1998-2140, widened to all ranks)
+// Several root -> everybody broadcasts of contiguous byte ranges in one go (the reference's listBcast,
+// include/slate/BaseMatrix.hh:1998-2140).  SB200_BCAST = 0: one grouped ncclBroadcast per range (ring: the root's
+// egress carries the range once per channel and every hop adds latency).  1: scatter + all-gather (van de Geijn):
+// the root sends 1/N of the range to every rank, then ONE in-place ncclAllGather over NVSwitch completes it -- every
+// link carries 1/N of the bytes at a time and the all-gather is the collective NCCL runs through NVLS multicast.
+// Ranges below 4 MiB, and the < 16 N byte remainder that does not split evenly, stay plain broadcasts.
+int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s)
+{
+    if (g.size() <= 1 || items.empty()) return SB200_OK;
+    static const int mode = [] { const char* e = getenv("SB200_BCAST"); return e ? atoi(e) : SB200_BCAST_DEFAULT; }();
+    static const size_t min_bytes = [] { const char* e = getenv("SB200_BCAST_MIN"); return e ? size_t(atoll(e)) : (size_t(4) << 20); }();
+    const int N = g.size();
+    auto split = [&](const BcastItem& it) -> size_t {          // bytes per rank of the all-gather part (0: plain broadcast)
+        if (mode == 0 || it.bytes < min_bytes) return 0;
+        return it.bytes / N / 16 * 16;
+    };
+    bool any_split = false;
+    for (const auto& it : items) any_split |= split(it) > 0;
+    if (any_split) {
+        NCCL_TRY(ncclGroupStart());
+        for (const auto& it : items) {
+            const size_t c = split(it);
+            if (c == 0) continue;
+            if (g.rank == it.root) {
+                for (int r = 0; r < N; ++r)
+                    if (r != it.root)
+                        NCCL_TRY(ncclSend(static_cast<const char*>(it.src) + size_t(r) * c, c, ncclChar, r, g.world, s));
+            }
+            else
+                NCCL_TRY(ncclRecv(static_cast<char*>(it.dst) + size_t(g.rank) * c, c, ncclChar, it.root, g.world, s));
+        }
+        NCCL_TRY(ncclGroupEnd());
+    }
+    NCCL_TRY(ncclGroupStart());
+    for (const auto& it : items) {
+        const size_t c = split(it);
+        const char* src = static_cast<const char*>(g.rank == it.root ? it.src : it.dst);
+        char* dst = static_cast<char*>(it.dst);
+        if (c > 0) NCCL_TRY(ncclAllGather(src + size_t(g.rank) * c, dst, c, ncclChar, g.world, s));
+        const size_t done = c * size_t(N);
+        if (it.bytes > done)
+            NCCL_TRY(ncclBroadcast(src + done, dst + done, it.bytes - done, ncclChar, it.root, g.world, s));
+    }
+    NCCL_TRY(ncclGroupEnd());
+    return SB200_OK;
+}
+
+// every rank receives tiles (i, k), i >= i_first, of block column k of A: p ranges that are contiguous in their
+// root's pool (the reference's listBcast to a row+column rank set, widened to all ranks)
 template <typename T>
 static int bcast_block_column(Grid& g, Matrix& A, int64_t k, int64_t i_first, const PanelWs<T>& ws, cudaStream_t s)
 {
     const int64_t mt = A.mt, te = A.tile_elems();
-    NCCL_TRY(ncclGroupStart());
+    std::vector<BcastItem> items;
     for (int r = 0; r < g.p; ++r) {
         int64_t i0 = i_first + ((r - i_first) % g.p + g.p) % g.p;
         if (i0 >= mt) continue;
         const int64_t cnt = (mt - 1 - i0) / g.p + 1;
         const int root = g.rank_of(i0, k);
         const T* src = (g.rank == root) ? A.tile_as<T>(i0, k) : ws.at(i0, k);
-        NCCL_TRY(ncclBroadcast(src, ws.at(i0, k), size_t(cnt * te) * sizeof(T), ncclChar, root, g.world, s));
+        items.push_back({src, ws.at(i0, k), size_t(cnt * te) * sizeof(T), root});
     }
-    NCCL_TRY(ncclGroupEnd());
-    return SB200_OK;
+    return bcast_many(g, items, s);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -222,6 +222,11 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
 };
 
+// grouped root -> everybody broadcasts of contiguous ranges (runtime.cu); src is read on the root only
+struct BcastItem { const void* src; void* dst; size_t bytes; int root; };
+constexpr int SB200_BCAST_DEFAULT = 0;
+int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s);
+
 // drivers (runtime.cu)
 // lookahead <= 0: the library default (SB200_LOOKAHEAD or POTRF_DEFAULT_LOOKAHEAD)
 constexpr int POTRF_DEFAULT_LOOKAHEAD = 2, MAX_LOOKAHEAD = 8;
