@@ -16,7 +16,13 @@
 #include "sb200_abi.hh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
+#include <type_traits>
+#include <unordered_map>
 #include <vector>
+
+#include <cuda_runtime.h>
 
 namespace {
 
@@ -42,6 +48,57 @@ T** upload(std::vector<T*> const& src, size_t first, size_t count, int slot, bla
 
 // bytes of queue.work() reserved for pointer arrays; kernel scratch (trsm) lives behind them
 constexpr size_t kPtrBytes = 3 * size_t(blas::MaxBatchChunk) * sizeof(void*);
+
+// ---- 'N','N' -> 'N','T': the B tiles of a batch are few and shared (SUMMA step: nt distinct B(k,j) under mt x nt
+// products; LU trailing update: the row U(k, :)), and our FP64 kernel stages an N-contiguous B operand with TMA bulk
+// copies (0.95 of the DMMA peak) but a K-contiguous one with 16-byte cp.async (0.85; the incumbent cuBLAS: 0.86).
+// So each DISTINCT B tile is transposed once into a per-stream scratch (<= 0.1 % of the step's traffic) and the
+// batch runs as 'N','T'.  Same products in the same order: bitwise the same C.  SB200_SHIM_GEMM_BT=0 turns it off.
+struct BtScratch { void* buf = nullptr; size_t bytes = 0; };
+inline void* bt_scratch(cudaStream_t s, size_t bytes)
+{
+    static std::mutex mu;
+    static std::unordered_map<cudaStream_t, BtScratch> map;      // stream-ordered reuse: one buffer per queue
+    std::lock_guard<std::mutex> lk(mu);
+    BtScratch& e = map[s];
+    if (e.bytes < bytes) {
+        if (e.buf) { cudaStreamSynchronize(s); cudaFree(e.buf); }
+        e.buf = nullptr; e.bytes = 0;
+        if (cudaMalloc(&e.buf, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        e.bytes = bytes;
+    }
+    return e.buf;
+}
+inline bool bt_enabled()
+{
+    static const bool on = [] { const char* e = std::getenv("SB200_SHIM_GEMM_BT"); return ! e || std::atoi(e) != 0; }();
+    return on;
+}
+// Barray[first .. first+cnt) -> pointers to transposed copies (n x k, ld n); false = not applicable, nothing done
+template <typename T>
+bool transpose_b_tiles(std::vector<T*> const& Barray, size_t first, size_t cnt, int64_t k, int64_t n, int64_t ldb,
+                       std::vector<T*>& Bt, blas::Queue& queue)
+{
+    if constexpr (! (std::is_same<T, double>::value || std::is_same<T, std::complex<double>>::value)) return false;
+    if (! bt_enabled() || k > 1024 || n > 1024 || k < 16 || n < 16 || cnt < 8) return false;
+    std::unordered_map<T*, size_t> slot;
+    std::vector<T*> uniq;
+    for (size_t i = 0; i < cnt; ++i)
+        if (slot.emplace(Barray[first + i], uniq.size()).second) uniq.push_back(Barray[first + i]);
+    if (uniq.size() * 4 > cnt) return false;                     // not shared enough to pay for the copies
+    const size_t te = size_t(n) * size_t(k);
+    T* buf = static_cast<T*>(bt_scratch(queue.stream(), uniq.size() * te * sizeof(T)));
+    if (! buf) return false;
+    std::vector<T*> dstv(uniq.size());
+    for (size_t u = 0; u < uniq.size(); ++u) dstv[u] = buf + u * te;
+    T** dsrc = upload(uniq, 0, uniq.size(), 0, queue);           // slots 0 / 1 are re-filled with A / B afterwards
+    T** ddst = upload(dstv, 0, dstv.size(), 1, queue);           // (same stream: ordered behind the transposes)
+    check(transpose_batched(tag<T>(), 0, k, n, cpp(dsrc), ldb, pp(ddst), n, int64_t(uniq.size()), queue.stream()),
+          "batch::gemm (B transposes)");
+    Bt.resize(cnt);
+    for (size_t i = 0; i < cnt; ++i) Bt[i] = dstv[slot[Barray[first + i]]];
+    return true;
+}
 
 template <typename T>
 void batch_gemm(blas::Layout layout,
@@ -69,11 +126,14 @@ void batch_gemm(blas::Layout layout,
         queue.work_ensure_size<char>(kPtrBytes);
         for (size_t i = 0; i < batch_size; i += blas::MaxBatchChunk) {
             const size_t cnt = std::min(size_t(blas::MaxBatchChunk), batch_size - i);
+            std::vector<T*> Bt;
+            const bool bt = layout == blas::Layout::ColMajor && transB[0] == blas::Op::NoTrans
+                && transpose_b_tiles(Barray, i, cnt, k[0], n[0], ldb[0], Bt, queue);
             T** dA = upload(Aarray, i, cnt, 0, queue);
-            T** dB = upload(Barray, i, cnt, 1, queue);
+            T** dB = bt ? upload(Bt, 0, cnt, 1, queue) : upload(Barray, i, cnt, 1, queue);
             T** dC = upload(Carray, i, cnt, 2, queue);
-            check(gemm_batched(tag<T>(), ch(layout), ch(transA[0]), ch(transB[0]), m[0], n[0], k[0],
-                               to_abi(alpha[0]), cpp(dA), lda[0], cpp(dB), ldb[0],
+            check(gemm_batched(tag<T>(), ch(layout), ch(transA[0]), bt ? int('T') : ch(transB[0]), m[0], n[0], k[0],
+                               to_abi(alpha[0]), cpp(dA), lda[0], cpp(dB), bt ? n[0] : ldb[0],
                                to_abi(beta[0]), pp(dC), ldc[0], int64_t(cnt), queue.stream()),
                   "batch::gemm");
         }

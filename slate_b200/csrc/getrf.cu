@@ -598,12 +598,12 @@ struct PanelCtx {
 // one cooperative launch: columns [c0, c0+w) over panel rows [c0, m_p), interchanges applied to all
 // kw panel columns by the extra (row-less) CTA
 template <typename T>
-static int panel_base_wide(const PanelCtx<T>& x, int c0, int w)
+static int panel_base_wide(const PanelCtx<T>& x, int c0, int w, int upd_c0 = -1)
 {
     if (x.ps->use_v3) {
         x.pt->begin("pnl_base", x.s);
         SB_TRY(launch_base_v3<T>(x.stack, x.nb, x.m_p, c0, w, x.kw, x.piv_tile, x.piv_off, x.dinfo, x.info_base,
-                                 x.rowmap, *x.ps, x.s));
+                                 x.rowmap, *x.ps, x.s, upd_c0));
         x.pt->end(x.s);
         return SB200_OK;
     }
@@ -735,6 +735,8 @@ static int panel_recurse(const PanelCtx<T>& x, int c0, int w)
     int w1 = int(ceil_div(w / 2, PW)) * PW;
     if (w1 >= w) w1 = w - PW;
     SB_TRY(panel_recurse<T>(x, c0, w1));
+    // a 32-column block that follows a 32-column block takes that block's update inside its own launch
+    if (base_v3_can_fuse(*x.ps, x.m_p, c0 + w1, w1, w - w1)) return panel_base_wide<T>(x, c0 + w1, w - w1, c0);
     SB_TRY(panel_update<T>(x, c0, w1, c0 + w1, w - w1));
     return panel_recurse<T>(x, c0 + w1, w - w1);
 }

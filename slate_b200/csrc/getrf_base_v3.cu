@@ -94,6 +94,7 @@ struct V3Args {
     unsigned long long* drow;                 // [PW][2 PW]     diagonal row of column j (published by CTA 0)
     unsigned long long* pivrec;               // [PW]           pivot row of column j (published by CTA 0)
     unsigned gen_base; int gmax;
+    int upd_c0;                               // >= 0 (v4 only): first fold in the update by the 32-column block [upd_c0, upd_c0 + 32)
     long long* trace;                         // debug (SB200_V3_TRACE=1): [G][8] cycles per phase, thread 0 of every row CTA
 };
 #define V3_MARK(k) do { if (a.trace && tid == 0) { const long long t_ = clock64(); tr_acc[k] += t_ - tr_last; tr_last = t_; } } while (0)
@@ -317,6 +318,19 @@ getrf_base_v3_kernel(const V3Args<T> a)
 // ------------------------------------------------------------------------------------------
 constexpr int V4_THREADS = 512;
 
+// argmax over a warp of (|value| as its 64 bits {hi, lo}, row): larger value first, then the smaller row.  Three
+// redux.sync instead of five shuffle rounds of three registers; every lane gets the result.  (hi, lo) = 0 and
+// row = INT_MAX stand for "no candidate": a candidate of value 0 and none at all lead to the same decision (the
+// diagonal is kept unless a candidate is STRICTLY larger).
+__device__ __forceinline__ void v4_argmax(unsigned& hi, unsigned& lo, int& row)
+{
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const bool top = hi == mh && lo == ml;
+    row = int(__reduce_min_sync(0xffffffffu, top ? unsigned(row) : unsigned(INT_MAX)));
+    hi = mh; lo = ml;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(V4_THREADS, 1)
 getrf_base_v4_kernel(const V3Args<T> a)
@@ -324,10 +338,10 @@ getrf_base_v4_kernel(const V3Args<T> a)
     __shared__ __align__(16) T s_prow[PW];
     __shared__ __align__(16) T s_drow[PW];
     constexpr int NWARP = V4_THREADS / 32;
-    __shared__ double s_val[NWARP];
-    __shared__ int    s_row[NWARP];
-    __shared__ double g_val[NWARP];
-    __shared__ int    g_row[NWARP], g_cta[NWARP];
+    __shared__ unsigned s_hi[NWARP], s_lo[NWARP];
+    __shared__ int      s_row[NWARP];
+    __shared__ unsigned g_hi[NWARP], g_lo[NWARP];
+    __shared__ int      g_row[NWARP];
     const int G = a.G, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = a.nb, w = a.w;
 
@@ -356,11 +370,64 @@ getrf_base_v4_kernel(const V3Args<T> a)
     const bool have = tid < a.rows_per && r < a.m_p;
     T* rowp = have ? a.tiles[r / nb] + (r % nb) + int64_t(a.c0) * nb : nullptr;
     T x[PW];
-    #pragma unroll
-    for (int c = 0; c < PW; ++c) x[c] = (have && c < w) ? rowp[int64_t(c) * nb] : T(0);
+    __shared__ T sL[PW][PW + 1];                               // fused update: L11 | A12 -> U12
+    __shared__ __align__(16) T sU[PW][PW];
 
-    double best = (have && r > a.c0) ? double(fabs(x[0])) : -1.0;
-    int brow = (have && r > a.c0) ? r : INT_MAX;
+    if (a.upd_c0 >= 0) {
+        // ---- fused update by the previous 32-column block [u0, u0 + 32) (the w1 = n2 = 32 updates of the recursive panel:
+        //      8 of the 15 per nb = 512 panel, each a triangular-solve launch + a tile-GEMM launch before):
+        //      U12 = L11^-1 A12 (every CTA, redundantly: 32 x 32), then this thread's row: x -= L21(r, :) U12.
+        //      The interchange CTAs of THIS launch only touch L21 after the first pivot is known, i.e. after every
+        //      row CTA has published its first candidate, i.e. after it has finished reading L21 here.
+        const int u0 = a.upd_c0;
+        for (int e = tid; e < PW * PW; e += V4_THREADS) {
+            const int i = e % PW, k = e / PW;
+            const int rr = u0 + i;
+            const T* base = a.tiles[rr / nb] + (rr % nb);
+            sL[i][k] = base[int64_t(u0 + k) * nb];
+            sU[i][k] = k < w ? base[int64_t(a.c0 + k) * nb] : T(0);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane c owns column c of U12: forward substitution with the unit-lower L11, in place
+            #pragma unroll
+            for (int i = 1; i < PW; ++i) {
+                T sacc = sU[i][lane];
+                #pragma unroll
+                for (int k = 0; k < i; ++k) sacc = v3_fma(-sL[i][k], sU[k][lane], sacc);
+                sU[i][lane] = sacc;
+            }
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int c = 0; c < PW; ++c) x[c] = (have && c < w) ? rowp[int64_t(c) * nb] : T(0);
+        if (have) {
+            const T* lrow = a.tiles[r / nb] + (r % nb) + int64_t(u0) * nb;
+            #pragma unroll 1
+            for (int k0 = 0; k0 < PW; k0 += 8) {
+                T l[8];
+                #pragma unroll
+                for (int kk = 0; kk < 8; ++kk) l[kk] = lrow[int64_t(k0 + kk) * nb];
+                #pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    #pragma unroll
+                    for (int c = 0; c < PW; ++c) x[c] = v3_fma(-l[kk], sU[k0 + kk][c], x[c]);
+                }
+            }
+        }
+    }
+    else {
+        #pragma unroll
+        for (int c = 0; c < PW; ++c) x[c] = (have && c < w) ? rowp[int64_t(c) * nb] : T(0);
+    }
+
+    // candidate of the first column (NaN is never a candidate: the reference's `abs > max` is false for it)
+    unsigned khi = 0, klo = 0;
+    int krow = INT_MAX;
+    {
+        const double v = double(fabs(x[0]));
+        if (have && r > a.c0 && v == v) { khi = unsigned(__double2hiint(v)); klo = unsigned(__double2loint(v)); krow = r; }
+    }
 
     #pragma unroll
     for (int j = 0; j < PW; ++j) {
@@ -369,34 +436,24 @@ getrf_base_v4_kernel(const V3Args<T> a)
             const unsigned gen = a.gen_base + unsigned(j) + 1u;
             unsigned long long* slot = a.rec + size_t(j) * a.gmax * V3_REC;
             // ---- this CTA's candidate: warp, then block
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-                if (v3_better(ov, orow, best, brow)) { best = ov; brow = orow; }
-            }
-            if (lane == 0) { s_val[warp] = best; s_row[warp] = brow; }
+            v4_argmax(khi, klo, krow);
+            if (lane == 0) { s_hi[warp] = khi; s_lo[warp] = klo; s_row[warp] = krow; }
             __syncthreads();
-            best = lane < NWARP ? s_val[lane] : -1.0;
-            brow = lane < NWARP ? s_row[lane] : INT_MAX;
-            #pragma unroll
-            for (int o = NWARP / 2; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-                if (v3_better(ov, orow, best, brow)) { best = ov; brow = orow; }
-            }
-            best = __shfl_sync(0xffffffffu, best, 0);
-            brow = __shfl_sync(0xffffffffu, brow, 0);
+            khi = lane < NWARP ? s_hi[lane] : 0u;
+            klo = lane < NWARP ? s_lo[lane] : 0u;
+            krow = lane < NWARP ? s_row[lane] : INT_MAX;
+            v4_argmax(khi, klo, krow);
             // ---- publish: the owner of the candidate row sends header + row, the owner of row d the diagonal row
             {
                 unsigned long long* R = slot + size_t(b) * V3_REC;
-                if (brow == INT_MAX ? tid == 0 : (have && r == brow)) {
-                    if (brow != INT_MAX) {
+                if (krow == INT_MAX ? tid == 0 : (have && r == krow)) {
+                    if (krow != INT_MAX) {
                         #pragma unroll
                         for (int c = 0; c < PW; ++c) v3_store_double(R + V3_HDR + 2 * c, double(x[c]), gen);
                     }
-                    v3_store_double(R, best, gen);
-                    v3_store(R + 2, unsigned(brow), gen);
+                    const unsigned long long gg = static_cast<unsigned long long>(gen) << 32;
+                    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(R), "l"(gg | klo), "l"(gg | khi) : "memory");
+                    v3_store(R + 2, unsigned(krow), gen);
                 }
                 if (b == 0 && tid == j) {
                     #pragma unroll
@@ -404,8 +461,8 @@ getrf_base_v4_kernel(const V3Args<T> a)
                 }
             }
             // ---- gather: thread c polls the header of CTA c; the last warp polls the diagonal row
-            double bv = -1.0;
-            int br = INT_MAX, bw = -1;
+            unsigned bhi = 0, blo = 0;
+            int br = INT_MAX;
             if (tid < G) {
                 const unsigned long long* R = slot + size_t(tid) * V3_REC;
                 unsigned long long w0, w1, w2, w3;
@@ -415,42 +472,27 @@ getrf_base_v4_kernel(const V3Args<T> a)
                     if (unsigned(w0 >> 32) == gen && unsigned(w1 >> 32) == gen && unsigned(w2 >> 32) == gen) break;
                     spin_watchdog(t0);
                 }
-                bv = __hiloint2double(int(unsigned(w1)), int(unsigned(w0)));
+                blo = unsigned(w0); bhi = unsigned(w1);
                 br = int(unsigned(w2));
-                bw = tid;
             }
             if (warp == NWARP - 1)
                 s_drow[lane] = T(v3_wait_double(a.drow + (size_t(j) * PW + lane) * 2, gen));
-            if (warp * 32 < G) {
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const int orow = __shfl_xor_sync(0xffffffffu, br, o);
-                    const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                    if (v3_better(ov, orow, bv, br)) { bv = ov; br = orow; bw = ow; }
-                }
-            }
-            if (lane == 0) { g_val[warp] = bv; g_row[warp] = br; g_cta[warp] = bw; }
+            if (warp * 32 < G) v4_argmax(bhi, blo, br);
+            if (lane == 0) { g_hi[warp] = bhi; g_lo[warp] = blo; g_row[warp] = br; }
             __syncthreads();
-            bv = lane < NWARP ? g_val[lane] : -1.0;
+            bhi = lane < NWARP ? g_hi[lane] : 0u;
+            blo = lane < NWARP ? g_lo[lane] : 0u;
             br = lane < NWARP ? g_row[lane] : INT_MAX;
-            bw = lane < NWARP ? g_cta[lane] : -1;
-            #pragma unroll
-            for (int o = NWARP / 2; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int orow = __shfl_xor_sync(0xffffffffu, br, o);
-                const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                if (v3_better(ov, orow, bv, br)) { bv = ov; br = orow; bw = ow; }
-            }
-            bv = __shfl_sync(0xffffffffu, bv, 0);
-            br = __shfl_sync(0xffffffffu, br, 0);
-            bw = __shfl_sync(0xffffffffu, bw, 0);
+            v4_argmax(bhi, blo, br);
             // ---- every CTA picks the same winner: strictly larger than the diagonal, or the diagonal (ties, NaN)
+            const double bv = __hiloint2double(int(bhi), int(blo));
             const double dv = double(fabs(s_drow[j]));
-            const int p = (bv > dv) ? br : d;
-            if (warp == 0)
+            const int p = (br != INT_MAX && bv > dv) ? br : d;
+            if (warp == 0) {
+                const int bw = (p - a.c0) / a.rows_per;                 // the CTA that holds row p
                 s_prow[lane] = (p == d) ? s_drow[lane]
                                         : T(v3_wait_double(slot + size_t(bw) * V3_REC + V3_HDR + 2 * lane, gen));
+            }
             if (b == 0 && tid == 2 * 32) {
                 a.piv_tile[d] = p / nb;
                 a.piv_off[d] = p % nb;
@@ -481,9 +523,11 @@ getrf_base_v4_kernel(const V3Args<T> a)
                 for (int c = j + 1; c < PW; ++c) x[c] = v3_fma(-l, s_prow[c], x[c]);
             }
             if (j + 1 < PW) {
-                const bool cand = have && r > d + 1;
-                best = cand ? double(fabs(x[j + 1 < PW ? j + 1 : j])) : -1.0;
-                brow = cand ? r : INT_MAX;
+                const double v = double(fabs(x[j + 1 < PW ? j + 1 : j]));
+                const bool cand = have && r > d + 1 && v == v;
+                khi = cand ? unsigned(__double2hiint(v)) : 0u;
+                klo = cand ? unsigned(__double2loint(v)) : 0u;
+                krow = cand ? r : INT_MAX;
             }
         }
     }
@@ -492,6 +536,14 @@ getrf_base_v4_kernel(const V3Args<T> a)
         for (int c = 0; c < PW; ++c)
             if (c < w) rowp[int64_t(c) * nb] = x[c];
     }
+    // U12 goes back to the panel only now: every row CTA read A12 from that place before it published its first
+    // candidate, and CTA 0 has seen all of those
+    if (a.upd_c0 >= 0 && b == 0)
+        for (int e = tid; e < PW * PW; e += V4_THREADS) {
+            const int i = e % PW, k = e / PW;
+            const int rr = a.upd_c0 + i;
+            if (k < w) (a.tiles[rr / nb] + (rr % nb))[int64_t(a.c0 + k) * nb] = sU[i][k];
+        }
 }
 
 } // namespace
@@ -519,7 +571,7 @@ int base_v3_init()
 // columns [c0, c0+w) of the panel over rows [c0, m_p); interchanges applied panel-wide (kw columns) by the extra CTAs
 template <typename T>
 int launch_base_v3(T* const* stack, int nb, int m_p, int c0, int w, int kw, int64_t* piv_tile, int64_t* piv_off,
-                   int* dinfo, int info_base, int* rowmap, PanelScratch& ps, cudaStream_t s)
+                   int* dinfo, int info_base, int* rowmap, PanelScratch& ps, cudaStream_t s, int upd_c0)
 {
     const int active = m_p - c0;
     const int ctas = ps.max_ctas - V3_NWIDE;
@@ -528,6 +580,7 @@ int launch_base_v3(T* const* stack, int nb, int m_p, int c0, int w, int kw, int6
     int rows_per = v4 ? V4_THREADS : std::max(int(ceil_div(active, ctas)), std::min(active, PROWS_MAX));
     rows_per = std::max(rows_per, PW);
     if (rows_per > PROWS_MAX) return SB200_ENOTSUP;
+    if (upd_c0 >= 0 && ! v4) return SB200_EINVAL;             // callers ask base_v3_can_fuse first
     const int G = int(ceil_div(active, rows_per));
     if (ps.v3_gen > 0xF0000000u) {                        // tags about to wrap: start over from clean slots
         CUDA_TRY(cudaMemsetAsync(ps.v3_buf, 0, base_v3_scratch_bytes(ps.max_ctas), s));
@@ -536,7 +589,7 @@ int launch_base_v3(T* const* stack, int nb, int m_p, int c0, int w, int kw, int6
     V3Args<T> a{};
     a.tiles = stack; a.nb = nb; a.m_p = m_p; a.c0 = c0; a.w = w; a.rows_per = rows_per; a.G = G;
     a.piv_tile = piv_tile; a.piv_off = piv_off; a.info = dinfo; a.info_base = info_base;
-    a.rowmap = rowmap; a.kw_wide = kw;
+    a.rowmap = rowmap; a.kw_wide = kw; a.upd_c0 = upd_c0;
     a.rec = ps.v3_buf;
     a.drow = a.rec + size_t(PW) * ps.max_ctas * V3_REC;
     a.pivrec = a.drow + size_t(PW) * 2 * PW;
@@ -567,7 +620,16 @@ int launch_base_v3(T* const* stack, int nb, int m_p, int c0, int w, int kw, int6
     return launch_status();
 }
 
-template int launch_base_v3<double>(double* const*, int, int, int, int, int, int64_t*, int64_t*, int*, int, int*, PanelScratch&, cudaStream_t);
-template int launch_base_v3<float>(float* const*, int, int, int, int, int, int64_t*, int64_t*, int*, int, int*, PanelScratch&, cudaStream_t);
+template int launch_base_v3<double>(double* const*, int, int, int, int, int, int64_t*, int64_t*, int*, int, int*, PanelScratch&, cudaStream_t, int);
+template int launch_base_v3<float>(float* const*, int, int, int, int, int, int64_t*, int64_t*, int*, int, int*, PanelScratch&, cudaStream_t, int);
+
+// can the block [c0, c0 + w) of an m_p-row panel take its update by the previous 32-column block inside its own launch?
+bool base_v3_can_fuse(const PanelScratch& ps, int m_p, int c0, int w1, int w)
+{
+    static const int v4_sel = [] { const char* e = getenv("SB200_PANEL_V4"); return e ? atoi(e) : 1; }();
+    static const int fuse_sel = [] { const char* e = getenv("SB200_PANEL_FUSE"); return e ? atoi(e) : 1; }();
+    return ps.use_v3 && v4_sel != 0 && fuse_sel != 0 && w1 == PW && w >= 1 && w <= PW
+        && (m_p - c0) <= (ps.max_ctas - V3_NWIDE) * V4_THREADS && (m_p - c0) >= 1;
+}
 
 } // namespace sb200

@@ -55,7 +55,8 @@ size_t base_v3_scratch_bytes(int max_ctas);
 int base_v3_init();
 template <typename T>
 int launch_base_v3(T* const* stack, int nb, int m_p, int c0, int w, int kw, int64_t* piv_tile, int64_t* piv_off,
-                   int* dinfo, int info_base, int* rowmap, PanelScratch& ps, cudaStream_t s);
+                   int* dinfo, int info_base, int* rowmap, PanelScratch& ps, cudaStream_t s, int upd_c0 = -1);
+bool base_v3_can_fuse(const PanelScratch& ps, int m_p, int c0, int w1, int w);
 
 // fused row interchanges of one panel over a block-column range (getrf.cu)
 template <typename T>

@@ -50,6 +50,15 @@ __device__ inline float  fma_r(float a, float b, float c)    { return fmaf(a, b,
 __device__ inline double fma_r(double a, double b, double c) { return ::fma(a, b, c); }
 template <typename R> struct SumSq {
     R scale = R(0), sumsq = R(1), inv = R(0);
+    // N values at once: bmax = their maximum (0 if none counts), nan = one of them is NaN
+    template <int N> __device__ inline void add_batch(const R (&v)[N], const R (&wgt)[N], R bmax, bool nan)
+    {
+        if (nan) { R t = R(0); for (int u = 0; u < N; ++u) t += v[u]; scale = t; return; }      // NaN poisons the result
+        if (scale != scale || bmax == R(0)) return;
+        if (scale < bmax) { const R r = scale / bmax; sumsq = sumsq * r * r; scale = bmax; inv = R(1) / bmax; }
+        #pragma unroll
+        for (int u = 0; u < N; ++u) { const R r = v[u] * inv; sumsq = fma_r(r * wgt[u], r, sumsq); }
+    }
     __device__ inline void add(R absx)
     {
         if (absx != absx) { scale = absx; return; }             // NaN poisons the result
@@ -134,16 +143,34 @@ norm_kernel(int mode, NormCfg cfg, int m, int n, const T* const* A, int64_t lda,
                     const int i = i0 + 32 * u;
                     raw[u] = (i < m) ? a[i + int64_t(j) * lda] : zero_of<T>();
                 }
-                #pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const int i = i0 + 32 * u;
-                    if (i >= m || ! in_shape(cfg, i, j)) continue;
-                    const R v = abs_loaded(cfg, raw[u], i, j);
-                    if (mode == 'M') vmax = max_nan(vmax, v);
-                    else {
-                        ss.add(v);
-                        if (cfg.sym && i != j) ss.add(v);     // mirrored entry
+                if (mode == 'M') {
+                    // NaN-propagating max (device_util.cuh:22-25) as a plain max + one sticky NaN per batch
+                    R bm = R(0), bnan = R(0);
+                    #pragma unroll
+                    for (int u = 0; u < UN; ++u) {
+                        const int i = i0 + 32 * u;
+                        const bool on = i < m && in_shape(cfg, i, j);
+                        const R v = on ? abs_loaded(cfg, raw[u], i, j) : R(0);
+                        if (v != v) bnan = v;
+                        bm = v > bm ? v : bm;
                     }
+                    vmax = (bnan != bnan) ? bnan : max_nan(vmax, bm);
+                }
+                else {
+                    // Frobenius: ONE rescale decision per batch of UN loaded values (the branchy per-element lassq
+                    // update made this kernel instruction-bound: 3.7 of 6.5 TB/s), then UN straight multiply + FMA
+                    R v[UN], wgt[UN], bmax = R(0);
+                    bool nan = false;
+                    #pragma unroll
+                    for (int u = 0; u < UN; ++u) {
+                        const int i = i0 + 32 * u;
+                        const bool on = i < m && in_shape(cfg, i, j);
+                        v[u] = on ? abs_loaded(cfg, raw[u], i, j) : R(0);
+                        wgt[u] = (cfg.sym && i != j) ? R(2) : R(1);          // mirrored entry counts twice
+                        nan |= v[u] != v[u];
+                        bmax = v[u] > bmax ? v[u] : bmax;
+                    }
+                    ss.add_batch(v, wgt, bmax, nan);
                 }
             }
         }
