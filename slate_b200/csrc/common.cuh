@@ -27,15 +27,13 @@ inline int launch_status()
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ----------------------------------------------------------------------------- opt-in switches
-// Defaults of the round-2 candidates in ONE place (all 0 = off until they have run on a B200; flip here once
-// validated).  The environment variable of the same name overrides the default; every site reads it per call.
+// Defaults of the per-call switches in ONE place (each was measured on a B200 before it was turned on; the losers
+// of round 2 -- multi-warp / warp-synchronous diagonal kernels, tagged-word LU kernel of getrf.cu, hand-rolled grid
+// barrier, skinny panel update, persistent trailing GEMM -- were deleted).  The environment variable of the same name overrides the default; every site reads it per call.
 struct Switch { const char* env; int dflt; };
-constexpr Switch SW_DIAG_MW      {"SB200_DIAG_MW", 0};        // multi-warp 64 x 64 Cholesky / inverse (diag64.cuh): 1 | 2 (rsqrt)
-constexpr Switch SW_TILE_FUSED   {"SB200_TILE_FUSED", 0};     // one-launch tile Cholesky: 1 | 2 (rsqrt)
+constexpr Switch SW_TILE_FUSED   {"SB200_TILE_FUSED", 0};     // one-launch tile Cholesky: 1 | 2 (rsqrt); the potrf driver turns it on when the chain has its own SM partition
 constexpr Switch SW_TRSM_FUSED   {"SB200_TRSM_FUSED", 7};     // bit 0 panel solve, bit 1 row solve, bit 2 small-triangle (<= 32) solve: measured r2a, on
-constexpr Switch SW_PANEL_LL     {"SB200_PANEL_LL", 0};       // LU base kernel with tagged-word exchange
 constexpr Switch SW_PANEL_V3     {"SB200_PANEL_V3", 1};       // LU base kernel with one exchange round per column (getrf_base_v3.cu)
-constexpr Switch SW_PANEL_SKINNY {"SB200_PANEL_SKINNY", 0};   // one-launch skinny update inside the LU panel
 constexpr Switch SW_GEMM_BT      {"SB200_GEMM_BT", 1};        // transposed B panel / U row: 'N','T' multiply (measured r2a: dgemm 30.5 -> 35.3 TF/s), on
 inline int switch_value(const Switch& s)
 {

@@ -8,8 +8,9 @@
 // latency behind; the arithmetic itself (2 016 FMAs per thread) is ~2 us.  Here the same O(64^3) work is spread over
 // all threads of the CTA with two barriers per column, so every latency is overlapped by 4-8 warps.
 //
-// OPT-IN (SB200_DIAG_MW for the stand-alone kernels in factor_small.cu; always used by the opt-in fused tile
-// kernel): round-2 candidates written after round 1's GPU budget was spent, not yet run.
+// Used by the one-launch tile Cholesky (potrf_tile_fused.cu), which the potrf driver takes when the chain runs on its
+// own SM partition.  As stand-alone replacements of the register kernels they lost (665 us against 555 us per nb = 512
+// tile, profiles/r02a_bench_tile_chain_kernels.jsonl) and that use was deleted.
 //
 // Layout: column-major with leading dimension LD (padded), element (r, c) at M[c * LD + r].
 #pragma once

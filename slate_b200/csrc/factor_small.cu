@@ -212,9 +212,11 @@ __device__ __forceinline__ void store_inverse(R* __restrict__ Xs, const R (&x)[I
     }
 }
 
-// RSQ (opt-in, SB200_DIAG_RSQRT=1): one rsqrt per column instead of two divisions and a square root -- the
-// dependent chain of software FP64 divisions is what this kernel's 109 us are made of;
-// L_ij = a_ij * rinv, update with (a_ij * rinv^2), diag = d * rinv: <= 2-3 ulp from the divided form.
+// RSQ (the default since round 2; SB200_DIAG_RSQRT=0 for the divided form): one rsqrt per column instead of two
+// divisions and a square root -- the dependent chain of software FP64 divisions is what this kernel's 109 us were made
+// of; L_ij = a_ij * rinv, update with (a_ij * rinv^2), diag = d * rinv: <= 2-3 ulp from the
+// divided form.  Measured (profiles/r02b_pytest_gpu_tail.txt, r2b): the nb = 512 tile 566 -> 458 us, parity tests green.
+// The warp-synchronous (474 us) and multi-warp shared-memory (665 us) variants tried in round 2 lost and were deleted.
 template <typename R, bool RSQ = false>
 __global__ void __launch_bounds__(IB, 1)
 potrf_diag_fast_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv,
@@ -272,111 +274,6 @@ potrf_diag_fast_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv,
     store_inverse<R>(Ls, x, i, Winv, false);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Warp-synchronous variant of the diagonal-block Cholesky (opt-in: SB200_DIAG_WARP=1; round-2 candidate,
-// written after round 1's GPU budget was spent, NOT yet run).  Same contract as potrf_diag_fast_kernel.
-// The 64 x 64 block is handled as 2 x 2 blocks of 32: a 32 x 32 Cholesky lives entirely in ONE warp
-// (thread = row, the pivot and the normalised column travel by shuffles: no shared memory, no block
-// barrier on the 32-step chain), and each column costs one rsqrt instead of two divisions and a sqrt.
-//   warp 0: L11 = chol(A11)                                   (shuffles)
-//   warp 1: L21 = A21 L11^-T (rows independent), A22 -= L21 L21^T (L21 via shared memory), L22 = chol(A22)
-// Two block barriers in total; then the inverse exactly as in the fast kernel.
-// ---------------------------------------------------------------------------------------------
-template <typename R>
-__device__ __forceinline__ int chol32_warp(R (&a)[IB], int c0, int lane, R& rdiag)
-{
-    // in-warp Cholesky of the 32 x 32 block whose row `lane` sits in a[c0 .. c0 + 32); returns the first failing
-    // column + 1 (warp-uniform) or 0.  On return a[c0 + j] = L(lane, j) for j <= lane; rdiag = 1 / L(lane, lane).
-    int fail = 0;
-    #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const R d = __shfl_sync(0xffffffffu, a[c0 + j], j);
-        if (fail == 0 && !(d > R(0))) fail = j + 1;
-        const R rinv = rsqrt(d);
-        const R lj = (lane == j) ? d * rinv : a[c0 + j] * rinv;          // L(lane, j) for lane >= j
-        a[c0 + j] = lj;
-        if (lane == j) rdiag = rinv;
-        #pragma unroll
-        for (int c = j + 1; c < 32; ++c) {
-            const R lc = __shfl_sync(0xffffffffu, lj, c);                // L(c, j)
-            a[c0 + c] = fma(-lj, lc, a[c0 + c]);                         // meaningful for lane >= c
-        }
-    }
-    return fail;
-}
-
-template <typename R>
-__global__ void __launch_bounds__(IB, 1)
-potrf_diag_warp_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv,
-                       int* __restrict__ info, int info_base)
-{
-    extern __shared__ __align__(16) unsigned char smem_dyn[];
-    R* Ls = reinterpret_cast<R*>(smem_dyn);        // [IB*(IB+1)]: L columns (stride IB), later padded staging
-    R* rd = Ls + IB * (IB + 1);                    // [IB] reciprocal diagonal
-    __shared__ int s_fail;
-    const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
-    if (*info != 0) return;                        // an earlier block already failed: leave the tile alone
-    if (i == 0) s_fail = 0;
-    R a[IB];
-    #pragma unroll
-    for (int c = 0; c < IB; ++c)
-        a[c] = (i < nv && c < nv) ? (c <= i ? A[i + int64_t(c) * lda] : R(0)) : (i == c ? R(1) : R(0));
-    R rdiag = R(1);
-    __syncthreads();
-    if (warp == 0) {
-        const int f = chol32_warp<R>(a, 0, lane, rdiag);
-        if (f && lane == 0) s_fail = f;
-        #pragma unroll
-        for (int c = 0; c < 32; ++c) Ls[c * IB + i] = a[c];              // L11, column-major (rows 0..31)
-        rd[i] = rdiag;
-    }
-    __syncthreads();
-    if (s_fail) {
-        if (i == 0 && *info == 0) *info = info_base + s_fail;
-        return;
-    }
-    if (warp == 1) {
-        // L21 row: forward substitution against L11 (column-oriented: after l_j is known, update the later entries)
-        #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const R lj = a[j] * rd[j];
-            a[j] = lj;
-            #pragma unroll
-            for (int c = j + 1; c < 32; ++c) a[c] = fma(-lj, Ls[j * IB + c], a[c]);      // L11(c, j)
-        }
-        // park L21 in shared memory (rows 32..63 of the same column-major array), then A22 -= L21 L21^T (lower part)
-        #pragma unroll
-        for (int c = 0; c < 32; ++c) Ls[c * IB + i] = a[c];
-        __syncwarp();
-        #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            R acc = a[32 + c];
-            #pragma unroll
-            for (int q = 0; q < 32; ++q) acc = fma(-a[q], Ls[q * IB + 32 + c], acc);      // L21(i, q) * L21(32 + c, q)
-            a[32 + c] = acc;                                                              // meaningful for c <= lane
-        }
-        const int f = chol32_warp<R>(a, 32, lane, rdiag);
-        if (f && lane == 0) s_fail = 32 + f;
-    }
-    __syncthreads();
-    if (s_fail) {
-        if (i == 0 && *info == 0) *info = info_base + s_fail;
-        return;
-    }
-    #pragma unroll
-    for (int c = 0; c < IB; ++c)
-        if (c <= i && i < nv) A[i + int64_t(c) * lda] = a[c];
-    // L (final) into shared memory for the inverse; rows above the diagonal are never read
-    __syncthreads();
-    #pragma unroll
-    for (int c = 0; c < IB; ++c) Ls[c * IB + i] = a[c];
-    rd[i] = rdiag;
-    __syncthreads();
-    R x[IB];
-    inv_lower_column<R>(Ls, rd, i, x);
-    store_inverse<R>(Ls, x, i, Winv, false);
-}
-
 // fast trtri of the diagonal IB-blocks (real types): same contract as trtri_diag_kernel
 template <typename R>
 __global__ void __launch_bounds__(IB, 1)
@@ -413,88 +310,6 @@ trtri_diag_fast_kernel(const R* __restrict__ Tm, int ldt, int na, int lower, int
     store_inverse<R>(Ls, x, tid, W + int64_t(b) * IB * IB, lower == 0);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Multi-warp variants of the two diagonal-block kernels (opt-in: SB200_DIAG_MW=1 | 2; round-2 candidates, not yet
-// run): same contracts as potrf_diag_fast_kernel / trtri_diag_fast_kernel, the 64 x 64 block lives in shared memory
-// and all 256 threads work on it with rolled loops (diag64.cuh explains why: the register kernels above run at
-// 15-19 cycles per instruction).
-// ---------------------------------------------------------------------------------------------
-constexpr int MW_THREADS = 256;
-constexpr int MW_LD = IB + 1;
-template <typename R> constexpr size_t mw_smem() { return (size_t(2) * IB * MW_LD + IB) * sizeof(R); }
-
-template <typename R, bool RSQ>
-__global__ void __launch_bounds__(MW_THREADS)
-potrf_diag_mw_kernel(R* __restrict__ A, int lda, int nv, R* __restrict__ Winv, int* __restrict__ info, int info_base)
-{
-    extern __shared__ __align__(16) unsigned char smem_dyn[];
-    R* As = reinterpret_cast<R*>(smem_dyn);        // work matrix, later the inverse
-    R* Ls = As + IB * MW_LD;                       // L
-    R* rd = Ls + IB * MW_LD;                       // reciprocal diagonal
-    const int tid = threadIdx.x;
-    if (*info != 0) return;                        // an earlier block already failed: leave the tile alone
-    for (int e = tid; e < IB * IB; e += MW_THREADS) {
-        const int r = e % IB, c = e / IB;
-        As[c * MW_LD + r] = (r < nv && c < nv) ? (c <= r ? A[r + int64_t(c) * lda] : R(0)) : (r == c ? R(1) : R(0));
-    }
-    __syncthreads();
-    const int fail = chol64_smem<R, MW_THREADS, MW_LD, RSQ>(As, Ls, rd, tid);
-    if (fail) {
-        if (tid == 0 && *info == 0) *info = info_base + fail;
-        return;
-    }
-    for (int e = tid; e < IB * IB; e += MW_THREADS) {
-        const int r = e % IB, c = e / IB;
-        if (c <= r && r < nv) A[r + int64_t(c) * lda] = Ls[c * MW_LD + r];
-    }
-    inv64_smem<R, MW_THREADS, MW_LD>(Ls, rd, As, tid);
-    for (int e = tid; e < IB * IB; e += MW_THREADS) Winv[e] = As[(e / IB) * MW_LD + (e % IB)];      // W[i + j*IB] = X_ij
-}
-
-template <typename R>
-__global__ void __launch_bounds__(MW_THREADS)
-trtri_diag_mw_kernel(const R* __restrict__ Tm, int ldt, int na, int lower, int unit, R* __restrict__ W,
-                     const R* const* __restrict__ Tarr = nullptr, int na_last = 0)
-{
-    extern __shared__ __align__(16) unsigned char smem_dyn[];
-    R* Xs = reinterpret_cast<R*>(smem_dyn);
-    R* Ls = Xs + IB * MW_LD;
-    R* rd = Ls + IB * MW_LD;
-    const int b = blockIdx.x, tid = threadIdx.x;
-    if (Tarr) {
-        Tm = Tarr[blockIdx.y];
-        W += int64_t(blockIdx.y) * gridDim.x * IB * IB;
-        if (blockIdx.y == gridDim.y - 1) na = na_last;
-    }
-    const int o = b * IB;
-    const int nv = max(0, min(IB, na - o));
-    // always handled as LOWER: upper blocks are transposed in
-    for (int e = tid; e < IB * IB; e += MW_THREADS) {
-        const int i = e % IB, j = e / IB;              // for an upper block the transposing read is strided: 32 KB, once
-        R v = (i == j) ? R(1) : R(0);
-        if (i < nv && j < nv) {
-            if (i > j)                v = lower ? Tm[o + i + int64_t(o + j) * ldt] : Tm[o + j + int64_t(o + i) * ldt];
-            else if (i == j && !unit) v = Tm[o + i + int64_t(o + j) * ldt];
-        }
-        Ls[j * MW_LD + i] = v;
-        if (i == j) rd[i] = R(1) / v;
-    }
-    __syncthreads();
-    inv64_smem<R, MW_THREADS, MW_LD>(Ls, rd, Xs, tid);
-    R* Wb = W + int64_t(b) * IB * IB;
-    // inverse of the transpose = transpose of the inverse
-    for (int e = tid; e < IB * IB; e += MW_THREADS) {
-        const int i = e % IB, j = e / IB;
-        Wb[e] = lower ? Xs[j * MW_LD + i] : Xs[i * MW_LD + j];
-    }
-}
-
-// SB200_DIAG_MW (read per call so that a test can switch it): 0 = register kernels, 1 = multi-warp (sqrt + reciprocal),
-// 2 = multi-warp with one rsqrt per column
-static int diag_mw_mode()
-{
-    return switch_value(SW_DIAG_MW);
-}
 
 template <typename T> struct IsRealType { static constexpr bool value = false; };
 template <> struct IsRealType<float>  { static constexpr bool value = true; };
@@ -504,16 +319,9 @@ template <typename T>
 static int launch_potrf_diag(T* A, int lda, int nv, T* Winv, int* info, int info_base, cudaStream_t stream)
 {
     if constexpr (IsRealType<T>::value) {
-        const int mw = diag_mw_mode();
-        if (mw > 0) {
-            if (mw == 2) potrf_diag_mw_kernel<T, true><<<1, MW_THREADS, mw_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
-            else         potrf_diag_mw_kernel<T, false><<<1, MW_THREADS, mw_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
-            return launch_status();
-        }
-        static const bool rsq = [] { const char* e = getenv("SB200_DIAG_RSQRT"); return e && atoi(e) != 0; }();
-        static const bool wrp = [] { const char* e = getenv("SB200_DIAG_WARP"); return e && atoi(e) != 0; }();
-        if (wrp)      potrf_diag_warp_kernel<T><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
-        else if (rsq) potrf_diag_fast_kernel<T, true><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
+        const char* e = getenv("SB200_DIAG_RSQRT");                  // per call: a test switches it
+        const bool rsq = ! e || atoi(e) != 0;
+        if (rsq) potrf_diag_fast_kernel<T, true><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
         else     potrf_diag_fast_kernel<T, false><<<1, IB, fast_smem<T>(), stream>>>(A, lda, nv, Winv, info, info_base);
     }
     else
@@ -525,8 +333,7 @@ template <typename T>
 static int launch_trtri_diag(int nblk, const T* Tm, int ldt, int na, int lower, int unit, T* W, cudaStream_t stream)
 {
     if constexpr (IsRealType<T>::value) {
-        if (diag_mw_mode() > 0) trtri_diag_mw_kernel<T><<<nblk, MW_THREADS, mw_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
-        else                    trtri_diag_fast_kernel<T><<<nblk, IB, fast_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
+        trtri_diag_fast_kernel<T><<<nblk, IB, fast_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
     }
     else
         trtri_diag_kernel<T><<<nblk, 256, small_smem<T>(), stream>>>(Tm, ldt, na, lower, unit, W);
@@ -542,10 +349,7 @@ static int launch_trtri_diag_batched(int ntiles, const T* const* Tarr, int ldt, 
     const int nblk = int(ceil_div(na, IB));
     if (ntiles <= 0 || nblk <= 0) return SB200_OK;
     if constexpr (IsRealType<T>::value) {
-        if (diag_mw_mode() > 0)
-            trtri_diag_mw_kernel<T><<<dim3(nblk, ntiles), MW_THREADS, mw_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
-        else
-            trtri_diag_fast_kernel<T><<<dim3(nblk, ntiles), IB, fast_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
+        trtri_diag_fast_kernel<T><<<dim3(nblk, ntiles), IB, fast_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
     }
     else
         trtri_diag_kernel<T><<<dim3(nblk, ntiles), 256, small_smem<T>(), stream>>>(nullptr, ldt, na, lower, unit, W, Tarr, na_last);
@@ -564,11 +368,7 @@ static void small_kernels_init()
     if constexpr (IsRealType<T>::value) {
         cudaFuncSetAttribute(potrf_diag_fast_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
         cudaFuncSetAttribute(potrf_diag_fast_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
-        cudaFuncSetAttribute(potrf_diag_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
         cudaFuncSetAttribute(trtri_diag_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem<T>()));
-        cudaFuncSetAttribute(potrf_diag_mw_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mw_smem<T>()));
-        cudaFuncSetAttribute(potrf_diag_mw_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mw_smem<T>()));
-        cudaFuncSetAttribute(trtri_diag_mw_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mw_smem<T>()));
     }
     done[dev & 63] = true;
 }
@@ -611,7 +411,7 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
     const int nblk = int(ceil_div(na, IB));
     small_kernels_init<T>();
     if constexpr (IsRealType<T>::value) {
-        // opt-in (round-2 candidate, not yet run): bit 2 = a small triangle (na <= 64: the U12 solves inside the LU panel)
+        // SB200_TRSM_FUSED (default 7, measured r2a): bit 2 = a small triangle (na <= 64: the U12 solves inside the LU panel)
         // by direct substitution in one launch, no inversion kernel
         if ((switch_value(SW_TRSM_FUSED) & 4) && left && lower && op == 'N' && na <= 32) {      // 13 us vs 24 us (na = 32); slower than the inverse path at 64
             if constexpr (std::is_same<T, double>::value) return trsm_lln_small_d(na, n, alpha, unit, Tm, ldt, dB, offB, ldb, batch, stream);
@@ -621,7 +421,7 @@ int trsm_colmajor(bool left, bool lower, int op, bool unit, int m, int n, T alph
     int st = launch_trtri_diag<T>(nblk, Tm, ldt, na, lower ? 1 : 0, unit ? 1 : 0, W, stream);
     if (st) return st;
     if constexpr (IsRealType<T>::value) {
-        // opt-in (round-2 candidates, not yet run; potrf_tile_fused.cu): one launch after the inverses for
+        // bits 0 / 1 (potrf_tile_fused.cu): one launch after the inverses for
         //   bit 0: the Cholesky panel solve (Right, Lower, Trans, NonUnit)
         //   bit 1: the LU row solve (Left, Lower, NoTrans, Unit / NonUnit)      (bit 2: see above)
         // read per call so that a test can switch it

@@ -99,17 +99,10 @@ struct BaseArgs {
     int kw_wide;       // > 0: the LAST CTA of the grid owns no rows and applies every interchange of this
                        // block to the panel columns outside [c0, c0+w) (all kw_wide columns of the panel)
                        // while the other CTAs go on factoring -- no laswp launches between blocks
-    unsigned* bar;     // opt-in (SB200_PANEL_BARRIER=1, round-2 candidate): arrival counter of a hand-rolled grid
-                       // barrier (zeroed before the launch) used instead of cooperative-groups grid.sync()
+    unsigned* bar;     // unused (kept: ptxas's register allocation for this kernel depends on the size of the struct)
 };
 // (BaseArgs is left exactly as validated: ptxas's register allocation for getrf_base_kernel changes with the size of
 // its parameter struct -- 64 registers as measured in round 1, 40 + a spill with two more fields.)
-template <typename T>
-struct LLArgs {
-    BaseArgs<T> b;
-    unsigned long long* ll;   // opt-in (SB200_PANEL_LL=1, round-2 candidate): flag-in-data exchange buffers of
-    unsigned gen_base;        // getrf_base_ll_kernel; column j of this launch is tagged gen_base + j + 1
-};
 
 // NOPIV = true (getrf_nopiv, src/getrf_nopiv.cc): no candidate is ever proposed, so the diagonal entry is the pivot of
 // every column and the interchange logic below degenerates to the identity; everything else (the diagonal row's
@@ -180,20 +173,7 @@ getrf_base_kernel(const BaseArgs<T> a)
             if (d >= r_begin && d < r_end) a.gdiag[par * PW + tid] = blk[tid * RP + (d - r_begin)];
         }
         __threadfence();
-        if (a.bar) {
-            // one arrival per CTA per column; released when all gridDim.x CTAs of this launch have arrived j + 1 times
-            __syncthreads();
-            if (tid == 0) {
-                atomicAdd(a.bar, 1u);
-                const unsigned target = unsigned(j + 1) * gridDim.x;
-                unsigned seen;
-                const long long t0 = clock64();
-                do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.bar) : "memory"); spin_watchdog(t0); } while (seen < target);
-            }
-            __syncthreads();
-            __threadfence();          // every thread orders its reads of the other CTAs' candidates after the release it waited for
-        }
-        else grid.sync();
+        grid.sync();
 
         // ---- every CTA picks the same winner: diagonal first, then strictly larger candidates
         if (warp == 0) {
@@ -273,225 +253,6 @@ getrf_base_kernel(const BaseArgs<T> a)
         }
 }
 
-// ------------------------------------------------------------------------------------------
-// Flag-in-data variant of the base kernel (opt-in: SB200_PANEL_LL=1; round-2 candidate, written after round 1's GPU
-// budget was spent, NOT yet run).  Same contract, same pivot rule, same arithmetic as getrf_base_kernel.
-//
-// Why: the per-column cost of getrf_base_kernel (9.6 us measured; 315 ms of the 1011 ms dgetrf at n = 32768) is a chain
-// of L2 round trips -- candidate stores + __threadfence, the grid barrier (arrive + poll), the candidate scan, the
-// diagonal value, the winner's row -- not arithmetic.  Here every value that crosses CTAs travels as 8-byte words
-// {32 data bits | 32-bit generation tag} (the NCCL "LL" protocol: an aligned 8-byte store is single-copy atomic, so a
-// reader that sees the tag of the current column sees the data; no fence, no counter, no barrier).  Per column:
-//   every CTA stores its candidate (|max|, row) + that row's 32 values, the diagonal owner stores the diagonal row;
-//   every CTA polls all G candidate records (one record per thread: ONE round trip) and the diagonal row, picks the
-//   winner, then polls the winner's row (second round trip).
-// Slots are double-buffered by column parity: a CTA can only be two columns ahead of another one after that one has
-// published the column in between, i.e. after it finished reading the slot that is being overwritten.
-// Tags grow monotonically over the launches of one driver call (PanelScratch::gen_base), so stale slots never match.
-// All CTAs must be co-resident (they spin on each other): the launch stays a cooperative launch.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned data, unsigned gen)
-{
-    const unsigned long long w = (static_cast<unsigned long long>(gen) << 32) | data;
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-// a double travels as two tagged words; both loads are in flight together, re-polled until both carry `gen`
-__device__ __forceinline__ double ll_wait_double(const unsigned long long* p, unsigned gen)
-{
-    unsigned long long lo, hi;
-    const long long t0 = clock64();
-    for (;;) {
-        lo = ll_load(p); hi = ll_load(p + 1);
-        if (unsigned(lo >> 32) == gen && unsigned(hi >> 32) == gen) break;
-        spin_watchdog(t0);
-    }
-    return __hiloint2double(int(unsigned(hi)), int(unsigned(lo)));
-}
-__device__ __forceinline__ void ll_store_double(unsigned long long* p, double v, unsigned gen)
-{
-    ll_store(p, unsigned(__double2loint(v)), gen);
-    ll_store(p + 1, unsigned(__double2hiint(v)), gen);
-}
-
-template <typename T>
-__global__ void __launch_bounds__(PTHREADS)
-getrf_base_ll_kernel(const LLArgs<T> q)
-{
-    const BaseArgs<T>& a = q.b;
-    extern __shared__ __align__(16) unsigned char blk_raw[];
-    T* blk = reinterpret_cast<T*>(blk_raw);          // [w][RP]
-    __shared__ T s_prow[PW], s_drow[PW];
-    __shared__ double s_val[PTHREADS / 32];
-    __shared__ int    s_row[PTHREADS / 32], s_cta[PTHREADS / 32];
-    __shared__ int    s_p, s_w;
-    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int RP = a.rows_per | 1;
-    const int r_begin = a.c0 + b * a.rows_per;
-    const int r_end = min(r_begin + a.rows_per, a.m_p);
-    const int nr = max(r_end - r_begin, 0);
-    const int nb = a.nb;
-    unsigned long long* rec  = q.ll;                                   // [2][G][4]: |max| (2 words), row, pad
-    unsigned long long* cand = rec + size_t(2) * G * 4;                // [2][G][PW][2]
-    unsigned long long* diag = cand + size_t(2) * G * PW * 2;          // [2][PW][2]
-
-    for (int c = 0; c < a.w; ++c)
-        for (int lr = tid; lr < nr; lr += PTHREADS) {
-            const int r = r_begin + lr;
-            blk[c * RP + lr] = a.tiles[r / nb][(r % nb) + int64_t(a.c0 + c) * nb];
-        }
-    __syncthreads();
-
-    for (int j = 0; j < a.w; ++j) {
-        const int d = a.c0 + j;                    // panel row of the diagonal entry
-        const int par = j & 1;
-        const unsigned gen = q.gen_base + unsigned(j) + 1u;
-        // ---- local candidate: first maximum of |a| over this CTA's rows below the diagonal
-        double best = -1.0;
-        int brow = INT_MAX;
-        for (int lr = tid; lr < nr; lr += PTHREADS) {
-            const int r = r_begin + lr;
-            if (r > d) {
-                const double v = double(fabs(blk[j * RP + lr]));
-                if (v > best) { best = v; brow = r; }      // rows ascend per thread: first max kept
-            }
-        }
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-            if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; }
-        }
-        if (lane == 0) { s_val[warp] = best; s_row[warp] = brow; }
-        __syncthreads();
-        if (warp == 0) {
-            best = lane < PTHREADS / 32 ? s_val[lane] : -1.0;
-            brow = lane < PTHREADS / 32 ? s_row[lane] : INT_MAX;
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
-                if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; }
-            }
-            if (lane == 0) {
-                s_p = brow;
-                unsigned long long* r = rec + (size_t(par) * G + b) * 4;
-                ll_store_double(r, best, gen);
-                ll_store(r + 2, unsigned(brow), gen);
-            }
-        }
-        __syncthreads();
-        // ---- publish the candidate row (and the diagonal row, if this CTA holds it): thread c sends column c
-        if (tid < a.w) {
-            const int cr = s_p;
-            if (cr != INT_MAX)
-                ll_store_double(cand + ((size_t(par) * G + b) * PW + tid) * 2, double(blk[tid * RP + (cr - r_begin)]), gen);
-            if (d >= r_begin && d < r_end)
-                ll_store_double(diag + (size_t(par) * PW + tid) * 2, double(blk[tid * RP + (d - r_begin)]), gen);
-        }
-        // ---- gather: thread c < G polls the record of CTA c; the last warp polls the diagonal row
-        double bv = -1.0;
-        int br = INT_MAX, bw = -1;
-        for (int c = tid; c < G; c += PTHREADS) {               // G <= PTHREADS - 32 in practice: one record per thread
-            const unsigned long long* r = rec + (size_t(par) * G + c) * 4;
-            unsigned long long w0, w1, w2;
-            const long long t0 = clock64();
-            for (;;) {
-                w0 = ll_load(r); w1 = ll_load(r + 1); w2 = ll_load(r + 2);
-                if (unsigned(w0 >> 32) == gen && unsigned(w1 >> 32) == gen && unsigned(w2 >> 32) == gen) break;
-                spin_watchdog(t0);
-            }
-            const double v = __hiloint2double(int(unsigned(w1)), int(unsigned(w0)));
-            const int rr = int(unsigned(w2));
-            if (v > bv || (v == bv && rr < br)) { bv = v; br = rr; bw = c; }
-        }
-        if (warp == PTHREADS / 32 - 1 && lane < a.w)
-            s_drow[lane] = T(ll_wait_double(diag + (size_t(par) * PW + lane) * 2, gen));
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int orow = __shfl_xor_sync(0xffffffffu, br, o);
-            const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
-            if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; bw = ow; }
-        }
-        if (lane == 0) { s_val[warp] = bv; s_row[warp] = br; s_cta[warp] = bw; }
-        __syncthreads();
-        // ---- every CTA picks the same winner: diagonal first, then strictly larger candidates
-        if (warp == 0) {
-            bv = lane < PTHREADS / 32 ? s_val[lane] : -1.0;
-            br = lane < PTHREADS / 32 ? s_row[lane] : INT_MAX;
-            bw = lane < PTHREADS / 32 ? s_cta[lane] : -1;
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int orow = __shfl_xor_sync(0xffffffffu, br, o);
-                const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; bw = ow; }
-            }
-            if (lane == 0) {
-                const double dv = double(fabs(s_drow[j]));
-                if (bv > dv) { s_p = br; s_w = bw; }        // strict: the diagonal wins ties (and NaN)
-                else         { s_p = d;  s_w = -1; }
-            }
-        }
-        __syncthreads();
-        const int p = s_p;
-        if (tid < a.w)
-            s_prow[tid] = (p == d) ? s_drow[tid]
-                                   : T(ll_wait_double(cand + ((size_t(par) * G + s_w) * PW + tid) * 2, gen));
-        __syncthreads();
-        if (p != d && tid < a.w) {
-            if (p >= r_begin && p < r_end) blk[tid * RP + (p - r_begin)] = s_drow[tid];
-            if (d >= r_begin && d < r_end) blk[tid * RP + (d - r_begin)] = s_prow[tid];
-        }
-        if (b == 0 && tid == 0) {
-            a.piv_tile[d] = p / nb;
-            a.piv_off[d] = p % nb;
-            if (a.rowmap && p != d) { const int t = a.rowmap[d]; a.rowmap[d] = a.rowmap[p]; a.rowmap[p] = t; }
-        }
-        if (a.kw_wide > 0 && b == G - 1 && p != d) {
-            T* rd_ = a.tiles[d / nb] + (d % nb);
-            T* rp_ = a.tiles[p / nb] + (p % nb);
-            for (int c = tid; c < a.kw_wide; c += PTHREADS)
-                if (c < a.c0 || c >= a.c0 + a.w) {
-                    const T t0 = rd_[int64_t(c) * nb], t1 = rp_[int64_t(c) * nb];
-                    rd_[int64_t(c) * nb] = t1;
-                    rp_[int64_t(c) * nb] = t0;
-                }
-        }
-        __syncthreads();
-        const T pv = s_prow[j];
-        if (pv == T(0)) {
-            if (b == 0 && tid == 0 && *a.info == 0) *a.info = a.info_base + d + 1;
-        }
-        else {
-            const bool use_rcp = fabs(pv) >= tiny_of<T>();
-            const T rcp = T(1) / pv;
-            for (int lr = tid; lr < nr; lr += PTHREADS) {
-                const int r = r_begin + lr;
-                if (r > d) {
-                    T l = blk[j * RP + lr];
-                    l = use_rcp ? l * rcp : l / pv;
-                    blk[j * RP + lr] = l;
-                    for (int c = j + 1; c < a.w; ++c)
-                        blk[c * RP + lr] = fma_t(-l, s_prow[c], blk[c * RP + lr]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    for (int c = 0; c < a.w; ++c)
-        for (int lr = tid; lr < nr; lr += PTHREADS) {
-            const int r = r_begin + lr;
-            a.tiles[r / nb][(r % nb) + int64_t(a.c0 + c) * nb] = blk[c * RP + lr];
-        }
-}
-
 // set by the getrf_nopiv entry points around their driver call (the drivers construct their PanelScratch on the
 // calling thread); read once per driver call by PanelScratch::init
 static thread_local bool g_getrf_nopiv = false;
@@ -503,9 +264,8 @@ int PanelScratch::init()
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     max_ctas = sms;
     const size_t G = size_t(sms);
-    ll_bytes = (2 * G * 4 + 2 * G * PW * 2 + 2 * PW * 2) * sizeof(unsigned long long);
     const size_t v3_bytes = base_v3_scratch_bytes(sms);
-    const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8 + 64 + ll_bytes + 16 + v3_bytes;
+    const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8 + 64 + 16 + v3_bytes;
     CUDA_TRY(cudaMalloc(&raw, bytes));
     char* p = static_cast<char*>(raw);
     gval = reinterpret_cast<double*>(p); p += 2 * G * 8;
@@ -514,20 +274,15 @@ int PanelScratch::init()
     gdiag = reinterpret_cast<double*>(p); p += 2 * PW * 8;
     W = reinterpret_cast<double*>(p); p += 16 * 64 * 64 * 8;
     bar = reinterpret_cast<unsigned*>(p); p += 64;
-    ll = reinterpret_cast<unsigned long long*>(p); p += ll_bytes;
     p = static_cast<char*>(raw) + (size_t(p - static_cast<char*>(raw)) + 15) / 16 * 16;      // 16-byte vector accesses
     v3_buf = reinterpret_cast<unsigned long long*>(p);
-    { const char* e = getenv("SB200_PANEL_BARRIER"); use_bar = e && atoi(e) != 0; }
-    use_ll = switch_value(SW_PANEL_LL) != 0;
     nopiv = g_getrf_nopiv;
-    use_v3 = ! nopiv && ! use_ll && ! use_bar && switch_value(SW_PANEL_V3) != 0;
+    use_v3 = ! nopiv && switch_value(SW_PANEL_V3) != 0;
     if (use_v3) {
         CUDA_TRY(cudaMemset(v3_buf, 0, v3_bytes));             // tag 0 is never used by a launch
         SB_TRY(base_v3_init());
     }
     v3_gen = 0;
-    if (use_ll) CUDA_TRY(cudaMemset(ll, 0, ll_bytes));          // tag 0 is never used by a launch
-    gen_base = 0;
     static thread_local bool attr_done[64] = {};
     if (! attr_done[dev & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -537,10 +292,6 @@ int PanelScratch::init()
         CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(PW * (PROWS_MAX | 1) * sizeof(double))));
         CUDA_TRY(cudaFuncSetAttribute(getrf_base_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(PW * (PROWS_MAX | 1) * sizeof(float))));
-        CUDA_TRY(cudaFuncSetAttribute(getrf_base_ll_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(PW * (PROWS_MAX | 1) * sizeof(double))));
-        CUDA_TRY(cudaFuncSetAttribute(getrf_base_ll_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(PW * (PROWS_MAX | 1) * sizeof(float))));
         attr_done[dev & 63] = true;
     }
@@ -558,8 +309,8 @@ static int panel_version()
     return e ? atoi(e) : 2;
 }
 
-// one base-block launch: the cooperative-groups kernel, or (opt-in) the flag-in-data kernel -- still launched
-// cooperatively because its CTAs spin on each other and must be co-resident
+// one base-block launch of the cooperative-groups kernel (getrf_nopiv, SB200_PANEL=1, SB200_PANEL_V3=0; the default
+// path is getrf_base_v3.cu)
 template <typename T>
 static int launch_base(BaseArgs<T>& a, int grid, size_t smem, PanelScratch& ps, cudaStream_t s)
 {
@@ -567,16 +318,6 @@ static int launch_base(BaseArgs<T>& a, int grid, size_t smem, PanelScratch& ps, 
     if (ps.nopiv) {                                             // getrf_nopiv: the barrier kernel without a pivot search
         void* args[] = {&a};
         e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_kernel<T, true>), dim3(grid), dim3(PTHREADS), args, smem, s);
-    }
-    else if (ps.use_ll) {
-        if (ps.gen_base > 0xF0000000u) {                        // tags about to wrap: start over from clean slots
-            CUDA_TRY(cudaMemsetAsync(ps.ll, 0, ps.ll_bytes, s));
-            ps.gen_base = 0;
-        }
-        LLArgs<T> q{a, ps.ll, ps.gen_base};
-        ps.gen_base += unsigned(PW);
-        void* args[] = {&q};
-        e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_ll_kernel<T>), dim3(grid), dim3(PTHREADS), args, smem, s);
     }
     else {
         void* args[] = {&a};
@@ -616,62 +357,12 @@ static int panel_base_wide(const PanelCtx<T>& x, int c0, int w, int upd_c0 = -1)
     BaseArgs<T> a{x.stack, x.nb, x.m_p, c0, w, rows_per, x.piv_tile, x.piv_off,
                   reinterpret_cast<T*>(x.ps->gval), x.ps->grow, reinterpret_cast<T*>(x.ps->gcand),
                   reinterpret_cast<T*>(x.ps->gdiag), x.dinfo, x.info_base, x.rowmap, x.kw,
-                  x.ps->use_bar ? x.ps->bar : nullptr};
-    if (x.ps->use_bar) CUDA_TRY(cudaMemsetAsync(x.ps->bar, 0, sizeof(unsigned), x.s));
+                  nullptr};
     const size_t smem = size_t(w) * (rows_per | 1) * sizeof(T);
     x.pt->begin("pnl_base", x.s);
     SB_TRY(launch_base<T>(a, G + 1, smem, *x.ps, x.s));
     x.pt->end(x.s);
     return SB200_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// Skinny panel update (opt-in: SB200_PANEL_SKINNY=1; round-2 candidate, not yet run):
-//   A22(r, cc + c) -= sum_k L21(r, c0 + k) U12(k, c)      for every panel row r >= r0,  w1 <= 64,  n2 <= 64
-// in ONE launch over the whole tile stack.  12 of the 15 updates of an nb = 512 panel have w1, n2 <= 64; today each is
-// three launches of the tensor-core tile GEMM (top partial tile, full tiles, ragged last tile: ~17 us each, fixed
-// cost), although the work is 2 m_p w1 n2 flop on data that sits in L2.  Thread = one panel row (loads coalesced down
-// the tile columns), U12 broadcast from shared memory, the row's n2 results in registers.  Sums run over k in
-// increasing order with FMAs from zero and C - acc at the end, as the tile GEMM does.
-// ------------------------------------------------------------------------------------------
-constexpr int PSK_ROWS = 128;
-template <typename T, int N2T>
-__global__ void __launch_bounds__(PSK_ROWS)
-panel_update_skinny_kernel(T* const* __restrict__ tiles, int nb, int m_p, int r0, int c0, int w1, int cc, int n2)
-{
-    __shared__ T Us[64 * N2T];                       // Us[k * N2T + c] = U12(k, c), zero beyond n2
-    const int tid = threadIdx.x;
-    const T* top = tiles[0];
-    for (int e = tid; e < w1 * N2T; e += PSK_ROWS) {
-        const int k = e / N2T, c = e - k * N2T;
-        Us[e] = (c < n2) ? top[(c0 + k) + int64_t(cc + c) * nb] : T(0);
-    }
-    __syncthreads();
-    const int r = r0 + blockIdx.x * PSK_ROWS + tid;
-    if (r >= m_p) return;
-    T* row = tiles[r / nb] + (r % nb);
-    T acc[N2T];
-    #pragma unroll
-    for (int c = 0; c < N2T; ++c) acc[c] = T(0);
-    #pragma unroll 2
-    for (int k = 0; k < w1; ++k) {
-        const T l = row[int64_t(c0 + k) * nb];
-        #pragma unroll
-        for (int c = 0; c < N2T; ++c) acc[c] = fma_t(l, Us[k * N2T + c], acc[c]);
-    }
-    #pragma unroll
-    for (int c = 0; c < N2T; ++c)
-        if (c < n2) { T* p = row + int64_t(cc + c) * nb; *p = *p - acc[c]; }
-}
-
-template <typename T>
-static int launch_panel_update_skinny(T* const* stack, int nb, int m_p, int r0, int c0, int w1, int cc, int n2, cudaStream_t s)
-{
-    if (m_p <= r0) return SB200_OK;
-    const unsigned grid = unsigned(ceil_div(m_p - r0, PSK_ROWS));
-    if (n2 <= 32) panel_update_skinny_kernel<T, 32><<<grid, PSK_ROWS, 0, s>>>(stack, nb, m_p, r0, c0, w1, cc, n2);
-    else          panel_update_skinny_kernel<T, 64><<<grid, PSK_ROWS, 0, s>>>(stack, nb, m_p, r0, c0, w1, cc, n2);
-    return launch_status();
 }
 
 // columns [cc, cc+n2) of the panel, given that columns [c0, c0+w1) are factored:
@@ -688,14 +379,6 @@ static int panel_update(const PanelCtx<T>& x, int c0, int w1, int cc, int n2)
     x.pt->begin("pnl_gemm", x.s);
     const T* U12 = x.tile0 + c0 + int64_t(cc) * nb;
     const int r0 = c0 + w1;                                   // first row of A22 (inside the top tile)
-    {
-        // opt-in (round-2 candidate, not yet run), read per call
-        if (switch_value(SW_PANEL_SKINNY) != 0 && w1 <= 64 && n2 <= 64) {
-            SB_TRY(launch_panel_update_skinny<T>(x.stack, nb, x.m_p, r0, c0, w1, cc, n2, x.s));
-            x.pt->end(x.s);
-            return SB200_OK;
-        }
-    }
     const int top_rows = std::min(nb, x.m_p) - r0;
     if (top_rows > 0) {
         GemmParamsT<T> p{};
@@ -774,8 +457,7 @@ static int getrf_panel_v1(T* const* stack, T* tile0, int ntile, int nb, int m_p,
         const int G = int(ceil_div(active, rows_per));
         BaseArgs<T> a{stack, nb, m_p, c0, w, rows_per, piv_tile, piv_off,
                       reinterpret_cast<T*>(ps.gval), ps.grow, reinterpret_cast<T*>(ps.gcand),
-                      reinterpret_cast<T*>(ps.gdiag), dinfo, info_base, rowmap, 0, ps.use_bar ? ps.bar : nullptr};
-        if (ps.use_bar) CUDA_TRY(cudaMemsetAsync(ps.bar, 0, sizeof(unsigned), s));
+                      reinterpret_cast<T*>(ps.gdiag), dinfo, info_base, rowmap, 0, nullptr};
         const size_t smem = size_t(w) * (rows_per | 1) * sizeof(T);
         pt.begin("pnl_base", s);
         SB_TRY(launch_base<T>(a, G, smem, ps, s));
@@ -881,7 +563,7 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
             tbl[size_t(i + j * mt)] = A.tile_as<T>(i, j);
             tblT[size_t(j + i * nt)] = A.tile_as<T>(i, j);
         }
-    // opt-in (SB200_GEMM_BT=1, double, not the tcgen05 path; round-2 candidate, not yet run): the row U(k, k+2:) is
+    // SB200_GEMM_BT (default 1, measured r2a; double, not the tcgen05 path): the row U(k, k+2:) is
     // transposed once per step after its solve, so that the trailing update runs as 'N','T' (both operands staged by TMA
     // bulk copies: the variant of the potrf trailing update, 0.91 of the DMMA peak) instead of 'N','N' (K-major B through
     // 16-byte cp.async; 0.80 measured here).  Same products in the same order: bitwise the same factor.
@@ -1137,7 +819,7 @@ using namespace sb200;
 extern "C" {
 
 /* LU without pivoting (slate::getrf_nopiv, src/getrf_nopiv.cc): the getrf drivers with the pivot search switched off.
- * STATUS: written after round 1's GPU budget was spent, not yet run (guarded test). */
+ * STATUS: validated on B200 in round 2 (1-, 2- and 8-GPU runs, profiles/r02*). */
 static int getrf_nopiv_any(sb200_matrix_t h, int64_t* info, bool is_float)
 {
     if (! h) return SB200_EINVAL;

@@ -548,6 +548,14 @@ getrf_base_v4_kernel(const V3Args<T> a)
 
 } // namespace
 
+// SB200_PANEL_V4=0: rows in shared memory (the fallback for panels taller than (#SMs - NWIDE) x 512) for every panel;
+// read per call so that a test can switch it
+static bool v4_enabled()
+{
+    const char* e = getenv("SB200_PANEL_V4");
+    return ! e || atoi(e) != 0;
+}
+
 size_t base_v3_scratch_bytes(int max_ctas)
 {
     return (size_t(PW) * max_ctas * V3_REC + size_t(PW) * 2 * PW + PW) * sizeof(unsigned long long);
@@ -575,8 +583,7 @@ int launch_base_v3(T* const* stack, int nb, int m_p, int c0, int w, int kw, int6
 {
     const int active = m_p - c0;
     const int ctas = ps.max_ctas - V3_NWIDE;
-    static const int v4_sel = [] { const char* e = getenv("SB200_PANEL_V4"); return e ? atoi(e) : 1; }();
-    const bool v4 = v4_sel != 0 && active <= ctas * V4_THREADS;     // register-resident rows: <= 512 rows per CTA
+    const bool v4 = v4_enabled() && active <= ctas * V4_THREADS;    // register-resident rows: <= 512 rows per CTA
     int rows_per = v4 ? V4_THREADS : std::max(int(ceil_div(active, ctas)), std::min(active, PROWS_MAX));
     rows_per = std::max(rows_per, PW);
     if (rows_per > PROWS_MAX) return SB200_ENOTSUP;
@@ -626,9 +633,9 @@ template int launch_base_v3<float>(float* const*, int, int, int, int, int, int64
 // can the block [c0, c0 + w) of an m_p-row panel take its update by the previous 32-column block inside its own launch?
 bool base_v3_can_fuse(const PanelScratch& ps, int m_p, int c0, int w1, int w)
 {
-    static const int v4_sel = [] { const char* e = getenv("SB200_PANEL_V4"); return e ? atoi(e) : 1; }();
-    static const int fuse_sel = [] { const char* e = getenv("SB200_PANEL_FUSE"); return e ? atoi(e) : 1; }();
-    return ps.use_v3 && v4_sel != 0 && fuse_sel != 0 && w1 == PW && w >= 1 && w <= PW
+    const char* e = getenv("SB200_PANEL_FUSE");
+    const bool fuse = ! e || atoi(e) != 0;
+    return ps.use_v3 && v4_enabled() && fuse && w1 == PW && w >= 1 && w <= PW
         && (m_p - c0) <= (ps.max_ctas - V3_NWIDE) * V4_THREADS && (m_p - c0) >= 1;
 }
 

@@ -27,7 +27,7 @@
 // the grid; with use_tc05 its trailing / lookahead GEMMs run on the tcgen05 FP32-emulated kernel, the panel
 // workspace tiles (A role) and the U slots (B role) being split-packed once per step.
 // STATUS of T = float: validated on ONE GPU through the test hook SB200_GETRF_DIST=1 (the p x q algorithm minus the
-// NCCL calls: FP32 LU tests with and without the tcgen05 update, gesv_mixed on top of it); not yet run on a grid.
+// NCCL calls) and on 1x2, 2x1 and 2x4 grids (scratch/mgpu_check.py: gesv_mixed; profiles/r02m2_*, r02g8_*).
 #include "runtime_internal.hh"
 #include "getrf_internal.hh"
 #include <algorithm>
@@ -179,7 +179,7 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
     SB_TRY(pws.alloc(size_t(2) * mt * te * sizeof(T)));
     SB_TRY(uws.alloc(size_t(std::max(nt_loc, 1)) * te * sizeof(T)));
     SB_TRY(ula.alloc(size_t(te) * sizeof(T)));
-    // opt-in (SB200_GEMM_BT=1, double, not the tcgen05 path; round-2 candidate, not yet run): transposed copies of the U
+    // SB200_GEMM_BT (default 1; double, not the tcgen05 path): transposed copies of the U
     // slots, written once per step after the row solve, so that the trailing update runs as 'N','T' (see getrf.cu)
     bool use_bt = false;
     if constexpr (std::is_same<T, double>::value) {

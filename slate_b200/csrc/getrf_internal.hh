@@ -13,16 +13,11 @@ constexpr int V3_NWIDE = 4;       // interchange CTAs of the one-round base kern
 struct PanelScratch {
     double* gval = nullptr; int* grow = nullptr; double* gcand = nullptr; double* gdiag = nullptr;
     double* W = nullptr;            // trsm workspace of the panel stream
-    unsigned* bar = nullptr;        // arrival counter of the opt-in hand-rolled grid barrier (SB200_PANEL_BARRIER=1)
-    bool use_bar = false;
-    unsigned long long* ll = nullptr;   // exchange buffers of the opt-in flag-in-data base kernel (SB200_PANEL_LL=1)
-    unsigned gen_base = 0;              // generation tag of the next launch's first column, minus 1
-    bool use_ll = false;
+    unsigned* bar = nullptr;
     bool nopiv = false;                 // getrf_nopiv: base kernel without the pivot search
     unsigned long long* v3_buf = nullptr;   // per-column exchange records of getrf_base_v3_kernel (getrf_base_v3.cu)
     unsigned v3_gen = 0;
     bool use_v3 = false;
-    size_t ll_bytes = 0;
     int max_ctas = 0;
     void* raw = nullptr;
     int init();

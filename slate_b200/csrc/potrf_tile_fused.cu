@@ -1,6 +1,7 @@
 // potrf_tile_fused.cu -- the lower Cholesky of ONE diagonal tile (n <= 1024) in ONE launch.
-// OPT-IN (SB200_TILE_FUSED=1 | 2); round-2 candidate written after round 1's GPU budget was spent: compiled,
-// desk-checked, NOT yet run on a GPU.  The default path (potrf_tile_lower in factor_small.cu) is unchanged.
+// Taken by the potrf driver when the chain runs on its own SM partition (sm_partition.cu: 0.69 ms per nb = 512 tile
+// against 1.1 ms for the launch chain of factor_small.cu there; on an idle whole device the launch chain wins, 0.56
+// against 0.66 ms), or with SB200_TILE_FUSED=1 | 2.  Validated on B200 in round 2 (tests/test_zzz_gpu_round2_candidates.py).
 //
 // Why (profiles/r01e_launches_potrf_n2048_per_grid.txt): the diagonal tile of every potrf
 // step (reference: internal::potrf<Devices> -> cusolverDn?potrf, src/internal/internal_potrf.cc:57-81) is
@@ -274,7 +275,7 @@ potrf_tile_fused_kernel(R* __restrict__ A, int lda, int n, int* __restrict__ inf
 }
 
 // ---------------------------------------------------------------------------------------------
-// Panel solve of the Cholesky step in ONE launch (opt-in, SB200_TRSM_FUSED=1; round-2 candidate, not yet run):
+// Panel solve of the Cholesky step in ONE launch (SB200_TRSM_FUSED bit 0, on by default):
 //   B_t <- alpha B_t L^{-T}      (Right, Lower, Trans, NonUnit;  reference: internal::trsm<Devices>,
 //                                 src/internal/internal_trsm.cc:132-262 -> cublas?trsmBatched)
 // The rows of B are independent, so one CTA takes 64 rows of one B tile through the whole block substitution
@@ -349,7 +350,7 @@ __device__ __forceinline__ void load_block_t(R* __restrict__ dst, const R* src, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Row solve of the LU step in ONE launch (opt-in, SB200_TRSM_FUSED bit 1; round-2 candidate, not yet run):
+// Row solve of the LU step in ONE launch (SB200_TRSM_FUSED bit 1, on by default):
 //   B_t <- alpha L^{-1} B_t      (Left, Lower, NoTrans, Unit or NonUnit: the diagonal only enters through W)
 // The columns of B are independent: one CTA takes 64 columns of one B tile through
 //   for j = 0 .. nblk-1:   X_j = W_j (alpha B_j - sum_{c<j} L(j,c) X_c)
@@ -403,7 +404,7 @@ trsm_lln_fused_kernel(int na, int n, R alpha, const R* __restrict__ Tm, int ldt,
 
 // ---------------------------------------------------------------------------------------------
 // Left / Lower / NoTrans solve with a SMALL triangle (na <= 64) by direct substitution, one launch
-// (opt-in, SB200_TRSM_FUSED bit 2; round-2 candidate, not yet run): the U12 = L11^-1 A12 steps inside the recursive
+// (SB200_TRSM_FUSED bit 2, on by default): the U12 = L11^-1 A12 steps inside the recursive
 // LU panel (w1 = 32 or 64; 12 of the 15 updates of an nb = 512 panel) are today an inversion kernel with a 64-step
 // dependent chain (~35 us) plus a GEMM launch.  Here: L and a 64-column slab of B in shared memory, axpy-form
 // substitution with rolled loops on 256 threads (one barrier per row of the triangle, two if the diagonal is not unit).

@@ -540,7 +540,7 @@ int gemm_driver(T alpha, Matrix& A, Matrix& B, T beta, Matrix& C)
         return wsB.as<T>() + ((k & 1) * C.nt_loc + (j - g.pcol) / g.q) * te;
     };
 
-    // opt-in (SB200_GEMM_BT=1, double only; round-2 candidate, not yet run): the B row panel of every step is transposed
+    // SB200_GEMM_BT (default 1, double only; measured r2a: 30.5 -> 35.3 TFLOP/s): the B row panel of every step is transposed
     // once (tile kernels, HBM-bound, ~50 us per step) so that the multiply runs as 'N','T' -- both operands staged by TMA
     // bulk copies, the variant the potrf trailing update runs at 0.91 of the DMMA peak -- instead of 'N','N', whose
     // K-major B operand goes through 16-byte cp.async (0.85 measured for dgemm).  Same products in the same order:
@@ -737,7 +737,7 @@ int herk_driver(typename RealOf<T>::type alpha, Matrix& A, typename RealOf<T>::t
 // (diagonal tiles triangle-masked; for complex types the diagonal is forced real after each launch, which only drops
 // imaginary parts that cancel between the two products).
 // STATUS: written after round 1's GPU budget was spent; compiled, pinned on the CPU side (oracle vs the reference's
-// golden output), NOT yet run on a GPU (guarded test in tests/test_zzz_gpu_round2_candidates.py).
+// golden output); validated on B200 in round 2 (1-, 2- and 8-GPU runs, profiles/r02*).
 // ------------------------------------------------------------------------------------------
 template <typename T>
 int her2k_driver(T alpha, Matrix& A, Matrix& B, typename RealOf<T>::type beta, Matrix& C)
@@ -824,7 +824,7 @@ int her2k_driver(T alpha, Matrix& A, Matrix& B, typename RealOf<T>::type beta, M
 // internal_syr2k.cc).  Same skeleton as herk_driver / her2k_driver: 'N','T' products, diagonal tiles triangle-masked,
 // the diagonal stays complex.  B == nullptr selects syrk.  SURVEY section 8(f) item 3.
 // STATUS: written after round 1's GPU budget was spent; oracle pinned to the reference's golden output on the CPU
-// side, NOT yet run on a GPU (guarded test).
+// side; validated on B200 in round 2 (1-, 2- and 8-GPU runs, profiles/r02*).
 // ------------------------------------------------------------------------------------------
 template <typename T>
 int sym_rank_update_driver(T alpha, Matrix& A, Matrix* B, T beta, Matrix& C)

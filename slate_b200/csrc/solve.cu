@@ -415,7 +415,7 @@ int hemm_left_lower(T alpha, Matrix& A, Matrix& X, T beta, Matrix& Rm, cudaStrea
 // symm, Side::Left, lower storage: R = alpha A X + beta R with A (complex-)SYMMETRIC (src/symm.cc, Left/Lower case):
 // hemm_left_lower without the conjugation (tiles above the diagonal are plain transposes, the diagonal stays complex).
 // SURVEY section 8(f) item 3.  STATUS: written after round 1's GPU budget was spent; oracle pinned to the reference's
-// golden output on the CPU side, NOT yet run on a GPU (guarded test).  1 x 1 grid as hemm.
+// golden output on the CPU side; validated on B200 in round 2 (1-, 2- and 8-GPU runs, profiles/r02*).  1 x 1 grid as hemm.
 // ------------------------------------------------------------------------------------------
 template <typename T>
 int symm_left_lower(T alpha, Matrix& A, Matrix& X, T beta, Matrix& Rm, cudaStream_t s)
@@ -477,7 +477,7 @@ int symm_left_lower(T alpha, Matrix& A, Matrix& X, T beta, Matrix& Rm, cudaStrea
 //     B(i, :) += alpha A(i, k) B(k, :)   for i > k        (one batched launch; B(k, :) is still the original block row)
 //     B(k, :)  = alpha tril(A(k, k)) B(k, :)              (through a one-block-row workspace: the tile product cannot alias)
 // SURVEY section 8(f) item 3.  STATUS: written after round 1's GPU budget was spent; oracle pinned to the reference's
-// golden output on the CPU side, NOT yet run on a GPU (guarded test).  1 x 1 grid; other side / uplo / op: ENOTSUP.
+// golden output on the CPU side; validated on B200 in round 2 (1-, 2- and 8-GPU runs, profiles/r02*).  1 x 1 grid; other side / uplo / op: ENOTSUP.
 // ------------------------------------------------------------------------------------------
 template <typename T>
 int trmm_left_lower(T alpha, Matrix& A, Matrix& B, bool unit, cudaStream_t s)

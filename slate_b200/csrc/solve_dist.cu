@@ -15,9 +15,10 @@
 // Per step: 2 small NCCL collectives; every factor tile is read exactly once per sweep, where it lives.
 // The residual R = B - A X works the same way (local products into a replicated accumulator, one all-reduce).
 //
-// STATUS: written in round 1 after the GPU budget of the round was spent -- compiled, NOT yet run on a p x q
-// grid.  Reached only when the grid has more than one rank (the 1 x 1 path in solve.cu
-// is the validated one); SB200_DIST_SOLVE=0 restores SB200_ENOTSUP.
+// STATUS: validated in round 2 on 1x2, 2x1 and 2x4 grids (scratch/mgpu_check.py: potrs, posv_mixed, gesv_mixed against
+// the oracle; profiles/r02m2_mgpu_check_2gpu.log, r02g8_mgpu_check_2x4.log) and through the one-rank hook
+// SB200_DIST_SOLVE=2 (tests/test_zzz_gpu_dist_solve.py); dposv_mixed / dgesv_mixed at n = 65536 on 8 GPUs:
+// profiles/r02g8_bench_{posv,gesv}_mixed_8gpu.json.  SB200_DIST_SOLVE=0 restores SB200_ENOTSUP on grids.
 #include "runtime_internal.hh"
 #include "getrf_internal.hh"
 #include <algorithm>

@@ -9,18 +9,13 @@
 * `potrf(A, in_local=..., out_local=...)` -- input AND output stream between pinned host memory and the device in chunks
   of block columns while the factorisation runs (`sb200_potrf_stream_*`, csrc/runtime.cu): bitwise the default factor.
 
-* SB200_PANEL_LL=1 -- LU panel base kernel whose per-column exchange (candidates, diagonal row, winner's row) travels as
-  {data | generation tag} 8-byte words instead of stores + fence + grid barrier (csrc/getrf.cu, getrf_base_ll_kernel):
-  identical pivots and factors.
+* the LU base-block kernels of csrc/getrf_base_v3.cu (per-column exchange as {data | generation tag} 8-byte words, rows
+  in registers, 32-column updates folded into the next launch) against their fallbacks: identical pivots.
 
-* SB200_DIAG_MW=1|2 -- multi-warp shared-memory versions of the 64 x 64 diagonal-block Cholesky / triangular inverse
-  (csrc/diag64.cuh; the register kernels run at 15-19 cycles per instruction), behind every potrf tile and every trsm.
+* the 64 x 64 diagonal-block Cholesky with one rsqrt per column (default) and in the divided form (SB200_DIAG_RSQRT=0).
 
 * SB200_GEMM_BT=1 -- dgemm (SUMMA) with the B row panel transposed once per step so that the multiply runs as 'N','T'
   (both operands through TMA bulk copies): bitwise the default C.
-
-* SB200_PANEL_SKINNY=1 -- the w1, n2 <= 64 updates inside the recursive LU panel as ONE row-per-thread launch over the
-  tile stack instead of three tile-GEMM launches (csrc/getrf.cu, panel_update_skinny_kernel).
 
 * `her2k`: C = alpha A B^H + conj(alpha) B A^H + beta C on the herk skeleton (two batched launches
   per step), against the reference's golden output and the oracle.
@@ -265,12 +260,27 @@ def test_potrf_streaming_reports_info(sl):
     assert sl.potrf(B, in_local=hin) == 701
 
 
+# LU base-block kernels (csrc/getrf_base_v3.cu): the default is the register-resident kernel with the 32-column updates
+# folded into the next launch; the others are its fallbacks (tall panels, getrf_nopiv, SB200_PANEL=1) and must give the
+# same pivots and the same factor up to rounding.
+BASE_VARIANTS = {"default": {}, "no_fused_update": {"SB200_PANEL_FUSE": "0"}, "shared_memory_rows": {"SB200_PANEL_V4": "0"},
+                 "cooperative_barrier": {"SB200_PANEL_V3": "0"}}
+
+
+def _set_variant(monkeypatch, variant):
+    for k in ("SB200_PANEL_FUSE", "SB200_PANEL_V4", "SB200_PANEL_V3"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in BASE_VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+
+
+@pytest.mark.parametrize("variant", list(BASE_VARIANTS))
 @pytest.mark.parametrize("dist", ["0", "1"])
 @pytest.mark.parametrize("panel", ["1", "2"])
 @pytest.mark.parametrize("m,n,nb", [(1024, 1024, 256), (700, 700, 128), (2048, 2048, 512), (700, 300, 128), (300, 700, 128),
-                                    (1100, 1100, 512)])
-def test_getrf_ll_panel_identical_pivots(sl, m, n, nb, panel, dist, monkeypatch):
-    monkeypatch.setenv("SB200_PANEL_LL", "1")
+                                    (1100, 1100, 512), (1000, 1000, 100)])
+def test_getrf_base_kernel_variants_identical_pivots(sl, m, n, nb, panel, dist, variant, monkeypatch):
+    _set_variant(monkeypatch, variant)
     monkeypatch.setenv("SB200_PANEL", panel)
     monkeypatch.setenv("SB200_GETRF_DIST", dist)
     A = sl.Matrix(m, n, nb).generate("rand", 42)
@@ -282,9 +292,10 @@ def test_getrf_ll_panel_identical_pivots(sl, m, n, nb, panel, dist, monkeypatch)
     assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
 
 
+@pytest.mark.parametrize("variant", list(BASE_VARIANTS))
 @pytest.mark.parametrize("panel", ["1", "2"])
-def test_getrf_ll_panel_zero_column_and_ties(sl, panel, monkeypatch):
-    monkeypatch.setenv("SB200_PANEL_LL", "1")
+def test_getrf_base_kernel_variants_zero_column_and_ties(sl, panel, variant, monkeypatch):
+    _set_variant(monkeypatch, variant)
     monkeypatch.setenv("SB200_PANEL", panel)
     n, nb = 256, 64
     A0 = o.generate("rand", n, n, 3); A0[:, 100] = 0.0
@@ -301,24 +312,42 @@ def test_getrf_ll_panel_zero_column_and_ties(sl, panel, monkeypatch):
     assert piv == pivo
 
 
-def test_getrf_ll_panel_tall_many_ctas_and_same_bits_as_default(sl, monkeypatch):
-    """m_p = 8192 rows: 11 + 1 CTAs exchange through the tagged words; the factor must be BITWISE the default kernel's
-    (same pivots => same arithmetic in the same order)."""
-    import torch
+def test_getrf_base_kernel_variants_nan_is_never_a_pivot_candidate(sl, monkeypatch):
+    """a NaN below the diagonal is skipped by the max search (the reference's `abs > max` is false for it), a NaN ON the
+    diagonal keeps the diagonal (every comparison with it is false): same pivots from every kernel"""
+    n, nb = 256, 128
+    A0 = o.generate("rand", n, n, 5)
+    A0[200, 3] = np.nan
+    pivs = []
+    for variant in BASE_VARIANTS:
+        _set_variant(monkeypatch, variant)
+        A = sl.Matrix(n, n, nb); A.from_host(np.asfortranarray(A0))
+        piv, _ = sl.getrf(A)
+        pivs.append(piv[:4])
+    assert all(p == pivs[0] for p in pivs)
+    assert all(int(t) * nb + int(off) != 200 for (t, off) in pivs[0][:4])
+
+
+def test_getrf_base_kernel_variants_tall_panel_many_ctas(sl, monkeypatch):
+    """m_p = 8192 rows: 16 + 4 CTAs exchange through the tagged words; every variant gives the default's pivots and its
+    factor up to rounding (the folded updates sum in a different order than the tile GEMM)"""
     n, nb = 8192, 512
-    A = sl.Matrix(n, n, nb).generate("rand", 42)
-    piv0, info0 = sl.getrf(A)
-    h0 = torch.empty(A.local_tiles * nb * nb, dtype=torch.float64).pin_memory(); A.to_host_local(h0)
-    monkeypatch.setenv("SB200_PANEL_LL", "1")
-    B = sl.Matrix(n, n, nb).generate("rand", 42)
-    piv1, info1 = sl.getrf(B)
-    h1 = torch.empty(B.local_tiles * nb * nb, dtype=torch.float64).pin_memory(); B.to_host_local(h1)
-    assert info0 == info1 == 0 and piv0 == piv1
-    assert torch.equal(h0.view(torch.uint8), h1.view(torch.uint8))
+    res = {}
+    for variant in BASE_VARIANTS:
+        _set_variant(monkeypatch, variant)
+        A = sl.Matrix(n, n, nb).generate("rand", 42)
+        piv, info = sl.getrf(A)
+        assert info == 0
+        res[variant] = (piv, A.to_host())
+    p0, a0 = res["default"]
+    for variant, (p1, a1) in res.items():
+        assert p1 == p0, variant
+        assert np.abs(a1 - a0).max() <= 1e-12 * np.abs(a0).max(), variant
 
 
-def test_gesv_mixed_with_ll_panel(sl, monkeypatch):
-    monkeypatch.setenv("SB200_PANEL_LL", "1")
+@pytest.mark.parametrize("variant", ["default", "shared_memory_rows"])
+def test_gesv_mixed_with_base_kernel_variants(sl, monkeypatch, variant):
+    _set_variant(monkeypatch, variant)
     n, nb = 2048, 512
     A = sl.Matrix(n, n, nb).generate("rand", 42)
     B = sl.Matrix(n, 10, nb).generate("rand", 43)
@@ -403,11 +432,12 @@ def test_permute_rows_other_types(t, layout):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("rsqrt", ["1", "0"])
 @pytest.mark.parametrize("t", ["d", "s"])
 @pytest.mark.parametrize("n", [37, 64, 200, 512, 130])
-def test_diag_mw_potrf_tile(monkeypatch, mode, t, n):
-    monkeypatch.setenv("SB200_DIAG_MW", mode)
+def test_potrf_tile_diag_block_forms(monkeypatch, rsqrt, t, n):
+    """the 64 x 64 diagonal-block Cholesky with one rsqrt per column (default) and with division + sqrt"""
+    monkeypatch.setenv("SB200_DIAG_RSQRT", rsqrt)
     rng = np.random.default_rng(5)
     G = rng.random((n, n))
     A = (G @ G.T + n * np.eye(n)).astype(np.float64 if t == "d" else np.float32)
@@ -419,58 +449,12 @@ def test_diag_mw_potrf_tile(monkeypatch, mode, t, n):
     assert np.array_equal(np.triu(out, 1), np.triu(A, 1))
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_diag_mw_potrf_tile_info(monkeypatch, mode):
-    monkeypatch.setenv("SB200_DIAG_MW", mode)
+@pytest.mark.parametrize("rsqrt", ["1", "0"])
+def test_potrf_tile_diag_block_forms_info(monkeypatch, rsqrt):
+    monkeypatch.setenv("SB200_DIAG_RSQRT", rsqrt)
     A = np.eye(128); A[70, 70] = -1.0
     _, info = _potrf_tile(A, 128)
     assert info == 71
-
-
-@pytest.mark.parametrize("t", ["d", "s"])
-@pytest.mark.parametrize("side,uplo,op,diag", [("R", "L", "T", "N"), ("L", "L", "N", "U"), ("L", "U", "N", "N"), ("R", "U", "N", "N"),
-                                               ("L", "L", "T", "N"), ("R", "L", "N", "U"), ("L", "U", "T", "U")])
-@pytest.mark.parametrize("m,n", [(200, 130), (512, 512), (64, 37)])
-def test_diag_mw_trsm_all_variants(monkeypatch, t, side, uplo, op, diag, m, n):
-    """every trsm goes through the inverted diagonal blocks: the multi-warp inverse serves lower / upper, unit / non-unit"""
-    from tests.gpu_util import DevTiles, fn, scal, stream, rng_tiles, NP, SC, c_int, c_i64, c_ptr
-    monkeypatch.setenv("SB200_DIAG_MW", "1")
-    rng = np.random.default_rng(4)
-    batch = 2
-    na = m if side == "L" else n
-    T = (rng.random((na, na)) / na + np.eye(na) * (1 + rng.random(na))).astype(NP[t])
-    B = rng_tiles(rng, batch, m, n, t)
-    alpha = 0.7
-    ref = [o.trsm_tile(side, uplo, op, diag, alpha, T.astype(np.float64), b.astype(np.float64)) for b in B]
-    dT, dB = DevTiles([T]), DevTiles(B)
-    f = fn(f"sb200_trsm_batched_{t}", [c_int] * 5 + [c_i64, c_i64, SC[t], c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr])
-    assert f(ord("C"), ord(side), ord(uplo), ord(op), ord(diag), m, n, scal(t, alpha), dT.t[0].data_ptr(), na,
-             dB.p, m, batch, None, stream()) == 0
-    eps = EPS if t == "d" else float(np.finfo(np.float32).eps)
-    for x, r in zip(dB.get(), ref):
-        assert np.abs(x - r).max() <= 200 * eps * np.abs(r).max()
-
-
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_diag_mw_drivers(sl, monkeypatch, mode):
-    monkeypatch.setenv("SB200_DIAG_MW", mode)
-    n, nb = 2048, 512
-    A = sl.HermitianMatrix(n, nb).generate("rand_dominant", 11)
-    assert sl.potrf(A) == 0
-    L = np.tril(A.to_host())
-    G = o.generate("rand_dominant", n, n, 11)
-    Af = np.tril(G) + np.tril(G, -1).T
-    Lo, info = o.potrf(Af, nb)
-    assert np.abs(L - Lo).max() <= 64 * EPS * np.abs(Lo).max()
-    B = sl.Matrix(n, 10, nb).generate("rand", 43)
-    sl.potrs(A, B)
-    Xo = o.potrs(Lo, o.generate("rand", n, 10, 43), nb)
-    assert np.abs(B.to_host() - Xo).max() <= 200 * EPS * np.abs(Xo).max()
-    M = sl.Matrix(n, n, nb).generate("rand", 42)
-    piv, info = sl.getrf(M)
-    LUo, pivo, info_o = o.getrf(o.generate("rand", n, n, 42), nb, 32)
-    assert info == info_o == 0 and piv == pivo
-    assert np.abs(M.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
 
 
 @pytest.mark.parametrize("m,n,k,nb", [(1024, 1024, 1024, 256), (700, 900, 500, 128), (2048, 1536, 1024, 512), (300, 200, 100, 512)])
@@ -509,31 +493,6 @@ def test_getrf_transposed_u_row_is_bitwise_the_default(sl, monkeypatch, m, n, nb
     p1, i1, a1 = run()
     assert i0 == i1 == 0 and p0 == p1
     assert np.array_equal(a0, a1)
-
-
-@pytest.mark.parametrize("t", ["d", "s"])
-@pytest.mark.parametrize("dist", ["0", "1"])
-@pytest.mark.parametrize("m,n,nb", [(2048, 2048, 512), (1100, 1100, 256), (700, 300, 128), (300, 700, 128), (8192, 512, 512)])
-def test_getrf_skinny_panel_update(sl, monkeypatch, m, n, nb, dist, t):
-    if t == "s" and dist == "1":
-        pytest.skip("the FP32 p x q driver is covered through gesv_mixed")
-    monkeypatch.setenv("SB200_GETRF_DIST", dist)
-
-    def run():
-        A = sl.Matrix(m, n, nb, dtype=t).generate("rand", 42)
-        piv, info = sl.getrf(A)
-        return piv, info, A.to_host()
-
-    monkeypatch.delenv("SB200_PANEL_SKINNY", raising=False)
-    p0, i0, a0 = run()
-    monkeypatch.setenv("SB200_PANEL_SKINNY", "1")
-    p1, i1, a1 = run()
-    assert i0 == i1 == 0 and p0 == p1, "pivots differ from the default path"
-    tol = 1e-13 if t == "d" else 1e-5
-    assert np.abs(a1.astype(np.float64) - a0.astype(np.float64)).max() <= tol * np.abs(a0).max()
-    if t == "d" and m * n <= 2048 * 2048:
-        LUo, pivo, info_o = o.getrf(o.generate("rand", m, n, 42), nb, 32)
-        assert p1 == pivo and np.abs(a1 - LUo).max() <= 1e-11 * np.abs(LUo).max()
 
 
 @pytest.mark.parametrize("t", ["d", "z", "s", "c"])
