@@ -323,9 +323,9 @@ def test_getrf_base_kernel_variants_nan_is_never_a_pivot_candidate(sl, monkeypat
         _set_variant(monkeypatch, variant)
         A = sl.Matrix(n, n, nb); A.from_host(np.asfortranarray(A0))
         piv, _ = sl.getrf(A)
-        pivs.append(piv[:4])
+        pivs.append(piv[0][:8])                                  # first panel, first columns
     assert all(p == pivs[0] for p in pivs)
-    assert all(int(t) * nb + int(off) != 200 for (t, off) in pivs[0][:4])
+    assert all(t * nb + off != 200 for (t, off) in pivs[0][:4])
 
 
 def test_getrf_base_kernel_variants_tall_panel_many_ctas(sl, monkeypatch):
@@ -342,7 +342,7 @@ def test_getrf_base_kernel_variants_tall_panel_many_ctas(sl, monkeypatch):
     p0, a0 = res["default"]
     for variant, (p1, a1) in res.items():
         assert p1 == p0, variant
-        assert np.abs(a1 - a0).max() <= 1e-12 * np.abs(a0).max(), variant
+        assert np.abs(a1 - a0).max() <= 1e-11 * np.abs(a0).max(), variant
 
 
 @pytest.mark.parametrize("variant", ["default", "shared_memory_rows"])
