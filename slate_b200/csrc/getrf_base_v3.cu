@@ -546,6 +546,14 @@ getrf_base_v4_kernel(const V3Args<T> a)
         }
 }
 
+
+// (A persistent variant -- up to 8 consecutive 32-column blocks in ONE cooperative launch, left-looking between the
+// blocks: every CTA recomputes U12 = L11^-1 A12 and updates its rows with FP64 FMAs -- was written, validated (244 parity
+// tests) and measured in round 2, and deleted: pnl_base + pnl_trsm + pnl_gemm = 273 / 280 / 250 / 268 ms at n = 32768 for
+// 1 / 2 / 4 / 8 blocks per launch, dgetrf 822 / 831 / 830 / 847 ms.  Next to the trailing update a column costs 1.5 us
+// more than on an idle device whatever the launch structure -- the exchange's L2 round trips compete with the GEMM's
+// traffic -- and the launch itself only ~20 us; profiles/r02l_persistent_lu_kernel_negative_result.txt.)
+
 } // namespace
 
 // SB200_PANEL_V4=0: rows in shared memory (the fallback for panels taller than (#SMs - NWIDE) x 512) for every panel;
@@ -571,6 +579,7 @@ int base_v3_init()
                                       int(PW * (PROWS_MAX | 1) * sizeof(double))));
         CUDA_TRY(cudaFuncSetAttribute(getrf_base_v3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(PW * (PROWS_MAX | 1) * sizeof(float))));
+
         done[dev & 63] = true;
     }
     return SB200_OK;
@@ -638,5 +647,6 @@ bool base_v3_can_fuse(const PanelScratch& ps, int m_p, int c0, int w1, int w)
     return ps.use_v3 && v4_enabled() && fuse && w1 == PW && w >= 1 && w <= PW
         && (m_p - c0) <= (ps.max_ctas - V3_NWIDE) * V4_THREADS && (m_p - c0) >= 1;
 }
+
 
 } // namespace sb200
