@@ -492,6 +492,7 @@ int trmm_left_lower(T alpha, Matrix& A, Matrix& B, bool unit, cudaStream_t s)
     DevBuf dtri, wrow;
     SB_TRY(dtri.alloc(size_t(nt) * te * sizeof(T)));
     SB_TRY(wrow.alloc(size_t(ntB) * te * sizeof(T)));
+    CUDA_TRY(cudaMemset(wrow.p, 0, size_t(ntB) * te * sizeof(T)));      // whole tiles are copied back: ragged tiles' padding stays defined
     struct Step { std::vector<Batch> below, diag; };
     std::vector<Step> steps(static_cast<size_t>(nt));
     std::vector<const T*> diag_ptrs;
