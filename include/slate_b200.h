@@ -363,6 +363,10 @@ int sb200_fp64_peak_probe(int kind, int iters, int ctas_per_sm, double* d_scratc
  * cusolverDn?potrf (src/internal/internal_potrf.cc:57-81) -- gets c whole SMs of its own (CUDA green context) and
  * every other stream the remaining ones.  Reports the split the device grants; SB200_ENOTSUP if it cannot. */
 int sb200_sm_partition_probe(int chain_sms, int* sm_chain, int* sm_rest);
+/* The drivers keep their device workspaces (panel rings, pointer plans, scratch) in a grow-only per-device cache
+ * between calls -- the reference keeps its workspace tiles in the matrix's memory pool the same way
+ * (include/slate/internal/MatrixStorage.hh:483-520, Memory::alloc / free).  This frees every idle block. */
+int sb200_release_workspaces(void);
 
 /* ---------------------------------------------------------------------------
  * Round-1 widening of the host runtime: all four scalar types, herk, the solve path and the

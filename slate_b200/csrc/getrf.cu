@@ -257,6 +257,8 @@ getrf_base_kernel(const BaseArgs<T> a)
 // calling thread); read once per driver call by PanelScratch::init
 static thread_local bool g_getrf_nopiv = false;
 
+PanelScratch::~PanelScratch() { if (raw) ws_cache_put(raw); }
+
 int PanelScratch::init()
 {
     int dev = 0, sms = 0;
@@ -266,7 +268,8 @@ int PanelScratch::init()
     const size_t G = size_t(sms);
     const size_t v3_bytes = base_v3_scratch_bytes(sms);
     const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8 + 64 + 16 + v3_bytes;
-    CUDA_TRY(cudaMalloc(&raw, bytes));
+    raw = ws_cache_get(bytes);
+    if (! raw) return SB200_ENOMEM;
     char* p = static_cast<char*>(raw);
     gval = reinterpret_cast<double*>(p); p += 2 * G * 8;
     grow = reinterpret_cast<int*>(p);    p += 2 * G * 8;

@@ -159,7 +159,9 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
     if (use_tc05 && ! is_float) return SB200_EINVAL;
     using DBuf = DevBuf;
     const ncclDataType_t nccl_t = is_float ? ncclFloat : ncclDouble;
+    HostTimes htm("getrf_dist");
     CUDA_TRY(cudaDeviceSynchronize());
+    htm.mark("entry_sync");
     const int64_t mt = A.mt, nt = A.nt, nb = A.nb, te = A.tile_elems();
     const int p = g.p, q = g.q, prow = g.prow, pcol = g.pcol;
     const int ld = int(nb);
@@ -287,6 +289,7 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
     SB_TRY(planb.alloc(hp.size() * sizeof(void*)));
     void** dplan = planb.as<void*>();
 
+    htm.mark("plan_and_buffers");
     PanelScratch ps;
     SB_TRY(ps.init());
     cudaStream_t P = nullptr, T_ = nullptr;
@@ -397,6 +400,7 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
         CUDA_TRY(cudaMemcpyAsync(dplan, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, P));
         CUDA_TRY(cudaMemsetAsync(infob.p, 0, sizeof(int), P));
         CUDA_TRY(cudaStreamSynchronize(P));
+        htm.mark("scratch_streams_upload");
         CUDA_TRY(cudaEventRecord(t0, P));
         for (int64_t k = 0; k < kt; ++k) {
             const int kw = int(A.tile_nb(k));
@@ -523,10 +527,12 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
                 ph.end(P);
             }
         }
+        htm.mark("enqueue");
         CUDA_TRY(cudaStreamWaitEvent(P, T_done(kt - 1), 0));
         CUDA_TRY(cudaEventRecord(t1, P));
         CUDA_TRY(cudaStreamSynchronize(P));
         CUDA_TRY(cudaStreamSynchronize(T_));
+        htm.mark("sync");
         return SB200_OK;
     };
     int status = body();

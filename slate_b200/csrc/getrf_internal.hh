@@ -21,7 +21,7 @@ struct PanelScratch {
     int max_ctas = 0;
     void* raw = nullptr;
     int init();
-    ~PanelScratch() { if (raw) cudaFree(raw); }
+    ~PanelScratch();
 };
 
 // Factor the panel given as a stack of `ntile` tiles (device pointer array `stack`, nb x nb, ld = nb;

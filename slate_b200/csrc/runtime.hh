@@ -17,6 +17,8 @@
 //     src/gemmC.cc:89-196) becomes two CUDA streams (panel = high priority, trailing) ordered
 //     by events; the host never blocks inside the step loop.
 #pragma once
+#include <ctime>
+#include <utility>
 #include "common.cuh"
 #include <nccl.h>
 #include <vector>
@@ -92,6 +94,24 @@ template <> struct TypeChar<cuDoubleComplex> { static constexpr int value = 'z';
 // Optional per-phase device timing of a driver call (SB200_PHASES=1): event pairs around named
 // phases of the panel / trailing streams, summed per phase and printed to stderr as one JSON line
 // when the driver returns.  Used to find what the lookahead has to hide; off by default.
+// SB200_HOST_TIMES=1: host wall clock between marks of a driver call, one JSON line on stderr when the object dies
+// (i.e. after the driver's local buffers, streams and events have been released)
+struct HostTimes {
+    const char* what; bool on; double t0, last;
+    std::vector<std::pair<const char*, double>> marks;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    explicit HostTimes(const char* w) : what(w) { const char* e = getenv("SB200_HOST_TIMES"); on = e && atoi(e) != 0; t0 = last = on ? now() : 0; }
+    void mark(const char* name) { if (! on) return; const double t = now(); marks.push_back({name, t - last}); last = t; }
+    ~HostTimes()
+    {
+        if (! on) return;
+        const double t = now();
+        fprintf(stderr, "{\"sb200_host_ms\": \"%s\"", what);
+        for (auto& m : marks) fprintf(stderr, ", \"%s\": %.3f", m.first, m.second);
+        fprintf(stderr, ", \"teardown\": %.3f, \"total\": %.3f}\n", t - last, t - t0);
+    }
+};
+
 struct PhaseTimer {
     struct Rec { const char* name; cudaEvent_t a, b; };
     std::vector<Rec> recs;

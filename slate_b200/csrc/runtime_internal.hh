@@ -69,6 +69,13 @@ inline void batch_add(std::vector<Batch>& v, int m, int n, int k, int tri,
     v.push_back(std::move(b));
 }
 
+// Device workspaces of the drivers (panel rings, plan buffers, scratch) come from a grow-only per-device cache: a
+// driver call at n = 65536 spent 40-130 ms of host time in cudaMalloc / cudaFree of buffers it allocates again,
+// identically, at the next call (profiles/r02n_host_times_potrf_n65536.txt).  Every driver synchronises its streams
+// before it returns, so a block handed back is idle.  sb200_release_workspaces() frees the cache.  (sm_partition.cu)
+void* ws_cache_get(size_t bytes);
+void ws_cache_put(void* p);
+
 struct PlanBuffer {
     std::vector<const void*> host;
     void** dev = nullptr;
@@ -92,12 +99,13 @@ struct PlanBuffer {
     int upload(cudaStream_t s)
     {
         if (host.empty()) return SB200_OK;
-        CUDA_TRY(cudaMalloc(&dev, host.size() * sizeof(void*)));
+        dev = static_cast<void**>(ws_cache_get(host.size() * sizeof(void*)));
+        if (! dev) return SB200_ENOMEM;
         CUDA_TRY(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(void*), cudaMemcpyHostToDevice, s));
         return SB200_OK;
     }
     template <typename T> T* const* at(size_t off) const { return reinterpret_cast<T* const*>(dev + off); }
-    ~PlanBuffer() { if (dev) cudaFree(dev); }
+    ~PlanBuffer() { if (dev) ws_cache_put(dev); }
 };
 
 // one batched launch per shape class; herk != 0 forces the diagonal of triangle-masked complex tiles real
@@ -217,9 +225,9 @@ struct Streams {
 
 struct DevBuf {
     void* p = nullptr;
-    int alloc(size_t bytes) { CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 16)); return SB200_OK; }
+    int alloc(size_t bytes) { p = ws_cache_get(bytes ? bytes : 16); return p ? SB200_OK : SB200_ENOMEM; }
     template <typename T> T* as() const { return static_cast<T*>(p); }
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) ws_cache_put(p); }
 };
 
 // grouped root -> everybody broadcasts of contiguous ranges (runtime.cu); src is read on the root only

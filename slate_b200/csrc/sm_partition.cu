@@ -155,6 +155,61 @@ int Streams::hop(cudaStream_t from, cudaStream_t to)
     return SB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// grow-only cache of device workspaces (see runtime_internal.hh)
+namespace {
+struct WsBlock { void* p; size_t bytes; int device; bool busy; };
+std::mutex g_ws_mu;
+std::vector<WsBlock> g_ws;
+}
+
+void* ws_cache_get(size_t bytes)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    bytes = (bytes + 255) / 256 * 256;
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        WsBlock* best = nullptr;
+        for (auto& b : g_ws)          // best fit among the idle blocks of this device that are not wastefully large
+            if (! b.busy && b.device == dev && b.bytes >= bytes && b.bytes <= 2 * bytes + (size_t(1) << 20)
+                && (! best || b.bytes < best->bytes)) best = &b;
+        if (best) { best->busy = true; return best->p; }
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        sb200_release_workspaces();                  // idle blocks of other sizes may be what is in the way
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    g_ws.push_back({p, bytes, dev, true});
+    return p;
+}
+
+void ws_cache_put(void* p)
+{
+    // what cudaFree did implicitly and some callers (asynchronous solve-path helpers) rely on: nothing on the device
+    // still uses the block when it becomes available again.  A no-op after a driver (its streams are synchronised).
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    for (auto& b : g_ws)
+        if (b.p == p) { b.busy = false; return; }
+}
+
+extern "C" int sb200_release_workspaces(void)
+{
+    std::vector<void*> gone;
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        for (size_t i = 0; i < g_ws.size();)
+            if (! g_ws[i].busy) { gone.push_back(g_ws[i].p); g_ws[i] = g_ws.back(); g_ws.pop_back(); }
+            else ++i;
+    }
+    for (void* p : gone) cudaFree(p);
+    return SB200_OK;
+}
+
 extern "C" int sb200_sm_partition_probe(int chain_sms, int* sm_chain, int* sm_rest)
 {
     Partition* p = partition_for(chain_sms);

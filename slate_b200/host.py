@@ -504,7 +504,7 @@ def getrf(A: Matrix, opts: dict | None = None):
     check(_getrf[key](A._h, flat, ctypes.byref(o), ctypes.byref(info)), "getrf")
     piv = np.frombuffer(flat, dtype=np.int64)[: 2 * mn].reshape(-1, 2)
     nb = A.nb
-    pivots = [[(int(t), int(off)) for t, off in piv[k0:min(k0 + nb, mn)]] for k0 in range(0, mn, nb)]
+    pivots = [list(map(tuple, piv[k0:min(k0 + nb, mn)].tolist())) for k0 in range(0, mn, nb)]      # (tileIndex, elementOffset) ints
     return pivots, int(info.value)
 
 
