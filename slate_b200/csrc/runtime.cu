@@ -1051,10 +1051,20 @@ int sb200_grid_create(int p, int q, int rank, const void* nccl_unique_id, sb200_
         if (! nccl_unique_id) { delete h; return SB200_EINVAL; }
         ncclUniqueId id;
         memcpy(&id, nccl_unique_id, sizeof(id));
-        if (ncclCommInitRank(&g.world, p * q, id, rank) != ncclSuccess) { delete h; return SB200_ENCCL; }
-        if (ncclCommSplit(g.world, g.prow, g.pcol, &g.row_comm, nullptr) != ncclSuccess
-            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm, nullptr) != ncclSuccess
-            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm2, nullptr) != ncclSuccess) {
+        // NCCL's CTAs run next to the trailing update and take SMs from it for as long as a collective waits for its
+        // peers: on 8 GPUs the DMMA kernel ran at 0.77 of its peak with NCCL's default channel count and at 0.83 with 8
+        // (profiles/r02g8b_*).  The panel broadcasts are latency- and chain-bound, not bandwidth-bound: cap the CTAs.
+        // SB200_NCCL_MAX_CTAS=0 leaves NCCL's default.
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        {
+            const char* e = getenv("SB200_NCCL_MAX_CTAS");
+            const int m = e ? atoi(e) : SB200_NCCL_MAX_CTAS_DEFAULT;
+            if (m > 0) cfg.maxCTAs = m;
+        }
+        if (ncclCommInitRankConfig(&g.world, p * q, id, rank, &cfg) != ncclSuccess) { delete h; return SB200_ENCCL; }
+        if (ncclCommSplit(g.world, g.prow, g.pcol, &g.row_comm, &cfg) != ncclSuccess
+            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm, &cfg) != ncclSuccess
+            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm2, &cfg) != ncclSuccess) {
             delete h; return SB200_ENCCL;
         }
     }

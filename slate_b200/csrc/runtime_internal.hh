@@ -232,7 +232,8 @@ struct DevBuf {
 
 // grouped root -> everybody broadcasts of contiguous ranges (runtime.cu); src is read on the root only
 struct BcastItem { const void* src; void* dst; size_t bytes; int root; };
-constexpr int SB200_BCAST_DEFAULT = 0;
+constexpr int SB200_BCAST_DEFAULT = 1;          // scatter + all-gather: measured on 8 GPUs (r2g8b): dpotrf 428 -> 408 ms, dgetrf 1043 -> 1008 ms
+constexpr int SB200_NCCL_MAX_CTAS_DEFAULT = 8;
 int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s);
 
 // drivers (runtime.cu)
