@@ -98,8 +98,9 @@ struct PanelWs {
 // the root sends 1/N of the range to every rank, then ONE in-place ncclAllGather over NVSwitch completes it -- every
 // link carries 1/N of the bytes at a time and the all-gather is the collective NCCL runs through NVLS multicast.
 // Ranges below 4 MiB, and the < 16 N byte remainder that does not split evenly, stay plain broadcasts.
-int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s)
+int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s, ncclComm_t comm)
 {
+    if (! comm) comm = g.world;
     if (g.size() <= 1 || items.empty()) return SB200_OK;
     static const int mode = [] { const char* e = getenv("SB200_BCAST"); return e ? atoi(e) : SB200_BCAST_DEFAULT; }();
     static const size_t min_bytes = [] { const char* e = getenv("SB200_BCAST_MIN"); return e ? size_t(atoll(e)) : (size_t(4) << 20); }();
@@ -118,10 +119,10 @@ int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s)
             if (g.rank == it.root) {
                 for (int r = 0; r < N; ++r)
                     if (r != it.root)
-                        NCCL_TRY(ncclSend(static_cast<const char*>(it.src) + size_t(r) * c, c, ncclChar, r, g.world, s));
+                        NCCL_TRY(ncclSend(static_cast<const char*>(it.src) + size_t(r) * c, c, ncclChar, r, comm, s));
             }
             else
-                NCCL_TRY(ncclRecv(static_cast<char*>(it.dst) + size_t(g.rank) * c, c, ncclChar, it.root, g.world, s));
+                NCCL_TRY(ncclRecv(static_cast<char*>(it.dst) + size_t(g.rank) * c, c, ncclChar, it.root, comm, s));
         }
         NCCL_TRY(ncclGroupEnd());
     }
@@ -130,10 +131,10 @@ int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s)
         const size_t c = split(it);
         const char* src = static_cast<const char*>(g.rank == it.root ? it.src : it.dst);
         char* dst = static_cast<char*>(it.dst);
-        if (c > 0) NCCL_TRY(ncclAllGather(src + size_t(g.rank) * c, dst, c, ncclChar, g.world, s));
+        if (c > 0) NCCL_TRY(ncclAllGather(src + size_t(g.rank) * c, dst, c, ncclChar, comm, s));
         const size_t done = c * size_t(N);
         if (it.bytes > done)
-            NCCL_TRY(ncclBroadcast(src + done, dst + done, it.bytes - done, ncclChar, it.root, g.world, s));
+            NCCL_TRY(ncclBroadcast(src + done, dst + done, it.bytes - done, ncclChar, it.root, comm, s));
     }
     NCCL_TRY(ncclGroupEnd());
     return SB200_OK;
@@ -142,7 +143,8 @@ int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s)
 // every rank receives tiles (i, k), i >= i_first, of block column k of A: p ranges that are contiguous in their
 // root's pool (the reference's listBcast to a row+column rank set, widened to all ranks)
 template <typename T>
-static int bcast_block_column(Grid& g, Matrix& A, int64_t k, int64_t i_first, const PanelWs<T>& ws, cudaStream_t s)
+static int bcast_block_column(Grid& g, Matrix& A, int64_t k, int64_t i_first, const PanelWs<T>& ws, cudaStream_t s,
+                              ncclComm_t comm = nullptr)
 {
     const int64_t mt = A.mt, te = A.tile_elems();
     std::vector<BcastItem> items;
@@ -154,7 +156,7 @@ static int bcast_block_column(Grid& g, Matrix& A, int64_t k, int64_t i_first, co
         const T* src = (g.rank == root) ? A.tile_as<T>(i0, k) : ws.at(i0, k);
         items.push_back({src, ws.at(i0, k), size_t(cnt * te) * sizeof(T), root});
     }
-    return bcast_many(g, items, s);
+    return bcast_many(g, items, s, comm);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -425,7 +427,8 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
                 T* db = dbuf.as<T>() + (k & 1) * te;
                 if (in_col && g.p > 1) {
                     const T* src = (g.rank == owner) ? A.tile_as<T>(k, k) : db;
-                    NCCL_TRY(ncclBroadcast(src, db, size_t(te) * sizeof(T), ncclChar, int(k % g.p), g.col_comm, P));
+                    NCCL_TRY(ncclBroadcast(src, db, size_t(te) * sizeof(T), ncclChar, int(k % g.p),
+                                           g.col_comm_lo ? g.col_comm_lo : g.col_comm, P));
                     Lkk = db;
                 }
                 else if (in_col) Lkk = A.tile_as<T>(k, k);
@@ -450,7 +453,7 @@ int potrf_driver(Matrix& A, int64_t* info_out, bool use_tc05, void* host_out, co
             }
             // -- panel broadcast: every rank receives the whole factored block column
             ph.begin("panel_bcast", P);
-            if (multi) SB_TRY(bcast_block_column<T>(g, A, k, k + 1, pws, P));
+            if (multi) SB_TRY(bcast_block_column<T>(g, A, k, k + 1, pws, P, g.world_lo));
             ph.end(P);
             if (use_tc05) {
                 ph.begin("panel_pack", P);
@@ -1051,20 +1054,24 @@ int sb200_grid_create(int p, int q, int rank, const void* nccl_unique_id, sb200_
         if (! nccl_unique_id) { delete h; return SB200_EINVAL; }
         ncclUniqueId id;
         memcpy(&id, nccl_unique_id, sizeof(id));
-        // NCCL's CTAs run next to the trailing update and take SMs from it for as long as a collective waits for its
-        // peers: on 8 GPUs the DMMA kernel ran at 0.77 of its peak with NCCL's default channel count and at 0.83 with 8
-        // (profiles/r02g8b_*).  The panel broadcasts are latency- and chain-bound, not bandwidth-bound: cap the CTAs.
-        // SB200_NCCL_MAX_CTAS=0 leaves NCCL's default.
-        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
-        {
-            const char* e = getenv("SB200_NCCL_MAX_CTAS");
-            const int m = e ? atoi(e) : SB200_NCCL_MAX_CTAS_DEFAULT;
-            if (m > 0) cfg.maxCTAs = m;
+        if (ncclCommInitRank(&g.world, p * q, id, rank) != ncclSuccess) { delete h; return SB200_ENCCL; }
+        if (ncclCommSplit(g.world, g.prow, g.pcol, &g.row_comm, nullptr) != ncclSuccess
+            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm, nullptr) != ncclSuccess
+            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm2, nullptr) != ncclSuccess) {
+            delete h; return SB200_ENCCL;
         }
-        if (ncclCommInitRankConfig(&g.world, p * q, id, rank, &cfg) != ncclSuccess) { delete h; return SB200_ENCCL; }
-        if (ncclCommSplit(g.world, g.prow, g.pcol, &g.row_comm, &cfg) != ncclSuccess
-            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm, &cfg) != ncclSuccess
-            || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm2, &cfg) != ncclSuccess) {
+        // A second communicator over all ranks, capped at a few CTAs, for the Cholesky panel broadcast: NCCL's CTAs run
+        // next to the trailing update and hold SMs for as long as the collective waits for its root -- with the default
+        // channel count the DMMA kernel ran at 0.77 of its peak on 8 GPUs, capped at 8 CTAs at 0.85 (dpotrf 428 ->
+        // 423 ms with both this and the scatter + all-gather form; profiles/r02g8b_*, r02g8c_*).  The LU's exchanges
+        // are bandwidth-bound and got slower with the cap (1008 -> 1081 ms): they keep the uncapped communicators.
+        // SB200_NCCL_MAX_CTAS=0: no second communicator.
+        const char* ce = getenv("SB200_NCCL_MAX_CTAS");
+        const int max_ctas = ce ? atoi(ce) : SB200_NCCL_MAX_CTAS_DEFAULT;
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.maxCTAs = max_ctas;
+        if (max_ctas > 0 && (ncclCommSplit(g.world, 0, rank, &g.world_lo, &cfg) != ncclSuccess
+                             || ncclCommSplit(g.world, p + g.pcol, g.prow, &g.col_comm_lo, &cfg) != ncclSuccess)) {
             delete h; return SB200_ENCCL;
         }
     }
@@ -1075,6 +1082,8 @@ int sb200_grid_create(int p, int q, int rank, const void* nccl_unique_id, sb200_
 int sb200_grid_destroy(sb200_grid_t h)
 {
     if (! h) return SB200_OK;
+    if (h->g.world_lo) ncclCommDestroy(h->g.world_lo);
+    if (h->g.col_comm_lo) ncclCommDestroy(h->g.col_comm_lo);
     if (h->g.row_comm) ncclCommDestroy(h->g.row_comm);
     if (h->g.col_comm) ncclCommDestroy(h->g.col_comm);
     if (h->g.col_comm2) ncclCommDestroy(h->g.col_comm2);

@@ -32,6 +32,8 @@ struct Grid {
     int p = 1, q = 1, rank = 0;
     int prow = 0, pcol = 0;
     ncclComm_t world = nullptr;      // null when p*q == 1
+    ncclComm_t world_lo = nullptr;   // the same ranks, capped at a few CTAs: the Cholesky panel broadcast (may be null)
+    ncclComm_t col_comm_lo = nullptr;   // col_comm capped the same way: the L_kk broadcast of the Cholesky chain
     ncclComm_t row_comm = nullptr;   // ranks with the same prow (size q), rank order = pcol
     ncclComm_t col_comm = nullptr;   // ranks with the same pcol (size p), rank order = prow
     ncclComm_t col_comm2 = nullptr;  // second communicator over the same ranks: collectives of the trailing stream

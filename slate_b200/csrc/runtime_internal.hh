@@ -234,7 +234,7 @@ struct DevBuf {
 struct BcastItem { const void* src; void* dst; size_t bytes; int root; };
 constexpr int SB200_BCAST_DEFAULT = 1;          // scatter + all-gather: measured on 8 GPUs (r2g8b): dpotrf 428 -> 408 ms, dgetrf 1043 -> 1008 ms
 constexpr int SB200_NCCL_MAX_CTAS_DEFAULT = 8;
-int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s);
+int bcast_many(Grid& g, const std::vector<BcastItem>& items, cudaStream_t s, ncclComm_t comm = nullptr);
 
 // drivers (runtime.cu)
 // lookahead <= 0: the library default (SB200_LOOKAHEAD or POTRF_DEFAULT_LOOKAHEAD)
