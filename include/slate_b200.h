@@ -298,6 +298,16 @@ typedef struct sb200_matrix_s* sb200_matrix_t;
 int sb200_grid_unique_id(void* out_id_128);
 int sb200_grid_create(int p, int q, int rank, const void* nccl_unique_id, sb200_grid_t* out);
 int sb200_grid_destroy(sb200_grid_t g);
+/* Tile broadcasts of one step in one go -- the hook for BaseMatrix::tileBcast / listBcast / listBcastMT
+ * (include/slate/BaseMatrix.hh:1889-2140: per tile an MPI broadcast to the ranks that need it, then a
+ * host-to-device copy).  Every rank of the grid calls it with the SAME list: range t is `bytes[t]` bytes that live at
+ * `src[t]` on rank `roots[t]` (a tile, or any number of tiles that are contiguous in the root's pool) and arrive at
+ * `dst[t]` on every rank (`src[t]` is read on the root only; the root's `dst[t]` may equal `src[t]`).  All arrays are
+ * HOST arrays of `count` entries, the pointers in them DEVICE pointers.  Ranges of >= 4 MiB travel as scatter +
+ * in-place all-gather over NVLink / NVSwitch, smaller ones as grouped NCCL broadcasts; asynchronous on `stream`.
+ * A 1 x 1 grid returns at once (the reference's single-rank early exit, BaseMatrix.hh:2006). */
+int sb200_bcast_tiles(sb200_grid_t g, int64_t count, const void* const* src, void* const* dst,
+                      const size_t* bytes, const int* roots, sb200_stream_t stream);
 
 /* kind: 'G' general m-by-n, 'H' Hermitian/symmetric n-by-n lower-stored.
  * layout: 'C' column-major tiles (gemm, potrf), 'R' row-major tiles (getrf on devices,

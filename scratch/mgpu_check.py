@@ -46,6 +46,28 @@ def main():
     ok = True
     for (p, q) in shapes:
         grid = sl.Grid.from_torch_distributed(p, q)
+        # ---- sb200_bcast_tiles (the listBcast hook): three ranges from different roots, one of them large enough for
+        #      the scatter + all-gather form, one with an odd byte count
+        if os.environ.get("MGPU_BCAST", "1") != "0":
+            good = True
+            rngs, bufs = [], []
+            for t, (nbytes, root) in enumerate([(8 << 20, 0), (777, world - 1), ((5 << 20) + 24, world // 2)]):
+                srcb = torch.full((nbytes,), 17 + t, dtype=torch.uint8, device="cuda") if rank == root else None
+                dstb = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+                if rank == root:
+                    srcb[::3] = (torch.arange(0, (nbytes + 2) // 3, device="cuda") % 251).to(torch.uint8)
+                bufs.append((srcb, dstb, nbytes, root, t))
+                rngs.append((srcb.data_ptr() if rank == root else 0, dstb.data_ptr(), nbytes, root))
+            grid.bcast_tiles(rngs)
+            torch.cuda.synchronize()
+            for (srcb, dstb, nbytes, root, t) in bufs:
+                ref = torch.full((nbytes,), 17 + t, dtype=torch.uint8, device="cuda")
+                ref[::3] = (torch.arange(0, (nbytes + 2) // 3, device="cuda") % 251).to(torch.uint8)
+                good &= bool(torch.equal(dstb, ref))
+            flag = torch.tensor([1 if good else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(f"grid {p}x{q} bcast_tiles: {'ok' if int(flag[0]) else 'FAILED'}", flush=True)
+            ok &= bool(int(flag[0]))
         sizes = [(1024, 128), (1000, 128), (2048, 256)]
         if os.environ.get("MGPU_SIZES"):
             sizes = [tuple(int(x) for x in a.split("x")) for a in os.environ["MGPU_SIZES"].split(",")]

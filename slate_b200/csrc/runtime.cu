@@ -1079,6 +1079,22 @@ int sb200_grid_create(int p, int q, int rank, const void* nccl_unique_id, sb200_
     return SB200_OK;
 }
 
+int sb200_bcast_tiles(sb200_grid_t h, int64_t count, const void* const* src, void* const* dst,
+                      const size_t* bytes, const int* roots, sb200_stream_t stream)
+{
+    if (! h || count < 0) return SB200_EINVAL;
+    Grid& g = h->g;
+    if (g.size() <= 1 || count == 0) return SB200_OK;
+    if (! src || ! dst || ! bytes || ! roots) return SB200_EINVAL;
+    std::vector<BcastItem> items;
+    items.reserve(size_t(count));
+    for (int64_t t = 0; t < count; ++t) {
+        if (roots[t] < 0 || roots[t] >= g.size() || ! dst[t] || (roots[t] == g.rank && ! src[t])) return SB200_EINVAL;
+        if (bytes[t]) items.push_back({src[t], dst[t], bytes[t], roots[t]});
+    }
+    return bcast_many(g, items, static_cast<cudaStream_t>(stream));
+}
+
 int sb200_grid_destroy(sb200_grid_t h)
 {
     if (! h) return SB200_OK;

@@ -44,6 +44,8 @@ class _Options(ctypes.Structure):
 _grid_unique_id = _sig("sb200_grid_unique_id", [c_ptr])
 _grid_create = _sig("sb200_grid_create", [c_int, c_int, c_int, c_ptr, ctypes.POINTER(c_ptr)])
 _grid_destroy = _sig("sb200_grid_destroy", [c_ptr])
+_bcast_tiles = _sig("sb200_bcast_tiles", [c_ptr, c_i64, ctypes.POINTER(c_ptr), ctypes.POINTER(c_ptr),
+                                          ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(c_int), c_ptr])
 class _MixedOptions(ctypes.Structure):
     _fields_ = [("max_iterations", c_i64), ("tolerance", c_dbl), ("use_fallback_solver", c_int),
                 ("reserved", c_int * 5)]
@@ -143,6 +145,17 @@ class Grid:
         t = torch.frombuffer(bytearray(uid.raw), dtype=torch.uint8).to(dev)
         dist.broadcast(t, 0)
         return cls(p, q, rank, bytes(t.cpu().numpy().tobytes()))
+
+    def bcast_tiles(self, ranges):
+        """Broadcast device ranges in one go (BaseMatrix::listBcast, include/slate/BaseMatrix.hh:1998-2140): `ranges` is
+        the same list on every rank of (src_ptr, dst_ptr, nbytes, root) with device pointers (src_ptr is read on the
+        root only).  Asynchronous on the current torch stream."""
+        n = len(ranges)
+        if n == 0:
+            return
+        src = (c_ptr * n)(*[r[0] for r in ranges]); dst = (c_ptr * n)(*[r[1] for r in ranges])
+        nbytes = (ctypes.c_size_t * n)(*[r[2] for r in ranges]); roots = (c_int * n)(*[r[3] for r in ranges])
+        check(_bcast_tiles(self._h, n, src, dst, nbytes, roots, _stream()), "bcast_tiles")
 
     def close(self):
         if getattr(self, "_h", None):

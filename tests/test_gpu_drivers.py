@@ -189,3 +189,16 @@ def test_getrf_grid_algorithm_rectangular_and_singular(sl, monkeypatch):
     A = sl.Matrix(n, n, nb); A.from_host(np.asfortranarray(A0))
     _, info = sl.getrf(A)
     assert info == o.getrf(A0, nb, 32)[2] == 101
+
+
+def test_bcast_tiles_hook_on_one_rank_is_the_single_rank_early_exit(sl):
+    """sb200_bcast_tiles on a 1 x 1 grid returns at once and touches nothing (BaseMatrix.hh:2006: one rank, no
+    broadcast); the multi-rank transfer itself is checked by scratch/mgpu_check.py on 2 and 8 GPUs."""
+    import torch
+    g = sl.Grid(1, 1, 0)
+    a = torch.arange(1024, dtype=torch.float64, device="cuda")
+    b = torch.zeros(1024, dtype=torch.float64, device="cuda")
+    g.bcast_tiles([(a.data_ptr(), b.data_ptr(), 8192, 0)])
+    torch.cuda.synchronize()
+    assert float(b.abs().sum()) == 0.0
+    g.close()
