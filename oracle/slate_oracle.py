@@ -20,6 +20,8 @@ results agree to rounding, not bitwise.
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 # ----------------------------------------------------------------------------
@@ -71,7 +73,15 @@ def generate(kind: str, m: int, n: int, seed: int, dtype=np.float64,
              i0: int = 0, j0: int = 0, n_global: int | None = None) -> np.ndarray:
     """Dense m-by-n block starting at global (i0, j0) of the reference `rand` /
     `rand_dominant` test matrix (matgen/generate_type_rand.hh:28-79: uniform [0,1),
-    dominant adds n to the diagonal; complex: (re, im) from the two Philox words)."""
+    dominant adds n to the diagonal; complex: (re, im) from the two Philox words).
+    The parametrised GPU tests ask for the same few matrices over and over (2.9 s for 2048 x 2048 in numpy): the last
+    few results are kept and a fresh copy is handed out."""
+    return _generate_cached(kind, int(m), int(n), int(seed), np.dtype(dtype).str, int(i0), int(j0),
+                            None if n_global is None else int(n_global)).copy(order="F")
+
+
+@functools.lru_cache(maxsize=12)
+def _generate_cached(kind, m, n, seed, dtype, i0, j0, n_global):
     dtype = np.dtype(dtype)
     real = np.float32 if dtype in (np.dtype(np.float32), np.dtype(np.complex64)) else np.float64
     ii = np.arange(i0, i0 + m, dtype=np.int64)[:, None]
@@ -226,7 +236,25 @@ def getrf_panel(P: np.ndarray, diag_len: int, ib: int, nb_rows: int):
     return piv, info
 
 
+_GETRF_MEMO: dict = {}
+
+
 def getrf(A, nb: int, ib: int = 16):
+    """Blocked LU with the reference's pivot rule.  Memoised on the input's bytes (the parametrised GPU tests factor the
+    same seeded matrix once per kernel variant); callers get copies."""
+    import hashlib
+    Af = np.asfortranarray(A)
+    key = (hashlib.blake2b(Af.tobytes(order="F"), digest_size=16).digest(), Af.shape, Af.dtype.str, int(nb), int(ib))
+    hit = _GETRF_MEMO.get(key)
+    if hit is None:
+        if len(_GETRF_MEMO) >= 12:
+            _GETRF_MEMO.pop(next(iter(_GETRF_MEMO)))
+        hit = _GETRF_MEMO[key] = _getrf_impl(Af, nb, ib)
+    LU, piv, info = hit
+    return LU.copy(order="F"), [list(c) for c in piv], info
+
+
+def _getrf_impl(A, nb: int, ib: int = 16):
     from scipy.linalg import solve_triangular
     A = np.array(A, order="F", copy=True)
     m, n = A.shape

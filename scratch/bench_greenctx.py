@@ -128,7 +128,7 @@ for name, n_small, flags in configs:
         print(json.dumps({"config": name, "error": str(ex)}), flush=True)
         continue
     rec = {"config": name, "sm_chain": sm_small, "sm_trailing": sm_big, "background_tflops": bg_rate(s_bg)}
-    for variant, env in (("default", {}), ("tile_fused", {"SB200_TILE_FUSED": "1"}), ("diag_mw", {"SB200_DIAG_MW": "1"})):
+    for variant, env in (("default", {}), ("tile_fused", {"SB200_TILE_FUSED": "1"})):
         for k, v in env.items():
             os.environ[k] = v
         for c in (False, True):

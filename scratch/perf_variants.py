@@ -1,6 +1,6 @@
 """One-process timing of the round-2 candidates against the default path (N = 1), per-phase device timers on stderr.
 Every variant is a set of environment switches read by the library PER CALL or at first use; variants whose switch is
-latched at first use (SB200_DIAG_RSQRT, SB200_DIAG_WARP, SB200_PANEL_BARRIER) are run in a FRESH process each:
+latched at first use are run in a FRESH process each:
     python scratch/perf_variants.py potrf 32768 512            # all potrf variants, one subprocess each
     python scratch/perf_variants.py getrf 32768 512
     python scratch/perf_variants.py one potrf 32768 512        # (internal) run with the current environment
@@ -10,35 +10,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 POTRF = [("default", {}),
-         ("diag_rsqrt", {"SB200_DIAG_RSQRT": "1"}),
-         ("diag_warp", {"SB200_DIAG_WARP": "1"}),
-         ("diag_mw", {"SB200_DIAG_MW": "1"}),
-         ("diag_mw_rsqrt", {"SB200_DIAG_MW": "2"}),
-         ("diag_mw+trsm_fused", {"SB200_DIAG_MW": "1", "SB200_TRSM_FUSED": "1"}),
+         ("diag_division_form", {"SB200_DIAG_RSQRT": "0"}),
          ("tile_fused", {"SB200_TILE_FUSED": "1"}),
          ("tile_fused_rsqrt", {"SB200_TILE_FUSED": "2"}),
-         ("trsm_fused", {"SB200_TRSM_FUSED": "1"}),
-         ("tile+trsm_fused", {"SB200_TILE_FUSED": "1", "SB200_TRSM_FUSED": "1"}),
-         ("tile_rsqrt+trsm_fused", {"SB200_TILE_FUSED": "2", "SB200_TRSM_FUSED": "1"})]
+         ("no_fused_solves", {"SB200_TRSM_FUSED": "0"}),
+         ("chain_on_4_sms", {"SB200_CHAIN_SMS": "4"}),
+         ("chain_on_8_sms", {"SB200_CHAIN_SMS": "8"})]
 GETRF = [("default", {}),
-         ("diag_mw", {"SB200_DIAG_MW": "1"}),
-         ("panel_barrier", {"SB200_PANEL_BARRIER": "1"}),
-         ("panel_ll", {"SB200_PANEL_LL": "1"}),
-         ("panel_ll+row_trsm_fused", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "2"}),
-         ("small_trsm_direct", {"SB200_TRSM_FUSED": "4"}),
-         ("transposed_U_row", {"SB200_GEMM_BT": "1"}),
-         ("skinny_panel_update", {"SB200_PANEL_SKINNY": "1"}),
-         ("panel_ll+all_row_solves", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6"}),
-         ("panel_ll+all_row_solves+diag_mw", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1"}),
-         ("everything", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1", "SB200_GEMM_BT": "1", "SB200_PANEL_SKINNY": "1"}),
-         ("row_trsm_fused", {"SB200_TRSM_FUSED": "2"}),
-         ("barrier+row_trsm_fused", {"SB200_PANEL_BARRIER": "1", "SB200_TRSM_FUSED": "2"})]
-MIXED = [("default", {}),
-         ("diag_mw", {"SB200_DIAG_MW": "1"}),
-         ("tile+trsm_fused+diag_mw", {"SB200_TILE_FUSED": "1", "SB200_TRSM_FUSED": "3", "SB200_DIAG_MW": "1"})]
-GEMM = [("default", {}), ("transposed_B_panel", {"SB200_GEMM_BT": "1"})]
-GMIXED = [("default", {}),
-          ("panel_ll+all_row_solves+diag_mw+skinny", {"SB200_PANEL_LL": "1", "SB200_TRSM_FUSED": "6", "SB200_DIAG_MW": "1", "SB200_PANEL_SKINNY": "1"})]
+         ("no_folded_updates", {"SB200_PANEL_FUSE": "0"}),
+         ("rows_in_shared_memory", {"SB200_PANEL_V4": "0"}),
+         ("cooperative_barrier_kernel", {"SB200_PANEL_V3": "0"}),
+         ("untransposed_U_row", {"SB200_GEMM_BT": "0"}),
+         ("no_fused_solves", {"SB200_TRSM_FUSED": "0"})]
+MIXED = [("default", {}), ("tile_fused", {"SB200_TILE_FUSED": "1"})]
+GEMM = [("default", {}), ("untransposed_B_panel", {"SB200_GEMM_BT": "0"})]
+GMIXED = [("default", {}), ("rows_in_shared_memory", {"SB200_PANEL_V4": "0"})]
 
 
 def one(routine, n, nb):

@@ -163,6 +163,8 @@ std::mutex g_ws_mu;
 std::vector<WsBlock> g_ws;
 }
 
+extern "C" int sb200_release_workspaces(void);
+
 void* ws_cache_get(size_t bytes)
 {
     int dev = 0;
@@ -192,9 +194,18 @@ void ws_cache_put(void* p)
     // what cudaFree did implicitly and some callers (asynchronous solve-path helpers) rely on: nothing on the device
     // still uses the block when it becomes available again.  A no-op after a driver (its streams are synchronised).
     cudaDeviceSynchronize();
-    std::lock_guard<std::mutex> lk(g_ws_mu);
-    for (auto& b : g_ws)
-        if (b.p == p) { b.busy = false; return; }
+    // a process that factors matrices of many different shapes must not accumulate idle blocks without bound:
+    // above SB200_WS_CACHE_MB (default 16 GiB) of idle memory everything idle is given back to the driver
+    static const size_t cap = [] { const char* e = getenv("SB200_WS_CACHE_MB"); return size_t(e ? atoll(e) : 16384) << 20; }();
+    size_t idle = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        for (auto& b : g_ws) {
+            if (b.p == p) b.busy = false;
+            if (! b.busy) idle += b.bytes;
+        }
+    }
+    if (idle > cap) sb200_release_workspaces();
 }
 
 extern "C" int sb200_release_workspaces(void)
