@@ -159,6 +159,16 @@ def cpu_reference_run(routine: str, n: int, nb: int, threads: int):
     t0 = time.time(); o.gemm(3.1, A, B, 2.7, C, nb); return time.time() - t0, "port"
 
 
+def pick_ref_n(routine, runs, budget_s=150.0, rate=0.65e12):
+    """Largest reference sample size whose `runs` executions fit the time budget: the HostTask rate still rises with n,
+    so the closer the sample is to the metric's n = 65536 the less the reference arm is under-estimated."""
+    r = routine if routine in ("potrf", "getrf", "gemm") else "getrf"
+    for n in (32768, 24576, 16384, 8192):
+        if runs * flops(r, n) / rate <= budget_s:
+            return n
+    return 8192
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path, all host threads,
     on a bounded sample of the workload."""
@@ -166,7 +176,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    n = args.ref_n
+    n = args.ref_n or pick_ref_n(args.routine, args.steps + 1)
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_reference_run(args.routine, n, args.nb, threads)
     secs, kind = [], "reference"
@@ -488,7 +498,7 @@ def run_extra(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline and mixed:
         try:
             threads = os.cpu_count() or 1
-            rn = min(args.ref_n, 8192)
+            rn = min(args.ref_n or 8192, 8192)
             secs, kind = cpu_reference_run(routine, rn, nb, threads)
             cpu = {"value": extra_flops(routine, rn, nrhs) / secs / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": kind,
                    "sample": f"d{routine} n={rn} nb={nb} nrhs={nrhs} Target::HostTask, one run, {secs:.2f} s"}
@@ -697,7 +707,9 @@ def main():
     ap.add_argument("--n", "--size", dest="n", type=int, default=0,
                     help="matrix size (use --size under torchrun, whose own parser claims the prefix --n)")
     ap.add_argument("--nb", type=int, default=512)
-    ap.add_argument("--ref-n", type=int, default=16384, help="bounded sample size for the CPU reference legs")
+    ap.add_argument("--ref-n", type=int, default=0,
+                    help="bounded sample size for the CPU reference legs (0 = the largest of 32768 / 24576 / 16384 / 8192 whose "
+                         "steps + warm-up finish in about 150 s at the reference's ~0.65 TFLOP/s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the dgetrf / dgemm sub-records of the default run")
@@ -781,9 +793,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             threads = os.cpu_count() or 1
-            secs, kind = cpu_reference_run(routine, args.ref_n, nb, threads)
-            cpu = {"value": flops(routine, args.ref_n) / secs / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": kind,
-                   "sample": f"d{routine} n={args.ref_n} nb={nb} Target::HostTask (the workload's generator and tile size at a "
+            ref_n = args.ref_n or 16384             # one run of 10-30 s of host work
+            secs, kind = cpu_reference_run(routine, ref_n, nb, threads)
+            cpu = {"value": flops(routine, ref_n) / secs / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": kind,
+                   "sample": f"d{routine} n={ref_n} nb={nb} Target::HostTask (the workload's generator and tile size at a "
                              f"bounded n), one run, {secs:.2f} s"}
         except Exception as ex:   # noqa: BLE001
             cpu = {"value": None, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
