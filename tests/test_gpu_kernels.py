@@ -99,18 +99,23 @@ def test_herk_batched(t, layout, uplo, op, n, k):
         assert np.abs(x - exp).max() <= tol * np.abs(r).max()
 
 
-@pytest.mark.parametrize("t", ["d", "s", "z", "c"])
-@pytest.mark.parametrize("layout", ["C", "R"])
-@pytest.mark.parametrize("side", ["L", "R"])
-@pytest.mark.parametrize("uplo", ["L", "U"])
-@pytest.mark.parametrize("op", ["N", "T", "C"])
-@pytest.mark.parametrize("diag", ["N", "U"])
-@pytest.mark.parametrize("m,n", [(64, 48), (200, 136), (77, 53), (512, 512)])
+def _trsm_cases():
+    """every side / uplo / op / diag / layout for the four types; op 'C' only where it differs from 'T' (complex), the
+    production tile size 512 x 512 for d (all ops) and z (N, C)"""
+    import itertools
+    out = []
+    for t, layout, side, uplo, op, diag, (m, n) in itertools.product("dszc", "CR", "LR", "LU", "NTC", "NU",
+                                                                     [(64, 48), (200, 136), (77, 53), (512, 512)]):
+        if t in "ds" and op == "C":
+            continue
+        if (m, n) == (512, 512) and (t in "sc" or (op == "T" and t == "z")):
+            continue
+        out.append((t, layout, side, uplo, op, diag, m, n))
+    return out
+
+
+@pytest.mark.parametrize("t,layout,side,uplo,op,diag,m,n", _trsm_cases())
 def test_trsm_batched(t, layout, side, uplo, op, diag, m, n):
-    if t in "ds" and op == "C":
-        pytest.skip("C == T for real types (covered by T)")
-    if (m, n) == (512, 512) and (t in "sc" or op == "T" and t == "z"):
-        pytest.skip("production tile size is checked for d (all ops) and z (N, C)")
     rng = np.random.default_rng(4)
     batch = 2
     na = m if side == "L" else n
