@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import slate_oracle as o
+from tests.gpu_util import GETRF_TOL
 
 pytestmark = pytest.mark.gpu
 EPS = np.finfo(np.float64).eps
@@ -33,7 +34,7 @@ def test_getrf_panel_variants_identical_pivots(sl, m, n, nb, panel, dist, monkey
     LUo, pivo, info_o = o.getrf(A0, nb, 32)
     assert info == info_o == 0
     assert piv == pivo, "pivot vectors differ from the oracle's"
-    assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
+    assert np.abs(A.to_host() - LUo).max() <= GETRF_TOL * np.abs(LUo).max()
 
 
 @pytest.mark.parametrize("panel", ["1", "2"])

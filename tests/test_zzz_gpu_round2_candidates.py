@@ -32,6 +32,7 @@ import numpy as np
 import pytest
 
 from oracle import slate_oracle as o
+from tests.gpu_util import GETRF_TOL
 
 pytestmark = [pytest.mark.gpu]
 EPS = float(np.finfo(np.float64).eps)
@@ -210,7 +211,7 @@ def test_getrf_with_fused_row_solve_identical_pivots(sl, monkeypatch, m, n, nb, 
     LUo, pivo, info_o = o.getrf(A0, nb, 32)
     assert info == info_o == 0
     assert piv == pivo, "pivot vectors differ from the oracle's"
-    assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
+    assert np.abs(A.to_host() - LUo).max() <= GETRF_TOL * np.abs(LUo).max()
 
 
 def test_gesv_mixed_with_all_fused_candidates(sl, monkeypatch):
@@ -289,7 +290,7 @@ def test_getrf_base_kernel_variants_identical_pivots(sl, m, n, nb, panel, dist, 
     LUo, pivo, info_o = o.getrf(A0, nb, 32)
     assert info == info_o == 0
     assert piv == pivo, "pivot vectors differ from the oracle's"
-    assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
+    assert np.abs(A.to_host() - LUo).max() <= GETRF_TOL * np.abs(LUo).max()
 
 
 @pytest.mark.parametrize("variant", list(BASE_VARIANTS))
@@ -390,7 +391,7 @@ def test_getrf_with_all_row_solve_candidates_identical_pivots(sl, monkeypatch, m
     LUo, pivo, info_o = o.getrf(A0, nb, 32)
     assert info == info_o == 0
     assert piv == pivo, "pivot vectors differ from the oracle's"
-    assert np.abs(A.to_host() - LUo).max() <= 1e-11 * np.abs(LUo).max()
+    assert np.abs(A.to_host() - LUo).max() <= GETRF_TOL * np.abs(LUo).max()
 
 
 @pytest.mark.parametrize("t", ["s", "c", "z"])
