@@ -159,10 +159,14 @@ def cpu_reference_run(routine: str, n: int, nb: int, threads: int):
     t0 = time.time(); o.gemm(3.1, A, B, 2.7, C, nb); return time.time() - t0, "port"
 
 
-def pick_ref_n(routine, runs, budget_s=150.0, rate=0.65e12):
+REF_RATE = {"potrf": 0.65e12, "getrf": 0.45e12, "gemm": 0.8e12}     # HostTask on 16 host threads, as measured in round 1 / 2
+
+
+def pick_ref_n(routine, runs, budget_s=150.0, rate=None):
     """Largest reference sample size whose `runs` executions fit the time budget: the HostTask rate still rises with n,
     so the closer the sample is to the metric's n = 65536 the less the reference arm is under-estimated."""
     r = routine if routine in ("potrf", "getrf", "gemm") else "getrf"
+    rate = rate or REF_RATE[r]
     for n in (32768, 24576, 16384, 8192):
         if runs * flops(r, n) / rate <= budget_s:
             return n

@@ -63,3 +63,16 @@ def test_reference_arm_prints_a_wellformed_line(ref_dump):
     assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
+
+
+def test_reference_sample_size_fits_its_time_budget():
+    """--impl reference without --ref-n: the largest sample whose steps + warm-up fit about 150 s at the reference's
+    ~0.65 TFLOP/s -- 32768 for a few steps, smaller for many"""
+    import bench
+    assert bench.pick_ref_n("potrf", 4) == 32768
+    assert bench.pick_ref_n("potrf", 21) == 16384
+    assert bench.pick_ref_n("getrf", 4) == 24576
+    for r in ("potrf", "getrf", "gemm"):
+        for runs in (1, 4, 21, 200):
+            n = bench.pick_ref_n(r, runs)
+            assert n == 8192 or runs * bench.flops(r, n) / bench.REF_RATE[r] <= 150.0
