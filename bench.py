@@ -50,7 +50,7 @@ def _switches() -> dict:
     """Library switches in effect (SB200_* environment): empty for the default paths, so that a line measured with an
     opt-in candidate turned on says so."""
     return {k: v for k, v in sorted(os.environ.items())
-            if k.startswith("SB200_") and k not in ("SB200_PHASES", "SB200_REFERENCE", "SB200_RUN_UNVALIDATED")}
+            if k.startswith("SB200_") and k not in ("SB200_PHASES", "SB200_REFERENCE", "SB200_HOST_TIMES")}
 
 
 def default_n(routine: str, ngpus: int) -> int:
