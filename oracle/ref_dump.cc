@@ -16,7 +16,7 @@
 // usage: ref_dump ROUTINE TYPE n nb seedA seedB seedC OUTPREFIX [key=value ...]
 //   ROUTINE  gen | gemm | herk | potrf | getrf | trsm | gesv_mixed | posv_mixed | posv | gesv | hemm | norms
 //   TYPE     s | d | c | z
-//   keys     kind=rand|rand_dominant  la=1  ib=16  threads=N  dump=0|1  nrhs=10  pt=panel threads
+//   keys     kind=rand|rand_dominant  la=1  ib=16  threads=N  dump=0|1  nrhs=10  pt=panel threads  method=pplu|calu (getrf)
 //            m= k= (gemm/herk rectangular)  uplo=l|u
 #include "slate/slate.hh"
 #include "slate/generate_matrix.hh"
@@ -217,8 +217,12 @@ int run(const Args& a)
         auto A = make_matrix<T>(m, n, nb, a.seedA, a.get("kind", "rand"));
         if (dump) { auto d = to_dense(A); write_raw(a.prefix + ".A.bin", d.data(), d.size()); }
         slate::Pivots pivots;
+        // method=calu: tournament pivoting (slate::getrf_tntpiv, src/getrf_tntpiv.cc) through the same lu_factor call
+        // (Option::MethodLU, src/getrf.cc:324-329); one rank here, so the tournament has a single participant
+        slate::Options lu_opts = opts;
+        if (a.get("method", "pplu") == "calu") lu_opts[slate::Option::MethodLU] = slate::MethodLU::CALU;
         auto t0 = tic();
-        info = slate::lu_factor(A, pivots, opts);
+        info = slate::lu_factor(A, pivots, lu_opts);
         seconds = toc(t0);
         gflop = lapack::Gflop<T>::getrf(m, n);
         if (dump) {

@@ -356,6 +356,130 @@ def getrs(LU, pivots, B, nb: int):
 
 
 # ----------------------------------------------------------------------------
+# getrf_tntpiv: LU with tournament pivoting (CALU).  src/getrf_tntpiv.cc:22-395 (driver),
+# src/internal/internal_getrf_tntpiv.cc:357-640 (panel: local LU per rank, binary tree of pairwise LUs of the
+# stacked candidate rows, permutation_to_sequential_pivot :42-120), src/internal/Tile_getrf_tntpiv.hh:69-300
+# (the LU used at every node: same pivot rule as tile::getrf).
+#
+#   per panel k:  ranks = the process rows that own tiles of block column k (tileRank(i, k) = i % p + ...), ordered by
+#     their first tile.  Stage 0: every rank factors a COPY of its own rows with partial pivoting and keeps the ORIGINAL
+#     rows that ended in its first piv_len positions.  Tree: at level l the rank at index x (x % 2^(l+1) == 0) stacks
+#     its candidate tile on the one of index x + 2^l, factors a copy, and keeps the original rows of the winners.
+#     The last LU (rank index 0) gives the factored diagonal tile and the nb winning rows; their sequence of row
+#     interchanges follows from where each winner sits when its turn comes.
+#   driver: interchanges applied to the whole block row range, A(k,k) <- factored tile, A(i,k) <- A(i,k) U_kk^-1 below
+#     it (trsm Right/Upper/NonUnit, :171-184), then the row solve and trailing update of getrf.
+#
+# PINNED for ranks = 1 (the only case the reference can run in this container: the MPI stub is serial) by
+# tests/golden/getrf_tntpiv_d*.npz; for ranks > 1 the tree is a restatement by reading -- parity UNPINNED.
+# With one rank the pivots are those of partial pivoting; the factor differs from getrf's in rounding only.
+# ----------------------------------------------------------------------------
+def tnt_winners_to_sequential(winners, m_p: int):
+    """Sequential interchanges (position j <-> piv[j]) that bring original row winners[j] to position j, and the final
+    arrangement row_at (row_at[x] = original row at position x).  internal_getrf_tntpiv.cc:42-120."""
+    row_at = np.arange(m_p)
+    pos_of = np.arange(m_p)
+    piv = np.zeros(len(winners), dtype=np.int64)
+    for j, w in enumerate(winners):
+        x = int(pos_of[w])
+        assert x >= j
+        piv[j] = x
+        rj = int(row_at[j])
+        row_at[j], row_at[x] = w, rj
+        pos_of[w], pos_of[rj] = j, x
+    return piv, row_at
+
+
+def tnt_panel(P: np.ndarray, nb: int, k: int, ranks: int, ib: int):
+    """Tournament over the m_p x kw panel P (ORIGINAL rows; tile t of the panel is global tile row k + t).
+    Returns (sequential pivots (panel-relative rows), factored top tile (diag rows x kw), info)."""
+    m_p, kw = P.shape
+    ntile = -(-m_p // nb)
+    tile_rows = [np.arange(t * nb, min((t + 1) * nb, m_p)) for t in range(ntile)]
+    order = []                                   # ranks by first tile (rank_rows, :456-470)
+    for t in range(ntile):
+        r = (k + t) % ranks
+        if r not in order:
+            order.append(r)
+    nranks = len(order)
+    if nranks > 1:
+        assert kw == nb, "tournament over several ranks restated for full-width panels only"
+    cand = []                                    # per rank index: original panel rows of its candidate tile, in order
+    info = 0
+    top = None
+    for x, r in enumerate(order):
+        rows = np.concatenate([tile_rows[t] for t in range(ntile) if (k + t) % ranks == r])
+        first_mb = len(tile_rows[[t for t in range(ntile) if (k + t) % ranks == r][0]])
+        piv_len = min(first_mb, kw)
+        W = np.array(P[rows], order="F", copy=True)
+        piv, iinfo = getrf_panel(W, piv_len, ib, nb)
+        ids = rows.copy()
+        for j, pj in enumerate(piv):
+            if pj != j:
+                ids[[j, pj]] = ids[[pj, j]]
+        cand.append(ids[:first_mb].copy())
+        if x == 0:
+            info = iinfo
+            top = W[:first_mb].copy()
+            seq = piv
+    if nranks == 1:
+        return seq, top, info
+    nlevels = int(np.ceil(np.log2(nranks)))
+    step = 1
+    for level in range(nlevels):
+        for x in range(0, nranks, 2 * step):
+            if x + step < nranks:
+                ids = np.concatenate([cand[x], cand[x + step]])
+                mb1 = len(cand[x])
+                W = np.array(P[ids], order="F", copy=True)
+                piv, iinfo = getrf_panel(W, min(mb1, kw), ib, nb)
+                for j, pj in enumerate(piv):
+                    if pj != j:
+                        ids[[j, pj]] = ids[[pj, j]]
+                cand[x] = ids[:mb1].copy()
+                if x == 0:
+                    if info == 0:
+                        info = iinfo
+                    top = W[:mb1].copy()
+        step *= 2
+    diag_len = min(len(tile_rows[0]), kw)
+    seq, _ = tnt_winners_to_sequential(cand[0][:diag_len], m_p)
+    return seq, top, info
+
+
+def getrf_tntpiv(A, nb: int, ib: int = 16, ranks: int = 1):
+    from scipy.linalg import solve_triangular
+    A = np.array(A, order="F", copy=True)
+    m, n = A.shape
+    info = 0
+    pivots = []
+    kk = 0
+    for k in range(min(-(-m // nb), -(-n // nb))):
+        r0, c0 = k * nb, k * nb
+        r1, c1 = min(r0 + nb, m), min(c0 + nb, n)
+        diag_len = min(r1 - r0, c1 - c0)
+        piv, top, iinfo = tnt_panel(A[r0:, c0:c1], nb, k, ranks, ib)
+        if info == 0 and iinfo > 0:
+            info = kk + iinfo
+        pivots.append([(int(p // nb), int(p % nb)) for p in piv[:diag_len]])
+        for j, p in enumerate(piv[:diag_len]):          # permuteRows on every block column, the panel's included
+            if p != j:
+                A[[r0 + j, r0 + p], :] = A[[r0 + p, r0 + j], :]
+        A[r0:r1, c0:c1] = top
+        if r1 < m:                                      # A(i, k) <- A(i, k) U_kk^-1
+            U = np.triu(top[:diag_len, :diag_len])
+            A[r1:, c0:c0 + diag_len] = solve_triangular(U, A[r1:, c0:c0 + diag_len].T, lower=False, trans=1).T
+        if c1 < n:
+            Lkk = A[r0:r1, c0:c1][:, :diag_len]
+            A[r0:r1, c1:] = solve_triangular(Lkk[:diag_len], A[r0:r1, c1:], lower=True, unit_diagonal=True)
+            if r1 < m:
+                for (j0, j1) in _tiles(n, nb)[k + 1:]:
+                    A[r1:, j0:j1] -= A[r1:, c0:c1] @ A[r0:r1, j0:j1]
+        kk += c1 - c0
+    return A, pivots, info
+
+
+# ----------------------------------------------------------------------------
 # getrf_nopiv: A = L U without pivoting (src/getrf_nopiv.cc:25-190; internal_getrf_nopiv.cc + Tile_getrf_nopiv.hh):
 # per step the diagonal tile is factored (ib-blocked, no search), the column below is solved against U_kk, the row to
 # the right against L_kk, the rest updated.  The factors of LU without pivoting are unique, so the blocking only

@@ -25,6 +25,7 @@ generator fixture pins that), only outputs:
   syrk_z.npz, syr2k_z.npz   complex-symmetric rank-k / rank-2k updates (no conjugation), n=200 k=100 nb=64
   getrf_nopiv_d.npz      LU without pivoting, rand_dominant, n=300 nb=128 (ragged)
   her2k_d.npz, her2k_z.npz  C = alpha A B^H + conj(alpha) B A^H + beta C lower, n=200 k=100 nb=64 (ragged tiles)
+  getrf_tntpiv_d{,_ragged,_tall}.npz   LU with tournament pivoting (MethodLU::CALU), 384x384 / 300x300 / 512x256, nb=128
 
 Usage (in the build container, where /root/reference exists):  python tests/golden/make_golden.py
 """
@@ -55,6 +56,13 @@ def run(routine, t, n, nb, seeds=(42, 43, 44), **kv):
         dtype = np.int64 if key == "piv" else (np.float64 if (routine == "norms" and key == "out") else DT[t])
         files[key] = np.fromfile(os.path.join(tmp, f), dtype=dtype)
     return files, meta
+
+
+def tntpiv_fixtures():
+    for name, m, n in (("getrf_tntpiv_d", 384, 384), ("getrf_tntpiv_d_ragged", 300, 300), ("getrf_tntpiv_d_tall", 512, 256)):
+        f, meta = run("getrf", "d", n, 128, ib=16, pt=1, method="calu", m=m)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), out=f["out"].reshape(m, n, order="F"),
+                            piv=f["piv"].reshape(-1, 2), info=meta["info"])
 
 
 def main():
@@ -112,7 +120,12 @@ def main():
     # section 8(f) item 2 widening: LU without pivoting
     f, meta = run("getrf_nopiv", "d", 300, 128)
     np.savez_compressed(os.path.join(OUT, "getrf_nopiv_d.npz"), out=f["out"].reshape(300, 300, order="F"), info=meta["info"])
+    # section 8(f) item 2 widening: LU with tournament pivoting (one rank: the serial MPI stub)
+    tntpiv_fixtures()
     print("golden fixtures written to", OUT)
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "tntpiv":
+        tntpiv_fixtures()
+    else:
+        main()

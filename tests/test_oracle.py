@@ -151,6 +151,43 @@ def test_getrf_nopiv_matches_reference(golden_dir):
     assert o.getrf_nopiv(Z, nb)[1] == 6
 
 
+@pytest.mark.parametrize("name,m,n", [("getrf_tntpiv_d", 384, 384), ("getrf_tntpiv_d_ragged", 300, 300),
+                                      ("getrf_tntpiv_d_tall", 512, 256)])
+def test_getrf_tntpiv_matches_reference(golden_dir, name, m, n):
+    """MethodLU::CALU on one rank (src/getrf_tntpiv.cc): the pivots of partial pivoting, L21 through a solve with U11."""
+    g = load(golden_dir, name)
+    A = o.generate("rand", m, n, 42)
+    LU, piv, info = o.getrf_tntpiv(A, 128, 16)
+    flat = np.array([p for col in piv for p in col], dtype=np.int64)
+    assert np.array_equal(flat, g["piv"]), "pivot vectors differ from the reference"
+    assert info == int(g["info"]) == 0
+    assert np.abs(LU - g["out"]).max() <= 1e-12 * np.abs(g["out"]).max()
+
+
+@pytest.mark.parametrize("ranks", [2, 3, 4])
+@pytest.mark.parametrize("m,n,nb", [(384, 384, 64), (300, 300, 64), (448, 256, 64)])
+def test_getrf_tntpiv_tournament_is_an_lu(ranks, m, n, nb):
+    """Several ranks per panel (restated by reading; the reference cannot run multi-rank here): P A = L U holds, the
+    winners of every panel are rows of that panel, and the growth |L| stays small."""
+    A = o.generate("rand", m, n, 42)
+    LU, piv, info = o.getrf_tntpiv(A, nb, 16, ranks=ranks)
+    assert info == 0
+    mn = min(m, n)
+    perm = o.pivots_to_perm(piv, m, nb)
+    assert sorted(perm) == list(range(m))
+    L = np.tril(LU, -1)[:, :mn] + np.eye(m, mn)
+    U = np.triu(LU)[:mn]
+    assert np.abs(A[perm] - L @ U).max() <= 1e-13 * m
+    assert np.abs(L).max() < 8.0
+
+
+def test_tnt_winners_to_sequential_is_the_reference_example():
+    # internal_getrf_tntpiv.cc:69-93: mt = 2, nb = 4, winners (1,1) (0,3) (0,0) (0,2) -> pivots (1,1) (0,3) (1,1) (1,1)
+    piv, row_at = o.tnt_winners_to_sequential([5, 3, 0, 2], 8)
+    assert list(piv) == [5, 3, 5, 5]
+    assert list(row_at[:4]) == [5, 3, 0, 2]
+
+
 def test_trsm_matches_reference(golden_dir):
     g = load(golden_dir, "trsm_d")
     m, n = 256, 128
