@@ -256,6 +256,15 @@ getrf_base_kernel(const BaseArgs<T> a)
 // set by the getrf_nopiv entry points around their driver call (the drivers construct their PanelScratch on the
 // calling thread); read once per driver call by PanelScratch::init
 static thread_local bool g_getrf_nopiv = false;
+// likewise for getrf_tntpiv: 0 = partial pivoting, > 0 = participants of the tournament
+static thread_local int g_getrf_tnt = 0;
+
+int tnt_ranks_for(const Grid& g)
+{
+    const char* e = getenv("SB200_TNT_RANKS");
+    const int r = e ? atoi(e) : 0;
+    return r > 0 ? r : std::max(g.p, 1);
+}
 
 PanelScratch::~PanelScratch() { if (raw) ws_cache_put(raw); }
 
@@ -280,6 +289,7 @@ int PanelScratch::init()
     p = static_cast<char*>(raw) + (size_t(p - static_cast<char*>(raw)) + 15) / 16 * 16;      // 16-byte vector accesses
     v3_buf = reinterpret_cast<unsigned long long*>(p);
     nopiv = g_getrf_nopiv;
+    tnt_ranks = g_getrf_tnt;
     use_v3 = ! nopiv && switch_value(SW_PANEL_V3) != 0;
     if (use_v3) {
         CUDA_TRY(cudaMemset(v3_buf, 0, v3_bytes));             // tag 0 is never used by a launch
@@ -638,6 +648,11 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
     Streams st;
     SB_TRY(st.init(size_t(2 * kt)));
     cudaStream_t P = st.panel, T_ = st.trail;
+    TntScratch tnt;                                       // getrf_tntpiv only
+    if (ps.tnt_ranks > 0) {
+        if (use_tc05 || ! tnt_shape_supported(A)) return SB200_ENOTSUP;
+        SB_TRY(tnt.init(mt, nb, A.m, int(sizeof(T)), ps.tnt_ranks, P));
+    }
     auto P_done = [&](int64_t k) { return st.ev[size_t(k)]; };
     auto T_done = [&](int64_t k) { return st.ev[size_t(kt + k)]; };
     double trail_flops = 0; int64_t trail_launches = 0;
@@ -700,6 +715,13 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
         T* const* stack_k = dtbl + k + k * mt;
         // ---- panel k (column k already carries every earlier update: lookahead below)
         SB_TRY(st.ptime(P));
+        if (ps.tnt_ranks > 0) {
+            std::vector<T*> htiles;
+            for (int64_t i = k; i < mt; ++i) htiles.push_back(A.tile_as<T>(i, k));
+            SB_TRY(getrf_panel_tnt<T>(stack_k, htiles, k, int(nb), m_p, kw, pt, po, dinfo.as<int>(), int(k * nb), ps, tnt, P,
+                                      nullptr, &ph));
+        }
+        else
         SB_TRY(getrf_panel<T>(stack_k, A.tile_as<T>(k, k), int(mt - k), int(nb), m_p, kw, pt, po, dinfo.as<int>(),
                               int(k * nb), ps, P, nullptr, &ph));
         if (use_tc05 && ! sk.a_src.empty()) {
@@ -832,6 +854,19 @@ static int getrf_nopiv_any(sb200_matrix_t h, int64_t* info, bool is_float)
 }
 int sb200_getrf_nopiv_d(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, false); }
 int sb200_getrf_nopiv_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, true); }
+
+/* LU with tournament pivoting (slate::getrf_tntpiv, src/getrf_tntpiv.cc; MethodLU::CALU of slate::lu_factor): the getrf
+ * drivers with the panel of getrf_tnt.cu.  Participants per panel = process rows of the grid.
+ * STATUS: see DESIGN.md section 0 (row (f)2). */
+static int getrf_tntpiv_any(sb200_matrix_t h, int64_t* pivots, int64_t* info, bool is_float)
+{
+    if (! h) return SB200_EINVAL;
+    if (! tnt_shape_supported(h->A)) return SB200_ENOTSUP;
+    struct Guard { explicit Guard(int r) { g_getrf_tnt = r; } ~Guard() { g_getrf_tnt = 0; } } guard(tnt_ranks_for(*h->A.g));
+    return is_float ? getrf_driver_s(h->A, pivots, info, false) : getrf_driver(h->A, pivots, info);
+}
+int sb200_getrf_tntpiv_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, false); }
+int sb200_getrf_tntpiv_s(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, true); }
 
 int sb200_getrf_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
 {

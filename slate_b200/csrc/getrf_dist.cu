@@ -292,6 +292,8 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
     htm.mark("plan_and_buffers");
     PanelScratch ps;
     SB_TRY(ps.init());
+    if (ps.tnt_ranks > 0 && (use_tc05 || ! tnt_shape_supported(A))) return SB200_ENOTSUP;       // getrf_tntpiv (getrf_tnt.cu)
+    TntScratch tnt;
     cudaStream_t P = nullptr, T_ = nullptr;
     int lo, hi;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -397,6 +399,7 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
     };
 
     auto body = [&]() -> int {
+        if (ps.tnt_ranks > 0) SB_TRY(tnt.init(mt, nb, A.m, int(sizeof(T)), ps.tnt_ranks, P));
         CUDA_TRY(cudaMemcpyAsync(dplan, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, P));
         CUDA_TRY(cudaMemsetAsync(infob.p, 0, sizeof(int), P));
         CUDA_TRY(cudaStreamSynchronize(P));
@@ -432,6 +435,14 @@ static int getrf_driver_dist_t(Matrix& A, int64_t* pivots_out, int64_t* info_out
                 iota_kernel<<<unsigned(ceil_div(m_p, 256)), 256, 0, P>>>(rowmapb.as<int>(), m_p);
                 SB_TRY(launch_status());
                 T* const* stack_k = reinterpret_cast<T* const*>(dplan + steps[k].stack_off);
+                if (ps.tnt_ranks > 0) {
+                    // tournament over the process rows, entirely on this GPU: the panel is already gathered here
+                    std::vector<T*> htiles;
+                    for (int64_t i = k; i < mt; ++i) htiles.push_back(int(i % p) == prow ? A.tile_as<T>(i, k) : pws_tile(i, k));
+                    SB_TRY(getrf_panel_tnt<T>(stack_k, htiles, k, int(nb), m_p, kw, pt, po, infob.as<int>(), int(k * nb), ps, tnt, P,
+                                              rowmapb.as<int>(), &ph));
+                }
+                else
                 SB_TRY(getrf_panel<T>(stack_k, A.tile_as<T>(k, k), int(mt - k), int(nb), m_p, kw, pt, po, infob.as<int>(),
                                      int(k * nb), ps, P, rowmapb.as<int>(), &ph));
                 perm_pack_kernel<<<unsigned(ceil_div(ntop, 256)), 256, 0, P>>>(rowmapb.as<int>(), pt, po, int(nb), ntop, perm);

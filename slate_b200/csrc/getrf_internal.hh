@@ -15,6 +15,7 @@ struct PanelScratch {
     double* W = nullptr;            // trsm workspace of the panel stream
     unsigned* bar = nullptr;
     bool nopiv = false;                 // getrf_nopiv: base kernel without the pivot search
+    int tnt_ranks = 0;                  // getrf_tntpiv: > 0 = participants of the tournament per panel (getrf_tnt.cu)
     unsigned long long* v3_buf = nullptr;   // per-column exchange records of getrf_base_v3_kernel (getrf_base_v3.cu)
     unsigned v3_gen = 0;
     bool use_v3 = false;
@@ -23,6 +24,33 @@ struct PanelScratch {
     int init();
     ~PanelScratch();
 };
+
+// scratch of the tournament panel (getrf_tnt.cu), per driver call
+struct TntScratch {
+    void* wcopy = nullptr;          // workspace copy of the panel, mt tiles
+    void* tmp = nullptr;            // the two stacked candidate tiles of a tree node
+    int* ids = nullptr;             // [ranks][nb] original panel rows of every participant's candidates
+    int* rm_sub = nullptr;          // row map of the node being factored
+    int* row_at = nullptr; int* pos_of = nullptr;      // winners -> sequential interchanges
+    int64_t* spiv = nullptr;        // [2][nb] pivots of the nodes (not the panel's)
+    void** ptrs = nullptr;          // [ranks][per_class] tile pointers of the workspace copy by residue class, then the pair
+    int* dummy_info = nullptr;      // info of the nodes the reference ignores (every rank but the first)
+    int ranks = 1, per_class = 0;
+    int64_t te = 0;
+    void* raw = nullptr;
+    int init(int64_t mt, int64_t nb, int64_t m, int esize, int ranks, cudaStream_t s);
+    ~TntScratch();
+};
+// tournament panel: see getrf_tnt.cu.  htiles = the panel's tile pointers as the host knows them (stack is the same
+// list on the device); k = block column (global tile row of the panel's first tile)
+template <typename T>
+int getrf_panel_tnt(T* const* stack, const std::vector<T*>& htiles, int64_t k, int nb, int m_p, int kw,
+                    int64_t* piv_tile, int64_t* piv_off, int* dinfo, int info_base,
+                    PanelScratch& ps, TntScratch& ts, cudaStream_t s, int* rowmap, PhaseTimer* ph);
+bool tnt_shape_supported(const Matrix& A);
+// participants per panel of a getrf_tntpiv call on grid g: its process rows, or SB200_TNT_RANKS (test hook: the
+// tournament of a p-row grid on fewer ranks -- the tree never leaves the GPU that holds the gathered panel)
+int tnt_ranks_for(const Grid& g);
 
 // Factor the panel given as a stack of `ntile` tiles (device pointer array `stack`, nb x nb, ld = nb;
 // last tile has m_p - (ntile-1)*nb rows), kw columns.  rowmap (optional, m_p ints, pre-set to the

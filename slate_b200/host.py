@@ -521,7 +521,36 @@ def getrf(A: Matrix, opts: dict | None = None):
     return pivots, int(info.value)
 
 
-lu_factor = getrf
+_getrf_tntpiv = {t: _sig(f"sb200_getrf_tntpiv_{t}", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)]) for t in "sd"}
+
+
+def getrf_tntpiv(A: Matrix, opts: dict | None = None):
+    """LU with tournament pivoting, CALU (slate::getrf_tntpiv, src/getrf_tntpiv.cc).  Returns (pivots, info) as getrf.
+    The participants of a panel's tournament are the process rows of A's grid."""
+    if A.t not in _getrf_tntpiv:
+        raise Exception_(f"getrf_tntpiv is implemented for float and double, not {A.dtype}")
+    o = _opts(opts)
+    info = c_i64(0)
+    mn = min(A.m, A.n)
+    flat = (c_i64 * (2 * max(mn, 1)))()
+    check(_getrf_tntpiv[A.t](A._h, flat, ctypes.byref(o), ctypes.byref(info)), "getrf_tntpiv")
+    piv = np.frombuffer(flat, dtype=np.int64)[: 2 * mn].reshape(-1, 2)
+    nb = A.nb
+    pivots = [list(map(tuple, piv[k0:min(k0 + nb, mn)].tolist())) for k0 in range(0, mn, nb)]
+    return pivots, int(info.value)
+
+
+def lu_factor(A: Matrix, opts: dict | None = None):
+    """slate::lu_factor (src/getrf.cc:320-350): Option::MethodLU picks partial pivoting (default), CALU or NoPiv;
+    NoPiv returns an empty pivot list, as the reference leaves `pivots` untouched."""
+    method = str((opts or {}).get("method_lu", "PPLU")).lower()
+    if method in ("pplu", "partialpiv", "auto"):
+        return getrf(A, opts)
+    if method == "calu":
+        return getrf_tntpiv(A, opts)
+    if method == "nopiv":
+        return [], getrf_nopiv(A, opts)
+    raise Exception_(f"unknown value for MethodLU: {method}")
 
 
 _getrf_nopiv = {t: _sig(f"sb200_getrf_nopiv_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64)]) for t in "sd"}
