@@ -353,6 +353,10 @@ int sb200_potrf_d(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
 /* P A = L U, partial pivoting       (slate::getrf, src/getrf.cc).  pivots: host array of
  * 2*min(m,n) int64 (tileIndex, elementOffset) pairs relative to each panel, as slate::Pivots. */
 int sb200_getrf_d(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
+/* complex LU: the pivot of a column is the first strict maximum of cabs1 = |re| + |im| (src/internal/Tile_getrf.hh:196-237),
+ * the column is scaled by the complex reciprocal of the pivot (:334-361).  1 x 1 grid (SB200_ENOTSUP on p x q grids). */
+int sb200_getrf_z(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
+int sb200_getrf_c(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
 /* LU without pivoting (slate::getrf_nopiv, src/getrf_nopiv.cc:  A = L U, unit lower L); info = first zero pivot + 1 */
 int sb200_getrf_nopiv_d(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
 int sb200_getrf_nopiv_s(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
@@ -463,6 +467,8 @@ int sb200_getrf_tc05_s(sb200_matrix_t A, int64_t* pivots, const sb200_options_t*
 /* B <- A^{-1} B from the LU factors and pivots   slate::getrs (src/getrs.cc:25-66); 1 x 1 grid */
 int sb200_getrs_d(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
 int sb200_getrs_s(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
+int sb200_getrs_z(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
+int sb200_getrs_c(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
 
 /* slate::posv_mixed / gesv_mixed <double, float> (src/posv_mixed.cc:111-297, src/gesv_mixed.cc:106-300):
  * factor a float copy of A (tcgen05 trailing update), solve, refine in FP64 until

@@ -88,21 +88,7 @@ int launch_laswp(T* const* tiles, int64_t ldt, int mb, int nb, int ld, int colma
 // Cooperative panel base block: columns [c0, c0+w) of the panel (tile stack `tiles`, panel rows
 // [c0, m_p) active), rows_per rows per CTA held in shared memory.
 // ------------------------------------------------------------------------------------------
-template <typename T>
-struct BaseArgs {
-    T* const* tiles;
-    int nb, m_p, c0, w, rows_per;
-    int64_t* piv_tile; int64_t* piv_off;
-    T* gval; int* grow; T* gcand; T* gdiag;     // [2][G], [2][G], [2][G][PW], [2][PW]
-    int* info; int info_base;
-    int* rowmap;       // optional: rowmap[x] = panel row whose ORIGINAL content now sits at position x
-    int kw_wide;       // > 0: the LAST CTA of the grid owns no rows and applies every interchange of this
-                       // block to the panel columns outside [c0, c0+w) (all kw_wide columns of the panel)
-                       // while the other CTAs go on factoring -- no laswp launches between blocks
-    unsigned* bar;     // unused (kept: ptxas's register allocation for this kernel depends on the size of the struct)
-};
-// (BaseArgs is left exactly as validated: ptxas's register allocation for getrf_base_kernel changes with the size of
-// its parameter struct -- 64 registers as measured in round 1, 40 + a spill with two more fields.)
+// BaseArgs<T>: getrf_internal.hh (shared with the complex base kernel, getrf_cplx.cu)
 
 // NOPIV = true (getrf_nopiv, src/getrf_nopiv.cc): no candidate is ever proposed, so the diagonal entry is the pivot of
 // every column and the interchange logic below degenerates to the identity; everything else (the diagonal row's
@@ -276,15 +262,15 @@ int PanelScratch::init()
     max_ctas = sms;
     const size_t G = size_t(sms);
     const size_t v3_bytes = base_v3_scratch_bytes(sms);
-    const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 8 + 2 * PW * 8 + 16 * 64 * 64 * 8 + 64 + 16 + v3_bytes;
+    const size_t bytes = 2 * G * 8 + 2 * G * 8 + 2 * G * PW * 16 + 2 * PW * 16 + 16 * 64 * 64 * 16 + 64 + 16 + v3_bytes;      // 16: complex<double> elements
     raw = ws_cache_get(bytes);
     if (! raw) return SB200_ENOMEM;
     char* p = static_cast<char*>(raw);
     gval = reinterpret_cast<double*>(p); p += 2 * G * 8;
     grow = reinterpret_cast<int*>(p);    p += 2 * G * 8;
-    gcand = reinterpret_cast<double*>(p); p += 2 * G * PW * 8;
-    gdiag = reinterpret_cast<double*>(p); p += 2 * PW * 8;
-    W = reinterpret_cast<double*>(p); p += 16 * 64 * 64 * 8;
+    gcand = reinterpret_cast<double*>(p); p += 2 * G * PW * 16;
+    gdiag = reinterpret_cast<double*>(p); p += 2 * PW * 16;
+    W = reinterpret_cast<double*>(p); p += 16 * 64 * 64 * 16;
     bar = reinterpret_cast<unsigned*>(p); p += 64;
     p = static_cast<char*>(raw) + (size_t(p - static_cast<char*>(raw)) + 15) / 16 * 16;      // 16-byte vector accesses
     v3_buf = reinterpret_cast<unsigned long long*>(p);
@@ -327,6 +313,11 @@ static int panel_version()
 template <typename T>
 static int launch_base(BaseArgs<T>& a, int grid, size_t smem, PanelScratch& ps, cudaStream_t s)
 {
+    if constexpr (IsComplex<T>::value) {
+        if (ps.nopiv) return SB200_ENOTSUP;
+        return launch_base_cplx<T>(a, grid, smem, s);
+    }
+    else {
     cudaError_t e;
     if (ps.nopiv) {                                             // getrf_nopiv: the barrier kernel without a pivot search
         void* args[] = {&a};
@@ -338,6 +329,7 @@ static int launch_base(BaseArgs<T>& a, int grid, size_t smem, PanelScratch& ps, 
     }
     if (e != cudaSuccess) return int(e);
     return launch_status();
+    }
 }
 
 namespace {
@@ -354,6 +346,7 @@ struct PanelCtx {
 template <typename T>
 static int panel_base_wide(const PanelCtx<T>& x, int c0, int w, int upd_c0 = -1)
 {
+    if constexpr (! IsComplex<T>::value) {             // the one-round kernels are real-type kernels
     if (x.ps->use_v3) {
         x.pt->begin("pnl_base", x.s);
         SB_TRY(launch_base_v3<T>(x.stack, x.nb, x.m_p, c0, w, x.kw, x.piv_tile, x.piv_off, x.dinfo, x.info_base,
@@ -361,11 +354,13 @@ static int panel_base_wide(const PanelCtx<T>& x, int c0, int w, int upd_c0 = -1)
         x.pt->end(x.s);
         return SB200_OK;
     }
+    }
+    constexpr int rows_max = panel_rows_max<T>();
     const int active = x.m_p - c0;
     const int ctas = x.ps->max_ctas - 1;                       // one SM is kept for the interchange CTA
-    int rows_per = std::max(int(ceil_div(active, ctas)), std::min(active, PROWS_MAX));
+    int rows_per = std::max(int(ceil_div(active, ctas)), std::min(active, rows_max));
     rows_per = std::max(rows_per, PW);
-    if (rows_per > PROWS_MAX) return SB200_ENOTSUP;
+    if (rows_per > rows_max) return SB200_ENOTSUP;
     const int G = int(ceil_div(active, rows_per));
     BaseArgs<T> a{x.stack, x.nb, x.m_p, c0, w, rows_per, x.piv_tile, x.piv_off,
                   reinterpret_cast<T*>(x.ps->gval), x.ps->grow, reinterpret_cast<T*>(x.ps->gcand),
@@ -385,8 +380,9 @@ static int panel_update(const PanelCtx<T>& x, int c0, int w1, int cc, int n2)
 {
     if (n2 <= 0 || w1 <= 0) return SB200_OK;
     const int nb = x.nb;
+    const T ONE = from_real<T>(1), MINUS_ONE = from_real<T>(-1);
     x.pt->begin("pnl_trsm", x.s);
-    SB_TRY(trsm_colmajor<T>(true, true, 'N', true, w1, n2, T(1), x.tile0 + c0 + int64_t(c0) * nb, nb,
+    SB_TRY(trsm_colmajor<T>(true, true, 'N', true, w1, n2, ONE, x.tile0 + c0 + int64_t(c0) * nb, nb,
                            x.stack, c0 + int64_t(cc) * nb, nb, 1, reinterpret_cast<T*>(x.ps->W), x.s));
     x.pt->end(x.s);
     x.pt->begin("pnl_gemm", x.s);
@@ -395,7 +391,7 @@ static int panel_update(const PanelCtx<T>& x, int c0, int w1, int cc, int n2)
     const int top_rows = std::min(nb, x.m_p) - r0;
     if (top_rows > 0) {
         GemmParamsT<T> p{};
-        p.m = top_rows; p.n = n2; p.k = w1; p.alpha = T(-1); p.beta = T(1); p.batch = 1;
+        p.m = top_rows; p.n = n2; p.k = w1; p.alpha = MINUS_ONE; p.beta = ONE; p.batch = 1;
         p.A0 = x.tile0 + r0 + int64_t(c0) * nb; p.lda = nb;
         p.B0 = U12; p.ldb = nb;
         p.C0 = x.tile0 + r0 + int64_t(cc) * nb; p.ldc = nb;
@@ -404,7 +400,7 @@ static int panel_update(const PanelCtx<T>& x, int c0, int w1, int cc, int n2)
     const int full = (x.m_p % nb == 0) ? x.ntile - 1 : x.ntile - 2;      // full-height tiles below tile 0
     if (full > 0) {
         GemmParamsT<T> p{};
-        p.m = nb; p.n = n2; p.k = w1; p.alpha = T(-1); p.beta = T(1); p.batch = full;
+        p.m = nb; p.n = n2; p.k = w1; p.alpha = MINUS_ONE; p.beta = ONE; p.batch = full;
         p.A = x.stack + 1; p.offA = int64_t(c0) * nb; p.lda = nb;
         p.B0 = U12; p.ldb = nb; p.strideB = 0;
         p.C = x.stack + 1; p.offC = int64_t(cc) * nb; p.ldc = nb;
@@ -412,7 +408,7 @@ static int panel_update(const PanelCtx<T>& x, int c0, int w1, int cc, int n2)
     }
     if (x.ntile > 1 && x.m_p % nb != 0) {
         GemmParamsT<T> p{};
-        p.m = x.m_p % nb; p.n = n2; p.k = w1; p.alpha = T(-1); p.beta = T(1); p.batch = 1;
+        p.m = x.m_p % nb; p.n = n2; p.k = w1; p.alpha = MINUS_ONE; p.beta = ONE; p.batch = 1;
         p.A = x.stack + (x.ntile - 1); p.offA = int64_t(c0) * nb; p.lda = nb;
         p.B0 = U12; p.ldb = nb;
         p.C = x.stack + (x.ntile - 1); p.offC = int64_t(cc) * nb; p.ldc = nb;
@@ -432,7 +428,9 @@ static int panel_recurse(const PanelCtx<T>& x, int c0, int w)
     if (w1 >= w) w1 = w - PW;
     SB_TRY(panel_recurse<T>(x, c0, w1));
     // a 32-column block that follows a 32-column block takes that block's update inside its own launch
-    if (base_v3_can_fuse(*x.ps, x.m_p, c0 + w1, w1, w - w1)) return panel_base_wide<T>(x, c0 + w1, w - w1, c0);
+    if constexpr (! IsComplex<T>::value) {
+        if (base_v3_can_fuse(*x.ps, x.m_p, c0 + w1, w1, w - w1)) return panel_base_wide<T>(x, c0 + w1, w - w1, c0);
+    }
     SB_TRY(panel_update<T>(x, c0, w1, c0 + w1, w - w1));
     return panel_recurse<T>(x, c0 + w1, w - w1);
 }
@@ -461,12 +459,14 @@ static int getrf_panel_v1(T* const* stack, T* tile0, int ntile, int nb, int m_p,
     off_timer.on = false;
     PhaseTimer& pt = ph ? *ph : off_timer;
     const int diag_len = std::min(m_p, kw);
+    const T ONE = from_real<T>(1), MINUS_ONE = from_real<T>(-1);
+    constexpr int rows_max = panel_rows_max<T>();
     for (int c0 = 0; c0 < diag_len; c0 += PW) {
         const int w = std::min(PW, diag_len - c0);
         const int active = m_p - c0;
-        int rows_per = std::max(int(ceil_div(active, ps.max_ctas)), std::min(active, PROWS_MAX));
+        int rows_per = std::max(int(ceil_div(active, ps.max_ctas)), std::min(active, rows_max));
         rows_per = std::max(rows_per, PW);
-        if (rows_per > PROWS_MAX) return SB200_ENOTSUP;       // panel taller than 148 * 768 rows
+        if (rows_per > rows_max) return SB200_ENOTSUP;       // panel taller than 148 * 768 rows
         const int G = int(ceil_div(active, rows_per));
         BaseArgs<T> a{stack, nb, m_p, c0, w, rows_per, piv_tile, piv_off,
                       reinterpret_cast<T*>(ps.gval), ps.grow, reinterpret_cast<T*>(ps.gcand),
@@ -484,7 +484,7 @@ static int getrf_panel_v1(T* const* stack, T* tile0, int ntile, int nb, int m_p,
         if (rest <= 0) continue;
         // U12 = L11^{-1} A12  (top tile, rows c0..c0+w)
         pt.begin("pnl_trsm", s);
-        SB_TRY(trsm_colmajor<T>(true, true, 'N', true, w, rest, T(1), tile0 + c0 + int64_t(c0) * nb, nb,
+        SB_TRY(trsm_colmajor<T>(true, true, 'N', true, w, rest, ONE, tile0 + c0 + int64_t(c0) * nb, nb,
                                stack, c0 + int64_t(c0 + w) * nb, nb, 1, reinterpret_cast<T*>(ps.W), s));
         pt.end(s);
         pt.begin("pnl_gemm", s);
@@ -493,7 +493,7 @@ static int getrf_panel_v1(T* const* stack, T* tile0, int ntile, int nb, int m_p,
         const int top_rows = std::min(nb, m_p) - (c0 + w);
         if (top_rows > 0) {
             GemmParamsT<T> p{};
-            p.m = top_rows; p.n = rest; p.k = w; p.alpha = T(-1); p.beta = T(1); p.batch = 1;
+            p.m = top_rows; p.n = rest; p.k = w; p.alpha = MINUS_ONE; p.beta = ONE; p.batch = 1;
             p.A0 = tile0 + (c0 + w) + int64_t(c0) * nb; p.lda = nb;
             p.B0 = U12; p.ldb = nb;
             p.C0 = tile0 + (c0 + w) + int64_t(c0 + w) * nb; p.ldc = nb;
@@ -502,7 +502,7 @@ static int getrf_panel_v1(T* const* stack, T* tile0, int ntile, int nb, int m_p,
         const int full = (m_p % nb == 0) ? ntile - 1 : ntile - 2;      // full-height tiles below tile 0
         if (full > 0) {
             GemmParamsT<T> p{};
-            p.m = nb; p.n = rest; p.k = w; p.alpha = T(-1); p.beta = T(1); p.batch = full;
+            p.m = nb; p.n = rest; p.k = w; p.alpha = MINUS_ONE; p.beta = ONE; p.batch = full;
             p.A = stack + 1; p.offA = int64_t(c0) * nb; p.lda = nb;
             p.B0 = U12; p.ldb = nb; p.strideB = 0;
             p.C = stack + 1; p.offC = int64_t(c0 + w) * nb; p.ldc = nb;
@@ -510,7 +510,7 @@ static int getrf_panel_v1(T* const* stack, T* tile0, int ntile, int nb, int m_p,
         }
         if (ntile > 1 && m_p % nb != 0) {
             GemmParamsT<T> p{};
-            p.m = m_p % nb; p.n = rest; p.k = w; p.alpha = T(-1); p.beta = T(1); p.batch = 1;
+            p.m = m_p % nb; p.n = rest; p.k = w; p.alpha = MINUS_ONE; p.beta = ONE; p.batch = 1;
             p.A = stack + (ntile - 1); p.offA = int64_t(c0) * nb; p.lda = nb;
             p.B0 = U12; p.ldb = nb;
             p.C = stack + (ntile - 1); p.offC = int64_t(c0 + w) * nb; p.ldc = nb;
@@ -557,6 +557,7 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
     const int64_t kt = std::min(mt, nt);
     const int64_t mn = std::min(A.m, A.n);
     if (mn == 0) { if (info_out) *info_out = 0; return SB200_OK; }
+    const T ONE = from_real<T>(1), MINUS_ONE = from_real<T>(-1);
 
     // packed operands of the tcgen05 path: L(i,k) in slot [k & 1][i], U(k,j) in slot [k & 1][j]
     DevBuf packA, packB;
@@ -650,7 +651,7 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
     cudaStream_t P = st.panel, T_ = st.trail;
     TntScratch tnt;                                       // getrf_tntpiv only
     if (ps.tnt_ranks > 0) {
-        if (use_tc05 || ! tnt_shape_supported(A)) return SB200_ENOTSUP;
+        if (use_tc05 || IsComplex<T>::value || ! tnt_shape_supported(A)) return SB200_ENOTSUP;
         SB_TRY(tnt.init(mt, nb, A.m, int(sizeof(T)), ps.tnt_ranks, P));
     }
     auto P_done = [&](int64_t k) { return st.ev[size_t(k)]; };
@@ -665,7 +666,7 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
         if constexpr (is_float) {
             if (use_tc05) return launch_batches_tc05(bs, pb, -1.0f, 1.0f, ld, s);
         }
-        return launch_batches<T>(bs, pb, 'N', b_transposed ? 'T' : 'N', T(-1), T(1), ld, 0, s);
+        return launch_batches<T>(bs, pb, 'N', b_transposed ? 'T' : 'N', MINUS_ONE, ONE, ld, 0, s);
     };
     // split-pack `cnt` tiles (full-size ones first, then the ragged one) for one operand role
     auto pack = [&](int role, size_t src_off, size_t dst_off, int cnt, int full, int rows_full, int rows_last,
@@ -694,10 +695,10 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
         const int kw = int(std::min(A.tile_mb(k), A.tile_nb(k)));
         const int64_t jfull_end = (A.tile_nb(nt - 1) == nb) ? j1 : std::min(j1, nt - 1);
         if (jfull_end > j0)
-            SB_TRY(trsm_colmajor<T>(true, true, 'N', true, kw, int(nb), T(1), A.tile_as<T>(k, k), ld,
+            SB_TRY(trsm_colmajor<T>(true, true, 'N', true, kw, int(nb), ONE, A.tile_as<T>(k, k), ld,
                                     dtblT + j0 + k * nt, 0, ld, int(jfull_end - j0), W, s));
         if (jfull_end < j1)
-            SB_TRY(trsm_colmajor<T>(true, true, 'N', true, kw, int(A.tile_nb(nt - 1)), T(1), A.tile_as<T>(k, k), ld,
+            SB_TRY(trsm_colmajor<T>(true, true, 'N', true, kw, int(A.tile_nb(nt - 1)), ONE, A.tile_as<T>(k, k), ld,
                                     dtblT + (nt - 1) + k * nt, 0, ld, 1, W, s));
         return SB200_OK;
     };
@@ -715,13 +716,17 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
         T* const* stack_k = dtbl + k + k * mt;
         // ---- panel k (column k already carries every earlier update: lookahead below)
         SB_TRY(st.ptime(P));
-        if (ps.tnt_ranks > 0) {
-            std::vector<T*> htiles;
-            for (int64_t i = k; i < mt; ++i) htiles.push_back(A.tile_as<T>(i, k));
-            SB_TRY(getrf_panel_tnt<T>(stack_k, htiles, k, int(nb), m_p, kw, pt, po, dinfo.as<int>(), int(k * nb), ps, tnt, P,
-                                      nullptr, &ph));
+        bool tnt_done = false;
+        if constexpr (! IsComplex<T>::value) {
+            if (ps.tnt_ranks > 0) {
+                std::vector<T*> htiles;
+                for (int64_t i = k; i < mt; ++i) htiles.push_back(A.tile_as<T>(i, k));
+                SB_TRY(getrf_panel_tnt<T>(stack_k, htiles, k, int(nb), m_p, kw, pt, po, dinfo.as<int>(), int(k * nb), ps, tnt, P,
+                                          nullptr, &ph));
+                tnt_done = true;
+            }
         }
-        else
+        if (! tnt_done)
         SB_TRY(getrf_panel<T>(stack_k, A.tile_as<T>(k, k), int(mt - k), int(nb), m_p, kw, pt, po, dinfo.as<int>(),
                               int(k * nb), ps, P, nullptr, &ph));
         if (use_tc05 && ! sk.a_src.empty()) {
@@ -829,6 +834,15 @@ int getrf_driver_s(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
     return getrf_driver_t<float>(A, pivots_out, info_out, use_tc05);
 }
 
+// complex LU (1 x 1 grid): the same driver, base blocks by getrf_cplx.cu, trailing update on the complex GEMM kernels
+int getrf_driver_cplx(Matrix& A, int64_t* pivots_out, int64_t* info_out)
+{
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.dtype == 'z') return getrf_driver_t<cuDoubleComplex>(A, pivots_out, info_out, false);
+    if (A.dtype == 'c') return getrf_driver_t<cuFloatComplex>(A, pivots_out, info_out, false);
+    return SB200_EINVAL;
+}
+
 template int getrf_panel<double>(double* const*, double*, int, int, int, int, int64_t*, int64_t*, int*, int, PanelScratch&, cudaStream_t, int*, PhaseTimer*);
 template int getrf_panel<float>(float* const*, float*, int, int, int, int, int64_t*, int64_t*, int*, int, PanelScratch&, cudaStream_t, int*, PhaseTimer*);
 
@@ -867,6 +881,20 @@ static int getrf_tntpiv_any(sb200_matrix_t h, int64_t* pivots, int64_t* info, bo
 }
 int sb200_getrf_tntpiv_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, false); }
 int sb200_getrf_tntpiv_s(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, true); }
+
+/* complex LU with partial pivoting (cabs1 rule); 1 x 1 grid */
+int sb200_getrf_z(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
+{
+    SB_TRY(options_status(opts));
+    if (! h || h->A.dtype != 'z') return SB200_EINVAL;
+    return getrf_driver_cplx(h->A, pivots, info);
+}
+int sb200_getrf_c(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
+{
+    SB_TRY(options_status(opts));
+    if (! h || h->A.dtype != 'c') return SB200_EINVAL;
+    return getrf_driver_cplx(h->A, pivots, info);
+}
 
 int sb200_getrf_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)
 {

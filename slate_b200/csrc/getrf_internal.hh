@@ -7,6 +7,8 @@ namespace sb200 {
 constexpr int PW = 32;            // panel base-block width (the tester's ib 32)
 constexpr int PROWS_MAX = 768;    // rows of the block one CTA keeps in shared memory
 constexpr int PTHREADS = 256;
+// complex<double> blocks keep half as many rows per CTA (16-byte elements: 32 x 385 x 16 B = 197 KB of shared memory)
+template <typename T> constexpr int panel_rows_max() { return sizeof(T) > 8 ? PROWS_MAX / 2 : PROWS_MAX; }
 constexpr int V3_NWIDE = 4;       // interchange CTAs of the one-round base kernel (getrf_base_v3.cu)
 
 // scratch of the cooperative panel kernel (per driver call)
@@ -24,6 +26,27 @@ struct PanelScratch {
     int init();
     ~PanelScratch();
 };
+
+// arguments of the cooperative base-block kernels (getrf.cu: float / double; getrf_cplx.cu: complex)
+template <typename T>
+struct BaseArgs {
+    T* const* tiles;
+    int nb, m_p, c0, w, rows_per;
+    int64_t* piv_tile; int64_t* piv_off;
+    T* gval; int* grow; T* gcand; T* gdiag;     // [2][G], [2][G], [2][G][PW], [2][PW]
+    int* info; int info_base;
+    int* rowmap;       // optional: rowmap[x] = panel row whose ORIGINAL content now sits at position x
+    int kw_wide;       // > 0: the LAST CTA of the grid owns no rows and applies every interchange of this
+                       // block to the panel columns outside [c0, c0+w) (all kw_wide columns of the panel)
+                       // while the other CTAs go on factoring -- no laswp launches between blocks
+    unsigned* bar;     // unused (kept: ptxas's register allocation for this kernel depends on the size of the struct)
+};
+// (BaseArgs is left exactly as validated: ptxas's register allocation for getrf_base_kernel changes with the size of
+// its parameter struct -- 64 registers as measured in round 1, 40 + a spill with two more fields.)
+
+
+// complex base block (getrf_cplx.cu)
+template <typename T> int launch_base_cplx(BaseArgs<T>& a, int grid, size_t smem, cudaStream_t s);
 
 // scratch of the tournament panel (getrf_tnt.cu), per driver call
 struct TntScratch {
@@ -72,6 +95,7 @@ int getrf_panel(T* const* stack, T* tile0, int ntile, int nb, int m_p, int kw,
                 PanelScratch& ps, cudaStream_t s, int* rowmap, PhaseTimer* ph);
 int getrf_driver(Matrix& A, int64_t* pivots_out, int64_t* info_out);                      // FP64, any grid
 int getrf_driver_s(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_tc05);     // FP32, 1 x 1 grid
+int getrf_driver_cplx(Matrix& A, int64_t* pivots_out, int64_t* info_out);                 // complex<float> / complex<double>, 1 x 1 grid
 
 // one-round base block (getrf_base_v3.cu)
 size_t base_v3_scratch_bytes(int max_ctas);

@@ -240,10 +240,10 @@ int getrf_panel_tnt(T* const* stack, const std::vector<T*>& htiles, int64_t k, i
         const int last_rows = rows_of_tile(ntile - 1);
         const int full = last_rows == nb ? ntile - 1 : ntile - 2;
         if (full > 0)
-            SB_TRY(trsm_colmajor<T>(false, false, 'N', false, nb, kw, T(1), htiles[0], nb, stack + 1, 0, nb, full,
+            SB_TRY(trsm_colmajor<T>(false, false, 'N', false, nb, kw, from_real<T>(1), htiles[0], nb, stack + 1, 0, nb, full,
                                     reinterpret_cast<T*>(ps.W), s));
         if (full < ntile - 1)
-            SB_TRY(trsm_colmajor<T>(false, false, 'N', false, last_rows, kw, T(1), htiles[0], nb, stack + (ntile - 1), 0, nb, 1,
+            SB_TRY(trsm_colmajor<T>(false, false, 'N', false, last_rows, kw, from_real<T>(1), htiles[0], nb, stack + (ntile - 1), 0, nb, 1,
                                     reinterpret_cast<T*>(ps.W), s));
     }
     pt.end(s);

@@ -795,6 +795,8 @@ static int getrs_any(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B)
     CUDA_TRY(cudaMemcpy(dp.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
     if (A->A.dtype == 'd') return getrs_t<double>(A->A, dp.as<int>(), B->A, nullptr);
     if (A->A.dtype == 's') return getrs_t<float>(A->A, dp.as<int>(), B->A, nullptr);
+    if (A->A.dtype == 'z') return getrs_t<cuDoubleComplex>(A->A, dp.as<int>(), B->A, nullptr);
+    if (A->A.dtype == 'c') return getrs_t<cuFloatComplex>(A->A, dp.as<int>(), B->A, nullptr);
     return SB200_ENOTSUP;
 }
 
@@ -802,6 +804,12 @@ int sb200_getrs_d(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, con
 { SB_TRY(options_status(opts)); return (A && A->A.dtype == 'd') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
 int sb200_getrs_s(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts)
 { SB_TRY(options_status(opts)); return (A && A->A.dtype == 's') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
+
+/* complex solves from the factors of sb200_getrf_{z,c}; 1 x 1 grid */
+int sb200_getrs_z(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts)
+{ SB_TRY(options_status(opts)); return (A && A->A.dtype == 'z') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
+int sb200_getrs_c(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts)
+{ SB_TRY(options_status(opts)); return (A && A->A.dtype == 'c') ? getrs_any(A, pivots, B) : SB200_EINVAL; }
 
 int sb200_posv_mixed_d(sb200_matrix_t A, sb200_matrix_t B, sb200_matrix_t Xm, const sb200_mixed_options_t* mo,
                        int* iter, int64_t* info, double* timers_ms8)

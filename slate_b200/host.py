@@ -79,8 +79,10 @@ _potrs = {t: _sig(f"sb200_potrs_{t}", [c_ptr, c_ptr, _OP]) for t in "sdcz"}
 _norm_inf = {t: _sig(f"sb200_norm_inf_{t}", [c_ptr, ctypes.POINTER(c_dbl)]) for t in "sdcz"}
 _getrf = {"d": _sig("sb200_getrf_d", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)]),
           "s": _sig("sb200_getrf_s", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)]),
+          "z": _sig("sb200_getrf_z", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)]),
+          "c": _sig("sb200_getrf_c", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)]),
           "s_tc05": _sig("sb200_getrf_tc05_s", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)])}
-_getrs = {t: _sig(f"sb200_getrs_{t}", [c_ptr, ctypes.POINTER(c_i64), c_ptr, _OP]) for t in "sd"}
+_getrs = {t: _sig(f"sb200_getrs_{t}", [c_ptr, ctypes.POINTER(c_i64), c_ptr, _OP]) for t in "sdcz"}
 _posv_mixed = _sig("sb200_posv_mixed_d", [c_ptr, c_ptr, c_ptr, ctypes.POINTER(_MixedOptions), ctypes.POINTER(c_int),
                                           ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)])
 _gesv_mixed = _sig("sb200_gesv_mixed_d", [c_ptr, ctypes.POINTER(c_i64), c_ptr, c_ptr, ctypes.POINTER(_MixedOptions),
@@ -513,7 +515,7 @@ def getrf(A: Matrix, opts: dict | None = None):
             raise Exception_("tensor_core_fp32 applies to float matrices")
         key = "s_tc05"
     if key not in _getrf:
-        raise Exception_(f"getrf is implemented for float and double, not {A.dtype}")
+        raise Exception_(f"getrf is not implemented for {A.dtype}")
     check(_getrf[key](A._h, flat, ctypes.byref(o), ctypes.byref(info)), "getrf")
     piv = np.frombuffer(flat, dtype=np.int64)[: 2 * mn].reshape(-1, 2)
     nb = A.nb
@@ -573,7 +575,7 @@ def getrs(A: Matrix, pivots, B: Matrix, opts: dict | None = None):
     """Solve A X = B with the LU factors and pivots from getrf; B is overwritten (slate::getrs, src/getrs.cc)."""
     t = _same_type(A, B)
     if t not in _getrs:
-        raise Exception_(f"getrs is implemented for float and double, not {A.dtype}")
+        raise Exception_(f"getrs is not implemented for {A.dtype}")
     o = _opts(opts)
     check(_getrs[t](A._h, _pivots_flat(pivots), B._h, ctypes.byref(o)), "getrs")
 

@@ -25,6 +25,7 @@ generator fixture pins that), only outputs:
   syrk_z.npz, syr2k_z.npz   complex-symmetric rank-k / rank-2k updates (no conjugation), n=200 k=100 nb=64
   getrf_nopiv_d.npz      LU without pivoting, rand_dominant, n=300 nb=128 (ragged)
   her2k_d.npz, her2k_z.npz  C = alpha A B^H + conj(alpha) B A^H + beta C lower, n=200 k=100 nb=64 (ragged tiles)
+  getrf_z.npz, getrf_c.npz  complex LU and pivots (cabs1 rule), n=192 / 200 (ragged) nb=64; gesv_z.npz its solve, n=200 nrhs=70
   getrf_tntpiv_d{,_ragged,_tall}.npz   LU with tournament pivoting (MethodLU::CALU), 384x384 / 300x300 / 512x256, nb=128
 
 Usage (in the build container, where /root/reference exists):  python tests/golden/make_golden.py
@@ -63,6 +64,17 @@ def tntpiv_fixtures():
         f, meta = run("getrf", "d", n, 128, ib=16, pt=1, method="calu", m=m)
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), out=f["out"].reshape(m, n, order="F"),
                             piv=f["piv"].reshape(-1, 2), info=meta["info"])
+
+
+def complex_lu_fixtures():
+    f, meta = run("getrf", "z", 192, 64, ib=16, pt=1)
+    np.savez_compressed(os.path.join(OUT, "getrf_z.npz"), out=f["out"].reshape(192, 192, order="F"),
+                        piv=f["piv"].reshape(-1, 2), info=meta["info"])
+    f, meta = run("getrf", "c", 200, 64, ib=16, pt=1)
+    np.savez_compressed(os.path.join(OUT, "getrf_c.npz"), out=f["out"].reshape(200, 200, order="F"),
+                        piv=f["piv"].reshape(-1, 2), info=meta["info"])
+    f, meta = run("gesv", "z", 200, 64, ib=16, pt=1, nrhs=70)
+    np.savez_compressed(os.path.join(OUT, "gesv_z.npz"), out=f["out"].reshape(200, 70, order="F"), info=meta["info"])
 
 
 def main():
@@ -122,10 +134,14 @@ def main():
     np.savez_compressed(os.path.join(OUT, "getrf_nopiv_d.npz"), out=f["out"].reshape(300, 300, order="F"), info=meta["info"])
     # section 8(f) item 2 widening: LU with tournament pivoting (one rank: the serial MPI stub)
     tntpiv_fixtures()
+    # complex LU (cabs1 pivot rule, src/internal/Tile_getrf.hh:210-237) and its solve
+    complex_lu_fixtures()
     print("golden fixtures written to", OUT)
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tntpiv":
         tntpiv_fixtures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "complex_lu":
+        complex_lu_fixtures()
     else:
         main()

@@ -188,6 +188,30 @@ def test_tnt_winners_to_sequential_is_the_reference_example():
     assert list(row_at[:4]) == [5, 3, 0, 2]
 
 
+@pytest.mark.parametrize("name,n,dt", [("getrf_z", 192, np.complex128), ("getrf_c", 200, np.complex64)])
+def test_complex_getrf_matches_reference_with_identical_pivots(golden_dir, name, n, dt):
+    """cabs1 pivot rule (|re| + |im|, src/internal/Tile_getrf.hh:210-237), complex reciprocal scaling."""
+    g = load(golden_dir, name)
+    A = o.generate("rand", n, n, 42, dtype=dt)
+    LU, piv, info = o.getrf(A, 64, 16)
+    flat = np.array([p for col in piv for p in col], dtype=np.int64)
+    assert np.array_equal(flat, g["piv"]), "pivot vectors differ from the reference"
+    assert info == int(g["info"]) == 0
+    eps = np.finfo(dt).eps
+    assert np.abs(LU - g["out"]).max() <= 1024 * eps * np.abs(g["out"]).max()
+
+
+def test_complex_gesv_matches_reference(golden_dir):
+    g = load(golden_dir, "gesv_z")
+    n, nb, nrhs = 200, 64, 70
+    A = o.generate("rand", n, n, 42, dtype=np.complex128)
+    B = o.generate("rand", n, nrhs, 43, dtype=np.complex128)
+    LU, piv, info = o.getrf(A, nb, 16)
+    X = o.getrs(LU, piv, B, nb)
+    assert info == int(g["info"]) == 0
+    assert np.abs(X - g["out"]).max() <= 1e-11 * np.abs(g["out"]).max()
+
+
 def test_trsm_matches_reference(golden_dir):
     g = load(golden_dir, "trsm_d")
     m, n = 256, 128
