@@ -486,6 +486,12 @@ int sb200_posv_mixed_d(sb200_matrix_t A, sb200_matrix_t B, sb200_matrix_t X, con
                        int* iter, int64_t* info, double* timers_ms8);
 int sb200_gesv_mixed_d(sb200_matrix_t A, int64_t* pivots, sb200_matrix_t B, sb200_matrix_t X,
                        const sb200_mixed_options_t* mo, int* iter, int64_t* info, double* timers_ms8);
+/* <complex<double>, complex<float>> (the second pair of explicit instantiations, src/gesv_mixed.cc:303-316): complex<float>
+ * factorisation, complex<double> refinement; same conventions.  1 x 1 grid. */
+int sb200_posv_mixed_z(sb200_matrix_t A, sb200_matrix_t B, sb200_matrix_t X, const sb200_mixed_options_t* mo,
+                       int* iter, int64_t* info, double* timers_ms8);
+int sb200_gesv_mixed_z(sb200_matrix_t A, int64_t* pivots, sb200_matrix_t B, sb200_matrix_t X,
+                       const sb200_mixed_options_t* mo, int* iter, int64_t* info, double* timers_ms8);
 
 #ifdef __cplusplus
 }

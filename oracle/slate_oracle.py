@@ -640,26 +640,28 @@ def solve_mixed(A, B, nb: int, hermitian: bool, itermax: int = 30, tol=None, use
                 ib: int = 16):
     """posv_mixed / gesv_mixed <double, float> (src/posv_mixed.cc:111-297, src/gesv_mixed.cc:106-300).
     A: full matrix (gesv) or lower triangle (posv).  Returns (X, iter, info)."""
-    A = np.asarray(A, dtype=np.float64)
-    B = np.asarray(B, dtype=np.float64)
+    # <double, float> or <complex<double>, complex<float>> (the explicit instantiations, gesv_mixed.cc:303-316)
+    hi, lo = (np.complex128, np.complex64) if np.iscomplexobj(A) else (np.float64, np.float32)
+    A = np.asarray(A, dtype=hi)
+    B = np.asarray(B, dtype=hi)
     n = A.shape[0]
     eps = np.finfo(np.float64).eps
     tol = eps * np.sqrt(n) if tol is None else tol
     Afull = he_full(A) if hermitian else A
     cte = norm_inf(A, hermitian) * tol
-    A_lo = (np.tril(A) if hermitian else A).astype(np.float32)
+    A_lo = (np.tril(A) if hermitian else A).astype(lo)
     if hermitian:
         F_lo, info = potrf(he_full(A_lo), nb)
-        solve_lo = lambda R: potrs(F_lo, R.astype(np.float32), nb)
+        solve_lo = lambda R: potrs(F_lo, R.astype(lo), nb)
     else:
         F_lo, piv, info = getrf(A_lo, nb, ib)
-        solve_lo = lambda R: getrs(F_lo, piv, R.astype(np.float32), nb)
+        solve_lo = lambda R: getrs(F_lo, piv, R.astype(lo), nb)
     converged, it = False, 0
     X = np.zeros_like(B)
     if info != 0:
         it = -3
     else:
-        X = solve_lo(B).astype(np.float64)
+        X = solve_lo(B).astype(hi)
         R = B - Afull @ X
         cm = lambda M: np.abs(M).max(axis=0)
         if iter_ref_converged(cm(R), cm(X), cte):
@@ -667,7 +669,7 @@ def solve_mixed(A, B, nb: int, hermitian: bool, itermax: int = 30, tol=None, use
         for iiter in range(itermax):
             if converged:
                 break
-            X = X + solve_lo(R).astype(np.float64)
+            X = X + solve_lo(R).astype(hi)
             R = B - Afull @ X
             if iter_ref_converged(cm(R), cm(X), cte):
                 it, converged = iiter + 1, True

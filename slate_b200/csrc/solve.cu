@@ -721,6 +721,166 @@ int solve_mixed_d(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B, Mat
     return SB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// posv_mixed / gesv_mixed, complex<double> <- complex<float> (the second pair of explicit instantiations,
+// src/gesv_mixed.cc:303-316, src/posv_mixed.cc): the control flow of solve_mixed_d with the complex drivers -- complex<float>
+// Cholesky (runtime.cu) / complex<float> LU (getrf_cplx.cu), complex solves, zhemm / zgemm residual on the split-complex DMMA
+// kernel, moduli in the column norms (colNorms uses std::abs).  1 x 1 grid.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) convert_z2c_kernel(const cuDoubleComplex* __restrict__ src, cuFloatComplex* __restrict__ dst, int64_t count)
+{
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < count; e += int64_t(gridDim.x) * blockDim.x)
+        dst[e] = make_cuFloatComplex(float(src[e].x), float(src[e].y));
+}
+__global__ void __launch_bounds__(256) convert_c2z_kernel(const cuFloatComplex* __restrict__ src, cuDoubleComplex* __restrict__ dst, int64_t count)
+{
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < count; e += int64_t(gridDim.x) * blockDim.x)
+        dst[e] = make_cuDoubleComplex(double(src[e].x), double(src[e].y));
+}
+static int convert_pool_z2c(const Matrix& src, Matrix& dst, cudaStream_t s)
+{
+    const int64_t count = src.ntiles_loc * src.tile_elems();
+    if (dst.ntiles_loc != src.ntiles_loc || dst.nb != src.nb || src.dtype != 'z' || dst.dtype != 'c') return SB200_EINVAL;
+    if (count == 0) return SB200_OK;
+    convert_z2c_kernel<<<ew_grid(count), 256, 0, s>>>(reinterpret_cast<const cuDoubleComplex*>(src.pool),
+                                                      reinterpret_cast<cuFloatComplex*>(dst.pool), count);
+    return launch_status();
+}
+static int convert_pool_c2z(const Matrix& src, Matrix& dst, cudaStream_t s)
+{
+    const int64_t count = src.ntiles_loc * src.tile_elems();
+    if (dst.ntiles_loc != src.ntiles_loc || dst.nb != src.nb || src.dtype != 'c' || dst.dtype != 'z') return SB200_EINVAL;
+    if (count == 0) return SB200_OK;
+    convert_c2z_kernel<<<ew_grid(count), 256, 0, s>>>(reinterpret_cast<const cuFloatComplex*>(src.pool),
+                                                      reinterpret_cast<cuDoubleComplex*>(dst.pool), count);
+    return launch_status();
+}
+
+int solve_mixed_z(bool hermitian, Matrix& A, int64_t* pivots_out, Matrix& B, Matrix& X,
+                  int64_t itermax, double tol, bool use_fallback, int* iter_out, int64_t* info_out, double* timers_ms)
+{
+    using Z = cuDoubleComplex;
+    using C = cuFloatComplex;
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.dtype != 'z' || B.dtype != 'z' || X.dtype != 'z') return SB200_EINVAL;
+    if (A.kind != (hermitian ? 'H' : 'G') || A.m != A.n || B.m != A.n || X.m != A.n || X.n != B.n
+        || B.nb != A.nb || X.nb != A.nb || B.kind != 'G' || X.kind != 'G') return SB200_EINVAL;
+    const double eps = std::numeric_limits<double>::epsilon();
+    if (tol <= 0) tol = eps * std::sqrt(double(A.m));
+    if (itermax < 0) itermax = 30;
+    double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    Clock total, c;
+    total.start();
+    cudaStream_t s = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    struct SG { cudaStream_t s; ~SG() { cudaStreamDestroy(s); } } sguard{s};
+
+    TmpMatrix Rm, A_lo, X_lo;
+    SB_TRY(Rm.like(B, 'z'));
+    SB_TRY(A_lo.like(A, 'c'));
+    SB_TRY(X_lo.like(X, 'c'));
+    DevBuf dnorm, dperm;
+    SB_TRY(dnorm.alloc(size_t(std::max<int64_t>(X.n, 1)) * sizeof(double)));
+    std::vector<double> cn_x, cn_r;
+    std::vector<int64_t> piv_lo(size_t(2 * std::max<int64_t>(A.m, 1)));
+    std::vector<int> perm;
+    const Z one = make_cuDoubleComplex(1.0, 0.0), minus_one = make_cuDoubleComplex(-1.0, 0.0);
+
+    c.start();
+    double Anorm = 0;
+    SB_TRY(norm_inf<Z>(A, &Anorm, s));
+    const double cte = Anorm * tol;
+    SB_TRY(convert_pool_z2c(B, X_lo.M, s));
+    SB_TRY(convert_pool_z2c(A, A_lo.M, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    tm[7] = c.stop();
+
+    bool converged = false;
+    int iter = 0;
+    int64_t info = 0;
+    c.start();
+    if (hermitian) SB_TRY(potrf_driver<C>(A_lo.M, &info, false));
+    else           SB_TRY(getrf_driver_cplx(A_lo.M, piv_lo.data(), &info));
+    tm[1] = c.stop();
+    X.last_trail_ms = A_lo.M.last_trail_ms; X.last_trail_flops = A_lo.M.last_trail_flops;
+    X.last_trail_launches = A_lo.M.last_trail_launches; X.last_panel_ms = A_lo.M.last_panel_ms;
+
+    auto solve_lo = [&]() -> int {
+        c.start();
+        if (hermitian) SB_TRY(potrs_t<C>(A_lo.M, X_lo.M, s));
+        else           SB_TRY(getrs_t<C>(A_lo.M, dperm.as<int>(), X_lo.M, s));
+        tm[2] += c.stop();
+        return SB200_OK;
+    };
+    auto residual = [&]() -> int {          // R = B - A X
+        c.start();
+        SB_TRY(copy_pool(B, Rm.M, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (hermitian) SB_TRY(hemm_left_lower<Z>(minus_one, A, X, one, Rm.M, s));
+        else           SB_TRY(gemm_driver<Z>(minus_one, A, X, one, Rm.M));
+        tm[3] += c.stop();
+        SB_TRY(col_norms_max<Z>(X, cn_x, dnorm.as<double>(), s));
+        SB_TRY(col_norms_max<Z>(Rm.M, cn_r, dnorm.as<double>(), s));
+        return SB200_OK;
+    };
+
+    if (info != 0) iter = -3;
+    else {
+        if (! hermitian) {
+            pivots_to_perm(piv_lo.data(), A.m, A.n, A.nb, perm);
+            SB_TRY(dperm.alloc(perm.size() * sizeof(int)));
+            CUDA_TRY(cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+        SB_TRY(solve_lo());
+        SB_TRY(convert_pool_c2z(X_lo.M, X, s));
+        SB_TRY(residual());
+        if (iter_ref_converged(cn_r, cn_x, cte)) { iter = 0; converged = true; }
+        for (int64_t iiter = 0; iiter < itermax && ! converged; ++iiter) {
+            SB_TRY(convert_pool_z2c(Rm.M, X_lo.M, s));
+            SB_TRY(solve_lo());
+            c.start();
+            SB_TRY(convert_pool_c2z(X_lo.M, Rm.M, s));
+            SB_TRY(add_pool<Z>(Rm.M, X, s));
+            tm[4] += c.stop();
+            SB_TRY(residual());
+            if (iter_ref_converged(cn_r, cn_x, cte)) { iter = int(iiter) + 1; converged = true; }
+        }
+    }
+    if (! converged) {
+        if (info == 0) iter = -int(itermax) - 1;
+        if (use_fallback) {
+            c.start();
+            if (hermitian) SB_TRY(potrf_driver<Z>(A, &info, false));
+            else           SB_TRY(getrf_driver_cplx(A, pivots_out ? pivots_out : piv_lo.data(), &info));
+            tm[5] = c.stop();
+            c.start();
+            if (info == 0) {
+                SB_TRY(copy_pool(B, X, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                if (hermitian) SB_TRY(potrs_t<Z>(A, X, s));
+                else {
+                    const int64_t* pv = pivots_out ? pivots_out : piv_lo.data();
+                    pivots_to_perm(pv, A.m, A.n, A.nb, perm);
+                    DevBuf dp;
+                    SB_TRY(dp.alloc(perm.size() * sizeof(int)));
+                    CUDA_TRY(cudaMemcpyAsync(dp.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+                    SB_TRY(getrs_t<Z>(A, dp.as<int>(), X, s));
+                }
+            }
+            tm[6] = c.stop();
+        }
+    }
+    else if (pivots_out && ! hermitian)
+        memcpy(pivots_out, piv_lo.data(), size_t(2 * std::min(A.m, A.n)) * sizeof(int64_t));
+    tm[0] = total.stop();
+    X.last_ms = tm[0];
+    if (timers_ms) memcpy(timers_ms, tm, sizeof(tm));
+    if (iter_out) *iter_out = iter;
+    if (info_out) *info_out = info;
+    return SB200_OK;
+}
+
 } // namespace sb200
 
 using namespace sb200;
@@ -824,6 +984,22 @@ int sb200_gesv_mixed_d(sb200_matrix_t A, int64_t* pivots, sb200_matrix_t B, sb20
 {
     if (! A || ! B || ! Xm) return SB200_EINVAL;
     return solve_mixed_d(false, A->A, pivots, B->A, Xm->A, mo ? mo->max_iterations : 30, mo ? mo->tolerance : 0.0,
+                         mo ? mo->use_fallback_solver != 0 : true, iter, info, timers_ms8);
+}
+
+int sb200_posv_mixed_z(sb200_matrix_t A, sb200_matrix_t B, sb200_matrix_t Xm, const sb200_mixed_options_t* mo,
+                       int* iter, int64_t* info, double* timers_ms8)
+{
+    if (! A || ! B || ! Xm) return SB200_EINVAL;
+    return solve_mixed_z(true, A->A, nullptr, B->A, Xm->A, mo ? mo->max_iterations : 30, mo ? mo->tolerance : 0.0,
+                         mo ? mo->use_fallback_solver != 0 : true, iter, info, timers_ms8);
+}
+
+int sb200_gesv_mixed_z(sb200_matrix_t A, int64_t* pivots, sb200_matrix_t B, sb200_matrix_t Xm,
+                       const sb200_mixed_options_t* mo, int* iter, int64_t* info, double* timers_ms8)
+{
+    if (! A || ! B || ! Xm) return SB200_EINVAL;
+    return solve_mixed_z(false, A->A, pivots, B->A, Xm->A, mo ? mo->max_iterations : 30, mo ? mo->tolerance : 0.0,
                          mo ? mo->use_fallback_solver != 0 : true, iter, info, timers_ms8);
 }
 

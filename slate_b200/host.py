@@ -87,6 +87,10 @@ _posv_mixed = _sig("sb200_posv_mixed_d", [c_ptr, c_ptr, c_ptr, ctypes.POINTER(_M
                                           ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)])
 _gesv_mixed = _sig("sb200_gesv_mixed_d", [c_ptr, ctypes.POINTER(c_i64), c_ptr, c_ptr, ctypes.POINTER(_MixedOptions),
                                           ctypes.POINTER(c_int), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)])
+_posv_mixed_z = _sig("sb200_posv_mixed_z", [c_ptr, c_ptr, c_ptr, ctypes.POINTER(_MixedOptions), ctypes.POINTER(c_int),
+                                            ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)])
+_gesv_mixed_z = _sig("sb200_gesv_mixed_z", [c_ptr, ctypes.POINTER(c_i64), c_ptr, c_ptr, ctypes.POINTER(_MixedOptions),
+                                            ctypes.POINTER(c_int), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)])
 tile_rank = _sig("sb200_tile_rank", [c_int, c_int, c_i64, c_i64])
 local_tile_count = _sig("sb200_local_tile_count", [c_int, c_int, c_int, c_int, c_i64, c_i64, c_i64], c_i64)
 local_tile_index = _sig("sb200_local_tile_index", [c_int, c_int, c_int, c_i64, c_i64, c_i64, c_i64, c_i64], c_i64)
@@ -599,7 +603,10 @@ def posv_mixed(A: HermitianMatrix, B: Matrix, X: Matrix, opts: dict | None = Non
     factor failed, -(max_iterations+1) not converged -> FP64 fallback, which overwrites A)."""
     mo = _mixed_opts(opts)
     it, info, tm = c_int(0), c_i64(0), (c_dbl * 8)()
-    check(_posv_mixed(A._h, B._h, X._h, ctypes.byref(mo), ctypes.byref(it), ctypes.byref(info), tm), "posv_mixed")
+    if A.t not in "dz":
+        raise Exception_(f"posv_mixed takes double or complex<double> matrices, not {A.dtype}")
+    f = _posv_mixed_z if A.t == "z" else _posv_mixed          # <complex<double>, complex<float>> | <double, float>
+    check(f(A._h, B._h, X._h, ctypes.byref(mo), ctypes.byref(it), ctypes.byref(info), tm), "posv_mixed")
     return int(info.value), int(it.value), dict(zip(MIXED_TIMERS, list(tm)))
 
 
@@ -610,7 +617,10 @@ def gesv_mixed(A: Matrix, B: Matrix, X: Matrix, opts: dict | None = None):
     it, info, tm = c_int(0), c_i64(0), (c_dbl * 8)()
     mn = min(A.m, A.n)
     flat = (c_i64 * (2 * max(mn, 1)))()
-    check(_gesv_mixed(A._h, flat, B._h, X._h, ctypes.byref(mo), ctypes.byref(it), ctypes.byref(info), tm), "gesv_mixed")
+    if A.t not in "dz":
+        raise Exception_(f"gesv_mixed takes double or complex<double> matrices, not {A.dtype}")
+    f = _gesv_mixed_z if A.t == "z" else _gesv_mixed
+    check(f(A._h, flat, B._h, X._h, ctypes.byref(mo), ctypes.byref(it), ctypes.byref(info), tm), "gesv_mixed")
     piv = np.frombuffer(flat, dtype=np.int64)[: 2 * mn].reshape(-1, 2)
     pivots = [[(int(t), int(off)) for t, off in piv[k0:min(k0 + A.nb, mn)]] for k0 in range(0, mn, A.nb)]
     return int(info.value), int(it.value), pivots, dict(zip(MIXED_TIMERS, list(tm)))

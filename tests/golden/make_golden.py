@@ -25,7 +25,8 @@ generator fixture pins that), only outputs:
   syrk_z.npz, syr2k_z.npz   complex-symmetric rank-k / rank-2k updates (no conjugation), n=200 k=100 nb=64
   getrf_nopiv_d.npz      LU without pivoting, rand_dominant, n=300 nb=128 (ragged)
   her2k_d.npz, her2k_z.npz  C = alpha A B^H + conj(alpha) B A^H + beta C lower, n=200 k=100 nb=64 (ragged tiles)
-  getrf_z.npz, getrf_c.npz  complex LU and pivots (cabs1 rule), n=192 / 200 (ragged) nb=64; gesv_z.npz its solve, n=200 nrhs=70
+  getrf_z.npz, getrf_c.npz  complex LU and pivots (cabs1 rule), n=192 / 200 (ragged) nb=64; gesv_z.npz its solve, n=200 nrhs=70;
+                            gesv_mixed_z.npz, posv_mixed_z.npz complex mixed solvers (solution + iteration count), n=256 nb=64
   getrf_tntpiv_d{,_ragged,_tall}.npz   LU with tournament pivoting (MethodLU::CALU), 384x384 / 300x300 / 512x256, nb=128
 
 Usage (in the build container, where /root/reference exists):  python tests/golden/make_golden.py
@@ -75,6 +76,11 @@ def complex_lu_fixtures():
                         piv=f["piv"].reshape(-1, 2), info=meta["info"])
     f, meta = run("gesv", "z", 200, 64, ib=16, pt=1, nrhs=70)
     np.savez_compressed(os.path.join(OUT, "gesv_z.npz"), out=f["out"].reshape(200, 70, order="F"), info=meta["info"])
+    # complex mixed-precision solvers <complex<double>, complex<float>> (src/gesv_mixed.cc:303-316, src/posv_mixed.cc)
+    for r in ("gesv_mixed", "posv_mixed"):
+        f, meta = run(r, "z", 256, 64, ib=16, pt=1)
+        np.savez_compressed(os.path.join(OUT, f"{r}_z.npz"), out=f["out"].reshape(256, 10, order="F"),
+                            iters=meta["iters"], info=meta["info"])
 
 
 def main():

@@ -346,6 +346,19 @@ def test_gesv_mixed_matches_reference(golden_dir):
     assert np.abs(X - g["out"]).max() <= 1e-11 * np.abs(g["out"]).max()
 
 
+@pytest.mark.parametrize("routine,kind,herm", [("gesv_mixed", "rand", False), ("posv_mixed", "rand_dominant", True)])
+def test_complex_mixed_solvers_match_reference(golden_dir, routine, kind, herm):
+    """<complex<double>, complex<float>> instantiations (src/gesv_mixed.cc:303-316): same iteration count, same solution."""
+    g = load(golden_dir, routine + "_z")
+    n, nb = 256, 64
+    A = o.generate(kind, n, n, 42, dtype=np.complex128); B = o.generate("rand", n, 10, 43, dtype=np.complex128)
+    X, it, info = o.solve_mixed(np.tril(A) if herm else A, B, nb, hermitian=herm)
+    assert info == int(g["info"]) == 0
+    assert it == int(g["iters"])
+    assert np.abs(X - g["out"]).max() <= 1e-11 * np.abs(g["out"]).max()
+    assert o.solve_residual(o.he_full(np.tril(A)) if herm else A, X, B) <= 25 * EPS
+
+
 def test_mixed_fallback_and_failure_codes():
     """iter = -3 when the low-precision factorisation fails, -(itermax+1) when refinement does not converge."""
     n, nb = 96, 32

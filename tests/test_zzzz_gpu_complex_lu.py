@@ -102,3 +102,57 @@ def test_zgetrf_rectangular_and_zero_pivot_info(sl):
     A = sl.Matrix(n, n, nb, dtype=np.complex128); A.from_host(np.asfortranarray(A0))
     _, info = sl.getrf(A)
     assert info == o.getrf(A0, nb, 32)[2] == 101
+
+
+@pytest.mark.parametrize("routine,kind,herm", [("gesv_mixed", "rand", False), ("posv_mixed", "rand_dominant", True)])
+def test_complex_mixed_solvers_match_reference_golden(sl, golden_dir, routine, kind, herm):
+    """<complex<double>, complex<float>> (src/gesv_mixed.cc:303-316): complex<float> factor, complex<double> refinement;
+    the reference's iteration count (one more allowed: the FP32 roundings differ) and its solution."""
+    g = np.load(os.path.join(golden_dir, routine + "_z.npz"))
+    n, nb = 256, 64
+    A = (sl.HermitianMatrix(n, nb, dtype=np.complex128) if herm else sl.Matrix(n, n, nb, dtype=np.complex128)).generate(kind, 42)
+    B = sl.Matrix(n, 10, nb, dtype=np.complex128).generate("rand", 43)
+    X = sl.Matrix(n, 10, nb, dtype=np.complex128)
+    res = sl.posv_mixed(A, B, X) if herm else sl.gesv_mixed(A, B, X)
+    info, it = res[0], res[1]
+    assert info == int(g["info"]) == 0
+    assert 0 <= it <= int(g["iters"]) + 1
+    x = X.to_host()
+    assert np.abs(x - g["out"]).max() <= 1e-11 * np.abs(g["out"]).max()
+    a = o.generate(kind, n, n, 42, dtype=np.complex128)
+    af = o.he_full(np.tril(a)) if herm else a
+    assert o.solve_residual(af, x, o.generate("rand", n, 10, 43, dtype=np.complex128)) <= 25 * EPS
+
+
+@pytest.mark.parametrize("routine,n,nb", [("posv", 1000, 128), ("gesv", 700, 128), ("gesv", 2048, 512)])
+def test_complex_mixed_solvers_vs_oracle_and_tester_residual(sl, routine, n, nb):
+    herm = routine == "posv"
+    kind = "rand_dominant" if herm else "rand"
+    A = (sl.HermitianMatrix(n, nb, dtype=np.complex128) if herm else sl.Matrix(n, n, nb, dtype=np.complex128)).generate(kind, 42)
+    B = sl.Matrix(n, 10, nb, dtype=np.complex128).generate("rand", 43)
+    X = sl.Matrix(n, 10, nb, dtype=np.complex128)
+    res = sl.posv_mixed(A, B, X) if herm else sl.gesv_mixed(A, B, X)
+    info, it = res[0], res[1]
+    assert info == 0 and 0 <= it <= 30
+    a = o.generate(kind, n, n, 42, dtype=np.complex128); b = o.generate("rand", n, 10, 43, dtype=np.complex128)
+    af = o.he_full(np.tril(a)) if herm else a
+    x = X.to_host()
+    assert o.solve_residual(af, x, b) <= 25 * EPS
+    if n <= 1000:
+        xo, ito, _ = o.solve_mixed(np.tril(a) if herm else a, b, nb, hermitian=herm)
+        assert abs(it - ito) <= 1
+        assert np.abs(x - xo).max() <= 1e-10 * np.abs(xo).max()
+
+
+def test_complex_mixed_not_converged_takes_the_fallback(sl):
+    """itermax = 0 with a tolerance no complex<float> factor meets: iter = -(itermax + 1), complex<double> fallback solves."""
+    n, nb = 300, 64
+    A = sl.Matrix(n, n, nb, dtype=np.complex128).generate("rand", 42)
+    B = sl.Matrix(n, 4, nb, dtype=np.complex128).generate("rand", 43)
+    X = sl.Matrix(n, 4, nb, dtype=np.complex128)
+    info, it, piv, _ = sl.gesv_mixed(A, B, X, {"max_iterations": 0, "tolerance": 1e-30})
+    assert info == 0 and it == -1
+    a = o.generate("rand", n, n, 42, dtype=np.complex128); b = o.generate("rand", n, 4, 43, dtype=np.complex128)
+    assert o.solve_residual(a, X.to_host(), b) <= 25 * EPS
+    _, pivo, _ = o.getrf(a, nb, 32)
+    assert piv == pivo
