@@ -360,6 +360,8 @@ int sb200_getrf_c(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts
 /* LU without pivoting (slate::getrf_nopiv, src/getrf_nopiv.cc:  A = L U, unit lower L); info = first zero pivot + 1 */
 int sb200_getrf_nopiv_d(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
 int sb200_getrf_nopiv_s(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
+int sb200_getrf_nopiv_z(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);     /* complex: 1 x 1 grid */
+int sb200_getrf_nopiv_c(sb200_matrix_t A, const sb200_options_t* opts, int64_t* info);
 /* LU with tournament pivoting, CALU (slate::getrf_tntpiv, src/getrf_tntpiv.cc:22-395; Option::MethodLU = CALU of
  * slate::lu_factor, src/getrf.cc:324-329).  Per panel the process rows of the grid hold a tournament (local LU, binary
  * tree of pairwise LUs of the stacked candidate rows, src/internal/internal_getrf_tntpiv.cc:357-640); the rows below
@@ -367,6 +369,8 @@ int sb200_getrf_nopiv_s(sb200_matrix_t A, const sb200_options_t* opts, int64_t* 
  * reference throws otherwise, include/slate/TriangularMatrix.hh:459): SB200_ENOTSUP for other shapes. */
 int sb200_getrf_tntpiv_d(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
 int sb200_getrf_tntpiv_s(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
+int sb200_getrf_tntpiv_z(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);     /* complex: 1 x 1 grid */
+int sb200_getrf_tntpiv_c(sb200_matrix_t A, int64_t* pivots, const sb200_options_t* opts, int64_t* info);
 /* device time of the last driver call on this matrix, milliseconds (CUDA events) */
 double sb200_last_driver_ms(sb200_matrix_t A);
 /* summed device time of the panel-stream critical work (diagonal factor / LU panel + solve +

@@ -314,8 +314,7 @@ template <typename T>
 static int launch_base(BaseArgs<T>& a, int grid, size_t smem, PanelScratch& ps, cudaStream_t s)
 {
     if constexpr (IsComplex<T>::value) {
-        if (ps.nopiv) return SB200_ENOTSUP;
-        return launch_base_cplx<T>(a, grid, smem, s);
+        return launch_base_cplx<T>(a, grid, smem, ps.nopiv, s);
     }
     else {
     cudaError_t e;
@@ -651,7 +650,7 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
     cudaStream_t P = st.panel, T_ = st.trail;
     TntScratch tnt;                                       // getrf_tntpiv only
     if (ps.tnt_ranks > 0) {
-        if (use_tc05 || IsComplex<T>::value || ! tnt_shape_supported(A)) return SB200_ENOTSUP;
+        if (use_tc05 || ! tnt_shape_supported(A)) return SB200_ENOTSUP;
         SB_TRY(tnt.init(mt, nb, A.m, int(sizeof(T)), ps.tnt_ranks, P));
     }
     auto P_done = [&](int64_t k) { return st.ev[size_t(k)]; };
@@ -716,17 +715,13 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
         T* const* stack_k = dtbl + k + k * mt;
         // ---- panel k (column k already carries every earlier update: lookahead below)
         SB_TRY(st.ptime(P));
-        bool tnt_done = false;
-        if constexpr (! IsComplex<T>::value) {
-            if (ps.tnt_ranks > 0) {
-                std::vector<T*> htiles;
-                for (int64_t i = k; i < mt; ++i) htiles.push_back(A.tile_as<T>(i, k));
-                SB_TRY(getrf_panel_tnt<T>(stack_k, htiles, k, int(nb), m_p, kw, pt, po, dinfo.as<int>(), int(k * nb), ps, tnt, P,
-                                          nullptr, &ph));
-                tnt_done = true;
-            }
+        if (ps.tnt_ranks > 0) {
+            std::vector<T*> htiles;
+            for (int64_t i = k; i < mt; ++i) htiles.push_back(A.tile_as<T>(i, k));
+            SB_TRY(getrf_panel_tnt<T>(stack_k, htiles, k, int(nb), m_p, kw, pt, po, dinfo.as<int>(), int(k * nb), ps, tnt, P,
+                                      nullptr, &ph));
         }
-        if (! tnt_done)
+        else
         SB_TRY(getrf_panel<T>(stack_k, A.tile_as<T>(k, k), int(mt - k), int(nb), m_p, kw, pt, po, dinfo.as<int>(),
                               int(k * nb), ps, P, nullptr, &ph));
         if (use_tc05 && ! sk.a_src.empty()) {
@@ -845,6 +840,8 @@ int getrf_driver_cplx(Matrix& A, int64_t* pivots_out, int64_t* info_out)
 
 template int getrf_panel<double>(double* const*, double*, int, int, int, int, int64_t*, int64_t*, int*, int, PanelScratch&, cudaStream_t, int*, PhaseTimer*);
 template int getrf_panel<float>(float* const*, float*, int, int, int, int, int64_t*, int64_t*, int*, int, PanelScratch&, cudaStream_t, int*, PhaseTimer*);
+template int getrf_panel<cuFloatComplex>(cuFloatComplex* const*, cuFloatComplex*, int, int, int, int, int64_t*, int64_t*, int*, int, PanelScratch&, cudaStream_t, int*, PhaseTimer*);
+template int getrf_panel<cuDoubleComplex>(cuDoubleComplex* const*, cuDoubleComplex*, int, int, int, int, int64_t*, int64_t*, int*, int, PanelScratch&, cudaStream_t, int*, PhaseTimer*);
 
 template int launch_laswp<double>(double* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);
 template int launch_laswp<float>(float* const*, int64_t, int, int, int, int, const int64_t*, const int64_t*, int, int, int, int64_t, int64_t, cudaStream_t);
@@ -859,28 +856,34 @@ extern "C" {
 
 /* LU without pivoting (slate::getrf_nopiv, src/getrf_nopiv.cc): the getrf drivers with the pivot search switched off.
  * STATUS: validated on B200 in round 2 (1-, 2- and 8-GPU runs, profiles/r02*). */
-static int getrf_nopiv_any(sb200_matrix_t h, int64_t* info, bool is_float)
+static int getrf_nopiv_any(sb200_matrix_t h, int64_t* info, int dtype)
 {
-    if (! h) return SB200_EINVAL;
+    if (! h || h->A.dtype != dtype) return SB200_EINVAL;
     struct Guard { Guard() { g_getrf_nopiv = true; } ~Guard() { g_getrf_nopiv = false; } } guard;
     std::vector<int64_t> piv(size_t(2 * std::max<int64_t>(std::min(h->A.m, h->A.n), 1)));
-    return is_float ? getrf_driver_s(h->A, piv.data(), info, false) : getrf_driver(h->A, piv.data(), info);
+    if (dtype == 'z' || dtype == 'c') return getrf_driver_cplx(h->A, piv.data(), info);
+    return dtype == 's' ? getrf_driver_s(h->A, piv.data(), info, false) : getrf_driver(h->A, piv.data(), info);
 }
-int sb200_getrf_nopiv_d(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, false); }
-int sb200_getrf_nopiv_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, true); }
+int sb200_getrf_nopiv_z(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, 'z'); }
+int sb200_getrf_nopiv_c(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, 'c'); }
+int sb200_getrf_nopiv_d(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, 'd'); }
+int sb200_getrf_nopiv_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_nopiv_any(h, info, 's'); }
 
 /* LU with tournament pivoting (slate::getrf_tntpiv, src/getrf_tntpiv.cc; MethodLU::CALU of slate::lu_factor): the getrf
  * drivers with the panel of getrf_tnt.cu.  Participants per panel = process rows of the grid.
  * STATUS: see DESIGN.md section 0 (row (f)2). */
-static int getrf_tntpiv_any(sb200_matrix_t h, int64_t* pivots, int64_t* info, bool is_float)
+static int getrf_tntpiv_any(sb200_matrix_t h, int64_t* pivots, int64_t* info, int dtype)
 {
-    if (! h) return SB200_EINVAL;
+    if (! h || h->A.dtype != dtype) return SB200_EINVAL;
     if (! tnt_shape_supported(h->A)) return SB200_ENOTSUP;
     struct Guard { explicit Guard(int r) { g_getrf_tnt = r; } ~Guard() { g_getrf_tnt = 0; } } guard(tnt_ranks_for(*h->A.g));
-    return is_float ? getrf_driver_s(h->A, pivots, info, false) : getrf_driver(h->A, pivots, info);
+    if (dtype == 'z' || dtype == 'c') return getrf_driver_cplx(h->A, pivots, info);           // 1 x 1 grid
+    return dtype == 's' ? getrf_driver_s(h->A, pivots, info, false) : getrf_driver(h->A, pivots, info);
 }
-int sb200_getrf_tntpiv_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, false); }
-int sb200_getrf_tntpiv_s(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, true); }
+int sb200_getrf_tntpiv_d(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, 'd'); }
+int sb200_getrf_tntpiv_s(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, 's'); }
+int sb200_getrf_tntpiv_z(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, 'z'); }
+int sb200_getrf_tntpiv_c(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info) { SB_TRY(options_status(opts)); return getrf_tntpiv_any(h, pivots, info, 'c'); }
 
 /* complex LU with partial pivoting (cabs1 rule); 1 x 1 grid */
 int sb200_getrf_z(sb200_matrix_t h, int64_t* pivots, const sb200_options_t* opts, int64_t* info)

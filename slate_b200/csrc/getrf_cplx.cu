@@ -28,7 +28,8 @@ template <typename R> __device__ __forceinline__ R tiny_real();
 template <> __device__ __forceinline__ float  tiny_real<float>()  { return FLT_MIN; }
 template <> __device__ __forceinline__ double tiny_real<double>() { return DBL_MIN; }
 
-template <typename T>
+// NOPIV (getrf_nopiv): no candidate is proposed, so the diagonal entry is the pivot of every column
+template <typename T, bool NOPIV>
 __global__ void __launch_bounds__(PTHREADS)
 getrf_base_cplx_kernel(const BaseArgs<T> a)
 {
@@ -62,12 +63,14 @@ getrf_base_cplx_kernel(const BaseArgs<T> a)
         // ---- local candidate: first maximum of cabs1 over this CTA's rows below the diagonal
         R best = R(-1);
         int brow = INT_MAX;
+        if constexpr (! NOPIV) {
         for (int lr = tid; lr < nr; lr += PTHREADS) {
             const int r = r_begin + lr;
             if (r > d) {
                 const R v = abs1(blk[j * RP + lr]);
                 if (v > best) { best = v; brow = r; }      // rows ascend per thread: first max kept
             }
+        }
         }
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -182,24 +185,25 @@ getrf_base_cplx_kernel(const BaseArgs<T> a)
 
 // one cooperative launch of `grid` CTAs (the caller's BaseArgs: getrf.cu panel_base_wide / getrf_panel_v1)
 template <typename T>
-int launch_base_cplx(BaseArgs<T>& a, int grid, size_t smem, cudaStream_t s)
+int launch_base_cplx(BaseArgs<T>& a, int grid, size_t smem, bool nopiv, cudaStream_t s)
 {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     static thread_local bool attr_done[64] = {};
     if (! attr_done[dev & 63]) {
-        CUDA_TRY(cudaFuncSetAttribute(getrf_base_cplx_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(PW * (panel_rows_max<T>() | 1) * sizeof(T))));
+        const int max_smem = int(PW * (panel_rows_max<T>() | 1) * sizeof(T));
+        CUDA_TRY(cudaFuncSetAttribute(getrf_base_cplx_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_TRY(cudaFuncSetAttribute(getrf_base_cplx_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_done[dev & 63] = true;
     }
     void* args[] = {&a};
-    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(getrf_base_cplx_kernel<T>), dim3(grid), dim3(PTHREADS),
-                                                      args, smem, s);
+    void* fn = nopiv ? reinterpret_cast<void*>(getrf_base_cplx_kernel<T, true>) : reinterpret_cast<void*>(getrf_base_cplx_kernel<T, false>);
+    const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PTHREADS), args, smem, s);
     if (e != cudaSuccess) return int(e);
     return launch_status();
 }
 
-template int launch_base_cplx<cuFloatComplex>(BaseArgs<cuFloatComplex>&, int, size_t, cudaStream_t);
-template int launch_base_cplx<cuDoubleComplex>(BaseArgs<cuDoubleComplex>&, int, size_t, cudaStream_t);
+template int launch_base_cplx<cuFloatComplex>(BaseArgs<cuFloatComplex>&, int, size_t, bool, cudaStream_t);
+template int launch_base_cplx<cuDoubleComplex>(BaseArgs<cuDoubleComplex>&, int, size_t, bool, cudaStream_t);
 
 } // namespace sb200

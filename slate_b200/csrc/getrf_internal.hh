@@ -46,7 +46,7 @@ struct BaseArgs {
 
 
 // complex base block (getrf_cplx.cu)
-template <typename T> int launch_base_cplx(BaseArgs<T>& a, int grid, size_t smem, cudaStream_t s);
+template <typename T> int launch_base_cplx(BaseArgs<T>& a, int grid, size_t smem, bool nopiv, cudaStream_t s);
 
 // scratch of the tournament panel (getrf_tnt.cu), per driver call
 struct TntScratch {

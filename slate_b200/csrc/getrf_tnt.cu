@@ -254,6 +254,10 @@ template int getrf_panel_tnt<double>(double* const*, const std::vector<double*>&
                                      PanelScratch&, TntScratch&, cudaStream_t, int*, PhaseTimer*);
 template int getrf_panel_tnt<float>(float* const*, const std::vector<float*>&, int64_t, int, int, int, int64_t*, int64_t*, int*, int,
                                     PanelScratch&, TntScratch&, cudaStream_t, int*, PhaseTimer*);
+template int getrf_panel_tnt<cuFloatComplex>(cuFloatComplex* const*, const std::vector<cuFloatComplex*>&, int64_t, int, int, int, int64_t*,
+                                             int64_t*, int*, int, PanelScratch&, TntScratch&, cudaStream_t, int*, PhaseTimer*);
+template int getrf_panel_tnt<cuDoubleComplex>(cuDoubleComplex* const*, const std::vector<cuDoubleComplex*>&, int64_t, int, int, int, int64_t*,
+                                              int64_t*, int*, int, PanelScratch&, TntScratch&, cudaStream_t, int*, PhaseTimer*);
 
 // every diagonal tile square (the reference's TriangularMatrix view of A(k, k) requires it)
 bool tnt_shape_supported(const Matrix& A)

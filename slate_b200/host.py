@@ -527,7 +527,7 @@ def getrf(A: Matrix, opts: dict | None = None):
     return pivots, int(info.value)
 
 
-_getrf_tntpiv = {t: _sig(f"sb200_getrf_tntpiv_{t}", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)]) for t in "sd"}
+_getrf_tntpiv = {t: _sig(f"sb200_getrf_tntpiv_{t}", [c_ptr, ctypes.POINTER(c_i64), _OP, ctypes.POINTER(c_i64)]) for t in "sdcz"}
 
 
 def getrf_tntpiv(A: Matrix, opts: dict | None = None):
@@ -559,7 +559,7 @@ def lu_factor(A: Matrix, opts: dict | None = None):
     raise Exception_(f"unknown value for MethodLU: {method}")
 
 
-_getrf_nopiv = {t: _sig(f"sb200_getrf_nopiv_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64)]) for t in "sd"}
+_getrf_nopiv = {t: _sig(f"sb200_getrf_nopiv_{t}", [c_ptr, _OP, ctypes.POINTER(c_i64)]) for t in "sdcz"}
 
 
 def getrf_nopiv(A: Matrix, opts: dict | None = None) -> int:

@@ -26,7 +26,8 @@ generator fixture pins that), only outputs:
   getrf_nopiv_d.npz      LU without pivoting, rand_dominant, n=300 nb=128 (ragged)
   her2k_d.npz, her2k_z.npz  C = alpha A B^H + conj(alpha) B A^H + beta C lower, n=200 k=100 nb=64 (ragged tiles)
   getrf_z.npz, getrf_c.npz  complex LU and pivots (cabs1 rule), n=192 / 200 (ragged) nb=64; gesv_z.npz its solve, n=200 nrhs=70;
-                            gesv_mixed_z.npz, posv_mixed_z.npz complex mixed solvers (solution + iteration count), n=256 nb=64
+                            gesv_mixed_z.npz, posv_mixed_z.npz complex mixed solvers (solution + iteration count), n=256 nb=64;
+                            getrf_tntpiv_z.npz (CALU, n=192), getrf_nopiv_z.npz (rand_dominant, n=200)
   getrf_tntpiv_d{,_ragged,_tall}.npz   LU with tournament pivoting (MethodLU::CALU), 384x384 / 300x300 / 512x256, nb=128
 
 Usage (in the build container, where /root/reference exists):  python tests/golden/make_golden.py
@@ -76,6 +77,11 @@ def complex_lu_fixtures():
                         piv=f["piv"].reshape(-1, 2), info=meta["info"])
     f, meta = run("gesv", "z", 200, 64, ib=16, pt=1, nrhs=70)
     np.savez_compressed(os.path.join(OUT, "gesv_z.npz"), out=f["out"].reshape(200, 70, order="F"), info=meta["info"])
+    f, meta = run("getrf", "z", 192, 64, ib=16, pt=1, method="calu")
+    np.savez_compressed(os.path.join(OUT, "getrf_tntpiv_z.npz"), out=f["out"].reshape(192, 192, order="F"),
+                        piv=f["piv"].reshape(-1, 2), info=meta["info"])
+    f, meta = run("getrf_nopiv", "z", 200, 64)
+    np.savez_compressed(os.path.join(OUT, "getrf_nopiv_z.npz"), out=f["out"].reshape(200, 200, order="F"), info=meta["info"])
     # complex mixed-precision solvers <complex<double>, complex<float>> (src/gesv_mixed.cc:303-316, src/posv_mixed.cc)
     for r in ("gesv_mixed", "posv_mixed"):
         f, meta = run(r, "z", 256, 64, ib=16, pt=1)

@@ -212,6 +212,19 @@ def test_complex_gesv_matches_reference(golden_dir):
     assert np.abs(X - g["out"]).max() <= 1e-11 * np.abs(g["out"]).max()
 
 
+def test_complex_tntpiv_and_nopiv_match_reference(golden_dir):
+    g = load(golden_dir, "getrf_tntpiv_z")
+    A = o.generate("rand", 192, 192, 42, dtype=np.complex128)
+    LU, piv, info = o.getrf_tntpiv(A, 64, 16)
+    assert np.array_equal(np.array([p for col in piv for p in col], dtype=np.int64), g["piv"]) and info == int(g["info"]) == 0
+    assert np.abs(LU - g["out"]).max() <= 1e-12 * np.abs(g["out"]).max()
+    g = load(golden_dir, "getrf_nopiv_z")
+    A = o.generate("rand_dominant", 200, 200, 42, dtype=np.complex128)
+    LU, info = o.getrf_nopiv(A, 64)
+    assert info == int(g["info"]) == 0
+    assert np.abs(LU - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+
+
 def test_trsm_matches_reference(golden_dir):
     g = load(golden_dir, "trsm_d")
     m, n = 256, 128

@@ -156,3 +156,40 @@ def test_complex_mixed_not_converged_takes_the_fallback(sl):
     assert o.solve_residual(a, X.to_host(), b) <= 25 * EPS
     _, pivo, _ = o.getrf(a, nb, 32)
     assert piv == pivo
+
+
+def test_complex_tntpiv_matches_reference_golden_and_tournament_oracle(sl, golden_dir, monkeypatch):
+    g = np.load(os.path.join(golden_dir, "getrf_tntpiv_z.npz"))
+    n, nb = 192, 64
+    A = sl.Matrix(n, n, nb, dtype=np.complex128).generate("rand", 42)
+    piv, info = sl.lu_factor(A, {"method_lu": "CALU"})
+    assert info == int(g["info"]) == 0
+    assert np.array_equal(np.array([x for c in piv for x in c], dtype=np.int64), g["piv"])
+    assert np.abs(A.to_host() - g["out"]).max() <= CPLX_TOL * np.abs(g["out"]).max()
+    # several participants per panel (the process rows of a grid), against the restatement of internal_getrf_tntpiv.cc
+    monkeypatch.setenv("SB200_TNT_RANKS", "3")
+    for (m, n, nb) in [(300, 300, 64), (448, 256, 64)]:
+        A = sl.Matrix(m, n, nb, dtype=np.complex128).generate("rand", 42)
+        piv, info = sl.getrf_tntpiv(A)
+        A0 = o.generate("rand", m, n, 42, dtype=np.complex128)
+        LUo, pivo, _ = o.getrf_tntpiv(A0, nb, 32, ranks=3)
+        assert info == 0 and piv == pivo
+        assert np.abs(A.to_host() - LUo).max() <= CPLX_TOL * np.abs(LUo).max()
+
+
+def test_complex_nopiv_matches_reference_golden(sl, golden_dir):
+    g = np.load(os.path.join(golden_dir, "getrf_nopiv_z.npz"))
+    n, nb = 200, 64
+    A = sl.Matrix(n, n, nb, dtype=np.complex128).generate("rand_dominant", 42)
+    assert sl.getrf_nopiv(A) == int(g["info"]) == 0
+    assert np.abs(A.to_host() - g["out"]).max() <= CPLX_TOL * np.abs(g["out"]).max()
+    # complex<float>: A = L U to working precision; the pivot search is back on the next call
+    C = sl.Matrix(n, n, nb, dtype=np.complex64).generate("rand_dominant", 42)
+    assert sl.getrf_nopiv(C) == 0
+    LU = C.to_host().astype(np.complex128)
+    A0 = o.generate("rand_dominant", n, n, 42, dtype=np.complex64).astype(np.complex128)
+    L = np.tril(LU, -1) + np.eye(n); U = np.triu(LU)
+    assert np.abs(L @ U - A0).max() <= 64 * np.finfo(np.float32).eps * np.abs(A0).max()
+    B = sl.Matrix(n, n, nb, dtype=np.complex128).generate("rand", 42)
+    piv, _ = sl.getrf(B)
+    assert piv == o.getrf(o.generate("rand", n, n, 42, dtype=np.complex128), nb, 32)[1]
