@@ -221,9 +221,9 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # Secondary bench lines (not the driver's default): BASELINE configs[3] (zgemm / zherk), configs[4]
 # (mixed-precision solves) and the HBM-bound tile kernels.
-#   python bench.py --routine zgemm|zherk|zpotrf|posv_mixed|gesv_mixed|tileops [--n N] [--gpus N]
+#   python bench.py --routine zgemm|zherk|zpotrf|zgetrf|getrf_tntpiv|posv_mixed|gesv_mixed|tileops [--n N] [--gpus N]
 # ------------------------------------------------------------------------------------------------
-EXTRA_ROUTINES = ["zgemm", "zherk", "zpotrf", "posv_mixed", "gesv_mixed", "tileops"]
+EXTRA_ROUTINES = ["zgemm", "zherk", "zpotrf", "zgetrf", "getrf_tntpiv", "posv_mixed", "gesv_mixed", "tileops"]
 
 
 def extra_flops(routine: str, n: int, nrhs: int) -> float:
@@ -234,6 +234,10 @@ def extra_flops(routine: str, n: int, nrhs: int) -> float:
         return 4.0 * n * n * (n + 1)             # n x n result, k = n: herk = 4 * k n (n+1) / ... real-flop count
     if routine == "zpotrf":
         return 4.0 * flops("potrf", int(n))
+    if routine == "zgetrf":
+        return 4.0 * flops("getrf", int(n))      # complex LU (1 x 1 grid)
+    if routine == "getrf_tntpiv":
+        return flops("getrf", int(n))            # CALU: lapack::Gflop::getrf, as the tester reports it
     if routine == "posv_mixed":
         return flops("potrf", int(n)) + 2.0 * n * n * nrhs      # lapack::Gflop::posv (FP64-equivalent work)
     if routine == "gesv_mixed":
@@ -374,8 +378,10 @@ def run_extra(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    n = args.n or ({"zgemm": 16384, "zherk": 16384, "zpotrf": 24576, "posv_mixed": 32768, "gesv_mixed": 32768}[routine]
-                   if world == 1 else {"zgemm": 40960, "zherk": 40960, "zpotrf": 40960, "posv_mixed": 65536, "gesv_mixed": 65536}[routine])
+    n = args.n or ({"zgemm": 16384, "zherk": 16384, "zpotrf": 24576, "zgetrf": 16384, "getrf_tntpiv": 32768,
+                    "posv_mixed": 32768, "gesv_mixed": 32768}[routine]
+                   if world == 1 else {"zgemm": 40960, "zherk": 40960, "zpotrf": 40960, "zgetrf": 40960, "getrf_tntpiv": 65536,
+                                       "posv_mixed": 65536, "gesv_mixed": 65536}[routine])
     grid = sl.Grid.from_torch_distributed() if world > 1 else sl.Grid()
     st = torch.cuda.current_stream().cuda_stream
 
@@ -407,6 +413,18 @@ def run_extra(args):
             if sl.potrf(out) != 0:
                 raise SystemExit("zpotrf: info != 0")
         kernel = "gemm_zdmma_kernel (complex128 trailing update of zpotrf)"
+    elif routine in ("zgetrf", "getrf_tntpiv"):
+        dt = "z" if routine == "zgetrf" else "d"
+        A0 = sl.Matrix(n, n, nb, grid, dt).generate("rand", 42)
+        out = sl.Matrix(n, n, nb, grid, dt)
+
+        def run():
+            out.copy_from(A0)
+            _, info = sl.getrf(out) if routine == "zgetrf" else sl.getrf_tntpiv(out)
+            if info != 0:
+                raise SystemExit(f"{routine}: info != 0")
+        kernel = ("gemm_zdmma_kernel (complex128 trailing update of zgetrf; cooperative complex panel)" if routine == "zgetrf"
+                  else "gemm_dmma_kernel (FP64 trailing update of the LU with tournament pivoting)")
     else:
         herm = routine == "posv_mixed"
         Am = (sl.HermitianMatrix(n, nb, grid) if herm else sl.Matrix(n, n, nb, grid)).generate(
@@ -464,9 +482,10 @@ def run_extra(args):
     if not args.no_e2e:
         tdt = torch.complex128 if routine[0] == "z" else torch.float64
         esz = 16 if routine[0] == "z" else 8
+        fact = routine in ("zpotrf", "zgetrf", "getrf_tntpiv")          # factorisations: host tiles -> out, factored in place
         ins = [m for m in ((Am, Bm, out) if routine == "zgemm" else (Am, out) if routine == "zherk" else
-                           (A0,) if routine == "zpotrf" else (Am, Bm))]
-        dst = {id(A0): out} if routine == "zpotrf" else {}
+                           (A0,) if fact else (Am, Bm))]
+        dst = {id(A0): out} if fact else {}
         hosts = []
         for m in ins:
             h = torch.empty(m.local_tiles * nb * nb, dtype=tdt).pin_memory()
@@ -480,6 +499,9 @@ def run_extra(args):
             if routine == "zpotrf":
                 if sl.potrf(out) != 0:
                     raise SystemExit("zpotrf: info != 0")
+            elif fact:
+                if (sl.getrf(out) if routine == "zgetrf" else sl.getrf_tntpiv(out))[1] != 0:
+                    raise SystemExit(f"{routine}: info != 0")
             else:
                 run()
             out.to_host_local(res)
@@ -515,7 +537,7 @@ def run_extra(args):
             "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": 1 if mixed else max(args.warmup, 3), "ms_per_step": ms_per_step,
             "wall_ms_per_step": float(t[1]), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "c128" if routine[0] == "z" else "f32 factor (3xTF32 tensor cores) + f64 refinement",
+            "dtype": "c128" if routine[0] == "z" else "f64" if routine == "getrf_tntpiv" else "f32 factor (3xTF32 tensor cores) + f64 refinement",
             "data": "synthetic (reference matgen: Philox-2x64 rand_dominant/rand, seeds 42/43/44, generated on device)",
             "config": {"workload": f"{name} n={n} nb={nb}" + (f" nrhs={nrhs}" if mixed else "")
                                    + f", {grid.p}x{grid.q} block-cyclic grid over {world} B200",

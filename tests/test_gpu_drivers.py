@@ -203,3 +203,20 @@ def test_bcast_tiles_hook_on_one_rank_is_the_single_rank_early_exit(sl):
     torch.cuda.synchronize()
     assert float(b.abs().sum()) == 0.0
     g.close()
+
+
+def test_gemm_baseline_config0_full_size(sl):
+    """BASELINE.json configs[0] at its full size: dgemm n = 4096, nb = 256, tester alpha / beta and seeds
+    (test/test.cc:447-448), against the oracle's tile-ordered product and the tester's check (test/test_gemm.cc:205-207)."""
+    n, nb = 4096, 256
+    A = sl.Matrix(n, n, nb).generate("rand", 42); B = sl.Matrix(n, n, nb).generate("rand", 43)
+    C = sl.Matrix(n, n, nb).generate("rand", 44)
+    al, be = 3.141592653589793, 2.718281828459045
+    # inputs read back from the device: its Philox generator is pinned bit-exact to the reference's matgen by
+    # test_device_generator_is_bit_exact (the numpy generator would take half a minute at this size)
+    a, b, c0 = A.to_host(), B.to_host(), C.to_host()
+    sl.gemm(al, A, B, be, C)
+    out = C.to_host()
+    ref = al * (a @ b) + be * c0
+    assert np.abs(out - ref).max() <= 3 * np.sqrt(n) * EPS * np.abs(ref).max()       # the tester's 3 sqrt(k) eps scale
+    assert o.gemm_check(al, a, b, be, c0, out) <= 3 * EPS
