@@ -753,7 +753,7 @@ int getrf_driver_t(Matrix& A, int64_t* pivots_out, int64_t* info_out, bool use_t
                 SB_TRY(st.time_begin(T_));
                 SB_TRY(run_batches(sk.tr, T_, use_bt));
                 SB_TRY(st.time_end(T_));
-                trail_flops += batches_flops(sk.tr, false);
+                trail_flops += batches_flops(sk.tr, IsComplex<T>::value);
                 trail_launches += int64_t(sk.tr.size());
             }
         }

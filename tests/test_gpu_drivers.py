@@ -207,7 +207,7 @@ def test_bcast_tiles_hook_on_one_rank_is_the_single_rank_early_exit(sl):
 
 def test_gemm_baseline_config0_full_size(sl):
     """BASELINE.json configs[0] at its full size: dgemm n = 4096, nb = 256, tester alpha / beta and seeds
-    (test/test.cc:447-448), against the oracle's tile-ordered product and the tester's check (test/test_gemm.cc:205-207)."""
+    (test/test.cc:447-448), against the FP64 product of the same inputs and the tester's check (test/test_gemm.cc:205-207)."""
     n, nb = 4096, 256
     A = sl.Matrix(n, n, nb).generate("rand", 42); B = sl.Matrix(n, n, nb).generate("rand", 43)
     C = sl.Matrix(n, n, nb).generate("rand", 44)
