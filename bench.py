@@ -477,6 +477,16 @@ def run_extra(args):
                 "frac": achieved / peak if peak else None, "traffic": None, "peak_source": psrc,
                 "launches_timed": int(trail_launches), "trailing_ms_per_step": trail_ms / args.steps}
 
+    # untimed check of a fresh factorisation: the tester's LU check with one probe vector (test/test_gesv.cc:371-377)
+    extra_check = None
+    if routine in ("zgetrf", "getrf_tntpiv"):
+        try:
+            out.copy_from(A0)
+            piv, _ = sl.getrf(out) if routine == "zgetrf" else sl.getrf_tntpiv(out)
+            extra_check = sl.getrf_residual(A0, out, piv)
+        except Exception as ex:   # noqa: BLE001  (the timed numbers above stand on their own)
+            extra_check = {"error": str(ex)}
+
     # e2e: operands from pinned HOST memory, result back to the host, inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -546,6 +556,8 @@ def run_extra(args):
                        "switches": _switches()},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         }
+        if extra_check is not None:
+            line["check"] = extra_check
         line["step_ms"] = step_ms
         if mixed:
             timed_phases["iter"] = timers.get("iter")
