@@ -173,6 +173,20 @@ def main():
                     print(f"grid {p}x{q} n={n} nb={nb}: zher2k err={errs[0]:.2e} zsyrk err={errs[1]:.2e} zsyr2k err={errs[2]:.2e} "
                           f"getrf_nopiv err={en:.2e} {'ok' if good else 'FAILED'}", flush=True)
                     ok &= good
+            # ---- LU with tournament pivoting on the grid (written after round 2's GPU budget was spent: the tournament
+            #      itself is validated on one rank through SB200_TNT_RANKS; this checks it behind the real gather /
+            #      broadcast).  Participants per panel = the grid's process rows.  MGPU_TNT=0 skips it.
+            if os.environ.get("MGPU_TNT", "1") != "0":
+                At = sl.Matrix(n, n, nb, grid).generate("rand", 42)
+                pivt, infot = sl.getrf_tntpiv(At)
+                LUt = gather(At, n, n)
+                if rank == 0:
+                    LUo, pivo, info_o = o.getrf_tntpiv(o.generate("rand", n, n, 42), nb, 32, ranks=p)
+                    e = np.abs(LUt - LUo).max() / np.abs(LUo).max()
+                    good = (pivt == pivo) and infot == info_o == 0 and e <= 1e-11
+                    print(f"grid {p}x{q} getrf_tntpiv n={n} nb={nb}: pivots {'identical' if pivt == pivo else 'DIFFER'}, "
+                          f"|LU-LUo|/|LUo|={e:.2e} {'ok' if good else 'FAILED'}", flush=True)
+                    ok &= good
             # ---- solve path on the grid (replicated right-hand sides, solve_dist.cu): potrs and posv_mixed
             if os.environ.get("MGPU_SOLVE", "1") != "0":
                 Hd = sl.HermitianMatrix(n, nb, grid).generate("rand_dominant", 42)
