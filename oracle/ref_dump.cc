@@ -16,7 +16,7 @@
 // usage: ref_dump ROUTINE TYPE n nb seedA seedB seedC OUTPREFIX [key=value ...]
 //   ROUTINE  gen | gemm | herk | potrf | getrf | trsm | gesv_mixed | posv_mixed | posv | gesv | hemm | norms
 //   TYPE     s | d | c | z
-//   keys     kind=rand|rand_dominant  la=1  ib=16  threads=N  dump=0|1  nrhs=10  pt=panel threads  method=pplu|calu (getrf)
+//   keys     p=1 q=1 (process grid; > 1 rank: oracle/_ref/ref_dump_mp under oracle/mprun.py)  kind=rand|rand_dominant  la=1  ib=16  threads=N  dump=0|1  nrhs=10  pt=panel threads  method=pplu|calu (getrf)
 //            m= k= (gemm/herk rectangular)  uplo=l|u
 #include "slate/slate.hh"
 #include "slate/generate_matrix.hh"
@@ -35,6 +35,11 @@
 namespace {
 
 using Clock = std::chrono::steady_clock;
+
+// process grid (keys p=, q=; the world size has to be p * q).  More than one rank needs the multi-process MPI replacement
+// (oracle/mpi_mp, started through oracle/mprun.py); every rank then writes the tiles IT owns (other tiles stay zero) to
+// PREFIX.r<rank>.<name>.bin and the caller assembles them with the tile map  rank(i, j) = i % p + (j % q) * p.
+int g_p = 1, g_q = 1, g_rank = 0, g_world = 1;
 
 struct Args {
     std::string routine, type, prefix;
@@ -69,11 +74,13 @@ std::vector<T> to_dense(slate::Matrix<T>& A)
     for (int64_t j = 0; j < A.nt(); ++j) {
         int64_t i0 = 0;
         for (int64_t i = 0; i < A.mt(); ++i) {
-            A.tileGetForReading(i, j, slate::LayoutConvert::ColMajor);
-            auto t = A(i, j);
-            for (int64_t jj = 0; jj < t.nb(); ++jj)
-                for (int64_t ii = 0; ii < t.mb(); ++ii)
-                    out[size_t(i0 + ii) + size_t(j0 + jj) * m] = t(ii, jj);
+            if (A.tileIsLocal(i, j)) {
+                A.tileGetForReading(i, j, slate::LayoutConvert::ColMajor);
+                auto t = A(i, j);
+                for (int64_t jj = 0; jj < t.nb(); ++jj)
+                    for (int64_t ii = 0; ii < t.mb(); ++ii)
+                        out[size_t(i0 + ii) + size_t(j0 + jj) * m] = t(ii, jj);
+            }
             i0 += A.tileMb(i);
         }
         j0 += A.tileNb(j);
@@ -92,7 +99,7 @@ std::vector<T> tz_to_dense(MatrixT& A, bool lower)
         int64_t i0 = 0;
         for (int64_t i = 0; i < A.mt(); ++i) {
             bool stored = lower ? (i >= j) : (i <= j);
-            if (stored) {
+            if (stored && A.tileIsLocal(i, j)) {
                 A.tileGetForReading(i, j, slate::LayoutConvert::ColMajor);
                 auto t = A(i, j);
                 for (int64_t jj = 0; jj < t.nb(); ++jj)
@@ -109,7 +116,7 @@ std::vector<T> tz_to_dense(MatrixT& A, bool lower)
 template <typename T>
 slate::Matrix<T> make_matrix(int64_t m, int64_t n, int64_t nb, int64_t seed, const std::string& kind)
 {
-    slate::Matrix<T> A(m, n, nb, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+    slate::Matrix<T> A(m, n, nb, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
     A.insertLocalTiles();
     slate::MatgenParams p;
     p.verbose = 0; p.kind = kind; p.cond_request = NAN; p.cond_actual = NAN; p.condD = NAN; p.seed = seed;
@@ -171,7 +178,7 @@ int run(const Args& a)
         bool lower = a.get("uplo", "l") == "l";
         auto A = make_matrix<T>(n, k, nb, a.seedA, "rand");
         slate::HermitianMatrix<T> C(lower ? slate::Uplo::Lower : slate::Uplo::Upper, n, nb,
-                                    slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+                                    slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         C.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedC;
         p.cond_request = p.cond_actual = p.condD = NAN;
@@ -194,7 +201,7 @@ int run(const Args& a)
     else if (a.routine == "potrf") {
         bool lower = a.get("uplo", "l") == "l";
         slate::HermitianMatrix<T> A(lower ? slate::Uplo::Lower : slate::Uplo::Upper, n, nb,
-                                    slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+                                    slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand_dominant"); p.seed = a.seedA;
         p.cond_request = p.cond_actual = p.condD = NAN;
@@ -248,7 +255,7 @@ int run(const Args& a)
         // Left/Lower/NoTrans/NonUnit solve  A X = alpha B, A = rand_dominant lower triangle
         int64_t m = a.geti("m", n);   // A is m x m, B is m x n
         slate::TriangularMatrix<T> A(slate::Uplo::Lower, slate::Diag::NonUnit, m, nb,
-                                     slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+                                     slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = "rand_dominant"; p.seed = a.seedA;
         p.cond_request = p.cond_actual = p.condD = NAN;
@@ -269,7 +276,7 @@ int run(const Args& a)
         if constexpr (std::is_same<real_t, double>::value) {
             auto A = make_matrix<T>(n, n, nb, a.seedA, a.get("kind", "rand"));
             auto B = make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
-            slate::Matrix<T> X(n, nrhs, nb, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+            slate::Matrix<T> X(n, nrhs, nb, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
             X.insertLocalTiles();
             if (dump) {
                 auto d = to_dense(A); write_raw(a.prefix + ".A.bin", d.data(), d.size());
@@ -290,7 +297,7 @@ int run(const Args& a)
     else if (a.routine == "posv_mixed" || a.routine == "posv") {
         // Hermitian positive definite solve: posv = chol_factor + chol_solve_using_factor
         // (test/test_posv.cc:205-232); posv_mixed = src/posv_mixed.cc
-        slate::HermitianMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        slate::HermitianMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand_dominant"); p.seed = a.seedA;
         p.cond_request = p.cond_actual = p.condD = NAN;
@@ -305,7 +312,7 @@ int run(const Args& a)
             if (dump) { auto d = to_dense(B); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
         }
         else if constexpr (std::is_same<real_t, double>::value) {
-            slate::Matrix<T> X(n, nrhs, nb, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+            slate::Matrix<T> X(n, nrhs, nb, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
             X.insertLocalTiles();
             auto t0 = tic();
             info = slate::posv_mixed(A, B, X, iters, opts);
@@ -332,7 +339,7 @@ int run(const Args& a)
     }
     else if (a.routine == "hemm") {
         // C = alpha A B + beta C, A Hermitian (lower), Side::Left (test/test_hemm.cc)
-        slate::HermitianMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        slate::HermitianMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand"); p.seed = a.seedA;
         p.cond_request = p.cond_actual = p.condD = NAN;
@@ -350,7 +357,7 @@ int run(const Args& a)
         int64_t k = a.geti("k", n);
         auto A = make_matrix<T>(n, k, nb, a.seedA, "rand");
         auto B = make_matrix<T>(n, k, nb, a.seedB, "rand");
-        slate::HermitianMatrix<T> C(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        slate::HermitianMatrix<T> C(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         C.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedC;
         p.cond_request = p.cond_actual = p.condD = NAN;
@@ -371,7 +378,7 @@ int run(const Args& a)
         int64_t k = a.geti("k", n);
         auto A = make_matrix<T>(n, k, nb, a.seedA, "rand");
         auto B = make_matrix<T>(n, k, nb, a.seedB, "rand");
-        slate::SymmetricMatrix<T> C(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        slate::SymmetricMatrix<T> C(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         C.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedC;
         p.cond_request = p.cond_actual = p.condD = NAN;
@@ -391,7 +398,7 @@ int run(const Args& a)
         int64_t m = a.geti("m", n);   // A is m x m, B is m x n
         bool unit = a.get("diag", "n") == "u";
         slate::TriangularMatrix<T> A(slate::Uplo::Lower, unit ? slate::Diag::Unit : slate::Diag::NonUnit, m, nb,
-                                     slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+                                     slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedA;
         p.cond_request = p.cond_actual = p.condD = NAN;
@@ -405,7 +412,7 @@ int run(const Args& a)
     }
     else if (a.routine == "symm") {
         // C = alpha A B + beta C, A complex-symmetric (lower), Side::Left (test/test_symm.cc; slate::symm, src/symm.cc)
-        slate::SymmetricMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, 1, 1, MPI_COMM_WORLD);
+        slate::SymmetricMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand"); p.seed = a.seedA;
         p.cond_request = p.cond_actual = p.condD = NAN;
@@ -437,6 +444,7 @@ int run(const Args& a)
         std::fprintf(stderr, "unknown routine %s\n", a.routine.c_str());
         return 2;
     }
+    if (g_rank == 0)
     std::printf("{\"routine\": \"%s\", \"type\": \"%s\", \"n\": %lld, \"nb\": %lld, \"seconds\": %.6f, "
                 "\"gflops\": %.3f, \"threads\": %d, \"info\": %lld, \"iters\": %d, \"target\": \"HostTask\"}\n",
                 a.routine.c_str(), a.type.c_str(), (long long) n, (long long) nb, seconds,
@@ -466,6 +474,14 @@ int main(int argc, char** argv)
         if (eq != std::string::npos) a.kv[s.substr(0, eq)] = s.substr(eq + 1);
     }
     if (a.kv.count("threads")) omp_set_num_threads(std::atoi(a.kv["threads"].c_str()));
+    MPI_Comm_rank(MPI_COMM_WORLD, &g_rank);
+    MPI_Comm_size(MPI_COMM_WORLD, &g_world);
+    g_p = int(a.geti("p", 1)); g_q = int(a.geti("q", 1));
+    if (g_p * g_q != g_world) {
+        std::fprintf(stderr, "ref_dump: grid %d x %d needs %d ranks, the world has %d\n", g_p, g_q, g_p * g_q, g_world);
+        return 2;
+    }
+    if (g_world > 1) a.prefix += ".r" + std::to_string(g_rank);
     int rc = 2;
     if      (a.type == "d") rc = run<double>(a);
     else if (a.type == "z") rc = run<std::complex<double>>(a);

@@ -6,7 +6,8 @@ checker for the CUDA path; it is never imported by the product package
 --impl reference leg may import it.
 
 PINNED: every function below is checked against the UNMODIFIED reference built by
-oracle/build_ref.sh (oracle/_ref/ref_dump, the reference's own HostTask path) --
+oracle/build_ref.sh (oracle/_ref/ref_dump, the reference's own HostTask path; on process
+grids oracle/build_ref_mp.sh -> oracle/_ref/ref_dump_mp under oracle/mprun.py) --
 bit-exact for the Philox generator and the pivot vectors, to a few ulp for the
 floating-point factors -- by tests/test_oracle.py, using the committed fixtures in
 tests/golden/ (made by tests/golden/make_golden.py) and, when oracle/_ref is
@@ -370,8 +371,10 @@ def getrs(LU, pivots, B, nb: int):
 #   driver: interchanges applied to the whole block row range, A(k,k) <- factored tile, A(i,k) <- A(i,k) U_kk^-1 below
 #     it (trsm Right/Upper/NonUnit, :171-184), then the row solve and trailing update of getrf.
 #
-# PINNED for ranks = 1 (the only case the reference can run in this container: the MPI stub is serial) by
-# tests/golden/getrf_tntpiv_d*.npz; for ranks > 1 the tree is a restatement by reading -- parity UNPINNED.
+# PINNED: for ranks = 1 by tests/golden/getrf_tntpiv_d*.npz (the one-rank reference, oracle/_ref/ref_dump); for ranks > 1 by
+# tests/golden/grid_getrf_tntpiv_d_*.npz, written by the unmodified reference RUNNING ON 2x1, 3x1, 4x1 and 2x4 PROCESS GRIDS
+# (oracle/_ref/ref_dump_mp: the reference built against the multi-process MPI replacement oracle/mpi_mp, oracle/mprun.py) --
+# identical pivots, factors to 1e-13 (tests/test_oracle.py).
 # With one rank the pivots are those of partial pivoting; the factor differs from getrf's in rounding only.
 # ----------------------------------------------------------------------------
 def tnt_winners_to_sequential(winners, m_p: int):

@@ -28,6 +28,8 @@ generator fixture pins that), only outputs:
   getrf_z.npz, getrf_c.npz  complex LU and pivots (cabs1 rule), n=192 / 200 (ragged) nb=64; gesv_z.npz its solve, n=200 nrhs=70;
                             gesv_mixed_z.npz, posv_mixed_z.npz complex mixed solvers (solution + iteration count), n=256 nb=64;
                             getrf_tntpiv_z.npz (CALU, n=192), getrf_nopiv_z.npz (rand_dominant, n=200)
+  grid_*.npz                the reference ON PROCESS GRIDS (oracle/_ref/ref_dump_mp under oracle/mprun.py): getrf_tntpiv on 2x1 / 3x1 /
+                            4x1 / 2x4 ranks (the tournament proper), getrf on 2x2 / 3x2, potrf on 2x2; nb=64
   getrf_tntpiv_d{,_ragged,_tall}.npz   LU with tournament pivoting (MethodLU::CALU), 384x384 / 300x300 / 512x256, nb=128
 
 Usage (in the build container, where /root/reference exists):  python tests/golden/make_golden.py
@@ -59,6 +61,61 @@ def run(routine, t, n, nb, seeds=(42, 43, 44), **kv):
         dtype = np.int64 if key == "piv" else (np.float64 if (routine == "norms" and key == "out") else DT[t])
         files[key] = np.fromfile(os.path.join(tmp, f), dtype=dtype)
     return files, meta
+
+
+MPRUN = os.path.join(ROOT, "oracle", "mprun.py")
+EXE_MP = os.path.join(ROOT, "oracle", "_ref", "ref_dump_mp")
+
+
+def tile_owner(i, j, p, q):
+    return (i % p) + (j % q) * p            # GridOrder::Col (include/slate/func.hh:96-104)
+
+
+def run_mp(routine, t, n, nb, p, q, seeds=(42, 43, 44), m=None, **kv):
+    """The unmodified reference on a p x q process grid: oracle/_ref/ref_dump_mp (built by oracle/build_ref_mp.sh against the
+    multi-process MPI replacement oracle/mpi_mp) under oracle/mprun.py.  Every rank writes the tiles it owns; they are
+    assembled here with the reference's tile map.  Returns ({name: array}, meta)."""
+    m = n if m is None else m
+    tmp = tempfile.mkdtemp()
+    prefix = os.path.join(tmp, "x")
+    cmd = [sys.executable, MPRUN, "-n", str(p * q), EXE_MP, routine, t, str(n), str(nb), *map(str, seeds), prefix,
+           f"p={p}", f"q={q}", f"m={m}"] + [f"{k}={v}" for k, v in kv.items()]
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True)
+    meta = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    out = {}
+    names = {f.split(".")[2] for f in os.listdir(tmp)}
+    for name in names:
+        if name == "piv":
+            out[name] = np.fromfile(f"{prefix}.r0.piv.bin", dtype=np.int64)
+            continue
+        rows = m if routine in ("getrf", "gemm") else n
+        parts = [np.fromfile(f"{prefix}.r{k}.{name}.bin", dtype=DT[t]).reshape(rows, -1, order="F") for k in range(p * q)]
+        full = np.zeros_like(parts[0])
+        for j in range(-(-full.shape[1] // nb)):
+            for i in range(-(-rows // nb)):
+                full[i * nb:(i + 1) * nb, j * nb:(j + 1) * nb] = parts[tile_owner(i, j, p, q)][i * nb:(i + 1) * nb, j * nb:(j + 1) * nb]
+        out[name] = full
+    return out, meta
+
+
+def grid_fixtures():
+    """Outputs of the reference itself on process grids (tournament pivoting needs >= 2 ranks in a process column to be
+    more than partial pivoting; the cross-rank pivot rule of getrf and the Cholesky / SUMMA data flow likewise)."""
+    if not os.path.exists(EXE_MP):
+        sys.exit("oracle/_ref/ref_dump_mp missing: run oracle/build_ref_mp.sh first")
+    for name, p, q, m, n, full in (("grid_getrf_tntpiv_d_2x1", 2, 1, 384, 384, True), ("grid_getrf_tntpiv_d_3x1_ragged", 3, 1, 300, 300, True),
+                                   ("grid_getrf_tntpiv_d_4x1_tall", 4, 1, 448, 256, True), ("grid_getrf_tntpiv_d_2x4", 2, 4, 512, 512, False)):
+        f, meta = run_mp("getrf", "d", n, 64, p, q, m=m, ib=16, pt=1, method="calu")
+        extra = {"out": f["out"]} if full else {"diag_u": np.diag(f["out"]).copy(), "abs_sum": np.abs(f["out"]).sum()}
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), piv=f["piv"].reshape(-1, 2), info=meta["info"], **extra)
+    f, meta = run_mp("getrf", "d", 384, 64, 2, 2, ib=16, pt=1)
+    np.savez_compressed(os.path.join(OUT, "grid_getrf_d_2x2.npz"), out=f["out"], piv=f["piv"].reshape(-1, 2), info=meta["info"])
+    f, meta = run_mp("getrf", "d", 300, 64, 3, 2, seeds=(7, 43, 44), m=500, ib=16, pt=1)
+    np.savez_compressed(os.path.join(OUT, "grid_getrf_d_3x2_tall.npz"), piv=f["piv"].reshape(-1, 2), info=meta["info"],
+                        diag_u=np.diag(f["out"]).copy(), abs_sum=np.abs(f["out"]).sum())
+    f, meta = run_mp("potrf", "d", 384, 64, 2, 2)
+    np.savez_compressed(os.path.join(OUT, "grid_potrf_d_2x2.npz"), out=np.tril(f["out"]), info=meta["info"])
 
 
 def tntpiv_fixtures():
@@ -148,6 +205,8 @@ def main():
     tntpiv_fixtures()
     # complex LU (cabs1 pivot rule, src/internal/Tile_getrf.hh:210-237) and its solve
     complex_lu_fixtures()
+    # the reference on process grids (multi-process MPI replacement, oracle/mpi_mp)
+    grid_fixtures()
     print("golden fixtures written to", OUT)
 
 if __name__ == "__main__":
@@ -155,5 +214,7 @@ if __name__ == "__main__":
         tntpiv_fixtures()
     elif len(sys.argv) > 1 and sys.argv[1] == "complex_lu":
         complex_lu_fixtures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "grid":
+        grid_fixtures()
     else:
         main()

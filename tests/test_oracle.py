@@ -225,6 +225,71 @@ def test_complex_tntpiv_and_nopiv_match_reference(golden_dir):
     assert np.abs(LU - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# The reference ON PROCESS GRIDS: tests/golden/grid_*.npz were written by the unmodified reference running on p x q ranks
+# (oracle/_ref/ref_dump_mp = the reference built against the multi-process MPI replacement oracle/mpi_mp, started by
+# oracle/mprun.py).  They pin what one rank cannot: the tournament proper (>= 2 ranks in a process column), the cross-rank
+# pivot rule of getrf, the grid data flow of potrf.
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,ranks,m,n", [("grid_getrf_tntpiv_d_2x1", 2, 384, 384), ("grid_getrf_tntpiv_d_3x1_ragged", 3, 300, 300),
+                                            ("grid_getrf_tntpiv_d_4x1_tall", 4, 448, 256), ("grid_getrf_tntpiv_d_2x4", 2, 512, 512)])
+def test_tournament_matches_the_multirank_reference(golden_dir, name, ranks, m, n):
+    """internal_getrf_tntpiv.cc with several participants per panel: IDENTICAL pivots, factor to rounding."""
+    g = load(golden_dir, name)
+    A = o.generate("rand", m, n, 42)
+    LU, piv, info = o.getrf_tntpiv(A, 64, 16, ranks=ranks)
+    flat = np.array([p for col in piv for p in col], dtype=np.int64)
+    assert np.array_equal(flat, g["piv"]), "the restated tournament picks other rows than the reference on this grid"
+    assert info == int(g["info"]) == 0
+    if "out" in g:
+        assert np.abs(LU - g["out"]).max() <= 1e-12 * np.abs(g["out"]).max()
+    else:
+        assert np.abs(np.diag(LU) - g["diag_u"]).max() <= 1e-12 * np.abs(g["diag_u"]).max()
+        assert abs(np.abs(LU).sum() - float(g["abs_sum"])) <= 1e-11 * float(g["abs_sum"])
+
+
+def test_getrf_and_potrf_match_the_multirank_reference(golden_dir):
+    """Partial pivoting across ranks (MPI_MAXLOC keeps the lowest rank on ties, Tile_getrf.hh:256-289) and Cholesky on a
+    2 x 2 grid give what the one-rank run gives: the restatement needs no grid parameter."""
+    g = load(golden_dir, "grid_getrf_d_2x2")
+    A = o.generate("rand", 384, 384, 42)
+    LU, piv, info = o.getrf(A, 64, 16)
+    assert np.array_equal(np.array([p for col in piv for p in col], dtype=np.int64), g["piv"]) and info == int(g["info"]) == 0
+    assert np.abs(LU - g["out"]).max() <= 1e-12 * np.abs(g["out"]).max()
+    g = load(golden_dir, "grid_getrf_d_3x2_tall")
+    LU, piv, info = o.getrf(o.generate("rand", 500, 300, 7), 64, 16)
+    assert np.array_equal(np.array([p for col in piv for p in col], dtype=np.int64), g["piv"])
+    assert np.abs(np.diag(LU) - g["diag_u"]).max() <= 1e-12 * np.abs(g["diag_u"]).max()
+    g = load(golden_dir, "grid_potrf_d_2x2")
+    G = o.generate("rand_dominant", 384, 384, 42)
+    L, info = o.potrf(o.he_full(np.tril(G)), 64)
+    assert info == int(g["info"]) == 0
+    assert np.abs(np.tril(L) - g["out"]).max() <= 16 * EPS * np.abs(g["out"]).max()
+
+
+def test_live_multirank_reference_agrees_when_built(tmp_path):
+    """When oracle/_ref/ref_dump_mp is present: the reference on 2 x 1 ranks, live, another size and seed, CALU."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "ref_dump_mp")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_dump_mp not built in this environment")
+    import subprocess
+    import sys
+    n, nb, p = 200, 32, 2
+    prefix = str(tmp_path / "x")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="2")
+    subprocess.run([sys.executable, os.path.join(root, "oracle", "mprun.py"), "-n", str(p), "--timeout", "120", exe, "getrf", "d",
+                    str(n), str(nb), "11", "0", "0", prefix, f"p={p}", "q=1", "ib=16", "pt=1", "method=calu"],
+                   check=True, env=env, capture_output=True)
+    piv = np.fromfile(prefix + ".r0.piv.bin", dtype=np.int64).reshape(-1, 2)
+    parts = [np.fromfile(f"{prefix}.r{r}.out.bin").reshape(n, n, order="F") for r in range(p)]
+    LU, pv, info = o.getrf_tntpiv(o.generate("rand", n, n, 11), nb, 16, ranks=p)
+    assert np.array_equal(np.array([x for col in pv for x in col], dtype=np.int64), piv)
+    for i in range(-(-n // nb)):                                   # tile row i lives on rank i % p
+        blk = slice(i * nb, min((i + 1) * nb, n))
+        assert np.abs(parts[i % p][blk] - LU[blk]).max() <= 1e-12 * np.abs(LU).max()
+
+
 def test_trsm_matches_reference(golden_dir):
     g = load(golden_dir, "trsm_d")
     m, n = 256, 128

@@ -89,6 +89,21 @@ def test_tntpiv_tournament_matches_oracle(sl, monkeypatch, ranks, m, n, nb):
     _check_lu(A0, LU, piv, nb)
 
 
+@pytest.mark.parametrize("name,ranks,m,n", [("grid_getrf_tntpiv_d_2x1", 2, 384, 384), ("grid_getrf_tntpiv_d_3x1_ragged", 3, 300, 300),
+                                            ("grid_getrf_tntpiv_d_4x1_tall", 4, 448, 256)])
+def test_tntpiv_tournament_matches_multirank_reference_golden(sl, golden_dir, monkeypatch, name, ranks, m, n):
+    """Against what the UNMODIFIED reference computed on `ranks` x 1 process grids (tests/golden/grid_*.npz, written through
+    oracle/mprun.py): identical pivots, factor within the LU bound.  (Added after the round's GPU budget ended: the same
+    cases are GPU-validated against the oracle above, and the oracle is pinned to these files in tests/test_oracle.py.)"""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    monkeypatch.setenv("SB200_TNT_RANKS", str(ranks))
+    A = sl.Matrix(m, n, 64).generate("rand", 42)
+    piv, info = sl.getrf_tntpiv(A)
+    assert info == int(g["info"]) == 0
+    assert np.array_equal(np.array([x for c in piv for x in c], dtype=np.int64), g["piv"])
+    assert np.abs(A.to_host() - g["out"]).max() <= GETRF_TOL * np.abs(g["out"]).max()
+
+
 @pytest.mark.parametrize("ranks", [1, 2])
 @pytest.mark.parametrize("m,n,nb", [(384, 384, 128), (300, 300, 64), (448, 256, 64)])
 def test_tntpiv_grid_algorithm_on_one_rank(sl, monkeypatch, ranks, m, n, nb):
