@@ -71,15 +71,15 @@ def tile_owner(i, j, p, q):
     return (i % p) + (j % q) * p            # GridOrder::Col (include/slate/func.hh:96-104)
 
 
-def run_mp(routine, t, n, nb, p, q, seeds=(42, 43, 44), m=None, **kv):
+def run_mp(routine, t, n, nb, p, q, seeds=(42, 43, 44), m=None, rows=None, **kv):
     """The unmodified reference on a p x q process grid: oracle/_ref/ref_dump_mp (built by oracle/build_ref_mp.sh against the
     multi-process MPI replacement oracle/mpi_mp) under oracle/mprun.py.  Every rank writes the tiles it owns; they are
     assembled here with the reference's tile map.  Returns ({name: array}, meta)."""
-    m = n if m is None else m
     tmp = tempfile.mkdtemp()
     prefix = os.path.join(tmp, "x")
     cmd = [sys.executable, MPRUN, "-n", str(p * q), EXE_MP, routine, t, str(n), str(nb), *map(str, seeds), prefix,
-           f"p={p}", f"q={q}", f"m={m}"] + [f"{k}={v}" for k, v in kv.items()]
+           f"p={p}", f"q={q}"] + ([f"m={m}"] if m is not None else []) + [f"{k}={v}" for k, v in kv.items()]
+    m = n if m is None else m
     env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="2")
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True)
     meta = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
@@ -89,11 +89,11 @@ def run_mp(routine, t, n, nb, p, q, seeds=(42, 43, 44), m=None, **kv):
         if name == "piv":
             out[name] = np.fromfile(f"{prefix}.r0.piv.bin", dtype=np.int64)
             continue
-        rows = m if routine in ("getrf", "gemm") else n
-        parts = [np.fromfile(f"{prefix}.r{k}.{name}.bin", dtype=DT[t]).reshape(rows, -1, order="F") for k in range(p * q)]
+        nrows = rows if rows is not None else (m if routine in ("getrf", "gemm") else n)
+        parts = [np.fromfile(f"{prefix}.r{k}.{name}.bin", dtype=DT[t]).reshape(nrows, -1, order="F") for k in range(p * q)]
         full = np.zeros_like(parts[0])
         for j in range(-(-full.shape[1] // nb)):
-            for i in range(-(-rows // nb)):
+            for i in range(-(-nrows // nb)):
                 full[i * nb:(i + 1) * nb, j * nb:(j + 1) * nb] = parts[tile_owner(i, j, p, q)][i * nb:(i + 1) * nb, j * nb:(j + 1) * nb]
         out[name] = full
     return out, meta

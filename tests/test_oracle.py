@@ -450,3 +450,51 @@ def test_mixed_fallback_and_failure_codes():
     X, it, info = o.solve_mixed(A, rng.random((n, 3)), nb, hermitian=False, itermax=0, tol=1e-30, use_fallback=True)
     assert it == -1 and info == 0
     assert o.solve_residual(A, X, (A @ X)) <= 25 * EPS       # fallback solved in FP64
+
+
+# one-rank golden file, routine, type, n, nb, extra keys, rows of the output, tolerance (relative to the largest entry)
+_GRID_CASES = [
+    ("potrf_d", "potrf", "d", 384, 128, {}, 384, 64 * EPS),
+    ("getrf_d_ragged", "getrf", "d", 300, 128, {"ib": 16, "pt": 1}, 300, 1e-12),
+    ("getrf_z", "getrf", "z", 192, 64, {"ib": 16, "pt": 1}, 192, 1e-12),
+    ("gemm_d", "gemm", "d", 256, 64, {}, 256, 64 * EPS),
+    ("herk_z", "herk", "z", 256, 64, {"k": 128}, 256, 64 * EPS),
+    ("trsm_d", "trsm", "d", 128, 64, {"m": 256}, 256, 1e-12),
+    ("posv_d", "posv", "d", 300, 128, {}, 300, 1e-12),
+    ("gesv_d", "gesv", "d", 300, 128, {"ib": 16, "pt": 1}, 300, 1e-11),
+    ("hemm_z", "hemm", "z", 192, 64, {"nrhs": 70}, 192, 64 * EPS),
+    ("her2k_z", "her2k", "z", 200, 64, {"k": 100}, 200, 64 * EPS),
+    ("getrf_nopiv_d", "getrf_nopiv", "d", 300, 128, {}, 300, 1e-12),
+    ("gesv_mixed_d", "gesv_mixed", "d", 256, 64, {"ib": 16, "pt": 1}, 256, 1e-11),
+    ("posv_mixed_z", "posv_mixed", "z", 256, 64, {}, 256, 1e-11),
+]
+
+
+@pytest.mark.parametrize("golden,routine,t,n,nb,kv,rows,tol", _GRID_CASES, ids=[c[0] for c in _GRID_CASES])
+def test_reference_on_a_2x2_grid_reproduces_its_one_rank_golden(golden_dir, golden, routine, t, n, nb, kv, rows, tol):
+    """Live, when oracle/_ref/ref_dump_mp is present: the unmodified reference on a 2 x 2 process grid (oracle/mpi_mp)
+    gives, tile by tile, what it gave on one rank (the committed fixture) -- same pivots, same refinement iteration counts,
+    outputs to rounding.  This is what licenses comparing the multi-GPU runs of the product with the one-rank oracle."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "ref_dump_mp")):
+        pytest.skip("oracle/_ref/ref_dump_mp not built in this environment")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = load(golden_dir, golden)
+    kv = dict(kv)
+    m = kv.pop("m", None)
+    f, meta = mg.run_mp(routine, t, n, nb, 2, 2, m=m, rows=rows, **kv)
+    out = f["out"]
+    ref = g["out"]
+    if routine in ("potrf", "herk", "her2k"):
+        out, ref = np.tril(out), np.tril(ref)
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
+    if "piv" in g:
+        assert np.array_equal(f["piv"].reshape(-1, 2), g["piv"])
+    if "iters" in g:
+        assert int(meta["iters"]) == int(g["iters"])
+    if "info" in g:
+        assert int(meta["info"]) == int(g["info"])
