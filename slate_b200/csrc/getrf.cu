@@ -871,7 +871,9 @@ int sb200_getrf_nopiv_s(sb200_matrix_t h, const sb200_options_t* opts, int64_t* 
 
 /* LU with tournament pivoting (slate::getrf_tntpiv, src/getrf_tntpiv.cc; MethodLU::CALU of slate::lu_factor): the getrf
  * drivers with the panel of getrf_tnt.cu.  Participants per panel = process rows of the grid.
- * STATUS: see DESIGN.md section 0 (row (f)2). */
+ * STATUS: validated on one B200 at the end of round 2 (profiles/r02r1_*, r02r2_*): 1 - 4 participants per panel through
+ * SB200_TNT_RANKS, single-rank and grid driver, identical pivots against the oracle, which is pinned to the reference's own
+ * runs on 2x1 ... 2x4 process grids (tests/golden/grid_getrf_tntpiv_d_*.npz); not yet run on a real p x q grid. */
 static int getrf_tntpiv_any(sb200_matrix_t h, int64_t* pivots, int64_t* info, int dtype)
 {
     if (! h || h->A.dtype != dtype) return SB200_EINVAL;

@@ -13,7 +13,7 @@
 // B200-first: the low-precision factorisation is FP32 whose trailing update runs on the tcgen05
 // FP32-emulated (3 x TF32) kernel (gemm_tc05.cu); every sweep / product is a handful of batched
 // launches from a pointer plan built once per call; nothing is staged through the host.
-// This round the solve path runs on a 1 x 1 grid (one GPU); p x q grids return SB200_ENOTSUP.
+// This file is the 1 x 1-grid solve path; real-type solves on p x q grids are solve_dist.cu (complex: SB200_ENOTSUP there).
 #include "runtime_internal.hh"
 #include "getrf_internal.hh"
 #include <algorithm>
