@@ -133,13 +133,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
+# bench routine -> (ref_dump routine, type, extra keys) of the reference's own HostTask run
+REF_ROUTINE = {"zgemm": ("gemm", "z", []), "zherk": ("herk", "z", []), "zpotrf": ("potrf", "z", []), "zgetrf": ("getrf", "z", []),
+               "getrf_tntpiv": ("getrf", "d", ["method=calu"])}
+
+
 def cpu_reference_run(routine: str, n: int, nb: int, threads: int):
     """Time the UNMODIFIED reference's HostTask path (oracle/_ref/ref_dump) on the host cores.
     Falls back to the numpy restatement (kind 'port') only if oracle/_ref is absent."""
     exe = os.path.join(HERE, "oracle", "_ref", "ref_dump")
     if os.path.exists(exe):
         env = dict(os.environ, OMP_NUM_THREADS=str(threads), OPENBLAS_NUM_THREADS="1")
-        out = subprocess.run([exe, routine, "d", str(n), str(nb), "42", "43", "44", "/tmp/_sb200_ref", "dump=0"],
+        rr, rt, rkv = REF_ROUTINE.get(routine, (routine, "d", []))
+        out = subprocess.run([exe, rr, rt, str(n), str(nb), "42", "43", "44", "/tmp/_sb200_ref", "dump=0"] + rkv,
                              capture_output=True, text=True, env=env, timeout=1800)
         line = [l for l in out.stdout.splitlines() if l.startswith("{")]
         if not line:
@@ -180,7 +186,12 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
+    if args.routine == "tileops":
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU reference leg for --routine tileops"}))
+        return 0
     n = args.ref_n or pick_ref_n(args.routine, args.steps + 1)
+    if not args.ref_n and args.routine[0] == "z":
+        n = min(n, 8192)                      # four times the real flops per element: keep the sample within the time bound
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_reference_run(args.routine, n, args.nb, threads)
     secs, kind = [], "reference"
@@ -188,11 +199,8 @@ def run_reference(args):
         s, kind = cpu_reference_run(args.routine, n, args.nb, threads)
         secs.append(s)
     ms = 1e3 * sum(secs) / len(secs)
-    if args.routine in ("posv_mixed", "gesv_mixed"):
+    if args.routine in EXTRA_ROUTINES:
         val = extra_flops(args.routine, n, args.nrhs) / (ms * 1e-3) / 1e12
-    elif args.routine in EXTRA_ROUTINES:
-        print(json.dumps({"impl": "reference", "unavailable": f"no CPU reference leg for --routine {args.routine}"}))
-        return 0
     else:
         val = flops(args.routine, n) / (ms * 1e-3) / 1e12
     n_full = args.n or default_n(args.routine, args.gpus)
@@ -204,9 +212,9 @@ def run_reference(args):
               f"sample of the n={n_full} workload (same generator, seed and tile size; the full size takes minutes per step "
               f"on the host) -- the metric is a rate")
     line = {
-        "impl": "reference", "metric": f"d{args.routine} TFLOP/s", "value": val, "unit": "TFLOP/s",
+        "impl": "reference", "metric": f"{args.routine if args.routine[0] == 'z' else 'd' + args.routine} TFLOP/s", "value": val, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128" if args.routine[0] == "z" else "f64",
         "data": "synthetic (reference matgen Philox rand/rand_dominant, seed 42)",
         "config": workload_config(args.routine, n_full, args.nb, p, q, args.gpus),
         "sample_n": n,
