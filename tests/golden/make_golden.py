@@ -77,11 +77,11 @@ def run_mp(routine, t, n, nb, p, q, seeds=(42, 43, 44), m=None, rows=None, **kv)
     assembled here with the reference's tile map.  Returns ({name: array}, meta)."""
     tmp = tempfile.mkdtemp()
     prefix = os.path.join(tmp, "x")
-    cmd = [sys.executable, MPRUN, "-n", str(p * q), EXE_MP, routine, t, str(n), str(nb), *map(str, seeds), prefix,
+    cmd = [sys.executable, MPRUN, "-n", str(p * q), "--timeout", "150", EXE_MP, routine, t, str(n), str(nb), *map(str, seeds), prefix,
            f"p={p}", f"q={q}"] + ([f"m={m}"] if m is not None else []) + [f"{k}={v}" for k, v in kv.items()]
     m = n if m is None else m
     env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="2")
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True, timeout=200)
     meta = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     out = {}
     names = {f.split(".")[2] for f in os.listdir(tmp)}
