@@ -5,6 +5,7 @@
 #   oracle/_ref/libslate_ref_mp.so   SLATE + matgen compiled with oracle/mpi_mp/mpi.h (blaspp / lapackpp objects: those of
 #                                    oracle/build_ref.sh, they do not see MPI)
 #   oracle/_ref/ref_dump_mp          oracle/ref_dump.cc linked to it; run it through  python oracle/mprun.py -n N ... p=P q=Q
+#   oracle/_ref/tester_mp            the reference's own tester:  python oracle/mprun.py -n 4 oracle/_ref/tester_mp --grid 2x2 ... getrf
 # Sources are compiled where they lie under /root/reference; nothing is copied.  Needs oracle/build_ref.sh to have run.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -54,3 +55,15 @@ g++ -shared -fopenmp -o "$OUT/libslate_ref_mp.so" "$OBJMP"/slate/*.o "$OBJMP/mpi
 $CXX -O2 $I_SL "$HERE/ref_dump.cc" -o "$OUT/ref_dump_mp" \
     -L"$OUT" -lslate_ref_mp "$OB" -Wl,-rpath,"$OUT" -Wl,-rpath,"$(dirname "$OB")" -Wl,-rpath,'$ORIGIN' -lpthread
 echo "build_ref_mp: ref_dump_mp linked ($((SECONDS-t0)) s)"
+
+# the reference's own tester on process grids: python oracle/mprun.py -n 4 oracle/_ref/tester_mp --grid 2x2 ... getrf
+if [ "${SB200_SKIP_TESTER:-0}" != "1" ]; then
+    mkdir -p "$OBJMP/ts" "$OBJMP/test"
+    TS=( "$R"/testsweeper/testsweeper.cc "$R"/testsweeper/version.cc )
+    TEST=( "$R"/test/*.cc )
+    compile_set "$OBJMP/ts"   -O2 $I_SL -I"$R/testsweeper" -- "${TS[@]}"
+    compile_set "$OBJMP/test" -O1 $I_SL -I"$R/testsweeper" -I"$R/test" -- "${TEST[@]}"
+    g++ -fopenmp -o "$OUT/tester_mp" "$OBJMP"/test/*.o "$OBJMP"/ts/*.o \
+        -L"$OUT" -lslate_ref_mp "$OB" -Wl,-rpath,"$OUT" -Wl,-rpath,"$(dirname "$OB")" -Wl,-rpath,'$ORIGIN' -lpthread
+    echo "build_ref_mp: tester_mp linked ($((SECONDS-t0)) s)"
+fi

@@ -510,3 +510,25 @@ def test_reference_on_a_2x2_grid_reproduces_its_one_rank_golden(golden_dir, gold
         assert int(meta["iters"]) == int(g["iters"])
     if "info" in g:
         assert int(meta["info"]) == int(g["info"])
+
+
+@pytest.mark.parametrize("grid,routine,extra", [("2x2", "potrf", []), ("2x2", "getrf", ["--method-lu", "PPLU,CALU"]), ("2x4", "getrf", ["--method-lu", "CALU"]),
+                                                ("2x2", "gemm", []), ("2x2", "gesv_mixed", []), ("3x1", "getrf", ["--method-lu", "CALU", "--type", "z"])])
+def test_reference_tester_passes_on_process_grids(grid, routine, extra):
+    """The reference's OWN acceptance checks (test/test_posv.cc:304-345, test_gesv.cc:371-377, test_gemm.cc:205-207) pass when the
+    unmodified reference runs on p x q ranks over the multi-process MPI replacement (oracle/_ref/tester_mp): the replacement
+    is faithful enough to carry the grid golden vectors."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "tester_mp")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/tester_mp not built in this environment")
+    import subprocess
+    import sys
+    p, q = (int(x) for x in grid.split("x"))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, os.path.join(root, "oracle", "mprun.py"), "-n", str(p * q), "--timeout", "150", exe, "--grid", grid,
+           "--type", "d", "--dim", "300", "--nb", "64", "--target", "t", "--check", "y", "--ref", "n"] + extra + [routine]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=200)
+    assert r.returncode == 0, r.stdout[-800:] + r.stderr[-400:]
+    assert f"All tests passed: {routine}" in r.stdout
+    assert "FAILED" not in r.stdout
