@@ -532,3 +532,43 @@ def test_reference_tester_passes_on_process_grids(grid, routine, extra):
     assert r.returncode == 0, r.stdout[-800:] + r.stderr[-400:]
     assert f"All tests passed: {routine}" in r.stdout
     assert "FAILED" not in r.stdout
+
+
+def _sweep_cases():
+    rng = np.random.default_rng(20261018)
+    out = []
+    for _ in range(10):
+        nb = int(rng.choice([16, 24, 32, 48]))
+        p, q = int(rng.integers(2, 5)), int(rng.integers(1, 3))
+        if rng.random() < 0.5:
+            n = int(rng.integers(3, 9)) * nb + int(rng.integers(0, nb))          # square, ragged last tile
+            m = n
+        else:
+            n = int(rng.integers(2, 6)) * nb                                      # tall, full-width panels
+            m = n + int(rng.integers(1, 4 * nb))
+        out.append((m, n, nb, p, q, int(rng.integers(1, 1000))))
+    return out
+
+
+@pytest.mark.parametrize("m,n,nb,p,q,seed", _sweep_cases())
+def test_tournament_sweep_against_the_live_multirank_reference(tmp_path, m, n, nb, p, q, seed):
+    """Seeded sweep over shapes, tile sizes and grids: the restated tournament picks the reference's pivots everywhere."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "ref_dump_mp")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_dump_mp not built in this environment")
+    import subprocess
+    import sys
+    prefix = str(tmp_path / "x")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="2")
+    subprocess.run([sys.executable, os.path.join(root, "oracle", "mprun.py"), "-n", str(p * q), "--timeout", "150", exe, "getrf", "d",
+                    str(n), str(nb), str(seed), "0", "0", prefix, f"p={p}", f"q={q}", f"m={m}", "ib=8", "pt=1", "method=calu"],
+                   check=True, env=env, capture_output=True, timeout=200)
+    piv = np.fromfile(prefix + ".r0.piv.bin", dtype=np.int64).reshape(-1, 2)
+    LU, pv, info = o.getrf_tntpiv(o.generate("rand", m, n, seed), nb, 8, ranks=p)
+    assert np.array_equal(np.array([x for col in pv for x in col], dtype=np.int64), piv)
+    parts = [np.fromfile(f"{prefix}.r{r}.out.bin").reshape(m, n, order="F") for r in range(p * q)]
+    for j in range(-(-n // nb)):
+        for i in range(-(-m // nb)):
+            ri, cj = slice(i * nb, min((i + 1) * nb, m)), slice(j * nb, min((j + 1) * nb, n))
+            assert np.abs(parts[(i % p) + (j % q) * p][ri, cj] - LU[ri, cj]).max() <= 1e-11 * np.abs(LU).max()
