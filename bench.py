@@ -166,6 +166,7 @@ def cpu_reference_run(routine: str, n: int, nb: int, threads: int):
 
 
 REF_RATE = {"potrf": 0.65e12, "getrf": 0.45e12, "gemm": 0.8e12}     # HostTask on 16 host threads, as measured in round 1 / 2
+REF_PROBE_N = 8192                                                  # size of the rate probe of --impl reference
 
 
 def pick_ref_n(routine, runs, budget_s=150.0, rate=None):
@@ -189,7 +190,16 @@ def run_reference(args):
     if args.routine == "tileops":
         print(json.dumps({"impl": "reference", "unavailable": "no CPU reference leg for --routine tileops"}))
         return 0
-    n = args.ref_n or pick_ref_n(args.routine, args.steps + 1)
+    probe = None
+    if not args.ref_n and args.routine in REF_RATE:
+        # the tabulated rates are from one box; measure this box's (one short run: the HostTask rate only rises with n,
+        # so a size chosen with the probe's rate finishes inside the bound)
+        try:
+            s0, _ = cpu_reference_run(args.routine, REF_PROBE_N, args.nb, threads)
+            probe = flops(args.routine, REF_PROBE_N) / s0
+        except Exception:   # noqa: BLE001
+            probe = None
+    n = args.ref_n or pick_ref_n(args.routine, args.steps + 1, rate=probe)
     if not args.ref_n and args.routine[0] == "z":
         n = min(n, 8192)                      # four times the real flops per element: keep the sample within the time bound
     for _ in range(args.warmup if args.warmup < 2 else 1):
@@ -217,7 +227,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128" if args.routine[0] == "z" else "f64",
         "data": "synthetic (reference matgen Philox rand/rand_dominant, seed 42)",
         "config": workload_config(args.routine, n_full, args.nb, p, q, args.gpus),
-        "sample_n": n,
+        "sample_n": n, "sample_rate_probe_tflops": (probe / 1e12 if probe else None),
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -839,7 +849,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             threads = os.cpu_count() or 1
-            ref_n = args.ref_n or 16384             # one run of 10-30 s of host work
+            ref_n = args.ref_n or 32768             # one run of 10-30 s of host work (11.7 TFLOP at about 1.1 TFLOP/s on 16 threads)
             secs, kind = cpu_reference_run(routine, ref_n, nb, threads)
             cpu = {"value": flops(routine, ref_n) / secs / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": kind,
                    "sample": f"d{routine} n={ref_n} nb={nb} Target::HostTask (the workload's generator and tile size at a "

@@ -76,3 +76,6 @@ def test_reference_sample_size_fits_its_time_budget():
         for runs in (1, 4, 21, 200):
             n = bench.pick_ref_n(r, runs)
             assert n == 8192 or runs * bench.flops(r, n) / bench.REF_RATE[r] <= 150.0
+    # with the rate the arm probes on the box (one n = 8192 run) instead of the tabulated one
+    assert bench.pick_ref_n("potrf", 21, rate=1.0e12) == 24576
+    assert bench.pick_ref_n("potrf", 21, rate=0.1e12) == 8192
