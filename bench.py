@@ -849,7 +849,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             threads = os.cpu_count() or 1
-            ref_n = args.ref_n or 32768             # one run of 10-30 s of host work (11.7 TFLOP at about 1.1 TFLOP/s on 16 threads)
+            # one run of about 10 s of host work on 16 threads: dpotrf 11.7 TFLOP at 1.1 TFLOP/s; dgetrf 2.9 at 0.45; dgemm 8.8 at 0.8
+            ref_n = args.ref_n or (32768 if routine == "potrf" else 16384)
             secs, kind = cpu_reference_run(routine, ref_n, nb, threads)
             cpu = {"value": flops(routine, ref_n) / secs / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": kind,
                    "sample": f"d{routine} n={ref_n} nb={nb} Target::HostTask (the workload's generator and tile size at a "
