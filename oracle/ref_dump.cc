@@ -338,18 +338,21 @@ int run(const Args& a)
         if (dump) { auto d = to_dense(B); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
     }
     else if (a.routine == "hemm") {
-        // C = alpha A B + beta C, A Hermitian (lower), Side::Left (test/test_hemm.cc)
+        // C = alpha A B + beta C (side=l, default: A n x n, B and C n x nrhs) or C = alpha B A + beta C (side=r: B and C
+        // nrhs x n), A Hermitian (lower)  (test/test_hemm.cc:92-194)
+        const bool right = a.get("side", "l") == "r";
+        const slate::Side side = right ? slate::Side::Right : slate::Side::Left;
         slate::HermitianMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand"); p.seed = a.seedA;
         p.cond_request = p.cond_actual = p.condD = NAN;
         slate::generate_matrix(p, A);
-        auto B = make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
-        auto C = make_matrix<T>(n, nrhs, nb, a.seedC, "rand");
+        auto B = right ? make_matrix<T>(nrhs, n, nb, a.seedB, "rand") : make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
+        auto C = right ? make_matrix<T>(nrhs, n, nb, a.seedC, "rand") : make_matrix<T>(n, nrhs, nb, a.seedC, "rand");
         auto t0 = tic();
-        slate::hemm(slate::Side::Left, alpha, A, B, beta, C, opts);
+        slate::hemm(side, alpha, A, B, beta, C, opts);
         seconds = toc(t0);
-        gflop = blas::Gflop<T>::hemm(slate::Side::Left, n, nrhs);
+        gflop = right ? blas::Gflop<T>::hemm(side, nrhs, n) : blas::Gflop<T>::hemm(side, n, nrhs);
         if (dump) { auto d = to_dense(C); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
     }
     else if (a.routine == "her2k") {
@@ -394,35 +397,45 @@ int run(const Args& a)
         }
     }
     else if (a.routine == "trmm") {
-        // B = alpha A B, A lower triangular (rand), Side::Left, NoTrans (test/test_trmm.cc; slate::trmm, src/trmm.cc)
-        int64_t m = a.geti("m", n);   // A is m x m, B is m x n
+        // B = alpha op(A) B (side=l, default: A m x m) or B = alpha B op(A) (side=r: A n x n), B m x n, A lower triangular
+        // (rand), op=n|t|c as a transposed view of A  (test/test_trmm.cc:84-174; slate::trmm, src/trmm.cc)
+        int64_t m = a.geti("m", n);
         bool unit = a.get("diag", "n") == "u";
-        slate::TriangularMatrix<T> A(slate::Uplo::Lower, unit ? slate::Diag::Unit : slate::Diag::NonUnit, m, nb,
+        const bool right = a.get("side", "l") == "r";
+        const slate::Side side = right ? slate::Side::Right : slate::Side::Left;
+        const std::string op = a.get("op", "n");
+        slate::TriangularMatrix<T> A(slate::Uplo::Lower, unit ? slate::Diag::Unit : slate::Diag::NonUnit, right ? n : m, nb,
                                      slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedA;
         p.cond_request = p.cond_actual = p.condD = NAN;
         slate::generate_matrix(p, A);
         auto B = make_matrix<T>(m, n, nb, a.seedB, "rand");
+        auto opA = A;
+        if (op == "t") opA = slate::transpose(A);
+        else if (op == "c") opA = slate::conj_transpose(A);
         auto t0 = tic();
-        slate::trmm(slate::Side::Left, alpha, A, B, opts);
+        slate::trmm(side, alpha, opA, B, opts);
         seconds = toc(t0);
-        gflop = blas::Gflop<T>::trmm(slate::Side::Left, m, n);
+        gflop = blas::Gflop<T>::trmm(side, m, n);
         if (dump) { auto d = to_dense(B); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
     }
     else if (a.routine == "symm") {
-        // C = alpha A B + beta C, A complex-symmetric (lower), Side::Left (test/test_symm.cc; slate::symm, src/symm.cc)
+        // C = alpha A B + beta C (side=l) or C = alpha B A + beta C (side=r: B and C nrhs x n), A complex-symmetric (lower)
+        // (test/test_symm.cc; slate::symm, src/symm.cc)
+        const bool right = a.get("side", "l") == "r";
+        const slate::Side side = right ? slate::Side::Right : slate::Side::Left;
         slate::SymmetricMatrix<T> A(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = a.get("kind", "rand"); p.seed = a.seedA;
         p.cond_request = p.cond_actual = p.condD = NAN;
         slate::generate_matrix(p, A);
-        auto B = make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
-        auto C = make_matrix<T>(n, nrhs, nb, a.seedC, "rand");
+        auto B = right ? make_matrix<T>(nrhs, n, nb, a.seedB, "rand") : make_matrix<T>(n, nrhs, nb, a.seedB, "rand");
+        auto C = right ? make_matrix<T>(nrhs, n, nb, a.seedC, "rand") : make_matrix<T>(n, nrhs, nb, a.seedC, "rand");
         auto t0 = tic();
-        slate::symm(slate::Side::Left, alpha, A, B, beta, C, opts);
+        slate::symm(side, alpha, A, B, beta, C, opts);
         seconds = toc(t0);
-        gflop = blas::Gflop<T>::symm(slate::Side::Left, n, nrhs);
+        gflop = right ? blas::Gflop<T>::symm(side, nrhs, n) : blas::Gflop<T>::symm(side, n, nrhs);
         if (dump) { auto d = to_dense(C); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
     }
     else if (a.routine == "norms") {

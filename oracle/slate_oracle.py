@@ -586,13 +586,17 @@ def he_full(A_lower):
     return F
 
 
-def hemm(alpha, A_lower, B, beta, C, nb: int):
-    """C = alpha A B + beta C, A Hermitian given by its lower triangle; accumulated one block column
-    of A at a time (src/hemmC.cc: Left, Lower)."""
+def hemm(alpha, A_lower, B, beta, C, nb: int, side: str = "L"):
+    """C = alpha A B + beta C (Side::Left) or C = alpha B A + beta C (Side::Right), A Hermitian given by its lower
+    triangle; accumulated one block column (Left) / block row (Right) of A at a time (src/hemmC.cc, src/hemmA.cc;
+    Side::Right is the Left algorithm on conjugate-transposed views, src/hemmC.cc:57-70)."""
     A = he_full(A_lower)
     C = beta * np.array(C, order="F", copy=True)
     for (k0, k1) in _tiles(A.shape[0], nb):
-        C += alpha * (A[:, k0:k1] @ B[k0:k1])
+        if side == "L":
+            C += alpha * (A[:, k0:k1] @ B[k0:k1])
+        else:
+            C += alpha * (B[:, k0:k1] @ A[k0:k1, :])
     return C
 
 
@@ -602,32 +606,45 @@ def sy_full(A_lower):
     return L + np.tril(L, -1).T
 
 
-def symm(alpha, A_lower, B, beta, C, nb: int):
-    """C = alpha A B + beta C, A symmetric given by its lower triangle; one block column of A per step (src/symm.cc:
-    Left, Lower)."""
+def symm(alpha, A_lower, B, beta, C, nb: int, side: str = "L"):
+    """C = alpha A B + beta C (Side::Left) or C = alpha B A + beta C (Side::Right), A symmetric given by its lower
+    triangle; one block column / block row of A per step (src/symm.cc)."""
     A = sy_full(A_lower)
     C = beta * np.array(C, order="F", copy=True)
     for (k0, k1) in _tiles(A.shape[0], nb):
-        C += alpha * (A[:, k0:k1] @ B[k0:k1])
+        if side == "L":
+            C += alpha * (A[:, k0:k1] @ B[k0:k1])
+        else:
+            C += alpha * (B[:, k0:k1] @ A[k0:k1, :])
     return C
 
 
-def trmm(alpha, A_lower, B, nb: int, unit: bool = False):
-    """B <- alpha A B, A lower triangular, Side::Left, NoTrans (src/trmm.cc -> work::trmm, src/work/work_trmm.cc): block
-    row i of the result = alpha (A_ii B_i + sum_{k<i} A_ik B_k) from the ORIGINAL B, computed bottom-up in place."""
+def trmm(alpha, A_lower, B, nb: int, unit: bool = False, side: str = "L", op: str = "N"):
+    """B <- alpha op(A) B (Side::Left) or B <- alpha B op(A) (Side::Right), A lower triangular, op = N / T / C a
+    transposed view of it (src/trmm.cc -> work::trmm, src/work/work_trmm.cc; Side::Right runs the Left algorithm on
+    the (conjugate-)transposed views, :78-98).  Every block row (Left) / block column (Right) of the result is formed
+    from the ORIGINAL B: the diagonal-tile product first, then the off-diagonal tiles in ascending order."""
     A = np.tril(A_lower).astype(np.result_type(A_lower, B), copy=True)
     if unit:
         np.fill_diagonal(A, 1.0)
-    B = np.array(B, order="F", copy=True)
+    M = {"N": A, "T": A.T, "C": A.conj().T}[op]             # lower triangular for N, upper for T / C
+    B0 = np.array(B, order="F", copy=True)
+    out = np.empty_like(B0)
     tiles = _tiles(A.shape[0], nb)
-    for (i0, i1) in reversed(tiles):
-        acc = A[i0:i1, i0:i1] @ B[i0:i1]
-        for (k0, k1) in tiles:
-            if k0 >= i0:
-                break
-            acc += A[i0:i1, k0:k1] @ B[k0:k1]
-        B[i0:i1] = alpha * acc
-    return B
+    for (i0, i1) in tiles:
+        if side == "L":
+            acc = M[i0:i1, i0:i1] @ B0[i0:i1]
+            for (k0, k1) in tiles:
+                if k0 != i0 and np.any(M[i0:i1, k0:k1]):
+                    acc += M[i0:i1, k0:k1] @ B0[k0:k1]
+            out[i0:i1] = alpha * acc
+        else:
+            acc = B0[:, i0:i1] @ M[i0:i1, i0:i1]
+            for (k0, k1) in tiles:
+                if k0 != i0 and np.any(M[k0:k1, i0:i1]):
+                    acc += B0[:, k0:k1] @ M[k0:k1, i0:i1]
+            out[:, i0:i1] = alpha * acc
+    return out
 
 
 def norm_inf(A, hermitian_lower: bool = False):

@@ -28,6 +28,8 @@ generator fixture pins that), only outputs:
   getrf_z.npz, getrf_c.npz  complex LU and pivots (cabs1 rule), n=192 / 200 (ragged) nb=64; gesv_z.npz its solve, n=200 nrhs=70;
                             gesv_mixed_z.npz, posv_mixed_z.npz complex mixed solvers (solution + iteration count), n=256 nb=64;
                             getrf_tntpiv_z.npz (CALU, n=192), getrf_nopiv_z.npz (rand_dominant, n=200)
+  trmm_{z_left_conj,d_left_trans,d_right,z_right_trans,z_right_conj}.npz, hemm_{z,d}_right.npz, symm_z_right.npz
+                            the other side / op variants of trmm / hemm / symm (lower storage), nb=64
   grid_*.npz                the reference ON PROCESS GRIDS (oracle/_ref/ref_dump_mp under oracle/mprun.py): getrf_tntpiv on 2x1 / 3x1 /
                             4x1 / 2x4 ranks (the tournament proper), getrf on 2x2 / 3x2, potrf on 2x2; nb=64
   getrf_tntpiv_d{,_ragged,_tall}.npz   LU with tournament pivoting (MethodLU::CALU), 384x384 / 300x300 / 512x256, nb=128
@@ -146,6 +148,35 @@ def complex_lu_fixtures():
                             iters=meta["iters"], info=meta["info"])
 
 
+BLAS3_VARIANTS = [
+    # name, routine, type, kv of ref_dump: trmm is m x n (n positional), hemm / symm n x n with nrhs rows or columns
+    ("trmm_z_left_conj",   "trmm", "z", dict(n=70,  m=200, op="c")),
+    ("trmm_d_left_trans",  "trmm", "d", dict(n=70,  m=200, op="t", diag="u")),
+    ("trmm_d_right",       "trmm", "d", dict(n=200, m=70)),
+    ("trmm_z_right_trans", "trmm", "z", dict(n=200, m=70, op="t")),
+    ("trmm_z_right_conj",  "trmm", "z", dict(n=200, m=70, op="c", diag="u")),
+    ("hemm_z_right",       "hemm", "z", dict(n=192, nrhs=70, side="r")),
+    ("hemm_d_right",       "hemm", "d", dict(n=200, nrhs=70, side="r")),
+    ("symm_z_right",       "symm", "z", dict(n=192, nrhs=70, side="r")),
+]
+
+
+def blas3_variant_fixtures():
+    """SURVEY section 8(f) item 3, the other side / op variants: slate::trmm with Side::Right and with transposed /
+    conjugate-transposed views of a lower-triangular A, slate::hemm / slate::symm with Side::Right (nb = 64)."""
+    for name, routine, t, kv in BLAS3_VARIANTS:
+        kv = dict(kv)
+        n = kv.pop("n")
+        if routine == "trmm" and name.split("_")[2] == "right":
+            kv["side"] = "r"
+        f, _ = run(routine, t, n, 64, **kv)
+        if routine == "trmm":
+            shape = (kv["m"], n)
+        else:
+            shape = (kv["nrhs"], n)            # Side::Right: B and C are nrhs x n
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), out=f["out"].reshape(shape, order="F"))
+
+
 def main():
     if not os.path.exists(EXE):
         sys.exit("oracle/_ref/ref_dump missing: run oracle/build_ref.sh first")
@@ -198,6 +229,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "syrk_z.npz"), out=f["out"].reshape(200, 200, order="F"))
     f, _ = run("syr2k", "z", 200, 64, k=100)
     np.savez_compressed(os.path.join(OUT, "syr2k_z.npz"), out=f["out"].reshape(200, 200, order="F"))
+    blas3_variant_fixtures()
     # section 8(f) item 2 widening: LU without pivoting
     f, meta = run("getrf_nopiv", "d", 300, 128)
     np.savez_compressed(os.path.join(OUT, "getrf_nopiv_d.npz"), out=f["out"].reshape(300, 300, order="F"), info=meta["info"])
@@ -216,5 +248,7 @@ if __name__ == "__main__":
         complex_lu_fixtures()
     elif len(sys.argv) > 1 and sys.argv[1] == "grid":
         grid_fixtures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "blas3_variants":
+        blas3_variant_fixtures()
     else:
         main()

@@ -127,6 +127,38 @@ def test_trmm_matches_reference(golden_dir):
     assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
 
 
+@pytest.mark.parametrize("name,t,side,op,unit", [
+    ("trmm_z_left_conj", "z", "L", "C", False), ("trmm_d_left_trans", "d", "L", "T", True),
+    ("trmm_d_right", "d", "R", "N", False), ("trmm_z_right_trans", "z", "R", "T", False),
+    ("trmm_z_right_conj", "z", "R", "C", True)])
+def test_trmm_side_op_variants_match_reference(golden_dir, name, t, side, op, unit):
+    """slate::trmm with Side::Right and with (conjugate-)transposed views of a lower-triangular A: the unmodified
+    reference's outputs (tests/golden/make_golden.py blas3_variants)."""
+    g = load(golden_dir, name)
+    dt = np.complex128 if t == "z" else np.float64
+    (m, n), nb = ((200, 70) if side == "L" else (70, 200)), 64
+    na = m if side == "L" else n
+    A = np.tril(o.generate("rand", na, na, 42, dt))
+    B = o.generate("rand", m, n, 43, dt)
+    out = o.trmm(ALPHA if t == "z" else ALPHA.real, A, B, nb, unit=unit, side=side, op=op)
+    assert out.shape == g["out"].shape
+    assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+
+
+@pytest.mark.parametrize("name,routine,t,n", [("hemm_z_right", "hemm", "z", 192), ("hemm_d_right", "hemm", "d", 200),
+                                              ("symm_z_right", "symm", "z", 192)])
+def test_hemm_symm_right_match_reference(golden_dir, name, routine, t, n):
+    g = load(golden_dir, name)
+    dt = np.complex128 if t == "z" else np.float64
+    nb, nrhs = 64, 70
+    A = np.tril(o.generate("rand", n, n, 42, dt))
+    B = o.generate("rand", nrhs, n, 43, dt)
+    C = o.generate("rand", nrhs, n, 44, dt)
+    al, be = (ALPHA, BETA) if t == "z" else (ALPHA.real, BETA.real)
+    out = (o.hemm if routine == "hemm" else o.symm)(al, A, B, be, C, nb, side="R")
+    assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+
+
 def test_symm_matches_reference(golden_dir):
     g = load(golden_dir, "symm_z")
     n, nb, nrhs = 192, 64, 70
