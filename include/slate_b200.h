@@ -456,8 +456,13 @@ int sb200_potrs_##X(sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* o
 int sb200_hemm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* C = alpha A X + beta C, A (complex-)symmetric lower, Side::Left, no conjugation   slate::symm (src/symm.cc); 1 x 1 grid */ \
 int sb200_symm_##X(T alpha, sb200_matrix_t A, sb200_matrix_t X, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
-/* B = alpha A B, A lower triangular (lower tiles of a kind 'H' matrix), side 'L', uplo 'L', op 'N', diag 'N' | 'U' \
- * slate::trmm (src/trmm.cc); other side / uplo / op: SB200_ENOTSUP; 1 x 1 grid */ \
+/* the same with slate::hemm's / slate::symm's Side argument: side 'R' = C = alpha X A + beta C (X and C m x n, A n x n); \
+ * 'L' forwards to the entry points above.  1 x 1 grid */ \
+int sb200_hemm_side_##X(int side, T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
+int sb200_symm_side_##X(int side, T alpha, sb200_matrix_t A, sb200_matrix_t X, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
+/* B = alpha op(A) B (side 'L') or B = alpha B op(A) (side 'R'), A lower triangular (lower tiles of a kind 'H' matrix), \
+ * uplo 'L', op 'N' | 'T' | 'C' (the transposed views slate::trmm takes, src/trmm.cc:61-75), diag 'N' | 'U'; \
+ * uplo 'U': SB200_ENOTSUP; 1 x 1 grid */ \
 int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
 /* norm(Norm::Inf, A), A general or Hermitian   slate::norm (src/norm.cc); 1 x 1 grid */ \
 int sb200_norm_inf_##X(sb200_matrix_t A, double* value);

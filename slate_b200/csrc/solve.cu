@@ -525,6 +525,156 @@ int trmm_left_lower(T alpha, Matrix& A, Matrix& B, bool unit, cudaStream_t s)
     return SB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// trmm, the other side / op variants on lower storage (src/trmm.cc: "the matrices can be transposed or
+// conjugate-transposed beforehand"; src/work/work_trmm.cc serves Side::Right as the Left algorithm on transposed views):
+//     Left,  op = T | C :  B <- alpha op(A) B      op(A) upper triangular: block row i of the result takes the rows k >= i
+//     Right, op = N     :  B <- alpha B A          block column j takes the columns k >= j
+//     Right, op = T | C :  B <- alpha B op(A)      block column j takes the columns k <= j
+// In place and source-oriented like trmm_left_lower: the steps run in the order in which block row / column k of B is
+// still the ORIGINAL one when it is read (ascending k for the first two, descending for the third); step k adds its
+// contribution to every target that is already final but for later additions (one batched launch, distinct targets), then
+// forms alpha * (B_k x diagonal tile) through a one-block workspace.  Same kernels and launch helper as hemm / symm /
+// trmm_left_lower (op on the A-role operand as their `above` batches, op on the B-role operand as the 'N','T' / 'N','C'
+// products of herk / syrk).  1 x 1 grid.
+// STATUS: written after round 2's GPU budget was spent -- oracle pinned to the unmodified reference's golden output on
+// the CPU side (tests/golden/trmm_*), NOT yet run on a GPU (tests/test_zzzzz_gpu_blas3_variants.py).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int trmm_lower_variant(int side, int op, T alpha, Matrix& A, Matrix& B, bool unit, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    const bool left = side == 'L';
+    if (A.kind != 'H' || B.kind != 'G' || (left ? B.m : B.n) != A.n || B.nb != A.nb) return SB200_EINVAL;
+    if (left && op == 'N') return SB200_EINVAL;                           // trmm_left_lower's case
+    if (! IsComplex<T>::value && op == 'C') op = 'T';
+    const int64_t nt = A.nt, nb = A.nb, mtB = B.mt, ntB = B.nt, te = A.tile_elems();
+    if (nt == 0 || mtB == 0 || ntB == 0) return SB200_OK;
+    const int ld = int(nb);
+    const T one = from_real<T>(R(1)), zero = zero_of<T>();
+    const int64_t nw = left ? ntB : mtB;                                  // tiles of one block row / block column of B
+    DevBuf dtri, wblk;
+    SB_TRY(dtri.alloc(size_t(nt) * te * sizeof(T)));
+    SB_TRY(wblk.alloc(size_t(nw) * te * sizeof(T)));
+    CUDA_TRY(cudaMemset(wblk.p, 0, size_t(nw) * te * sizeof(T)));        // whole tiles are copied back: ragged tiles' padding stays defined
+    struct Step { std::vector<Batch> off, diag; };
+    std::vector<Step> steps(static_cast<size_t>(nt));
+    std::vector<const T*> diag_ptrs;
+    PlanBuffer pb;
+    for (int64_t k = 0; k < nt; ++k) {
+        Step& st = steps[size_t(k)];
+        diag_ptrs.push_back(A.tile_as<T>(k, k));
+        if (left) {
+            // B(i, j) += alpha op(A(k, i)) B(k, j) for i < k;   w(j) = alpha op(tril A(k, k)) B(k, j)
+            for (int64_t j = 0; j < ntB; ++j) {
+                for (int64_t i = 0; i < k; ++i)
+                    batch_add(st.off, int(B.tile_mb(i)), int(B.tile_nb(j)), int(B.tile_mb(k)), 0,
+                              A.tile_as<T>(k, i), B.tile_as<T>(k, j), B.tile_as<T>(i, j));
+                batch_add(st.diag, int(B.tile_mb(k)), int(B.tile_nb(j)), int(B.tile_mb(k)), 0,
+                          dtri.as<T>() + k * te, B.tile_as<T>(k, j), wblk.as<T>() + j * te);
+            }
+        }
+        else {
+            // op = N: B(i, j) += alpha B(i, k) A(k, j) for j < k;   op = T | C: B(i, j) += alpha B(i, k) op(A(j, k)) for j > k;
+            // w(i) = alpha B(i, k) op(tril A(k, k))
+            const int64_t j0 = (op == 'N') ? 0 : k + 1, j1 = (op == 'N') ? k : nt;
+            for (int64_t i = 0; i < mtB; ++i) {
+                for (int64_t j = j0; j < j1; ++j)
+                    batch_add(st.off, int(B.tile_mb(i)), int(B.tile_nb(j)), int(B.tile_nb(k)), 0,
+                              B.tile_as<T>(i, k), (op == 'N') ? A.tile_as<T>(k, j) : A.tile_as<T>(j, k), B.tile_as<T>(i, j));
+                batch_add(st.diag, int(B.tile_mb(i)), int(B.tile_nb(k)), int(B.tile_nb(k)), 0,
+                          B.tile_as<T>(i, k), dtri.as<T>() + k * te, wblk.as<T>() + i * te);
+            }
+        }
+        pb.reserve(st.off); pb.reserve(st.diag);
+    }
+    const size_t diag_off = pb.push(diag_ptrs);
+    SB_TRY(pb.upload(s));
+    tr_fill_kernel<T><<<dim3(64, unsigned(nt)), 256, 0, s>>>(pb.at<const T>(diag_off), dtri.as<T>(), ld, te,
+                                                            int(nb), int(A.tile_mb(nt - 1)), int(nt), unit ? 1 : 0);
+    SB_TRY(launch_status());
+    const int opA = left ? op : 'N', opB = left ? 'N' : op;
+    const bool ascending = left || op == 'N';
+    for (int64_t step = 0; step < nt; ++step) {
+        const int64_t k = ascending ? step : nt - 1 - step;
+        const Step& st = steps[size_t(k)];
+        SB_TRY(launch_batches<T>(st.off, pb, opA, opB, alpha, one, ld, 0, s));
+        SB_TRY(launch_batches<T>(st.diag, pb, opA, opB, alpha, zero, ld, 0, s));
+        for (int64_t w = 0; w < nw; ++w)
+            CUDA_TRY(cudaMemcpyAsync(left ? B.tile_as<T>(k, w) : B.tile_as<T>(w, k), wblk.as<T>() + w * te,
+                                     size_t(te) * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// hemm / symm, Side::Right, lower storage: R = alpha X A + beta R with A Hermitian (conj = true) or (complex-)symmetric
+// (src/hemmC.cc:57-70 and src/symm.cc run Side::Right as the Left algorithm on transposed views).  Step k adds block
+// ROW k of the full A times block column k of X: stored tiles A(k, j) left of the diagonal, (conjugate-)transposed
+// stored tiles A(j, k) right of it, the diagonal tile from the filled-in copy -- distinct targets within a step.
+// STATUS: as trmm_lower_variant (oracle pinned to tests/golden/{hemm,symm}_*_right.npz, NOT yet run on a GPU).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int hemm_symm_right_lower(bool conj, T alpha, Matrix& A, Matrix& X, T beta, Matrix& Rm, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.kind != 'H' || X.kind != 'G' || Rm.kind != 'G' || X.n != A.n || Rm.n != A.n || X.m != Rm.m
+        || X.nb != A.nb || Rm.nb != A.nb) return SB200_EINVAL;
+    const int64_t nt = A.nt, nb = A.nb, mtB = X.mt, te = A.tile_elems();
+    if (nt == 0 || mtB == 0) return SB200_OK;
+    const int ld = int(nb);
+    const int opH = (conj && IsComplex<T>::value) ? 'C' : 'T';
+    const T one = from_real<T>(R(1));
+
+    const int64_t count = Rm.ntiles_loc * te;
+    const bool beta_zero = is_zero(beta);
+    if (beta_zero || ! is_zero(sub(beta, one))) {
+        scale_kernel<T><<<ew_grid(count), 256, 0, s>>>(reinterpret_cast<T*>(Rm.pool), beta, beta_zero ? 1 : 0, count);
+        SB_TRY(launch_status());
+    }
+    DevBuf dfull;
+    SB_TRY(dfull.alloc(size_t(nt) * te * sizeof(T)));
+    struct Step { std::vector<Batch> stored, mirrored, diag; };
+    std::vector<Step> steps(static_cast<size_t>(nt));
+    std::vector<const T*> diag_ptrs;
+    PlanBuffer pb;
+    for (int64_t k = 0; k < nt; ++k) {
+        Step& st = steps[size_t(k)];
+        diag_ptrs.push_back(A.tile_as<T>(k, k));
+        for (int64_t i = 0; i < mtB; ++i) {
+            for (int64_t j = 0; j < k; ++j)
+                batch_add(st.stored, int(Rm.tile_mb(i)), int(Rm.tile_nb(j)), int(X.tile_nb(k)), 0,
+                          X.tile_as<T>(i, k), A.tile_as<T>(k, j), Rm.tile_as<T>(i, j));
+            for (int64_t j = k + 1; j < nt; ++j)
+                batch_add(st.mirrored, int(Rm.tile_mb(i)), int(Rm.tile_nb(j)), int(X.tile_nb(k)), 0,
+                          X.tile_as<T>(i, k), A.tile_as<T>(j, k), Rm.tile_as<T>(i, j));
+            batch_add(st.diag, int(Rm.tile_mb(i)), int(Rm.tile_nb(k)), int(X.tile_nb(k)), 0,
+                      X.tile_as<T>(i, k), dfull.as<T>() + k * te, Rm.tile_as<T>(i, k));
+        }
+        pb.reserve(st.stored); pb.reserve(st.mirrored); pb.reserve(st.diag);
+    }
+    const size_t diag_off = pb.push(diag_ptrs);
+    SB_TRY(pb.upload(s));
+    if (conj)
+        he_fill_kernel<T><<<dim3(64, unsigned(nt)), 256, 0, s>>>(pb.at<const T>(diag_off), dfull.as<T>(), ld, te,
+                                                                int(nb), int(A.tile_mb(nt - 1)), int(nt));
+    else
+        sy_fill_kernel<T><<<dim3(64, unsigned(nt)), 256, 0, s>>>(pb.at<const T>(diag_off), dfull.as<T>(), ld, te,
+                                                                int(nb), int(A.tile_mb(nt - 1)), int(nt));
+    SB_TRY(launch_status());
+    for (int64_t k = 0; k < nt; ++k) {
+        const Step& st = steps[size_t(k)];
+        SB_TRY(launch_batches<T>(st.stored, pb, 'N', 'N', alpha, one, ld, 0, s));
+        SB_TRY(launch_batches<T>(st.mirrored, pb, 'N', opH, alpha, one, ld, 0, s));
+        SB_TRY(launch_batches<T>(st.diag, pb, 'N', 'N', alpha, one, ld, 0, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SB200_OK;
+}
+
 // norm(Norm::Inf, A): max absolute row sum; A general or Hermitian (lower tiles)
 template <typename T>
 int norm_inf(Matrix& A, double* out, cudaStream_t s)
@@ -925,10 +1075,31 @@ int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t
     SB_TRY(options_status(opts));\
     if (! A || ! B) return SB200_EINVAL; \
     if (! valid_side(side) || ! valid_uplo(uplo) || ! valid_op(op) || ! valid_diag(diag)) return SB200_EINVAL; \
-    if (side != 'L' || uplo != 'L' || op != 'N') return SB200_ENOTSUP; \
+    if (uplo != 'L') return SB200_ENOTSUP; \
     if (A->A.dtype != TypeChar<CuS<T>::type>::value || B->A.dtype != A->A.dtype) return SB200_EINVAL; \
     CUDA_TRY(cudaDeviceSynchronize()); \
-    return trmm_left_lower<CuS<T>::type>(cvv(alpha), A->A, B->A, diag == 'U', nullptr); \
+    if (side == 'L' && op == 'N') return trmm_left_lower<CuS<T>::type>(cvv(alpha), A->A, B->A, diag == 'U', nullptr); \
+    return trmm_lower_variant<CuS<T>::type>(side, op, cvv(alpha), A->A, B->A, diag == 'U', nullptr); \
+} \
+int sb200_hemm_side_##X(int side, T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    if (! valid_side(side)) return SB200_EINVAL; \
+    if (side == 'L') return sb200_hemm_##X(alpha, A, Xm, beta, C, opts); \
+    SB_TRY(options_status(opts));\
+    if (! A || ! Xm || ! C) return SB200_EINVAL; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || Xm->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return hemm_symm_right_lower<CuS<T>::type>(true, cvv(alpha), A->A, Xm->A, cvv(beta), C->A, nullptr); \
+} \
+int sb200_symm_side_##X(int side, T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    if (! valid_side(side)) return SB200_EINVAL; \
+    if (side == 'L') return sb200_symm_##X(alpha, A, Xm, beta, C, opts); \
+    SB_TRY(options_status(opts));\
+    if (! A || ! Xm || ! C) return SB200_EINVAL; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || Xm->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return hemm_symm_right_lower<CuS<T>::type>(false, cvv(alpha), A->A, Xm->A, cvv(beta), C->A, nullptr); \
 } \
 int sb200_norm_inf_##X(sb200_matrix_t A, double* value) \
 { \

@@ -415,21 +415,35 @@ def syr2k(alpha, A: Matrix, B: Matrix, beta, C: "HermitianMatrix", opts: dict | 
     check(_syr2k[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "syr2k")
 
 
-def hemm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | None = None):
-    """C = alpha A B + beta C with A Hermitian, Side::Left (slate::hemm, src/hemmC.cc)."""
+_hemm_side = {t: _sig(f"sb200_hemm_side_{t}", [c_int, SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+
+
+def hemm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | None = None, side: str = "L"):
+    """C = alpha A B + beta C (side "L") or C = alpha B A + beta C (side "R") with A Hermitian, lower tiles
+    (slate::hemm(side, ...), src/hemmC.cc)."""
     t = _same_type(A, B, C)
     o = _opts(opts)
-    check(_hemm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "hemm")
+    if side == "L":
+        check(_hemm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "hemm")
+    else:
+        check(_hemm_side[t](ord(side), scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "hemm")
 
 
 _symm = {t: _sig(f"sb200_symm_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
 
 
-def symm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | None = None):
-    """C = alpha A B + beta C with A (complex-)symmetric (lower tiles), Side::Left, no conjugation (slate::symm, src/symm.cc)."""
+_symm_side = {t: _sig(f"sb200_symm_side_{t}", [c_int, SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+
+
+def symm(alpha, A: "HermitianMatrix", B: Matrix, beta, C: Matrix, opts: dict | None = None, side: str = "L"):
+    """C = alpha A B + beta C (side "L") or C = alpha B A + beta C (side "R") with A (complex-)symmetric (lower tiles), no
+    conjugation (slate::symm(side, ...), src/symm.cc)."""
     t = _same_type(A, B, C)
     o = _opts(opts)
-    check(_symm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "symm")
+    if side == "L":
+        check(_symm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "symm")
+    else:
+        check(_symm_side[t](ord(side), scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "symm")
 
 
 _trmm = {t: _sig(f"sb200_trmm_{t}", [c_int, c_int, c_int, c_int, SCALAR_T[t], c_ptr, c_ptr, _OP]) for t in "sdcz"}
@@ -437,7 +451,8 @@ _trmm = {t: _sig(f"sb200_trmm_{t}", [c_int, c_int, c_int, c_int, SCALAR_T[t], c_
 
 def trmm(alpha, A: "HermitianMatrix", B: Matrix, side: str = "L", uplo: str = "L", op: str = "N", diag: str = "N",
          opts: dict | None = None):
-    """B = alpha A B with A lower triangular (the lower tiles of A), Side::Left, NoTrans (slate::trmm, src/trmm.cc)."""
+    """B = alpha op(A) B (side "L") or B = alpha B op(A) (side "R") with A lower triangular (the lower tiles of A) and
+    op "N" | "T" | "C" the transposed view slate::trmm would be handed (slate::trmm(side, alpha, A, B), src/trmm.cc)."""
     t = _same_type(A, B)
     o = _opts(opts)
     check(_trmm[t](ord(side), ord(uplo), ord(op), ord(diag), scalar(t, alpha), A._h, B._h, ctypes.byref(o)), "trmm")

@@ -1,0 +1,126 @@
+"""CPU check of the SCHEDULES of the side / op variants of trmm / hemm / symm (slate_b200/csrc/solve.cu:
+trmm_lower_variant, hemm_symm_right_lower): the step order, the batches of a step, the operand roles and the in-place
+update through a one-block workspace are restated here tile by tile in numpy, exactly as the driver issues them, and
+compared with the oracle (which is pinned to the unmodified reference's golden output, tests/test_oracle.py).  What this
+does NOT cover is the C++ transcription and the kernels: that is tests/test_zzzzz_gpu_blas3_variants.py on a GPU."""
+import numpy as np
+import pytest
+
+from oracle import slate_oracle as o
+
+EPS = np.finfo(np.float64).eps
+OP = {"N": lambda x: x, "T": lambda x: x.T, "C": lambda x: x.conj().T}
+
+
+def tiles(n, nb):
+    return [(i, min(i + nb, n)) for i in range(0, n, nb)]
+
+
+def gemm(opa, opb, alpha, a, b, beta, c):
+    """what one entry of a batched launch does: c <- alpha opa(a) opb(b) + beta c, c not aliased with a / b"""
+    return alpha * (OP[opa](a) @ OP[opb](b)) + beta * c
+
+
+def trmm_lower_variant(side, op, alpha, A_lower, B, nb, unit):
+    A = np.array(A_lower)                      # only tiles (i, j) with i >= j are read, as with kind 'H' storage
+    B = np.array(B, order="F", copy=True)
+    left = side == "L"
+    assert not (left and op == "N")
+    ta = tiles(A.shape[0], nb)
+    tr, tc = tiles(B.shape[0], nb), tiles(B.shape[1], nb)
+    nt = len(ta)
+    dtri = []
+    for (k0, k1) in ta:                        # tr_fill_kernel
+        d = np.tril(A[k0:k1, k0:k1]).copy()
+        if unit:
+            np.fill_diagonal(d, 1.0)
+        dtri.append(d)
+    opa, opb = (op, "N") if left else ("N", op)
+    order = range(nt) if (left or op == "N") else range(nt - 1, -1, -1)
+    for k in order:
+        k0, k1 = ta[k]
+        snapshot = B.copy()                    # a batched launch reads its operands while other entries write THEIR targets:
+        if left:                               # sources and targets of one launch must be disjoint -- asserted below
+            targets = [(i, j) for j in range(len(tc)) for i in range(k)]
+            for (i, j) in targets:
+                (i0, i1), (j0, j1) = tr[i], tc[j]
+                assert i != k
+                B[i0:i1, j0:j1] = gemm(opa, opb, alpha, A[k0:k1, i0:i1], snapshot[k0:k1, j0:j1], 1.0, snapshot[i0:i1, j0:j1])
+            w = [gemm(opa, opb, alpha, dtri[k], B[k0:k1, j0:j1], 0.0, 0.0) for (j0, j1) in tc]
+            for (j0, j1), wj in zip(tc, w):
+                B[k0:k1, j0:j1] = wj
+        else:
+            js = range(0, k) if op == "N" else range(k + 1, nt)
+            for i, (i0, i1) in enumerate(tr):
+                for j in js:
+                    j0, j1 = tc[j]
+                    a_tile = A[k0:k1, j0:j1] if op == "N" else A[j0:j1, k0:k1]        # stored: row index >= column index
+                    assert (k >= j) if op == "N" else (j >= k)
+                    B[i0:i1, j0:j1] = gemm(opa, opb, alpha, snapshot[i0:i1, k0:k1], a_tile, 1.0, snapshot[i0:i1, j0:j1])
+            w = [gemm(opa, opb, alpha, B[i0:i1, k0:k1], dtri[k], 0.0, 0.0) for (i0, i1) in tr]
+            for (i0, i1), wi in zip(tr, w):
+                B[i0:i1, k0:k1] = wi
+    return B
+
+
+def hemm_symm_right_lower(conj, alpha, A_lower, X, beta, C, nb):
+    A = np.array(A_lower)
+    C = beta * np.array(C, order="F", copy=True)           # scale_kernel
+    ta = tiles(A.shape[0], nb)
+    tr = tiles(X.shape[0], nb)
+    oph = "C" if conj else "T"
+    dfull = []
+    for (k0, k1) in ta:                                    # he_fill_kernel / sy_fill_kernel
+        d = np.tril(A[k0:k1, k0:k1])
+        if conj:
+            full = d + np.tril(d, -1).conj().T
+            full[np.diag_indices_from(full)] = np.real(np.diag(d))
+        else:
+            full = d + np.tril(d, -1).T
+        dfull.append(full)
+    for k, (k0, k1) in enumerate(ta):
+        for (i0, i1) in tr:
+            for j, (j0, j1) in enumerate(ta):
+                if j < k:
+                    C[i0:i1, j0:j1] = gemm("N", "N", alpha, X[i0:i1, k0:k1], A[k0:k1, j0:j1], 1.0, C[i0:i1, j0:j1])
+                elif j > k:
+                    C[i0:i1, j0:j1] = gemm("N", oph, alpha, X[i0:i1, k0:k1], A[j0:j1, k0:k1], 1.0, C[i0:i1, j0:j1])
+                else:
+                    C[i0:i1, k0:k1] = gemm("N", "N", alpha, X[i0:i1, k0:k1], dfull[k], 1.0, C[i0:i1, k0:k1])
+    return C
+
+
+ALPHA = 3.141592653589793 + 1.414213562373095j
+BETA = 2.718281828459045 + 1.732050807568877j
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+@pytest.mark.parametrize("unit", [False, True])
+@pytest.mark.parametrize("side,op", [("L", "T"), ("L", "C"), ("R", "N"), ("R", "T"), ("R", "C")])
+@pytest.mark.parametrize("m,n,nb", [(200, 70, 64), (70, 200, 64), (128, 128, 64), (50, 300, 128)])
+def test_trmm_variant_schedule_matches_oracle(dt, unit, side, op, m, n, nb):
+    na = m if side == "L" else n
+    A = np.tril(o.generate("rand", na, na, 42, dt))
+    A = A + np.triu(np.full((na, na), np.nan), 1)          # the upper tiles do not exist in lower storage: reading them would show
+    B = o.generate("rand", m, n, 43, dt)
+    al = ALPHA if dt is np.complex128 else ALPHA.real
+    out = trmm_lower_variant(side, op, al, A, B, nb, unit)
+    ref = o.trmm(al, np.tril(np.nan_to_num(A)), B, nb, unit=unit, side=side, op=op)
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() <= 64 * EPS * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+@pytest.mark.parametrize("conj", [True, False])
+@pytest.mark.parametrize("m,n,nb", [(70, 192, 64), (200, 200, 64), (10, 300, 128)])
+def test_hemm_symm_right_schedule_matches_oracle(dt, conj, m, n, nb):
+    A = np.tril(o.generate("rand", n, n, 42, dt))
+    A = A + np.triu(np.full((n, n), np.nan), 1)
+    X = o.generate("rand", m, n, 43, dt)
+    C = o.generate("rand", m, n, 44, dt)
+    al, be = (ALPHA, BETA) if dt is np.complex128 else (ALPHA.real, BETA.real)
+    out = hemm_symm_right_lower(conj, al, A, X, be, C, nb)
+    Al = np.tril(np.nan_to_num(A))
+    ref = (o.hemm if conj else o.symm)(al, Al, X, be, C, nb, side="R")
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() <= 64 * EPS * np.abs(ref).max()

@@ -662,6 +662,6 @@ def test_trmm_left_lower_matches_oracle_and_reference_golden(sl, golden_dir, t, 
 def test_trmm_unsupported_variants_say_so(sl):
     A = sl.HermitianMatrix(64, 32); B = sl.Matrix(64, 8, 32)
     with pytest.raises(sl.SB200Error):
-        sl.trmm(1.0, A, B, side="R")
+        sl.trmm(1.0, A, B, side="R")                       # Side::Right needs A.n == B.n (8 != 64): SB200_EINVAL
     with pytest.raises(sl.SB200Error):
-        sl.trmm(1.0, A, B, op="T")
+        sl.trmm(1.0, A, B, uplo="U")                       # lower storage only: SB200_ENOTSUP

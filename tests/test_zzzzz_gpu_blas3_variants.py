@@ -1,0 +1,136 @@
+"""GPU parity tests of the other side / op variants of trmm / hemm / symm on lower storage (SURVEY section 8(f) item 3;
+slate_b200/csrc/solve.cu: trmm_lower_variant, hemm_symm_right_lower), through the host mirror of the reference API,
+against (1) the golden vectors the UNMODIFIED reference wrote (tests/golden/make_golden.py blas3_variants) and (2) the
+numpy restatement pinned to them (tests/test_oracle.py).
+
+STATUS: written after round 2's GPU budget was spent.  The drivers are host-side compositions of launches that ARE validated
+(the batched tile GEMM with an op on either operand, the diagonal-tile fill kernels, the one-block workspace of
+trmm_left_lower) -- the shipped library's 179 kernels are bitwise the measured ones (scratch/sass_compare.py) -- and
+their schedules are checked on the CPU (tests/test_blas3_variant_schedule.py), but this file has NOT yet run on a B200.
+It sorts last and is marked xfail(strict=False) for that reason alone: the tail of the first GPU run says whether the
+cases XPASS (then the mark goes) without a first-run surprise hiding the 1 600 validated tests before it under `-x`."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import slate_oracle as o
+from tests.gpu_util import NP
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="written after the round's GPU budget ended: first run on a B200 pending")]
+EPS = float(np.finfo(np.float64).eps)
+ALPHA = 3.141592653589793 + 1.414213562373095j
+BETA = 2.718281828459045 + 1.732050807568877j
+
+
+@pytest.fixture(scope="module")
+def sl():
+    import torch
+    torch.cuda.set_device(0)
+    import slate_b200.host as sl_
+    return sl_
+
+
+def _eps(t):
+    return EPS if t in "dz" else float(np.finfo(np.float32).eps)
+
+
+def _wide(t):
+    return np.complex128 if t in "cz" else np.float64
+
+
+@pytest.mark.parametrize("name,t,side,op,diag", [
+    ("trmm_z_left_conj", "z", "L", "C", "N"), ("trmm_d_left_trans", "d", "L", "T", "U"),
+    ("trmm_d_right", "d", "R", "N", "N"), ("trmm_z_right_trans", "z", "R", "T", "N"),
+    ("trmm_z_right_conj", "z", "R", "C", "U")])
+def test_trmm_variants_match_reference_golden(sl, golden_dir, name, t, side, op, diag):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))["out"]
+    (m, n), nb = ((200, 70) if side == "L" else (70, 200)), 64
+    A = sl.HermitianMatrix(m if side == "L" else n, nb, dtype=t).generate("rand", 42)      # its lower tiles are the triangle
+    B = sl.Matrix(m, n, nb, dtype=t).generate("rand", 43)
+    sl.trmm(ALPHA if t == "z" else ALPHA.real, A, B, side=side, op=op, diag=diag)
+    assert np.abs(B.to_host() - g).max() <= 3 * np.sqrt(max(m, n)) * EPS * 4 * np.abs(g).max()
+
+
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("side,op", [("L", "T"), ("L", "C"), ("R", "N"), ("R", "T"), ("R", "C")])
+@pytest.mark.parametrize("diag", ["N", "U"])
+@pytest.mark.parametrize("m,n,nb", [(200, 70, 64), (70, 200, 64), (512, 512, 128), (300, 1000, 256)])
+def test_trmm_variants_match_oracle(sl, t, side, op, diag, m, n, nb):
+    al = ALPHA if t in "cz" else ALPHA.real
+    na = m if side == "L" else n
+    A = sl.HermitianMatrix(na, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(m, n, nb, dtype=t).generate("rand", 43)
+    sl.trmm(al, A, B, side=side, op=op, diag=diag)
+    a = np.tril(o.generate("rand", na, na, 42, NP[t])).astype(_wide(t))
+    b = o.generate("rand", m, n, 43, NP[t]).astype(_wide(t))
+    ref = o.trmm(al, a, b, nb, unit=(diag == "U"), side=side, op=op)
+    assert np.abs(B.to_host() - ref).max() <= 3 * np.sqrt(na) * _eps(t) * 4 * np.abs(ref).max()
+
+
+def test_trmm_left_notrans_still_takes_the_validated_driver(sl):
+    """side L, op N is trmm_left_lower as before (bitwise: the same launches)"""
+    m, n, nb = 200, 70, 64
+    out = []
+    for _ in range(2):
+        A = sl.HermitianMatrix(m, nb).generate("rand", 42)
+        B = sl.Matrix(m, n, nb).generate("rand", 43)
+        sl.trmm(ALPHA.real, A, B, side="L", op="N")
+        out.append(B.to_host())
+    ref = o.trmm(ALPHA.real, np.tril(o.generate("rand", m, m, 42)), o.generate("rand", m, n, 43), nb)
+    assert np.array_equal(out[0], out[1])
+    assert np.abs(out[0] - ref).max() <= 3 * np.sqrt(m) * EPS * 4 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name,routine,t,n", [("hemm_z_right", "hemm", "z", 192), ("hemm_d_right", "hemm", "d", 200),
+                                              ("symm_z_right", "symm", "z", 192)])
+def test_hemm_symm_right_match_reference_golden(sl, golden_dir, name, routine, t, n):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))["out"]
+    nb, m = 64, 70
+    A = sl.HermitianMatrix(n, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(m, n, nb, dtype=t).generate("rand", 43)
+    C = sl.Matrix(m, n, nb, dtype=t).generate("rand", 44)
+    al, be = (ALPHA, BETA) if t == "z" else (ALPHA.real, BETA.real)
+    (sl.hemm if routine == "hemm" else sl.symm)(al, A, B, be, C, side="R")
+    assert np.abs(C.to_host() - g).max() <= 8 * np.sqrt(n) * EPS * np.abs(g).max()
+
+
+@pytest.mark.parametrize("routine", ["hemm", "symm"])
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("m,n,nb,beta", [(70, 192, 64, None), (10, 1000, 128, 1.0), (300, 512, 256, 0.0), (7, 300, 64, -0.5)])
+def test_hemm_symm_right_match_oracle(sl, routine, t, m, n, nb, beta):
+    al = ALPHA if t in "cz" else ALPHA.real
+    be = (BETA if t in "cz" else BETA.real) if beta is None else beta
+    A = sl.HermitianMatrix(n, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(m, n, nb, dtype=t).generate("rand", 43)
+    C = sl.Matrix(m, n, nb, dtype=t).generate("rand", 44)
+    (sl.hemm if routine == "hemm" else sl.symm)(al, A, B, be, C, side="R")
+    a = np.tril(o.generate("rand", n, n, 42, NP[t])).astype(_wide(t))
+    b, c = (o.generate("rand", m, n, seed, NP[t]).astype(_wide(t)) for seed in (43, 44))
+    ref = (o.hemm if routine == "hemm" else o.symm)(al, a, b, be, c, nb, side="R")
+    full = o.he_full(a) if routine == "hemm" else o.sy_full(a)
+    scale = np.abs(b) @ np.abs(full)
+    assert (np.abs(C.to_host() - ref) <= 4 * np.sqrt(n) * _eps(t) * (abs(al) * scale + abs(be) * np.abs(c) + 1.0)).all()
+
+
+def test_side_argument_left_forwards_and_bad_shapes_are_rejected(sl):
+    n, nb, nrhs = 192, 64, 70
+    res = []
+    for side in (None, "L"):
+        A = sl.HermitianMatrix(n, nb, dtype="z").generate("rand", 42)
+        B = sl.Matrix(n, nrhs, nb, dtype="z").generate("rand", 43)
+        C = sl.Matrix(n, nrhs, nb, dtype="z").generate("rand", 44)
+        if side is None:
+            sl.hemm(ALPHA, A, B, BETA, C)
+        else:
+            sl.hemm(ALPHA, A, B, BETA, C, side=side)
+        res.append(C.to_host())
+    assert np.array_equal(res[0], res[1])
+    A = sl.HermitianMatrix(64, 32); B = sl.Matrix(64, 8, 32); C = sl.Matrix(64, 8, 32)
+    with pytest.raises(sl.SB200Error):
+        sl.hemm(1.0, A, B, 0.0, C, side="R")               # Side::Right needs B.n == A.n
+    with pytest.raises(sl.SB200Error):
+        sl.trmm(1.0, A, B, side="R")
+    with pytest.raises(sl.SB200Error):
+        sl.trmm(1.0, A, B, uplo="U")                       # lower storage only
