@@ -464,6 +464,10 @@ int sb200_symm_side_##X(int side, T alpha, sb200_matrix_t A, sb200_matrix_t X, T
  * uplo 'L', op 'N' | 'T' | 'C' (the transposed views slate::trmm takes, src/trmm.cc:61-75), diag 'N' | 'U'; \
  * uplo 'U': SB200_ENOTSUP; 1 x 1 grid */ \
 int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
+/* B = alpha op(A)^{-1} B (side 'L') or B = alpha B op(A)^{-1} (side 'R') at matrix level, A triangular: the lower tiles of a \
+ * kind 'H' matrix (uplo 'L') or the lower / upper triangle of a general square matrix such as an LU factor; op 'N' | 'T' | 'C', \
+ * diag 'N' | 'U'.  slate::trsm / triangular_solve (src/trsm.cc -> work::trsm, src/work/work_trsm.cc:24-387); 1 x 1 grid */ \
+int sb200_trsm_mat_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
 /* norm(Norm::Inf, A), A general or Hermitian   slate::norm (src/norm.cc); 1 x 1 grid */ \
 int sb200_norm_inf_##X(sb200_matrix_t A, double* value);
 SB200_FOR_TYPES(SB200_DECL_RUNTIME)

@@ -252,9 +252,13 @@ int run(const Args& a)
         if (dump) { auto d = to_dense(A); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
     }
     else if (a.routine == "trsm") {
-        // Left/Lower/NoTrans/NonUnit solve  A X = alpha B, A = rand_dominant lower triangle
-        int64_t m = a.geti("m", n);   // A is m x m, B is m x n
-        slate::TriangularMatrix<T> A(slate::Uplo::Lower, slate::Diag::NonUnit, m, nb,
+        // op(A) X = alpha B (side=l, default: A m x m) or X op(A) = alpha B (side=r: A n x n), B m x n; A = rand_dominant
+        // lower triangle, op=n|t|c as a transposed view, diag=n|u  (test/test_trsm.cc; slate::trsm, src/trsm.cc)
+        int64_t m = a.geti("m", n);
+        const bool right = a.get("side", "l") == "r";
+        const bool unit = a.get("diag", "n") == "u";
+        const std::string op = a.get("op", "n");
+        slate::TriangularMatrix<T> A(slate::Uplo::Lower, unit ? slate::Diag::Unit : slate::Diag::NonUnit, right ? n : m, nb,
                                      slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         A.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = "rand_dominant"; p.seed = a.seedA;
@@ -266,10 +270,14 @@ int run(const Args& a)
             write_raw(a.prefix + ".A.bin", d.data(), d.size());
             d = to_dense(B); write_raw(a.prefix + ".B.bin", d.data(), d.size());
         }
+        auto opA = A;
+        if (op == "t") opA = slate::transpose(A);
+        else if (op == "c") opA = slate::conj_transpose(A);
         auto t0 = tic();
-        slate::triangular_solve(alpha, A, B, opts);
+        if (right) slate::trsm(slate::Side::Right, alpha, opA, B, opts);
+        else       slate::triangular_solve(alpha, opA, B, opts);
         seconds = toc(t0);
-        gflop = blas::Gflop<T>::trsm(slate::Side::Left, m, n);
+        gflop = blas::Gflop<T>::trsm(right ? slate::Side::Right : slate::Side::Left, m, n);
         if (dump) { auto d = to_dense(B); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
     }
     else if (a.routine == "gesv_mixed") {

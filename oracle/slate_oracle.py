@@ -342,6 +342,34 @@ def tri_sweep(Tm, B, nb: int, lower: bool, op: str = "N", unit: bool = False):
     return B
 
 
+def tri_sweep_right(Tm, B, nb: int, lower: bool, op: str = "N", unit: bool = False):
+    """B <- B op(T)^{-1}: the block-column sweep slate::trsm runs for Side::Right (src/trsm.cc -> work::trsm on the
+    (conjugate-)transposed views, src/work/work_trsm.cc:78-98): one diagonal-tile solve of block column k + gemm update
+    of the block columns that still wait, backward when op(T) is lower, forward when it is upper."""
+    from scipy.linalg import solve_triangular
+    B = np.array(B, order="F", copy=True)
+    tl = _tiles(Tm.shape[0], nb)
+    trans = op != "N"
+    M = Tm if not trans else (Tm.conj().T if op == "C" else Tm.T)      # op(T) as a math matrix
+    eff_lower = lower != trans
+    order = tl[::-1] if eff_lower else tl
+    for (k0, k1) in order:
+        # X_k M_kk = B_k  <=>  M_kk^T X_k^T = B_k^T
+        B[:, k0:k1] = solve_triangular(M[k0:k1, k0:k1], B[:, k0:k1].T, lower=eff_lower, trans=1, unit_diagonal=unit).T
+        cols = [(j0, j1) for (j0, j1) in tl if (j0 < k0 if eff_lower else j0 > k0)]
+        for (j0, j1) in cols:
+            B[:, j0:j1] -= B[:, k0:k1] @ M[k0:k1, j0:j1]
+    return B
+
+
+def trsm(alpha, T, B, nb: int, side: str = "L", lower: bool = True, op: str = "N", unit: bool = False):
+    """slate::trsm(side, alpha, op(T), B): B <- alpha op(T)^{-1} B (Left) or alpha B op(T)^{-1} (Right), T the lower / upper
+    triangle of the tile matrix (src/trsm.cc; alpha is applied to B before the sweep, src/work/work_trsm.cc:100-130)."""
+    Tm = (np.tril(T) if lower else np.triu(T)).astype(np.result_type(T, B), copy=True)
+    Bs = alpha * np.asarray(B)
+    return (tri_sweep if side == "L" else tri_sweep_right)(Tm, Bs, nb, lower, op, unit)
+
+
 def potrs(L, B, nb: int):
     """Solve A X = B with A = L L^H (lower factor from potrf)."""
     Y = tri_sweep(np.tril(L), B, nb, lower=True, op="N")

@@ -305,6 +305,95 @@ int tri_sweep(Matrix& A, bool lower, int op, bool unit, Matrix& B, cudaStream_t 
     return SB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Block-column sweep  B <- B op(T)^{-1}  (slate::trsm with Side::Right; src/trsm.cc -> work::trsm on the transposed
+// views, src/work/work_trsm.cc:78-98).  Mirror image of tri_sweep: step k solves block column k of B against the
+// diagonal tile (trsm_colmajor, right side: the launches behind sb200_trsm_batched_* and the Cholesky panel solve),
+// then ONE batched GEMM takes X(:, k) op(T)(k, j) off the block columns j that still wait -- backward when op(T) is
+// lower, forward when it is upper.
+// STATUS: written after round 2's GPU budget was spent; oracle pinned to the unmodified reference (tests/golden/trsm_*_right*),
+// schedule checked on the CPU (tests/test_blas3_variant_schedule.py), NOT yet run on a GPU.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int tri_sweep_right(Matrix& A, bool lower, int op, bool unit, Matrix& B, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1 || B.g != A.g) return SB200_ENOTSUP;
+    if (A.m != A.n || B.n != A.n || A.nb != B.nb || B.kind != 'G') return SB200_EINVAL;
+    if (A.dtype != TypeChar<T>::value || B.dtype != A.dtype) return SB200_EINVAL;
+    if (A.kind == 'H' && ! lower) return SB200_EINVAL;     // only the lower tiles of a Hermitian matrix exist
+    if (! IsComplex<T>::value && op == 'C') op = 'T';
+    const int64_t kt = A.nt, nb = A.nb, mtB = B.mt;
+    if (kt == 0 || mtB == 0) return SB200_OK;
+    const int ld = int(nb);
+    const bool trans = (op != 'N');
+    const bool eff_lower = (lower != trans);               // op(T) as a math matrix
+    const bool forward = ! eff_lower;                      // X M = B with M upper: forward over the block columns
+
+    struct Step { size_t full_off = 0, last_off = 0; int nfull = 0, nlast = 0; std::vector<Batch> upd; };
+    std::vector<Step> steps(static_cast<size_t>(kt));
+    PlanBuffer pb;
+    for (int64_t sidx = 0; sidx < kt; ++sidx) {
+        const int64_t k = forward ? sidx : kt - 1 - sidx;
+        Step& st = steps[size_t(sidx)];
+        std::vector<T*> full, last;
+        for (int64_t i = 0; i < mtB; ++i)
+            (B.tile_mb(i) == nb ? full : last).push_back(B.tile_as<T>(i, k));
+        const int64_t j0 = forward ? k + 1 : 0, j1 = forward ? kt : k;
+        for (int64_t j = j0; j < j1; ++j)
+            for (int64_t i = 0; i < mtB; ++i) {
+                const T* Mkj = trans ? A.tile_as<T>(j, k) : A.tile_as<T>(k, j);      // op(T)(k, j) = op(T(j, k))
+                batch_add(st.upd, int(B.tile_mb(i)), int(B.tile_nb(j)), int(B.tile_nb(k)), 0, B.tile_as<T>(i, k), Mkj,
+                          B.tile_as<T>(i, j));
+            }
+        st.nfull = int(full.size()); st.nlast = int(last.size());
+        st.full_off = pb.push(full); st.last_off = pb.push(last);
+        pb.reserve(st.upd);
+    }
+    const int nblk = int(ceil_div(nb, FACTOR_IB));
+    DevBuf W;
+    SB_TRY(W.alloc(size_t(nblk) * FACTOR_IB * FACTOR_IB * sizeof(T)));
+    SB_TRY(pb.upload(s));
+    const T one = from_real<T>(R(1)), minus_one = from_real<T>(R(-1));
+    for (int64_t sidx = 0; sidx < kt; ++sidx) {
+        const int64_t k = forward ? sidx : kt - 1 - sidx;
+        const Step& st = steps[size_t(sidx)];
+        const int nk = int(B.tile_nb(k));
+        for (int part = 0; part < 2; ++part) {
+            const int cnt = part == 0 ? st.nfull : st.nlast;
+            if (cnt == 0) continue;
+            const int rows = part == 0 ? int(nb) : int(B.tile_mb(mtB - 1));
+            T* const* ptrs = pb.at<T>(part == 0 ? st.full_off : st.last_off);
+            SB_TRY(trsm_colmajor<T>(false, lower, op, unit, rows, nk, one, A.tile_as<T>(k, k), ld, ptrs, 0, ld, cnt,
+                                    W.as<T>(), s));
+        }
+        SB_TRY(launch_batches<T>(st.upd, pb, 'N', trans ? op : 'N', minus_one, one, ld, 0, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));       // the plan and W die with this frame
+    return SB200_OK;
+}
+
+// slate::trsm(side, alpha, op(A), B) at matrix level (src/trsm.cc): B <- alpha op(T)^{-1} B or alpha B op(T)^{-1}, T the
+// lower triangle of a kind 'H' matrix or the lower / upper triangle of a general one (an LU factor).  alpha is applied to
+// B first (src/work/work_trsm.cc:100-130 scales the block row it solves; the same product up to rounding), then the sweep.
+template <typename T>
+int trsm_mat(int side, bool lower, int op, bool unit, T alpha, Matrix& A, Matrix& B, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.m != A.n || (side == 'L' ? B.m : B.n) != A.n || A.nb != B.nb || B.kind != 'G') return SB200_EINVAL;
+    if (A.kind == 'H' && ! lower) return SB200_ENOTSUP;
+    if (! IsComplex<T>::value && op == 'C') op = 'T';
+    const int64_t count = B.ntiles_loc * B.tile_elems();
+    const bool alpha_zero = is_zero(alpha);
+    if (count > 0 && (alpha_zero || ! is_zero(sub(alpha, from_real<T>(R(1)))))) {
+        scale_kernel<T><<<ew_grid(count), 256, 0, s>>>(reinterpret_cast<T*>(B.pool), alpha, alpha_zero ? 1 : 0, count);
+        SB_TRY(launch_status());
+    }
+    if (alpha_zero) { CUDA_TRY(cudaStreamSynchronize(s)); return SB200_OK; }
+    return side == 'L' ? tri_sweep<T>(A, lower, op, unit, B, s) : tri_sweep_right<T>(A, lower, op, unit, B, s);
+}
+
 template <typename T>
 int potrs_t(Matrix& A, Matrix& B, cudaStream_t s)
 {
@@ -1080,6 +1169,15 @@ int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t
     CUDA_TRY(cudaDeviceSynchronize()); \
     if (side == 'L' && op == 'N') return trmm_left_lower<CuS<T>::type>(cvv(alpha), A->A, B->A, diag == 'U', nullptr); \
     return trmm_lower_variant<CuS<T>::type>(side, op, cvv(alpha), A->A, B->A, diag == 'U', nullptr); \
+} \
+int sb200_trsm_mat_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts) \
+{ \
+    SB_TRY(options_status(opts));\
+    if (! A || ! B) return SB200_EINVAL; \
+    if (! valid_side(side) || ! valid_uplo(uplo) || ! valid_op(op) || ! valid_diag(diag)) return SB200_EINVAL; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || B->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return trsm_mat<CuS<T>::type>(side, uplo == 'L', op, diag == 'U', cvv(alpha), A->A, B->A, nullptr); \
 } \
 int sb200_hemm_side_##X(int side, T alpha, sb200_matrix_t A, sb200_matrix_t Xm, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
 { \

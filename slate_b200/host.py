@@ -458,6 +458,9 @@ def trmm(alpha, A: "HermitianMatrix", B: Matrix, side: str = "L", uplo: str = "L
     check(_trmm[t](ord(side), ord(uplo), ord(op), ord(diag), scalar(t, alpha), A._h, B._h, ctypes.byref(o)), "trmm")
 
 
+triangular_multiply = trmm
+
+
 def norm_inf(A: Matrix) -> float:
     """slate::norm(Norm::Inf, A) for a general or Hermitian matrix."""
     v = c_dbl(0.0)
@@ -600,6 +603,43 @@ def getrs(A: Matrix, pivots, B: Matrix, opts: dict | None = None):
 
 
 lu_solve_using_factor = getrs
+
+
+def posv(A: HermitianMatrix, B: Matrix, opts: dict | None = None) -> int:
+    """Solve A X = B, A Hermitian positive definite: potrf, then potrs if the factorisation succeeded; A holds the
+    factor, B the solution (slate::posv / chol_solve, src/posv.cc:80-94).  Returns info."""
+    info = potrf(A, opts)
+    if info == 0:
+        potrs(A, B, opts)
+    return info
+
+
+def gesv(A: Matrix, B: Matrix, opts: dict | None = None):
+    """Solve A X = B: getrf, then getrs if no pivot was exactly zero; A holds L and U, B the solution
+    (slate::gesv / lu_solve, src/gesv.cc:95-109).  Returns (pivots, info)."""
+    pivots, info = getrf(A, opts)
+    if info == 0:
+        getrs(A, pivots, B, opts)
+    return pivots, info
+
+
+chol_solve = posv
+lu_solve = gesv
+
+_trsm_mat = {t: _sig(f"sb200_trsm_mat_{t}", [c_int, c_int, c_int, c_int, SCALAR_T[t], c_ptr, c_ptr, _OP]) for t in "sdcz"}
+
+
+def trsm(alpha, A: Matrix, B: Matrix, side: str = "L", uplo: str = "L", op: str = "N", diag: str = "N",
+         opts: dict | None = None):
+    """B = alpha op(A)^-1 B (side "L") or B = alpha B op(A)^-1 (side "R") with A triangular: the lower tiles of a
+    HermitianMatrix handle, or the lower / upper triangle of a square Matrix (an LU factor); op "N" | "T" | "C" is the
+    transposed view slate::trsm would be handed (slate::trsm(side, alpha, A, B) / triangular_solve, src/trsm.cc)."""
+    t = _same_type(A, B)
+    o = _opts(opts)
+    check(_trsm_mat[t](ord(side), ord(uplo), ord(op), ord(diag), scalar(t, alpha), A._h, B._h, ctypes.byref(o)), "trsm")
+
+
+triangular_solve = trsm
 
 MIXED_TIMERS = ("total", "factor_lo", "solve_lo", "residual_hi", "add_hi", "factor_hi", "solve_hi", "norm_convert")
 

@@ -28,7 +28,7 @@ generator fixture pins that), only outputs:
   getrf_z.npz, getrf_c.npz  complex LU and pivots (cabs1 rule), n=192 / 200 (ragged) nb=64; gesv_z.npz its solve, n=200 nrhs=70;
                             gesv_mixed_z.npz, posv_mixed_z.npz complex mixed solvers (solution + iteration count), n=256 nb=64;
                             getrf_tntpiv_z.npz (CALU, n=192), getrf_nopiv_z.npz (rand_dominant, n=200)
-  trmm_{z_left_conj,d_left_trans,d_right,z_right_trans,z_right_conj}.npz, hemm_{z,d}_right.npz, symm_z_right.npz
+  {trmm,trsm}_{z_left_conj,d_left_trans,d_right,z_right_trans,z_right_conj}.npz, hemm_{z,d}_right.npz, symm_z_right.npz
                             the other side / op variants of trmm / hemm / symm (lower storage), nb=64
   grid_*.npz                the reference ON PROCESS GRIDS (oracle/_ref/ref_dump_mp under oracle/mprun.py): getrf_tntpiv on 2x1 / 3x1 /
                             4x1 / 2x4 ranks (the tournament proper), getrf on 2x2 / 3x2, potrf on 2x2; nb=64
@@ -155,6 +155,11 @@ BLAS3_VARIANTS = [
     ("trmm_d_right",       "trmm", "d", dict(n=200, m=70)),
     ("trmm_z_right_trans", "trmm", "z", dict(n=200, m=70, op="t")),
     ("trmm_z_right_conj",  "trmm", "z", dict(n=200, m=70, op="c", diag="u")),
+    ("trsm_z_left_conj",   "trsm", "z", dict(n=70,  m=200, op="c")),
+    ("trsm_d_left_trans",  "trsm", "d", dict(n=70,  m=200, op="t", diag="u")),
+    ("trsm_d_right",       "trsm", "d", dict(n=200, m=70)),
+    ("trsm_z_right_trans", "trsm", "z", dict(n=200, m=70, op="t", diag="u")),
+    ("trsm_z_right_conj",  "trsm", "z", dict(n=200, m=70, op="c")),
     ("hemm_z_right",       "hemm", "z", dict(n=192, nrhs=70, side="r")),
     ("hemm_d_right",       "hemm", "d", dict(n=200, nrhs=70, side="r")),
     ("symm_z_right",       "symm", "z", dict(n=192, nrhs=70, side="r")),
@@ -162,15 +167,16 @@ BLAS3_VARIANTS = [
 
 
 def blas3_variant_fixtures():
-    """SURVEY section 8(f) item 3, the other side / op variants: slate::trmm with Side::Right and with transposed /
-    conjugate-transposed views of a lower-triangular A, slate::hemm / slate::symm with Side::Right (nb = 64)."""
+    """SURVEY section 8(f) items 1 and 3, the other side / op variants: slate::trmm and slate::trsm with Side::Right and with
+    transposed / conjugate-transposed views of a lower-triangular A (trsm: rand_dominant), slate::hemm / slate::symm with
+    Side::Right (nb = 64)."""
     for name, routine, t, kv in BLAS3_VARIANTS:
         kv = dict(kv)
         n = kv.pop("n")
-        if routine == "trmm" and name.split("_")[2] == "right":
+        if routine in ("trmm", "trsm") and name.split("_")[2] == "right":
             kv["side"] = "r"
         f, _ = run(routine, t, n, 64, **kv)
-        if routine == "trmm":
+        if routine in ("trmm", "trsm"):
             shape = (kv["m"], n)
         else:
             shape = (kv["nrhs"], n)            # Side::Right: B and C are nrhs x n

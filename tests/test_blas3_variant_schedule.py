@@ -1,5 +1,5 @@
-"""CPU check of the SCHEDULES of the side / op variants of trmm / hemm / symm (slate_b200/csrc/solve.cu:
-trmm_lower_variant, hemm_symm_right_lower): the step order, the batches of a step, the operand roles and the in-place
+"""CPU check of the SCHEDULES of the side / op variants of trmm / hemm / symm / trsm (slate_b200/csrc/solve.cu:
+trmm_lower_variant, hemm_symm_right_lower, tri_sweep_right): the step order, the batches of a step, the operand roles and the in-place
 update through a one-block workspace are restated here tile by tile in numpy, exactly as the driver issues them, and
 compared with the oracle (which is pinned to the unmodified reference's golden output, tests/test_oracle.py).  What this
 does NOT cover is the C++ transcription and the kernels: that is tests/test_zzzzz_gpu_blas3_variants.py on a GPU."""
@@ -88,6 +88,54 @@ def hemm_symm_right_lower(conj, alpha, A_lower, X, beta, C, nb):
                 else:
                     C[i0:i1, k0:k1] = gemm("N", "N", alpha, X[i0:i1, k0:k1], dfull[k], 1.0, C[i0:i1, k0:k1])
     return C
+
+
+def tri_sweep_right(A_tri, lower, op, unit, B, nb):
+    """solve.cu: tri_sweep_right -- per step one right-side diagonal-tile solve of block column k (trsm_colmajor, whose
+    result the oracle's trsm_tile states) and one batched update of the block columns that still wait"""
+    A = np.array(A_tri)
+    B = np.array(B, order="F", copy=True)
+    ta = tiles(A.shape[0], nb)
+    tr = tiles(B.shape[0], nb)
+    kt = len(ta)
+    trans = op != "N"
+    forward = not (lower != trans)
+    for sidx in range(kt):
+        k = sidx if forward else kt - 1 - sidx
+        k0, k1 = ta[k]
+        for (i0, i1) in tr:
+            B[i0:i1, k0:k1] = o.trsm_tile("R", "L" if lower else "U", op, "U" if unit else "N", 1.0, A[k0:k1, k0:k1], B[i0:i1, k0:k1])
+        js = range(k + 1, kt) if forward else range(0, k)
+        snapshot = B.copy()
+        for j in js:
+            j0, j1 = ta[j]
+            m_tile = A[j0:j1, k0:k1] if trans else A[k0:k1, j0:j1]
+            assert np.isfinite(m_tile).all(), "the update read a tile outside the stored triangle"
+            for (i0, i1) in tr:
+                B[i0:i1, j0:j1] = gemm("N", op if trans else "N", -1.0, snapshot[i0:i1, k0:k1], m_tile, 1.0, snapshot[i0:i1, j0:j1])
+    return B
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+@pytest.mark.parametrize("lower,op", [(True, "N"), (True, "T"), (True, "C"), (False, "N"), (False, "T"), (False, "C")])
+@pytest.mark.parametrize("unit", [False, True])
+@pytest.mark.parametrize("m,n,nb", [(70, 200, 64), (128, 128, 64), (300, 50, 128), (10, 260, 128)])
+def test_trsm_right_sweep_schedule_matches_oracle(dt, lower, op, unit, m, n, nb):
+    G = o.generate("rand_dominant", n, n, 42, dt)
+    tri = np.tril(G) if lower else np.triu(G)
+    outside = np.triu(np.full((n, n), np.nan), 1) if lower else np.tril(np.full((n, n), np.nan), -1)
+    # tiles wholly outside the triangle do not exist (lower storage) or are never to be read: poison them; the diagonal
+    # tiles keep zeros outside the triangle as trsm_colmajor only reads their triangle
+    poisoned = tri + outside
+    for (k0, k1) in tiles(n, nb):
+        poisoned[k0:k1, k0:k1] = tri[k0:k1, k0:k1]
+    B = o.generate("rand", m, n, 43, dt)
+    out = tri_sweep_right(poisoned, lower, op, unit, B, nb)
+    ref = o.trsm(1.0, tri, B, nb, side="R", lower=lower, op=op, unit=unit)
+    direct = o.trsm_tile("R", "L" if lower else "U", op, "U" if unit else "N", 1.0, tri, B)
+    assert np.isfinite(out).all()
+    scale = max(np.abs(ref).max(), 1.0)
+    assert np.abs(out - ref).max() <= 1e-11 * scale and np.abs(direct - ref).max() <= 1e-11 * scale
 
 
 ALPHA = 3.141592653589793 + 1.414213562373095j

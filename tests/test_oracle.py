@@ -145,6 +145,24 @@ def test_trmm_side_op_variants_match_reference(golden_dir, name, t, side, op, un
     assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
 
 
+@pytest.mark.parametrize("name,t,side,op,unit", [
+    ("trsm_z_left_conj", "z", "L", "C", False), ("trsm_d_left_trans", "d", "L", "T", True),
+    ("trsm_d_right", "d", "R", "N", False), ("trsm_z_right_trans", "z", "R", "T", True),
+    ("trsm_z_right_conj", "z", "R", "C", False)])
+def test_trsm_side_op_variants_match_reference(golden_dir, name, t, side, op, unit):
+    """slate::trsm with Side::Right and with (conjugate-)transposed views of a lower-triangular A (rand_dominant)."""
+    g = load(golden_dir, name)
+    dt = np.complex128 if t == "z" else np.float64
+    (m, n), nb = ((200, 70) if side == "L" else (70, 200)), 64
+    na = m if side == "L" else n
+    A = np.tril(o.generate("rand_dominant", na, na, 42, dt))
+    B = o.generate("rand", m, n, 43, dt)
+    out = o.trsm(ALPHA if t == "z" else ALPHA.real, A, B, nb, side=side, lower=True, op=op, unit=unit)
+    assert out.shape == g["out"].shape
+    # a unit-diagonal solve with a rand lower triangle grows: compare relative to the largest entry
+    assert np.abs(out - g["out"]).max() <= 1e-12 * np.abs(g["out"]).max()
+
+
 @pytest.mark.parametrize("name,routine,t,n", [("hemm_z_right", "hemm", "z", 192), ("hemm_d_right", "hemm", "d", 200),
                                               ("symm_z_right", "symm", "z", 192)])
 def test_hemm_symm_right_match_reference(golden_dir, name, routine, t, n):

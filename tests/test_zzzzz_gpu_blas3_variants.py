@@ -134,3 +134,92 @@ def test_side_argument_left_forwards_and_bad_shapes_are_rejected(sl):
         sl.trmm(1.0, A, B, side="R")
     with pytest.raises(sl.SB200Error):
         sl.trmm(1.0, A, B, uplo="U")                       # lower storage only
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# slate::trsm at matrix level (sb200_trsm_mat_*): Side::Left through the sweep potrs / getrs run (tri_sweep), Side::Right
+# through tri_sweep_right; posv / gesv (slate::posv, slate::gesv: factor, then solve when info == 0)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,t,side,op,diag", [
+    ("trsm_d", "d", "L", "N", "N"),                       # the round-1 golden: slate::triangular_solve, m = 256, n = 128
+    ("trsm_z_left_conj", "z", "L", "C", "N"), ("trsm_d_left_trans", "d", "L", "T", "U"),
+    ("trsm_d_right", "d", "R", "N", "N"), ("trsm_z_right_trans", "z", "R", "T", "U"),
+    ("trsm_z_right_conj", "z", "R", "C", "N")])
+def test_trsm_matrix_level_matches_reference_golden(sl, golden_dir, name, t, side, op, diag):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))["out"]
+    (m, n), nb = ((256, 128) if name == "trsm_d" else (200, 70) if side == "L" else (70, 200)), 64
+    A = sl.HermitianMatrix(m if side == "L" else n, nb, dtype=t).generate("rand_dominant", 42)
+    B = sl.Matrix(m, n, nb, dtype=t).generate("rand", 43)
+    sl.trsm(ALPHA if t == "z" else ALPHA.real, A, B, side=side, op=op, diag=diag)
+    # unit-diagonal solves with this triangle grow (|X| up to 7e9): the bound is relative to the largest entry
+    assert np.abs(B.to_host() - g).max() <= 1e-10 * np.abs(g).max()
+
+
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("side", ["L", "R"])
+@pytest.mark.parametrize("op", ["N", "T", "C"])
+@pytest.mark.parametrize("m,n,nb", [(200, 70, 64), (70, 200, 64), (512, 512, 128), (300, 1000, 256)])
+def test_trsm_matrix_level_lower_vs_oracle(sl, t, side, op, m, n, nb):
+    al = ALPHA if t in "cz" else ALPHA.real
+    na = m if side == "L" else n
+    A = sl.HermitianMatrix(na, nb, dtype=t).generate("rand_dominant", 42)
+    B = sl.Matrix(m, n, nb, dtype=t).generate("rand", 43)
+    sl.trsm(al, A, B, side=side, op=op)
+    a = np.tril(o.generate("rand_dominant", na, na, 42, NP[t])).astype(_wide(t))
+    b = o.generate("rand", m, n, 43, NP[t]).astype(_wide(t))
+    ref = o.trsm(al, a, b, nb, side=side, lower=True, op=op)
+    assert np.abs(B.to_host() - ref).max() <= 200 * _eps(t) * np.abs(ref).max()        # the bound of the tile-level trsm tests
+
+
+@pytest.mark.parametrize("side,uplo,op,diag", [("L", "U", "N", "N"), ("L", "U", "C", "N"), ("R", "U", "N", "N"), ("R", "U", "T", "N"),
+                                               ("L", "L", "N", "U"), ("R", "L", "N", "U"), ("R", "L", "C", "U")])
+@pytest.mark.parametrize("t", ["d", "z"])
+def test_trsm_matrix_level_on_an_lu_factor(sl, t, side, uplo, op, diag):
+    """A general square matrix as the triangle holder (what getrs does with L and U): upper triangle, and the unit lower
+    one.  Checked through the backward error || op(T) X - alpha B ||_1 / (|| T ||_1 || X ||_1) (Left; Right likewise) --
+    the reference tester's residual (test/test_trsm.cc:160-184: <= 3 eps) normalised by || X || instead of N so that it
+    stays meaningful for the unit-diagonal solves, which grow to 1e7 ... 1e14 on this triangle; the oracle's own sweep
+    reaches 1.9 eps, the bound here is 16 eps -- and against the oracle where the solve does not grow."""
+    n, nb, nrhs = 300, 64, 70
+    A = sl.Matrix(n, n, nb, dtype=t).generate("rand_dominant", 42)
+    shape = (n, nrhs) if side == "L" else (nrhs, n)
+    B = sl.Matrix(*shape, nb, dtype=t).generate("rand", 43)
+    al = ALPHA if t == "z" else ALPHA.real
+    sl.trsm(al, A, B, side=side, uplo=uplo, op=op, diag=diag)
+    X = B.to_host()
+    a = o.generate("rand_dominant", n, n, 42, NP[t])
+    tri = np.tril(a) if uplo == "L" else np.triu(a)
+    if diag == "U":
+        np.fill_diagonal(tri, 1.0)
+    M = {"N": tri, "T": tri.T, "C": tri.conj().T}[op]
+    b = o.generate("rand", *shape, 43, NP[t])
+    R = (M @ X - al * b) if side == "L" else (X @ M - al * b)
+    resid = np.abs(R).sum(axis=0).max() / (np.abs(M).sum(axis=0).max() * np.abs(X).sum(axis=0).max())
+    assert resid <= 16 * EPS
+    if diag == "N":
+        ref = o.trsm(al, a, b, nb, side=side, lower=(uplo == "L"), op=op)
+        assert np.abs(X - ref).max() <= 200 * EPS * np.abs(ref).max()
+
+
+def test_posv_and_gesv_are_factor_then_solve(sl, golden_dir):
+    """slate::posv / slate::gesv (src/posv.cc:80-94, src/gesv.cc:95-109) against the reference's golden solutions; a
+    matrix that is not positive definite returns its info and leaves B alone."""
+    g = np.load(os.path.join(golden_dir, "posv_d.npz"))
+    n, nb = 300, 128
+    A = sl.HermitianMatrix(n, nb).generate("rand_dominant", 42)
+    B = sl.Matrix(n, 10, nb).generate("rand", 43)
+    assert sl.posv(A, B) == 0 == int(g["info"])
+    assert np.abs(B.to_host() - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+    g = np.load(os.path.join(golden_dir, "gesv_d.npz"))
+    A = sl.Matrix(n, n, nb).generate("rand", 42)
+    B = sl.Matrix(n, 10, nb).generate("rand", 43)
+    piv, info = sl.lu_solve(A, B)
+    assert info == 0 == int(g["info"]) and len(piv) == 3
+    assert np.abs(B.to_host() - g["out"]).max() <= 1e-10 * np.abs(g["out"]).max()
+    H = sl.HermitianMatrix(n, nb).generate("rand", 42)                 # rand is not positive definite
+    B = sl.Matrix(n, 10, nb).generate("rand", 43)
+    b0 = B.to_host()
+    info = sl.chol_solve(H, B)
+    _, iref = o.potrf(o.he_full(np.tril(o.generate("rand", n, n, 42))), nb)
+    assert info == iref > 0
+    assert np.array_equal(B.to_host(), b0)
