@@ -464,6 +464,9 @@ int sb200_symm_side_##X(int side, T alpha, sb200_matrix_t A, sb200_matrix_t X, T
  * uplo 'L', op 'N' | 'T' | 'C' (the transposed views slate::trmm takes, src/trmm.cc:61-75), diag 'N' | 'U'; \
  * uplo 'U': SB200_ENOTSUP; 1 x 1 grid */ \
 int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
+/* C = alpha op(A) op(B) + beta C with the (conjugate-)transposed views slate::gemm is handed (opA / opB 'N' | 'T' | 'C'; \
+ * A is stored k x m when opA != 'N', B n x k when opB != 'N').  'N','N' forwards to sb200_gemm_X; other pairs: 1 x 1 grid */ \
+int sb200_gemm_op_##X(int opA, int opB, T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* B = alpha op(A)^{-1} B (side 'L') or B = alpha B op(A)^{-1} (side 'R') at matrix level, A triangular: the lower tiles of a \
  * kind 'H' matrix (uplo 'L') or the lower / upper triangle of a general square matrix such as an LU factor; op 'N' | 'T' | 'C', \
  * diag 'N' | 'U'.  slate::trsm / triangular_solve (src/trsm.cc -> work::trsm, src/work/work_trsm.cc:24-387); 1 x 1 grid */ \

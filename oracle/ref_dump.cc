@@ -158,17 +158,23 @@ int run(const Args& a)
         write_raw(a.prefix + ".A.bin", d.data(), d.size());
     }
     else if (a.routine == "gemm") {
+        // C = alpha op(A) op(B) + beta C; opa / opb = n|t|c: A is stored k x m / B n x k and handed over as a (conjugate-)
+        // transposed view (test/test_gemm.cc:96-135)
         int64_t m = a.geti("m", n), k = a.geti("k", n);
-        auto A = make_matrix<T>(m, k, nb, a.seedA, "rand");
-        auto B = make_matrix<T>(k, n, nb, a.seedB, "rand");
+        const std::string opa = a.get("opa", "n"), opb = a.get("opb", "n");
+        auto A = opa == "n" ? make_matrix<T>(m, k, nb, a.seedA, "rand") : make_matrix<T>(k, m, nb, a.seedA, "rand");
+        auto B = opb == "n" ? make_matrix<T>(k, n, nb, a.seedB, "rand") : make_matrix<T>(n, k, nb, a.seedB, "rand");
         auto C = make_matrix<T>(m, n, nb, a.seedC, "rand");
         if (dump) {
             auto d = to_dense(A); write_raw(a.prefix + ".A.bin", d.data(), d.size());
             d = to_dense(B);      write_raw(a.prefix + ".B.bin", d.data(), d.size());
             d = to_dense(C);      write_raw(a.prefix + ".C.bin", d.data(), d.size());
         }
+        auto opA = A, opB = B;
+        if (opa == "t") opA = slate::transpose(A); else if (opa == "c") opA = slate::conj_transpose(A);
+        if (opb == "t") opB = slate::transpose(B); else if (opb == "c") opB = slate::conj_transpose(B);
         auto t0 = tic();
-        slate::multiply(alpha, A, B, beta, C, opts);
+        slate::multiply(alpha, opA, opB, beta, C, opts);
         seconds = toc(t0);
         gflop = blas::Gflop<T>::gemm(m, n, k);
         if (dump) { auto d = to_dense(C); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }

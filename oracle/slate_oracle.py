@@ -119,7 +119,11 @@ def cabs1(x):
 # with the k = 0 block, then one rank-nb update per block column k of A.
 # tile op: include/slate/Tile_blas.hh:29-98 -> blas::gemm
 # ----------------------------------------------------------------------------
-def gemm(alpha, A, B, beta, C, nb: int):
+def gemm(alpha, A, B, beta, C, nb: int, opa: str = "N", opb: str = "N"):
+    """C = alpha op(A) op(B) + beta C, one block column of op(A) per step (src/gemmC.cc:124-182); op = N / T / C are the
+    (conjugate-)transposed views slate::gemm is handed (A stored k x m, B stored n x k)."""
+    view = {"N": lambda x: x, "T": lambda x: x.T, "C": lambda x: x.conj().T}
+    A, B = view[opa](np.asarray(A)), view[opb](np.asarray(B))
     C = np.array(C, order="F", copy=True)
     kt = _tiles(A.shape[1], nb)
     for idx, (k0, k1) in enumerate(kt):

@@ -615,6 +615,47 @@ int trmm_left_lower(T alpha, Matrix& A, Matrix& B, bool unit, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------
+// gemm with (conjugate-)transposed views: C = alpha op(A) op(B) + beta C, A stored k x m when opA != 'N', B stored n x k
+// when opB != 'N' (slate::gemm is handed transposed views, test/test_gemm.cc:96-135; src/gemmC.cc:124-182 then reads
+// tile (k, i) of the stored A with the op on the tile).  One batched launch per block column k of op(A) over every C
+// tile, the op passed to the tile GEMM; beta in the first step.  'N','N' stays on gemm_driver (runtime.cu: SUMMA on
+// grids, the transposed-B-panel path).  1 x 1 grid.
+// STATUS: written after round 2's GPU budget was spent; golden vectors from the unmodified reference + oracle (CPU);
+// every (opA, opB) pair of the tile GEMM is validated at kernel level (tests/test_gpu_kernels.py); NOT yet run on a GPU.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int gemm_ops(int opA, int opB, T alpha, Matrix& A, Matrix& B, T beta, Matrix& C, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.kind != 'G' || B.kind != 'G' || C.kind != 'G') return SB200_EINVAL;
+    if (! IsComplex<T>::value) { if (opA == 'C') opA = 'T'; if (opB == 'C') opB = 'T'; }
+    const bool ta = opA != 'N', tb = opB != 'N';
+    const int64_t m = ta ? A.n : A.m, ka = ta ? A.m : A.n, kb = tb ? B.n : B.m, n = tb ? B.m : B.n;
+    if (m != C.m || n != C.n || ka != kb || A.nb != C.nb || B.nb != C.nb) return SB200_EINVAL;
+    const int64_t kt = ta ? A.mt : A.nt, nb = C.nb;
+    if (C.m == 0 || C.n == 0) return SB200_OK;
+    if (kt == 0) return SB200_ENOTSUP;                                    // k == 0 is not served (as gemm_driver)
+    const int ld = int(nb);
+    std::vector<std::vector<Batch>> plan(static_cast<size_t>(kt));
+    PlanBuffer pb;
+    for (int64_t k = 0; k < kt; ++k) {
+        const int kk = int(ta ? A.tile_mb(k) : A.tile_nb(k));
+        for (int64_t j = 0; j < C.nt; ++j)
+            for (int64_t i = 0; i < C.mt; ++i)
+                batch_add(plan[size_t(k)], int(C.tile_mb(i)), int(C.tile_nb(j)), kk, 0,
+                          ta ? A.tile_as<T>(k, i) : A.tile_as<T>(i, k), tb ? B.tile_as<T>(j, k) : B.tile_as<T>(k, j),
+                          C.tile_as<T>(i, j));
+        pb.reserve(plan[size_t(k)]);
+    }
+    SB_TRY(pb.upload(s));
+    for (int64_t k = 0; k < kt; ++k)
+        SB_TRY(launch_batches<T>(plan[size_t(k)], pb, opA, opB, alpha, k == 0 ? beta : from_real<T>(R(1)), ld, 0, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // trmm, the other side / op variants on lower storage (src/trmm.cc: "the matrices can be transposed or
 // conjugate-transposed beforehand"; src/work/work_trmm.cc serves Side::Right as the Left algorithm on transposed views):
 //     Left,  op = T | C :  B <- alpha op(A) B      op(A) upper triangular: block row i of the result takes the rows k >= i
@@ -1169,6 +1210,16 @@ int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t
     CUDA_TRY(cudaDeviceSynchronize()); \
     if (side == 'L' && op == 'N') return trmm_left_lower<CuS<T>::type>(cvv(alpha), A->A, B->A, diag == 'U', nullptr); \
     return trmm_lower_variant<CuS<T>::type>(side, op, cvv(alpha), A->A, B->A, diag == 'U', nullptr); \
+} \
+int sb200_gemm_op_##X(int opA, int opB, T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    if (! valid_op(opA) || ! valid_op(opB)) return SB200_EINVAL; \
+    if (opA == 'N' && opB == 'N') return sb200_gemm_##X(alpha, A, B, beta, C, opts); \
+    SB_TRY(options_status(opts));\
+    if (! A || ! B || ! C) return SB200_EINVAL; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || B->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return gemm_ops<CuS<T>::type>(opA, opB, cvv(alpha), A->A, B->A, cvv(beta), C->A, nullptr); \
 } \
 int sb200_trsm_mat_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts) \
 { \

@@ -366,11 +366,18 @@ def _same_type(*ms):
     return t
 
 
-def gemm(alpha, A: Matrix, B: Matrix, beta, C: Matrix, opts: dict | None = None):
-    """C = alpha A B + beta C  (slate::gemm, src/gemm.cc:82-105 -> gemmC)."""
+_gemm_op = {t: _sig(f"sb200_gemm_op_{t}", [c_int, c_int, SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+
+
+def gemm(alpha, A: Matrix, B: Matrix, beta, C: Matrix, opts: dict | None = None, opA: str = "N", opB: str = "N"):
+    """C = alpha op(A) op(B) + beta C  (slate::gemm, src/gemm.cc:82-105 -> gemmC).  opA / opB "T" | "C" stand for the
+    (conjugate-)transposed views slate::gemm is handed: A is then the stored k x m matrix, B the stored n x k one."""
     t = _same_type(A, B, C)
     o = _opts(opts)
-    check(_gemm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "gemm")
+    if opA == "N" and opB == "N":
+        check(_gemm[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "gemm")
+    else:
+        check(_gemm_op[t](ord(opA), ord(opB), scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "gemm")
 
 
 multiply = gemm     # simplified API name (include/slate/simplified_api.hh)

@@ -28,6 +28,7 @@ generator fixture pins that), only outputs:
   getrf_z.npz, getrf_c.npz  complex LU and pivots (cabs1 rule), n=192 / 200 (ragged) nb=64; gesv_z.npz its solve, n=200 nrhs=70;
                             gesv_mixed_z.npz, posv_mixed_z.npz complex mixed solvers (solution + iteration count), n=256 nb=64;
                             getrf_tntpiv_z.npz (CALU, n=192), getrf_nopiv_z.npz (rand_dominant, n=200)
+  gemm_{d_tn,d_nt,z_cn,z_tc,z_nc}.npz   slate::multiply with (conjugate-)transposed views of A / B, m=150 n=200 k=100 nb=64
   {trmm,trsm}_{z_left_conj,d_left_trans,d_right,z_right_trans,z_right_conj}.npz, hemm_{z,d}_right.npz, symm_z_right.npz
                             the other side / op variants of trmm / hemm / symm (lower storage), nb=64
   grid_*.npz                the reference ON PROCESS GRIDS (oracle/_ref/ref_dump_mp under oracle/mprun.py): getrf_tntpiv on 2x1 / 3x1 /
@@ -155,6 +156,11 @@ BLAS3_VARIANTS = [
     ("trmm_d_right",       "trmm", "d", dict(n=200, m=70)),
     ("trmm_z_right_trans", "trmm", "z", dict(n=200, m=70, op="t")),
     ("trmm_z_right_conj",  "trmm", "z", dict(n=200, m=70, op="c", diag="u")),
+    ("gemm_d_tn",          "gemm", "d", dict(n=200, m=150, k=100, opa="t")),
+    ("gemm_d_nt",          "gemm", "d", dict(n=200, m=150, k=100, opb="t")),
+    ("gemm_z_cn",          "gemm", "z", dict(n=200, m=150, k=100, opa="c")),
+    ("gemm_z_tc",          "gemm", "z", dict(n=200, m=150, k=100, opa="t", opb="c")),
+    ("gemm_z_nc",          "gemm", "z", dict(n=200, m=150, k=100, opb="c")),
     ("trsm_z_left_conj",   "trsm", "z", dict(n=70,  m=200, op="c")),
     ("trsm_d_left_trans",  "trsm", "d", dict(n=70,  m=200, op="t", diag="u")),
     ("trsm_d_right",       "trsm", "d", dict(n=200, m=70)),
@@ -176,7 +182,7 @@ def blas3_variant_fixtures():
         if routine in ("trmm", "trsm") and name.split("_")[2] == "right":
             kv["side"] = "r"
         f, _ = run(routine, t, n, 64, **kv)
-        if routine in ("trmm", "trsm"):
+        if routine in ("trmm", "trsm", "gemm"):
             shape = (kv["m"], n)
         else:
             shape = (kv["nrhs"], n)            # Side::Right: B and C are nrhs x n

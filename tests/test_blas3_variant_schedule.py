@@ -1,5 +1,5 @@
 """CPU check of the SCHEDULES of the side / op variants of trmm / hemm / symm / trsm (slate_b200/csrc/solve.cu:
-trmm_lower_variant, hemm_symm_right_lower, tri_sweep_right): the step order, the batches of a step, the operand roles and the in-place
+trmm_lower_variant, hemm_symm_right_lower, tri_sweep_right, gemm_ops): the step order, the batches of a step, the operand roles and the in-place
 update through a one-block workspace are restated here tile by tile in numpy, exactly as the driver issues them, and
 compared with the oracle (which is pinned to the unmodified reference's golden output, tests/test_oracle.py).  What this
 does NOT cover is the C++ transcription and the kernels: that is tests/test_zzzzz_gpu_blas3_variants.py on a GPU."""
@@ -136,6 +136,36 @@ def test_trsm_right_sweep_schedule_matches_oracle(dt, lower, op, unit, m, n, nb)
     assert np.isfinite(out).all()
     scale = max(np.abs(ref).max(), 1.0)
     assert np.abs(out - ref).max() <= 1e-11 * scale and np.abs(direct - ref).max() <= 1e-11 * scale
+
+
+def gemm_ops(opa, opb, alpha, A, B, beta, C, nb):
+    """solve.cu: gemm_ops -- step k multiplies STORED tile (k, i) of A (opA != N) or (i, k), and STORED tile (j, k) of B
+    (opB != N) or (k, j), with the op handed to the tile GEMM"""
+    C = np.array(C, order="F", copy=True)
+    ta, tb = opa != "N", opb != "N"
+    tk = tiles(A.shape[0] if ta else A.shape[1], nb)
+    for k, (k0, k1) in enumerate(tk):
+        for (j0, j1) in tiles(C.shape[1], nb):
+            for (i0, i1) in tiles(C.shape[0], nb):
+                a_tile = A[k0:k1, i0:i1] if ta else A[i0:i1, k0:k1]
+                b_tile = B[j0:j1, k0:k1] if tb else B[k0:k1, j0:j1]
+                C[i0:i1, j0:j1] = gemm(opa, opb, alpha, a_tile, b_tile, beta if k == 0 else 1.0, C[i0:i1, j0:j1])
+    return C
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+@pytest.mark.parametrize("opa", ["N", "T", "C"])
+@pytest.mark.parametrize("opb", ["N", "T", "C"])
+@pytest.mark.parametrize("m,n,k,nb", [(150, 200, 100, 64), (70, 10, 300, 64)])
+def test_gemm_ops_schedule_matches_oracle(dt, opa, opb, m, n, k, nb):
+    A = o.generate("rand", *((m, k) if opa == "N" else (k, m)), 42, dt)
+    B = o.generate("rand", *((k, n) if opb == "N" else (n, k)), 43, dt)
+    C = o.generate("rand", m, n, 44, dt)
+    al, be = (3.1 + 1.4j, 2.7 + 1.7j) if dt is np.complex128 else (3.1, 2.7)
+    out = gemm_ops(opa, opb, al, A, B, be, C, nb)
+    ref = al * (OP[opa](A) @ OP[opb](B)) + be * C
+    assert np.abs(out - ref).max() <= 64 * EPS * np.abs(ref).max()
+    assert np.abs(out - o.gemm(al, A, B, be, C, nb, opa=opa, opb=opb)).max() <= 64 * EPS * np.abs(ref).max()
 
 
 ALPHA = 3.141592653589793 + 1.414213562373095j

@@ -145,6 +145,20 @@ def test_trmm_side_op_variants_match_reference(golden_dir, name, t, side, op, un
     assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
 
 
+@pytest.mark.parametrize("name,t,opa,opb", [("gemm_d_tn", "d", "T", "N"), ("gemm_d_nt", "d", "N", "T"), ("gemm_z_cn", "z", "C", "N"),
+                                           ("gemm_z_tc", "z", "T", "C"), ("gemm_z_nc", "z", "N", "C")])
+def test_gemm_with_transposed_views_matches_reference(golden_dir, name, t, opa, opb):
+    g = load(golden_dir, name)
+    dt = np.complex128 if t == "z" else np.float64
+    m, n, k, nb = 150, 200, 100, 64
+    A = o.generate("rand", *((m, k) if opa == "N" else (k, m)), 42, dt)
+    B = o.generate("rand", *((k, n) if opb == "N" else (n, k)), 43, dt)
+    C = o.generate("rand", m, n, 44, dt)
+    al, be = (ALPHA, BETA) if t == "z" else (ALPHA.real, BETA.real)
+    out = o.gemm(al, A, B, be, C, nb, opa=opa, opb=opb)
+    assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
+
+
 @pytest.mark.parametrize("name,t,side,op,unit", [
     ("trsm_z_left_conj", "z", "L", "C", False), ("trsm_d_left_trans", "d", "L", "T", True),
     ("trsm_d_right", "d", "R", "N", False), ("trsm_z_right_trans", "z", "R", "T", True),

@@ -223,3 +223,38 @@ def test_posv_and_gesv_are_factor_then_solve(sl, golden_dir):
     _, iref = o.potrf(o.he_full(np.tril(o.generate("rand", n, n, 42))), nb)
     assert info == iref > 0
     assert np.array_equal(B.to_host(), b0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# slate::gemm with (conjugate-)transposed views (sb200_gemm_op_*: solve.cu gemm_ops)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,t,opa,opb", [("gemm_d_tn", "d", "T", "N"), ("gemm_d_nt", "d", "N", "T"), ("gemm_z_cn", "z", "C", "N"),
+                                           ("gemm_z_tc", "z", "T", "C"), ("gemm_z_nc", "z", "N", "C")])
+def test_gemm_transposed_views_match_reference_golden(sl, golden_dir, name, t, opa, opb):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))["out"]
+    m, n, k, nb = 150, 200, 100, 64
+    A = sl.Matrix(*((m, k) if opa == "N" else (k, m)), nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(*((k, n) if opb == "N" else (n, k)), nb, dtype=t).generate("rand", 43)
+    C = sl.Matrix(m, n, nb, dtype=t).generate("rand", 44)
+    al, be = (ALPHA, BETA) if t == "z" else (ALPHA.real, BETA.real)
+    sl.gemm(al, A, B, be, C, opA=opa, opB=opb)
+    assert np.abs(C.to_host() - g).max() <= 3 * np.sqrt(k) * EPS * 4 * np.abs(g).max()
+
+
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("opa", ["N", "T", "C"])
+@pytest.mark.parametrize("opb", ["N", "T", "C"])
+@pytest.mark.parametrize("m,n,k,nb", [(150, 200, 100, 64), (512, 512, 512, 128), (70, 10, 300, 64), (300, 1000, 260, 256)])
+def test_gemm_transposed_views_vs_oracle_and_tester_check(sl, t, opa, opb, m, n, k, nb):
+    al, be = (ALPHA, BETA) if t in "cz" else (ALPHA.real, BETA.real)
+    sa, sb = ((m, k) if opa == "N" else (k, m)), ((k, n) if opb == "N" else (n, k))
+    A = sl.Matrix(*sa, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(*sb, nb, dtype=t).generate("rand", 43)
+    C = sl.Matrix(m, n, nb, dtype=t).generate("rand", 44)
+    sl.gemm(al, A, B, be, C, opA=opa, opB=opb)
+    a, b, c0 = (o.generate("rand", *shape, seed, NP[t]).astype(_wide(t)) for shape, seed in ((sa, 42), (sb, 43), ((m, n), 44)))
+    ref = o.gemm(al, a, b, be, c0, nb, opa=opa, opb=opb)
+    out = C.to_host()
+    assert np.abs(out - ref).max() <= 3 * np.sqrt(k) * _eps(t) * 4 * np.abs(ref).max()
+    view = {"N": lambda x: x, "T": lambda x: x.T, "C": lambda x: x.conj().T}
+    assert o.gemm_check(al, view[opa](a), view[opb](b), be, c0, out.astype(_wide(t))) <= 3 * _eps(t)     # test/test_gemm.cc:192-208
