@@ -621,7 +621,8 @@ int trmm_left_lower(T alpha, Matrix& A, Matrix& B, bool unit, cudaStream_t s)
 // tile, the op passed to the tile GEMM; beta in the first step.  'N','N' stays on gemm_driver (runtime.cu: SUMMA on
 // grids, the transposed-B-panel path).  1 x 1 grid.
 // STATUS: written after round 2's GPU budget was spent; golden vectors from the unmodified reference + oracle (CPU);
-// every (opA, opB) pair of the tile GEMM is validated at kernel level (tests/test_gpu_kernels.py); NOT yet run on a GPU.
+// the tile GEMM is validated at kernel level for the pairs NN, NT, TN, NC, CC (tests/test_gpu_kernels.py) and CN / TN
+// through hemm / symm; the other pairs combine the same per-operand transposition / conjugation paths.  NOT yet run on a GPU.
 // ------------------------------------------------------------------------------------------
 template <typename T>
 int gemm_ops(int opA, int opB, T alpha, Matrix& A, Matrix& B, T beta, Matrix& C, cudaStream_t s)
