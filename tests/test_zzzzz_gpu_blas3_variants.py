@@ -258,3 +258,36 @@ def test_gemm_transposed_views_vs_oracle_and_tester_check(sl, t, opa, opb, m, n,
     assert np.abs(out - ref).max() <= 3 * np.sqrt(k) * _eps(t) * 4 * np.abs(ref).max()
     view = {"N": lambda x: x, "T": lambda x: x.T, "C": lambda x: x.conj().T}
     assert o.gemm_check(al, view[opa](a), view[opb](b), be, c0, out.astype(_wide(t))) <= 3 * _eps(t)     # test/test_gemm.cc:192-208
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# More of the reference's OWN tester through the shim (oracle/_ref/tester_sb200, see tests/test_reference_tester_gpu.py):
+# routines of SURVEY section 8(f) and BASELINE configs[4] whose SLATE drivers reach these kernels through the
+# blas::batch::gemm / trsm / herk, lapack::potrf and slate::device::* seams under Target::Devices.  The tester's own
+# residual checks decide; routines it can only check against ScaLAPACK report "no check" and prove that the Devices
+# driver runs to completion on these kernels.  (First run pending like the rest of this file; each run is a subprocess.)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("routine,extra,nrows", [
+    ("posv_mixed",  ["--type", "d", "--dim", "2048", "--nb", "256"], 1),
+    ("gesv_mixed",  ["--type", "d", "--dim", "2048", "--nb", "256"], 1),
+    ("potrs",       ["--type", "d,z", "--dim", "2048", "--nb", "256"], 2),
+    ("getrs",       ["--type", "d", "--dim", "2048", "--nb", "256"], 1),
+    ("getrf_nopiv", ["--type", "d", "--dim", "2048", "--nb", "256", "--matrix", "rand_dominant"], 1),
+    ("gesv_nopiv",  ["--type", "d", "--dim", "2048", "--nb", "256", "--matrix", "rand_dominant"], 1),
+    ("her2k",       ["--type", "d,z", "--dim", "1024", "--nb", "256"], 2),
+    ("syr2k",       ["--type", "d,z", "--dim", "768", "--nb", "256"], 2),
+    ("gemmA",       ["--type", "d", "--dim", "1024x64x1024", "--nb", "256"], 1),
+    ("tzadd",       ["--type", "d,z", "--dim", "1000x800", "--nb", "256", "--uplo", "l,u"], 4),
+    ("tzscale",     ["--type", "d,z", "--dim", "1000x800", "--nb", "256", "--uplo", "l,u"], 4),
+    ("tzcopy",      ["--type", "d,z", "--dim", "1000x800", "--nb", "256", "--uplo", "l,u"], 4),
+    ("tzset",       ["--type", "d,z", "--dim", "1000x800", "--nb", "256", "--uplo", "l,u"], 4),
+    ("scale_row_col", ["--type", "d,z", "--dim", "1000x800", "--nb", "256"], 2),
+])
+def test_more_reference_tester_routines_on_our_kernels(routine, extra, nrows):
+    from tests.test_reference_tester_gpu import run_tester
+    rc, text, rows = run_tester("--target", "d", "--origin", "d", "--check", "y", "--ref", "n", *extra, routine)
+    assert rc == 0, text[-3000:]
+    assert len(rows) >= nrows, text[-3000:]
+    for r in rows:
+        assert ("pass" in r or "no check" in r) and "FAILED" not in r and "failed" not in r, r
+    assert "All tests passed" in text, text[-2000:]
