@@ -648,6 +648,26 @@ def trsm(alpha, A: Matrix, B: Matrix, side: str = "L", uplo: str = "L", op: str 
 
 triangular_solve = trsm
 
+
+def getrs_nopiv(A: Matrix, B: Matrix, opts: dict | None = None):
+    """Solve A X = B with the factors of getrf_nopiv: forward substitution with the unit lower triangle of A, backward
+    substitution with its upper triangle -- the two sweeps getrs runs, without the row permutation
+    (slate::getrs_nopiv, src/getrs_nopiv.cc:20-53)."""
+    trsm(1.0, A, B, side="L", uplo="L", op="N", diag="U", opts=opts)
+    trsm(1.0, A, B, side="L", uplo="U", op="N", diag="N", opts=opts)
+
+
+def gesv_nopiv(A: Matrix, B: Matrix, opts: dict | None = None) -> int:
+    """getrf_nopiv, then getrs_nopiv when no pivot was zero (slate::gesv_nopiv, src/gesv_nopiv.cc).  Returns info."""
+    info = getrf_nopiv(A, opts)
+    if info == 0:
+        getrs_nopiv(A, B, opts)
+    return info
+
+
+lu_solve_using_factor_nopiv = getrs_nopiv
+lu_solve_nopiv = gesv_nopiv
+
 MIXED_TIMERS = ("total", "factor_lo", "solve_lo", "residual_hi", "add_hi", "factor_hi", "solve_hi", "norm_convert")
 
 

@@ -291,3 +291,21 @@ def test_more_reference_tester_routines_on_our_kernels(routine, extra, nrows):
     for r in rows:
         assert ("pass" in r or "no check" in r) and "FAILED" not in r and "failed" not in r, r
     assert "All tests passed" in text, text[-2000:]
+
+
+@pytest.mark.parametrize("t", ["d", "s"])
+@pytest.mark.parametrize("n,nb,nrhs", [(300, 64, 10), (1024, 256, 130)])
+def test_gesv_nopiv_is_factor_then_two_sweeps(sl, t, n, nb, nrhs):
+    """slate::gesv_nopiv (src/gesv_nopiv.cc; getrs_nopiv = the unit-lower and the upper sweep of getrs without the
+    permutation, src/getrs_nopiv.cc:20-53) on a diagonally dominant matrix: the tester's solve residual."""
+    A = sl.Matrix(n, n, nb, dtype=t).generate("rand_dominant", 42)
+    B = sl.Matrix(n, nrhs, nb, dtype=t).generate("rand", 43)
+    assert sl.lu_solve_nopiv(A, B) == 0
+    a = o.generate("rand_dominant", n, n, 42, NP[t]).astype(np.float64)
+    b = o.generate("rand", n, nrhs, 43, NP[t]).astype(np.float64)
+    X = B.to_host().astype(np.float64)
+    assert o.solve_residual(a, X, b) <= 25 * _eps(t)                     # test/test_gesv.cc:371-377
+    LUo, info = o.getrf_nopiv(a, nb)
+    assert info == 0
+    Xo = o.tri_sweep(np.triu(LUo), o.tri_sweep(np.tril(LUo), b, nb, lower=True, unit=True), nb, lower=False)
+    assert np.abs(X - Xo).max() <= 200 * _eps(t) * np.abs(Xo).max()
