@@ -770,6 +770,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the dgetrf / dgemm sub-records of the default run")
     ap.add_argument("--also-steps", type=int, default=2)
+    ap.add_argument("--grid", default="", help="process grid PxQ of the default routines (default: the reference's rule, 2x4 on 8 ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -794,7 +795,8 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     routine, nb = args.routine, args.nb
     n = args.n or default_n(routine, world)
-    grid = sl.Grid.from_torch_distributed() if world > 1 else sl.Grid()
+    gp, gq = (int(x) for x in args.grid.lower().split("x")) if args.grid else (None, None)
+    grid = sl.Grid.from_torch_distributed(gp, gq) if world > 1 else sl.Grid()
     st = torch.cuda.current_stream().cuda_stream
     env = {"torch": torch, "dist": dist, "sl": sl, "lib": lib, "check": check, "c_dbl": c_dbl, "c_ptr": c_ptr}
     warmup = max(args.warmup, 3)
