@@ -467,6 +467,13 @@ int sb200_trmm_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t
 /* C = alpha op(A) op(B) + beta C with the (conjugate-)transposed views slate::gemm is handed (opA / opB 'N' | 'T' | 'C'; \
  * A is stored k x m when opA != 'N', B n x k when opB != 'N').  'N','N' forwards to sb200_gemm_X; other pairs: 1 x 1 grid */ \
 int sb200_gemm_op_##X(int opA, int opB, T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
+/* the rank-k / rank-2k updates handed (conjugate-)transposed views (slate::herk / her2k: op 'C', real types also 'T'; \
+ * slate::syrk / syr2k: op 'T'): A (and B) are stored k x n, C = alpha A^H A + beta C etc.  op 'N' forwards to the \
+ * _mat entry points (grids); other ops: 1 x 1 grid, SB200_ENOTSUP for the op the routine does not take */ \
+int sb200_herk_op_##X(int op, R alpha, sb200_matrix_t A, R beta, sb200_matrix_t C, const sb200_options_t* opts); \
+int sb200_her2k_op_##X(int op, T alpha, sb200_matrix_t A, sb200_matrix_t B, R beta, sb200_matrix_t C, const sb200_options_t* opts); \
+int sb200_syrk_op_##X(int op, T alpha, sb200_matrix_t A, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
+int sb200_syr2k_op_##X(int op, T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, const sb200_options_t* opts); \
 /* B = alpha op(A)^{-1} B (side 'L') or B = alpha B op(A)^{-1} (side 'R') at matrix level, A triangular: the lower tiles of a \
  * kind 'H' matrix (uplo 'L') or the lower / upper triangle of a general square matrix such as an LU factor; op 'N' | 'T' | 'C', \
  * diag 'N' | 'U'.  slate::trsm / triangular_solve (src/trsm.cc -> work::trsm, src/work/work_trsm.cc:24-387); 1 x 1 grid */ \

@@ -180,9 +180,11 @@ int run(const Args& a)
         if (dump) { auto d = to_dense(C); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }
     }
     else if (a.routine == "herk") {
+        // trans=c: A is stored k x n and handed over as its conjugate-transposed view, C = alpha A^H A + beta C (test/test_herk.cc)
         int64_t k = a.geti("k", n);
         bool lower = a.get("uplo", "l") == "l";
-        auto A = make_matrix<T>(n, k, nb, a.seedA, "rand");
+        const bool tr = a.get("trans", "n") != "n";
+        auto A = tr ? make_matrix<T>(k, n, nb, a.seedA, "rand") : make_matrix<T>(n, k, nb, a.seedA, "rand");
         slate::HermitianMatrix<T> C(lower ? slate::Uplo::Lower : slate::Uplo::Upper, n, nb,
                                     slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         C.insertLocalTiles();
@@ -196,7 +198,9 @@ int run(const Args& a)
         }
         real_t ra = std::real(alpha), rb = std::real(beta);
         auto t0 = tic();
-        slate::rank_k_update(ra, A, rb, C, opts);
+        auto opA = A;
+        if (tr) opA = slate::conj_transpose(A);
+        slate::rank_k_update(ra, opA, rb, C, opts);
         seconds = toc(t0);
         gflop = blas::Gflop<T>::herk(n, k);
         if (dump) {
@@ -372,8 +376,9 @@ int run(const Args& a)
     else if (a.routine == "her2k") {
         // C = alpha A B^H + conj(alpha) B A^H + beta C, C Hermitian lower (test/test_her2k.cc; slate::her2k, src/her2k.cc)
         int64_t k = a.geti("k", n);
-        auto A = make_matrix<T>(n, k, nb, a.seedA, "rand");
-        auto B = make_matrix<T>(n, k, nb, a.seedB, "rand");
+        const bool tr = a.get("trans", "n") != "n";          // trans=c: A, B stored k x n, conjugate-transposed views
+        auto A = tr ? make_matrix<T>(k, n, nb, a.seedA, "rand") : make_matrix<T>(n, k, nb, a.seedA, "rand");
+        auto B = tr ? make_matrix<T>(k, n, nb, a.seedB, "rand") : make_matrix<T>(n, k, nb, a.seedB, "rand");
         slate::HermitianMatrix<T> C(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         C.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedC;
@@ -381,7 +386,9 @@ int run(const Args& a)
         slate::generate_matrix(p, C);
         real_t rb = std::real(beta);
         auto t0 = tic();
-        slate::her2k(alpha, A, B, rb, C, opts);
+        auto opA = A, opB = B;
+        if (tr) { opA = slate::conj_transpose(A); opB = slate::conj_transpose(B); }
+        slate::her2k(alpha, opA, opB, rb, C, opts);
         seconds = toc(t0);
         gflop = blas::Gflop<T>::her2k(n, k);
         if (dump) {
@@ -393,16 +400,19 @@ int run(const Args& a)
         // complex-symmetric rank-k / rank-2k updates (no conjugation; slate::syrk, src/syrk.cc; slate::syr2k, src/syr2k.cc):
         // C = alpha A A^T + beta C   /   C = alpha A B^T + alpha B A^T + beta C,  C symmetric lower, alpha / beta scalar_t
         int64_t k = a.geti("k", n);
-        auto A = make_matrix<T>(n, k, nb, a.seedA, "rand");
-        auto B = make_matrix<T>(n, k, nb, a.seedB, "rand");
+        const bool tr = a.get("trans", "n") != "n";          // trans=t: A, B stored k x n, transposed views
+        auto A = tr ? make_matrix<T>(k, n, nb, a.seedA, "rand") : make_matrix<T>(n, k, nb, a.seedA, "rand");
+        auto B = tr ? make_matrix<T>(k, n, nb, a.seedB, "rand") : make_matrix<T>(n, k, nb, a.seedB, "rand");
         slate::SymmetricMatrix<T> C(slate::Uplo::Lower, n, nb, slate::GridOrder::Col, g_p, g_q, MPI_COMM_WORLD);
         C.insertLocalTiles();
         slate::MatgenParams p; p.verbose = 0; p.kind = "rand"; p.seed = a.seedC;
         p.cond_request = p.cond_actual = p.condD = NAN;
         slate::generate_matrix(p, C);
         auto t0 = tic();
-        if (a.routine == "syrk") slate::syrk(alpha, A, beta, C, opts);
-        else                     slate::syr2k(alpha, A, B, beta, C, opts);
+        auto opA = A, opB = B;
+        if (tr) { opA = slate::transpose(A); opB = slate::transpose(B); }
+        if (a.routine == "syrk") slate::syrk(alpha, opA, beta, C, opts);
+        else                     slate::syr2k(alpha, opA, opB, beta, C, opts);
         seconds = toc(t0);
         gflop = a.routine == "syrk" ? blas::Gflop<T>::syrk(n, k) : blas::Gflop<T>::syr2k(n, k);
         if (dump) {

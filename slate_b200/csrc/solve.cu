@@ -657,6 +657,54 @@ int gemm_ops(int opA, int opB, T alpha, Matrix& A, Matrix& B, T beta, Matrix& C,
 }
 
 // ------------------------------------------------------------------------------------------
+// herk / her2k / syrk / syr2k handed (conjugate-)transposed views: A (and B) stored k x n,
+//     conj:  C = alpha A^H A + beta C   |   C = alpha A^H B + conj(alpha) B^H A + beta C      (slate::herk, slate::her2k)
+//     else:  C = alpha A^T A + beta C   |   C = alpha A^T B + alpha B^T A + beta C            (slate::syrk, slate::syr2k)
+// C Hermitian / symmetric, lower tiles.  The drivers of runtime.cu with the roles of the tile indices exchanged: step kk
+// takes block ROW kk of the stored A (B), the op moves from the B-role operand ('N', op) to the A-role one (op, 'N');
+// diagonal tiles triangle-masked in the epilogue (the mask does not depend on the operand layout), Hermitian diagonal
+// forced real.  One (rank-2k: two) batched launch per step.  1 x 1 grid.
+// STATUS: written after round 2's GPU budget was spent; golden vectors from the unmodified reference + oracle (CPU),
+// schedule checked on the CPU; NOT yet run on a GPU.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int rank_update_trans(bool conj, T alpha, Matrix& A, Matrix* B, T beta, Matrix& C, cudaStream_t s)
+{
+    using R = typename RealOf<T>::type;
+    if (A.g->size() > 1) return SB200_ENOTSUP;
+    if (A.kind != 'G' || C.kind != 'H' || (B && B->kind != 'G')) return SB200_EINVAL;
+    if (A.n != C.n || A.nb != C.nb || (B && (B->m != A.m || B->n != A.n || B->nb != A.nb))) return SB200_EINVAL;
+    const int64_t kt = A.mt, nt = C.nt, nb = C.nb;
+    if (C.n == 0) return SB200_OK;
+    if (kt == 0) return SB200_ENOTSUP;                                   // k == 0 is not served (as the NoTrans drivers)
+    const int ld = int(nb);
+    const int opH = (conj && IsComplex<T>::value) ? 'C' : 'T';
+    const T one = from_real<T>(R(1));
+    std::vector<std::vector<Batch>> plan_ab(static_cast<size_t>(kt)), plan_ba(static_cast<size_t>(B ? kt : 0));
+    PlanBuffer pb;
+    for (int64_t k = 0; k < kt; ++k) {
+        for (int64_t j = 0; j < nt; ++j)
+            for (int64_t i = j; i < nt; ++i) {
+                batch_add(plan_ab[size_t(k)], int(C.tile_mb(i)), int(C.tile_nb(j)), int(A.tile_mb(k)), i == j ? 1 : 0,
+                          A.tile_as<T>(k, i), B ? B->tile_as<T>(k, j) : A.tile_as<T>(k, j), C.tile_as<T>(i, j));
+                if (B)
+                    batch_add(plan_ba[size_t(k)], int(C.tile_mb(i)), int(C.tile_nb(j)), int(A.tile_mb(k)), i == j ? 1 : 0,
+                              B->tile_as<T>(k, i), A.tile_as<T>(k, j), C.tile_as<T>(i, j));
+            }
+        pb.reserve(plan_ab[size_t(k)]);
+        if (B) pb.reserve(plan_ba[size_t(k)]);
+    }
+    SB_TRY(pb.upload(s));
+    const T alpha2 = conj ? conj_(alpha) : alpha;
+    for (int64_t k = 0; k < kt; ++k) {
+        SB_TRY(launch_batches<T>(plan_ab[size_t(k)], pb, opH, 'N', alpha, k == 0 ? beta : one, ld, conj ? 1 : 0, s));
+        if (B) SB_TRY(launch_batches<T>(plan_ba[size_t(k)], pb, opH, 'N', alpha2, one, ld, conj ? 1 : 0, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // trmm, the other side / op variants on lower storage (src/trmm.cc: "the matrices can be transposed or
 // conjugate-transposed beforehand"; src/work/work_trmm.cc serves Side::Right as the Left algorithm on transposed views):
 //     Left,  op = T | C :  B <- alpha op(A) B      op(A) upper triangular: block row i of the result takes the rows k >= i
@@ -1221,6 +1269,51 @@ int sb200_gemm_op_##X(int opA, int opB, T alpha, sb200_matrix_t A, sb200_matrix_
     if (A->A.dtype != TypeChar<CuS<T>::type>::value || B->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
     CUDA_TRY(cudaDeviceSynchronize()); \
     return gemm_ops<CuS<T>::type>(opA, opB, cvv(alpha), A->A, B->A, cvv(beta), C->A, nullptr); \
+} \
+/* op 'N' forwards to the grid-aware drivers of runtime.cu; Hermitian updates take 'C' ('T' too for real types), symmetric ones 'T' */ \
+int sb200_herk_op_##X(int op, R alpha, sb200_matrix_t A, R beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    if (! valid_op(op)) return SB200_EINVAL; \
+    if (op == 'N') return sb200_herk_mat_##X(alpha, A, beta, C, opts); \
+    SB_TRY(options_status(opts));\
+    if (! A || ! C) return SB200_EINVAL; \
+    if (IsComplex<CuS<T>::type>::value && op != 'C') return SB200_ENOTSUP; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return rank_update_trans<CuS<T>::type>(true, from_real<CuS<T>::type>(alpha), A->A, nullptr, from_real<CuS<T>::type>(beta), C->A, nullptr); \
+} \
+int sb200_her2k_op_##X(int op, T alpha, sb200_matrix_t A, sb200_matrix_t B, R beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    if (! valid_op(op)) return SB200_EINVAL; \
+    if (op == 'N') return sb200_her2k_mat_##X(alpha, A, B, beta, C, opts); \
+    SB_TRY(options_status(opts));\
+    if (! A || ! B || ! C) return SB200_EINVAL; \
+    if (IsComplex<CuS<T>::type>::value && op != 'C') return SB200_ENOTSUP; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || B->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return rank_update_trans<CuS<T>::type>(true, cvv(alpha), A->A, &B->A, from_real<CuS<T>::type>(beta), C->A, nullptr); \
+} \
+int sb200_syrk_op_##X(int op, T alpha, sb200_matrix_t A, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    if (! valid_op(op)) return SB200_EINVAL; \
+    if (op == 'N') return sb200_syrk_mat_##X(alpha, A, beta, C, opts); \
+    SB_TRY(options_status(opts));\
+    if (! A || ! C) return SB200_EINVAL; \
+    if (IsComplex<CuS<T>::type>::value && op != 'T') return SB200_ENOTSUP; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return rank_update_trans<CuS<T>::type>(false, cvv(alpha), A->A, nullptr, cvv(beta), C->A, nullptr); \
+} \
+int sb200_syr2k_op_##X(int op, T alpha, sb200_matrix_t A, sb200_matrix_t B, T beta, sb200_matrix_t C, const sb200_options_t* opts) \
+{ \
+    if (! valid_op(op)) return SB200_EINVAL; \
+    if (op == 'N') return sb200_syr2k_mat_##X(alpha, A, B, beta, C, opts); \
+    SB_TRY(options_status(opts));\
+    if (! A || ! B || ! C) return SB200_EINVAL; \
+    if (IsComplex<CuS<T>::type>::value && op != 'T') return SB200_ENOTSUP; \
+    if (A->A.dtype != TypeChar<CuS<T>::type>::value || B->A.dtype != A->A.dtype || C->A.dtype != A->A.dtype) return SB200_EINVAL; \
+    CUDA_TRY(cudaDeviceSynchronize()); \
+    return rank_update_trans<CuS<T>::type>(false, cvv(alpha), A->A, &B->A, cvv(beta), C->A, nullptr); \
 } \
 int sb200_trsm_mat_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts) \
 { \

@@ -383,23 +383,36 @@ def gemm(alpha, A: Matrix, B: Matrix, beta, C: Matrix, opts: dict | None = None,
 multiply = gemm     # simplified API name (include/slate/simplified_api.hh)
 
 
-def herk(alpha: float, A: Matrix, beta: float, C: "HermitianMatrix", opts: dict | None = None):
+_herk_op = {t: _sig(f"sb200_herk_op_{t}", [c_int, REAL_T[t], c_ptr, REAL_T[t], c_ptr, _OP]) for t in "sdcz"}
+_her2k_op = {t: _sig(f"sb200_her2k_op_{t}", [c_int, SCALAR_T[t], c_ptr, c_ptr, REAL_T[t], c_ptr, _OP]) for t in "sdcz"}
+_syrk_op = {t: _sig(f"sb200_syrk_op_{t}", [c_int, SCALAR_T[t], c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+_syr2k_op = {t: _sig(f"sb200_syr2k_op_{t}", [c_int, SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
+
+
+def herk(alpha: float, A: Matrix, beta: float, C: "HermitianMatrix", opts: dict | None = None, op: str = "N"):
     """C = alpha A A^H + beta C, C Hermitian (lower), alpha / beta real (slate::herk, src/herk.cc:25-162;
-    for real types this is syrk, as in the reference)."""
+    for real types this is syrk, as in the reference).  op "C": A is the stored k x n matrix whose conjugate-transposed
+    view slate::herk is handed, C = alpha A^H A + beta C."""
     t = _same_type(A, C)
     o = _opts(opts)
-    check(_herk[t](REAL_T[t](float(alpha)), A._h, REAL_T[t](float(beta)), C._h, ctypes.byref(o)), "herk")
+    if op == "N":
+        check(_herk[t](REAL_T[t](float(alpha)), A._h, REAL_T[t](float(beta)), C._h, ctypes.byref(o)), "herk")
+    else:
+        check(_herk_op[t](ord(op), REAL_T[t](float(alpha)), A._h, REAL_T[t](float(beta)), C._h, ctypes.byref(o)), "herk")
 
 
 rank_k_update = herk
 
 
-def her2k(alpha, A: Matrix, B: Matrix, beta: float, C: "HermitianMatrix", opts: dict | None = None):
+def her2k(alpha, A: Matrix, B: Matrix, beta: float, C: "HermitianMatrix", opts: dict | None = None, op: str = "N"):
     """C = alpha A B^H + conj(alpha) B A^H + beta C, C Hermitian (lower), beta real (slate::her2k, src/her2k.cc:27-170;
-    for real types this is syr2k)."""
+    for real types this is syr2k).  op "C": A, B stored k x n, C = alpha A^H B + conj(alpha) B^H A + beta C."""
     t = _same_type(A, B, C)
     o = _opts(opts)
-    check(_her2k[t](scalar(t, alpha), A._h, B._h, REAL_T[t](float(beta)), C._h, ctypes.byref(o)), "her2k")
+    if op == "N":
+        check(_her2k[t](scalar(t, alpha), A._h, B._h, REAL_T[t](float(beta)), C._h, ctypes.byref(o)), "her2k")
+    else:
+        check(_her2k_op[t](ord(op), scalar(t, alpha), A._h, B._h, REAL_T[t](float(beta)), C._h, ctypes.byref(o)), "her2k")
 
 
 rank_2k_update = her2k
@@ -408,18 +421,26 @@ _syrk = {t: _sig(f"sb200_syrk_mat_{t}", [SCALAR_T[t], c_ptr, SCALAR_T[t], c_ptr,
 _syr2k = {t: _sig(f"sb200_syr2k_mat_{t}", [SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}
 
 
-def syrk(alpha, A: Matrix, beta, C: "HermitianMatrix", opts: dict | None = None):
-    """C = alpha A A^T + beta C, C symmetric (lower tiles), no conjugation (slate::syrk, src/syrk.cc)."""
+def syrk(alpha, A: Matrix, beta, C: "HermitianMatrix", opts: dict | None = None, op: str = "N"):
+    """C = alpha A A^T + beta C, C symmetric (lower tiles), no conjugation (slate::syrk, src/syrk.cc).
+    op "T": A stored k x n (its transposed view is what slate::syrk is handed), C = alpha A^T A + beta C."""
     t = _same_type(A, C)
     o = _opts(opts)
-    check(_syrk[t](scalar(t, alpha), A._h, scalar(t, beta), C._h, ctypes.byref(o)), "syrk")
+    if op == "N":
+        check(_syrk[t](scalar(t, alpha), A._h, scalar(t, beta), C._h, ctypes.byref(o)), "syrk")
+    else:
+        check(_syrk_op[t](ord(op), scalar(t, alpha), A._h, scalar(t, beta), C._h, ctypes.byref(o)), "syrk")
 
 
-def syr2k(alpha, A: Matrix, B: Matrix, beta, C: "HermitianMatrix", opts: dict | None = None):
-    """C = alpha A B^T + alpha B A^T + beta C, C symmetric (lower tiles), no conjugation (slate::syr2k, src/syr2k.cc)."""
+def syr2k(alpha, A: Matrix, B: Matrix, beta, C: "HermitianMatrix", opts: dict | None = None, op: str = "N"):
+    """C = alpha A B^T + alpha B A^T + beta C, C symmetric (lower tiles), no conjugation (slate::syr2k, src/syr2k.cc).
+    op "T": A, B stored k x n, C = alpha A^T B + alpha B^T A + beta C."""
     t = _same_type(A, B, C)
     o = _opts(opts)
-    check(_syr2k[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "syr2k")
+    if op == "N":
+        check(_syr2k[t](scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "syr2k")
+    else:
+        check(_syr2k_op[t](ord(op), scalar(t, alpha), A._h, B._h, scalar(t, beta), C._h, ctypes.byref(o)), "syr2k")
 
 
 _hemm_side = {t: _sig(f"sb200_hemm_side_{t}", [c_int, SCALAR_T[t], c_ptr, c_ptr, SCALAR_T[t], c_ptr, _OP]) for t in "sdcz"}

@@ -28,6 +28,8 @@ generator fixture pins that), only outputs:
   getrf_z.npz, getrf_c.npz  complex LU and pivots (cabs1 rule), n=192 / 200 (ragged) nb=64; gesv_z.npz its solve, n=200 nrhs=70;
                             gesv_mixed_z.npz, posv_mixed_z.npz complex mixed solvers (solution + iteration count), n=256 nb=64;
                             getrf_tntpiv_z.npz (CALU, n=192), getrf_nopiv_z.npz (rand_dominant, n=200)
+  herk_{z_conj,d_trans}.npz, her2k_z_conj.npz, syrk_z_trans.npz, syr2k_z_trans.npz   rank-k / rank-2k updates with A (and B) stored
+                            k x n and handed over as (conjugate-)transposed views, n=200 k=100 nb=64
   gemm_{d_tn,d_nt,z_cn,z_tc,z_nc}.npz   slate::multiply with (conjugate-)transposed views of A / B, m=150 n=200 k=100 nb=64
   {trmm,trsm}_{z_left_conj,d_left_trans,d_right,z_right_trans,z_right_conj}.npz, hemm_{z,d}_right.npz, symm_z_right.npz
                             the other side / op variants of trmm / hemm / symm (lower storage), nb=64
@@ -161,6 +163,11 @@ BLAS3_VARIANTS = [
     ("gemm_z_cn",          "gemm", "z", dict(n=200, m=150, k=100, opa="c")),
     ("gemm_z_tc",          "gemm", "z", dict(n=200, m=150, k=100, opa="t", opb="c")),
     ("gemm_z_nc",          "gemm", "z", dict(n=200, m=150, k=100, opb="c")),
+    ("herk_z_conj",        "herk",  "z", dict(n=200, k=100, trans="c")),
+    ("herk_d_trans",       "herk",  "d", dict(n=200, k=100, trans="c")),
+    ("her2k_z_conj",       "her2k", "z", dict(n=200, k=100, trans="c")),
+    ("syrk_z_trans",       "syrk",  "z", dict(n=200, k=100, trans="t")),
+    ("syr2k_z_trans",      "syr2k", "z", dict(n=200, k=100, trans="t")),
     ("trsm_z_left_conj",   "trsm", "z", dict(n=70,  m=200, op="c")),
     ("trsm_d_left_trans",  "trsm", "d", dict(n=70,  m=200, op="t", diag="u")),
     ("trsm_d_right",       "trsm", "d", dict(n=200, m=70)),
@@ -182,7 +189,9 @@ def blas3_variant_fixtures():
         if routine in ("trmm", "trsm") and name.split("_")[2] == "right":
             kv["side"] = "r"
         f, _ = run(routine, t, n, 64, **kv)
-        if routine in ("trmm", "trsm", "gemm"):
+        if routine in ("herk", "her2k", "syrk", "syr2k"):
+            shape = (n, n)
+        elif routine in ("trmm", "trsm", "gemm"):
             shape = (kv["m"], n)
         else:
             shape = (kv["nrhs"], n)            # Side::Right: B and C are nrhs x n

@@ -1,5 +1,5 @@
 """CPU check of the SCHEDULES of the side / op variants of trmm / hemm / symm / trsm (slate_b200/csrc/solve.cu:
-trmm_lower_variant, hemm_symm_right_lower, tri_sweep_right, gemm_ops): the step order, the batches of a step, the operand roles and the in-place
+trmm_lower_variant, hemm_symm_right_lower, tri_sweep_right, gemm_ops, rank_update_trans): the step order, the batches of a step, the operand roles and the in-place
 update through a one-block workspace are restated here tile by tile in numpy, exactly as the driver issues them, and
 compared with the oracle (which is pinned to the unmodified reference's golden output, tests/test_oracle.py).  What this
 does NOT cover is the C++ transcription and the kernels: that is tests/test_zzzzz_gpu_blas3_variants.py on a GPU."""
@@ -166,6 +166,59 @@ def test_gemm_ops_schedule_matches_oracle(dt, opa, opb, m, n, k, nb):
     ref = al * (OP[opa](A) @ OP[opb](B)) + be * C
     assert np.abs(out - ref).max() <= 64 * EPS * np.abs(ref).max()
     assert np.abs(out - o.gemm(al, A, B, be, C, nb, opa=opa, opb=opb)).max() <= 64 * EPS * np.abs(ref).max()
+
+
+def rank_update_trans(conj, alpha, A, B, beta, C_lower, nb):
+    """solve.cu: rank_update_trans -- step kk multiplies STORED tiles (kk, i) and (kk, j) of the k x n matrices with the op on
+    the A-role operand; diagonal tiles keep their lower triangle (epilogue mask), Hermitian diagonal forced real"""
+    C = np.array(C_lower, order="F", copy=True)
+    oph = "C" if conj else "T"
+    tn = tiles(C.shape[0], nb)
+    alpha2 = np.conj(alpha) if conj else alpha
+    for kk, (k0, k1) in enumerate(tiles(A.shape[0], nb)):
+        launches = [(A, B if B is not None else A, alpha, beta if kk == 0 else 1.0)]
+        if B is not None:
+            launches.append((B, A, alpha2, 1.0))
+        for (X, Y, al, be) in launches:
+            for j, (j0, j1) in enumerate(tn):
+                for i, (i0, i1) in enumerate(tn):
+                    if i < j:
+                        continue
+                    upd = gemm(oph, "N", al, X[k0:k1, i0:i1], Y[k0:k1, j0:j1], be, C[i0:i1, j0:j1])
+                    if i == j:
+                        mask = np.tril(np.ones(upd.shape, dtype=bool))
+                        blk = C[i0:i1, j0:j1]
+                        blk[mask] = upd[mask]
+                        if conj and np.iscomplexobj(blk):
+                            di = np.arange(blk.shape[0])
+                            blk[di, di] = blk[di, di].real
+                    else:
+                        C[i0:i1, j0:j1] = upd
+    return C
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+@pytest.mark.parametrize("routine", ["herk", "her2k", "syrk", "syr2k"])
+@pytest.mark.parametrize("n,k,nb", [(200, 100, 64), (128, 300, 64), (70, 10, 128)])
+def test_rank_update_trans_schedule_matches_oracle(dt, routine, n, k, nb):
+    A0 = o.generate("rand", k, n, 42, dt)
+    B0 = o.generate("rand", k, n, 43, dt)
+    C = np.tril(o.generate("rand", n, n, 44, dt))
+    cplx = dt is np.complex128
+    al, be = (ALPHA, BETA) if cplx else (ALPHA.real, BETA.real)
+    if routine == "herk":
+        out = rank_update_trans(True, al.real, A0, None, be.real, C, nb)
+        ref = o.herk(al.real, A0.conj().T, be.real, C, nb)
+    elif routine == "her2k":
+        out = rank_update_trans(True, al, A0, B0, be.real, C, nb)
+        ref = o.her2k(al, A0.conj().T, B0.conj().T, be.real, C, nb)
+    elif routine == "syrk":
+        out = rank_update_trans(False, al, A0, None, be, C, nb)
+        ref = o.syrk(al, A0.T, be, C, nb)
+    else:
+        out = rank_update_trans(False, al, A0, B0, be, C, nb)
+        ref = o.syr2k(al, A0.T, B0.T, be, C, nb)
+    assert np.abs(np.tril(out) - np.tril(ref)).max() <= 64 * EPS * np.abs(np.tril(ref)).max()
 
 
 ALPHA = 3.141592653589793 + 1.414213562373095j

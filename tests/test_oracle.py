@@ -145,6 +145,33 @@ def test_trmm_side_op_variants_match_reference(golden_dir, name, t, side, op, un
     assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
 
 
+@pytest.mark.parametrize("name,routine,t", [("herk_z_conj", "herk", "z"), ("herk_d_trans", "herk", "d"), ("her2k_z_conj", "her2k", "z"),
+                                            ("syrk_z_trans", "syrk", "z"), ("syr2k_z_trans", "syr2k", "z")])
+def test_rank_updates_with_transposed_views_match_reference(golden_dir, name, routine, t):
+    """slate::herk / her2k / syrk / syr2k handed (conjugate-)transposed views of A (and B) stored k x n: the same update as
+    with the n x k matrix A^H (A^T), so the restatements are called on that."""
+    g = load(golden_dir, name)
+    dt = np.complex128 if t == "z" else np.float64
+    n, k, nb = 200, 100, 64
+    A0 = o.generate("rand", k, n, 42, dt)
+    B0 = o.generate("rand", k, n, 43, dt)
+    C = np.tril(o.generate("rand", n, n, 44, dt))
+    if routine in ("herk", "her2k"):
+        A, B = A0.conj().T, B0.conj().T
+    else:
+        A, B = A0.T, B0.T
+    if routine == "herk":
+        out = o.herk(ALPHA.real, A, BETA.real, C, nb)
+    elif routine == "her2k":
+        out = o.her2k(ALPHA if t == "z" else ALPHA.real, A, B, BETA.real, C, nb)
+    elif routine == "syrk":
+        out = o.syrk(ALPHA, A, BETA, C, nb)
+    else:
+        out = o.syr2k(ALPHA, A, B, BETA, C, nb)
+    ref = np.tril(g["out"])
+    assert np.abs(np.tril(out) - ref).max() <= 64 * EPS * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("name,t,opa,opb", [("gemm_d_tn", "d", "T", "N"), ("gemm_d_nt", "d", "N", "T"), ("gemm_z_cn", "z", "C", "N"),
                                            ("gemm_z_tc", "z", "T", "C"), ("gemm_z_nc", "z", "N", "C")])
 def test_gemm_with_transposed_views_matches_reference(golden_dir, name, t, opa, opb):

@@ -309,3 +309,57 @@ def test_gesv_nopiv_is_factor_then_two_sweeps(sl, t, n, nb, nrhs):
     assert info == 0
     Xo = o.tri_sweep(np.triu(LUo), o.tri_sweep(np.tril(LUo), b, nb, lower=True, unit=True), nb, lower=False)
     assert np.abs(X - Xo).max() <= 200 * _eps(t) * np.abs(Xo).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# herk / her2k / syrk / syr2k handed (conjugate-)transposed views (sb200_{herk,her2k,syrk,syr2k}_op_*: rank_update_trans)
+# ---------------------------------------------------------------------------------------------------------------
+def _rank_update(sl, routine, t, n, k, nb):
+    cplx = t in "cz"
+    al, be = (ALPHA, BETA) if cplx else (ALPHA.real, BETA.real)
+    A = sl.Matrix(k, n, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(k, n, nb, dtype=t).generate("rand", 43)
+    C = sl.HermitianMatrix(n, nb, dtype=t).generate("rand", 44)
+    a0, b0 = (o.generate("rand", k, n, seed, NP[t]).astype(_wide(t)) for seed in (42, 43))
+    c = np.tril(o.generate("rand", n, n, 44, NP[t]).astype(_wide(t)))
+    if routine == "herk":
+        sl.herk(al.real, A, be.real, C, op="C")
+        ref = o.herk(al.real, a0.conj().T, be.real, c, nb)
+    elif routine == "her2k":
+        sl.her2k(al, A, B, be.real, C, op="C")
+        ref = o.her2k(al, a0.conj().T, b0.conj().T, be.real, c, nb)
+    elif routine == "syrk":
+        sl.syrk(al, A, be, C, op="T")
+        ref = o.syrk(al, a0.T, be, c, nb)
+    else:
+        sl.syr2k(al, A, B, be, C, op="T")
+        ref = o.syr2k(al, a0.T, b0.T, be, c, nb)
+    return np.tril(C.to_host()), np.tril(ref)
+
+
+@pytest.mark.parametrize("name,routine,t", [("herk_z_conj", "herk", "z"), ("herk_d_trans", "herk", "d"), ("her2k_z_conj", "her2k", "z"),
+                                            ("syrk_z_trans", "syrk", "z"), ("syr2k_z_trans", "syr2k", "z")])
+def test_rank_updates_with_transposed_views_match_reference_golden(sl, golden_dir, name, routine, t):
+    g = np.tril(np.load(os.path.join(golden_dir, name + ".npz"))["out"])
+    out, _ = _rank_update(sl, routine, t, 200, 100, 64)
+    assert np.abs(out - g).max() <= 64 * EPS * np.abs(g).max()
+
+
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("routine", ["herk", "her2k", "syrk", "syr2k"])
+@pytest.mark.parametrize("n,k,nb", [(200, 100, 64), (512, 512, 128), (300, 1000, 256), (70, 10, 64)])
+def test_rank_updates_with_transposed_views_vs_oracle(sl, t, routine, n, k, nb):
+    out, ref = _rank_update(sl, routine, t, n, k, nb)
+    assert np.abs(out - ref).max() <= 3 * np.sqrt(k) * _eps(t) * 4 * np.abs(ref).max()
+    if routine in ("herk", "her2k") and t in "cz":
+        assert np.all(np.diag(out).imag == 0)                      # the Hermitian diagonal is stored real
+
+
+def test_rank_update_op_arguments_are_checked(sl):
+    A = sl.Matrix(32, 64, 32, dtype="z"); C = sl.HermitianMatrix(64, 32, dtype="z")
+    with pytest.raises(sl.SB200Error):
+        sl.herk(1.0, A, 0.0, C, op="T")                            # complex herk takes a conjugate-transposed view only
+    with pytest.raises(sl.SB200Error):
+        sl.syrk(1.0, A, 0.0, C, op="C")                            # complex syrk a transposed one
+    with pytest.raises(sl.SB200Error):
+        sl.herk(1.0, sl.Matrix(32, 48, 32, dtype="z"), 0.0, C, op="C")       # stored k x n: n has to match C
