@@ -492,6 +492,9 @@ int sb200_getrs_d(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, con
 int sb200_getrs_s(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
 int sb200_getrs_z(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
 int sb200_getrs_c(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
+/* op(A) X = B with the factors of A: slate::getrs handed a (conjugate-)transposed view (src/getrs.cc:97-112); op 'N' | 'T' | 'C';
+ * the handle carries the element type.  'N' as sb200_getrs_X; other ops: 1 x 1 grid */
+int sb200_getrs_op(int op, sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts);
 
 /* slate::posv_mixed / gesv_mixed <double, float> (src/posv_mixed.cc:111-297, src/gesv_mixed.cc:106-300):
  * factor a float copy of A (tcgen05 trailing update), solve, refine in FP64 until

@@ -350,7 +350,11 @@ int run(const Args& a)
         slate::Pivots pivots;
         auto t0 = tic();
         info = slate::lu_factor(A, pivots, opts);
-        if (info == 0) slate::lu_solve_using_factor(A, pivots, B, opts);
+        // trans=t|c: solve op(A) X = B with the factors of A (src/getrs.cc:97-112; test/test_gesv.cc `trans`)
+        const std::string tr = a.get("trans", "n");
+        auto opA = A;
+        if (tr == "t") opA = slate::transpose(A); else if (tr == "c") opA = slate::conj_transpose(A);
+        if (info == 0) slate::lu_solve_using_factor(opA, pivots, B, opts);
         seconds = toc(t0);
         gflop = lapack::Gflop<T>::gesv(n, nrhs);
         if (dump) { auto d = to_dense(B); write_raw(a.prefix + ".out.bin", d.data(), d.size()); }

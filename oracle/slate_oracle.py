@@ -380,12 +380,19 @@ def potrs(L, B, nb: int):
     return tri_sweep(np.tril(L), Y, nb, lower=True, op="C")
 
 
-def getrs(LU, pivots, B, nb: int):
-    """Solve A X = B with P A = L U from getrf (pivots as slate::Pivots)."""
+def getrs(LU, pivots, B, nb: int, op: str = "N"):
+    """Solve op(A) X = B with P A = L U from getrf (pivots as slate::Pivots; src/getrs.cc:81-112): NoTrans = permute,
+    L sweep, U sweep; transposed = op(U) sweep, op(L) sweep, inverse permutation."""
     perm = pivots_to_perm(pivots, LU.shape[0], nb)
-    PB = np.asarray(B)[perm]
-    Y = tri_sweep(np.tril(LU, -1) + np.eye(LU.shape[0], dtype=LU.dtype), PB, nb, lower=True, unit=True)
-    return tri_sweep(np.triu(LU), Y, nb, lower=False)
+    Lm = np.tril(LU, -1) + np.eye(LU.shape[0], dtype=LU.dtype)
+    if op == "N":
+        Y = tri_sweep(Lm, np.asarray(B)[perm], nb, lower=True, unit=True)
+        return tri_sweep(np.triu(LU), Y, nb, lower=False)
+    Y = tri_sweep(np.triu(LU), B, nb, lower=False, op=op)
+    Xh = tri_sweep(Lm, Y, nb, lower=True, op=op, unit=True)
+    X = np.empty_like(Xh)
+    X[perm] = Xh                                   # X = P^T Xhat
+    return X
 
 
 # ----------------------------------------------------------------------------

@@ -440,6 +440,31 @@ int getrs_t(Matrix& A, const int* dperm, Matrix& B, cudaStream_t s)
     return tri_sweep<T>(A, false, 'N', false, B, s);        // U
 }
 
+// getrs handed a (conjugate-)transposed view of the factored matrix: op(A) X = B  (src/getrs.cc:97-112):
+// Y = op(U)^{-1} B, Xhat = op(L)^{-1} Y (the sweeps of tri_sweep with the op), X = P^T Xhat as ONE out-of-place row gather
+// with the inverse of the composed permutation (replaces permuteRows Backward).  1 x 1 grid.
+// STATUS: written after round 2's GPU budget was spent; golden vectors + oracle on the CPU; NOT yet run on a GPU.
+template <typename T>
+int getrs_trans_t(Matrix& A, const int* dinvperm, int op, Matrix& B, cudaStream_t s)
+{
+    if (A.kind != 'G' || A.g->size() > 1) return A.kind != 'G' ? SB200_EINVAL : SB200_ENOTSUP;
+    if (A.m != A.n || B.m != A.m || B.dtype != A.dtype) return SB200_EINVAL;
+    if (! IsComplex<T>::value && op == 'C') op = 'T';
+    SB_TRY(tri_sweep<T>(A, false, op, false, B, s));        // op(U)
+    SB_TRY(tri_sweep<T>(A, true, op, true, B, s));          // op(L), unit diagonal
+    DevBuf tmp;
+    SB_TRY(tmp.alloc(B.pool_bytes()));
+    CUDA_TRY(cudaMemcpyAsync(tmp.p, B.pool, B.pool_bytes(), cudaMemcpyDeviceToDevice, s));
+    const int64_t cnt = B.m * B.n;
+    if (cnt > 0) {
+        gather_rows_kernel<T><<<ew_grid(cnt), 256, 0, s>>>(tmp.as<T>(), reinterpret_cast<T*>(B.pool), dinvperm,
+                                                           B.m, B.n, int(B.nb), B.mt);
+        SB_TRY(launch_status());
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));                     // tmp dies with this frame
+    return SB200_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // hemm, Side::Left, lower storage: R = alpha A X + beta R  (src/hemmC.cc, Left/Lower case).
 // Step k adds block column k of the full Hermitian A: tiles below the diagonal as stored, tiles above
@@ -1371,6 +1396,30 @@ static int getrs_any(sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B)
     if (A->A.dtype == 's') return getrs_t<float>(A->A, dp.as<int>(), B->A, nullptr);
     if (A->A.dtype == 'z') return getrs_t<cuDoubleComplex>(A->A, dp.as<int>(), B->A, nullptr);
     if (A->A.dtype == 'c') return getrs_t<cuFloatComplex>(A->A, dp.as<int>(), B->A, nullptr);
+    return SB200_ENOTSUP;
+}
+
+// op(A) X = B with the factors of A; the matrix handle carries the element type
+int sb200_getrs_op(int op, sb200_matrix_t A, const int64_t* pivots, sb200_matrix_t B, const sb200_options_t* opts)
+{
+    SB_TRY(options_status(opts));
+    if (! valid_op(op)) return SB200_EINVAL;
+    if (op == 'N') return getrs_any(A, pivots, B);
+    if (! A || ! B || ! pivots) return SB200_EINVAL;
+    if (A->A.g->size() > 1) return SB200_ENOTSUP;
+    if (B->A.dtype != A->A.dtype) return SB200_EINVAL;
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<int> perm, inv;
+    pivots_to_perm(pivots, A->A.m, A->A.n, A->A.nb, perm);
+    inv.resize(perm.size());
+    for (size_t x = 0; x < perm.size(); ++x) inv[size_t(perm[x])] = int(x);      // row perm[x] of X is row x of Xhat
+    DevBuf dp;
+    SB_TRY(dp.alloc(std::max<size_t>(inv.size(), 1) * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(dp.p, inv.data(), inv.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (A->A.dtype == 'd') return getrs_trans_t<double>(A->A, dp.as<int>(), op, B->A, nullptr);
+    if (A->A.dtype == 's') return getrs_trans_t<float>(A->A, dp.as<int>(), op, B->A, nullptr);
+    if (A->A.dtype == 'z') return getrs_trans_t<cuDoubleComplex>(A->A, dp.as<int>(), op, B->A, nullptr);
+    if (A->A.dtype == 'c') return getrs_trans_t<cuFloatComplex>(A->A, dp.as<int>(), op, B->A, nullptr);
     return SB200_ENOTSUP;
 }
 

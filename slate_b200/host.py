@@ -621,8 +621,17 @@ def getrf_nopiv(A: Matrix, opts: dict | None = None) -> int:
 lu_factor_nopiv = getrf_nopiv
 
 
-def getrs(A: Matrix, pivots, B: Matrix, opts: dict | None = None):
-    """Solve A X = B with the LU factors and pivots from getrf; B is overwritten (slate::getrs, src/getrs.cc)."""
+_getrs_op = _sig("sb200_getrs_op", [c_int, c_ptr, ctypes.POINTER(c_i64), c_ptr, _OP])
+
+
+def getrs(A: Matrix, pivots, B: Matrix, opts: dict | None = None, op: str = "N"):
+    """Solve A X = B with the LU factors and pivots from getrf; B is overwritten (slate::getrs, src/getrs.cc).
+    op "T" | "C": solve op(A) X = B, as slate::getrs does when it is handed a (conjugate-)transposed view (:97-112)."""
+    if op != "N":
+        _same_type(A, B)
+        o = _opts(opts)
+        check(_getrs_op(ord(op), A._h, _pivots_flat(pivots), B._h, ctypes.byref(o)), "getrs")
+        return
     t = _same_type(A, B)
     if t not in _getrs:
         raise Exception_(f"getrs is not implemented for {A.dtype}")

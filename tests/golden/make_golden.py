@@ -30,6 +30,7 @@ generator fixture pins that), only outputs:
                             getrf_tntpiv_z.npz (CALU, n=192), getrf_nopiv_z.npz (rand_dominant, n=200)
   herk_{z_conj,d_trans}.npz, her2k_z_conj.npz, syrk_z_trans.npz, syr2k_z_trans.npz   rank-k / rank-2k updates with A (and B) stored
                             k x n and handed over as (conjugate-)transposed views, n=200 k=100 nb=64
+  gesv_d_trans.npz, gesv_z_conj.npz   lu_factor, then lu_solve_using_factor with the (conjugate-)transposed view: op(A) X = B
   gemm_{d_tn,d_nt,z_cn,z_tc,z_nc}.npz   slate::multiply with (conjugate-)transposed views of A / B, m=150 n=200 k=100 nb=64
   {trmm,trsm}_{z_left_conj,d_left_trans,d_right,z_right_trans,z_right_conj}.npz, hemm_{z,d}_right.npz, symm_z_right.npz
                             the other side / op variants of trmm / hemm / symm (lower storage), nb=64
@@ -168,6 +169,8 @@ BLAS3_VARIANTS = [
     ("her2k_z_conj",       "her2k", "z", dict(n=200, k=100, trans="c")),
     ("syrk_z_trans",       "syrk",  "z", dict(n=200, k=100, trans="t")),
     ("syr2k_z_trans",      "syr2k", "z", dict(n=200, k=100, trans="t")),
+    ("gesv_d_trans",       "gesv", "d", dict(n=300, nrhs=70, trans="t", ib=16, pt=1)),
+    ("gesv_z_conj",        "gesv", "z", dict(n=200, nrhs=70, trans="c", ib=16, pt=1)),
     ("trsm_z_left_conj",   "trsm", "z", dict(n=70,  m=200, op="c")),
     ("trsm_d_left_trans",  "trsm", "d", dict(n=70,  m=200, op="t", diag="u")),
     ("trsm_d_right",       "trsm", "d", dict(n=200, m=70)),
@@ -189,7 +192,9 @@ def blas3_variant_fixtures():
         if routine in ("trmm", "trsm") and name.split("_")[2] == "right":
             kv["side"] = "r"
         f, _ = run(routine, t, n, 64, **kv)
-        if routine in ("herk", "her2k", "syrk", "syr2k"):
+        if routine == "gesv":
+            shape = (n, kv["nrhs"])
+        elif routine in ("herk", "her2k", "syrk", "syr2k"):
             shape = (n, n)
         elif routine in ("trmm", "trsm", "gemm"):
             shape = (kv["m"], n)

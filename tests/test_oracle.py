@@ -145,6 +145,22 @@ def test_trmm_side_op_variants_match_reference(golden_dir, name, t, side, op, un
     assert np.abs(out - g["out"]).max() <= 64 * EPS * np.abs(g["out"]).max()
 
 
+@pytest.mark.parametrize("name,t,n,op", [("gesv_d_trans", "d", 300, "T"), ("gesv_z_conj", "z", 200, "C")])
+def test_getrs_with_transposed_view_matches_reference(golden_dir, name, t, n, op):
+    """lu_solve_using_factor handed a (conjugate-)transposed view of the factored matrix: op(A) X = B (src/getrs.cc:97-112)."""
+    g = load(golden_dir, name)
+    dt = np.complex128 if t == "z" else np.float64
+    nb, nrhs = 64, 70
+    A = o.generate("rand", n, n, 42, dt)
+    B = o.generate("rand", n, nrhs, 43, dt)
+    LU, piv, info = o.getrf(A, nb)
+    assert info == 0
+    X = o.getrs(LU, piv, B, nb, op=op)
+    assert np.abs(X - g["out"]).max() <= 1e-10 * np.abs(g["out"]).max()
+    M = A.T if op == "T" else A.conj().T
+    assert o.solve_residual(M, X, B) <= 25 * EPS
+
+
 @pytest.mark.parametrize("name,routine,t", [("herk_z_conj", "herk", "z"), ("herk_d_trans", "herk", "d"), ("her2k_z_conj", "her2k", "z"),
                                             ("syrk_z_trans", "syrk", "z"), ("syr2k_z_trans", "syr2k", "z")])
 def test_rank_updates_with_transposed_views_match_reference(golden_dir, name, routine, t):

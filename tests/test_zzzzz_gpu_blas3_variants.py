@@ -363,3 +363,42 @@ def test_rank_update_op_arguments_are_checked(sl):
         sl.syrk(1.0, A, 0.0, C, op="C")                            # complex syrk a transposed one
     with pytest.raises(sl.SB200Error):
         sl.herk(1.0, sl.Matrix(32, 48, 32, dtype="z"), 0.0, C, op="C")       # stored k x n: n has to match C
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# getrs handed a (conjugate-)transposed view: op(A) X = B with the factors of A (sb200_getrs_op: getrs_trans_t)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,t,n,op", [("gesv_d_trans", "d", 300, "T"), ("gesv_z_conj", "z", 200, "C")])
+def test_getrs_transposed_matches_reference_golden(sl, golden_dir, name, t, n, op):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))["out"]
+    nb, nrhs = 64, 70
+    A = sl.Matrix(n, n, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(n, nrhs, nb, dtype=t).generate("rand", 43)
+    piv, info = sl.getrf(A)
+    assert info == 0
+    sl.getrs(A, piv, B, op=op)
+    X = B.to_host()
+    assert np.abs(X - g).max() <= 1e-9 * np.abs(g).max()
+    a = o.generate("rand", n, n, 42, NP[t])
+    M = a.T if op == "T" else a.conj().T
+    assert o.solve_residual(M, X, o.generate("rand", n, nrhs, 43, NP[t])) <= 25 * EPS        # test/test_gesv.cc:371-377
+
+
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("op", ["T", "C"])
+@pytest.mark.parametrize("n,nb,nrhs", [(1024, 256, 10), (700, 128, 130), (300, 64, 3)])
+def test_getrs_transposed_vs_oracle_and_tester_residual(sl, t, op, n, nb, nrhs):
+    A = sl.Matrix(n, n, nb, dtype=t).generate("rand", 42)
+    B = sl.Matrix(n, nrhs, nb, dtype=t).generate("rand", 43)
+    piv, info = sl.getrf(A)
+    assert info == 0
+    LU = A.to_host().astype(_wide(t))
+    sl.getrs(A, piv, B, op=op)
+    X = B.to_host().astype(_wide(t))
+    a = o.generate("rand", n, n, 42, NP[t]).astype(_wide(t))
+    b = o.generate("rand", n, nrhs, 43, NP[t]).astype(_wide(t))
+    M = a.T if (op == "T" or t in "ds") else a.conj().T
+    assert o.solve_residual(M, X, b) <= 25 * _eps(t)
+    if t in "dz":
+        Xo = o.getrs(LU, piv, b, nb, op=op)                 # the same factors through the oracle's sweeps
+        assert np.abs(X - Xo).max() <= 1e-9 * np.abs(Xo).max()
