@@ -478,6 +478,10 @@ int sb200_syr2k_op_##X(int op, T alpha, sb200_matrix_t A, sb200_matrix_t B, T be
  * kind 'H' matrix (uplo 'L') or the lower / upper triangle of a general square matrix such as an LU factor; op 'N' | 'T' | 'C', \
  * diag 'N' | 'U'.  slate::trsm / triangular_solve (src/trsm.cc -> work::trsm, src/work/work_trsm.cc:24-387); 1 x 1 grid */ \
 int sb200_trsm_mat_##X(int side, int uplo, int op, int diag, T alpha, sb200_matrix_t A, sb200_matrix_t B, const sb200_options_t* opts); \
+/* slate::norm(norm, A) (src/norm.cc): norm 'M' max, 'O' | '1' one, 'I' inf, 'F' Frobenius; A general, or lower tiles read as a \
+ * Hermitian (flavour 'H') or symmetric (flavour 'S') matrix; per-tile kernels + host combination as the reference's \
+ * internal::norm<Devices> (src/internal/internal_genorm.cc:440-560).  1 x 1 grid */ \
+int sb200_norm_##X(int norm, int flavour, sb200_matrix_t A, double* value); \
 /* norm(Norm::Inf, A), A general or Hermitian   slate::norm (src/norm.cc); 1 x 1 grid */ \
 int sb200_norm_inf_##X(sb200_matrix_t A, double* value);
 SB200_FOR_TYPES(SB200_DECL_RUNTIME)

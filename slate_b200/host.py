@@ -489,6 +489,22 @@ def trmm(alpha, A: "HermitianMatrix", B: Matrix, side: str = "L", uplo: str = "L
 triangular_multiply = trmm
 
 
+_norm = {t: _sig(f"sb200_norm_{t}", [c_int, c_int, c_ptr, ctypes.POINTER(c_dbl)]) for t in "sdcz"}
+_NORM_CHAR = {"max": "M", "one": "O", "1": "O", "inf": "I", "fro": "F", "M": "M", "O": "O", "I": "I", "F": "F"}
+
+
+def norm(kind: str, A: Matrix, symmetric: bool = False) -> float:
+    """slate::norm(Norm::Max | One | Inf | Fro, A) (src/norm.cc): kind "max" | "one" | "inf" | "fro"; A a general Matrix, or a
+    HermitianMatrix handle whose lower tiles are read as a Hermitian matrix (default) or, with symmetric=True, as a
+    (complex-)symmetric one (slate::SymmetricMatrix)."""
+    if kind not in _NORM_CHAR:
+        raise Exception_(f"unknown norm {kind!r}")
+    v = c_dbl(0.0)
+    flavour = ("S" if symmetric else "H") if A._kind == "H" else "G"
+    check(_norm[A.t](ord(_NORM_CHAR[kind]), ord(flavour), A._h, ctypes.byref(v)), "norm")
+    return float(v.value)
+
+
 def norm_inf(A: Matrix) -> float:
     """slate::norm(Norm::Inf, A) for a general or Hermitian matrix."""
     v = c_dbl(0.0)

@@ -402,3 +402,56 @@ def test_getrs_transposed_vs_oracle_and_tester_residual(sl, t, op, n, nb, nrhs):
     if t in "dz":
         Xo = o.getrs(LU, piv, b, nb, op=op)                 # the same factors through the oracle's sweeps
         assert np.abs(X - Xo).max() <= 1e-9 * np.abs(Xo).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# slate::norm at matrix level, all four norms (sb200_norm_*: per-tile kernels + host combination, solve.cu norm_mat)
+# ---------------------------------------------------------------------------------------------------------------
+def test_norms_match_reference_golden(sl, golden_dir):
+    g = np.load(os.path.join(golden_dir, "norms_d.npz"))["out"]           # max, one, inf, fro of rand 200 x 136, nb = 64
+    A = sl.Matrix(200, 136, 64).generate("rand", 42)
+    assert sl.norm("max", A) == g[0]
+    assert abs(sl.norm("one", A) - g[1]) <= 8 * EPS * g[1]
+    assert abs(sl.norm("inf", A) - g[2]) <= 8 * EPS * g[2]
+    assert abs(sl.norm("fro", A) - g[3]) <= 64 * EPS * g[3]
+
+
+def _np_norms(F):
+    a = np.abs(F.astype(np.complex128 if np.iscomplexobj(F) else np.float64))
+    return {"max": a.max(), "one": a.sum(axis=0).max(), "inf": a.sum(axis=1).max(), "fro": np.sqrt((a * a).sum())}
+
+
+@pytest.mark.parametrize("t", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("m,n,nb", [(200, 136, 64), (1000, 800, 256), (64, 64, 64), (50, 300, 128)])
+def test_general_norms_vs_numpy(sl, t, m, n, nb):
+    A = sl.Matrix(m, n, nb, dtype=t).generate("rand", 42)
+    ref = _np_norms(o.generate("rand", m, n, 42, NP[t]))
+    for kind, r in ref.items():
+        v = sl.norm(kind, A)
+        assert abs(v - r) <= (1 if kind == "max" else 4 * np.sqrt(max(m, n))) * _eps(t) * r, kind
+    assert abs(sl.norm("inf", A) - sl.norm_inf(A)) <= 8 * max(m, n) * _eps(t) * ref["inf"]      # the validated one-kernel row sums
+
+
+@pytest.mark.parametrize("t", ["d", "z", "c"])
+@pytest.mark.parametrize("symmetric", [False, True])
+@pytest.mark.parametrize("n,nb", [(200, 64), (1000, 256), (300, 512)])
+def test_hermitian_and_symmetric_norms_vs_numpy(sl, t, symmetric, n, nb):
+    A = sl.HermitianMatrix(n, nb, dtype=t).generate("rand", 42)
+    a = np.tril(o.generate("rand", n, n, 42, NP[t])).astype(_wide(t))
+    full = o.sy_full(a) if symmetric else o.he_full(a)            # he_full takes the stored diagonal real, as the kernels do
+    ref = _np_norms(full)
+    for kind, r in ref.items():
+        v = sl.norm(kind, A, symmetric=symmetric)
+        assert abs(v - r) <= (1 if kind == "max" else 4 * np.sqrt(n)) * _eps(t) * r, kind
+    assert abs(sl.norm("one", A, symmetric=symmetric) - sl.norm("inf", A, symmetric=symmetric)) <= 8 * n * _eps(t) * ref["one"]
+
+
+def test_norm_propagates_nan_and_rejects_unknown_norms(sl):
+    import torch
+    h = np.asfortranarray(o.generate("rand", 100, 70, 1))
+    h[37, 11] = np.nan
+    A = sl.Matrix(100, 70, 32).from_host(h)
+    for kind in ("max", "one", "inf", "fro"):
+        assert np.isnan(sl.norm(kind, A)), kind
+    with pytest.raises(sl.SB200Error):
+        sl.norm("two", A)
