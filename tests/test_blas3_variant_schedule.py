@@ -1,5 +1,5 @@
 """CPU check of the SCHEDULES of the side / op variants of trmm / hemm / symm / trsm (slate_b200/csrc/solve.cu:
-trmm_lower_variant, hemm_symm_right_lower, tri_sweep_right, gemm_ops, rank_update_trans): the step order, the batches of a step, the operand roles and the in-place
+trmm_lower_variant, hemm_symm_right_lower, tri_sweep_right, gemm_ops, rank_update_trans, norm_mat): the step order, the batches of a step, the operand roles and the in-place
 update through a one-block workspace are restated here tile by tile in numpy, exactly as the driver issues them, and
 compared with the oracle (which is pinned to the unmodified reference's golden output, tests/test_oracle.py).  What this
 does NOT cover is the C++ transcription and the kernels: that is tests/test_zzzzz_gpu_blas3_variants.py on a GPU."""
@@ -219,6 +219,80 @@ def test_rank_update_trans_schedule_matches_oracle(dt, routine, n, k, nb):
         out = rank_update_trans(False, al, A0, B0, be, C, nb)
         ref = o.syr2k(al, A0.T, B0.T, be, C, nb)
     assert np.abs(np.tril(out) - np.tril(ref)).max() <= 64 * EPS * np.abs(np.tril(ref)).max()
+
+
+def norm_mat(norm, A, nb, kind="G", symmetric=False):
+    """solve.cu: norm_mat -- per-tile partial results (the oracle's restatements of the tile kernels) combined on the host:
+    column / row sums per block column / row, an off-diagonal tile of a Hermitian / symmetric matrix also stands for its
+    mirror image (row sums -> the mirror's columns, sumsq twice), (scale, sumsq) pairs as lassq"""
+    m, n = A.shape
+    tr, tc = tiles(m, nb), tiles(n, nb)
+    he = kind == "H"
+
+    def diag_tile(T):
+        if symmetric:
+            L = np.tril(T)
+            return L + np.tril(L, -1).T
+        return None
+
+    parts_max, pairs = [], []
+    acc = np.zeros(m if (not he and norm == "I") else n)
+    for j, (j0, j1) in enumerate(tc):
+        for i, (i0, i1) in enumerate(tr):
+            if he and i < j:
+                continue
+            T = A[i0:i1, j0:j1]
+            diag = he and i == j
+            if diag:
+                F = diag_tile(T)
+                val = (lambda nm: o.genorm(nm, F)) if symmetric else (lambda nm: o.henorm(nm, "L", T))
+            else:
+                val = lambda nm: o.genorm(nm, T)
+            if norm == "M":
+                parts_max.append(val("M"))
+            elif norm == "F":
+                s, q = val("F")
+                pairs.append((s, (2.0 if (he and not diag) else 1.0) * q))
+            elif not he:
+                if norm == "O":
+                    acc[j0:j1] += val("O")
+                else:
+                    acc[i0:i1] += val("I")
+            else:
+                acc[j0:j1] += val("O")
+                if not diag:
+                    acc[i0:i1] += val("I")
+    if norm == "M":
+        return o.combine_norm("M", parts_max)
+    if norm == "F":
+        return o.combine_norm("F", pairs)
+    return acc.max()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+@pytest.mark.parametrize("m,n,nb", [(200, 136, 64), (64, 64, 64), (50, 300, 128)])
+def test_norm_combination_general(dt, m, n, nb):
+    A = o.generate("rand", m, n, 42, dt)
+    a = np.abs(A)
+    ref = {"M": a.max(), "O": a.sum(axis=0).max(), "I": a.sum(axis=1).max(), "F": np.sqrt((a * a).sum())}
+    for nm, r in ref.items():
+        assert abs(norm_mat(nm, A, nb) - r) <= 64 * EPS * r, nm
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128])
+@pytest.mark.parametrize("symmetric", [False, True])
+@pytest.mark.parametrize("n,nb", [(200, 64), (300, 512), (128, 64)])
+def test_norm_combination_hermitian_and_symmetric(dt, symmetric, n, nb):
+    L = np.tril(o.generate("rand", n, n, 42, dt))
+    stored = L + np.triu(np.full((n, n), np.nan), 1)
+    for (k0, k1) in tiles(n, nb):                       # diagonal tiles exist as whole tiles; their upper part is never read
+        stored[k0:k1, k0:k1] = np.where(np.tril(np.ones((k1 - k0, k1 - k0), dtype=bool)), L[k0:k1, k0:k1], 7.0)
+    full = o.sy_full(L) if symmetric else o.he_full(L)
+    a = np.abs(full)
+    ref = {"M": a.max(), "O": a.sum(axis=0).max(), "I": a.sum(axis=1).max(), "F": np.sqrt((a * a).sum())}
+    for nm, r in ref.items():
+        v = norm_mat(nm, stored, nb, kind="H", symmetric=symmetric)
+        assert np.isfinite(v) and abs(v - r) <= 64 * EPS * r, nm
 
 
 ALPHA = 3.141592653589793 + 1.414213562373095j
