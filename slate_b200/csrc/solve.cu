@@ -761,7 +761,7 @@ int trmm_lower_variant(int side, int op, T alpha, Matrix& A, Matrix& B, bool uni
     DevBuf dtri, wblk;
     SB_TRY(dtri.alloc(size_t(nt) * te * sizeof(T)));
     SB_TRY(wblk.alloc(size_t(nw) * te * sizeof(T)));
-    CUDA_TRY(cudaMemset(wblk.p, 0, size_t(nw) * te * sizeof(T)));        // whole tiles are copied back: ragged tiles' padding stays defined
+    CUDA_TRY(cudaMemset(wblk.p, 0, size_t(nw) * te * sizeof(T)));        // defined workspace (the products use beta = 0 and never read it)
     struct Step { std::vector<Batch> off, diag; };
     std::vector<Step> steps(static_cast<size_t>(nt));
     std::vector<const T*> diag_ptrs;
@@ -805,9 +805,13 @@ int trmm_lower_variant(int side, int op, T alpha, Matrix& A, Matrix& B, bool uni
         const Step& st = steps[size_t(k)];
         SB_TRY(launch_batches<T>(st.off, pb, opA, opB, alpha, one, ld, 0, s));
         SB_TRY(launch_batches<T>(st.diag, pb, opA, opB, alpha, zero, ld, 0, s));
-        for (int64_t w = 0; w < nw; ++w)
-            CUDA_TRY(cudaMemcpyAsync(left ? B.tile_as<T>(k, w) : B.tile_as<T>(w, k), wblk.as<T>() + w * te,
-                                     size_t(te) * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        for (int64_t w = 0; w < nw; ++w) {
+            // only the tile's own rows and columns: the padding of a ragged tile of B stays what it was
+            const int64_t rows = left ? B.tile_mb(k) : B.tile_mb(w), cols = left ? B.tile_nb(w) : B.tile_nb(k);
+            CUDA_TRY(cudaMemcpy2DAsync(left ? B.tile_as<T>(k, w) : B.tile_as<T>(w, k), size_t(ld) * sizeof(T),
+                                       wblk.as<T>() + w * te, size_t(ld) * sizeof(T), size_t(rows) * sizeof(T), size_t(cols),
+                                       cudaMemcpyDeviceToDevice, s));
+        }
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     return SB200_OK;
