@@ -6,7 +6,9 @@ numpy restatement pinned to them (tests/test_oracle.py).
 STATUS: written after round 2's GPU budget was spent.  The drivers are host-side compositions of launches that ARE validated
 (the batched tile GEMM with an op on either operand, the diagonal-tile fill kernels, the one-block workspace of
 trmm_left_lower) -- the shipped library's 179 kernels are bitwise the measured ones (scratch/sass_compare.py) -- and
-their schedules are checked on the CPU (tests/test_blas3_variant_schedule.py), but this file has NOT yet run on a B200.
+their schedules are checked on the CPU (tests/test_blas3_variant_schedule.py), and the logic of THIS file (shapes, goldens,
+tolerances) passes against an independent numpy stand-in for the host API (scratch/cpu_standin/check_gpu_test_logic.py: 604
+cases), but this file has NOT yet run on a B200.
 It sorts last and is marked xfail(strict=False) for that reason alone: the tail of the first GPU run says whether the
 cases XPASS (then the mark goes) without a first-run surprise hiding the 1 600 validated tests before it under `-x`."""
 import os
