@@ -8,7 +8,8 @@ STATUS: written after round 2's GPU budget was spent.  The drivers are host-side
 trmm_left_lower) -- the shipped library's 179 kernels are bitwise the measured ones (scratch/sass_compare.py) -- and
 their schedules are checked on the CPU (tests/test_blas3_variant_schedule.py), and the logic of THIS file (shapes, goldens,
 tolerances) passes against an independent numpy stand-in for the host API (scratch/cpu_standin/check_gpu_test_logic.py: 604
-cases), but this file has NOT yet run on a B200.
+cases) and the shipped host code passes all of them on the CPU over an emulated CUDA runtime (scratch/cpu_standin/fake_cudart.cc,
+profiles/r02t_host_code_on_emulated_runtime.txt), but this file has NOT yet run on a B200.
 It sorts last and is marked xfail(strict=False) for that reason alone: the tail of the first GPU run says whether the
 cases XPASS (then the mark goes) without a first-run surprise hiding the 1 600 validated tests before it under `-x`."""
 import os
