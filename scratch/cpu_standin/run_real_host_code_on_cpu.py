@@ -125,7 +125,8 @@ def main():
             kw = {}
             for d in combo:
                 kw.update(d)
-            if max(kw.get("n", 0), kw.get("m", 0), kw.get("k", 0)) > 520 and not os.environ.get("STANDIN_ALL"):
+            if max(kw.get("n", 0), kw.get("m", 0), kw.get("k", 0)) > int(os.environ.get("STANDIN_MAX_DIM", "520")) \
+                    and not os.environ.get("STANDIN_ALL"):
                 continue                                     # the emulated GEMM is a triple loop: keep to the small and ragged shapes
             argnames = getattr(f, "argnames", None) or f.__code__.co_varnames[:f.__code__.co_argcount]
             if "sl" in argnames:
